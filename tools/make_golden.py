@@ -1,0 +1,128 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (neu-vi/ezflow,
+imported from /root/reference through tests/refshim.py) on seeded inputs.
+
+The reference cannot travel to the GPU box, so its outputs are committed as small
+fixtures.  Re-run with:  python tools/make_golden.py
+Every fixture stores its inputs, so tests never depend on RNG reproducibility.
+"""
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import refshim  # noqa: E402
+
+ez = refshim.import_reference()
+assert ez is not None and refshim.reference_root() == "/root/reference", "needs /root/reference"
+
+from ezflow.similarity import SIMILARITY_REGISTRY  # noqa: E402
+from ezflow.similarity.correlation.sampler import iter_spatial_correlation_sample  # noqa: E402
+from ezflow.utils import coords_grid  # noqa: E402
+from ezflow.utils.warp import warp  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+torch.set_num_threads(4)
+
+
+def npy(t):
+    return t.detach().cpu().numpy()
+
+
+def save(name, **arrs):
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **{k: (npy(v) if torch.is_tensor(v) else np.asarray(v)) for k, v in arrs.items()})
+    print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def pairwise_case(name, shape, levels, radius, seed, jitter, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    b, c, h, w = shape
+    f1 = (torch.randn(shape, generator=g) * scale).requires_grad_(True)
+    f2 = (torch.randn(shape, generator=g) * scale).requires_grad_(True)
+    coords = coords_grid(b, h, w) + (torch.rand(b, 2, h, w, generator=g) * 2 - 1) * jitter
+    dout = torch.randn(b, levels * (2 * radius + 1) ** 2, h, w, generator=g)
+    cls = SIMILARITY_REGISTRY.get("MutliScalePairwise4DCorr")
+    obj = cls(f1, f2, num_levels=levels, corr_radius=radius)
+    for p in obj.corr_pyramid:
+        p.retain_grad()
+    out = obj(coords)
+    (out * dout).sum().backward()
+    arrs = dict(
+        f1=f1, f2=f2, coords=coords, dout=dout, out=out, df1=f1.grad, df2=f2.grad,
+        levels=levels, radius=radius,
+    )
+    if b * h * w <= 200:
+        arrs["corr"] = cls.corr(f1, f2)
+    for i, p in enumerate(obj.corr_pyramid):
+        arrs[f"pyr{i}"] = p
+        arrs[f"dpyr{i}"] = p.grad
+    save(name, **arrs)
+
+
+def sampler_case(name, shape, seed, **kw):
+    g = torch.Generator().manual_seed(seed)
+    x1 = torch.randn(shape, generator=g).requires_grad_(True)
+    x2 = torch.randn(shape, generator=g).requires_grad_(True)
+    out = iter_spatial_correlation_sample(x1, x2, **kw)
+    dout = torch.randn(out.shape, generator=g)
+    (out * dout).sum().backward()
+    params = {k: np.asarray(v) for k, v in kw.items()}
+    save(name, x1=x1, x2=x2, out=out, dout=dout, dx1=x1.grad, dx2=x2.grad, **{"p_" + k: v for k, v in params.items()})
+
+
+def main():
+    # ---- RAFT all-pairs correlation + pyramid + lookup (K1, K2, K3, K3b, K1b) ----
+    pairwise_case("pairwise_l4_r4", (2, 32, 16, 21), 4, 4, seed=1, jitter=6.0)
+    pairwise_case("pairwise_l3_r3", (1, 24, 10, 14), 3, 3, seed=2, jitter=3.0)
+    pairwise_case("pairwise_scaled", (1, 64, 9, 12), 2, 2, seed=3, jitter=2.0, scale=30.0)
+
+    # ---- local correlation (K4, K4b) ----
+    sampler_case("sampler_p9", (2, 8, 13, 18), 11, patch_size=9)
+    sampler_case("sampler_flownetc", (1, 16, 12, 20), 12, kernel_size=1, patch_size=21, padding=0, dilation_patch=2)
+    sampler_case("sampler_stride2", (2, 6, 13, 17), 13, patch_size=5, stride=2)
+    sampler_case("sampler_aniso", (2, 5, 11, 14), 14, patch_size=(3, 5), stride=(1, 2), padding=(1, 2), dilation_patch=(2, 1))
+    sampler_case("sampler_dcv_s4", (1, 12, 24, 32), 15, patch_size=9, stride=4, dilation_patch=1)
+    sampler_case("sampler_dil16", (1, 8, 12, 20), 16, patch_size=9, stride=1, dilation_patch=16)
+
+    # ---- CorrelationLayer ----
+    g = torch.Generator().manual_seed(21)
+    a = torch.randn(2, 8, 12, 15, generator=g)
+    b_ = torch.randn(2, 8, 12, 15, generator=g)
+    save("corr_layer", x1=a, x2=b_, out=SIMILARITY_REGISTRY.get("CorrelationLayer")()(a, b_),
+         out_p2_d3=SIMILARITY_REGISTRY.get("CorrelationLayer")(pad_size=3, max_displacement=3)(a, b_))
+
+    # ---- Matryoshka (K6) ----
+    g = torch.Generator().manual_seed(31)
+    x1 = torch.randn(2, 16, 10, 14, generator=g)
+    x2 = torch.randn(2, 16, 10, 14, generator=g)
+    M = SIMILARITY_REGISTRY.get("MatryoshkaDilatedCostVolume")
+    m0 = M()
+    m1 = M(num_groups=4, max_displacement=2, stride=2, dilations=[1, 3], use_relu=True)
+    save("matryoshka", x1=x1, x2=x2, out_default=m0(x1, x2), offsets_default=m0.get_relative_offsets(),
+         out_g4=m1(x1, x2), offsets_g4=m1.get_relative_offsets())
+    ML = SIMILARITY_REGISTRY.get("MatryoshkaDilatedCostVolumeList")
+    xa = [torch.randn(1, 8, 32, 48, generator=g), torch.randn(1, 12, 8, 12, generator=g)]
+    xb = [torch.randn(1, 8, 32, 48, generator=g), torch.randn(1, 12, 8, 12, generator=g)]
+    l0 = ML()
+    l1 = ML(normalize_feat_l2=True, use_relu=True)
+    save("matryoshka_list", xa0=xa[0], xa1=xa[1], xb0=xb[0], xb1=xb[1], out_default=l0(xa, xb),
+         out_norm_relu=l1(xa, xb), offsets_2d=l0.get_global_flow_offsets())
+
+    # ---- warp (K5) ----
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(2, 6, 11, 15, generator=g).requires_grad_(True)
+    flow = (torch.randn(2, 2, 11, 15, generator=g) * 3.0).requires_grad_(True)
+    out = warp(x, flow)
+    dout = torch.randn(out.shape, generator=g)
+    (out * dout).sum().backward()
+    save("warp", x=x, flow=flow, out=out, dout=dout, dx=x.grad, dflow=flow.grad)
+
+
+if __name__ == "__main__":
+    main()
