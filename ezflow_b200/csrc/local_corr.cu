@@ -1,0 +1,285 @@
+// K4 / K4b / K6: local displacement-window correlation (FlowNetC, PWC-Net, CorrelationLayer) and the
+// DCVNet Matryoshka multi-dilation cost volume built on it.
+//
+// Replaces iter_spatial_correlation_sample (reference ezflow/similarity/correlation/sampler.py:29-129)
+// and MatryoshkaDilatedCostVolume.forward (ezflow/similarity/learnable_cost.py:306-325):
+//   out[b,pi,pj,y,x] = sum_c in1p[b,c,y*sh,x*sw] * in2p[b,c, y*sh + pi*dph - mdh, x*sw + pj*dpw - mdw]
+// where in*p are the inputs zero-padded by (padh,padw) and md = dp*(P-1)/2.
+//
+// Forward kernel: a block owns one output row segment (64 pixels) of one (batch*group, dilation) and
+// walks the vertical displacements; for each it streams channel chunks of the in1 row segment and of
+// the matching in2 row window through shared memory, every thread accumulating up to 6 horizontal
+// displacements for its pixel in registers (fp32 exact).  Output rows are written coalesced, straight
+// into the (possibly concatenated, K6) destination; scale and LeakyReLU are fused.
+#include "ezb_common.cuh"
+
+namespace ezb {
+namespace k4 {
+
+constexpr int TX = 64;       // output pixels per block (along x)
+constexpr int NT = 256;      // threads: 64 pixels x 4 displacement groups
+constexpr int CC = 16;       // channels per shared-memory chunk
+constexpr int NJ = 6;        // horizontal displacements per thread per pass (covers Pw <= 24 in one pass)
+constexpr int MAX_DIL = 8;
+
+struct Params {
+  const float* in1;
+  const float* in2;
+  float* out;
+  int BG, G, C, H, W;  // inputs viewed (BG = B*G, C per group, H, W)
+  int Ph, Pw, sh, sw, padh, padw;
+  int D;               // number of dilations
+  int dph[MAX_DIL], dpw[MAX_DIL];
+  int oh, ow;
+  int rx_max;          // shared-memory row length of the in2 window
+  float scale, slope;
+  long long out_bstride;
+};
+
+__global__ void __launch_bounds__(NT) local_corr_fwd_kernel(const Params P) {
+  extern __shared__ float sm[];
+  float* sA = sm;                 // [CC][TX]
+  float* sB = sm + CC * TX;       // [CC][rx_max]
+  const int x0 = blockIdx.x * TX, y = blockIdx.y;
+  const int bg = blockIdx.z / P.D, d = blockIdx.z - bg * P.D;
+  const int b = bg / P.G, g = bg - b * P.G;
+  const int dph = P.dph[d], dpw = P.dpw[d];
+  const int mdh = dph * (P.Ph - 1) / 2, mdw = dpw * (P.Pw - 1) / 2;
+  const int tid = threadIdx.x, xl = tid & (TX - 1), jg = tid / TX;
+  const int RX = (TX - 1) * P.sw + (P.Pw - 1) * dpw + 1;
+  const long long plane = (long long)P.H * P.W;
+  const float* in1 = P.in1 + (long long)bg * P.C * plane;
+  const float* in2 = P.in2 + (long long)bg * P.C * plane;
+  const int y1 = y * P.sh - P.padh;             // in1 row (unpadded coordinates)
+  const bool y1_ok = y1 >= 0 && y1 < P.H;
+  const int xb = x0 * P.sw - mdw - P.padw;      // first in2 column of the window (unpadded coordinates)
+  const long long ohw = (long long)P.oh * P.ow;
+  float* out = P.out + (long long)b * P.out_bstride + ((long long)(d * P.G + g) * P.Ph * P.Pw) * ohw + (long long)y * P.ow;
+  const bool x_ok = x0 + xl < P.ow;
+
+  for (int pi = 0; pi < P.Ph; ++pi) {
+    const int y2 = y * P.sh + pi * dph - mdh - P.padh;
+    const bool rows_ok = y1_ok && y2 >= 0 && y2 < P.H;
+    for (int jbase = 0; jbase < P.Pw; jbase += 4 * NJ) {
+      float acc[NJ];
+#pragma unroll
+      for (int m = 0; m < NJ; ++m) acc[m] = 0.f;
+      if (rows_ok) {
+        for (int c0 = 0; c0 < P.C; c0 += CC) {
+          for (int i = tid; i < CC * TX; i += NT) {
+            const int cc = i / TX, xx = i - cc * TX;
+            const int c = c0 + cc, x1 = (x0 + xx) * P.sw - P.padw;
+            sA[i] = (c < P.C && x0 + xx < P.ow && x1 >= 0 && x1 < P.W) ? __ldg(in1 + c * plane + (long long)y1 * P.W + x1) : 0.f;
+          }
+          for (int i = tid; i < CC * RX; i += NT) {
+            const int cc = i / RX, rx = i - cc * RX;
+            const int c = c0 + cc, x2 = xb + rx;
+            sB[cc * P.rx_max + rx] = (c < P.C && x2 >= 0 && x2 < P.W) ? __ldg(in2 + c * plane + (long long)y2 * P.W + x2) : 0.f;
+          }
+          __syncthreads();
+#pragma unroll 4
+          for (int cc = 0; cc < CC; ++cc) {
+            const float a = sA[cc * TX + xl];
+            const float* brow = sB + cc * P.rx_max + xl * P.sw;
+#pragma unroll
+            for (int m = 0; m < NJ; ++m) {
+              const int pj = jbase + jg + 4 * m;
+              if (pj < P.Pw) acc[m] = fmaf(a, brow[pj * dpw], acc[m]);
+            }
+          }
+          __syncthreads();
+        }
+      }
+      if (x_ok) {
+#pragma unroll
+        for (int m = 0; m < NJ; ++m) {
+          const int pj = jbase + jg + 4 * m;
+          if (pj < P.Pw) {
+            float v = acc[m] * P.scale;
+            v = v >= 0.f ? v : v * P.slope;
+            out[(long long)(pi * P.Pw + pj) * ohw + x0 + xl] = v;
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ K4b
+struct BwdParams {
+  const float* in1;
+  const float* in2;
+  const float* dout;
+  float* din1;
+  float* din2;
+  int B, C, H, W, Ph, Pw, sh, sw, padh, padw, dph, dpw, oh, ow;
+  float scale;
+  long long dout_bstride;
+};
+
+// din1[b,c,y1,x1] = scale * sum_{pi,pj} dout[b,pi,pj,y,x] * in2[b,c,y2,x2]  (only strided (y1,x1) are hit)
+__global__ void local_corr_bwd_in1_kernel(const BwdParams P) {
+  const long long total = (long long)P.B * P.C * P.H * P.W;
+  const int mdh = P.dph * (P.Ph - 1) / 2, mdw = P.dpw * (P.Pw - 1) / 2;
+  const long long ohw = (long long)P.oh * P.ow;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x1 = (int)(i % P.W), y1 = (int)((i / P.W) % P.H);
+    const int c = (int)((i / ((long long)P.W * P.H)) % P.C), b = (int)(i / ((long long)P.W * P.H * P.C));
+    float acc = 0.f;
+    const int yp = y1 + P.padh, xp = x1 + P.padw;  // padded coordinates
+    if (yp % P.sh == 0 && xp % P.sw == 0) {
+      const int y = yp / P.sh, x = xp / P.sw;
+      const float* d = P.dout + (long long)b * P.dout_bstride + (long long)y * P.ow + x;
+      const float* i2 = P.in2 + ((long long)b * P.C + c) * P.H * P.W;
+      for (int pi = 0; pi < P.Ph; ++pi) {
+        const int y2 = yp + pi * P.dph - mdh - P.padh;
+        if (y2 < 0 || y2 >= P.H) continue;
+        for (int pj = 0; pj < P.Pw; ++pj) {
+          const int x2 = xp + pj * P.dpw - mdw - P.padw;
+          if (x2 < 0 || x2 >= P.W) continue;
+          acc = fmaf(__ldg(d + (long long)(pi * P.Pw + pj) * ohw), __ldg(i2 + (long long)y2 * P.W + x2), acc);
+        }
+      }
+    }
+    P.din1[i] = acc * P.scale;
+  }
+}
+
+// din2[b,c,y2,x2] = scale * sum_{pi,pj} dout[b,pi,pj,y,x] * in1[b,c,y1,x1] with y*sh = y2p - pi*dph + mdh
+__global__ void local_corr_bwd_in2_kernel(const BwdParams P) {
+  const long long total = (long long)P.B * P.C * P.H * P.W;
+  const int mdh = P.dph * (P.Ph - 1) / 2, mdw = P.dpw * (P.Pw - 1) / 2;
+  const long long ohw = (long long)P.oh * P.ow;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x2 = (int)(i % P.W), y2 = (int)((i / P.W) % P.H);
+    const int c = (int)((i / ((long long)P.W * P.H)) % P.C), b = (int)(i / ((long long)P.W * P.H * P.C));
+    const float* d = P.dout + (long long)b * P.dout_bstride;
+    const float* i1 = P.in1 + ((long long)b * P.C + c) * P.H * P.W;
+    float acc = 0.f;
+    for (int pi = 0; pi < P.Ph; ++pi) {
+      const int yp = y2 + P.padh - pi * P.dph + mdh;  // padded in1 row = y*sh
+      if (yp < 0 || yp % P.sh) continue;
+      const int y = yp / P.sh, y1 = yp - P.padh;
+      if (y >= P.oh || y1 < 0 || y1 >= P.H) continue;
+      for (int pj = 0; pj < P.Pw; ++pj) {
+        const int xp = x2 + P.padw - pj * P.dpw + mdw;
+        if (xp < 0 || xp % P.sw) continue;
+        const int x = xp / P.sw, x1 = xp - P.padw;
+        if (x >= P.ow || x1 < 0 || x1 >= P.W) continue;
+        acc = fmaf(__ldg(d + (long long)(pi * P.Pw + pj) * ohw + (long long)y * P.ow + x), __ldg(i1 + (long long)y1 * P.W + x1), acc);
+      }
+    }
+    P.din2[i] = acc * P.scale;
+  }
+}
+
+// x / (||x||_2 over channels + eps)        learnable_cost.py:426-428
+__global__ void l2_normalize_kernel(const float* __restrict__ x, float* __restrict__ out, int C, long long HW, long long total_px,
+                                    float eps) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_px; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / HW, p = i - b * HW;
+    const float* src = x + b * C * HW + p;
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float v = __ldg(src + c * HW);
+      s = fmaf(v, v, s);
+    }
+    const float inv = 1.0f / (sqrtf(s) + eps);
+    float* dst = out + b * C * HW + p;
+    for (int c = 0; c < C; ++c) dst[c * HW] = __ldg(src + c * HW) * inv;
+  }
+}
+
+static int launch_fwd(Params& P, cudaStream_t st) {
+  int rx = 0;
+  for (int d = 0; d < P.D; ++d) rx = std::max(rx, (TX - 1) * P.sw + (P.Pw - 1) * P.dpw[d] + 1);
+  P.rx_max = rx | 1;
+  const size_t smem = (size_t)(CC * TX + CC * P.rx_max) * sizeof(float);
+  if (smem > 200 * 1024)
+    return fail(EZB_ERR_UNSUPPORTED, "displacement window too wide for the shared-memory tile (patch %d, dilation_patch up to %d, stride %d)",
+                P.Pw, P.dpw[0], P.sw);
+  EZB_CUDA_OK(cudaFuncSetAttribute(local_corr_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(cdiv(P.ow, TX), P.oh, P.BG * P.D);
+  EZB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "output too large for one launch");
+  local_corr_fwd_kernel<<<grid, NT, smem, st>>>(P);
+  EZB_LAUNCH_OK();
+  return EZB_OK;
+}
+
+}  // namespace k4
+}  // namespace ezb
+
+using namespace ezb;
+
+static int check_local_args(int B, int C, int H, int W, int Ph, int Pw, int sh, int sw, int padh, int padw, int dph, int dpw) {
+  EZB_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "bad input shape B=%d C=%d H=%d W=%d", B, C, H, W);
+  EZB_REQUIRE(Ph > 0 && Pw > 0 && sh > 0 && sw > 0 && padh >= 0 && padw >= 0 && dph > 0 && dpw > 0, "bad correlation parameters");
+  if ((Ph % 2) == 0 || (Pw % 2) == 0) return fail(EZB_ERR_UNSUPPORTED, "Only odd patch sizes are supperted.");  // sampler.py:93-94
+  return EZB_OK;
+}
+
+extern "C" int ezb_local_corr_fwd(const float* in1, const float* in2, int B, int C, int H, int W, int Ph, int Pw, int sh,
+                                  int sw, int padh, int padw, int dph, int dpw, float scale, float slope, float* out,
+                                  int64_t out_batch_stride, void* stream) {
+  EZB_REQUIRE(in1 && in2 && out, "null pointer");
+  if (int r = check_local_args(B, C, H, W, Ph, Pw, sh, sw, padh, padw, dph, dpw)) return r;
+  k4::Params P;
+  P.in1 = in1; P.in2 = in2; P.out = out;
+  P.BG = B; P.G = 1; P.C = C; P.H = H; P.W = W;
+  P.Ph = Ph; P.Pw = Pw; P.sh = sh; P.sw = sw; P.padh = padh; P.padw = padw;
+  P.D = 1; P.dph[0] = dph; P.dpw[0] = dpw;
+  P.oh = cdiv(H + 2 * padh, sh); P.ow = cdiv(W + 2 * padw, sw);
+  P.scale = scale; P.slope = slope;
+  P.out_bstride = out_batch_stride > 0 ? out_batch_stride : (int64_t)Ph * Pw * P.oh * P.ow;
+  return k4::launch_fwd(P, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ezb_matryoshka_fwd(const float* x1, const float* x2, int B, int G, int Cg, int H, int W, int P_, int stride,
+                                  const int* dil, int D, float slope, float* out, int64_t out_batch_stride, void* stream) {
+  EZB_REQUIRE(x1 && x2 && out && dil, "null pointer");
+  EZB_REQUIRE(G > 0 && D > 0 && D <= k4::MAX_DIL, "bad group/dilation count G=%d D=%d (max %d dilations)", G, D, k4::MAX_DIL);
+  if (int r = check_local_args(B, Cg, H, W, P_, P_, stride, stride, 0, 0, 1, 1)) return r;
+  k4::Params P;
+  P.in1 = x1; P.in2 = x2; P.out = out;
+  P.BG = B * G; P.G = G; P.C = Cg; P.H = H; P.W = W;
+  P.Ph = P_; P.Pw = P_; P.sh = stride; P.sw = stride; P.padh = 0; P.padw = 0;
+  P.D = D;
+  for (int d = 0; d < D; ++d) {
+    EZB_REQUIRE(dil[d] > 0, "dilation must be positive");
+    P.dph[d] = dil[d];
+    P.dpw[d] = dil[d];
+  }
+  P.oh = cdiv(H, stride); P.ow = cdiv(W, stride);
+  P.scale = 1.f; P.slope = slope;
+  P.out_bstride = out_batch_stride > 0 ? out_batch_stride : (int64_t)D * G * P_ * P_ * P.oh * P.ow;
+  return k4::launch_fwd(P, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ezb_local_corr_bwd(const float* in1, const float* in2, const float* dout, int B, int C, int H, int W, int Ph,
+                                  int Pw, int sh, int sw, int padh, int padw, int dph, int dpw, float scale,
+                                  int64_t dout_batch_stride, float* din1, float* din2, void* stream) {
+  EZB_REQUIRE(in1 && in2 && dout && (din1 || din2), "null pointer");
+  if (int r = check_local_args(B, C, H, W, Ph, Pw, sh, sw, padh, padw, dph, dpw)) return r;
+  k4::BwdParams P;
+  P.in1 = in1; P.in2 = in2; P.dout = dout; P.din1 = din1; P.din2 = din2;
+  P.B = B; P.C = C; P.H = H; P.W = W; P.Ph = Ph; P.Pw = Pw; P.sh = sh; P.sw = sw;
+  P.padh = padh; P.padw = padw; P.dph = dph; P.dpw = dpw;
+  P.oh = cdiv(H + 2 * padh, sh); P.ow = cdiv(W + 2 * padw, sw);
+  P.scale = scale;
+  P.dout_bstride = dout_batch_stride > 0 ? dout_batch_stride : (int64_t)Ph * Pw * P.oh * P.ow;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long total = (long long)B * C * H * W;
+  const int blocks = (int)std::min<long long>(cdiv64(total, 256), 148 * 32);
+  if (din1) { k4::local_corr_bwd_in1_kernel<<<blocks, 256, 0, st>>>(P); EZB_LAUNCH_OK(); }
+  if (din2) { k4::local_corr_bwd_in2_kernel<<<blocks, 256, 0, st>>>(P); EZB_LAUNCH_OK(); }
+  return EZB_OK;
+}
+
+extern "C" int ezb_l2_normalize_fwd(const float* x, int B, int C, int HW, float eps, float* out, void* stream) {
+  EZB_REQUIRE(x && out && B > 0 && C > 0 && HW > 0, "bad arguments");
+  const long long total = (long long)B * HW;
+  const int blocks = (int)std::min<long long>(cdiv64(total, 256), 148 * 32);
+  k4::l2_normalize_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, C, HW, total, eps);
+  EZB_LAUNCH_OK();
+  return EZB_OK;
+}

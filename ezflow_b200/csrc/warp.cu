@@ -1,0 +1,139 @@
+// K5: backward feature warping used by PWC-Net before each local correlation.
+//
+// Replaces warp (reference ezflow/utils/warp.py:5-42):
+//   out = grid_sample(x, pixel_grid + flow, bilinear, zeros, align_corners=True) * mask,
+//   mask = grid_sample(ones, same grid) binarised (mask < 0.9999 -> 0, else 1).
+// One thread per output pixel computes the four taps once and sweeps the channels (reads and writes
+// are coalesced along x).  HBM-bound: C*(4 B read + 4 B write) + 8 B of flow per pixel.
+#include "ezb_common.cuh"
+
+namespace ezb {
+namespace k5 {
+
+struct Taps {
+  int x0, y0;
+  float wx0, wx1, wy0, wy1;
+  bool vx0, vx1, vy0, vy1;
+  float mask;
+};
+
+__device__ __forceinline__ Taps make_taps(float fx, float fy, int x, int y, int H, int W) {
+  // follow the reference's normalise -> grid_sample un-normalise round trip (warp.py:32-33)
+  const float gx = 2.0f * ((float)x + fx) / (float)max(W - 1, 1) - 1.0f;
+  const float gy = 2.0f * ((float)y + fy) / (float)max(H - 1, 1) - 1.0f;
+  const float ix = ((gx + 1.f) / 2.f) * (float)(W - 1);
+  const float iy = ((gy + 1.f) / 2.f) * (float)(H - 1);
+  Taps t;
+  const float x0f = floorf(ix), y0f = floorf(iy);
+  t.wx1 = ix - x0f;
+  t.wx0 = 1.f - t.wx1;
+  t.wy1 = iy - y0f;
+  t.wy0 = 1.f - t.wy1;
+  const float xc = fminf(fmaxf(x0f, -2.f), (float)W), yc = fminf(fmaxf(y0f, -2.f), (float)H);
+  t.x0 = (xc == xc) ? (int)xc : -2;
+  t.y0 = (yc == yc) ? (int)yc : -2;
+  t.vx0 = t.x0 >= 0 && t.x0 < W;
+  t.vx1 = t.x0 + 1 >= 0 && t.x0 + 1 < W;
+  t.vy0 = t.y0 >= 0 && t.y0 < H;
+  t.vy1 = t.y0 + 1 >= 0 && t.y0 + 1 < H;
+  float m = 0.f;
+  if (t.vy0 && t.vx0) m += t.wy0 * t.wx0;
+  if (t.vy0 && t.vx1) m += t.wy0 * t.wx1;
+  if (t.vy1 && t.vx0) m += t.wy1 * t.wx0;
+  if (t.vy1 && t.vx1) m += t.wy1 * t.wx1;
+  t.mask = (m < 0.9999f) ? 0.f : 1.f;  // mask<0.9999 -> 0 ; mask>0 -> 1   (warp.py:39-40)
+  return t;
+}
+
+__global__ void warp_fwd_kernel(const float* __restrict__ x, const float* __restrict__ flow, float* __restrict__ out, int B,
+                                int C, int H, int W) {
+  const long long HW = (long long)H * W, total = (long long)B * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / HW);
+    const long long p = i - (long long)b * HW;
+    const int py = (int)(p / W), px = (int)(p - (long long)py * W);
+    const Taps t = make_taps(__ldg(flow + (long long)b * 2 * HW + p), __ldg(flow + (long long)b * 2 * HW + HW + p), px, py, H, W);
+    const float* src = x + (long long)b * C * HW;
+    float* dst = out + (long long)b * C * HW + p;
+    if (t.mask == 0.f) {
+      for (int c = 0; c < C; ++c) dst[c * HW] = 0.f;
+      continue;
+    }
+    const long long o00 = (long long)t.y0 * W + t.x0;
+    for (int c = 0; c < C; ++c) {
+      const float* s = src + c * HW + o00;
+      float v = 0.f;
+      if (t.vy0 && t.vx0) v += t.wy0 * t.wx0 * __ldg(s);
+      if (t.vy0 && t.vx1) v += t.wy0 * t.wx1 * __ldg(s + 1);
+      if (t.vy1 && t.vx0) v += t.wy1 * t.wx0 * __ldg(s + W);
+      if (t.vy1 && t.vx1) v += t.wy1 * t.wx1 * __ldg(s + W + 1);
+      dst[c * HW] = v;
+    }
+  }
+}
+
+// dx (pre-zeroed) += scatter of dout*mask through the bilinear taps; dflow = d(sample)/d(position).
+// The binarised mask carries no gradient (it is overwritten by constants in the reference).
+__global__ void warp_bwd_kernel(const float* __restrict__ x, const float* __restrict__ flow, const float* __restrict__ dout,
+                                float* __restrict__ dx, float* __restrict__ dflow, int B, int C, int H, int W) {
+  const long long HW = (long long)H * W, total = (long long)B * HW;
+  const float sx = (W > 1) ? 1.f : 0.f, sy = (H > 1) ? 1.f : 0.f;  // (2/max(W-1,1)) * ((W-1)/2)
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / HW);
+    const long long p = i - (long long)b * HW;
+    const int py = (int)(p / W), px = (int)(p - (long long)py * W);
+    const Taps t = make_taps(__ldg(flow + (long long)b * 2 * HW + p), __ldg(flow + (long long)b * 2 * HW + HW + p), px, py, H, W);
+    float gx = 0.f, gy = 0.f;
+    if (t.mask != 0.f) {
+      const long long o00 = (long long)t.y0 * W + t.x0;
+      for (int c = 0; c < C; ++c) {
+        const float g = __ldg(dout + ((long long)b * C + c) * HW + p);
+        const long long cb = ((long long)b * C + c) * HW + o00;
+        const float v00 = (t.vy0 && t.vx0) ? __ldg(x + cb) : 0.f;
+        const float v01 = (t.vy0 && t.vx1) ? __ldg(x + cb + 1) : 0.f;
+        const float v10 = (t.vy1 && t.vx0) ? __ldg(x + cb + W) : 0.f;
+        const float v11 = (t.vy1 && t.vx1) ? __ldg(x + cb + W + 1) : 0.f;
+        gx += g * (t.wy0 * (v01 - v00) + t.wy1 * (v11 - v10));
+        gy += g * (t.wx0 * (v10 - v00) + t.wx1 * (v11 - v01));
+        if (dx) {
+          if (t.vy0 && t.vx0) atomicAdd(dx + cb, g * t.wy0 * t.wx0);
+          if (t.vy0 && t.vx1) atomicAdd(dx + cb + 1, g * t.wy0 * t.wx1);
+          if (t.vy1 && t.vx0) atomicAdd(dx + cb + W, g * t.wy1 * t.wx0);
+          if (t.vy1 && t.vx1) atomicAdd(dx + cb + W + 1, g * t.wy1 * t.wx1);
+        }
+      }
+    }
+    if (dflow) {
+      dflow[(long long)b * 2 * HW + p] = gx * sx;
+      dflow[(long long)b * 2 * HW + HW + p] = gy * sy;
+    }
+  }
+}
+
+}  // namespace k5
+}  // namespace ezb
+
+using namespace ezb;
+
+extern "C" int ezb_warp_fwd(const float* x, const float* flow, int B, int C, int H, int W, float* out, void* stream) {
+  EZB_REQUIRE(x && flow && out, "null pointer");
+  EZB_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
+  const long long total = (long long)B * H * W;
+  const int blocks = (int)std::min<long long>(cdiv64(total, 128), 148 * 32);
+  k5::warp_fwd_kernel<<<blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(x, flow, out, B, C, H, W);
+  EZB_LAUNCH_OK();
+  return EZB_OK;
+}
+
+extern "C" int ezb_warp_bwd(const float* x, const float* flow, const float* dout, int B, int C, int H, int W, float* dx,
+                            float* dflow, void* stream) {
+  EZB_REQUIRE(x && flow && dout && (dx || dflow), "null pointer");
+  EZB_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dx) EZB_CUDA_OK(cudaMemsetAsync(dx, 0, (size_t)B * C * H * W * sizeof(float), st));
+  const long long total = (long long)B * H * W;
+  const int blocks = (int)std::min<long long>(cdiv64(total, 128), 148 * 32);
+  k5::warp_bwd_kernel<<<blocks, 128, 0, st>>>(x, flow, dout, dx, dflow, B, C, H, W);
+  EZB_LAUNCH_OK();
+  return EZB_OK;
+}

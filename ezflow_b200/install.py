@@ -1,0 +1,73 @@
+"""Installs the B200 similarity classes into a live ``ezflow`` so its unmodified YAML configs
+(configs/models/raft.yaml, flownet_c.yaml, pwcnet.yaml, dcvnet.yaml) pick them up.
+
+The reference's ``Registry`` asserts on duplicate names (ezflow/utils/registry.py:23-25), so the
+entries are overwritten in ``_obj_map``.  FlowNetC and PWC-Net bypass the registry and import the
+sampler by name (ezflow/models/flownet_c.py:9, ezflow/decoder/pyramid.py:6), and
+``learnable_cost`` binds a module-global alias (ezflow/similarity/learnable_cost.py:6-9); those
+globals are rebound too, as is ``warp`` in the PWC decoder (ezflow/decoder/pyramid.py:138).
+All of them are read at model-construction / call time, so ``install()`` must run before ``build_model``.
+"""
+
+import importlib
+
+from . import similarity as S
+from . import utils as U
+
+_REGISTRY_NAMES = (
+    "MutliScalePairwise4DCorr",
+    "IterSpatialCorrelationSampler",
+    "CorrelationLayer",
+    "MatryoshkaDilatedCostVolume",
+    "MatryoshkaDilatedCostVolumeList",
+)
+
+_saved = {}
+
+
+def _rebind(modname, attr, value):
+    mod = importlib.import_module(modname)
+    key = (modname, attr)
+    if key not in _saved:
+        _saved[key] = getattr(mod, attr, None)
+    setattr(mod, attr, value)
+
+
+def install(patch_warp=True):
+    """Returns the list of (module, attribute) pairs that were rebound."""
+    ez_sim = importlib.import_module("ezflow.similarity")
+    reg = ez_sim.SIMILARITY_REGISTRY
+    for name in _REGISTRY_NAMES:
+        key = ("<registry>", name)
+        if key not in _saved:
+            _saved[key] = reg._obj_map.get(name)
+        reg._obj_map[name] = getattr(S, name)
+        _rebind("ezflow.similarity", name, getattr(S, name))
+    for name in ("MutliScalePairwise4DCorr", "IterSpatialCorrelationSampler", "CorrelationLayer"):
+        _rebind("ezflow.similarity.correlation", name, getattr(S, name))
+    _rebind("ezflow.similarity.correlation.sampler", "iter_spatial_correlation_sample", S.iter_spatial_correlation_sample)
+    for name in ("MatryoshkaDilatedCostVolume", "MatryoshkaDilatedCostVolumeList"):
+        _rebind("ezflow.similarity.learnable_cost", name, getattr(S, name))
+    # by-name imports that bypass the registry
+    _rebind("ezflow.models.flownet_c", "SpatialCorrelationSampler", S.IterSpatialCorrelationSampler)
+    _rebind("ezflow.decoder.pyramid", "SpatialCorrelationSampler", S.IterSpatialCorrelationSampler)
+    _rebind("ezflow.similarity.learnable_cost", "SpatialCorrelationSampler", S.IterSpatialCorrelationSampler)
+    if patch_warp:
+        _rebind("ezflow.decoder.pyramid", "warp", U.warp)
+        _rebind("ezflow.utils.warp", "warp", U.warp)
+        _rebind("ezflow.utils", "warp", U.warp)
+    return [k for k in _saved if k[0] != "<registry>"]
+
+
+def uninstall():
+    """Restores every binding ``install`` replaced."""
+    ez_sim = importlib.import_module("ezflow.similarity")
+    for (modname, attr), old in list(_saved.items()):
+        if modname == "<registry>":
+            if old is None:
+                ez_sim.SIMILARITY_REGISTRY._obj_map.pop(attr, None)
+            else:
+                ez_sim.SIMILARITY_REGISTRY._obj_map[attr] = old
+        elif old is not None:
+            setattr(importlib.import_module(modname), attr, old)
+    _saved.clear()

@@ -1,0 +1,18 @@
+from ..registry import SIMILARITY_REGISTRY, build_similarity
+from .layer import CorrelationLayer
+from .matryoshka import MatryoshkaDilatedCostVolume, MatryoshkaDilatedCostVolumeList
+from .pairwise import MutliScalePairwise4DCorr, get_pyramid_dtype, set_pyramid_dtype
+from .sampler import IterSpatialCorrelationSampler, iter_spatial_correlation_sample
+
+__all__ = [
+    "SIMILARITY_REGISTRY",
+    "build_similarity",
+    "CorrelationLayer",
+    "MatryoshkaDilatedCostVolume",
+    "MatryoshkaDilatedCostVolumeList",
+    "MutliScalePairwise4DCorr",
+    "IterSpatialCorrelationSampler",
+    "iter_spatial_correlation_sample",
+    "set_pyramid_dtype",
+    "get_pyramid_dtype",
+]

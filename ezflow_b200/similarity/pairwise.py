@@ -1,0 +1,237 @@
+"""RAFT multi-scale all-pairs 4-D correlation on B200 (K1 + K2 + K3).
+
+Drop-in for ``ezflow.similarity.correlation.pairwise.MutliScalePairwise4DCorr`` (reference
+ezflow/similarity/correlation/pairwise.py:9-88): same name (sic), constructor arguments,
+``from_config`` keys, ``__call__`` signature and output layout.  It is a plain class, not an
+``nn.Module``, exactly like the reference.
+
+Deviations, all documented in DESIGN.md §6:
+* the pyramid is stored in the library's padded layout, by default as fp16 with a per-pair
+  power-of-two scale (fp32 selectable with ``set_pyramid_dtype("fp32")``); ``corr_pyramid`` is
+  therefore a property that materialises reference-shaped fp32 tensors on demand;
+* no gradient w.r.t. ``coords`` (RAFT detaches them, reference models/raft.py:115);
+* CPU tensors raise ``RuntimeError`` — there is no CPU fallback.
+"""
+
+import ctypes
+import os
+
+import torch
+
+from .. import _cabi
+from ..config import configurable
+from ..registry import SIMILARITY_REGISTRY
+
+_PYRAMID_DTYPE = os.environ.get("EZB_PYRAMID_DTYPE", "fp16").lower()
+
+
+def set_pyramid_dtype(name):
+    """'fp16' (default; halves HBM traffic, ~2e-4 relative storage error) or 'fp32'."""
+    global _PYRAMID_DTYPE
+    name = str(name).lower()
+    if name not in ("fp16", "fp32"):
+        raise ValueError("pyramid dtype must be 'fp16' or 'fp32'")
+    _PYRAMID_DTYPE = name
+
+
+def get_pyramid_dtype():
+    return _PYRAMID_DTYPE
+
+
+def pyramid_layout(H, W, L, dtype_code):
+    h = (ctypes.c_int * L)()
+    w = (ctypes.c_int * L)()
+    pitch = (ctypes.c_int * L)()
+    qs = (ctypes.c_int64 * L)()
+    _cabi.check(_cabi.lib().ezb_corr_pyramid_layout(H, W, L, dtype_code, h, w, pitch, qs))
+    return [(h[i], w[i], pitch[i], qs[i]) for i in range(L)]
+
+
+class _PyramidState:
+    """Device buffers of one pyramid plus (lazily) its fp32 gradient accumulator."""
+
+    def __init__(self, fmap1, fmap2, num_levels, dtype_name):
+        self.B, self.C, self.H, self.W = fmap1.shape
+        self.L = int(num_levels)
+        self.dtype_code = _cabi.EZB_F16 if dtype_name == "fp16" else _cabi.EZB_F32
+        self.tdtype = torch.float16 if dtype_name == "fp16" else torch.float32
+        self.device = fmap1.device
+        self.fmap1, self.fmap2 = fmap1, fmap2
+        self.N = self.H * self.W
+        self.layout = pyramid_layout(self.H, self.W, self.L, self.dtype_code)
+        self.levels = None
+        self.deq = None
+        self.grad_levels = None
+        self.grad_layout = None
+
+    def build(self, ev_gemm=None):
+        """ev_gemm: optional (start, end) raw cudaEvent handles recorded around the GEMM launch (bench only)."""
+        lib = _cabi.lib()
+        ev0, ev1 = ev_gemm if ev_gemm is not None else (None, None)
+        with torch.cuda.device(self.device):
+            rows = self.B * self.N
+            self.levels = [torch.empty(rows * qs, dtype=self.tdtype, device=self.device) for (_, _, _, qs) in self.layout]
+            self.deq = torch.empty(self.B, dtype=torch.float32, device=self.device)
+            nbytes = ctypes.c_size_t(0)
+            _cabi.check(lib.ezb_corr_pyramid_workspace_bytes(self.B, self.C, self.H, self.W, ctypes.byref(nbytes)))
+            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+            _cabi.check(
+                lib.ezb_corr_pyramid_fwd_ex(
+                    _cabi.ptr(self.fmap1), _cabi.ptr(self.fmap2), self.B, self.C, self.H, self.W, self.L, self.dtype_code,
+                    _cabi.ptr_array(self.levels), _cabi.ptr(self.deq), _cabi.ptr(ws), nbytes.value, _cabi.stream_ptr(self.device),
+                    ev0, ev1,
+                )
+            )
+            # ws is released to the caching allocator here; stream ordering keeps that safe
+
+    def level_view(self, l, buffers=None, layout=None):
+        """(B*N, 1, h_l, w_l) strided view of level l in the library layout."""
+        buffers = self.levels if buffers is None else buffers
+        h, w, pitch, qs = (self.layout if layout is None else layout)[l]
+        return buffers[l].as_strided((self.B * self.N, 1, h, w), (qs, qs, pitch, 1))
+
+    def ensure_grad(self):
+        if self.grad_levels is None:
+            self.grad_layout = pyramid_layout(self.H, self.W, self.L, _cabi.EZB_F32)
+            rows = self.B * self.N
+            self.grad_levels = [torch.zeros(rows * qs, dtype=torch.float32, device=self.device) for (_, _, _, qs) in self.grad_layout]
+        return self.grad_levels
+
+
+class _BuildFn(torch.autograd.Function):
+    """fmap1, fmap2 -> token.  The pyramid lives in ``state``; the token only threads autograd."""
+
+    @staticmethod
+    def forward(ctx, fmap1, fmap2, state):
+        state.build()
+        ctx.state = state
+        return torch.zeros((), dtype=torch.float32, device=fmap1.device)
+
+    @staticmethod
+    def backward(ctx, _gtoken):
+        st = ctx.state
+        if st.grad_levels is None:  # no lookup contributed a gradient
+            return torch.zeros_like(st.fmap1), torch.zeros_like(st.fmap2), None
+        df1 = torch.empty_like(st.fmap1)
+        df2 = torch.empty_like(st.fmap2)
+        with torch.cuda.device(st.device):
+            _cabi.check(
+                _cabi.lib().ezb_corr_pyramid_bwd(
+                    _cabi.ptr_array(st.grad_levels), _cabi.ptr(st.fmap1), _cabi.ptr(st.fmap2), st.B, st.C, st.H, st.W, st.L,
+                    _cabi.ptr(df1), _cabi.ptr(df2), _cabi.stream_ptr(st.device),
+                )
+            )
+        st.grad_levels = None  # consumed (folded in place)
+        return df1, df2, None
+
+
+def _lookup_forward(state, coords, radius):
+    B, _, H, W = coords.shape
+    K = 2 * radius + 1
+    out = torch.empty((B, state.L * K * K, H, W), dtype=torch.float32, device=coords.device)
+    with torch.cuda.device(state.device):
+        _cabi.check(
+            _cabi.lib().ezb_corr_lookup_fwd(
+                _cabi.ptr_array(state.levels), _cabi.ptr(state.deq), _cabi.ptr(coords), B, H, W, state.L, radius,
+                state.dtype_code, _cabi.ptr(out), _cabi.stream_ptr(state.device),
+            )
+        )
+    return out
+
+
+class _LookupFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, token, coords, state, radius):
+        ctx.state, ctx.radius = state, radius
+        ctx.save_for_backward(coords)
+        return _lookup_forward(state, coords, radius)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (coords,) = ctx.saved_tensors
+        st = ctx.state
+        dout = dout.contiguous().float()
+        glv = st.ensure_grad()
+        B, _, H, W = coords.shape
+        with torch.cuda.device(st.device):
+            _cabi.check(
+                _cabi.lib().ezb_corr_lookup_bwd(
+                    _cabi.ptr(dout), _cabi.ptr(coords), B, H, W, st.L, ctx.radius, _cabi.ptr_array(glv),
+                    _cabi.stream_ptr(st.device),
+                )
+            )
+        return torch.zeros((), dtype=torch.float32, device=dout.device), None, None, None
+
+
+@SIMILARITY_REGISTRY.register()
+class MutliScalePairwise4DCorr:
+    """
+    Pairwise 4D correlation at multiple scales (RAFT), computed by the sm_100a kernels.
+
+    Parameters
+    ----------
+    fmap1, fmap2 : torch.Tensor
+        (B, C, H, W) CUDA feature maps, C <= 256
+    num_levels : int
+        Number of levels in the correlation pyramid
+    corr_radius : int
+        Radius of the lookup window
+    """
+
+    @configurable
+    def __init__(self, fmap1, fmap2, num_levels=4, corr_radius=4):
+        self.num_levels = num_levels
+        self.corr_radius = corr_radius
+        f1 = _cabi.require_cuda_f32(fmap1, "fmap1")
+        f2 = _cabi.require_cuda_f32(fmap2, "fmap2")
+        if f1.dim() != 4 or f1.shape != f2.shape:
+            raise ValueError(f"fmap1/fmap2 must both be (B,C,H,W); got {tuple(fmap1.shape)} and {tuple(fmap2.shape)}")
+        if not (1 <= int(num_levels) <= _cabi.EZB_MAX_LEVELS):
+            raise ValueError(f"num_levels must be in [1, {_cabi.EZB_MAX_LEVELS}]")
+        self._state = _PyramidState(f1.detach(), f2.detach(), num_levels, _PYRAMID_DTYPE)
+        if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
+            self._token = _BuildFn.apply(f1, f2, self._state)
+        else:
+            self._state.build()
+            self._token = None
+
+    @property
+    def corr_pyramid(self):
+        """Reference-shaped list of (B*N, 1, h_l, w_l) fp32 tensors (pairwise.py:31-41).
+
+        fp32 storage: zero-copy strided views.  fp16 storage: dequantised copies (diagnostics only)."""
+        st = self._state
+        out = []
+        for l in range(st.L):
+            v = st.level_view(l)
+            if st.tdtype == torch.float16:
+                scale = st.deq.repeat_interleave(st.N).view(-1, 1, 1, 1)
+                v = v.float() * scale
+            out.append(v)
+        return out
+
+    def __call__(self, coords):
+        c = _cabi.require_cuda_f32(coords, "coords")
+        st = self._state
+        if c.dim() != 4 or c.shape[0] != st.B or c.shape[1] != 2 or c.shape[2] != st.H or c.shape[3] != st.W:
+            raise ValueError(f"coords must be ({st.B},2,{st.H},{st.W}); got {tuple(coords.shape)}")
+        if self._token is not None and torch.is_grad_enabled():
+            return _LookupFn.apply(self._token, c.detach(), st, int(self.corr_radius))
+        return _lookup_forward(st, c.detach(), int(self.corr_radius))
+
+    @classmethod
+    def from_config(cls, cfg):
+        return {
+            "num_levels": cfg.NUM_LEVELS,
+            "corr_radius": cfg.CORR_RADIUS,
+        }
+
+    @staticmethod
+    def corr(fmap1, fmap2):
+        """All-pairs correlation volume (B, H, W, 1, H, W) fp32 (pairwise.py:78-88), computed on tcgen05."""
+        f1 = _cabi.require_cuda_f32(fmap1, "fmap1")
+        f2 = _cabi.require_cuda_f32(fmap2, "fmap2")
+        st = _PyramidState(f1.detach(), f2.detach(), 1, "fp32")
+        st.build()
+        B, _, H, W = f1.shape
+        return st.level_view(0).reshape(B, H, W, 1, H, W)

@@ -1,0 +1,145 @@
+/*
+ * ezflow_b200 — C ABI of the B200-native similarity / cost-volume hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch
+ * types.  Every pointer is a DEVICE pointer unless it says "host".  Every entry
+ * point returns 0 on success and a negative ezb_status otherwise; it never aborts,
+ * never synchronises the device and never allocates device memory (callers pass
+ * outputs and workspaces).  The calling thread's current CUDA device must be the
+ * one that owns the pointers; work is enqueued on `stream` (a cudaStream_t).
+ * The library is re-entrant: no mutable global state besides a thread-local error
+ * string, so one thread per device (nn.DataParallel, reference
+ * ezflow/engine/eval.py:306) is safe.
+ *
+ * Each function cites the reference interface (neu-vi/ezflow v0.2.5, paths relative
+ * to the reference checkout) whose arithmetic it replaces.
+ */
+#ifndef EZFLOW_B200_H
+#define EZFLOW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EZB_VERSION 100 /* major*10000 + minor*100 + patch */
+
+typedef enum {
+  EZB_OK = 0,
+  EZB_ERR_INVALID = -1,     /* bad argument (null pointer, non-positive size, ...) -> ValueError   */
+  EZB_ERR_UNSUPPORTED = -2, /* valid in the reference but not built here -> NotImplementedError     */
+  EZB_ERR_CUDA = -3,        /* a CUDA runtime / driver call failed -> RuntimeError                   */
+  EZB_ERR_WORKSPACE = -4    /* workspace too small -> RuntimeError                                  */
+} ezb_status;
+
+/* storage type of the correlation pyramid (the arithmetic is always fp16 x fp16 -> fp32 on tcgen05) */
+typedef enum { EZB_F32 = 0, EZB_F16 = 1 } ezb_dtype;
+
+#define EZB_MAX_LEVELS 8
+
+int ezb_version(void);
+/* copies the calling thread's last error message (NUL-terminated) into buf; returns its length */
+int ezb_last_error(char* buf, size_t n);
+
+/* ---------------------------------------------------------------------------------------------
+ * RAFT all-pairs correlation pyramid (K1 + K2)
+ *   replaces MutliScalePairwise4DCorr.__init__ / .corr
+ *   ezflow/similarity/correlation/pairwise.py:26-41, :78-88
+ *
+ * Layout of level l (the library's choice, reported by ezb_corr_pyramid_layout):
+ *   element (b, q, y, x) at  lvl_ptr[l] + ((b*N + q) * qstride[l] + y * pitch[l] + x) * elsize
+ *   with q = h1*W + w1 the query pixel, (y,x) the target pixel at level l, h[l] = H >> l,
+ *   w[l] = W >> l (floor, F.avg_pool2d default), pitch[l] = w[l] rounded up to 16 bytes,
+ *   qstride[l] = h[l]*pitch[l].  Stored value * deq_scale[b] = reference value.
+ * ------------------------------------------------------------------------------------------- */
+int ezb_corr_pyramid_layout(int H, int W, int L, int dtype,
+                            int* h /*[L] host*/, int* w /*[L] host*/, int* pitch /*[L] host*/,
+                            int64_t* qstride /*[L] host*/);
+
+/* bytes of scratch ezb_corr_pyramid_fwd needs (fp16 K-major operand copies + scales) */
+int ezb_corr_pyramid_workspace_bytes(int B, int C, int H, int W, size_t* bytes /*host*/);
+
+int ezb_corr_pyramid_fwd(const float* fmap1, const float* fmap2, /* (B,C,H,W) fp32 contiguous */
+                         int B, int C, int H, int W, int L, int dtype,
+                         void* const* lvl_ptrs /*[L] host array of device pointers*/,
+                         float* deq_scale /*[B] device, written*/,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same as ezb_corr_pyramid_fwd; additionally records two CUDA events (cudaEvent_t, may be null) on
+ * `stream` immediately before and after the tcgen05 GEMM kernel so a caller can time that launch alone
+ * (bench.py's roofline leg).  The prep kernels (absmax / convert) run before ev_gemm_start. */
+int ezb_corr_pyramid_fwd_ex(const float* fmap1, const float* fmap2, int B, int C, int H, int W, int L, int dtype,
+                            void* const* lvl_ptrs, float* deq_scale, void* workspace, size_t workspace_bytes,
+                            void* stream, void* ev_gemm_start, void* ev_gemm_end);
+
+/* thin cudaEvent helpers so ctypes callers need no second CUDA binding */
+int ezb_event_create(void** ev /*host out*/);
+int ezb_event_destroy(void* ev);
+int ezb_event_elapsed_ms(void* ev_start, void* ev_end, float* ms /*host out*/); /* synchronises on ev_end */
+
+/* ---------------------------------------------------------------------------------------------
+ * Pyramid lookup (K3) and its adjoint w.r.t. the pyramid (K3b)
+ *   replaces MutliScalePairwise4DCorr.__call__ + bilinear_sampler
+ *   ezflow/similarity/correlation/pairwise.py:43-69, ezflow/utils/resampling.py:56-85
+ *   out (B, L*(2r+1)^2, H, W) fp32; channel l*(2r+1)^2 + i*(2r+1) + j samples level l at
+ *   (x/2^l + i - r, y/2^l + j - r) -- the slow window index offsets x.
+ * ------------------------------------------------------------------------------------------- */
+int ezb_corr_lookup_fwd(const void* const* lvl_ptrs /*[L] host*/, const float* deq_scale /*[B]*/,
+                        const float* coords /* (B,2,H,W): ch0 = x, ch1 = y */,
+                        int B, int H, int W, int L, int radius, int dtype,
+                        float* out, void* stream);
+
+/* dpyr levels are fp32 with the *fp32* layout of ezb_corr_pyramid_layout; accumulated into (+=). */
+int ezb_corr_lookup_bwd(const float* dout /* (B, L*(2r+1)^2, H, W) */, const float* coords,
+                        int B, int H, int W, int L, int radius,
+                        float* const* dlvl_ptrs /*[L] host*/, void* stream);
+
+/* Adjoint of the pyramid build (K2b + K1b): folds level gradients into level 0 (in place, dlvl[0]
+ * is overwritten with the total) and computes dfmap1, dfmap2 (B,C,H,W) fp32. */
+int ezb_corr_pyramid_bwd(float* const* dlvl_ptrs /*[L] host*/, const float* fmap1, const float* fmap2,
+                         int B, int C, int H, int W, int L, float* dfmap1, float* dfmap2, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Local displacement-window correlation (K4 / K4b), also CorrelationLayer and the engine of K6
+ *   replaces iter_spatial_correlation_sample  ezflow/similarity/correlation/sampler.py:29-129
+ *   out[b,pi,pj,y,x] = act( scale * sum_c in1p[b,c,y*sh,x*sw] * in2p[b,c,y*sh+pi*dph-mdh, x*sw+pj*dpw-mdw] )
+ *   in*p = inputs zero-padded by (padh,padw); md = dp*(P-1)/2; out (B,Ph,Pw,oh,ow),
+ *   oh = ceil((H+2*padh)/sh), ow likewise.  act = leaky_relu(slope) (slope 1 = identity).
+ *   `out_batch_stride` (elements) lets K6 write straight into a slice of the concatenated volume.
+ * ------------------------------------------------------------------------------------------- */
+int ezb_local_corr_fwd(const float* in1, const float* in2, int B, int C, int H, int W,
+                       int Ph, int Pw, int sh, int sw, int padh, int padw, int dph, int dpw,
+                       float scale, float slope, float* out, int64_t out_batch_stride, void* stream);
+
+int ezb_local_corr_bwd(const float* in1, const float* in2, const float* dout, int B, int C, int H, int W,
+                       int Ph, int Pw, int sh, int sw, int padh, int padw, int dph, int dpw,
+                       float scale, int64_t dout_batch_stride,
+                       float* din1, float* din2, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * DCVNet Matryoshka dilated cost volume (K6): all dilations of one scale in one launch
+ *   replaces MatryoshkaDilatedCostVolume.forward  ezflow/similarity/learnable_cost.py:306-325
+ *   x1,x2 (B, G*Cg, H, W) viewed (B*G, Cg, H, W); out[b, d*G+g, pi, pj, y, x]; P = 2*max_disp+1,
+ *   stride s, dilation_patch = dil[d]; optional leaky_relu(0.1) fused (slope).
+ * ------------------------------------------------------------------------------------------- */
+int ezb_matryoshka_fwd(const float* x1, const float* x2, int B, int G, int Cg, int H, int W,
+                       int P, int stride, const int* dil /*[D] host*/, int D, float slope,
+                       float* out, int64_t out_batch_stride, void* stream);
+
+/* x / (||x||_2 over channels + eps)   learnable_cost.py:426-428 */
+int ezb_l2_normalize_fwd(const float* x, int B, int C, int HW, float eps, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Feature warping (K5)   replaces warp  ezflow/utils/warp.py:5-42
+ *   out = grid_sample(x, pixel_grid + flow, bilinear, zeros, align_corners) * binarised validity mask
+ * ------------------------------------------------------------------------------------------- */
+int ezb_warp_fwd(const float* x, const float* flow, int B, int C, int H, int W, float* out, void* stream);
+int ezb_warp_bwd(const float* x, const float* flow, const float* dout, int B, int C, int H, int W,
+                 float* dx, float* dflow, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EZFLOW_B200_H */

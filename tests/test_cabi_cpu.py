@@ -1,0 +1,85 @@
+"""CPU-only: the C-ABI library loads, exports every symbol include/ezflow_b200.h declares, and its
+argument validation / layout logic (no compute, no GPU)."""
+
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from ezflow_b200 import _cabi, build
+
+    build.build()
+    return _cabi.lib()
+
+
+def test_exports_match_header(lib):
+    from ezflow_b200 import _cabi
+
+    text = open(os.path.join(ROOT, "include", "ezflow_b200.h")).read()
+    declared = set(re.findall(r"\bint\s+(ezb_[a-z0-9_]+)\s*\(", text))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_cabi.EXPORTED_SYMBOLS), declared ^ set(_cabi.EXPORTED_SYMBOLS)
+
+
+def test_version_and_error_string(lib):
+    from ezflow_b200 import _cabi
+
+    assert lib.ezb_version() == 100
+    rc = lib.ezb_corr_pyramid_layout(0, 4, 1, 0, None, None, None, None)
+    assert rc == -1 and "bad pyramid shape" in _cabi.last_error()
+    with pytest.raises(ValueError):
+        _cabi.check(rc)
+
+
+def test_pyramid_layout(lib):
+    from ezflow_b200.similarity.pairwise import pyramid_layout
+
+    # 1080p: floor pooling 135x240 -> 67x120 -> 33x60 -> 16x30
+    lay = pyramid_layout(135, 240, 4, 1)
+    assert [(h, w) for h, w, _, _ in lay] == [(135, 240), (67, 120), (33, 60), (16, 30)]
+    assert [p for _, _, p, _ in lay] == [240, 120, 64, 32]  # fp16 pitch: multiples of 8 elements
+    assert all(qs == h * p for h, _, p, qs in lay)
+    lay32 = pyramid_layout(46, 62, 4, 0)
+    assert [(h, w, p) for h, w, p, _ in lay32] == [(46, 62, 64), (23, 31, 32), (11, 15, 16), (5, 7, 8)]
+    with pytest.raises(ValueError):
+        pyramid_layout(4, 4, 4, 0)  # level 3 would be empty
+
+
+def test_argument_validation_without_gpu(lib):
+    from ezflow_b200 import _cabi
+
+    assert lib.ezb_corr_pyramid_fwd(None, None, 1, 8, 8, 8, 1, 0, None, None, None, 0, None) == -1
+    assert lib.ezb_corr_lookup_fwd(None, None, None, 1, 8, 8, 1, 4, 0, None, None) == -1
+    one = ctypes.c_void_p(16)
+    # even patch size -> unsupported, same message as the reference (sampler.py:93-94)
+    rc = lib.ezb_local_corr_fwd(one, one, 1, 2, 4, 4, 4, 4, 1, 1, 0, 0, 1, 1, 1.0, 1.0, one, 0, None)
+    assert rc == -2 and "odd patch sizes" in _cabi.last_error()
+    with pytest.raises(NotImplementedError):
+        _cabi.check(rc)
+    n = ctypes.c_size_t(0)
+    assert lib.ezb_corr_pyramid_workspace_bytes(1, 256, 135, 240, ctypes.byref(n)) == 0
+    assert n.value >= 2 * 32400 * 256 * 2
+
+
+def test_sass_is_blackwell_native():
+    """The GEMM must be tcgen05 + TMA (SASS: UTCHMMA / LDTM / UTMALDG / UTMASTG), not mma.sync."""
+    import shutil
+    import subprocess
+
+    from ezflow_b200 import build
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", build.LIBPATH], capture_output=True, text=True).stdout
+    for mnem in ("UTCHMMA", "LDTM", "UTMALDG", "UTMASTG"):
+        assert mnem in sass, f"{mnem} missing from SASS"
+    assert "HMMA." not in sass.replace("UTCHMMA", "")

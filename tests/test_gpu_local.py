@@ -1,0 +1,172 @@
+"""GPU parity: local displacement-window correlation (K4/K4b), CorrelationLayer, Matryoshka (K6), warp (K5).
+fp32 SIMT arithmetic: tolerance 1e-5 relative (summation order only)."""
+
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import assert_close, dev, to_gpu
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2e-5
+SAMPLER = ["sampler_p9", "sampler_flownetc", "sampler_stride2", "sampler_aniso", "sampler_dcv_s4", "sampler_dil16"]
+
+
+def _kw(g):
+    kw = {}
+    for k, v in g.items():
+        if k.startswith("p_"):
+            kw[k[2:]] = int(v) if v.ndim == 0 else tuple(int(t) for t in v)
+    return kw
+
+
+@pytest.mark.parametrize("name", SAMPLER)
+def test_sampler_vs_reference_golden(golden, name):
+    import ezflow_b200 as E
+
+    g = golden(name)
+    kw = _kw(g)
+    x1, x2 = to_gpu(g["x1"], True), to_gpu(g["x2"], True)
+    mod = E.IterSpatialCorrelationSampler(**kw)
+    out = mod(x1, x2)
+    assert out.is_contiguous() and tuple(out.shape) == g["out"].shape
+    assert_close(out, g["out"], TOL, f"{name} fwd")
+    (out * to_gpu(g["dout"])).sum().backward()
+    assert_close(x1.grad, g["dx1"], TOL, f"{name} dinput1")
+    assert_close(x2.grad, g["dx2"], TOL, f"{name} dinput2")
+    # functional form, no grad
+    with torch.no_grad():
+        out2 = E.iter_spatial_correlation_sample(to_gpu(g["x1"]), to_gpu(g["x2"]), **kw)
+    assert torch.equal(out2, out.detach())
+
+
+def test_sampler_rejects_like_reference():
+    import ezflow_b200 as E
+
+    x = torch.zeros(1, 2, 4, 4, device=dev())
+    for kw in (dict(kernel_size=3), dict(dilation=2), dict(patch_size=4)):
+        with pytest.raises(NotImplementedError):
+            E.IterSpatialCorrelationSampler(**kw)(x, x)
+    with pytest.raises(RuntimeError):
+        E.IterSpatialCorrelationSampler()(x.cpu(), x.cpu())
+
+
+def test_view_like_callers():
+    """FlowNetC / PWC call .view(B, -1, H, W) on the result (models/flownet_c.py:87-89, decoder/pyramid.py:101)."""
+    import ezflow_b200 as E
+
+    x = torch.randn(2, 16, 8, 12, device=dev())
+    out = E.IterSpatialCorrelationSampler(kernel_size=1, patch_size=9, padding=0)(x, x)
+    assert tuple(out.view(2, -1, 8, 12).shape) == (2, 81, 8, 12)
+
+
+def test_corr_layer(golden):
+    import ezflow_b200 as E
+
+    g = golden("corr_layer")
+    out = E.CorrelationLayer()(to_gpu(g["x1"]), to_gpu(g["x2"]))
+    assert_close(out, g["out"], TOL, "CorrelationLayer default")
+    out = E.CorrelationLayer(pad_size=3, max_displacement=3)(to_gpu(g["x1"]), to_gpu(g["x2"]))
+    assert_close(out, g["out_p2_d3"], TOL, "CorrelationLayer 3/3")
+
+
+def test_matryoshka(golden):
+    import ezflow_b200 as E
+
+    g = golden("matryoshka")
+    x1, x2 = to_gpu(g["x1"]), to_gpu(g["x2"])
+    m0 = E.MatryoshkaDilatedCostVolume().to(dev())
+    assert m0.get_search_range() == 9
+    np.testing.assert_array_equal(m0.get_relative_offsets().cpu().numpy(), g["offsets_default"])
+    assert_close(m0(x1, x2), g["out_default"], TOL, "matryoshka default")
+    m1 = E.MatryoshkaDilatedCostVolume(num_groups=4, max_displacement=2, stride=2, dilations=[1, 3], use_relu=True).to(dev())
+    assert_close(m1(x1, x2), g["out_g4"], TOL, "matryoshka groups/relu")
+    np.testing.assert_array_equal(m1.get_relative_offsets().cpu().numpy(), g["offsets_g4"])
+
+
+def test_matryoshka_list(golden):
+    import ezflow_b200 as E
+
+    g = golden("matryoshka_list")
+    xa = [to_gpu(g["xa0"]), to_gpu(g["xa1"])]
+    xb = [to_gpu(g["xb0"]), to_gpu(g["xb1"])]
+    l0 = E.MatryoshkaDilatedCostVolumeList().to(dev())
+    out = l0(xa, xb)
+    assert out.is_contiguous()
+    assert_close(out, g["out_default"], TOL, "matryoshka list default")
+    np.testing.assert_array_equal(l0.get_global_flow_offsets().cpu().numpy(), g["offsets_2d"])
+    b, c, u, v, h, w = out.shape
+    out.view(b, c * u * v, h, w)  # decoder/dilated_flow_stack_filter.py:132-133
+    l1 = E.MatryoshkaDilatedCostVolumeList(normalize_feat_l2=True, use_relu=True).to(dev())
+    assert_close(l1(xa, xb), g["out_norm_relu"], TOL, "matryoshka list norm+relu")
+
+
+def test_matryoshka_backward_vs_oracle():
+    import ezflow_b200 as E
+    from oracle import similarity_oracle as O
+
+    rng = np.random.default_rng(5)
+    x1 = rng.standard_normal((1, 8, 9, 11)).astype(np.float32)
+    x2 = rng.standard_normal((1, 8, 9, 11)).astype(np.float32)
+    m = E.MatryoshkaDilatedCostVolume(num_groups=2, max_displacement=1, dilations=[1, 2]).to(dev())
+    a, b = to_gpu(x1, True), to_gpu(x2, True)
+    out = m(a, b)
+    dout = rng.standard_normal(tuple(out.shape)).astype(np.float32)
+    (out * to_gpu(dout)).sum().backward()
+    d1 = np.zeros_like(x1).reshape(2, 4, 9, 11)
+    d2 = np.zeros_like(d1)
+    for i, d in enumerate([1, 2]):
+        g = dout[:, i * 2 : (i + 1) * 2].reshape(2, 3, 3, 9, 11)
+        e1, e2 = O.iter_spatial_correlation_sample_bwd(x1.reshape(2, 4, 9, 11), x2.reshape(2, 4, 9, 11), g, 3, 1, 0, d)
+        d1 += e1
+        d2 += e2
+    assert_close(a.grad, d1.reshape(x1.shape), TOL, "matryoshka dx1")
+    assert_close(b.grad, d2.reshape(x2.shape), TOL, "matryoshka dx2")
+
+
+def test_warp(golden):
+    import ezflow_b200 as E
+
+    g = golden("warp")
+    x, flow = to_gpu(g["x"], True), to_gpu(g["flow"], True)
+    out = E.warp(x, flow)
+    assert_close(out, g["out"], TOL, "warp fwd")
+    (out * to_gpu(g["dout"])).sum().backward()
+    assert_close(x.grad, g["dx"], TOL, "warp dx")
+    assert_close(flow.grad, g["dflow"], 1e-4, "warp dflow")
+
+
+@pytest.mark.parametrize("cfg", ["flownetc", "pwc", "dcv"])
+def test_baseline_config_shapes_vs_oracle(cfg):
+    """BASELINE configs 2-4 at full spatial size (batch reduced so the numpy oracle stays in seconds)."""
+    import ezflow_b200 as E
+    from oracle import similarity_oracle as O
+
+    rng = np.random.default_rng(17)
+    if cfg == "flownetc":
+        x1 = rng.standard_normal((1, 256, 48, 64)).astype(np.float32)
+        x2 = rng.standard_normal((1, 256, 48, 64)).astype(np.float32)
+        out = E.IterSpatialCorrelationSampler(kernel_size=1, patch_size=21, padding=0, dilation_patch=2)(to_gpu(x1), to_gpu(x2))
+        ref = O.iter_spatial_correlation_sample(x1, x2, patch_size=21, dilation_patch=2)
+        assert tuple(out.shape) == (1, 21, 21, 48, 64)
+        assert_close(out, ref, TOL, "cfg2")
+    elif cfg == "pwc":
+        for (c, h, w) in [(196, 7, 16), (128, 14, 32), (96, 28, 64), (64, 56, 128), (32, 112, 256)]:
+            x1 = rng.standard_normal((2, c, h, w)).astype(np.float32)
+            x2 = rng.standard_normal((2, c, h, w)).astype(np.float32)
+            flow = (rng.standard_normal((2, 2, h, w)) * 2).astype(np.float32)
+            wg = E.warp(to_gpu(x2), to_gpu(flow))
+            wr = O.warp(x2, flow)
+            assert_close(wg, wr, TOL, f"cfg3 warp {c}x{h}x{w}")
+            out = E.IterSpatialCorrelationSampler(kernel_size=1, patch_size=9, padding=0)(to_gpu(x1), wg)
+            ref = O.iter_spatial_correlation_sample(x1, wr, patch_size=9)
+            assert_close(out, ref, 5e-5, f"cfg3 corr {c}x{h}x{w}")
+    else:
+        xa = [rng.standard_normal((1, 128, 192, 384)).astype(np.float32), rng.standard_normal((1, 256, 48, 96)).astype(np.float32)]
+        xb = [rng.standard_normal((1, 128, 192, 384)).astype(np.float32), rng.standard_normal((1, 256, 48, 96)).astype(np.float32)]
+        m = E.MatryoshkaDilatedCostVolumeList().to(dev())
+        out = m([to_gpu(t) for t in xa], [to_gpu(t) for t in xb])
+        assert tuple(out.shape) == (1, 7, 9, 9, 48, 96)
+        ref = O.matryoshka_cost_volume_list(xa, xb)
+        assert_close(out, ref, TOL, "cfg4")

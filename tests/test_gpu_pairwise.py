@@ -1,0 +1,234 @@
+"""GPU parity: RAFT all-pairs correlation pyramid + lookup (K1, K2, K3, K3b, K1b) through the drop-in
+class, against (a) golden vectors produced by the unmodified reference and (b) the numpy oracle.
+
+Tolerances (north_star): correlation volumes <= 1e-3 relative error (fp16 tensor-core contraction vs the
+reference's fp32); lookups inherit that bound."""
+
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import assert_close, dev, rel_fro, to_gpu
+
+pytestmark = pytest.mark.gpu
+
+VOL_TOL = 1e-3   # correlation volumes / pyramid levels (north_star)
+LOOK_TOL = 1e-3  # lookup output, relative to the reference's output
+GRAD_TOL = 2e-3  # adjoints: two chained fp32 reductions in different orders + fp16 pyramid not involved
+
+
+@pytest.fixture(autouse=True)
+def _restore_dtype():
+    import ezflow_b200 as E
+
+    old = E.get_pyramid_dtype()
+    yield
+    E.set_pyramid_dtype(old)
+
+
+PAIRWISE = ["pairwise_l4_r4", "pairwise_l3_r3", "pairwise_scaled"]
+
+
+@pytest.mark.parametrize("store", ["fp16", "fp32"])
+@pytest.mark.parametrize("name", PAIRWISE)
+def test_pyramid_and_lookup_vs_reference_golden(golden, name, store):
+    import ezflow_b200 as E
+
+    g = golden(name)
+    L, r = int(g["levels"]), int(g["radius"])
+    E.set_pyramid_dtype(store)
+    obj = E.MutliScalePairwise4DCorr(to_gpu(g["f1"]), to_gpu(g["f2"]), num_levels=L, corr_radius=r)
+    assert obj.num_levels == L and obj.corr_radius == r
+    pyr = obj.corr_pyramid
+    assert len(pyr) == L
+    for i in range(L):
+        assert tuple(pyr[i].shape) == g[f"pyr{i}"].shape
+        assert_close(pyr[i], g[f"pyr{i}"], VOL_TOL, f"{name} level {i} ({store})")
+    out = obj(to_gpu(g["coords"]))
+    assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == g["out"].shape
+    assert_close(out, g["out"], LOOK_TOL, f"{name} lookup ({store})")
+
+
+@pytest.mark.parametrize("name", ["pairwise_l3_r3", "pairwise_scaled"])
+def test_corr_static(golden, name):
+    import ezflow_b200 as E
+
+    g = golden(name)
+    corr = E.MutliScalePairwise4DCorr.corr(to_gpu(g["f1"]), to_gpu(g["f2"]))
+    assert tuple(corr.shape) == g["corr"].shape
+    assert_close(corr, g["corr"], VOL_TOL, f"{name} corr()")
+
+
+@pytest.mark.parametrize("name", PAIRWISE)
+def test_backward_vs_reference_golden(golden, name):
+    import ezflow_b200 as E
+
+    g = golden(name)
+    L, r = int(g["levels"]), int(g["radius"])
+    f1, f2 = to_gpu(g["f1"], True), to_gpu(g["f2"], True)
+    obj = E.MutliScalePairwise4DCorr(f1, f2, num_levels=L, corr_radius=r)
+    out = obj(to_gpu(g["coords"]))
+    (out * to_gpu(g["dout"])).sum().backward()
+    assert_close(f1.grad, g["df1"], GRAD_TOL, f"{name} dfmap1")
+    assert_close(f2.grad, g["df2"], GRAD_TOL, f"{name} dfmap2")
+
+
+def test_backward_two_lookups_accumulate(golden):
+    """Two lookups through one pyramid: gradients add (RAFT calls the object 12x, models/raft.py:116)."""
+    import ezflow_b200 as E
+
+    g = golden("pairwise_l3_r3")
+    L, r = int(g["levels"]), int(g["radius"])
+    f1, f2 = to_gpu(g["f1"], True), to_gpu(g["f2"], True)
+    obj = E.MutliScalePairwise4DCorr(f1, f2, num_levels=L, corr_radius=r)
+    c = to_gpu(g["coords"])
+    d = to_gpu(g["dout"])
+    ((obj(c) * d).sum() + (obj(c) * d).sum()).backward()
+    assert_close(f1.grad, 2 * g["df1"], GRAD_TOL, "2x dfmap1")
+    assert_close(f2.grad, 2 * g["df2"], GRAD_TOL, "2x dfmap2")
+
+
+@pytest.mark.parametrize("store", ["fp16", "fp32"])
+def test_cfg1_shape_vs_oracle(store):
+    """BASELINE config 1 feature size (368x496 -> 46x62, C=256): CUDA path vs numpy oracle."""
+    import ezflow_b200 as E
+    from oracle import similarity_oracle as O
+
+    rng = np.random.default_rng(1234)
+    f1 = rng.standard_normal((1, 256, 46, 62)).astype(np.float32)
+    f2 = rng.standard_normal((1, 256, 46, 62)).astype(np.float32)
+    coords = O.coords_grid(1, 46, 62) + rng.uniform(-8, 8, (1, 2, 46, 62)).astype(np.float32)
+    ref_pyr = O.corr_pyramid(f1, f2, 4)
+    ref_out = O.corr_lookup(ref_pyr, coords, 4)
+    E.set_pyramid_dtype(store)
+    obj = E.MutliScalePairwise4DCorr(to_gpu(f1), to_gpu(f2), num_levels=4, corr_radius=4)
+    pyr = obj.corr_pyramid
+    for i in range(4):
+        rf, mr = assert_close(pyr[i], ref_pyr[i], VOL_TOL, f"cfg1 level {i} ({store})")
+    out = obj(to_gpu(coords))
+    assert tuple(out.shape) == (1, 324, 46, 62)
+    assert_close(out, ref_out, LOOK_TOL, f"cfg1 lookup ({store})")
+
+
+def test_batch_and_odd_channels_vs_oracle():
+    """B=3, C=96 (Cp padded to 128), odd H/W so every level drops a row/col; radius 3, 3 levels."""
+    import ezflow_b200 as E
+    from oracle import similarity_oracle as O
+
+    rng = np.random.default_rng(7)
+    f1 = rng.standard_normal((3, 96, 19, 37)).astype(np.float32)
+    f2 = rng.standard_normal((3, 96, 19, 37)).astype(np.float32)
+    f1[1] *= 40.0  # per-pair scales differ by orders of magnitude
+    f2[2] *= 1e-3
+    coords = O.coords_grid(3, 19, 37) + rng.uniform(-5, 5, (3, 2, 19, 37)).astype(np.float32)
+    ref_pyr = O.corr_pyramid(f1, f2, 3)
+    ref_out = O.corr_lookup(ref_pyr, coords, 3)
+    obj = E.MutliScalePairwise4DCorr(to_gpu(f1), to_gpu(f2), num_levels=3, corr_radius=3)
+    n = 19 * 37
+    pyr = obj.corr_pyramid
+    for b in range(3):  # per pair: scales differ, so relative error is judged per pair
+        for i in range(3):
+            assert_close(pyr[i][b * n : (b + 1) * n], ref_pyr[i][b * n : (b + 1) * n], VOL_TOL, f"pair {b} level {i}")
+        assert_close(obj(to_gpu(coords))[b], ref_out[b], LOOK_TOL, f"pair {b} lookup")
+
+
+def test_lookup_edge_coordinates():
+    """Windows fully / partially outside, exactly-integer coordinates, huge values: zeros padding."""
+    import ezflow_b200 as E
+    from oracle import similarity_oracle as O
+
+    rng = np.random.default_rng(3)
+    H, W = 12, 20
+    f1 = rng.standard_normal((1, 64, H, W)).astype(np.float32)
+    f2 = rng.standard_normal((1, 64, H, W)).astype(np.float32)
+    coords = O.coords_grid(1, H, W)
+    coords[0, 0, 0, :] = -50.0       # far left
+    coords[0, 1, 1, :] = 1e6         # far below
+    coords[0, 0, 2, :] = W - 1 + 3.5 # straddling the right border
+    coords[0, :, 3, :] = -0.5        # straddling the top-left corner
+    coords[0, 0, 4, :] = -1e9
+    E.set_pyramid_dtype("fp32")
+    obj = E.MutliScalePairwise4DCorr(to_gpu(f1), to_gpu(f2), num_levels=2, corr_radius=4)
+    out = obj(to_gpu(coords)).cpu().numpy()
+    ref = O.corr_lookup(O.corr_pyramid(f1, f2, 2), coords, 4)
+    assert np.isfinite(out).all()
+    assert np.all(out[0, :, 0, :] == 0) and np.all(out[0, :, 1, :] == 0) and np.all(out[0, :, 4, :] == 0)
+    assert_close(out, ref, LOOK_TOL, "edge lookup")
+
+
+def test_sharding_invariance():
+    """Per-pair scaling => a pair's result does not depend on which batch (GPU shard) it is in: bit-exact."""
+    import ezflow_b200 as E
+
+    g = torch.Generator(device="cpu").manual_seed(5)
+    f1 = torch.randn(4, 128, 16, 24, generator=g).to(dev())
+    f2 = torch.randn(4, 128, 16, 24, generator=g).to(dev())
+    f2[3] *= 100
+    coords = (E.coords_grid(4, 16, 24, device=dev()) + torch.rand(4, 2, 16, 24, generator=g).to(dev()) * 6 - 3)
+    whole = E.MutliScalePairwise4DCorr(f1, f2)(coords)
+    for lo, hi in ((0, 2), (2, 4)):
+        part = E.MutliScalePairwise4DCorr(f1[lo:hi], f2[lo:hi])(coords[lo:hi])
+        assert torch.equal(part, whole[lo:hi])
+
+
+def test_many_levels_uses_extra_pool_kernel():
+    import ezflow_b200 as E
+    from oracle import similarity_oracle as O
+
+    rng = np.random.default_rng(9)
+    f1 = rng.standard_normal((1, 64, 32, 48)).astype(np.float32)
+    f2 = rng.standard_normal((1, 64, 32, 48)).astype(np.float32)
+    ref = O.corr_pyramid(f1, f2, 5)
+    obj = E.MutliScalePairwise4DCorr(to_gpu(f1), to_gpu(f2), num_levels=5, corr_radius=1)
+    pyr = obj.corr_pyramid
+    assert_close(pyr[4], ref[4], 2e-3, "level 4 (pooled from fp16 level 3)")
+
+
+def test_errors():
+    import ezflow_b200 as E
+
+    with pytest.raises(RuntimeError):
+        E.MutliScalePairwise4DCorr(torch.rand(1, 8, 8, 8), torch.rand(1, 8, 8, 8))  # CPU tensors: no fallback
+    with pytest.raises(NotImplementedError):
+        E.MutliScalePairwise4DCorr(torch.rand(1, 320, 8, 8, device=dev()), torch.rand(1, 320, 8, 8, device=dev()))
+    with pytest.raises(ValueError):
+        E.MutliScalePairwise4DCorr(torch.rand(1, 8, 4, 4, device=dev()), torch.rand(1, 8, 4, 4, device=dev()), num_levels=4)
+
+
+def test_full_size_1080p_properties():
+    """BASELINE headline size (135x240, C=256): size-independent checks instead of a full oracle run.
+    (a) sampled rows of level 0 vs an fp32 matmul; (b) pooled levels are averages of the level below;
+    (c) lookup at integer coordinates returns pyramid entries; (d) linearity in fmap1."""
+    import ezflow_b200 as E
+
+    H, W, C = 135, 240, 256
+    N = H * W
+    g = torch.Generator(device="cpu").manual_seed(11)
+    f1 = torch.randn(1, C, H, W, generator=g).to(dev())
+    f2 = torch.randn(1, C, H, W, generator=g).to(dev())
+    obj = E.MutliScalePairwise4DCorr(f1, f2)
+    st = obj._state
+    qs = torch.tensor([0, 1, 239, 240, 12345, N - 1], device=dev())
+    lv = [st.level_view(l) for l in range(4)]
+    deq = st.deq[0].item()
+    # (a)
+    ref_rows = (f1.view(C, N)[:, qs].t().double() @ f2.view(C, N).double() / 16.0).view(-1, H, W)
+    got_rows = lv[0][qs, 0].double() * deq
+    assert rel_fro(got_rows.cpu().numpy(), ref_rows.cpu().numpy()) <= VOL_TOL
+    # (b) level l+1 == floor-avg-pool of the exact fp32 level below (computed from ref rows)
+    cur = ref_rows
+    for l in range(1, 4):
+        h, w = cur.shape[-2] // 2, cur.shape[-1] // 2
+        cur = cur[:, : 2 * h, : 2 * w].reshape(-1, h, 2, w, 2).mean(dim=(2, 4))
+        got = lv[l][qs, 0].double() * deq
+        assert tuple(got.shape[-2:]) == (h, w)
+        assert rel_fro(got.cpu().numpy(), cur.cpu().numpy()) <= VOL_TOL
+    # (c) integer coords: centre tap (i=j=r) of level 0 equals corr[q, q]
+    coords = E.coords_grid(1, H, W, device=dev())
+    out = obj(coords)
+    centre = out[0, 4 * 9 + 4].reshape(-1)[qs].double()
+    diag = torch.stack([got_rows[i].reshape(-1)[q] for i, q in enumerate(qs.tolist())])
+    assert torch.allclose(centre, diag, rtol=1e-5, atol=1e-6)
+    # (d) linearity: scaling fmap1 by 3 scales every lookup by 3 (power-of-two pre-scale makes this near-exact)
+    out3 = E.MutliScalePairwise4DCorr(3.0 * f1, f2)(coords)
+    assert rel_fro(out3.cpu().numpy(), (3.0 * out).cpu().numpy()) <= 5e-4
