@@ -26,17 +26,22 @@ _P = ctypes.POINTER
 _SIGNATURES = {
     "ezb_version": ([], c_int),
     "ezb_last_error": ([ctypes.c_char_p, c_sz], c_int),
-    "ezb_corr_pyramid_layout": ([c_int, c_int, c_int, c_int, _P(c_int), _P(c_int), _P(c_int), _P(c_i64)], c_int),
+    "ezb_corr_pyramid_layout": (
+        [c_int, c_int, c_int, c_int, _P(c_int), _P(c_int), _P(c_int), _P(c_int), _P(c_int), _P(c_i64), _P(c_i64)],
+        c_int,
+    ),
+    "ezb_corr_pyramid_elem_offset": ([c_int, c_int, c_int, c_int, c_int], c_i64),
+    "ezb_corr_grad_layout": ([c_int, c_int, c_int, _P(c_int), _P(c_int), _P(c_int), _P(c_i64)], c_int),
     "ezb_corr_pyramid_workspace_bytes": ([c_int, c_int, c_int, c_int, _P(c_sz)], c_int),
-    "ezb_corr_pyramid_fwd": ([c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, _P(c_vp), c_vp, c_vp, c_sz, c_vp], c_int),
+    "ezb_corr_pyramid_fwd": ([c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_sz, c_vp], c_int),
     "ezb_corr_pyramid_fwd_ex": (
-        [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, _P(c_vp), c_vp, c_vp, c_sz, c_vp, c_vp, c_vp],
+        [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_sz, c_vp, c_vp, c_vp],
         c_int,
     ),
     "ezb_event_create": ([_P(c_vp)], c_int),
     "ezb_event_destroy": ([c_vp], c_int),
     "ezb_event_elapsed_ms": ([c_vp, c_vp, _P(c_f32)], c_int),
-    "ezb_corr_lookup_fwd": ([_P(c_vp), c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp], c_int),
+    "ezb_corr_lookup_fwd": ([c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp], c_int),
     "ezb_corr_lookup_bwd": ([c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, _P(c_vp), c_vp], c_int),
     "ezb_corr_pyramid_bwd": ([_P(c_vp), c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp], c_int),
     "ezb_local_corr_fwd": ([c_vp, c_vp] + [c_int] * 12 + [c_f32, c_f32, c_vp, c_i64, c_vp], c_int),

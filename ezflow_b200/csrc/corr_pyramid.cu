@@ -12,7 +12,8 @@
 //            sweeps query blocks (A operand streamed through a 4-stage TMA ring).  Because every
 //            thread of the epilogue owns one query row and a whole 8x32 target patch, all four
 //            pyramid levels (8x32 -> 4x16 -> 2x8 -> 1x4) are reduced in registers from the fp32
-//            accumulators and written once with TMA stores: the pyramid is never re-read.
+//            accumulators and written once, as contiguous 4 KB sections (bulk shared->global copies)
+//            of the warp-strip-major pyramid layout (ezb_common.cuh): the pyramid is never re-read.
 #include "ezb_common.cuh"
 #include "ezb_ptx.cuh"
 
@@ -27,7 +28,7 @@ constexpr int KB_MAX = 4;         // resident B k-blocks  (C <= 256)
 constexpr int STAGES = 4;         // A ring
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_KB_BYTES = BN * BK * 2;      // 32 KB
-constexpr int SLOT_BYTES = 4096;             // one staged TMA store: 32 queries x 128 B
+constexpr int SLOT_BYTES = 4096;             // one staged section: 32 queries x 128 B
 constexpr int SLOTS_PER_WARP = 2;
 constexpr int NUM_THREADS = 256;
 constexpr int SMEM_B = 0;
@@ -39,12 +40,10 @@ constexpr int TMEM_COLS = 512;                     // two 256-column accumulator
 
 struct GemmParams {
   int B, N, KB, L;
-  int n_pw, n_patches, n_qblocks;
-  long long total_tiles;
+  int n_pw, n_patches, n_qblocks, n_groups;
+  long long total_tiles, group_bytes;
   const float* epi_scale;  // [B]
-  void* lvl3;              // level-3 buffer (plain stores), may be null when L < 4
-  int h3, pitch3;
-  long long qstride3;
+  char* pyr;               // pyramid buffer, group blocks ordered [pair][patch][group]
 };
 
 // ------------------------------------------------------------------------------ prep kernels
@@ -133,21 +132,6 @@ __global__ void __launch_bounds__(256) convert_kmajor_kernel(const float* __rest
   }
 }
 
-// Generic 2x2 floor average pool between two pyramid levels (only used for levels >= 4).
-template <typename T>
-__global__ void pool_level_kernel(const T* __restrict__ in, T* __restrict__ out, long long rows, int ho, int wo,
-                                  int pitch_in, long long qs_in, int pitch_out, long long qs_out) {
-  const long long total = rows * ho * wo;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % wo);
-    const int y = (int)((i / wo) % ho);
-    const long long q = i / ((long long)wo * ho);
-    const T* p = in + q * qs_in + (long long)(2 * y) * pitch_in + 2 * x;
-    const float v = 0.25f * (((float)p[0] + (float)p[1]) + ((float)p[pitch_in] + (float)p[pitch_in + 1]));
-    out[q * qs_out + (long long)y * pitch_out + x] = (T)v;
-  }
-}
-
 // ----------------------------------------------------------------------------- epilogue helpers
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
@@ -156,50 +140,38 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(src_smem), "r"(bytes)
+               : "memory");
+}
 
-// One staged TMA store issued by a warp: every lane owns NWORDS 32-bit words (its query's rows of the
-// box, row-major), the box is (w, rows, 32 queries, 1 batch).  `swz` = 7/3/1/0 for the tensor map's
-// 128B/64B/32B/no swizzle: physical = off ^ (((off >> 7) & swz) << 4)  (slot base is 1024-aligned).
+// One section of a group block (32 lines, one per lane, NWORDS*4 bytes each): every lane writes its line
+// into the staging slot with the layout's XOR chunk swizzle (bank-conflict free), then lane 0 issues ONE
+// contiguous bulk copy shared -> global for the whole section (4 KB / 2 KB).
 template <int NWORDS>
-__device__ __forceinline__ void staged_store(uint32_t slot, int lane, const uint32_t (&w)[NWORDS], uint32_t swz,
-                                             const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
-  static_assert(NWORDS % 4 == 0 && NWORDS <= 32, "lane payload must be 16..128 bytes");
+__device__ __forceinline__ void staged_section_store(uint32_t slot, int lane, const uint32_t (&w)[NWORDS], char* gdst) {
+  static_assert(NWORDS == 32 || NWORDS == 16, "lines are 128 or 64 bytes");
+  constexpr uint32_t kSwz = NWORDS / 4 - 1;
   if (lane == 0) ptx::tma_wait_group_read<SLOTS_PER_WARP - 1>();  // the slot written two stores ago is free
   __syncwarp();
 #pragma unroll
-  for (int c = 0; c < NWORDS / 4; ++c) {
-    const uint32_t off = (uint32_t)lane * (NWORDS * 4) + c * 16;
-    st_shared_v4(slot + (off ^ (((off >> 7) & swz) << 4)), w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
-  }
+  for (int c = 0; c < NWORDS / 4; ++c)
+    st_shared_v4(slot + lane * (NWORDS * 4) + ((c ^ (lane & kSwz)) << 4), w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
   ptx::fence_proxy_async_smem();
   __syncwarp();
   if (lane == 0) {
-    ptx::tma_store_4d(tm, slot, c0, c1, c2, c3);
+    bulk_store(gdst, slot, 32 * NWORDS * 4);
     ptx::tma_commit_group();
   }
 }
 
-template <typename OutT>
-struct OutTraits;
-template <>
-struct OutTraits<__half> {
-  static constexpr uint32_t swz_l0 = 3, swz_l1 = 1, swz_l2 = 0;  // inner box 64 B / 32 B / 16 B
-};
-template <>
-struct OutTraits<float> {
-  static constexpr uint32_t swz_l0 = 7, swz_l1 = 3, swz_l2 = 1;  // inner box 128 B / 64 B / 32 B
-};
-
-// Epilogue of one tile for one warp: 32 queries (one per lane) x one 8x32 target patch.
+// Epilogue of one tile for one warp: 32 queries (one per lane) x one 8x32 target patch -> one group block.
 // Strip s holds patch rows 2s and 2s+1; level-1 row s is their 2x2 average.  Levels 2 and 3 follow
 // from level 1, all from the fp32 accumulators (the reference pools fp32 values too).
 template <typename OutT>
 __device__ __forceinline__ void epilogue_tile(uint32_t t_base, uint32_t stg_base, uint32_t& slot_ctr, int lane,
-                                              float scale, uint32_t tmem_empty_bar, const CUtensorMap* tmL0,
-                                              const CUtensorMap* tmL1, const CUtensorMap* tmL2, const GemmParams& p,
-                                              int b, int ph, int pw, int q0) {
+                                              float scale, uint32_t tmem_empty_bar, int L, char* gblock) {
   constexpr bool kHalf = sizeof(OutT) == 2;
-  using TR = OutTraits<OutT>;
   auto next_slot = [&]() { return stg_base + (slot_ctr++ & (SLOTS_PER_WARP - 1)) * SLOT_BYTES; };
   float l1[4][16];
 #pragma unroll
@@ -213,6 +185,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_base, uint32_t stg_base
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tmem_empty_bar);
     }
+    if (gblock == nullptr) continue;  // query group entirely beyond N: nothing to store
     float v0[32], v1[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -223,78 +196,71 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_base, uint32_t stg_base
     for (int j = 0; j < 16; ++j) l1[s][j] = 0.25f * ((v0[2 * j] + v0[2 * j + 1]) + (v1[2 * j] + v1[2 * j + 1]));
 
     if constexpr (kHalf) {
-      uint32_t w[32];  // [row 2s: 32 halfs][row 2s+1: 32 halfs]  -> box (32 w, 2 h, 32 q, 1)
+      uint32_t w[32];  // line = [row 2s: 32 halfs][row 2s+1: 32 halfs]        (section s)
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         w[j] = pack_half2(v0[2 * j], v0[2 * j + 1]);
         w[16 + j] = pack_half2(v1[2 * j], v1[2 * j + 1]);
       }
-      staged_store<32>(next_slot(), lane, w, TR::swz_l0, tmL0, pw * PW, ph * PH + 2 * s, q0, b);
+      staged_section_store<32>(next_slot(), lane, w, gblock + s * 4096);
     } else {
-      uint32_t w[32];  // one row of 32 floats per store -> box (32 w, 1 h, 32 q, 1)
+      uint32_t w[32];  // line = one row of 32 floats                            (sections 2s, 2s+1)
 #pragma unroll
       for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(v0[j]);
-      staged_store<32>(next_slot(), lane, w, TR::swz_l0, tmL0, pw * PW, ph * PH + 2 * s, q0, b);
+      staged_section_store<32>(next_slot(), lane, w, gblock + (2 * s) * 4096);
 #pragma unroll
       for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(v1[j]);
-      staged_store<32>(next_slot(), lane, w, TR::swz_l0, tmL0, pw * PW, ph * PH + 2 * s + 1, q0, b);
-      if (p.L > 1 && (s & 1)) {  // level-1 rows s-1, s as fp32 -> box (16 w, 2 h, 32 q, 1)
+      staged_section_store<32>(next_slot(), lane, w, gblock + (2 * s + 1) * 4096);
+      if (L > 1 && (s & 1)) {  // level-1 rows s-1, s                              (section 8 + s/2)
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           w[j] = __float_as_uint(l1[s - 1][j]);
           w[16 + j] = __float_as_uint(l1[s][j]);
         }
-        staged_store<32>(next_slot(), lane, w, TR::swz_l1, tmL1, pw * (PW / 2), ph * (PH / 2) + s - 1, q0, b);
+        staged_section_store<32>(next_slot(), lane, w, gblock + (8 + (s >> 1)) * 4096);
       }
     }
   }
-  if (p.L > 1) {
-    if constexpr (kHalf) {
-      uint32_t w[32];  // 4 rows x 16 halfs -> box (16 w, 4 h, 32 q, 1)
+  if (gblock == nullptr || L < 2) return;
+  if constexpr (kHalf) {
+    uint32_t w[32];  // 4 rows x 16 halfs                                          (section 4)
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) w[r * 8 + j] = pack_half2(l1[r][2 * j], l1[r][2 * j + 1]);
-      staged_store<32>(next_slot(), lane, w, TR::swz_l1, tmL1, pw * (PW / 2), ph * (PH / 2), q0, b);
-    }
+      for (int j = 0; j < 8; ++j) w[r * 8 + j] = pack_half2(l1[r][2 * j], l1[r][2 * j + 1]);
+    staged_section_store<32>(next_slot(), lane, w, gblock + 4 * 4096);
   }
-  if (p.L > 2) {
-    float l2[2][8];
+  if (L < 3) return;
+  float l2[2][8], l3[4];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      l2[r][j] = 0.25f * ((l1[2 * r][2 * j] + l1[2 * r][2 * j + 1]) + (l1[2 * r + 1][2 * j] + l1[2 * r + 1][2 * j + 1]));
+#pragma unroll
+  for (int j = 0; j < 4; ++j) l3[j] = 0.25f * ((l2[0][2 * j] + l2[0][2 * j + 1]) + (l2[1][2 * j] + l2[1][2 * j + 1]));
+  if constexpr (kHalf) {
+    uint32_t w[16];  // [level 2: 2 x 8 halfs = 32 B][level 3: 4 halfs = 8 B][pad]   (section 5, 64-byte lines)
 #pragma unroll
     for (int r = 0; r < 2; ++r)
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        l2[r][j] = 0.25f * ((l1[2 * r][2 * j] + l1[2 * r][2 * j + 1]) + (l1[2 * r + 1][2 * j] + l1[2 * r + 1][2 * j + 1]));
-    if constexpr (kHalf) {
-      uint32_t w[8];  // 2 rows x 8 halfs -> box (8 w, 2 h, 32 q, 1)
+      for (int j = 0; j < 4; ++j) w[r * 4 + j] = pack_half2(l2[r][2 * j], l2[r][2 * j + 1]);
+    w[8] = pack_half2(l3[0], l3[1]);
+    w[9] = pack_half2(l3[2], l3[3]);
 #pragma unroll
-      for (int r = 0; r < 2; ++r)
+    for (int j = 10; j < 16; ++j) w[j] = 0u;
+    staged_section_store<16>(next_slot(), lane, w, gblock + 5 * 4096);
+  } else {
+    uint32_t w[32];  // [level 2: 2 x 8 floats = 64 B][level 3: 4 floats = 16 B][pad] (section 10)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) w[r * 4 + j] = pack_half2(l2[r][2 * j], l2[r][2 * j + 1]);
-      staged_store<8>(next_slot(), lane, w, TR::swz_l2, tmL2, pw * (PW / 4), ph * (PH / 4), q0, b);
-    } else {
-      uint32_t w[16];
+    for (int r = 0; r < 2; ++r)
 #pragma unroll
-      for (int r = 0; r < 2; ++r)
+      for (int j = 0; j < 8; ++j) w[r * 8 + j] = __float_as_uint(l2[r][j]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) w[r * 8 + j] = __float_as_uint(l2[r][j]);
-      staged_store<16>(next_slot(), lane, w, TR::swz_l2, tmL2, pw * (PW / 4), ph * (PH / 4), q0, b);
-    }
-    if (p.L > 3) {  // level 3: 1 x 4 values per query, 8 or 16 bytes: plain vector store
-      const int q = q0 + lane;
-      if (q < p.N && ph < p.h3 && pw * 4 < p.pitch3) {
-        float l3[4];
+    for (int j = 0; j < 4; ++j) w[16 + j] = __float_as_uint(l3[j]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) l3[j] = 0.25f * ((l2[0][2 * j] + l2[0][2 * j + 1]) + (l2[1][2 * j] + l2[1][2 * j + 1]));
-        OutT* dst = reinterpret_cast<OutT*>(p.lvl3) + ((long long)b * p.N + q) * p.qstride3 + (long long)ph * p.pitch3 + pw * 4;
-        if constexpr (kHalf) {
-          uint2 v = make_uint2(pack_half2(l3[0], l3[1]), pack_half2(l3[2], l3[3]));
-          *reinterpret_cast<uint2*>(dst) = v;
-        } else {
-          *reinterpret_cast<float4*>(dst) = make_float4(l3[0], l3[1], l3[2], l3[3]);
-        }
-      }
-    }
+    for (int j = 20; j < 32; ++j) w[j] = 0u;
+    staged_section_store<32>(next_slot(), lane, w, gblock + 10 * 4096);
   }
 }
 
@@ -302,8 +268,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_base, uint32_t stg_base
 template <typename OutT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     corr_pyramid_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                             const __grid_constant__ CUtensorMap tmL0, const __grid_constant__ CUtensorMap tmL1,
-                             const __grid_constant__ CUtensorMap tmL2, const GemmParams p) {
+                             const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -321,9 +286,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
-    ptx::prefetch_tmap(&tmL0);
-    ptx::prefetch_tmap(&tmL1);
-    ptx::prefetch_tmap(&tmL2);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -413,25 +375,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     const uint32_t stg_base = sStg + quad * (SLOTS_PER_WARP * SLOT_BYTES);
     uint32_t slot_ctr = 0, tile = 0;
     long long cur_bp = -1;
-    int b = 0, ph = 0, pw = 0;
+    char* patch_base = nullptr;
     float scale = 1.f;
     for (long long t = t_begin; t < t_end; ++t, ++tile) {
       const long long bp = t / p.n_qblocks;
       const int qb = (int)(t - bp * p.n_qblocks);
       if (bp != cur_bp) {
-        b = (int)(bp / p.n_patches);
-        const int patch = (int)(bp - (long long)b * p.n_patches);
-        ph = patch / p.n_pw;
-        pw = patch - ph * p.n_pw;
+        const int b = (int)(bp / p.n_patches);
         scale = __ldg(p.epi_scale + b);
+        patch_base = p.pyr + bp * p.n_groups * p.group_bytes;  // blocks are ordered [pair][patch][group]
         cur_bp = bp;
       }
       const uint32_t acc = tile & 1, aphase = (tile >> 1) & 1;
       ptx::mbar_wait(tmem_full(acc), aphase);
       ptx::tc_fence_after();
       const uint32_t t_base = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
-      epilogue_tile<OutT>(t_base, stg_base, slot_ctr, lane, scale, tmem_empty(acc), &tmL0, &tmL1, &tmL2, p, b, ph, pw,
-                          qb * BM + quad * 32);
+      const int grp = qb * (BM / 32) + quad;  // query group of this warp
+      epilogue_tile<OutT>(t_base, stg_base, slot_ctr, lane, scale, tmem_empty(acc), p.L,
+                          grp < p.n_groups ? patch_base + (long long)grp * p.group_bytes : nullptr);
     }
     if (lane == 0) ptx::tma_wait_group<0>();  // all bulk stores done before smem goes away
   }
@@ -469,13 +430,6 @@ static int make_tmap(CUtensorMap* tm, CUtensorMapDataType dt, int rank, void* pt
   return EZB_OK;
 }
 
-static CUtensorMapSwizzle swz_for_inner_bytes(int bytes) {
-  return bytes >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-         : bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
-         : bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
-                       : CU_TENSOR_MAP_SWIZZLE_NONE;
-}
-
 struct Workspace {
   unsigned int* amax;  // [2][B]
   float* epi;          // [B]
@@ -506,11 +460,10 @@ static size_t ws_layout(int B, int C, int N, void* base, Workspace* ws) {
 }
 
 template <typename OutT>
-static int launch_gemm(const Workspace& ws, int B, int C, int H, int W, int L, const LevelGeom* g, void* const* lvl,
-                       cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
-  const int N = H * W, Cp = round_up(C, BK), es = (int)sizeof(OutT);
-  const CUtensorMapDataType odt = es == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-  CUtensorMap tmA, tmB, tmL[3];
+static int launch_gemm(const Workspace& ws, int B, int C, const PyrLayout& lay, void* pyr, cudaStream_t st, cudaEvent_t ev0,
+                       cudaEvent_t ev1) {
+  const int H = lay.H, W = lay.W, N = H * W, Cp = round_up(C, BK);
+  CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[3] = {(cuuint64_t)Cp, (cuuint64_t)N, (cuuint64_t)B};
     cuuint64_t str[2] = {(cuuint64_t)Cp * 2, (cuuint64_t)N * Cp * 2};
@@ -525,38 +478,26 @@ static int launch_gemm(const Workspace& ws, int B, int C, int H, int W, int L, c
     int r = make_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, ws.f2h, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (r) return r;
   }
-  // store boxes: (w, rows, 32 queries, 1); rows chosen so a lane's payload is <= 128 B
-  const int box_w[3] = {PW, PW / 2, PW / 4};
-  const int box_h[3] = {es == 2 ? 2 : 1, es == 2 ? 4 : 2, 2};
-  for (int l = 0; l < 3; ++l) {
-    const int ll = l < L ? l : 0;  // unused maps alias level 0 (never dereferenced by the kernel)
-    cuuint64_t dims[4] = {(cuuint64_t)g[ll].w, (cuuint64_t)g[ll].h, (cuuint64_t)N, (cuuint64_t)B};
-    cuuint64_t str[3] = {(cuuint64_t)g[ll].pitch * es, (cuuint64_t)g[ll].qstride * es, (cuuint64_t)N * g[ll].qstride * es};
-    cuuint32_t box[4] = {(cuuint32_t)box_w[l], (cuuint32_t)box_h[l], 32, 1};
-    int r = make_tmap(&tmL[l], odt, 4, lvl[ll], dims, str, box, swz_for_inner_bytes(box_w[l] * es));
-    if (r) return r;
-  }
   GemmParams p;
   p.B = B;
   p.N = N;
   p.KB = Cp / BK;
-  p.L = L < 4 ? L : 4;
-  p.n_pw = cdiv(W, PW);
-  p.n_patches = p.n_pw * cdiv(H, PH);
+  p.L = lay.L;
+  p.n_pw = lay.n_pw;
+  p.n_patches = lay.n_patches;
   p.n_qblocks = cdiv(N, BM);
+  p.n_groups = lay.n_groups;
+  p.group_bytes = lay.group_bytes;
   p.total_tiles = (long long)B * p.n_patches * p.n_qblocks;
   p.epi_scale = ws.epi;
-  p.lvl3 = L > 3 ? lvl[3] : nullptr;
-  p.h3 = L > 3 ? g[3].h : 0;
-  p.pitch3 = L > 3 ? g[3].pitch : 0;
-  p.qstride3 = L > 3 ? g[3].qstride : 0;
+  p.pyr = static_cast<char*>(pyr);
 
   auto kern = corr_pyramid_gemm_kernel<OutT>;
   EZB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   long long grid = num_sms();
   if (grid > p.total_tiles) grid = p.total_tiles;
   if (ev0) EZB_CUDA_OK(cudaEventRecord(ev0, st));
-  kern<<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, tmL[0], tmL[1], tmL[2], p);
+  kern<<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, p);
   EZB_LAUNCH_OK();
   if (ev1) EZB_CUDA_OK(cudaEventRecord(ev1, st));
   return EZB_OK;
@@ -567,18 +508,30 @@ static int launch_gemm(const Workspace& ws, int B, int C, int H, int W, int L, c
 
 using namespace ezb;
 
-extern "C" int ezb_corr_pyramid_layout(int H, int W, int L, int dtype, int* h, int* w, int* pitch, int64_t* qstride) {
-  EZB_REQUIRE(H > 0 && W > 0 && L >= 1 && L <= EZB_MAX_LEVELS, "bad pyramid shape H=%d W=%d L=%d", H, W, L);
+extern "C" int ezb_corr_pyramid_layout(int H, int W, int L, int dtype, int* h, int* w, int* n_ph, int* n_pw, int* n_groups,
+                                       int64_t* group_bytes, int64_t* pair_bytes) {
+  EZB_REQUIRE(H > 0 && W > 0 && L >= 1, "bad pyramid shape H=%d W=%d L=%d", H, W, L);
   EZB_REQUIRE(dtype == EZB_F32 || dtype == EZB_F16, "bad dtype %d", dtype);
-  LevelGeom g[EZB_MAX_LEVELS];
-  EZB_REQUIRE(pyramid_geom(H, W, L, dtype, g), "feature map %dx%d too small for %d pyramid levels", H, W, L);
+  if (L > PYR_MAX_LEVELS) return fail(EZB_ERR_UNSUPPORTED, "num_levels %d > %d is not supported by the fused pyramid", L, PYR_MAX_LEVELS);
+  PyrLayout lay;
+  EZB_REQUIRE(pyr_layout(H, W, L, dtype, &lay), "feature map %dx%d too small for %d pyramid levels", H, W, L);
   for (int l = 0; l < L; ++l) {
-    if (h) h[l] = g[l].h;
-    if (w) w[l] = g[l].w;
-    if (pitch) pitch[l] = g[l].pitch;
-    if (qstride) qstride[l] = g[l].qstride;
+    if (h) h[l] = H >> l;
+    if (w) w[l] = W >> l;
   }
+  if (n_ph) *n_ph = lay.n_ph;
+  if (n_pw) *n_pw = lay.n_pw;
+  if (n_groups) *n_groups = lay.n_groups;
+  if (group_bytes) *group_bytes = lay.group_bytes;
+  if (pair_bytes) *pair_bytes = lay.pair_bytes;
   return EZB_OK;
+}
+
+extern "C" int64_t ezb_corr_pyramid_elem_offset(int dtype, int level, int lane, int yy, int xx) {
+  if ((dtype != EZB_F32 && dtype != EZB_F16) || level < 0 || level >= PYR_MAX_LEVELS || lane < 0 || lane >= PYR_QG || yy < 0 ||
+      yy >= (PYR_PH >> level) || xx < 0 || xx >= (PYR_PW >> level))
+    return -1;
+  return pyr_elem_offset(dtype == EZB_F16 ? 2 : 4, level, lane, yy, xx);
 }
 
 extern "C" int ezb_corr_pyramid_workspace_bytes(int B, int C, int H, int W, size_t* bytes) {
@@ -588,17 +541,17 @@ extern "C" int ezb_corr_pyramid_workspace_bytes(int B, int C, int H, int W, size
 }
 
 extern "C" int ezb_corr_pyramid_fwd_ex(const float* fmap1, const float* fmap2, int B, int C, int H, int W, int L, int dtype,
-                                       void* const* lvl_ptrs, float* deq_scale, void* workspace, size_t workspace_bytes,
+                                       void* pyramid, float* deq_scale, void* workspace, size_t workspace_bytes,
                                        void* stream, void* ev_gemm_start, void* ev_gemm_end) {
-  EZB_REQUIRE(fmap1 && fmap2 && lvl_ptrs && deq_scale && workspace, "null pointer");
-  EZB_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && L >= 1 && L <= EZB_MAX_LEVELS, "bad shape B=%d C=%d H=%d W=%d L=%d", B, C,
-              H, W, L);
+  EZB_REQUIRE(fmap1 && fmap2 && pyramid && deq_scale && workspace, "null pointer");
+  EZB_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && L >= 1, "bad shape B=%d C=%d H=%d W=%d L=%d", B, C, H, W, L);
   EZB_REQUIRE(dtype == EZB_F32 || dtype == EZB_F16, "bad dtype %d", dtype);
   if (round_up(C, k1::BK) > k1::KB_MAX * k1::BK)
     return fail(EZB_ERR_UNSUPPORTED, "all-pairs correlation supports C <= %d (got %d)", k1::KB_MAX * k1::BK, C);
-  LevelGeom g[EZB_MAX_LEVELS];
-  EZB_REQUIRE(pyramid_geom(H, W, L, dtype, g), "feature map %dx%d too small for %d pyramid levels", H, W, L);
-  for (int l = 0; l < L; ++l) EZB_REQUIRE(lvl_ptrs[l] && (reinterpret_cast<uintptr_t>(lvl_ptrs[l]) & 15) == 0, "level %d pointer null/unaligned", l);
+  if (L > PYR_MAX_LEVELS) return fail(EZB_ERR_UNSUPPORTED, "num_levels %d > %d is not supported by the fused pyramid", L, PYR_MAX_LEVELS);
+  PyrLayout lay;
+  EZB_REQUIRE(pyr_layout(H, W, L, dtype, &lay), "feature map %dx%d too small for %d pyramid levels", H, W, L);
+  EZB_REQUIRE((reinterpret_cast<uintptr_t>(pyramid) & 127) == 0, "pyramid buffer must be 128-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int N = H * W, Cp = round_up(C, k1::BK);
 
@@ -623,28 +576,12 @@ extern "C" int ezb_corr_pyramid_fwd_ex(const float* fmap1, const float* fmap2, i
   EZB_LAUNCH_OK();
 
   cudaEvent_t ev0 = static_cast<cudaEvent_t>(ev_gemm_start), ev1 = static_cast<cudaEvent_t>(ev_gemm_end);
-  int r = dtype == EZB_F16 ? k1::launch_gemm<__half>(ws, B, C, H, W, L, g, lvl_ptrs, st, ev0, ev1)
-                           : k1::launch_gemm<float>(ws, B, C, H, W, L, g, lvl_ptrs, st, ev0, ev1);
-  if (r) return r;
-
-  for (int l = 4; l < L; ++l) {  // levels beyond the fused four: plain pooling passes (tiny)
-    const long long rows = (long long)B * N;
-    const long long total = rows * g[l].h * g[l].w;
-    const int blocks = (int)std::min<long long>(cdiv64(total, 256), 148 * 16);
-    if (dtype == EZB_F16)
-      k1::pool_level_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)lvl_ptrs[l - 1], (__half*)lvl_ptrs[l], rows, g[l].h,
-                                                            g[l].w, g[l - 1].pitch, g[l - 1].qstride, g[l].pitch, g[l].qstride);
-    else
-      k1::pool_level_kernel<float><<<blocks, 256, 0, st>>>((const float*)lvl_ptrs[l - 1], (float*)lvl_ptrs[l], rows, g[l].h,
-                                                           g[l].w, g[l - 1].pitch, g[l - 1].qstride, g[l].pitch, g[l].qstride);
-    EZB_LAUNCH_OK();
-  }
-  return EZB_OK;
+  return dtype == EZB_F16 ? k1::launch_gemm<__half>(ws, B, C, lay, pyramid, st, ev0, ev1)
+                          : k1::launch_gemm<float>(ws, B, C, lay, pyramid, st, ev0, ev1);
 }
 
 extern "C" int ezb_corr_pyramid_fwd(const float* fmap1, const float* fmap2, int B, int C, int H, int W, int L, int dtype,
-                                    void* const* lvl_ptrs, float* deq_scale, void* workspace, size_t workspace_bytes,
-                                    void* stream) {
-  return ezb_corr_pyramid_fwd_ex(fmap1, fmap2, B, C, H, W, L, dtype, lvl_ptrs, deq_scale, workspace, workspace_bytes, stream,
+                                    void* pyramid, float* deq_scale, void* workspace, size_t workspace_bytes, void* stream) {
+  return ezb_corr_pyramid_fwd_ex(fmap1, fmap2, B, C, H, W, L, dtype, pyramid, deq_scale, workspace, workspace_bytes, stream,
                                  nullptr, nullptr);
 }

@@ -6,9 +6,9 @@ ezflow/similarity/correlation/pairwise.py:9-88): same name (sic), constructor ar
 ``nn.Module``, exactly like the reference.
 
 Deviations, all documented in DESIGN.md §6:
-* the pyramid is stored in the library's padded layout, by default as fp16 with a per-pair
-  power-of-two scale (fp32 selectable with ``set_pyramid_dtype("fp32")``); ``corr_pyramid`` is
-  therefore a property that materialises reference-shaped fp32 tensors on demand;
+* the pyramid is stored in the library's tiled ("warp-strip-major") layout, by default as fp16 with a
+  per-pair power-of-two scale (fp32 selectable with ``set_pyramid_dtype("fp32")``); ``corr_pyramid`` is
+  therefore a property that materialises reference-shaped fp32 tensors on demand; at most 4 levels;
 * no gradient w.r.t. ``coords`` (RAFT detaches them, reference models/raft.py:115);
 * CPU tensors raise ``RuntimeError`` — there is no CPU fallback.
 """
@@ -38,12 +38,46 @@ def get_pyramid_dtype():
     return _PYRAMID_DTYPE
 
 
-def pyramid_layout(H, W, L, dtype_code):
+class PyramidLayout:
+    """Geometry of the warp-strip-major pyramid buffer (include/ezflow_b200.h)."""
+
+    def __init__(self, H, W, L, dtype_code):
+        h = (ctypes.c_int * L)()
+        w = (ctypes.c_int * L)()
+        n_ph, n_pw, n_groups = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        gb, pb = ctypes.c_int64(), ctypes.c_int64()
+        _cabi.check(
+            _cabi.lib().ezb_corr_pyramid_layout(
+                H, W, L, dtype_code, h, w, ctypes.byref(n_ph), ctypes.byref(n_pw), ctypes.byref(n_groups),
+                ctypes.byref(gb), ctypes.byref(pb),
+            )
+        )
+        self.levels = [(h[i], w[i]) for i in range(L)]
+        self.n_ph, self.n_pw, self.n_groups = n_ph.value, n_pw.value, n_groups.value
+        self.group_bytes, self.pair_bytes = gb.value, pb.value
+        self.dtype_code = dtype_code
+        self.es = 2 if dtype_code == _cabi.EZB_F16 else 4
+
+    def level_index(self, l, device):
+        """Element offsets (32 lanes, th, tw) of level l inside a group block, from the library itself."""
+        th, tw = 8 >> l, 32 >> l
+        fn = _cabi.lib().ezb_corr_pyramid_elem_offset
+        idx = torch.empty((32, th, tw), dtype=torch.int64)
+        for lane in range(32):
+            for yy in range(th):
+                for xx in range(tw):
+                    off = fn(self.dtype_code, l, lane, yy, xx)
+                    assert off >= 0 and off % self.es == 0
+                    idx[lane, yy, xx] = off // self.es
+        return idx.to(device)
+
+
+def grad_layout(H, W, L):
     h = (ctypes.c_int * L)()
     w = (ctypes.c_int * L)()
     pitch = (ctypes.c_int * L)()
     qs = (ctypes.c_int64 * L)()
-    _cabi.check(_cabi.lib().ezb_corr_pyramid_layout(H, W, L, dtype_code, h, w, pitch, qs))
+    _cabi.check(_cabi.lib().ezb_corr_grad_layout(H, W, L, h, w, pitch, qs))
     return [(h[i], w[i], pitch[i], qs[i]) for i in range(L)]
 
 
@@ -58,8 +92,8 @@ class _PyramidState:
         self.device = fmap1.device
         self.fmap1, self.fmap2 = fmap1, fmap2
         self.N = self.H * self.W
-        self.layout = pyramid_layout(self.H, self.W, self.L, self.dtype_code)
-        self.levels = None
+        self.layout = PyramidLayout(self.H, self.W, self.L, self.dtype_code)
+        self.pyr = None
         self.deq = None
         self.grad_levels = None
         self.grad_layout = None
@@ -69,8 +103,7 @@ class _PyramidState:
         lib = _cabi.lib()
         ev0, ev1 = ev_gemm if ev_gemm is not None else (None, None)
         with torch.cuda.device(self.device):
-            rows = self.B * self.N
-            self.levels = [torch.empty(rows * qs, dtype=self.tdtype, device=self.device) for (_, _, _, qs) in self.layout]
+            self.pyr = torch.empty(self.B * self.layout.pair_bytes // self.layout.es, dtype=self.tdtype, device=self.device)
             self.deq = torch.empty(self.B, dtype=torch.float32, device=self.device)
             nbytes = ctypes.c_size_t(0)
             _cabi.check(lib.ezb_corr_pyramid_workspace_bytes(self.B, self.C, self.H, self.W, ctypes.byref(nbytes)))
@@ -78,21 +111,38 @@ class _PyramidState:
             _cabi.check(
                 lib.ezb_corr_pyramid_fwd_ex(
                     _cabi.ptr(self.fmap1), _cabi.ptr(self.fmap2), self.B, self.C, self.H, self.W, self.L, self.dtype_code,
-                    _cabi.ptr_array(self.levels), _cabi.ptr(self.deq), _cabi.ptr(ws), nbytes.value, _cabi.stream_ptr(self.device),
+                    _cabi.ptr(self.pyr), _cabi.ptr(self.deq), _cabi.ptr(ws), nbytes.value, _cabi.stream_ptr(self.device),
                     ev0, ev1,
                 )
             )
             # ws is released to the caching allocator here; stream ordering keeps that safe
 
-    def level_view(self, l, buffers=None, layout=None):
-        """(B*N, 1, h_l, w_l) strided view of level l in the library layout."""
-        buffers = self.levels if buffers is None else buffers
-        h, w, pitch, qs = (self.layout if layout is None else layout)[l]
-        return buffers[l].as_strided((self.B * self.N, 1, h, w), (qs, qs, pitch, 1))
+    def level_tensor(self, l, queries=None):
+        """Level l as a reference-shaped (rows, 1, h_l, w_l) tensor in storage dtype (a gathered copy).
+
+        queries: optional 1-D LongTensor of flat row indices b*N+q to extract; default all B*N rows."""
+        lay = self.layout
+        h, w = lay.levels[l]
+        th, tw = 8 >> l, 32 >> l
+        ge = lay.group_bytes // lay.es
+        blocks = self.pyr.view(self.B, lay.n_ph, lay.n_pw, lay.n_groups, ge)
+        idx = lay.level_index(l, self.device)  # (32, th, tw)
+        if queries is None:
+            t = blocks[..., idx]  # (B, n_ph, n_pw, G, 32, th, tw)
+            t = t.permute(0, 3, 4, 1, 5, 2, 6).reshape(self.B, lay.n_groups * 32, lay.n_ph * th, lay.n_pw * tw)
+            return t[:, : self.N, :h, :w].reshape(self.B * self.N, 1, h, w)
+        b = queries // self.N
+        q = queries % self.N
+        t = blocks[b, :, :, q // 32][..., :]  # (nq, n_ph, n_pw, ge)
+        sel = idx[q % 32]  # (nq, th, tw)
+        t = torch.gather(t.reshape(len(queries), lay.n_ph * lay.n_pw, ge), 2,
+                         sel.reshape(len(queries), 1, th * tw).expand(-1, lay.n_ph * lay.n_pw, -1))
+        t = t.reshape(len(queries), lay.n_ph, lay.n_pw, th, tw).permute(0, 1, 3, 2, 4)
+        return t.reshape(len(queries), 1, lay.n_ph * th, lay.n_pw * tw)[:, :, :h, :w]
 
     def ensure_grad(self):
         if self.grad_levels is None:
-            self.grad_layout = pyramid_layout(self.H, self.W, self.L, _cabi.EZB_F32)
+            self.grad_layout = grad_layout(self.H, self.W, self.L)
             rows = self.B * self.N
             self.grad_levels = [torch.zeros(rows * qs, dtype=torch.float32, device=self.device) for (_, _, _, qs) in self.grad_layout]
         return self.grad_levels
@@ -132,7 +182,7 @@ def _lookup_forward(state, coords, radius):
     with torch.cuda.device(state.device):
         _cabi.check(
             _cabi.lib().ezb_corr_lookup_fwd(
-                _cabi.ptr_array(state.levels), _cabi.ptr(state.deq), _cabi.ptr(coords), B, H, W, state.L, radius,
+                _cabi.ptr(state.pyr), _cabi.ptr(state.deq), _cabi.ptr(coords), B, H, W, state.L, radius,
                 state.dtype_code, _cabi.ptr(out), _cabi.stream_ptr(state.device),
             )
         )
@@ -186,8 +236,8 @@ class MutliScalePairwise4DCorr:
         f2 = _cabi.require_cuda_f32(fmap2, "fmap2")
         if f1.dim() != 4 or f1.shape != f2.shape:
             raise ValueError(f"fmap1/fmap2 must both be (B,C,H,W); got {tuple(fmap1.shape)} and {tuple(fmap2.shape)}")
-        if not (1 <= int(num_levels) <= _cabi.EZB_MAX_LEVELS):
-            raise ValueError(f"num_levels must be in [1, {_cabi.EZB_MAX_LEVELS}]")
+        if int(num_levels) < 1:
+            raise ValueError("num_levels must be >= 1")
         self._state = _PyramidState(f1.detach(), f2.detach(), num_levels, _PYRAMID_DTYPE)
         if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
             self._token = _BuildFn.apply(f1, f2, self._state)
@@ -199,16 +249,11 @@ class MutliScalePairwise4DCorr:
     def corr_pyramid(self):
         """Reference-shaped list of (B*N, 1, h_l, w_l) fp32 tensors (pairwise.py:31-41).
 
-        fp32 storage: zero-copy strided views.  fp16 storage: dequantised copies (diagnostics only)."""
+        The kernels keep the pyramid in a tiled layout, so these are dequantised *copies* gathered on
+        demand (diagnostics / tests); nothing on the lookup path uses them."""
         st = self._state
-        out = []
-        for l in range(st.L):
-            v = st.level_view(l)
-            if st.tdtype == torch.float16:
-                scale = st.deq.repeat_interleave(st.N).view(-1, 1, 1, 1)
-                v = v.float() * scale
-            out.append(v)
-        return out
+        scale = st.deq.repeat_interleave(st.N).view(-1, 1, 1, 1)
+        return [st.level_tensor(l).float() * scale for l in range(st.L)]
 
     def __call__(self, coords):
         c = _cabi.require_cuda_f32(coords, "coords")
@@ -234,4 +279,4 @@ class MutliScalePairwise4DCorr:
         st = _PyramidState(f1.detach(), f2.detach(), 1, "fp32")
         st.build()
         B, _, H, W = f1.shape
-        return st.level_view(0).reshape(B, H, W, 1, H, W)
+        return st.level_tensor(0).reshape(B, H, W, 1, H, W)

@@ -48,22 +48,29 @@ int ezb_last_error(char* buf, size_t n);
  *   replaces MutliScalePairwise4DCorr.__init__ / .corr
  *   ezflow/similarity/correlation/pairwise.py:26-41, :78-88
  *
- * Layout of level l (the library's choice, reported by ezb_corr_pyramid_layout):
- *   element (b, q, y, x) at  lvl_ptr[l] + ((b*N + q) * qstride[l] + y * pitch[l] + x) * elsize
- *   with q = h1*W + w1 the query pixel, (y,x) the target pixel at level l, h[l] = H >> l,
- *   w[l] = W >> l (floor, F.avg_pool2d default), pitch[l] = w[l] rounded up to 16 bytes,
- *   qstride[l] = h[l]*pitch[l].  Stored value * deq_scale[b] = reference value.
+ * Pyramid storage (the library's choice, "warp-strip-major"): ONE buffer per call holding
+ * all levels.  The target image of level l is cut into (8>>l) x (32>>l) tiles on the grid of the 8x32
+ * level-0 patches the GEMM tiles over; queries (q = h1*W + w1) are grouped 32 at a time.  Each
+ * (pair b, patch p, query group g) owns a contiguous *group block* of `group_bytes` at
+ *   ((b * n_patches + p) * n_groups + g) * group_bytes,      p = (y0/8) * n_pw + (x0/32)
+ * and ezb_corr_pyramid_elem_offset() gives the byte offset of an element inside a block.
+ * h[l] = H >> l, w[l] = W >> l (floor, F.avg_pool2d default).  At most 4 levels.
+ * Stored value * deq_scale[b] = reference value.
  * ------------------------------------------------------------------------------------------- */
 int ezb_corr_pyramid_layout(int H, int W, int L, int dtype,
-                            int* h /*[L] host*/, int* w /*[L] host*/, int* pitch /*[L] host*/,
-                            int64_t* qstride /*[L] host*/);
+                            int* h /*[L] host*/, int* w /*[L] host*/, int* n_ph, int* n_pw, int* n_groups,
+                            int64_t* group_bytes, int64_t* pair_bytes /* all host, may be null */);
+
+/* byte offset inside a group block of element (yy, xx) of the level-`level` tile for query `lane`
+ * (0..31) of the group; -1 on bad arguments */
+int64_t ezb_corr_pyramid_elem_offset(int dtype, int level, int lane, int yy, int xx);
 
 /* bytes of scratch ezb_corr_pyramid_fwd needs (fp16 K-major operand copies + scales) */
 int ezb_corr_pyramid_workspace_bytes(int B, int C, int H, int W, size_t* bytes /*host*/);
 
 int ezb_corr_pyramid_fwd(const float* fmap1, const float* fmap2, /* (B,C,H,W) fp32 contiguous */
                          int B, int C, int H, int W, int L, int dtype,
-                         void* const* lvl_ptrs /*[L] host array of device pointers*/,
+                         void* pyramid /* B * pair_bytes, 128-byte aligned, written */,
                          float* deq_scale /*[B] device, written*/,
                          void* workspace, size_t workspace_bytes, void* stream);
 
@@ -71,7 +78,7 @@ int ezb_corr_pyramid_fwd(const float* fmap1, const float* fmap2, /* (B,C,H,W) fp
  * `stream` immediately before and after the tcgen05 GEMM kernel so a caller can time that launch alone
  * (bench.py's roofline leg).  The prep kernels (absmax / convert) run before ev_gemm_start. */
 int ezb_corr_pyramid_fwd_ex(const float* fmap1, const float* fmap2, int B, int C, int H, int W, int L, int dtype,
-                            void* const* lvl_ptrs, float* deq_scale, void* workspace, size_t workspace_bytes,
+                            void* pyramid, float* deq_scale, void* workspace, size_t workspace_bytes,
                             void* stream, void* ev_gemm_start, void* ev_gemm_end);
 
 /* thin cudaEvent helpers so ctypes callers need no second CUDA binding */
@@ -86,12 +93,15 @@ int ezb_event_elapsed_ms(void* ev_start, void* ev_end, float* ms /*host out*/); 
  *   out (B, L*(2r+1)^2, H, W) fp32; channel l*(2r+1)^2 + i*(2r+1) + j samples level l at
  *   (x/2^l + i - r, y/2^l + j - r) -- the slow window index offsets x.
  * ------------------------------------------------------------------------------------------- */
-int ezb_corr_lookup_fwd(const void* const* lvl_ptrs /*[L] host*/, const float* deq_scale /*[B]*/,
+int ezb_corr_lookup_fwd(const void* pyramid, const float* deq_scale /*[B]*/,
                         const float* coords /* (B,2,H,W): ch0 = x, ch1 = y */,
                         int B, int H, int W, int L, int radius, int dtype,
                         float* out, void* stream);
 
-/* dpyr levels are fp32 with the *fp32* layout of ezb_corr_pyramid_layout; accumulated into (+=). */
+/* Gradient levels are separate fp32 buffers, row-major per query with a 16-byte row pitch:
+ * element (b,q,y,x) of level l at ((b*N+q)*h[l] + y)*pitch[l] + x, pitch[l] = w[l] rounded up to 4
+ * (ezb_corr_grad_layout).  The lookup adjoint accumulates into them (+=). */
+int ezb_corr_grad_layout(int H, int W, int L, int* h, int* w, int* pitch, int64_t* qstride /*[L] host*/);
 int ezb_corr_lookup_bwd(const float* dout /* (B, L*(2r+1)^2, H, W) */, const float* coords,
                         int B, int H, int W, int L, int radius,
                         float* const* dlvl_ptrs /*[L] host*/, void* stream);

@@ -22,7 +22,7 @@ def test_exports_match_header(lib):
     from ezflow_b200 import _cabi
 
     text = open(os.path.join(ROOT, "include", "ezflow_b200.h")).read()
-    declared = set(re.findall(r"\bint\s+(ezb_[a-z0-9_]+)\s*\(", text))
+    declared = set(re.findall(r"\b(?:int|int64_t)\s+(ezb_[a-z0-9_]+)\s*\(", text))
     assert declared, "no declarations parsed"
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
@@ -33,24 +33,41 @@ def test_version_and_error_string(lib):
     from ezflow_b200 import _cabi
 
     assert lib.ezb_version() == 100
-    rc = lib.ezb_corr_pyramid_layout(0, 4, 1, 0, None, None, None, None)
+    rc = lib.ezb_corr_pyramid_layout(0, 4, 1, 0, None, None, None, None, None, None, None)
     assert rc == -1 and "bad pyramid shape" in _cabi.last_error()
     with pytest.raises(ValueError):
         _cabi.check(rc)
 
 
 def test_pyramid_layout(lib):
-    from ezflow_b200.similarity.pairwise import pyramid_layout
+    from ezflow_b200 import _cabi
+    from ezflow_b200.similarity.pairwise import PyramidLayout, grad_layout
 
     # 1080p: floor pooling 135x240 -> 67x120 -> 33x60 -> 16x30
-    lay = pyramid_layout(135, 240, 4, 1)
-    assert [(h, w) for h, w, _, _ in lay] == [(135, 240), (67, 120), (33, 60), (16, 30)]
-    assert [p for _, _, p, _ in lay] == [240, 120, 64, 32]  # fp16 pitch: multiples of 8 elements
-    assert all(qs == h * p for h, _, p, qs in lay)
-    lay32 = pyramid_layout(46, 62, 4, 0)
-    assert [(h, w, p) for h, w, p, _ in lay32] == [(46, 62, 64), (23, 31, 32), (11, 15, 16), (5, 7, 8)]
+    lay = PyramidLayout(135, 240, 4, _cabi.EZB_F16)
+    assert lay.levels == [(135, 240), (67, 120), (33, 60), (16, 30)]
+    assert (lay.n_ph, lay.n_pw, lay.n_groups) == (17, 8, 1013)
+    assert lay.group_bytes == 22528 and lay.pair_bytes == 17 * 8 * 1013 * 22528
+    lay32 = PyramidLayout(46, 62, 4, _cabi.EZB_F32)
+    assert lay32.group_bytes == 45056 and (lay32.n_ph, lay32.n_pw, lay32.n_groups) == (6, 2, 90)
     with pytest.raises(ValueError):
-        pyramid_layout(4, 4, 4, 0)  # level 3 would be empty
+        PyramidLayout(4, 4, 4, 0)  # level 3 would be empty
+    with pytest.raises(NotImplementedError):
+        PyramidLayout(64, 64, 5, 0)
+    # every element of every level maps to a distinct, in-range, element-aligned offset of the block
+    for dt, es, gb in ((_cabi.EZB_F16, 2, 22528), (_cabi.EZB_F32, 4, 45056)):
+        seen = set()
+        for l in range(4):
+            for lane in range(32):
+                for yy in range(8 >> l):
+                    for xx in range(32 >> l):
+                        off = lib.ezb_corr_pyramid_elem_offset(dt, l, lane, yy, xx)
+                        assert 0 <= off < gb and off % es == 0 and off not in seen
+                        seen.add(off)
+        assert len(seen) == 32 * (256 + 64 + 16 + 4)
+    assert lib.ezb_corr_pyramid_elem_offset(1, 1, 0, 4, 0) == -1
+    g = grad_layout(46, 62, 4)
+    assert [(h, w, p) for h, w, p, _ in g] == [(46, 62, 64), (23, 31, 32), (11, 15, 16), (5, 7, 8)]
 
 
 def test_argument_validation_without_gpu(lib):
@@ -70,7 +87,7 @@ def test_argument_validation_without_gpu(lib):
 
 
 def test_sass_is_blackwell_native():
-    """The GEMM must be tcgen05 + TMA (SASS: UTCHMMA / LDTM / UTMALDG / UTMASTG), not mma.sync."""
+    """The GEMM must be tcgen05 + TMA (SASS: UTCHMMA / LDTM / UTMALDG / UBLKCP bulk stores), not mma.sync."""
     import shutil
     import subprocess
 
@@ -80,6 +97,6 @@ def test_sass_is_blackwell_native():
     if not os.path.exists(cuobjdump):
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([cuobjdump, "-sass", build.LIBPATH], capture_output=True, text=True).stdout
-    for mnem in ("UTCHMMA", "LDTM", "UTMALDG", "UTMASTG"):
+    for mnem in ("UTCHMMA", "LDTM", "UTMALDG", "UBLKCP"):
         assert mnem in sass, f"{mnem} missing from SASS"
     assert "HMMA." not in sass.replace("UTCHMMA", "")
