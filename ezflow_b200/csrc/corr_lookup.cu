@@ -25,7 +25,7 @@ constexpr int MAX_RADIUS = 8;
 
 struct LookupParams {
   const char* pyr;      // warp-strip-major pyramid (ezb_common.cuh)
-  int h[PYR_MAX_LEVELS], w[PYR_MAX_LEVELS];
+  int H, W;             // level l is (H >> l) x (W >> l)
   int n_pw, n_patches, n_groups;
   long long group_bytes;
   const float* deq;     // [B]
@@ -43,88 +43,113 @@ __device__ __forceinline__ int float_floor_to_int_clamped(float v, int lo, int h
 
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+  asm("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                : "l"(p));
   return r;
 }
 __device__ __forceinline__ uint2 ldg_nc_v2(const void* p) {
   uint2 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  asm("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
   return r;
 }
 
-template <typename T>
-__device__ __forceinline__ float word_elem(const uint32_t (&wd)[4], int j);
-template <>
-__device__ __forceinline__ float word_elem<__half>(const uint32_t (&wd)[4], int j) {
-  const uint32_t u = wd[j >> 1];
-  const __half_raw hr = {(unsigned short)((j & 1) ? (u >> 16) : (u & 0xffff))};
-  return __half2float(__half(hr));
-}
-template <>
-__device__ __forceinline__ float word_elem<float>(const uint32_t (&wd)[4], int j) {
-  return __uint_as_float(wd[j]);
+// shared-memory patch geometry, in 32-bit words: a patch row holds the `ng` aligned 16-byte (or 8-byte)
+// groups that cover its (2r+2) taps, copied verbatim in storage dtype; the taps start `off` elements in.
+struct PatchGeom {
+  int gw_log, ng, row_words, lvl_off;
+};
+template <int ES>
+__device__ __forceinline__ PatchGeom patch_geom(int l, int D) {
+  constexpr int EPC = 16 / ES;
+  PatchGeom g;
+  int off = 0;
+  for (int k = 0;; ++k) {
+    const int GW = min(EPC, 32 >> k);
+    g.gw_log = (GW == 8) ? 3 : 2;
+    g.ng = (GW - 1 + D + GW - 1) >> g.gw_log;
+    g.row_words = (g.ng << g.gw_log) * ES / 4;
+    g.lvl_off = off;
+    if (k == l) break;
+    off += D * g.row_words;
+  }
+  return g;
 }
 
 template <typename T>
-__global__ void __launch_bounds__(NTHREADS) corr_lookup_fwd_kernel(const LookupParams P) {
-  extern __shared__ float patches[];  // [QB][pstride]
+__global__ void __launch_bounds__(NTHREADS) corr_lookup_fwd_kernel(const LookupParams P, const int qstride_words) {
+  extern __shared__ uint32_t sm_words[];  // [QB][qstride_words] patches, then [L*QB] int2 item parameters
   constexpr int ES = (int)sizeof(T);
-  constexpr int EPC = 16 / ES;  // elements per 16-byte chunk
-  const int r = P.r, D = 2 * r + 2, DD = D * D, K = 2 * r + 1, KK = K * K;
-  const int pstride = (P.L * DD) | 1;
+  const int r = P.r, D = 2 * r + 2, K = 2 * r + 1, KK = K * K;
   const int b = blockIdx.y, grp = blockIdx.x, q0 = grp * QB;  // QB == PYR_QG: a block serves one query group
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float deq = __ldg(P.deq + b);
   const float* cx_ptr = P.coords + (long long)b * 2 * P.N;
   const float* cy_ptr = cx_ptr + P.N;
   const char* pair_base = P.pyr + (long long)b * P.n_patches * P.n_groups * P.group_bytes + (long long)grp * P.group_bytes;
   const long long patch_stride = (long long)P.n_groups * P.group_bytes;
+  int2* items = reinterpret_cast<int2*>(sm_words + QB * qstride_words);
 
-  // ---------------- phase 1: gather patches ----------------
-  // item = (level, query).  A patch row is fetched as aligned groups of GW consecutive x (one 16-byte
-  // chunk, or the 4-wide level-3 tile row); a group never straddles a tile because tile widths are
-  // multiples of GW.  task = (row, group); up to 30 lanes fetch a whole (2r+2)^2 patch per instruction.
-  for (int item = warp; item < QB * P.L; item += NTHREADS / 32) {
-    const int l = item / QB, ql = item - l * QB, q = q0 + ql;
-    if (q >= P.N) continue;
-    const int tw_log = 5 - l, th_log = 3 - l;              // tile (8>>l) x (32>>l)
-    const int GW = min(EPC, 1 << tw_log);
-    const int gw_log = (GW == 8) ? 3 : 2;
-    const int ng = (GW - 1 + D + GW - 1) >> gw_log;        // groups covering D elements at any misalignment
-    const int tasks = D * ng;
+  // ---------------- phase 0: per (level, query) patch origin, computed once ----------------
+  for (int it = threadIdx.x; it < QB * P.L; it += NTHREADS) {
+    const int l = it / QB, ql = it - l * QB, q = min(q0 + ql, P.N - 1);
     const float inv = 1.0f / (float)(1 << l);
-    const int hl = P.h[l], wl = P.w[l];
     const int x0 = float_floor_to_int_clamped(__ldg(cx_ptr + q) * inv, -(1 << 24), 1 << 24);
     const int y0 = float_floor_to_int_clamped(__ldg(cy_ptr + q) * inv, -(1 << 24), 1 << 24);
-    const int xs = max(-D, min(wl, x0 - r));  // first patch column / row (clamped: fully-outside stays fully outside)
-    const int ys = max(-D, min(hl, y0 - r));
-    const int g0 = (xs + 64) >> gw_log;       // floor(xs / GW) + 64/GW   (xs >= -D >= -18)
-    float* dst = patches + ql * pstride + l * DD;
-    for (int t = lane; t < tasks; t += 32) {
-      const int row = t / ng, gi = t - row * ng;
-      const int yy_abs = ys + row;
-      const int xg = ((g0 + gi) << gw_log) - 64;  // first x of this group
-      const bool ok = (yy_abs >= 0) && (yy_abs < hl) && (xg + GW > 0) && (xg < wl);
-      uint32_t wd[4] = {0u, 0u, 0u, 0u};
-      if (ok && xg >= 0) {
-        const int ph = yy_abs >> th_log, yy = yy_abs & ((1 << th_log) - 1);
-        const int pw = xg >> tw_log, xx = xg & ((1 << tw_log) - 1);
-        const char* src = pair_base + (long long)(ph * P.n_pw + pw) * patch_stride + pyr_elem_offset(ES, l, ql, yy, xx);
-        if (GW * ES == 16) {
-          const uint4 v = ldg_nc_v4(src);
-          wd[0] = v.x; wd[1] = v.y; wd[2] = v.z; wd[3] = v.w;
-        } else {  // fp16 level 3: 4 halfs = 8 bytes
-          const uint2 v = ldg_nc_v2(src);
-          wd[0] = v.x; wd[1] = v.y;
+    // clamped so that a window entirely outside the level stays entirely outside
+    items[it] = make_int2(max(-D, min(P.W >> l, x0 - r)), max(-D, min(P.H >> l, y0 - r)));
+  }
+  __syncthreads();
+
+  // ---------------- phase 1: gather patches ----------------
+  // task = (patch row, aligned group of GW elements); a round = 32 tasks of one (level, query).  Up to 30
+  // lanes fetch a whole (2r+2)^2 fp16 patch with one 16-byte load each and copy it verbatim to shared
+  // memory.  Per (level, round) sweep every warp serves 4 queries and keeps their 4 loads in flight.
+  // Everything outside a level's valid area is stored as zero by the GEMM epilogue, and groups outside
+  // the level are written as zeros here, so no per-element masking is needed.
+  for (int l = 0; l < P.L; ++l) {
+    const PatchGeom g = patch_geom<ES>(l, D);
+    const int GW = 1 << g.gw_log, tasks = D * g.ng, rounds = (tasks + 31) >> 5;
+    const int tw_log = 5 - l, th_log = 3 - l;  // tile (8>>l) x (32>>l)
+    const int hl = P.H >> l, wl = P.W >> l;
+    const bool wide = (GW * ES == 16);         // 16-byte groups; otherwise 8 bytes (fp16 level 3)
+    for (int rnd = 0; rnd < rounds; ++rnd) {
+      const int t = rnd * 32 + lane;
+      const int row = (g.ng == 3) ? (t * 43) >> 7 : (g.ng == 4) ? t >> 2 : t / g.ng;
+      const int gi = t - row * g.ng;
+      uint32_t wd[4][4];
+      uint32_t* dst[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ql = warp * 4 + i;  // NTHREADS/32 warps x 4 = QB queries
+        dst[i] = nullptr;
+        wd[i][0] = wd[i][1] = wd[i][2] = wd[i][3] = 0u;
+        if (t < tasks && q0 + ql < P.N) {
+          const int2 org = items[l * QB + ql];
+          const int yy_abs = org.y + row;
+          const int xg = ((((org.x + 64) >> g.gw_log) + gi) << g.gw_log) - 64;  // first x of the group (aligned to GW)
+          dst[i] = sm_words + ql * qstride_words + g.lvl_off + row * g.row_words + gi * (GW * ES / 4);
+          if (yy_abs >= 0 && yy_abs < hl && xg >= 0 && xg < wl) {
+            const int ph = yy_abs >> th_log, yy = yy_abs & ((1 << th_log) - 1);
+            const int pw = xg >> tw_log, xx = xg & ((1 << tw_log) - 1);
+            const char* src = pair_base + (long long)(ph * P.n_pw + pw) * patch_stride + pyr_elem_offset(ES, l, ql, yy, xx);
+            if (wide) {
+              const uint4 v = ldg_nc_v4(src);
+              wd[i][0] = v.x; wd[i][1] = v.y; wd[i][2] = v.z; wd[i][3] = v.w;
+            } else {
+              const uint2 v = ldg_nc_v2(src);
+              wd[i][0] = v.x; wd[i][1] = v.y;
+            }
+          }
         }
       }
 #pragma unroll
-      for (int j = 0; j < EPC; ++j) {
-        if (j < GW) {
-          const int xa = xg + j, xr = xa - xs;
-          if (xr >= 0 && xr < D) dst[row * D + xr] = (ok && xa >= 0 && xa < wl) ? word_elem<T>(wd, j) * deq : 0.f;
+      for (int i = 0; i < 4; ++i) {
+        if (dst[i] == nullptr) continue;
+        dst[i][0] = wd[i][0];
+        dst[i][1] = wd[i][1];
+        if (wide) {
+          dst[i][2] = wd[i][2];
+          dst[i][3] = wd[i][3];
         }
       }
     }
@@ -132,23 +157,31 @@ __global__ void __launch_bounds__(NTHREADS) corr_lookup_fwd_kernel(const LookupP
   __syncthreads();
 
   // ---------------- phase 2: bilinear taps, lane = query ----------------
+  // work item = (level, i): the 2r+1 outputs with x-offset i, walked down the window so each new output
+  // needs two fresh taps (the upper pair is the previous lower pair).  Stores are 128 contiguous bytes.
   const int q = q0 + lane;
   if (q >= P.N) return;
+  const float deq = __ldg(P.deq + b);
   const float x = __ldg(cx_ptr + q), y = __ldg(cy_ptr + q);
-  const float* mine = patches + lane * pstride;
   float* out = P.out + (long long)b * P.L * KK * P.N + q;
-  for (int l = 0; l < P.L; ++l) {
+  for (int item = warp; item < P.L * K; item += NTHREADS / 32) {
+    const int l = item / K, i = item - l * K;  // i offsets x (slow output index!), j offsets y   pairwise.py:53-61
+    const PatchGeom g = patch_geom<ES>(l, D);
     const float inv = 1.0f / (float)(1 << l);
     const float cx = x * inv, cy = y * inv;
     const float fx = cx - floorf(cx), fy = cy - floorf(cy);
     // a clamped patch origin means the window is entirely outside: the patch is all zeros, weights moot
-    const float w00 = (1.f - fx) * (1.f - fy), w01 = fx * (1.f - fy), w10 = (1.f - fx) * fy, w11 = fx * fy;
-    const float* pl = mine + l * DD;
-    for (int k = warp; k < KK; k += NTHREADS / 32) {
-      const int i = k / K, j = k - i * K;  // i offsets x (slow index!), j offsets y   pairwise.py:53-61
-      const float* p = pl + j * D + i;
-      const float v = w00 * p[0] + w01 * p[1] + w10 * p[D] + w11 * p[D + 1];
-      out[(long long)(l * KK + k) * P.N] = v;
+    const float wl0 = deq * (1.f - fx), wl1 = deq * fx;
+    const int off = (items[l * QB + lane].x + 64) & ((1 << g.gw_log) - 1);  // taps start `off` elements into the row
+    const int row_el = g.row_words * 4 / ES;
+    const T* p = reinterpret_cast<const T*>(sm_words + lane * qstride_words + g.lvl_off) + off + i;
+    float* o = out + (long long)(l * KK + i * K) * P.N;
+    float top = wl0 * (float)p[0] + wl1 * (float)p[1];  // horizontal lerp of row j
+    for (int j = 0; j < K; ++j) {
+      p += row_el;
+      const float bot = wl0 * (float)p[0] + wl1 * (float)p[1];
+      o[(long long)j * P.N] = top + fy * (bot - top);
+      top = bot;
     }
   }
 }
@@ -244,10 +277,8 @@ extern "C" int ezb_corr_lookup_fwd(const void* pyramid, const float* deq_scale, 
   EZB_REQUIRE((reinterpret_cast<uintptr_t>(pyramid) & 127) == 0, "pyramid buffer must be 128-byte aligned");
   k3::LookupParams P;
   const int N = H * W;
-  for (int l = 0; l < L; ++l) {
-    P.h[l] = H >> l;
-    P.w[l] = W >> l;
-  }
+  P.H = H;
+  P.W = W;
   P.pyr = static_cast<const char*>(pyramid);
   P.n_pw = lay.n_pw;
   P.n_patches = lay.n_patches;
@@ -260,18 +291,25 @@ extern "C" int ezb_corr_lookup_fwd(const void* pyramid, const float* deq_scale, 
   P.N = N;
   P.L = L;
   P.r = radius;
-  const int D = 2 * radius + 2;
-  const size_t smem = (size_t)k3::QB * ((L * D * D) | 1) * sizeof(float);
+  const int D = 2 * radius + 2, es = lay.es, epc = 16 / es;
+  int qwords = 0;  // per-query patch words over all levels (must match patch_geom in the kernel)
+  for (int l = 0; l < L; ++l) {
+    const int GW = std::min(epc, 32 >> l);
+    const int ng = (GW - 1 + D + GW - 1) / GW;
+    qwords += D * ng * GW * es / 4;
+  }
+  qwords |= 1;  // odd stride: lane = query reads are bank-conflict free
+  const size_t smem = (size_t)k3::QB * qwords * 4 + (size_t)L * k3::QB * sizeof(int2);
   if (smem > 200 * 1024) return fail(EZB_ERR_UNSUPPORTED, "lookup window too large (L=%d, r=%d)", L, radius);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static_assert(k3::QB == PYR_QG, "one lookup block per pyramid query group");
   dim3 grid(lay.n_groups, B);
   if (dtype == EZB_F16) {
     EZB_CUDA_OK(cudaFuncSetAttribute(k3::corr_lookup_fwd_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k3::corr_lookup_fwd_kernel<__half><<<grid, k3::NTHREADS, smem, st>>>(P);
+    k3::corr_lookup_fwd_kernel<__half><<<grid, k3::NTHREADS, smem, st>>>(P, qwords);
   } else {
     EZB_CUDA_OK(cudaFuncSetAttribute(k3::corr_lookup_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k3::corr_lookup_fwd_kernel<float><<<grid, k3::NTHREADS, smem, st>>>(P);
+    k3::corr_lookup_fwd_kernel<float><<<grid, k3::NTHREADS, smem, st>>>(P, qwords);
   }
   EZB_LAUNCH_OK();
   return EZB_OK;

@@ -30,16 +30,17 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_KB_BYTES = BN * BK * 2;      // 32 KB
 constexpr int SLOT_BYTES = 4096;             // one staged section: 32 queries x 128 B
 constexpr int SLOTS_PER_WARP = 2;
-constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARPS = 4;          // one warp per TMEM lane quadrant
+constexpr int NUM_THREADS = 128 + EPI_WARPS * 32;
 constexpr int SMEM_B = 0;
 constexpr int SMEM_A = SMEM_B + KB_MAX * B_KB_BYTES;
 constexpr int SMEM_STG = SMEM_A + STAGES * A_STAGE_BYTES;
-constexpr int SMEM_BAR = SMEM_STG + 4 * SLOTS_PER_WARP * SLOT_BYTES;
+constexpr int SMEM_BAR = SMEM_STG + EPI_WARPS * SLOTS_PER_WARP * SLOT_BYTES;
 constexpr int SMEM_BYTES = SMEM_BAR + 256 + 1024;  // + barrier block + alignment slack
 constexpr int TMEM_COLS = 512;                     // two 256-column accumulators
 
 struct GemmParams {
-  int B, N, KB, L;
+  int B, N, H, W, KB, L;
   int n_pw, n_patches, n_qblocks, n_groups;
   long long total_tiles, group_bytes;
   const float* epi_scale;  // [B]
@@ -140,28 +141,33 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ void bulk_store(void* gdst, uint32_t src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(src_smem), "r"(bytes)
-               : "memory");
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+  return r;
+}
+__device__ __forceinline__ void st_global_stream_v4(void* p, const uint4& v) {
+  // .cs: streaming / evict-first — the pyramid is written once and must not evict the GEMM operands from L2
+  asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// One section of a group block (32 lines, one per lane, NWORDS*4 bytes each): every lane writes its line
-// into the staging slot with the layout's XOR chunk swizzle (bank-conflict free), then lane 0 issues ONE
-// contiguous bulk copy shared -> global for the whole section (4 KB / 2 KB).
+// One section of a group block (32 lines, one per lane, NWORDS*4 bytes each).  Every lane writes its own
+// line into the warp's staging slot with the layout's XOR chunk swizzle (bank-conflict free); the slot
+// is then byte-identical to the section in global memory, and the warp streams it out with fully
+// coalesced 16-byte stores: each store instruction writes 512 contiguous bytes.
 template <int NWORDS>
 __device__ __forceinline__ void staged_section_store(uint32_t slot, int lane, const uint32_t (&w)[NWORDS], char* gdst) {
   static_assert(NWORDS == 32 || NWORDS == 16, "lines are 128 or 64 bytes");
   constexpr uint32_t kSwz = NWORDS / 4 - 1;
-  if (lane == 0) ptx::tma_wait_group_read<SLOTS_PER_WARP - 1>();  // the slot written two stores ago is free
-  __syncwarp();
+  __syncwarp();  // the previous section's read-back of this slot is complete in every lane
 #pragma unroll
   for (int c = 0; c < NWORDS / 4; ++c)
     st_shared_v4(slot + lane * (NWORDS * 4) + ((c ^ (lane & kSwz)) << 4), w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
-  ptx::fence_proxy_async_smem();
   __syncwarp();
-  if (lane == 0) {
-    bulk_store(gdst, slot, 32 * NWORDS * 4);
-    ptx::tma_commit_group();
+#pragma unroll
+  for (int c = 0; c < NWORDS / 4; ++c) {
+    const uint4 v = ld_shared_v4(slot + c * 512 + lane * 16);
+    st_global_stream_v4(gdst + c * 512 + lane * 16, v);
   }
 }
 
@@ -170,7 +176,11 @@ __device__ __forceinline__ void staged_section_store(uint32_t slot, int lane, co
 // from level 1, all from the fp32 accumulators (the reference pools fp32 values too).
 template <typename OutT>
 __device__ __forceinline__ void epilogue_tile(uint32_t t_base, uint32_t stg_base, uint32_t& slot_ctr, int lane,
-                                              float scale, uint32_t tmem_empty_bar, int L, char* gblock) {
+                                              float scale, uint32_t tmem_empty_bar, int L, char* gblock, int vr1,
+                                              int vc1) {
+  // vr1 / vc1: number of valid level-1 rows / columns in this tile (4 / 16 for interior tiles).  Level-0
+  // values outside the image are exact zeros (TMA zero-fills the f2 patch); pooled values outside their
+  // level are forced to zero here so the lookup never needs per-element masking.
   constexpr bool kHalf = sizeof(OutT) == 2;
   auto next_slot = [&]() { return stg_base + (slot_ctr++ & (SLOTS_PER_WARP - 1)) * SLOT_BYTES; };
   float l1[4][16];
@@ -193,7 +203,8 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_base, uint32_t stg_base
       v1[j] = __uint_as_float(r1[j]) * scale;
     }
 #pragma unroll
-    for (int j = 0; j < 16; ++j) l1[s][j] = 0.25f * ((v0[2 * j] + v0[2 * j + 1]) + (v1[2 * j] + v1[2 * j + 1]));
+    for (int j = 0; j < 16; ++j)
+      l1[s][j] = (s < vr1 && j < vc1) ? 0.25f * ((v0[2 * j] + v0[2 * j + 1]) + (v1[2 * j] + v1[2 * j + 1])) : 0.f;
 
     if constexpr (kHalf) {
       uint32_t w[32];  // line = [row 2s: 32 halfs][row 2s+1: 32 halfs]        (section s)
@@ -236,9 +247,12 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_base, uint32_t stg_base
   for (int r = 0; r < 2; ++r)
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      l2[r][j] = 0.25f * ((l1[2 * r][2 * j] + l1[2 * r][2 * j + 1]) + (l1[2 * r + 1][2 * j] + l1[2 * r + 1][2 * j + 1]));
+      l2[r][j] = (r < (vr1 >> 1) && j < (vc1 >> 1))
+                     ? 0.25f * ((l1[2 * r][2 * j] + l1[2 * r][2 * j + 1]) + (l1[2 * r + 1][2 * j] + l1[2 * r + 1][2 * j + 1]))
+                     : 0.f;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) l3[j] = 0.25f * ((l2[0][2 * j] + l2[0][2 * j + 1]) + (l2[1][2 * j] + l2[1][2 * j + 1]));
+  for (int j = 0; j < 4; ++j)
+    l3[j] = ((vr1 >> 2) > 0 && j < (vc1 >> 2)) ? 0.25f * ((l2[0][2 * j] + l2[0][2 * j + 1]) + (l2[1][2 * j] + l2[1][2 * j + 1])) : 0.f;
   if constexpr (kHalf) {
     uint32_t w[16];  // [level 2: 2 x 8 halfs = 32 B][level 3: 4 halfs = 8 B][pad]   (section 5, 64-byte lines)
 #pragma unroll
@@ -309,33 +323,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_slot;
 
-  // contiguous, balanced range of tiles for this CTA; tile t -> (bp = t / n_qblocks, qb = t % n_qblocks)
-  const long long t_begin = p.total_tiles * blockIdx.x / gridDim.x;
-  const long long t_end = p.total_tiles * (blockIdx.x + 1) / gridDim.x;
+  // Pairs are processed one after the other by the whole grid (so the L2 working set is ONE pair's
+  // operands); within a pair every CTA owns a contiguous, balanced range of tiles.
+  // tile t of pair b -> (patch = t / n_qblocks, qb = t % n_qblocks), bp = b * n_patches + patch.
+  const long long tiles_per_pair = (long long)p.n_patches * p.n_qblocks;
+  const long long t_begin = tiles_per_pair * blockIdx.x / gridDim.x;
+  const long long t_end = tiles_per_pair * (blockIdx.x + 1) / gridDim.x;
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
     uint32_t stage = 0, phase = 0, uphase = 0;
     long long cur_bp = -1;
+    for (int b = 0; b < p.B; ++b)
     for (long long t = t_begin; t < t_end; ++t) {
-      const long long bp = t / p.n_qblocks;
-      const int qb = (int)(t - bp * p.n_qblocks);
-      const int b = (int)(bp / p.n_patches);
+      const int patch = (int)(t / p.n_qblocks);
+      const int qb = (int)(t - (long long)patch * p.n_qblocks);
+      const long long bp = (long long)b * p.n_patches + patch;
       if (bp != cur_bp) {
-        const int patch = (int)(bp - (long long)b * p.n_patches);
         const int ph = patch / p.n_pw, pw = patch - ph * p.n_pw;
         if (cur_bp >= 0) {  // all MMAs reading the previous patch have completed
           ptx::mbar_wait(b_empty, uphase);
           uphase ^= 1;
         }
         ptx::mbar_expect_tx(b_full, (uint32_t)(p.KB * B_KB_BYTES));
-        for (int kb = 0; kb < p.KB; ++kb) ptx::tma_load_4d(sB + kb * B_KB_BYTES, &tmB, b_full, kb * BK, pw * PW, ph * PH, b);
+        for (int kb = 0; kb < p.KB; ++kb)
+          ptx::tma_load_4d_hint(sB + kb * B_KB_BYTES, &tmB, b_full, kb * BK, pw * PW, ph * PH, b, ptx::kEvictLast);
         cur_bp = bp;
       }
       for (int kb = 0; kb < p.KB; ++kb) {
         ptx::mbar_wait(empty_bar(stage), phase ^ 1);
         ptx::mbar_expect_tx(full_bar(stage), A_STAGE_BYTES);
-        ptx::tma_load_3d(sA + stage * A_STAGE_BYTES, &tmA, full_bar(stage), kb * BK, qb * BM, b);
+        // fmap1 is re-read by every patch sweep (136x at 1080p): pin it in L2
+        ptx::tma_load_3d_hint(sA + stage * A_STAGE_BYTES, &tmA, full_bar(stage), kb * BK, qb * BM, b, ptx::kEvictLast);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -344,8 +363,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     constexpr uint32_t idesc = ptx::umma_idesc(/*f16*/ 0, BM, BN);
     uint32_t stage = 0, phase = 0, uphase = 0, tile = 0;
     long long cur_bp = -1;
+    for (int b = 0; b < p.B; ++b)
     for (long long t = t_begin; t < t_end; ++t, ++tile) {
-      const long long bp = t / p.n_qblocks;
+      const long long bp = (long long)b * p.n_patches + t / p.n_qblocks;
       if (bp != cur_bp) {
         if (cur_bp >= 0) ptx::umma_commit(b_empty);
         ptx::mbar_wait(b_full, uphase);
@@ -371,17 +391,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-    const uint32_t stg_base = sStg + quad * (SLOTS_PER_WARP * SLOT_BYTES);
+    const int quad = warp & 3;             // TMEM lane quadrant this warp may access
+    const uint32_t stg_base = sStg + (warp - 4) * (SLOTS_PER_WARP * SLOT_BYTES);
     uint32_t slot_ctr = 0, tile = 0;
     long long cur_bp = -1;
     char* patch_base = nullptr;
     float scale = 1.f;
+    int vr1 = 4, vc1 = 16;
+    for (int b = 0; b < p.B; ++b)
     for (long long t = t_begin; t < t_end; ++t, ++tile) {
-      const long long bp = t / p.n_qblocks;
-      const int qb = (int)(t - bp * p.n_qblocks);
+      const int patch = (int)(t / p.n_qblocks);
+      const int qb = (int)(t - (long long)patch * p.n_qblocks);
+      const long long bp = (long long)b * p.n_patches + patch;
       if (bp != cur_bp) {
-        const int b = (int)(bp / p.n_patches);
+        const int ph = patch / p.n_pw, pw = patch - ph * p.n_pw;
+        vr1 = max(0, min(PH / 2, (p.H >> 1) - ph * (PH / 2)));  // valid level-1 rows / cols of this patch
+        vc1 = max(0, min(PW / 2, (p.W >> 1) - pw * (PW / 2)));
         scale = __ldg(p.epi_scale + b);
         patch_base = p.pyr + bp * p.n_groups * p.group_bytes;  // blocks are ordered [pair][patch][group]
         cur_bp = bp;
@@ -392,9 +417,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       const uint32_t t_base = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
       const int grp = qb * (BM / 32) + quad;  // query group of this warp
       epilogue_tile<OutT>(t_base, stg_base, slot_ctr, lane, scale, tmem_empty(acc), p.L,
-                          grp < p.n_groups ? patch_base + (long long)grp * p.group_bytes : nullptr);
+                          grp < p.n_groups ? patch_base + (long long)grp * p.group_bytes : nullptr, vr1, vc1);
     }
-    if (lane == 0) ptx::tma_wait_group<0>();  // all bulk stores done before smem goes away
   }
 
   ptx::tc_fence_before();
@@ -481,6 +505,8 @@ static int launch_gemm(const Workspace& ws, int B, int C, const PyrLayout& lay, 
   GemmParams p;
   p.B = B;
   p.N = N;
+  p.H = H;
+  p.W = W;
   p.KB = Cp / BK;
   p.L = lay.L;
   p.n_pw = lay.n_pw;
@@ -495,7 +521,7 @@ static int launch_gemm(const Workspace& ws, int B, int C, const PyrLayout& lay, 
   auto kern = corr_pyramid_gemm_kernel<OutT>;
   EZB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   long long grid = num_sms();
-  if (grid > p.total_tiles) grid = p.total_tiles;
+  if (grid > p.total_tiles / B) grid = p.total_tiles / B;  // tiles of one pair
   if (ev0) EZB_CUDA_OK(cudaEventRecord(ev0, st));
   kern<<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, p);
   EZB_LAUNCH_OK();
