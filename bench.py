@@ -410,7 +410,7 @@ def run_b200(args):
                 "gemm_share_of_step": (sum(gemm_ms) / ms) if ms > 0 else None,
             },
             "clocks": clocks,
-            "gpu_launches": args.steps * (P // MB) * (4 + ITERS),
+            "gpu_launches": args.steps * (P // MB) * (4 + (L - 1) + 1 + ITERS),  # absmax, scales, convert, pools, pack, gemm + lookups
         }
         if e2e:
             line["e2e"] = {

@@ -30,9 +30,10 @@ _SIGNATURES = {
         [c_int, c_int, c_int, c_int, _P(c_int), _P(c_int), _P(c_int), _P(c_int), _P(c_int), _P(c_i64), _P(c_i64)],
         c_int,
     ),
-    "ezb_corr_pyramid_elem_offset": ([c_int, c_int, c_int, c_int, c_int], c_i64),
+    "ezb_corr_pyramid_level_map": ([c_int, c_int, c_int, c_int, _P(ctypes.c_int32), _P(ctypes.c_int32)], c_int),
+    "ezb_corr_pyramid_record_offset": ([c_int, c_int, c_int], c_i64),
     "ezb_corr_grad_layout": ([c_int, c_int, c_int, _P(c_int), _P(c_int), _P(c_int), _P(c_i64)], c_int),
-    "ezb_corr_pyramid_workspace_bytes": ([c_int, c_int, c_int, c_int, _P(c_sz)], c_int),
+    "ezb_corr_pyramid_workspace_bytes": ([c_int, c_int, c_int, c_int, c_int, _P(c_sz)], c_int),
     "ezb_corr_pyramid_fwd": ([c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_sz, c_vp], c_int),
     "ezb_corr_pyramid_fwd_ex": (
         [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_sz, c_vp, c_vp, c_vp],

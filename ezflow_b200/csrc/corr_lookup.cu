@@ -24,9 +24,10 @@ constexpr int NTHREADS = 256;
 constexpr int MAX_RADIUS = 8;
 
 struct LookupParams {
-  const char* pyr;      // warp-strip-major pyramid (ezb_common.cuh)
+  const char* pyr;      // subtile-sequence pyramid (ezb_common.cuh)
   int H, W;             // level l is (H >> l) x (W >> l)
-  int n_pw, n_patches, n_groups;
+  int sw[PYR_MAX_LEVELS], sub_base[PYR_MAX_LEVELS];
+  int n_tiles, n_groups;
   long long group_bytes;
   const float* deq;     // [B]
   const float* coords;  // (B,2,N)
@@ -48,33 +49,18 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
                : "l"(p));
   return r;
 }
-__device__ __forceinline__ uint2 ldg_nc_v2(const void* p) {
-  uint2 r;
-  asm("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
-  return r;
-}
+__device__ __forceinline__ int div3(int v) { return (v * 43691) >> 17; }  // exact for 0 <= v < 98304
 
-// shared-memory patch geometry, in 32-bit words: a patch row holds the `ng` aligned 16-byte (or 8-byte)
-// groups that cover its (2r+2) taps, copied verbatim in storage dtype; the taps start `off` elements in.
-struct PatchGeom {
-  int gw_log, ng, row_words, lvl_off;
-};
+// Gather geometry.  A window row is fetched as `ng` aligned 16-byte chunks (VW = 8 fp16 / 4 fp32 pixels of
+// one subtile row); in shared memory a row keeps the ng*VW fetched pixels verbatim (storage dtype) and
+// the (2r+2) taps start `off` = xs mod VW pixels in.
 template <int ES>
-__device__ __forceinline__ PatchGeom patch_geom(int l, int D) {
-  constexpr int EPC = 16 / ES;
-  PatchGeom g;
-  int off = 0;
-  for (int k = 0;; ++k) {
-    const int GW = min(EPC, 32 >> k);
-    g.gw_log = (GW == 8) ? 3 : 2;
-    g.ng = (GW - 1 + D + GW - 1) >> g.gw_log;
-    g.row_words = (g.ng << g.gw_log) * ES / 4;
-    g.lvl_off = off;
-    if (k == l) break;
-    off += D * g.row_words;
-  }
-  return g;
-}
+struct Gather {
+  static constexpr int VW = 16 / ES, VW_LOG = (ES == 2) ? 3 : 2;
+  __host__ __device__ static constexpr int ng(int D) { return (VW - 1 + D + VW - 1) / VW; }
+  __host__ __device__ static constexpr int row_el(int D) { return ng(D) * VW; }
+  __device__ static __forceinline__ int chunk_floor(int xs) { return ((xs + 64) >> VW_LOG) - (64 >> VW_LOG); }  // xs >= -64
+};
 
 template <typename T>
 __global__ void __launch_bounds__(NTHREADS) corr_lookup_fwd_kernel(const LookupParams P, const int qstride_words) {
@@ -85,8 +71,8 @@ __global__ void __launch_bounds__(NTHREADS) corr_lookup_fwd_kernel(const LookupP
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* cx_ptr = P.coords + (long long)b * 2 * P.N;
   const float* cy_ptr = cx_ptr + P.N;
-  const char* pair_base = P.pyr + (long long)b * P.n_patches * P.n_groups * P.group_bytes + (long long)grp * P.group_bytes;
-  const long long patch_stride = (long long)P.n_groups * P.group_bytes;
+  const char* pair_base = P.pyr + (long long)b * P.n_tiles * P.n_groups * P.group_bytes + (long long)grp * P.group_bytes;
+  const long long tile_stride = (long long)P.n_groups * P.group_bytes;
   int2* items = reinterpret_cast<int2*>(sm_words + QB * qstride_words);
 
   // ---------------- phase 0: per (level, query) patch origin, computed once ----------------
@@ -101,56 +87,47 @@ __global__ void __launch_bounds__(NTHREADS) corr_lookup_fwd_kernel(const LookupP
   __syncthreads();
 
   // ---------------- phase 1: gather patches ----------------
-  // task = (patch row, aligned group of GW elements); a round = 32 tasks of one (level, query).  Up to 30
-  // lanes fetch a whole (2r+2)^2 fp16 patch with one 16-byte load each and copy it verbatim to shared
-  // memory.  Per (level, round) sweep every warp serves 4 queries and keeps their 4 loads in flight.
-  // Everything outside a level's valid area is stored as zero by the GEMM epilogue, and groups outside
-  // the level are written as zeros here, so no per-element masking is needed.
+  // task = (window row, chunk); a round = 32 tasks of one (level, query).  In fp16, 30 lanes fetch a whole
+  // (2r+2)^2 window with one 16-byte load each.  Per (level, round) sweep every warp serves 4 queries and
+  // keeps their 4 loads in flight.  Everything outside a level's valid area is stored as zero by the GEMM
+  // (zero operand rows), and chunks outside the level are written as zeros here, so no per-element masking
+  // is needed.
+  using G = Gather<ES>;
+  const int ng = G::ng(D), row_el = G::row_el(D);
+  const int tasks = D * ng, rounds = (tasks + 31) >> 5;
   for (int l = 0; l < P.L; ++l) {
-    const PatchGeom g = patch_geom<ES>(l, D);
-    const int GW = 1 << g.gw_log, tasks = D * g.ng, rounds = (tasks + 31) >> 5;
-    const int tw_log = 5 - l, th_log = 3 - l;  // tile (8>>l) x (32>>l)
     const int hl = P.H >> l, wl = P.W >> l;
-    const bool wide = (GW * ES == 16);         // 16-byte groups; otherwise 8 bytes (fp16 level 3)
+    const int sw = P.sw[l], sbase = P.sub_base[l];
     for (int rnd = 0; rnd < rounds; ++rnd) {
       const int t = rnd * 32 + lane;
-      const int row = (g.ng == 3) ? (t * 43) >> 7 : (g.ng == 4) ? t >> 2 : t / g.ng;
-      const int gi = t - row * g.ng;
-      uint32_t wd[4][4];
+      const int row = (ng == 3) ? div3(t) : (ng == 4) ? t >> 2 : t / ng;
+      const int gi = t - row * ng;
+      uint4 wd[4];
       uint32_t* dst[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int ql = warp * 4 + i;  // NTHREADS/32 warps x 4 = QB queries
         dst[i] = nullptr;
-        wd[i][0] = wd[i][1] = wd[i][2] = wd[i][3] = 0u;
+        wd[i] = make_uint4(0u, 0u, 0u, 0u);
         if (t < tasks && q0 + ql < P.N) {
           const int2 org = items[l * QB + ql];
-          const int yy_abs = org.y + row;
-          const int xg = ((((org.x + 64) >> g.gw_log) + gi) << g.gw_log) - 64;  // first x of the group (aligned to GW)
-          dst[i] = sm_words + ql * qstride_words + g.lvl_off + row * g.row_words + gi * (GW * ES / 4);
-          if (yy_abs >= 0 && yy_abs < hl && xg >= 0 && xg < wl) {
-            const int ph = yy_abs >> th_log, yy = yy_abs & ((1 << th_log) - 1);
-            const int pw = xg >> tw_log, xx = xg & ((1 << tw_log) - 1);
-            const char* src = pair_base + (long long)(ph * P.n_pw + pw) * patch_stride + pyr_elem_offset(ES, l, ql, yy, xx);
-            if (wide) {
-              const uint4 v = ldg_nc_v4(src);
-              wd[i][0] = v.x; wd[i][1] = v.y; wd[i][2] = v.z; wd[i][3] = v.w;
-            } else {
-              const uint2 v = ldg_nc_v2(src);
-              wd[i][0] = v.x; wd[i][1] = v.y;
-            }
+          const int y = org.y + row;
+          const int xg = (G::chunk_floor(org.x) + gi) * G::VW;  // first pixel of the chunk
+          dst[i] = sm_words + ql * qstride_words + ((l * D + row) * row_el + gi * G::VW) * ES / 4;
+          if (y >= 0 && y < hl && xg >= 0 && xg < wl) {
+            const int s = sbase + (y >> 2) * sw + (xg >> 3);
+            const int col = (s & (PYR_SUBS_PER_TILE - 1)) * PYR_SUB + (y & 3) * PYR_SX + (xg & 7);
+            wd[i] = ldg_nc_v4(pair_base + (long long)(s >> 3) * tile_stride + pyr_record_offset(ES, ql, col));
           }
         }
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         if (dst[i] == nullptr) continue;
-        dst[i][0] = wd[i][0];
-        dst[i][1] = wd[i][1];
-        if (wide) {
-          dst[i][2] = wd[i][2];
-          dst[i][3] = wd[i][3];
-        }
+        dst[i][0] = wd[i].x;  // the per-query stride is odd (in words): 4-byte stores
+        dst[i][1] = wd[i].y;
+        dst[i][2] = wd[i].z;
+        dst[i][3] = wd[i].w;
       }
     }
   }
@@ -166,15 +143,14 @@ __global__ void __launch_bounds__(NTHREADS) corr_lookup_fwd_kernel(const LookupP
   float* out = P.out + (long long)b * P.L * KK * P.N + q;
   for (int item = warp; item < P.L * K; item += NTHREADS / 32) {
     const int l = item / K, i = item - l * K;  // i offsets x (slow output index!), j offsets y   pairwise.py:53-61
-    const PatchGeom g = patch_geom<ES>(l, D);
     const float inv = 1.0f / (float)(1 << l);
     const float cx = x * inv, cy = y * inv;
     const float fx = cx - floorf(cx), fy = cy - floorf(cy);
     // a clamped patch origin means the window is entirely outside: the patch is all zeros, weights moot
     const float wl0 = deq * (1.f - fx), wl1 = deq * fx;
-    const int off = (items[l * QB + lane].x + 64) & ((1 << g.gw_log) - 1);  // taps start `off` elements into the row
-    const int row_el = g.row_words * 4 / ES;
-    const T* p = reinterpret_cast<const T*>(sm_words + lane * qstride_words + g.lvl_off) + off + i;
+    const int xs = items[l * QB + lane].x;
+    const int off = xs - G::chunk_floor(xs) * G::VW;  // taps start `off` pixels into the fetched row
+    const T* p = reinterpret_cast<const T*>(sm_words + lane * qstride_words) + l * D * row_el + off + i;
     float* o = out + (long long)(l * KK + i * K) * P.N;
     float top = wl0 * (float)p[0] + wl1 * (float)p[1];  // horizontal lerp of row j
     for (int j = 0; j < K; ++j) {
@@ -280,8 +256,11 @@ extern "C" int ezb_corr_lookup_fwd(const void* pyramid, const float* deq_scale, 
   P.H = H;
   P.W = W;
   P.pyr = static_cast<const char*>(pyramid);
-  P.n_pw = lay.n_pw;
-  P.n_patches = lay.n_patches;
+  for (int l = 0; l < PYR_MAX_LEVELS; ++l) {
+    P.sw[l] = lay.sw[l];
+    P.sub_base[l] = lay.sub_base[l];
+  }
+  P.n_tiles = lay.n_tiles;
   P.n_groups = lay.n_groups;
   P.group_bytes = lay.group_bytes;
   P.deq = deq_scale;
@@ -291,13 +270,10 @@ extern "C" int ezb_corr_lookup_fwd(const void* pyramid, const float* deq_scale, 
   P.N = N;
   P.L = L;
   P.r = radius;
-  const int D = 2 * radius + 2, es = lay.es, epc = 16 / es;
-  int qwords = 0;  // per-query patch words over all levels (must match patch_geom in the kernel)
-  for (int l = 0; l < L; ++l) {
-    const int GW = std::min(epc, 32 >> l);
-    const int ng = (GW - 1 + D + GW - 1) / GW;
-    qwords += D * ng * GW * es / 4;
-  }
+  const int D = 2 * radius + 2, es = lay.es;
+  // per-query window words over all levels (must match Gather<ES> in the kernel)
+  const int row_el = es == 2 ? k3::Gather<2>::row_el(D) : k3::Gather<4>::row_el(D);
+  int qwords = L * D * row_el * es / 4;
   qwords |= 1;  // odd stride: lane = query reads are bank-conflict free
   const size_t smem = (size_t)k3::QB * qwords * 4 + (size_t)L * k3::QB * sizeof(int2);
   if (smem > 200 * 1024) return fail(EZB_ERR_UNSUPPORTED, "lookup window too large (L=%d, r=%d)", L, radius);

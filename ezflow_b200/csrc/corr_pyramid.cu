@@ -1,28 +1,37 @@
-// K1 + K2: RAFT all-pairs correlation with the average-pool pyramid fused into the GEMM epilogue.
+// K1 + K2: RAFT all-pairs correlation pyramid, all levels produced by ONE tcgen05 GEMM.
 //
 // Replaces MutliScalePairwise4DCorr.__init__/.corr (reference ezflow/similarity/correlation/
 // pairwise.py:26-41, :78-88):  corr[b,q,t] = sum_c f1[b,c,q] f2[b,c,t] / sqrt(C), then L-1 floor
 // 2x2 average pools over the target axes (t = h2*W + w2).
 //
+// Average pooling is linear, so level l of the pyramid is the correlation of f1 with the l-times
+// average-pooled f2:  pool_l(corr)[q, t_l] = < f1[:,q], pool_l(f2)[:, t_l] > / sqrt(C).  The pooled
+// feature maps are tiny (1/4, 1/16, 1/64 of f2), so the pooled levels are simply more GEMM columns:
+// the tensor core does the pooling, the epilogue is a pure convert-and-store, and the pyramid is
+// written exactly once (never re-read to pool it).
+//
 // Design:
-//   prep   : per-pair absmax -> power-of-two pre-scale -> fp32 (B,C,N) to fp16 K-major (B,N,Cp)
-//   gemm   : persistent, warp-specialised tcgen05 kernel.  One CTA tile = 128 queries (TMEM lanes)
-//            x one 8x32 *patch* of target pixels (256 TMEM columns, column = y*32+x inside the patch).
-//            The patch of f2 (B operand, up to 128 KB) stays resident in shared memory while the CTA
-//            sweeps query blocks (A operand streamed through a 4-stage TMA ring).  Because every
-//            thread of the epilogue owns one query row and a whole 8x32 target patch, all four
-//            pyramid levels (8x32 -> 4x16 -> 2x8 -> 1x4) are reduced in registers from the fp32
-//            accumulators and written once, as contiguous 4 KB sections (bulk shared->global copies)
-//            of the warp-strip-major pyramid layout (ezb_common.cuh): the pyramid is never re-read.
+//   prep   : per-pair absmax -> power-of-two pre-scale;
+//            f1: fp32 (B,C,N) -> fp16 K-major (B,N,Cp)                                   [A operand]
+//            f2: fp32 2x2 pools -> levels 1..L-1; then for every record tile a 256 x Cp fp16
+//                operand tile whose row n is the (pooled) f2 pixel of record column n     [B operand]
+//                (ezb_common.cuh: 8 subtiles of 4x8 pixels, all levels in one sequence)
+//   gemm   : persistent, warp-specialised tcgen05 kernel.  One CTA tile = 128 queries (TMEM lanes) x
+//            one record (256 TMEM columns).  The record operand (128 KB for C=256) stays resident in
+//            shared memory while the CTA sweeps query blocks (A streamed through a 4-stage TMA ring);
+//            two 256-column accumulators double-buffer MMA against the epilogue.
+//   epilogue: TMEM -> registers -> (scale) -> fp16/fp32 -> swizzled staging -> coalesced streaming
+//            16-byte stores; a warp writes its 32 queries x 128-byte lines as contiguous 4 KB sections.
 #include "ezb_common.cuh"
 #include "ezb_ptx.cuh"
+
+#include <cstdlib>
 
 namespace ezb {
 namespace k1 {
 
 constexpr int BM = 128;           // queries per tile  (UMMA M, TMEM lanes)
-constexpr int PH = 8, PW = 32;    // target patch      (UMMA N = 256, TMEM columns)
-constexpr int BN = PH * PW;
+constexpr int BN = PYR_REC;       // record elements   (UMMA N = 256, TMEM columns)
 constexpr int BK = 64;            // fp16 elements per 128-byte swizzle row
 constexpr int KB_MAX = 4;         // resident B k-blocks  (C <= 256)
 constexpr int STAGES = 4;         // A ring
@@ -30,7 +39,7 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_KB_BYTES = BN * BK * 2;      // 32 KB
 constexpr int SLOT_BYTES = 4096;             // one staged section: 32 queries x 128 B
 constexpr int SLOTS_PER_WARP = 2;
-constexpr int EPI_WARPS = 4;          // one warp per TMEM lane quadrant
+constexpr int EPI_WARPS = 4;                 // one warp per TMEM lane quadrant
 constexpr int NUM_THREADS = 128 + EPI_WARPS * 32;
 constexpr int SMEM_B = 0;
 constexpr int SMEM_A = SMEM_B + KB_MAX * B_KB_BYTES;
@@ -40,11 +49,13 @@ constexpr int SMEM_BYTES = SMEM_BAR + 256 + 1024;  // + barrier block + alignmen
 constexpr int TMEM_COLS = 512;                     // two 256-column accumulators
 
 struct GemmParams {
-  int B, N, H, W, KB, L;
-  int n_pw, n_patches, n_qblocks, n_groups;
-  long long total_tiles, group_bytes;
+  int B, N, KB, L;
+  int n_recs, n_qblocks, n_groups;
+  long long group_bytes;
   const float* epi_scale;  // [B]
-  char* pyr;               // pyramid buffer, group blocks ordered [pair][patch][group]
+  char* pyr;               // pyramid buffer, group blocks ordered [pair][record tile][group]
+  int dbg;                 // profiling experiments only (EZB_GEMM_DEBUG env): 1 no global stores, 2 no staging either,
+                           // 4 no MMA issue, 8 no A loads
 };
 
 // ------------------------------------------------------------------------------ prep kernels
@@ -82,39 +93,43 @@ __device__ __forceinline__ float pow2f(int e) {  // 2^e, |e| <= 126
   e = max(-126, min(126, e));
   return __uint_as_float((unsigned int)(e + 127) << 23);
 }
+// fp16 storage: operands are pre-scaled into (-2,2), so |acc| < 4C.  Stored = acc * F with F the largest
+// power of two keeping |stored| < 2^15: fp16 keeps full relative precision over ~19 binades below that.
+// F is folded into the B operand (|B| < 2F: 64 for C = 256, at most 2^14 for C = 1 — still fp16-safe).
+__device__ __forceinline__ float fp16_store_factor(int C) {
+  int lg = 0;
+  while ((1 << lg) < 4 * C) ++lg;
+  return pow2f(15 - lg);
+}
 
-// epi_scale[b] multiplies the fp32 accumulator in the GEMM epilogue, deq[b] multiplies stored
-// values at lookup time;  epi*deq == 2^(e1+e2)/sqrt(C) always.
-__global__ void scales_kernel(const unsigned int* __restrict__ amax, int B, int C, int dtype, float* __restrict__ epi,
-                              float* __restrict__ deq) {
+// bscale[b] multiplies f2 when the B operand is packed, epi[b] multiplies the fp32 accumulator in the
+// epilogue, deq[b] multiplies stored values at lookup time:  2^-e1 * bscale * epi * deq == 1/sqrt(C).
+__global__ void scales_kernel(const unsigned int* __restrict__ amax, int B, int C, int dtype, float* __restrict__ bscale,
+                              float* __restrict__ epi, float* __restrict__ deq) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  const int e = pow2_exponent(amax[b]) + pow2_exponent(amax[B + b]);
-  const float true_scale = pow2f(e) * rsqrtf((float)C);  // exact for power-of-four C, <=1ulp otherwise
+  const int e1 = pow2_exponent(amax[b]), e2 = pow2_exponent(amax[B + b]);
+  const float true_scale = pow2f(e1 + e2) * rsqrtf((float)C);  // exact for power-of-four C, <= 1 ulp otherwise
   if (dtype == EZB_F16) {
-    // operands are pre-scaled into (-2,2): |acc| < 4C.  Store acc * F with F the largest power of two
-    // keeping |stored| < 2^15, so fp16 keeps full relative precision over ~19 binades below that.
-    int lg = 0;
-    while ((1 << lg) < 4 * C) ++lg;
-    const float F = pow2f(15 - lg);
-    epi[b] = F;
+    const float F = fp16_store_factor(C);
+    bscale[b] = pow2f(-e2) * F;
+    epi[b] = 1.0f;  // nothing left to do in the epilogue
     deq[b] = true_scale / F;
   } else {
+    bscale[b] = pow2f(-e2);
     epi[b] = true_scale;
     deq[b] = 1.0f;
   }
 }
 
-// fp32 (B,C,N) -> fp16 (B,N,Cp) scaled by 2^-e (per pair, per tensor); channels >= C zero-filled.
-__global__ void __launch_bounds__(256) convert_kmajor_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
-                                                             __half* __restrict__ o1, __half* __restrict__ o2,
-                                                             const unsigned int* __restrict__ amax, int B, int C, int Cp,
-                                                             int N) {
+// A operand: fp32 (B,C,N) -> fp16 (B,N,Cp) scaled by 2^-e1 (per pair); channels >= C zero-filled.
+__global__ void __launch_bounds__(256) convert_kmajor_kernel(const float* __restrict__ f1, __half* __restrict__ o1,
+                                                             const unsigned int* __restrict__ amax, int C, int Cp, int N) {
   __shared__ float tile[64][33];
-  const int which = blockIdx.z / B, b = blockIdx.z % B;
-  const float* src = (which ? f2 : f1) + (long long)b * C * N;
-  __half* dst = (which ? o2 : o1) + (long long)b * N * Cp;
-  const float s = pow2f(-pow2_exponent(amax[which * B + b]));
+  const int b = blockIdx.z;
+  const float* src = f1 + (long long)b * C * N;
+  __half* dst = o1 + (long long)b * N * Cp;
+  const float s = pow2f(-pow2_exponent(amax[b]));
   const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -131,6 +146,61 @@ __global__ void __launch_bounds__(256) convert_kmajor_kernel(const float* __rest
       *reinterpret_cast<__half2*>(dst + (long long)n * Cp + c0 + 2 * lane) = v;
     }
   }
+}
+
+// fmap2 levels 1..L-1: successive floor 2x2 average pools (F.avg_pool2d(.., 2, stride=2), pairwise.py:40)
+// applied to the feature map instead of the 4-D volume.  planes = B*C.
+__global__ void __launch_bounds__(256) pool2x2_kernel(const float* __restrict__ src, float* __restrict__ dst, long long planes,
+                                                      int hs, int ws, int hd, int wd) {
+  const long long total = planes * hd * wd;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % wd);
+    const long long r = i / wd;
+    const int y = (int)(r % hd);
+    const long long pl = r / hd;
+    const float* s = src + (pl * hs + 2 * y) * ws + 2 * x;
+    dst[i] = 0.25f * ((__ldg(s) + __ldg(s + 1)) + (__ldg(s + ws) + __ldg(s + ws + 1)));
+  }
+}
+
+// B operand: for every (pair, record tile) a [256 rows][Cp] fp16 tile; row n holds the level-l pixel of
+// (pooled) f2 that record column n stands for (zero outside the level).
+// Block = (record tile, 32-channel chunk, pair); thread n gathers its pixel over the chunk's channels (a
+// warp reads one 4x8 subtile of one channel: four full 32-byte sectors), then rows are written K-major.
+constexpr int PACK_CH = 32;
+struct PackParams {
+  const float* lvl[PYR_MAX_LEVELS];  // level l of f2: (B, C, h[l], w[l]) fp32
+  int h[PYR_MAX_LEVELS], w[PYR_MAX_LEVELS], sw[PYR_MAX_LEVELS], sub_base[PYR_MAX_LEVELS + 1];
+  int L, C, Cp, n_recs;
+  const float* bscale;  // [B]
+  __half* bp;           // (B, n_recs, 256, Cp)
+};
+__global__ void __launch_bounds__(256) pack_record_operand_kernel(const PackParams P) {
+  __shared__ float tile[PACK_CH][PYR_REC + 1];
+  const int rec = blockIdx.x, c0 = blockIdx.y * PACK_CH, b = blockIdx.z;
+  const int n = threadIdx.x;
+  const int s = rec * PYR_SUBS_PER_TILE + (n >> 5);
+  int l = 0;
+  while (l + 1 < P.L && s >= P.sub_base[l + 1]) ++l;
+  const float* src = nullptr;
+  long long cstride = 0;
+  if (s < P.sub_base[PYR_MAX_LEVELS]) {
+    const int ls = s - P.sub_base[l];
+    const int sy = ls / P.sw[l], sx = ls - sy * P.sw[l];
+    const int y = sy * PYR_SY + ((n >> 3) & 3), x = sx * PYR_SX + (n & 7);
+    if (y < P.h[l] && x < P.w[l]) {
+      cstride = (long long)P.h[l] * P.w[l];
+      src = P.lvl[l] + ((long long)b * P.C + c0) * cstride + (long long)y * P.w[l] + x;
+    }
+  }
+  const float sc = __ldg(P.bscale + b);
+  const int cmax = min(PACK_CH, P.C - c0);  // channels >= C are zero-filled
+#pragma unroll 8
+  for (int c = 0; c < PACK_CH; ++c) tile[c][n] = (src != nullptr && c < cmax) ? __ldg(src + c * cstride) * sc : 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __half* dst = P.bp + ((long long)b * P.n_recs + rec) * PYR_REC * P.Cp + c0 + lane;
+  for (int row = warp; row < PYR_REC; row += 8) dst[(long long)row * P.Cp] = __float2half_rn(tile[lane][row]);
 }
 
 // ----------------------------------------------------------------------------- epilogue helpers
@@ -151,130 +221,69 @@ __device__ __forceinline__ void st_global_stream_v4(void* p, const uint4& v) {
   asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// One section of a group block (32 lines, one per lane, NWORDS*4 bytes each).  Every lane writes its own
-// line into the warp's staging slot with the layout's XOR chunk swizzle (bank-conflict free); the slot
-// is then byte-identical to the section in global memory, and the warp streams it out with fully
-// coalesced 16-byte stores: each store instruction writes 512 contiguous bytes.
-template <int NWORDS>
-__device__ __forceinline__ void staged_section_store(uint32_t slot, int lane, const uint32_t (&w)[NWORDS], char* gdst) {
-  static_assert(NWORDS == 32 || NWORDS == 16, "lines are 128 or 64 bytes");
-  constexpr uint32_t kSwz = NWORDS / 4 - 1;
-  __syncwarp();  // the previous section's read-back of this slot is complete in every lane
+// One section of a group block (32 lines of 128 bytes, one per lane).  Every lane writes its own line
+// into the warp's staging slot with the layout's XOR chunk swizzle (bank-conflict free); the slot is then
+// byte-identical to the section in global memory, and the warp streams it out with fully coalesced
+// 16-byte stores: each store instruction writes 512 contiguous bytes.
+__device__ __forceinline__ void staged_section_store(uint32_t slot, int lane, const uint32_t (&w)[32], char* gdst, int dbg) {
+  if (dbg & 2) return;
 #pragma unroll
-  for (int c = 0; c < NWORDS / 4; ++c)
-    st_shared_v4(slot + lane * (NWORDS * 4) + ((c ^ (lane & kSwz)) << 4), w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+  for (int c = 0; c < 8; ++c)
+    st_shared_v4(slot + lane * 128 + ((c ^ (lane & 7)) << 4), w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
   __syncwarp();
 #pragma unroll
-  for (int c = 0; c < NWORDS / 4; ++c) {
+  for (int c = 0; c < 8; ++c) {
     const uint4 v = ld_shared_v4(slot + c * 512 + lane * 16);
-    st_global_stream_v4(gdst + c * 512 + lane * 16, v);
+    if (!(dbg & 1)) st_global_stream_v4(gdst + c * 512 + lane * 16, v);
   }
+  // the caller alternates between two slots; the __syncwarp of the next call orders these reads before
+  // the writes that reuse this slot two calls later
 }
 
-// Epilogue of one tile for one warp: 32 queries (one per lane) x one 8x32 target patch -> one group block.
-// Strip s holds patch rows 2s and 2s+1; level-1 row s is their 2x2 average.  Levels 2 and 3 follow
-// from level 1, all from the fp32 accumulators (the reference pools fp32 values too).
+// Epilogue of one tile for one warp: 32 queries (one per lane) x one 256-element record -> one group block.
+// TMEM loads are software-pipelined: the load of section s+1 is in flight while section s is converted,
+// staged and stored (tcgen05.wait::ld waits for everything outstanding, so it is issued right before the
+// next load).  A single warp per SM sub-partition has nobody else to hide the ~200-cycle TMEM latency.
 template <typename OutT>
 __device__ __forceinline__ void epilogue_tile(uint32_t t_base, uint32_t stg_base, uint32_t& slot_ctr, int lane,
-                                              float scale, uint32_t tmem_empty_bar, int L, char* gblock, int vr1,
-                                              int vc1) {
-  // vr1 / vc1: number of valid level-1 rows / columns in this tile (4 / 16 for interior tiles).  Level-0
-  // values outside the image are exact zeros (TMA zero-fills the f2 patch); pooled values outside their
-  // level are forced to zero here so the lookup never needs per-element masking.
+                                              float scale, uint32_t tmem_empty_bar, char* gblock, int dbg) {
   constexpr bool kHalf = sizeof(OutT) == 2;
+  constexpr int kSections = kHalf ? 4 : 8;       // 64 / 32 record elements per 128-byte line
+  constexpr int kLoads = kHalf ? 2 : 1;          // x32 TMEM loads per section
   auto next_slot = [&]() { return stg_base + (slot_ctr++ & (SLOTS_PER_WARP - 1)) * SLOT_BYTES; };
-  float l1[4][16];
+  uint32_t r[2][kLoads][32];                     // double-buffered raw accumulator columns
+  if (dbg & 16) {  // profiling experiment: no TMEM reads at all
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(tmem_empty_bar);
+    return;
+  }
 #pragma unroll
-  for (int s = 0; s < 4; ++s) {
-    uint32_t r0[32], r1[32];
-    ptx::tmem_ld_32x32b_x32(t_base + (2 * s) * 32, r0);
-    ptx::tmem_ld_32x32b_x32(t_base + (2 * s + 1) * 32, r1);
-    ptx::tmem_ld_wait();
-    if (s == 3) {  // accumulator fully drained into registers: hand the TMEM buffer back to the MMA warp
+  for (int k = 0; k < kLoads; ++k) ptx::tmem_ld_32x32b_x32(t_base + k * 32, r[0][k]);
+#pragma unroll
+  for (int s = 0; s < kSections; ++s) {
+    ptx::tmem_ld_wait();  // section s has landed
+    if (s + 1 < kSections) {
+#pragma unroll
+      for (int k = 0; k < kLoads; ++k) ptx::tmem_ld_32x32b_x32(t_base + (s + 1) * (kLoads * 32) + k * 32, r[(s + 1) & 1][k]);
+    } else {  // accumulator fully drained into registers: hand the TMEM buffer back to the MMA warp
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tmem_empty_bar);
     }
-    if (gblock == nullptr) continue;  // query group entirely beyond N: nothing to store
-    float v0[32], v1[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      v0[j] = __uint_as_float(r0[j]) * scale;
-      v1[j] = __uint_as_float(r1[j]) * scale;
-    }
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-      l1[s][j] = (s < vr1 && j < vc1) ? 0.25f * ((v0[2 * j] + v0[2 * j + 1]) + (v1[2 * j] + v1[2 * j + 1])) : 0.f;
-
+    uint32_t w[32];
     if constexpr (kHalf) {
-      uint32_t w[32];  // line = [row 2s: 32 halfs][row 2s+1: 32 halfs]        (section s)
+      // fp16 storage: the store factor is folded into the B operand, the accumulator is the stored value
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        w[j] = pack_half2(v0[2 * j], v0[2 * j + 1]);
-        w[16 + j] = pack_half2(v1[2 * j], v1[2 * j + 1]);
+        w[j] = pack_half2(__uint_as_float(r[s & 1][0][2 * j]), __uint_as_float(r[s & 1][0][2 * j + 1]));
+        w[16 + j] = pack_half2(__uint_as_float(r[s & 1][1][2 * j]), __uint_as_float(r[s & 1][1][2 * j + 1]));
       }
-      staged_section_store<32>(next_slot(), lane, w, gblock + s * 4096);
     } else {
-      uint32_t w[32];  // line = one row of 32 floats                            (sections 2s, 2s+1)
 #pragma unroll
-      for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(v0[j]);
-      staged_section_store<32>(next_slot(), lane, w, gblock + (2 * s) * 4096);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(v1[j]);
-      staged_section_store<32>(next_slot(), lane, w, gblock + (2 * s + 1) * 4096);
-      if (L > 1 && (s & 1)) {  // level-1 rows s-1, s                              (section 8 + s/2)
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          w[j] = __float_as_uint(l1[s - 1][j]);
-          w[16 + j] = __float_as_uint(l1[s][j]);
-        }
-        staged_section_store<32>(next_slot(), lane, w, gblock + (8 + (s >> 1)) * 4096);
-      }
+      for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(__uint_as_float(r[s & 1][0][j]) * scale);
     }
-  }
-  if (gblock == nullptr || L < 2) return;
-  if constexpr (kHalf) {
-    uint32_t w[32];  // 4 rows x 16 halfs                                          (section 4)
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) w[r * 8 + j] = pack_half2(l1[r][2 * j], l1[r][2 * j + 1]);
-    staged_section_store<32>(next_slot(), lane, w, gblock + 4 * 4096);
-  }
-  if (L < 3) return;
-  float l2[2][8], l3[4];
-#pragma unroll
-  for (int r = 0; r < 2; ++r)
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      l2[r][j] = (r < (vr1 >> 1) && j < (vc1 >> 1))
-                     ? 0.25f * ((l1[2 * r][2 * j] + l1[2 * r][2 * j + 1]) + (l1[2 * r + 1][2 * j] + l1[2 * r + 1][2 * j + 1]))
-                     : 0.f;
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-    l3[j] = ((vr1 >> 2) > 0 && j < (vc1 >> 2)) ? 0.25f * ((l2[0][2 * j] + l2[0][2 * j + 1]) + (l2[1][2 * j] + l2[1][2 * j + 1])) : 0.f;
-  if constexpr (kHalf) {
-    uint32_t w[16];  // [level 2: 2 x 8 halfs = 32 B][level 3: 4 halfs = 8 B][pad]   (section 5, 64-byte lines)
-#pragma unroll
-    for (int r = 0; r < 2; ++r)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) w[r * 4 + j] = pack_half2(l2[r][2 * j], l2[r][2 * j + 1]);
-    w[8] = pack_half2(l3[0], l3[1]);
-    w[9] = pack_half2(l3[2], l3[3]);
-#pragma unroll
-    for (int j = 10; j < 16; ++j) w[j] = 0u;
-    staged_section_store<16>(next_slot(), lane, w, gblock + 5 * 4096);
-  } else {
-    uint32_t w[32];  // [level 2: 2 x 8 floats = 64 B][level 3: 4 floats = 16 B][pad] (section 10)
-#pragma unroll
-    for (int r = 0; r < 2; ++r)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) w[r * 8 + j] = __float_as_uint(l2[r][j]);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) w[16 + j] = __float_as_uint(l3[j]);
-#pragma unroll
-    for (int j = 20; j < 32; ++j) w[j] = 0u;
-    staged_section_store<32>(next_slot(), lane, w, gblock + 10 * 4096);
+    if (gblock != nullptr) staged_section_store(next_slot(), lane, w, gblock + s * 4096, dbg);  // null: group beyond N
   }
 }
 
@@ -310,7 +319,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     ptx::mbar_init(b_empty, 1);
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(tmem_full(a), 1);
-      ptx::mbar_init(tmem_empty(a), 4);  // one arrive per epilogue warp
+      ptx::mbar_init(tmem_empty(a), EPI_WARPS);  // one arrive per epilogue warp
     }
     ptx::fence_mbar_init();
   }
@@ -325,8 +334,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 
   // Pairs are processed one after the other by the whole grid (so the L2 working set is ONE pair's
   // operands); within a pair every CTA owns a contiguous, balanced range of tiles.
-  // tile t of pair b -> (patch = t / n_qblocks, qb = t % n_qblocks), bp = b * n_patches + patch.
-  const long long tiles_per_pair = (long long)p.n_patches * p.n_qblocks;
+  // tile t of pair b -> (rec = t / n_qblocks, qb = t % n_qblocks), bp = b * n_recs + rec.
+  const long long tiles_per_pair = (long long)p.n_recs * p.n_qblocks;
   const long long t_begin = tiles_per_pair * blockIdx.x / gridDim.x;
   const long long t_end = tiles_per_pair * (blockIdx.x + 1) / gridDim.x;
 
@@ -335,89 +344,84 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     uint32_t stage = 0, phase = 0, uphase = 0;
     long long cur_bp = -1;
     for (int b = 0; b < p.B; ++b)
-    for (long long t = t_begin; t < t_end; ++t) {
-      const int patch = (int)(t / p.n_qblocks);
-      const int qb = (int)(t - (long long)patch * p.n_qblocks);
-      const long long bp = (long long)b * p.n_patches + patch;
-      if (bp != cur_bp) {
-        const int ph = patch / p.n_pw, pw = patch - ph * p.n_pw;
-        if (cur_bp >= 0) {  // all MMAs reading the previous patch have completed
-          ptx::mbar_wait(b_empty, uphase);
-          uphase ^= 1;
+      for (long long t = t_begin; t < t_end; ++t) {
+        const int patch = (int)(t / p.n_qblocks);  // record tile
+        const int qb = (int)(t - (long long)patch * p.n_qblocks);
+        const long long bp = (long long)b * p.n_recs + patch;
+        if (bp != cur_bp) {
+          if (cur_bp >= 0) {  // all MMAs reading the previous patch have completed
+            ptx::mbar_wait(b_empty, uphase);
+            uphase ^= 1;
+          }
+          ptx::mbar_expect_tx(b_full, (uint32_t)(p.KB * B_KB_BYTES));
+          for (int kb = 0; kb < p.KB; ++kb)
+            ptx::tma_load_2d_hint(sB + kb * B_KB_BYTES, &tmB, b_full, kb * BK, (int)(bp * BN), ptx::kEvictFirst);
+          cur_bp = bp;
         }
-        ptx::mbar_expect_tx(b_full, (uint32_t)(p.KB * B_KB_BYTES));
-        for (int kb = 0; kb < p.KB; ++kb)
-          ptx::tma_load_4d_hint(sB + kb * B_KB_BYTES, &tmB, b_full, kb * BK, pw * PW, ph * PH, b, ptx::kEvictLast);
-        cur_bp = bp;
+        for (int kb = 0; kb < p.KB; ++kb) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+          if (p.dbg & 8) {
+            ptx::mbar_arrive(full_bar(stage));
+          } else {
+            ptx::mbar_expect_tx(full_bar(stage), A_STAGE_BYTES);
+            // fmap1 is re-read by every patch sweep (170x at 1080p): pin it in L2
+            ptx::tma_load_3d_hint(sA + stage * A_STAGE_BYTES, &tmA, full_bar(stage), kb * BK, qb * BM, b, ptx::kEvictLast);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
       }
-      for (int kb = 0; kb < p.KB; ++kb) {
-        ptx::mbar_wait(empty_bar(stage), phase ^ 1);
-        ptx::mbar_expect_tx(full_bar(stage), A_STAGE_BYTES);
-        // fmap1 is re-read by every patch sweep (136x at 1080p): pin it in L2
-        ptx::tma_load_3d_hint(sA + stage * A_STAGE_BYTES, &tmA, full_bar(stage), kb * BK, qb * BM, b, ptx::kEvictLast);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      }
-    }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = ptx::umma_idesc(/*f16*/ 0, BM, BN);
     uint32_t stage = 0, phase = 0, uphase = 0, tile = 0;
     long long cur_bp = -1;
     for (int b = 0; b < p.B; ++b)
-    for (long long t = t_begin; t < t_end; ++t, ++tile) {
-      const long long bp = (long long)b * p.n_patches + t / p.n_qblocks;
-      if (bp != cur_bp) {
-        if (cur_bp >= 0) ptx::umma_commit(b_empty);
-        ptx::mbar_wait(b_full, uphase);
-        uphase ^= 1;
-        cur_bp = bp;
-      }
-      const uint32_t acc = tile & 1, aphase = (tile >> 1) & 1;
-      ptx::mbar_wait(tmem_empty(acc), aphase ^ 1);
-      ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < p.KB; ++kb) {
-        ptx::mbar_wait(full_bar(stage), phase);
+      for (long long t = t_begin; t < t_end; ++t, ++tile) {
+        const long long bp = (long long)b * p.n_recs + t / p.n_qblocks;
+        if (bp != cur_bp) {
+          if (cur_bp >= 0) ptx::umma_commit(b_empty);
+          ptx::mbar_wait(b_full, uphase);
+          uphase ^= 1;
+          cur_bp = bp;
+        }
+        const uint32_t acc = tile & 1, aphase = (tile >> 1) & 1;
+        ptx::mbar_wait(tmem_empty(acc), aphase ^ 1);
         ptx::tc_fence_after();
-        const uint64_t a_desc = ptx::umma_desc_kmajor_sw128(sA + stage * A_STAGE_BYTES);
-        const uint64_t b_desc = ptx::umma_desc_kmajor_sw128(sB + kb * B_KB_BYTES);
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.KB; ++kb) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint64_t a_desc = ptx::umma_desc_kmajor_sw128(sA + stage * A_STAGE_BYTES);
+          const uint64_t b_desc = ptx::umma_desc_kmajor_sw128(sB + kb * B_KB_BYTES);
+          if (!(p.dbg & 4)) {
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)  // UMMA_K = 16 fp16 = 32 B = +2 in the descriptor's 16-byte units
-          ptx::umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-        ptx::umma_commit(empty_bar(stage));
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            for (int k = 0; k < BK / 16; ++k)  // UMMA_K = 16 fp16 = 32 B = +2 in the descriptor's 16-byte units
+              ptx::umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          }
+          ptx::umma_commit(empty_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(tmem_full(acc));
       }
-      ptx::umma_commit(tmem_full(acc));
-    }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int quad = warp & 3;             // TMEM lane quadrant this warp may access
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     const uint32_t stg_base = sStg + (warp - 4) * (SLOTS_PER_WARP * SLOT_BYTES);
     uint32_t slot_ctr = 0, tile = 0;
-    long long cur_bp = -1;
-    char* patch_base = nullptr;
-    float scale = 1.f;
-    int vr1 = 4, vc1 = 16;
-    for (int b = 0; b < p.B; ++b)
-    for (long long t = t_begin; t < t_end; ++t, ++tile) {
-      const int patch = (int)(t / p.n_qblocks);
-      const int qb = (int)(t - (long long)patch * p.n_qblocks);
-      const long long bp = (long long)b * p.n_patches + patch;
-      if (bp != cur_bp) {
-        const int ph = patch / p.n_pw, pw = patch - ph * p.n_pw;
-        vr1 = max(0, min(PH / 2, (p.H >> 1) - ph * (PH / 2)));  // valid level-1 rows / cols of this patch
-        vc1 = max(0, min(PW / 2, (p.W >> 1) - pw * (PW / 2)));
-        scale = __ldg(p.epi_scale + b);
-        patch_base = p.pyr + bp * p.n_groups * p.group_bytes;  // blocks are ordered [pair][patch][group]
-        cur_bp = bp;
+    for (int b = 0; b < p.B; ++b) {
+      const float scale = __ldg(p.epi_scale + b);
+      for (long long t = t_begin; t < t_end; ++t, ++tile) {
+        const int patch = (int)(t / p.n_qblocks);  // record tile
+        const int qb = (int)(t - (long long)patch * p.n_qblocks);
+        const long long bp = (long long)b * p.n_recs + patch;
+        const uint32_t acc = tile & 1, aphase = (tile >> 1) & 1;
+        ptx::mbar_wait(tmem_full(acc), aphase);
+        ptx::tc_fence_after();
+        const uint32_t t_base = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
+        const int grp = qb * (BM / 32) + quad;  // query group of this warp; blocks are ordered [pair][patch][group]
+        char* gblock = grp < p.n_groups ? p.pyr + (bp * p.n_groups + grp) * p.group_bytes : nullptr;
+        epilogue_tile<OutT>(t_base, stg_base, slot_ctr, lane, scale, tmem_empty(acc), gblock, p.dbg);
       }
-      const uint32_t acc = tile & 1, aphase = (tile >> 1) & 1;
-      ptx::mbar_wait(tmem_full(acc), aphase);
-      ptx::tc_fence_after();
-      const uint32_t t_base = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
-      const int grp = qb * (BM / 32) + quad;  // query group of this warp
-      epilogue_tile<OutT>(t_base, stg_base, slot_ctr, lane, scale, tmem_empty(acc), p.L,
-                          grp < p.n_groups ? patch_base + (long long)grp * p.group_bytes : nullptr, vr1, vc1);
     }
   }
 
@@ -456,13 +460,15 @@ static int make_tmap(CUtensorMap* tm, CUtensorMapDataType dt, int rank, void* pt
 
 struct Workspace {
   unsigned int* amax;  // [2][B]
+  float* bscale;       // [B]
   float* epi;          // [B]
-  __half* f1h;         // (B,N,Cp)
-  __half* f2h;
+  __half* f1h;         // (B,N,Cp)            A operand
+  __half* f2p;         // (B,n_recs,256,Cp)   B operand record tiles
+  float* f2l[PYR_MAX_LEVELS];  // pooled f2 levels 1..L-1, (B,C,h_l,w_l) fp32
 };
 
-static size_t ws_layout(int B, int C, int N, void* base, Workspace* ws) {
-  const int Cp = round_up(C, BK);
+static size_t ws_layout(int B, int C, const PyrLayout& lay, void* base, Workspace* ws) {
+  const int Cp = round_up(C, BK), N = lay.H * lay.W;
   uintptr_t p = reinterpret_cast<uintptr_t>(base);
   auto take = [&](size_t bytes, size_t align) {
     p = (p + align - 1) / align * align;
@@ -471,14 +477,19 @@ static size_t ws_layout(int B, int C, int N, void* base, Workspace* ws) {
     return r;
   };
   const uintptr_t amax = take((size_t)2 * B * 4, 256);
+  const uintptr_t bscale = take((size_t)B * 4, 256);
   const uintptr_t epi = take((size_t)B * 4, 256);
   const uintptr_t f1h = take((size_t)B * N * Cp * 2, 1024);
-  const uintptr_t f2h = take((size_t)B * N * Cp * 2, 1024);
+  const uintptr_t f2p = take((size_t)B * lay.n_tiles * PYR_REC * Cp * 2, 1024);
+  uintptr_t f2l[PYR_MAX_LEVELS] = {0, 0, 0, 0};
+  for (int l = 1; l < lay.L; ++l) f2l[l] = take((size_t)B * C * (lay.H >> l) * (lay.W >> l) * 4, 256);
   if (ws) {
     ws->amax = reinterpret_cast<unsigned int*>(amax);
+    ws->bscale = reinterpret_cast<float*>(bscale);
     ws->epi = reinterpret_cast<float*>(epi);
     ws->f1h = reinterpret_cast<__half*>(f1h);
-    ws->f2h = reinterpret_cast<__half*>(f2h);
+    ws->f2p = reinterpret_cast<__half*>(f2p);
+    for (int l = 0; l < PYR_MAX_LEVELS; ++l) ws->f2l[l] = reinterpret_cast<float*>(f2l[l]);
   }
   return p - reinterpret_cast<uintptr_t>(base);
 }
@@ -486,7 +497,7 @@ static size_t ws_layout(int B, int C, int N, void* base, Workspace* ws) {
 template <typename OutT>
 static int launch_gemm(const Workspace& ws, int B, int C, const PyrLayout& lay, void* pyr, cudaStream_t st, cudaEvent_t ev0,
                        cudaEvent_t ev1) {
-  const int H = lay.H, W = lay.W, N = H * W, Cp = round_up(C, BK);
+  const int N = lay.H * lay.W, Cp = round_up(C, BK);
   CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[3] = {(cuuint64_t)Cp, (cuuint64_t)N, (cuuint64_t)B};
@@ -496,32 +507,31 @@ static int launch_gemm(const Workspace& ws, int B, int C, const PyrLayout& lay, 
     if (r) return r;
   }
   {
-    cuuint64_t dims[4] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t str[3] = {(cuuint64_t)Cp * 2, (cuuint64_t)W * Cp * 2, (cuuint64_t)N * Cp * 2};
-    cuuint32_t box[4] = {BK, PW, PH, 1};
-    int r = make_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, ws.f2h, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    cuuint64_t dims[2] = {(cuuint64_t)Cp, (cuuint64_t)B * lay.n_tiles * PYR_REC};
+    cuuint64_t str[1] = {(cuuint64_t)Cp * 2};
+    cuuint32_t box[2] = {BK, BN};
+    int r = make_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ws.f2p, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (r) return r;
   }
   GemmParams p;
   p.B = B;
   p.N = N;
-  p.H = H;
-  p.W = W;
   p.KB = Cp / BK;
   p.L = lay.L;
-  p.n_pw = lay.n_pw;
-  p.n_patches = lay.n_patches;
+  p.n_recs = lay.n_tiles;
   p.n_qblocks = cdiv(N, BM);
   p.n_groups = lay.n_groups;
   p.group_bytes = lay.group_bytes;
-  p.total_tiles = (long long)B * p.n_patches * p.n_qblocks;
   p.epi_scale = ws.epi;
   p.pyr = static_cast<char*>(pyr);
+  const char* dbg_env = getenv("EZB_GEMM_DEBUG");
+  p.dbg = dbg_env ? atoi(dbg_env) : 0;
 
   auto kern = corr_pyramid_gemm_kernel<OutT>;
   EZB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   long long grid = num_sms();
-  if (grid > p.total_tiles / B) grid = p.total_tiles / B;  // tiles of one pair
+  const long long tiles_per_pair = (long long)p.n_recs * p.n_qblocks;
+  if (grid > tiles_per_pair) grid = tiles_per_pair;
   if (ev0) EZB_CUDA_OK(cudaEventRecord(ev0, st));
   kern<<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, p);
   EZB_LAUNCH_OK();
@@ -534,7 +544,7 @@ static int launch_gemm(const Workspace& ws, int B, int C, const PyrLayout& lay, 
 
 using namespace ezb;
 
-extern "C" int ezb_corr_pyramid_layout(int H, int W, int L, int dtype, int* h, int* w, int* n_ph, int* n_pw, int* n_groups,
+extern "C" int ezb_corr_pyramid_layout(int H, int W, int L, int dtype, int* h, int* w, int* sub_base, int* n_tiles, int* n_groups,
                                        int64_t* group_bytes, int64_t* pair_bytes) {
   EZB_REQUIRE(H > 0 && W > 0 && L >= 1, "bad pyramid shape H=%d W=%d L=%d", H, W, L);
   EZB_REQUIRE(dtype == EZB_F32 || dtype == EZB_F16, "bad dtype %d", dtype);
@@ -544,25 +554,43 @@ extern "C" int ezb_corr_pyramid_layout(int H, int W, int L, int dtype, int* h, i
   for (int l = 0; l < L; ++l) {
     if (h) h[l] = H >> l;
     if (w) w[l] = W >> l;
+    if (sub_base) sub_base[l] = lay.sub_base[l];
   }
-  if (n_ph) *n_ph = lay.n_ph;
-  if (n_pw) *n_pw = lay.n_pw;
+  if (sub_base) sub_base[L] = lay.sub_base[PYR_MAX_LEVELS];
+  if (n_tiles) *n_tiles = lay.n_tiles;
   if (n_groups) *n_groups = lay.n_groups;
   if (group_bytes) *group_bytes = lay.group_bytes;
   if (pair_bytes) *pair_bytes = lay.pair_bytes;
   return EZB_OK;
 }
 
-extern "C" int64_t ezb_corr_pyramid_elem_offset(int dtype, int level, int lane, int yy, int xx) {
-  if ((dtype != EZB_F32 && dtype != EZB_F16) || level < 0 || level >= PYR_MAX_LEVELS || lane < 0 || lane >= PYR_QG || yy < 0 ||
-      yy >= (PYR_PH >> level) || xx < 0 || xx >= (PYR_PW >> level))
-    return -1;
-  return pyr_elem_offset(dtype == EZB_F16 ? 2 : 4, level, lane, yy, xx);
+extern "C" int ezb_corr_pyramid_level_map(int H, int W, int L, int level, int32_t* tile, int32_t* column) {
+  EZB_REQUIRE(tile && column, "null pointer");
+  EZB_REQUIRE(H > 0 && W > 0 && L >= 1 && level >= 0 && level < L, "bad arguments H=%d W=%d L=%d level=%d", H, W, L, level);
+  if (L > PYR_MAX_LEVELS) return fail(EZB_ERR_UNSUPPORTED, "num_levels %d > %d is not supported by the fused pyramid", L, PYR_MAX_LEVELS);
+  PyrLayout lay;
+  EZB_REQUIRE(pyr_layout(H, W, L, EZB_F16, &lay), "feature map %dx%d too small for %d pyramid levels", H, W, L);
+  const int hl = H >> level, wl = W >> level;
+  for (int y = 0; y < hl; ++y)
+    for (int x = 0; x < wl; ++x) {
+      const int s = lay.sub_base[level] + (y / PYR_SY) * lay.sw[level] + x / PYR_SX;
+      tile[y * wl + x] = s / PYR_SUBS_PER_TILE;
+      column[y * wl + x] = (s % PYR_SUBS_PER_TILE) * PYR_SUB + (y % PYR_SY) * PYR_SX + x % PYR_SX;
+    }
+  return EZB_OK;
 }
 
-extern "C" int ezb_corr_pyramid_workspace_bytes(int B, int C, int H, int W, size_t* bytes) {
-  EZB_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && bytes, "bad arguments");
-  *bytes = k1::ws_layout(B, C, H * W, nullptr, nullptr) + 1024;
+extern "C" int64_t ezb_corr_pyramid_record_offset(int dtype, int lane, int column) {
+  if ((dtype != EZB_F32 && dtype != EZB_F16) || lane < 0 || lane >= PYR_QG || column < 0 || column >= PYR_REC) return -1;
+  return pyr_record_offset(dtype == EZB_F16 ? 2 : 4, lane, column);
+}
+
+extern "C" int ezb_corr_pyramid_workspace_bytes(int B, int C, int H, int W, int L, size_t* bytes) {
+  EZB_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && L >= 1 && bytes, "bad arguments");
+  if (L > PYR_MAX_LEVELS) return fail(EZB_ERR_UNSUPPORTED, "num_levels %d > %d is not supported by the fused pyramid", L, PYR_MAX_LEVELS);
+  PyrLayout lay;
+  EZB_REQUIRE(pyr_layout(H, W, L, EZB_F16, &lay), "feature map %dx%d too small for %d pyramid levels", H, W, L);
+  *bytes = k1::ws_layout(B, C, lay, nullptr, nullptr) + 1024;
   return EZB_OK;
 }
 
@@ -578,13 +606,14 @@ extern "C" int ezb_corr_pyramid_fwd_ex(const float* fmap1, const float* fmap2, i
   PyrLayout lay;
   EZB_REQUIRE(pyr_layout(H, W, L, dtype, &lay), "feature map %dx%d too small for %d pyramid levels", H, W, L);
   EZB_REQUIRE((reinterpret_cast<uintptr_t>(pyramid) & 127) == 0, "pyramid buffer must be 128-byte aligned");
+  EZB_REQUIRE((long long)B * lay.n_tiles * PYR_REC < (1ll << 31), "batch too large for one launch (split it)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int N = H * W, Cp = round_up(C, k1::BK);
 
   // carve the workspace from a 1024-aligned base
   uintptr_t wbase = (reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023);
   k1::Workspace ws;
-  const size_t need = k1::ws_layout(B, C, N, reinterpret_cast<void*>(wbase), &ws) + (wbase - reinterpret_cast<uintptr_t>(workspace));
+  const size_t need = k1::ws_layout(B, C, lay, reinterpret_cast<void*>(wbase), &ws) + (wbase - reinterpret_cast<uintptr_t>(workspace));
   if (need > workspace_bytes) return fail(EZB_ERR_WORKSPACE, "workspace too small: need %zu, got %zu", need, workspace_bytes);
 
   EZB_CUDA_OK(cudaMemsetAsync(ws.amax, 0, (size_t)2 * B * 4, st));
@@ -595,10 +624,30 @@ extern "C" int ezb_corr_pyramid_fwd_ex(const float* fmap1, const float* fmap2, i
     k1::absmax_kernel<<<dim3(gx, B, 2), 256, 0, st>>>(fmap1, fmap2, per_b, ws.amax, B);
     EZB_LAUNCH_OK();
   }
-  k1::scales_kernel<<<cdiv(B, 128), 128, 0, st>>>(ws.amax, B, C, dtype, ws.epi, deq_scale);
+  k1::scales_kernel<<<cdiv(B, 128), 128, 0, st>>>(ws.amax, B, C, dtype, ws.bscale, ws.epi, deq_scale);
   EZB_LAUNCH_OK();
-  k1::convert_kmajor_kernel<<<dim3(cdiv(N, 32), Cp / 64, 2 * B), 256, 0, st>>>(fmap1, fmap2, ws.f1h, ws.f2h, ws.amax, B, C,
-                                                                              Cp, N);
+  EZB_REQUIRE(B <= 65535, "batch too large for one launch (split it)");
+  k1::convert_kmajor_kernel<<<dim3(cdiv(N, 32), Cp / 64, B), 256, 0, st>>>(fmap1, ws.f1h, ws.amax, C, Cp, N);
+  EZB_LAUNCH_OK();
+  k1::PackParams pk;
+  for (int l = 0; l < PYR_MAX_LEVELS; ++l) {
+    pk.lvl[l] = l == 0 ? fmap2 : ws.f2l[l];
+    pk.h[l] = H >> l;
+    pk.w[l] = W >> l;
+    pk.sw[l] = lay.sw[l];
+    pk.sub_base[l] = lay.sub_base[l];
+  }
+  pk.sub_base[PYR_MAX_LEVELS] = lay.sub_base[PYR_MAX_LEVELS];
+  pk.L = L; pk.C = C; pk.Cp = Cp; pk.n_recs = lay.n_tiles;
+  pk.bscale = ws.bscale;
+  pk.bp = ws.f2p;
+  for (int l = 1; l < L; ++l) {
+    const long long total = (long long)B * C * pk.h[l] * pk.w[l];
+    const int gx = (int)std::min<long long>(cdiv64(total, 256), 148 * 8);
+    k1::pool2x2_kernel<<<gx, 256, 0, st>>>(pk.lvl[l - 1], ws.f2l[l], (long long)B * C, pk.h[l - 1], pk.w[l - 1], pk.h[l], pk.w[l]);
+    EZB_LAUNCH_OK();
+  }
+  k1::pack_record_operand_kernel<<<dim3(lay.n_tiles, Cp / k1::PACK_CH, B), 256, 0, st>>>(pk);
   EZB_LAUNCH_OK();
 
   cudaEvent_t ev0 = static_cast<cudaEvent_t>(ev_gemm_start), ev1 = static_cast<cudaEvent_t>(ev_gemm_end);

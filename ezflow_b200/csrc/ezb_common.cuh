@@ -85,56 +85,58 @@ inline bool pyramid_geom(int H, int W, int L, int dtype, LevelGeom* g) {
 }
 
 // --------------------------------------------------------------------------------------------
-// Correlation-pyramid storage ("warp-strip-major").  The target image of every level is
-// cut into the 8x32 level-0 patches the GEMM tiles over (level l: (8>>l) x (32>>l)); queries are taken
-// 32 at a time (one epilogue warp).  For one (pair, patch, query group) everything is one contiguous
-// *group block*, split into sections of 32 lines (one line per query of the group):
-//   fp16:  sec 0-3  level-0 rows (2s, 2s+1)   128 B lines      fp32:  sec 0-7  level-0 row s      128 B lines
-//          sec 4    level-1 (4 x 16)           128 B lines             sec 8-9  level-1 rows 2k,2k+1 128 B lines
-//          sec 5    level-2 (2 x 8) + level-3  64 B lines              sec 10   level-2 + level-3    128 B lines
-// Inside a line the 16-byte chunks are XOR-swizzled with the lane index, so the epilogue's shared-memory
-// staging (which is byte-identical to the global block) is bank-conflict free; sectors and 64-byte
-// DRAM atoms are preserved by the XOR.  Blocks are ordered [pair][patch][group]: a GEMM tile (128
-// queries x one patch) writes 4 consecutive blocks = 88 KB (fp16) of contiguous memory.
+// Correlation-pyramid storage ("subtile-sequence").
+// For one query, level l of the pyramid is an (H>>l) x (W>>l) image.  Every level is cut into 4x8-pixel
+// *subtiles* (64 B in fp16: the unit the lookup gathers, so a (2r+2)^2 window touches few DRAM atoms);
+// the subtiles of all levels form one sequence   s = sub_base[l] + (y/4) * sw_l + (x/8),  sw_l = ceil(w_l/8),
+// and 8 consecutive subtiles are one GEMM *tile*: 256 accumulator columns = one 256-element *record* per
+// query,  column n = (s % 8) * 32 + (y % 4) * 8 + (x % 8).  The pooled levels are ordinary GEMM columns:
+// avg-pooling is linear, so level l is the correlation with the l-times pooled fmap2.
+// Queries are taken 32 at a time (one epilogue warp).  For one (pair, tile, query group) the 32 records
+// form a contiguous *group block* of sections; section j holds, for each of the 32 queries, a 128-byte
+// line with record elements [j*EPL, (j+1)*EPL), EPL = 64 (fp16) or 32 (fp32).  Inside a line the 16-byte
+// chunks are XOR-swizzled with the lane index so that the epilogue's shared-memory staging (byte-identical
+// to the global section) is bank-conflict free; 32-byte sectors and 64-byte subtiles are preserved by the
+// XOR (as sets).  Blocks are ordered [pair][tile][group]: one GEMM tile (128 queries x one record) writes 4
+// consecutive blocks = 64 KB (fp16) of contiguous memory.  Pixels outside a level's valid area (and
+// levels >= L) are exact zeros.
 // --------------------------------------------------------------------------------------------
-constexpr int PYR_PH = 8, PYR_PW = 32, PYR_QG = 32, PYR_MAX_LEVELS = 4;
+constexpr int PYR_SY = 4, PYR_SX = 8, PYR_SUB = PYR_SY * PYR_SX, PYR_QG = 32, PYR_MAX_LEVELS = 4, PYR_REC = 256;
+constexpr int PYR_SUBS_PER_TILE = PYR_REC / PYR_SUB;
 
 struct PyrLayout {
   int H, W, L, es;
-  int n_ph, n_pw, n_patches, n_groups;
+  int sw[PYR_MAX_LEVELS], sub_base[PYR_MAX_LEVELS + 1];  // subtiles per row of level l; first subtile of level l
+  int n_tiles, n_groups;
   long long group_bytes, pair_bytes;
 };
 
-__host__ __device__ inline long long pyr_group_bytes(int es) { return es == 2 ? 22528 : 45056; }
+__host__ __device__ inline long long pyr_group_bytes(int es) { return (long long)PYR_QG * PYR_REC * es; }
 
 inline bool pyr_layout(int H, int W, int L, int dtype, PyrLayout* p) {
   if (H < 1 || W < 1 || L < 1 || L > PYR_MAX_LEVELS) return false;
   if ((H >> (L - 1)) < 1 || (W >> (L - 1)) < 1) return false;
   p->H = H; p->W = W; p->L = L;
   p->es = dtype == EZB_F16 ? 2 : 4;
-  p->n_ph = cdiv(H, PYR_PH);
-  p->n_pw = cdiv(W, PYR_PW);
-  p->n_patches = p->n_ph * p->n_pw;
+  int base = 0;
+  for (int l = 0; l < PYR_MAX_LEVELS; ++l) {
+    p->sub_base[l] = base;
+    p->sw[l] = l < L ? cdiv(W >> l, PYR_SX) : 0;
+    if (l < L) base += cdiv(H >> l, PYR_SY) * p->sw[l];
+  }
+  p->sub_base[PYR_MAX_LEVELS] = base;
+  p->n_tiles = cdiv(base, PYR_SUBS_PER_TILE);
   p->n_groups = cdiv(H * W, PYR_QG);
   p->group_bytes = pyr_group_bytes(p->es);
-  p->pair_bytes = (long long)p->n_patches * p->n_groups * p->group_bytes;
+  p->pair_bytes = (long long)p->n_tiles * p->n_groups * p->group_bytes;
   return true;
 }
 
-// byte offset, inside a group block, of element (yy, xx) of level l's tile for query `lane` of the group
-__host__ __device__ inline int pyr_elem_offset(int es, int l, int lane, int yy, int xx) {
-  int sec, inl, line = 128;
-  if (es == 2) {
-    if (l == 0) { sec = yy >> 1; inl = (yy & 1) * 64 + xx * 2; }
-    else if (l == 1) { sec = 4; inl = yy * 32 + xx * 2; }
-    else { sec = 5; line = 64; inl = (l == 2) ? yy * 16 + xx * 2 : 32 + xx * 2; }
-  } else {
-    if (l == 0) { sec = yy; inl = xx * 4; }
-    else if (l == 1) { sec = 8 + (yy >> 1); inl = (yy & 1) * 64 + xx * 4; }
-    else { sec = 10; inl = (l == 2) ? yy * 32 + xx * 4 : 64 + xx * 4; }
-  }
-  const int chunk = (inl >> 4) ^ (lane & (line / 16 - 1));
-  return sec * 4096 + lane * line + chunk * 16 + (inl & 15);
+// byte offset, inside a group block, of record element n (0..255) of query `lane` of the group
+__host__ __device__ inline int pyr_record_offset(int es, int lane, int n) {
+  const int epl = 128 / es;  // record elements per 128-byte line
+  const int sec = n / epl, inl = (n - sec * epl) * es;
+  return sec * 4096 + lane * 128 + (((inl >> 4) ^ (lane & 7)) << 4) + (inl & 15);
 }
 
 }  // namespace ezb

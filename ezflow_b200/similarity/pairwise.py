@@ -6,7 +6,7 @@ ezflow/similarity/correlation/pairwise.py:9-88): same name (sic), constructor ar
 ``nn.Module``, exactly like the reference.
 
 Deviations, all documented in DESIGN.md §6:
-* the pyramid is stored in the library's tiled ("warp-strip-major") layout, by default as fp16 with a
+* the pyramid is stored in the library's tiled ("subtile-sequence") layout, by default as fp16 with a
   per-pair power-of-two scale (fp32 selectable with ``set_pyramid_dtype("fp32")``); ``corr_pyramid`` is
   therefore a property that materialises reference-shaped fp32 tensors on demand; at most 4 levels;
 * no gradient w.r.t. ``coords`` (RAFT detaches them, reference models/raft.py:115);
@@ -39,37 +39,54 @@ def get_pyramid_dtype():
 
 
 class PyramidLayout:
-    """Geometry of the warp-strip-major pyramid buffer (include/ezflow_b200.h)."""
+    """Geometry of the subtile-sequence pyramid buffer (include/ezflow_b200.h)."""
 
     def __init__(self, H, W, L, dtype_code):
         h = (ctypes.c_int * L)()
         w = (ctypes.c_int * L)()
-        n_ph, n_pw, n_groups = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        sub_base = (ctypes.c_int * (L + 1))()
+        n_tiles, n_groups = ctypes.c_int(), ctypes.c_int()
         gb, pb = ctypes.c_int64(), ctypes.c_int64()
         _cabi.check(
             _cabi.lib().ezb_corr_pyramid_layout(
-                H, W, L, dtype_code, h, w, ctypes.byref(n_ph), ctypes.byref(n_pw), ctypes.byref(n_groups),
+                H, W, L, dtype_code, h, w, sub_base, ctypes.byref(n_tiles), ctypes.byref(n_groups),
                 ctypes.byref(gb), ctypes.byref(pb),
             )
         )
+        self.H, self.W, self.L = H, W, L
         self.levels = [(h[i], w[i]) for i in range(L)]
-        self.n_ph, self.n_pw, self.n_groups = n_ph.value, n_pw.value, n_groups.value
+        self.sub_base = [sub_base[i] for i in range(L + 1)]
+        self.n_tiles, self.n_groups = n_tiles.value, n_groups.value
         self.group_bytes, self.pair_bytes = gb.value, pb.value
         self.dtype_code = dtype_code
         self.es = 2 if dtype_code == _cabi.EZB_F16 else 4
+        self._maps = {}
+        self._rec = None
 
-    def level_index(self, l, device):
-        """Element offsets (32 lanes, th, tw) of level l inside a group block, from the library itself."""
-        th, tw = 8 >> l, 32 >> l
-        fn = _cabi.lib().ezb_corr_pyramid_elem_offset
-        idx = torch.empty((32, th, tw), dtype=torch.int64)
-        for lane in range(32):
-            for yy in range(th):
-                for xx in range(tw):
-                    off = fn(self.dtype_code, l, lane, yy, xx)
+    def record_index(self):
+        """(32 lanes, 256 columns) element offsets inside a group block, from the library itself."""
+        if self._rec is None:
+            fn = _cabi.lib().ezb_corr_pyramid_record_offset
+            idx = torch.empty((32, 256), dtype=torch.int64)
+            for lane in range(32):
+                for n in range(256):
+                    off = fn(self.dtype_code, lane, n)
                     assert off >= 0 and off % self.es == 0
-                    idx[lane, yy, xx] = off // self.es
-        return idx.to(device)
+                    idx[lane, n] = off // self.es
+            self._rec = idx
+        return self._rec
+
+    def level_map(self, l):
+        """(tile, column) LongTensors of shape (h_l, w_l) for level l, from the library itself."""
+        if l not in self._maps:
+            h, w = self.levels[l]
+            tile = (ctypes.c_int32 * (h * w))()
+            col = (ctypes.c_int32 * (h * w))()
+            _cabi.check(_cabi.lib().ezb_corr_pyramid_level_map(self.H, self.W, self.L, l, tile, col))
+            t = torch.tensor(list(tile), dtype=torch.int64).view(h, w)
+            c = torch.tensor(list(col), dtype=torch.int64).view(h, w)
+            self._maps[l] = (t, c)
+        return self._maps[l]
 
 
 def grad_layout(H, W, L):
@@ -106,7 +123,7 @@ class _PyramidState:
             self.pyr = torch.empty(self.B * self.layout.pair_bytes // self.layout.es, dtype=self.tdtype, device=self.device)
             self.deq = torch.empty(self.B, dtype=torch.float32, device=self.device)
             nbytes = ctypes.c_size_t(0)
-            _cabi.check(lib.ezb_corr_pyramid_workspace_bytes(self.B, self.C, self.H, self.W, ctypes.byref(nbytes)))
+            _cabi.check(lib.ezb_corr_pyramid_workspace_bytes(self.B, self.C, self.H, self.W, self.L, ctypes.byref(nbytes)))
             ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
             _cabi.check(
                 lib.ezb_corr_pyramid_fwd_ex(
@@ -123,22 +140,21 @@ class _PyramidState:
         queries: optional 1-D LongTensor of flat row indices b*N+q to extract; default all B*N rows."""
         lay = self.layout
         h, w = lay.levels[l]
-        th, tw = 8 >> l, 32 >> l
         ge = lay.group_bytes // lay.es
-        blocks = self.pyr.view(self.B, lay.n_ph, lay.n_pw, lay.n_groups, ge)
-        idx = lay.level_index(l, self.device)  # (32, th, tw)
+        dev = self.device
+        tile, col = (t.to(dev).reshape(-1) for t in lay.level_map(l))  # (h*w,)
+        rec = lay.record_index().to(dev)  # (32, 256)
         if queries is None:
-            t = blocks[..., idx]  # (B, n_ph, n_pw, G, 32, th, tw)
-            t = t.permute(0, 3, 4, 1, 5, 2, 6).reshape(self.B, lay.n_groups * 32, lay.n_ph * th, lay.n_pw * tw)
-            return t[:, : self.N, :h, :w].reshape(self.B * self.N, 1, h, w)
-        b = queries // self.N
-        q = queries % self.N
-        t = blocks[b, :, :, q // 32][..., :]  # (nq, n_ph, n_pw, ge)
-        sel = idx[q % 32]  # (nq, th, tw)
-        t = torch.gather(t.reshape(len(queries), lay.n_ph * lay.n_pw, ge), 2,
-                         sel.reshape(len(queries), 1, th * tw).expand(-1, lay.n_ph * lay.n_pw, -1))
-        t = t.reshape(len(queries), lay.n_ph, lay.n_pw, th, tw).permute(0, 1, 3, 2, 4)
-        return t.reshape(len(queries), 1, lay.n_ph * th, lay.n_pw * tw)[:, :, :h, :w]
+            queries = torch.arange(self.B * self.N, device=dev)
+        queries = queries.to(dev)
+        b, q = queries // self.N, queries % self.N
+        out = torch.empty((len(queries), h * w), dtype=self.tdtype, device=dev)
+        chunk = max(1, (1 << 24) // (h * w))  # bound the index tensors (~128 MB of int64)
+        for i0 in range(0, len(queries), chunk):
+            bb, qq = b[i0 : i0 + chunk, None], q[i0 : i0 + chunk, None]
+            block = (bb * lay.n_tiles + tile[None, :]) * lay.n_groups + qq // 32
+            out[i0 : i0 + chunk] = self.pyr[block * ge + rec[(qq % 32).expand(-1, h * w), col[None, :].expand(len(bb), -1)]]
+        return out.view(len(queries), 1, h, w)
 
     def ensure_grad(self):
         if self.grad_levels is None:

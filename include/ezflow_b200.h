@@ -48,25 +48,31 @@ int ezb_last_error(char* buf, size_t n);
  *   replaces MutliScalePairwise4DCorr.__init__ / .corr
  *   ezflow/similarity/correlation/pairwise.py:26-41, :78-88
  *
- * Pyramid storage (the library's choice, "warp-strip-major"): ONE buffer per call holding
- * all levels.  The target image of level l is cut into (8>>l) x (32>>l) tiles on the grid of the 8x32
- * level-0 patches the GEMM tiles over; queries (q = h1*W + w1) are grouped 32 at a time.  Each
- * (pair b, patch p, query group g) owns a contiguous *group block* of `group_bytes` at
- *   ((b * n_patches + p) * n_groups + g) * group_bytes,      p = (y0/8) * n_pw + (x0/32)
- * and ezb_corr_pyramid_elem_offset() gives the byte offset of an element inside a block.
- * h[l] = H >> l, w[l] = W >> l (floor, F.avg_pool2d default).  At most 4 levels.
- * Stored value * deq_scale[b] = reference value.
+ * Pyramid storage (the library's choice, "subtile-sequence"): ONE buffer per call holding
+ * all levels.  h[l] = H >> l, w[l] = W >> l (floor, F.avg_pool2d default); at most 4 levels.  Level l of
+ * a query's correlation map is cut into 4x8-pixel subtiles; the subtiles of all levels form one sequence
+ *   s = sub_base[l] + (y/4) * ceil(w[l]/8) + x/8
+ * and 8 consecutive subtiles are one 256-element record (= one GEMM tile of 256 accumulator columns):
+ *   tile = s / 8,   column = (s % 8) * 32 + (y % 4) * 8 + x % 8.
+ * Queries (q = h1*W + w1) are grouped 32 at a time.  Each (pair b, tile t, query group g) owns a
+ * contiguous *group block* of `group_bytes` at  ((b * n_tiles + t) * n_groups + g) * group_bytes;
+ * ezb_corr_pyramid_record_offset() gives the byte offset of a record column inside a block.
+ * Pixels outside a level are stored as zeros.  Stored value * deq_scale[b] = reference value.
  * ------------------------------------------------------------------------------------------- */
 int ezb_corr_pyramid_layout(int H, int W, int L, int dtype,
-                            int* h /*[L] host*/, int* w /*[L] host*/, int* n_ph, int* n_pw, int* n_groups,
+                            int* h /*[L] host*/, int* w /*[L] host*/, int* sub_base /*[L+1] host*/,
+                            int* n_tiles, int* n_groups,
                             int64_t* group_bytes, int64_t* pair_bytes /* all host, may be null */);
 
-/* byte offset inside a group block of element (yy, xx) of the level-`level` tile for query `lane`
- * (0..31) of the group; -1 on bad arguments */
-int64_t ezb_corr_pyramid_elem_offset(int dtype, int level, int lane, int yy, int xx);
+/* (tile, column) of every pixel of one level, row-major (h[level] * w[level] entries each, host) */
+int ezb_corr_pyramid_level_map(int H, int W, int L, int level, int32_t* tile, int32_t* column);
 
-/* bytes of scratch ezb_corr_pyramid_fwd needs (fp16 K-major operand copies + scales) */
-int ezb_corr_pyramid_workspace_bytes(int B, int C, int H, int W, size_t* bytes /*host*/);
+/* byte offset inside a group block of record column `column` (0..255) for query `lane` (0..31) of the
+ * group; -1 on bad arguments */
+int64_t ezb_corr_pyramid_record_offset(int dtype, int lane, int column);
+
+/* bytes of scratch ezb_corr_pyramid_fwd needs (fp16 operand tiles, pooled fmap2 levels, scales) */
+int ezb_corr_pyramid_workspace_bytes(int B, int C, int H, int W, int L, size_t* bytes /*host*/);
 
 int ezb_corr_pyramid_fwd(const float* fmap1, const float* fmap2, /* (B,C,H,W) fp32 contiguous */
                          int B, int C, int H, int W, int L, int dtype,

@@ -43,29 +43,43 @@ def test_pyramid_layout(lib):
     from ezflow_b200 import _cabi
     from ezflow_b200.similarity.pairwise import PyramidLayout, grad_layout
 
-    # 1080p: floor pooling 135x240 -> 67x120 -> 33x60 -> 16x30
+    # 1080p: floor pooling 135x240 -> 67x120 -> 33x60 -> 16x30, 4x8-pixel subtiles
     lay = PyramidLayout(135, 240, 4, _cabi.EZB_F16)
     assert lay.levels == [(135, 240), (67, 120), (33, 60), (16, 30)]
-    assert (lay.n_ph, lay.n_pw, lay.n_groups) == (17, 8, 1013)
-    assert lay.group_bytes == 22528 and lay.pair_bytes == 17 * 8 * 1013 * 22528
+    assert lay.sub_base == [0, 34 * 30, 34 * 30 + 17 * 15, 34 * 30 + 17 * 15 + 9 * 8, 34 * 30 + 17 * 15 + 9 * 8 + 4 * 4]
+    assert (lay.n_tiles, lay.n_groups) == (171, 1013)
+    assert lay.group_bytes == 16384 and lay.pair_bytes == 171 * 1013 * 16384
     lay32 = PyramidLayout(46, 62, 4, _cabi.EZB_F32)
-    assert lay32.group_bytes == 45056 and (lay32.n_ph, lay32.n_pw, lay32.n_groups) == (6, 2, 90)
+    assert lay32.group_bytes == 32768 and lay32.n_groups == 90
+    assert lay32.n_tiles == -(-(12 * 8 + 6 * 4 + 3 * 2 + 2 * 1) // 8)
     with pytest.raises(ValueError):
         PyramidLayout(4, 4, 4, 0)  # level 3 would be empty
     with pytest.raises(NotImplementedError):
         PyramidLayout(64, 64, 5, 0)
-    # every element of every level maps to a distinct, in-range, element-aligned offset of the block
-    for dt, es, gb in ((_cabi.EZB_F16, 2, 22528), (_cabi.EZB_F32, 4, 45056)):
+    # every record column maps to a distinct, in-range, element-aligned offset of the block
+    for dt, es, gb in ((_cabi.EZB_F16, 2, 16384), (_cabi.EZB_F32, 4, 32768)):
         seen = set()
-        for l in range(4):
-            for lane in range(32):
-                for yy in range(8 >> l):
-                    for xx in range(32 >> l):
-                        off = lib.ezb_corr_pyramid_elem_offset(dt, l, lane, yy, xx)
-                        assert 0 <= off < gb and off % es == 0 and off not in seen
-                        seen.add(off)
-        assert len(seen) == 32 * (256 + 64 + 16 + 4)
-    assert lib.ezb_corr_pyramid_elem_offset(1, 1, 0, 4, 0) == -1
+        for lane in range(32):
+            for n in range(256):
+                off = lib.ezb_corr_pyramid_record_offset(dt, lane, n)
+                assert 0 <= off < gb and off % es == 0 and off not in seen
+                seen.add(off)
+        assert len(seen) == 32 * 256
+        # a 4x8 subtile (32 consecutive columns) stays inside one 64-byte (fp16) / 128-byte (fp32) atom
+        for lane in (0, 5, 31):
+            for sub in range(8):
+                offs = [lib.ezb_corr_pyramid_record_offset(dt, lane, sub * 32 + k) for k in range(32)]
+                assert len({o // (32 * es) for o in offs}) == 1
+    assert lib.ezb_corr_pyramid_record_offset(1, 32, 0) == -1
+    # every pixel of every level maps to a distinct (tile, column)
+    seen = set()
+    for l, (h, w) in enumerate(lay32.levels):
+        t, c = lay32.level_map(l)
+        assert tuple(t.shape) == (h, w)
+        assert int(t.max()) < lay32.n_tiles and int(c.max()) < 256 and int(c.min()) >= 0
+        pairs = set(zip(t.reshape(-1).tolist(), c.reshape(-1).tolist()))
+        assert len(pairs) == h * w and not (pairs & seen)
+        seen |= pairs
     g = grad_layout(46, 62, 4)
     assert [(h, w, p) for h, w, p, _ in g] == [(46, 62, 64), (23, 31, 32), (11, 15, 16), (5, 7, 8)]
 
@@ -82,12 +96,12 @@ def test_argument_validation_without_gpu(lib):
     with pytest.raises(NotImplementedError):
         _cabi.check(rc)
     n = ctypes.c_size_t(0)
-    assert lib.ezb_corr_pyramid_workspace_bytes(1, 256, 135, 240, ctypes.byref(n)) == 0
+    assert lib.ezb_corr_pyramid_workspace_bytes(1, 256, 135, 240, 4, ctypes.byref(n)) == 0
     assert n.value >= 2 * 32400 * 256 * 2
 
 
 def test_sass_is_blackwell_native():
-    """The GEMM must be tcgen05 + TMA (SASS: UTCHMMA / LDTM / UTMALDG / UBLKCP bulk stores), not mma.sync."""
+    """The GEMM must be tcgen05 + TMA (SASS: UTCHMMA / LDTM / UTMALDG), not mma.sync."""
     import shutil
     import subprocess
 
@@ -97,6 +111,6 @@ def test_sass_is_blackwell_native():
     if not os.path.exists(cuobjdump):
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([cuobjdump, "-sass", build.LIBPATH], capture_output=True, text=True).stdout
-    for mnem in ("UTCHMMA", "LDTM", "UTMALDG", "UBLKCP"):
+    for mnem in ("UTCHMMA", "LDTM", "UTMALDG"):
         assert mnem in sass, f"{mnem} missing from SASS"
     assert "HMMA." not in sass.replace("UTCHMMA", "")
