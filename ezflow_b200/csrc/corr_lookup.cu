@@ -63,7 +63,7 @@ struct Gather {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(NTHREADS) corr_lookup_fwd_kernel(const LookupParams P, const int qstride_words) {
+__global__ void __launch_bounds__(NTHREADS, 3) corr_lookup_fwd_kernel(const LookupParams P, const int qstride_words) {
   extern __shared__ uint32_t sm_words[];  // [QB][qstride_words] patches, then [L*QB] int2 item parameters
   constexpr int ES = (int)sizeof(T);
   const int r = P.r, D = 2 * r + 2, K = 2 * r + 1, KK = K * K;
@@ -75,59 +75,71 @@ __global__ void __launch_bounds__(NTHREADS) corr_lookup_fwd_kernel(const LookupP
   const long long tile_stride = (long long)P.n_groups * P.group_bytes;
   int2* items = reinterpret_cast<int2*>(sm_words + QB * qstride_words);
 
-  // ---------------- phase 0: per (level, query) patch origin, computed once ----------------
-  for (int it = threadIdx.x; it < QB * P.L; it += NTHREADS) {
-    const int l = it / QB, ql = it - l * QB, q = min(q0 + ql, P.N - 1);
+  // ---------------- phase 0: window origins ----------------
+  // Every warp serves 4 queries of the block; lane k < 16 owns item (query k/4, level k%4) and keeps its
+  // window origin in registers (shuffled to the other lanes below) and in shared memory (phase 2).
+  int2 org_mine;
+  {
+    const int qi = (lane >> 2) & 3, l = lane & 3;
+    const int q = min(q0 + warp * 4 + qi, P.N - 1);
     const float inv = 1.0f / (float)(1 << l);
     const int x0 = float_floor_to_int_clamped(__ldg(cx_ptr + q) * inv, -(1 << 24), 1 << 24);
     const int y0 = float_floor_to_int_clamped(__ldg(cy_ptr + q) * inv, -(1 << 24), 1 << 24);
     // clamped so that a window entirely outside the level stays entirely outside
-    items[it] = make_int2(max(-D, min(P.W >> l, x0 - r)), max(-D, min(P.H >> l, y0 - r)));
+    org_mine = make_int2(max(-D, min(P.W >> l, x0 - r)), max(-D, min(P.H >> l, y0 - r)));
+    if (lane < 16 && l < P.L) items[l * QB + warp * 4 + qi] = org_mine;
   }
-  __syncthreads();
 
-  // ---------------- phase 1: gather patches ----------------
+  // ---------------- phase 1: gather windows ----------------
   // task = (window row, chunk); a round = 32 tasks of one (level, query).  In fp16, 30 lanes fetch a whole
-  // (2r+2)^2 window with one 16-byte load each.  Per (level, round) sweep every warp serves 4 queries and
-  // keeps their 4 loads in flight.  Everything outside a level's valid area is stored as zero by the GEMM
-  // (zero operand rows), and chunks outside the level are written as zeros here, so no per-element masking
-  // is needed.
+  // (2r+2)^2 window with one 16-byte load each.  A warp keeps the loads of 2 queries x all levels (8 x 512
+  // bytes) in flight before it touches shared memory.  Everything outside a level's valid area is stored
+  // as zero by the GEMM (zero operand rows), and chunks outside the level are written as zeros here, so no
+  // per-element masking is needed.
   using G = Gather<ES>;
   const int ng = G::ng(D), row_el = G::row_el(D);
   const int tasks = D * ng, rounds = (tasks + 31) >> 5;
-  for (int l = 0; l < P.L; ++l) {
-    const int hl = P.H >> l, wl = P.W >> l;
-    const int sw = P.sw[l], sbase = P.sub_base[l];
-    for (int rnd = 0; rnd < rounds; ++rnd) {
-      const int t = rnd * 32 + lane;
-      const int row = (ng == 3) ? div3(t) : (ng == 4) ? t >> 2 : t / ng;
-      const int gi = t - row * ng;
-      uint4 wd[4];
-      uint32_t* dst[4];
+  for (int rnd = 0; rnd < rounds; ++rnd) {
+    const int t = rnd * 32 + lane;
+    const int row = (ng == 3) ? div3(t) : (ng == 4) ? t >> 2 : t / ng;
+    const int gi = t - row * ng;
+    const bool task_ok = t < tasks;
+    uint32_t* const dst_task = sm_words + (row * row_el + gi * G::VW) * ES / 4;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int ql = warp * 4 + i;  // NTHREADS/32 warps x 4 = QB queries
-        dst[i] = nullptr;
-        wd[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (t < tasks && q0 + ql < P.N) {
-          const int2 org = items[l * QB + ql];
-          const int y = org.y + row;
-          const int xg = (G::chunk_floor(org.x) + gi) * G::VW;  // first pixel of the chunk
-          dst[i] = sm_words + ql * qstride_words + ((l * D + row) * row_el + gi * G::VW) * ES / 4;
-          if (y >= 0 && y < hl && xg >= 0 && xg < wl) {
-            const int s = sbase + (y >> 2) * sw + (xg >> 3);
-            const int col = (s & (PYR_SUBS_PER_TILE - 1)) * PYR_SUB + (y & 3) * PYR_SX + (xg & 7);
-            wd[i] = ldg_nc_v4(pair_base + (long long)(s >> 3) * tile_stride + pyr_record_offset(ES, ql, col));
+    for (int hq = 0; hq < 2; ++hq) {
+      uint4 wd[2][PYR_MAX_LEVELS];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int qi = hq * 2 + i, ql = warp * 4 + qi;
+#pragma unroll
+        for (int l = 0; l < PYR_MAX_LEVELS; ++l) {
+          const int ox = __shfl_sync(0xffffffffu, org_mine.x, qi * 4 + l);
+          const int oy = __shfl_sync(0xffffffffu, org_mine.y, qi * 4 + l);
+          wd[i][l] = make_uint4(0u, 0u, 0u, 0u);
+          if (l < P.L && task_ok) {
+            const int y = oy + row;
+            const int xg = (G::chunk_floor(ox) + gi) * G::VW;  // first pixel of the chunk
+            if (y >= 0 && y < (P.H >> l) && xg >= 0 && xg < (P.W >> l)) {
+              const int s = P.sub_base[l] + (y / PYR_SY) * P.sw[l] + xg / PYR_SX;
+              const int col = (s % PYR_SUBS_PER_TILE) * PYR_SUB + (y % PYR_SY) * PYR_SX + xg % PYR_SX;
+              wd[i][l] = ldg_nc_v4(pair_base + (long long)(s / PYR_SUBS_PER_TILE) * tile_stride + pyr_record_offset(ES, ql, col));
+            }
           }
         }
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (dst[i] == nullptr) continue;
-        dst[i][0] = wd[i].x;  // the per-query stride is odd (in words): 4-byte stores
-        dst[i][1] = wd[i].y;
-        dst[i][2] = wd[i].z;
-        dst[i][3] = wd[i].w;
+      for (int i = 0; i < 2; ++i) {
+        const int ql = warp * 4 + hq * 2 + i;
+#pragma unroll
+        for (int l = 0; l < PYR_MAX_LEVELS; ++l) {
+          if (l < P.L && task_ok) {
+            uint32_t* dst = dst_task + ql * qstride_words + l * D * row_el * ES / 4;
+            dst[0] = wd[i][l].x;  // the per-query stride is odd (in words): 4-byte stores
+            dst[1] = wd[i][l].y;
+            dst[2] = wd[i][l].z;
+            dst[3] = wd[i][l].w;
+          }
+        }
       }
     }
   }

@@ -38,8 +38,8 @@ constexpr int STAGES = 4;         // A ring
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_KB_BYTES = BN * BK * 2;      // 32 KB
 constexpr int SLOT_BYTES = 4096;             // one staged section: 32 queries x 128 B
-constexpr int SLOTS_PER_WARP = 2;
-constexpr int EPI_WARPS = 4;                 // one warp per TMEM lane quadrant
+constexpr int SLOTS_PER_WARP = 1;
+constexpr int EPI_WARPS = 8;                 // two warps per TMEM lane quadrant, each takes half of the record
 constexpr int NUM_THREADS = 128 + EPI_WARPS * 32;
 constexpr int SMEM_B = 0;
 constexpr int SMEM_A = SMEM_B + KB_MAX * B_KB_BYTES;
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(256) pack_record_operand_kernel(const PackPara
   __shared__ float tile[PACK_CH][PYR_REC + 1];
   const int rec = blockIdx.x, c0 = blockIdx.y * PACK_CH, b = blockIdx.z;
   const int n = threadIdx.x;
-  const int s = rec * PYR_SUBS_PER_TILE + (n >> 5);
+  const int s = rec * PYR_SUBS_PER_TILE + n / PYR_SUB;
   int l = 0;
   while (l + 1 < P.L && s >= P.sub_base[l + 1]) ++l;
   const float* src = nullptr;
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(256) pack_record_operand_kernel(const PackPara
   if (s < P.sub_base[PYR_MAX_LEVELS]) {
     const int ls = s - P.sub_base[l];
     const int sy = ls / P.sw[l], sx = ls - sy * P.sw[l];
-    const int y = sy * PYR_SY + ((n >> 3) & 3), x = sx * PYR_SX + (n & 7);
+    const int y = sy * PYR_SY + (n % PYR_SUB) / PYR_SX, x = sx * PYR_SX + n % PYR_SX;
     if (y < P.h[l] && x < P.w[l]) {
       cstride = (long long)P.h[l] * P.w[l];
       src = P.lvl[l] + ((long long)b * P.C + c0) * cstride + (long long)y * P.w[l] + x;
@@ -227,6 +227,7 @@ __device__ __forceinline__ void st_global_stream_v4(void* p, const uint4& v) {
 // 16-byte stores: each store instruction writes 512 contiguous bytes.
 __device__ __forceinline__ void staged_section_store(uint32_t slot, int lane, const uint32_t (&w)[32], char* gdst, int dbg) {
   if (dbg & 2) return;
+  __syncwarp();  // the previous section's reads of this slot are done (shared-memory ops of a warp stay in order)
 #pragma unroll
   for (int c = 0; c < 8; ++c)
     st_shared_v4(slot + lane * 128 + ((c ^ (lane & 7)) << 4), w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
@@ -236,22 +237,21 @@ __device__ __forceinline__ void staged_section_store(uint32_t slot, int lane, co
     const uint4 v = ld_shared_v4(slot + c * 512 + lane * 16);
     if (!(dbg & 1)) st_global_stream_v4(gdst + c * 512 + lane * 16, v);
   }
-  // the caller alternates between two slots; the __syncwarp of the next call orders these reads before
-  // the writes that reuse this slot two calls later
 }
 
-// Epilogue of one tile for one warp: 32 queries (one per lane) x one 256-element record -> one group block.
+// Epilogue of one tile for one warp: 32 queries (one per lane) x HALF of a 256-element record (the two
+// warps of a TMEM lane quadrant split the record's sections) -> half of one group block.
 // TMEM loads are software-pipelined: the load of section s+1 is in flight while section s is converted,
 // staged and stored (tcgen05.wait::ld waits for everything outstanding, so it is issued right before the
-// next load).  A single warp per SM sub-partition has nobody else to hide the ~200-cycle TMEM latency.
+// next load).
 template <typename OutT>
-__device__ __forceinline__ void epilogue_tile(uint32_t t_base, uint32_t stg_base, uint32_t& slot_ctr, int lane,
-                                              float scale, uint32_t tmem_empty_bar, char* gblock, int dbg) {
+__device__ __forceinline__ void epilogue_tile(uint32_t t_base, uint32_t slot, int half, int lane, float scale,
+                                              uint32_t tmem_empty_bar, char* gblock, int dbg) {
   constexpr bool kHalf = sizeof(OutT) == 2;
-  constexpr int kSections = kHalf ? 4 : 8;       // 64 / 32 record elements per 128-byte line
-  constexpr int kLoads = kHalf ? 2 : 1;          // x32 TMEM loads per section
-  auto next_slot = [&]() { return stg_base + (slot_ctr++ & (SLOTS_PER_WARP - 1)) * SLOT_BYTES; };
-  uint32_t r[2][kLoads][32];                     // double-buffered raw accumulator columns
+  constexpr int kSections = (kHalf ? 4 : 8) / 2;  // sections per warp; 64 / 32 record elements per 128-byte line
+  constexpr int kLoads = kHalf ? 2 : 1;           // x32 TMEM loads per section
+  const int s0 = half * kSections;
+  uint32_t r[2][kLoads][32];                      // double-buffered raw accumulator columns
   if (dbg & 16) {  // profiling experiment: no TMEM reads at all
     ptx::tc_fence_before();
     __syncwarp();
@@ -259,14 +259,14 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_base, uint32_t stg_base
     return;
   }
 #pragma unroll
-  for (int k = 0; k < kLoads; ++k) ptx::tmem_ld_32x32b_x32(t_base + k * 32, r[0][k]);
+  for (int k = 0; k < kLoads; ++k) ptx::tmem_ld_32x32b_x32(t_base + (s0 * kLoads + k) * 32, r[0][k]);
 #pragma unroll
   for (int s = 0; s < kSections; ++s) {
     ptx::tmem_ld_wait();  // section s has landed
     if (s + 1 < kSections) {
 #pragma unroll
-      for (int k = 0; k < kLoads; ++k) ptx::tmem_ld_32x32b_x32(t_base + (s + 1) * (kLoads * 32) + k * 32, r[(s + 1) & 1][k]);
-    } else {  // accumulator fully drained into registers: hand the TMEM buffer back to the MMA warp
+      for (int k = 0; k < kLoads; ++k) ptx::tmem_ld_32x32b_x32(t_base + ((s0 + s + 1) * kLoads + k) * 32, r[(s + 1) & 1][k]);
+    } else {  // this warp's part of the accumulator is in registers: hand the TMEM buffer back to the MMA warp
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tmem_empty_bar);
@@ -283,7 +283,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_base, uint32_t stg_base
 #pragma unroll
       for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(__uint_as_float(r[s & 1][0][j]) * scale);
     }
-    if (gblock != nullptr) staged_section_store(next_slot(), lane, w, gblock + s * 4096, dbg);  // null: group beyond N
+    if (gblock != nullptr) staged_section_store(slot, lane, w, gblock + (s0 + s) * 4096, dbg);  // null: group beyond N
   }
 }
 
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         }
         for (int kb = 0; kb < p.KB; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1);
-          if (p.dbg & 8) {
+          if ((p.dbg & 8) || ((p.dbg & 32) && (kb & 1)) || ((p.dbg & 64) && (kb & 3))) {  // 32: half, 64: quarter of the A traffic
             ptx::mbar_arrive(full_bar(stage));
           } else {
             ptx::mbar_expect_tx(full_bar(stage), A_STAGE_BYTES);
@@ -405,9 +405,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-    const uint32_t stg_base = sStg + (warp - 4) * (SLOTS_PER_WARP * SLOT_BYTES);
-    uint32_t slot_ctr = 0, tile = 0;
+    const int quad = warp & 3;         // TMEM lane quadrant this warp may access
+    const int half = (warp - 4) >> 2;  // which half of the record's sections
+    const uint32_t slot = sStg + (warp - 4) * (SLOTS_PER_WARP * SLOT_BYTES);
+    uint32_t tile = 0;
     for (int b = 0; b < p.B; ++b) {
       const float scale = __ldg(p.epi_scale + b);
       for (long long t = t_begin; t < t_end; ++t, ++tile) {
@@ -420,7 +421,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         const uint32_t t_base = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
         const int grp = qb * (BM / 32) + quad;  // query group of this warp; blocks are ordered [pair][patch][group]
         char* gblock = grp < p.n_groups ? p.pyr + (bp * p.n_groups + grp) * p.group_bytes : nullptr;
-        epilogue_tile<OutT>(t_base, stg_base, slot_ctr, lane, scale, tmem_empty(acc), gblock, p.dbg);
+        epilogue_tile<OutT>(t_base, slot, half, lane, scale, tmem_empty(acc), gblock, p.dbg);
       }
     }
   }

@@ -86,22 +86,24 @@ inline bool pyramid_geom(int H, int W, int L, int dtype, LevelGeom* g) {
 
 // --------------------------------------------------------------------------------------------
 // Correlation-pyramid storage ("subtile-sequence").
-// For one query, level l of the pyramid is an (H>>l) x (W>>l) image.  Every level is cut into 4x8-pixel
-// *subtiles* (64 B in fp16: the unit the lookup gathers, so a (2r+2)^2 window touches few DRAM atoms);
-// the subtiles of all levels form one sequence   s = sub_base[l] + (y/4) * sw_l + (x/8),  sw_l = ceil(w_l/8),
-// and 8 consecutive subtiles are one GEMM *tile*: 256 accumulator columns = one 256-element *record* per
-// query,  column n = (s % 8) * 32 + (y % 4) * 8 + (x % 8).  The pooled levels are ordinary GEMM columns:
+// For one query, level l of the pyramid is an (H>>l) x (W>>l) image.  Every level is cut into 8x8-pixel
+// *subtiles* (128 B in fp16 = one DRAM fetch unit on B200, measured with tools/micro/dram_gran.cu: any
+// access to a 128-byte line costs 128 bytes of DRAM traffic; a (2r+2)^2 = 10x10 window touches on average
+// 4.5 such lines); the subtiles of all levels form one sequence
+//     s = sub_base[l] + (y/8) * sw_l + (x/8),  sw_l = ceil(w_l/8),
+// and 4 consecutive subtiles are one GEMM *tile*: 256 accumulator columns = one 256-element *record* per
+// query,  column n = (s % 4) * 64 + (y % 8) * 8 + (x % 8).  The pooled levels are ordinary GEMM columns:
 // avg-pooling is linear, so level l is the correlation with the l-times pooled fmap2.
 // Queries are taken 32 at a time (one epilogue warp).  For one (pair, tile, query group) the 32 records
 // form a contiguous *group block* of sections; section j holds, for each of the 32 queries, a 128-byte
 // line with record elements [j*EPL, (j+1)*EPL), EPL = 64 (fp16) or 32 (fp32).  Inside a line the 16-byte
 // chunks are XOR-swizzled with the lane index so that the epilogue's shared-memory staging (byte-identical
 // to the global section) is bank-conflict free; 32-byte sectors and 64-byte subtiles are preserved by the
-// XOR (as sets).  Blocks are ordered [pair][tile][group]: one GEMM tile (128 queries x one record) writes 4
+// XOR (as sets), and a subtile is one 128-byte line in fp16 (two in fp32).  Blocks are ordered [pair][tile][group]: one GEMM tile (128 queries x one record) writes 4
 // consecutive blocks = 64 KB (fp16) of contiguous memory.  Pixels outside a level's valid area (and
 // levels >= L) are exact zeros.
 // --------------------------------------------------------------------------------------------
-constexpr int PYR_SY = 4, PYR_SX = 8, PYR_SUB = PYR_SY * PYR_SX, PYR_QG = 32, PYR_MAX_LEVELS = 4, PYR_REC = 256;
+constexpr int PYR_SY = 8, PYR_SX = 8, PYR_SUB = PYR_SY * PYR_SX, PYR_QG = 32, PYR_MAX_LEVELS = 4, PYR_REC = 256;
 constexpr int PYR_SUBS_PER_TILE = PYR_REC / PYR_SUB;
 
 struct PyrLayout {

@@ -50,10 +50,10 @@ int ezb_last_error(char* buf, size_t n);
  *
  * Pyramid storage (the library's choice, "subtile-sequence"): ONE buffer per call holding
  * all levels.  h[l] = H >> l, w[l] = W >> l (floor, F.avg_pool2d default); at most 4 levels.  Level l of
- * a query's correlation map is cut into 4x8-pixel subtiles; the subtiles of all levels form one sequence
- *   s = sub_base[l] + (y/4) * ceil(w[l]/8) + x/8
- * and 8 consecutive subtiles are one 256-element record (= one GEMM tile of 256 accumulator columns):
- *   tile = s / 8,   column = (s % 8) * 32 + (y % 4) * 8 + x % 8.
+ * a query's correlation map is cut into 8x8-pixel subtiles; the subtiles of all levels form one sequence
+ *   s = sub_base[l] + (y/8) * ceil(w[l]/8) + x/8
+ * and 4 consecutive subtiles are one 256-element record (= one GEMM tile of 256 accumulator columns):
+ *   tile = s / 4,   column = (s % 4) * 64 + (y % 8) * 8 + x % 8.
  * Queries (q = h1*W + w1) are grouped 32 at a time.  Each (pair b, tile t, query group g) owns a
  * contiguous *group block* of `group_bytes` at  ((b * n_tiles + t) * n_groups + g) * group_bytes;
  * ezb_corr_pyramid_record_offset() gives the byte offset of a record column inside a block.

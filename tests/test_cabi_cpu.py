@@ -43,15 +43,15 @@ def test_pyramid_layout(lib):
     from ezflow_b200 import _cabi
     from ezflow_b200.similarity.pairwise import PyramidLayout, grad_layout
 
-    # 1080p: floor pooling 135x240 -> 67x120 -> 33x60 -> 16x30, 4x8-pixel subtiles
+    # 1080p: floor pooling 135x240 -> 67x120 -> 33x60 -> 16x30, 8x8-pixel subtiles
     lay = PyramidLayout(135, 240, 4, _cabi.EZB_F16)
     assert lay.levels == [(135, 240), (67, 120), (33, 60), (16, 30)]
-    assert lay.sub_base == [0, 34 * 30, 34 * 30 + 17 * 15, 34 * 30 + 17 * 15 + 9 * 8, 34 * 30 + 17 * 15 + 9 * 8 + 4 * 4]
-    assert (lay.n_tiles, lay.n_groups) == (171, 1013)
-    assert lay.group_bytes == 16384 and lay.pair_bytes == 171 * 1013 * 16384
+    assert lay.sub_base == [0, 17 * 30, 17 * 30 + 9 * 15, 17 * 30 + 9 * 15 + 5 * 8, 17 * 30 + 9 * 15 + 5 * 8 + 2 * 4]
+    assert (lay.n_tiles, lay.n_groups) == (174, 1013)
+    assert lay.group_bytes == 16384 and lay.pair_bytes == 174 * 1013 * 16384
     lay32 = PyramidLayout(46, 62, 4, _cabi.EZB_F32)
     assert lay32.group_bytes == 32768 and lay32.n_groups == 90
-    assert lay32.n_tiles == -(-(12 * 8 + 6 * 4 + 3 * 2 + 2 * 1) // 8)
+    assert lay32.n_tiles == -(-(6 * 8 + 3 * 4 + 2 * 2 + 1 * 1) // 4)
     with pytest.raises(ValueError):
         PyramidLayout(4, 4, 4, 0)  # level 3 would be empty
     with pytest.raises(NotImplementedError):
@@ -65,11 +65,11 @@ def test_pyramid_layout(lib):
                 assert 0 <= off < gb and off % es == 0 and off not in seen
                 seen.add(off)
         assert len(seen) == 32 * 256
-        # a 4x8 subtile (32 consecutive columns) stays inside one 64-byte (fp16) / 128-byte (fp32) atom
+        # an 8x8 subtile (64 consecutive columns) is exactly one (fp16) / two (fp32) 128-byte lines
         for lane in (0, 5, 31):
-            for sub in range(8):
-                offs = [lib.ezb_corr_pyramid_record_offset(dt, lane, sub * 32 + k) for k in range(32)]
-                assert len({o // (32 * es) for o in offs}) == 1
+            for sub in range(4):
+                offs = [lib.ezb_corr_pyramid_record_offset(dt, lane, sub * 64 + k) for k in range(64)]
+                assert len({o // 128 for o in offs}) == es // 2
     assert lib.ezb_corr_pyramid_record_offset(1, 32, 0) == -1
     # every pixel of every level maps to a distinct (tile, column)
     seen = set()
