@@ -20,6 +20,10 @@
 //            one record (256 TMEM columns).  The record operand (128 KB for C=256) stays resident in
 //            shared memory while the CTA sweeps query blocks (A streamed through a 4-stage TMA ring);
 //            two 256-column accumulators double-buffer MMA against the epilogue.
+//            CTAs run as clusters of 2 that sweep the SAME query blocks against two different records:
+//            each CTA fetches half of every A stage and TMA-multicasts it to both, which halves the L2
+//            read traffic of the re-streamed A operand (the kernel is L2-fabric bound otherwise:
+//            profiles/r01_gemm_experiments.md).
 //   epilogue: TMEM -> registers -> (scale) -> fp16/fp32 -> swizzled staging -> coalesced streaming
 //            16-byte stores; a warp writes its 32 queries x 128-byte lines as contiguous 4 KB sections.
 #include "ezb_common.cuh"
@@ -34,12 +38,22 @@ constexpr int BM = 128;           // queries per tile  (UMMA M, TMEM lanes)
 constexpr int BN = PYR_REC;       // record elements   (UMMA N = 256, TMEM columns)
 constexpr int BK = 64;            // fp16 elements per 128-byte swizzle row
 constexpr int KB_MAX = 4;         // resident B k-blocks  (C <= 256)
-constexpr int STAGES = 4;         // A ring
+#ifndef EZB_GEMM_STAGES
+#define EZB_GEMM_STAGES 5
+#endif
+#ifndef EZB_GEMM_EPI_WARPS
+#define EZB_GEMM_EPI_WARPS 4
+#endif
+constexpr int STAGES = EZB_GEMM_STAGES;  // A ring
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
+constexpr int CLUSTER = 2;                   // CTAs sharing one A stream
+constexpr int A_SLICE_ROWS = BM / CLUSTER;   // rows of an A stage each CTA of the cluster fetches (and multicasts)
 constexpr int B_KB_BYTES = BN * BK * 2;      // 32 KB
 constexpr int SLOT_BYTES = 4096;             // one staged section: 32 queries x 128 B
 constexpr int SLOTS_PER_WARP = 1;
-constexpr int EPI_WARPS = 8;                 // two warps per TMEM lane quadrant, each takes half of the record
+constexpr int EPI_WARPS = EZB_GEMM_EPI_WARPS;  // EPI_SPLIT warps per TMEM lane quadrant, each takes 1/EPI_SPLIT of the record
+constexpr int EPI_SPLIT = EPI_WARPS / 4;
+static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "one or two epilogue warps per TMEM lane quadrant");
 constexpr int NUM_THREADS = 128 + EPI_WARPS * 32;
 constexpr int SMEM_B = 0;
 constexpr int SMEM_A = SMEM_B + KB_MAX * B_KB_BYTES;
@@ -248,7 +262,7 @@ template <typename OutT>
 __device__ __forceinline__ void epilogue_tile(uint32_t t_base, uint32_t slot, int half, int lane, float scale,
                                               uint32_t tmem_empty_bar, char* gblock, int dbg) {
   constexpr bool kHalf = sizeof(OutT) == 2;
-  constexpr int kSections = (kHalf ? 4 : 8) / 2;  // sections per warp; 64 / 32 record elements per 128-byte line
+  constexpr int kSections = (kHalf ? 4 : 8) / EPI_SPLIT;  // sections per warp; 64 / 32 record elements per 128-byte line
   constexpr int kLoads = kHalf ? 2 : 1;           // x32 TMEM loads per section
   const int s0 = half * kSections;
   uint32_t r[2][kLoads][32];                      // double-buffered raw accumulator columns
@@ -313,7 +327,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(full_bar(s), 1);
-      ptx::mbar_init(empty_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), CLUSTER);  // the MMA warps of every CTA of the cluster release a stage
     }
     ptx::mbar_init(b_full, 1);
     ptx::mbar_init(b_empty, 1);
@@ -328,16 +342,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  ptx::cluster_sync();  // also a CTA barrier; the peer's mbarriers are initialised before anything lands on them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_slot;
 
   // Pairs are processed one after the other by the whole grid (so the L2 working set is ONE pair's
-  // operands); within a pair every CTA owns a contiguous, balanced range of tiles.
-  // tile t of pair b -> (rec = t / n_qblocks, qb = t % n_qblocks), bp = b * n_recs + rec.
-  const long long tiles_per_pair = (long long)p.n_recs * p.n_qblocks;
-  const long long t_begin = tiles_per_pair * blockIdx.x / gridDim.x;
-  const long long t_end = tiles_per_pair * (blockIdx.x + 1) / gridDim.x;
+  // operands); within a pair every cluster owns a contiguous, balanced range of cluster tiles.
+  // cluster tile t of pair b -> (record group rg = t / n_qblocks, qb = t % n_qblocks); CTA rank r of the
+  // cluster computes record rg * CLUSTER + r (idle columns if that is past the last record).
+  const uint32_t crank = ptx::cluster_ctarank();
+  const int n_clusters = gridDim.x / CLUSTER, cid = blockIdx.x / CLUSTER;
+  const long long tiles_per_pair = (long long)((p.n_recs + CLUSTER - 1) / CLUSTER) * p.n_qblocks;
+  const long long t_begin = tiles_per_pair * cid / n_clusters;
+  const long long t_end = tiles_per_pair * (cid + 1) / n_clusters;
+  constexpr uint16_t kClusterMask = (1u << CLUSTER) - 1;
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
@@ -345,11 +363,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     long long cur_bp = -1;
     for (int b = 0; b < p.B; ++b)
       for (long long t = t_begin; t < t_end; ++t) {
-        const int patch = (int)(t / p.n_qblocks);  // record tile
-        const int qb = (int)(t - (long long)patch * p.n_qblocks);
-        const long long bp = (long long)b * p.n_recs + patch;
+        const int rg = (int)(t / p.n_qblocks);
+        const int qb = (int)(t - (long long)rg * p.n_qblocks);
+        const long long bp = (long long)b * p.n_recs + min(rg * CLUSTER + (int)crank, p.n_recs - 1);
         if (bp != cur_bp) {
-          if (cur_bp >= 0) {  // all MMAs reading the previous patch have completed
+          if (cur_bp >= 0) {  // all MMAs reading the previous record have completed
             ptx::mbar_wait(b_empty, uphase);
             uphase ^= 1;
           }
@@ -360,12 +378,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         }
         for (int kb = 0; kb < p.KB; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1);
-          if ((p.dbg & 8) || ((p.dbg & 32) && (kb & 1)) || ((p.dbg & 64) && (kb & 3))) {  // 32: half, 64: quarter of the A traffic
+          if (p.dbg & 8) {
             ptx::mbar_arrive(full_bar(stage));
           } else {
+            // the whole stage (own slice + the peers' slices) lands on this CTA's barrier
             ptx::mbar_expect_tx(full_bar(stage), A_STAGE_BYTES);
-            // fmap1 is re-read by every patch sweep (170x at 1080p): pin it in L2
-            ptx::tma_load_3d_hint(sA + stage * A_STAGE_BYTES, &tmA, full_bar(stage), kb * BK, qb * BM, b, ptx::kEvictLast);
+            // fmap1 is re-read by every record sweep (87x at 1080p): pin it in L2
+            ptx::tma_load_3d_multicast_hint(sA + stage * A_STAGE_BYTES + crank * (A_SLICE_ROWS * BK * 2), &tmA, full_bar(stage),
+                                            kb * BK, qb * BM + (int)crank * A_SLICE_ROWS, b, kClusterMask, ptx::kEvictLast);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -377,7 +397,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     long long cur_bp = -1;
     for (int b = 0; b < p.B; ++b)
       for (long long t = t_begin; t < t_end; ++t, ++tile) {
-        const long long bp = (long long)b * p.n_recs + t / p.n_qblocks;
+        const long long bp = (long long)b * p.n_recs + min((int)(t / p.n_qblocks) * CLUSTER + (int)crank, p.n_recs - 1);
         if (bp != cur_bp) {
           if (cur_bp >= 0) ptx::umma_commit(b_empty);
           ptx::mbar_wait(b_full, uphase);
@@ -398,7 +418,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             for (int k = 0; k < BK / 16; ++k)  // UMMA_K = 16 fp16 = 32 B = +2 in the descriptor's 16-byte units
               ptx::umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
           }
-          ptx::umma_commit(empty_bar(stage));
+          ptx::umma_commit_multicast(empty_bar(stage), kClusterMask);  // every producer of the cluster writes this stage
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         ptx::umma_commit(tmem_full(acc));
@@ -412,22 +432,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     for (int b = 0; b < p.B; ++b) {
       const float scale = __ldg(p.epi_scale + b);
       for (long long t = t_begin; t < t_end; ++t, ++tile) {
-        const int patch = (int)(t / p.n_qblocks);  // record tile
-        const int qb = (int)(t - (long long)patch * p.n_qblocks);
-        const long long bp = (long long)b * p.n_recs + patch;
+        const int rg = (int)(t / p.n_qblocks);
+        const int qb = (int)(t - (long long)rg * p.n_qblocks);
+        const int rec = rg * CLUSTER + (int)crank;
+        const long long bp = (long long)b * p.n_recs + rec;
         const uint32_t acc = tile & 1, aphase = (tile >> 1) & 1;
         ptx::mbar_wait(tmem_full(acc), aphase);
         ptx::tc_fence_after();
         const uint32_t t_base = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
         const int grp = qb * (BM / 32) + quad;  // query group of this warp; blocks are ordered [pair][patch][group]
-        char* gblock = grp < p.n_groups ? p.pyr + (bp * p.n_groups + grp) * p.group_bytes : nullptr;
+        char* gblock = (grp < p.n_groups && rec < p.n_recs) ? p.pyr + (bp * p.n_groups + grp) * p.group_bytes : nullptr;
         epilogue_tile<OutT>(t_base, slot, half, lane, scale, tmem_empty(acc), gblock, p.dbg);
       }
     }
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  __syncwarp();         // the single-lane roles above rejoin their warps (the cluster barrier is .aligned)
+  ptx::cluster_sync();  // no CTA leaves while a peer may still multicast into it or arrive on its barriers
   if (warp == 2) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
@@ -503,7 +525,7 @@ static int launch_gemm(const Workspace& ws, int B, int C, const PyrLayout& lay, 
   {
     cuuint64_t dims[3] = {(cuuint64_t)Cp, (cuuint64_t)N, (cuuint64_t)B};
     cuuint64_t str[2] = {(cuuint64_t)Cp * 2, (cuuint64_t)N * Cp * 2};
-    cuuint32_t box[3] = {BK, BM, 1};
+    cuuint32_t box[3] = {BK, A_SLICE_ROWS, 1};
     int r = make_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, ws.f1h, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (r) return r;
   }
@@ -530,12 +552,28 @@ static int launch_gemm(const Workspace& ws, int B, int C, const PyrLayout& lay, 
 
   auto kern = corr_pyramid_gemm_kernel<OutT>;
   EZB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  long long grid = num_sms();
-  const long long tiles_per_pair = (long long)p.n_recs * p.n_qblocks;
-  if (grid > tiles_per_pair) grid = tiles_per_pair;
+  // persistent grid = as many clusters as are co-resident (a GPC with an odd SM count leaves one SM out)
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3((unsigned)(num_sms() / CLUSTER * CLUSTER), 1, 1);
+  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int max_clusters = 0;
+  EZB_CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+  if (max_clusters < 1) return fail(EZB_ERR_CUDA, "no cluster of %d CTAs with %d bytes of shared memory fits on this device", CLUSTER, SMEM_BYTES);
+  const long long tiles_per_pair = (long long)cdiv(p.n_recs, CLUSTER) * p.n_qblocks;
+  long long n_clusters = std::min<long long>(max_clusters, num_sms() / CLUSTER);
+  if (n_clusters > tiles_per_pair) n_clusters = tiles_per_pair;
+  cfg.gridDim = dim3((unsigned)(n_clusters * CLUSTER), 1, 1);
   if (ev0) EZB_CUDA_OK(cudaEventRecord(ev0, st));
-  kern<<<(unsigned)grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, p);
-  EZB_LAUNCH_OK();
+  EZB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
   if (ev1) EZB_CUDA_OK(cudaEventRecord(ev1, st));
   return EZB_OK;
 }

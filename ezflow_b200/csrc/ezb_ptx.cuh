@@ -24,6 +24,17 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ------------------------------------------------------------------- cluster
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// all threads of all CTAs of the cluster
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -106,6 +117,16 @@ __device__ __forceinline__ void tma_load_4d_hint(uint32_t dst, const CUtensorMap
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
       : "memory");
 }
+// Multicast variant: the box lands at the same CTA-relative offset in every CTA of `cta_mask`, and each
+// destination CTA's mbarrier (same offset) receives the complete_tx for the bytes written into it.
+__device__ __forceinline__ void tma_load_3d_multicast_hint(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1,
+                                                           int c2, uint16_t cta_mask, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint "
+      "[%0], [%1, {%3, %4, %5}], [%2], %6, %7;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask), "l"(policy)
+      : "memory");
+}
 // contiguous shared -> global bulk copy with an L2 policy (streaming output: evict-first)
 __device__ __forceinline__ void bulk_store_hint(void* gdst, uint32_t src_smem, uint32_t bytes, uint64_t policy) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst), "r"(src_smem),
@@ -170,6 +191,13 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
 // all previously issued tcgen05.mma of this thread arrive on `bar` when complete
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// ... and on the mbarrier at the same CTA-relative offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(cta_mask)
+               : "memory");
 }
 
 // TMEM -> registers: 32 lanes x 32 consecutive fp32 columns (thread i <- lane base+i).
