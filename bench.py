@@ -346,15 +346,12 @@ def run_b200(args):
             d2h = P * L * (2 * R + 1) ** 2 * N * 4
             e2e = (e2e_s, h2d, d2h)
 
-    # max over ranks
-    if world > 1:
-        import torch.distributed as dist
+    # max over ranks (device-timed step and end-to-end wall time)
+    from ezflow_b200.sharding import max_over_ranks
 
-        t = torch.tensor([ms, e2e[0] if e2e else 0.0], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t[0])
-        if e2e:
-            e2e = (float(t[1]), e2e[1], e2e[2])
+    ms, e2e_s = max_over_ranks([ms, e2e[0] if e2e else 0.0], device=dev)
+    if e2e:
+        e2e = (e2e_s, e2e[1], e2e[2])
 
     if rank == 0:
         peaks = load_peaks()
