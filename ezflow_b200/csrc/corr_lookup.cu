@@ -49,6 +49,10 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
                : "l"(p));
   return r;
 }
+// 16-byte asynchronous global -> shared copy, L2-only (.cg); src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ int div3(int v) { return (v * 43691) >> 17; }  // exact for 0 <= v < 98304
 
 // Gather geometry.  A window row is fetched as `ng` aligned 16-byte chunks (VW = 8 fp16 / 4 fp32 pixels of
@@ -64,7 +68,7 @@ struct Gather {
 
 template <typename T>
 __global__ void __launch_bounds__(NTHREADS, 3) corr_lookup_fwd_kernel(const LookupParams P, const int qstride_words) {
-  extern __shared__ uint32_t sm_words[];  // [QB][qstride_words] patches, then [L*QB] int2 item parameters
+  extern __shared__ __align__(16) uint32_t sm_words[];  // [QB][qstride_words] patches, then [L*QB] int2 item parameters
   constexpr int ES = (int)sizeof(T);
   const int r = P.r, D = 2 * r + 2, K = 2 * r + 1, KK = K * K;
   const int b = blockIdx.y, grp = blockIdx.x, q0 = grp * QB;  // QB == PYR_QG: a block serves one query group
@@ -92,57 +96,44 @@ __global__ void __launch_bounds__(NTHREADS, 3) corr_lookup_fwd_kernel(const Look
 
   // ---------------- phase 1: gather windows ----------------
   // task = (window row, chunk); a round = 32 tasks of one (level, query).  In fp16, 30 lanes fetch a whole
-  // (2r+2)^2 window with one 16-byte load each.  A warp keeps the loads of 2 queries x all levels (8 x 512
-  // bytes) in flight before it touches shared memory.  Everything outside a level's valid area is stored
-  // as zero by the GEMM (zero operand rows), and chunks outside the level are written as zeros here, so no
-  // per-element masking is needed.
+  // (2r+2)^2 window with one 16-byte asynchronous copy each (cp.async: global -> shared without a register
+  // round trip), so a warp has the windows of its 4 queries x all levels (16 x 480 bytes) in flight at once.
+  // Everything outside a level's valid area is stored as zero by the GEMM (zero operand rows), and chunks
+  // outside the level are zero-filled here (src-size 0), so no per-element masking is needed.
   using G = Gather<ES>;
   const int ng = G::ng(D), row_el = G::row_el(D);
   const int tasks = D * ng, rounds = (tasks + 31) >> 5;
+  const uint32_t sm_base = (uint32_t)__cvta_generic_to_shared(sm_words);
   for (int rnd = 0; rnd < rounds; ++rnd) {
     const int t = rnd * 32 + lane;
     const int row = (ng == 3) ? div3(t) : (ng == 4) ? t >> 2 : t / ng;
     const int gi = t - row * ng;
     const bool task_ok = t < tasks;
-    uint32_t* const dst_task = sm_words + (row * row_el + gi * G::VW) * ES / 4;
+    const uint32_t dst_task = sm_base + (row * row_el + gi * G::VW) * ES;
 #pragma unroll
-    for (int hq = 0; hq < 2; ++hq) {
-      uint4 wd[2][PYR_MAX_LEVELS];
+    for (int qi = 0; qi < 4; ++qi) {
+      const int ql = warp * 4 + qi;
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int qi = hq * 2 + i, ql = warp * 4 + qi;
-#pragma unroll
-        for (int l = 0; l < PYR_MAX_LEVELS; ++l) {
-          const int ox = __shfl_sync(0xffffffffu, org_mine.x, qi * 4 + l);
-          const int oy = __shfl_sync(0xffffffffu, org_mine.y, qi * 4 + l);
-          wd[i][l] = make_uint4(0u, 0u, 0u, 0u);
-          if (l < P.L && task_ok) {
-            const int y = oy + row;
-            const int xg = (G::chunk_floor(ox) + gi) * G::VW;  // first pixel of the chunk
-            if (y >= 0 && y < (P.H >> l) && xg >= 0 && xg < (P.W >> l)) {
-              const int s = P.sub_base[l] + (y / PYR_SY) * P.sw[l] + xg / PYR_SX;
-              const int col = (s % PYR_SUBS_PER_TILE) * PYR_SUB + (y % PYR_SY) * PYR_SX + xg % PYR_SX;
-              wd[i][l] = ldg_nc_v4(pair_base + (long long)(s / PYR_SUBS_PER_TILE) * tile_stride + pyr_record_offset(ES, ql, col));
-            }
+      for (int l = 0; l < PYR_MAX_LEVELS; ++l) {
+        const int ox = __shfl_sync(0xffffffffu, org_mine.x, qi * 4 + l);
+        const int oy = __shfl_sync(0xffffffffu, org_mine.y, qi * 4 + l);
+        if (l < P.L && task_ok) {
+          const int y = oy + row;
+          const int xg = (G::chunk_floor(ox) + gi) * G::VW;  // first pixel of the chunk
+          const char* src = pair_base;
+          uint32_t nbytes = 0;
+          if (y >= 0 && y < (P.H >> l) && xg >= 0 && xg < (P.W >> l)) {
+            const int s = P.sub_base[l] + (y / PYR_SY) * P.sw[l] + xg / PYR_SX;
+            const int col = (s % PYR_SUBS_PER_TILE) * PYR_SUB + (y % PYR_SY) * PYR_SX + xg % PYR_SX;
+            src = pair_base + (long long)(s / PYR_SUBS_PER_TILE) * tile_stride + pyr_record_offset(ES, ql, col);
+            nbytes = 16;
           }
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int ql = warp * 4 + hq * 2 + i;
-#pragma unroll
-        for (int l = 0; l < PYR_MAX_LEVELS; ++l) {
-          if (l < P.L && task_ok) {
-            uint32_t* dst = dst_task + ql * qstride_words + l * D * row_el * ES / 4;
-            dst[0] = wd[i][l].x;  // the per-query stride is odd (in words): 4-byte stores
-            dst[1] = wd[i][l].y;
-            dst[2] = wd[i][l].z;
-            dst[3] = wd[i][l].w;
-          }
+          cp_async_16(dst_task + ql * (qstride_words * 4) + l * D * row_el * ES, src, nbytes);
         }
       }
     }
   }
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
   // ---------------- phase 2: bilinear taps, lane = query ----------------
@@ -285,8 +276,11 @@ extern "C" int ezb_corr_lookup_fwd(const void* pyramid, const float* deq_scale, 
   const int D = 2 * radius + 2, es = lay.es;
   // per-query window words over all levels (must match Gather<ES> in the kernel)
   const int row_el = es == 2 ? k3::Gather<2>::row_el(D) : k3::Gather<4>::row_el(D);
-  int qwords = L * D * row_el * es / 4;
-  qwords |= 1;  // odd stride: lane = query reads are bank-conflict free
+  // per-query stride: an ODD number of 16-byte chunks (cp.async needs 16-byte alignment; an odd chunk count
+  // spreads the queries over all 8 chunk positions of a 128-byte bank row for the lane = query reads)
+  int qchunks = L * D * row_el * es / 16;
+  qchunks |= 1;
+  const int qwords = qchunks * 4;
   const size_t smem = (size_t)k3::QB * qwords * 4 + (size_t)L * k3::QB * sizeof(int2);
   if (smem > 200 * 1024) return fail(EZB_ERR_UNSUPPORTED, "lookup window too large (L=%d, r=%d)", L, radius);
   cudaStream_t st = static_cast<cudaStream_t>(stream);

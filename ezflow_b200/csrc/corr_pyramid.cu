@@ -82,13 +82,20 @@ __global__ void absmax_kernel(const float* __restrict__ f1, const float* __restr
   const float4* x4 = reinterpret_cast<const float4*>(x);
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   if (vec_ok) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n4; i += 4 * stride) {  // four independent 16-byte loads in flight per thread
+      const float4 a = __ldg(x4 + i), b = __ldg(x4 + i + stride), c = __ldg(x4 + i + 2 * stride), d = __ldg(x4 + i + 3 * stride);
+      m = fmaxf(m, fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
+                         fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)))));
+      m = fmaxf(m, fmaxf(fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fmaxf(fabsf(c.z), fabsf(c.w))),
+                         fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fmaxf(fabsf(d.z), fabsf(d.w)))));
+    }
+    for (; i < n4; i += stride) {
       float4 v = __ldg(x4 + i);
       m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
     }
-    for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_b;
-         i += (long long)gridDim.x * blockDim.x)
-      m = fmaxf(m, fabsf(x[i]));
+    for (long long k = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; k < per_b; k += stride) m = fmaxf(m, fabsf(x[k]));
   } else {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_b; i += (long long)gridDim.x * blockDim.x)
       m = fmaxf(m, fabsf(x[i]));
@@ -658,7 +665,7 @@ extern "C" int ezb_corr_pyramid_fwd_ex(const float* fmap1, const float* fmap2, i
   EZB_CUDA_OK(cudaMemsetAsync(ws.amax, 0, (size_t)2 * B * 4, st));
   {
     const long long per_b = (long long)C * N;
-    int gx = (int)std::min<long long>(cdiv64(per_b, 256 * 16), 4096);
+    int gx = (int)std::min<long long>(cdiv64(per_b, 256 * 64), 4096);  // 16 float4 per thread
     if (gx < 1) gx = 1;
     k1::absmax_kernel<<<dim3(gx, B, 2), 256, 0, st>>>(fmap1, fmap2, per_b, ws.amax, B);
     EZB_LAUNCH_OK();
