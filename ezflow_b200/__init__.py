@@ -14,8 +14,10 @@ from .similarity import (
     MatryoshkaDilatedCostVolume,
     MatryoshkaDilatedCostVolumeList,
     MutliScalePairwise4DCorr,
+    get_local_corr_mode,
     get_pyramid_dtype,
     iter_spatial_correlation_sample,
+    set_local_corr_mode,
     set_pyramid_dtype,
 )
 from .utils import coords_grid, warp

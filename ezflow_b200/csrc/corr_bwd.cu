@@ -4,9 +4,11 @@
 // pairwise.py:26-41, :78-88; closed forms SURVEY.md App. A7):
 //   fold   : dL_{l-1}[2y+a, 2x+b] += dL_l[y,x] / 4      (floor-pool adjoint; dropped rows/cols get 0)
 //   gemms  : df1[b,c,q] = sum_t g[q,t] f2[b,c,t] / sqrt(C),  df2[b,c,t] = sum_q g[q,t] f1[b,c,q] / sqrt(C)
-// Round-1 status: fp32-exact shared-memory-tiled SIMT GEMMs (correctness first); the tcgen05 kind::tf32
-// version that reads the fp32 gradient volume through TMA without a conversion pass is the next step.
+// The GEMMs run on tcgen05 (kind::tf32, corr_bwd_tc.cu) whenever TMA can describe the operands (C <= 256,
+// H*W a multiple of 4); the fp32 shared-memory-tiled SIMT GEMMs below cover the remaining shapes.
 #include "ezb_common.cuh"
+
+#include <cstdlib>
 
 namespace ezb {
 namespace k1b {
@@ -92,6 +94,13 @@ __global__ void __launch_bounds__(256) corr_bwd_gemm_kernel(const float* __restr
 }  // namespace k1b
 }  // namespace ezb
 
+namespace ezb {
+// corr_bwd_tc.cu
+bool corr_bwd_tc_supported(int C, int N, long long g_qstride);
+int corr_bwd_tc_launch(int mode, const float* g, long long g_qstride, const float* F, int B, int C, int N, float alpha, float* out,
+                       cudaStream_t st);
+}  // namespace ezb
+
 using namespace ezb;
 
 extern "C" int ezb_corr_pyramid_bwd(float* const* dlvl_ptrs, const float* fmap1, const float* fmap2, int B, int C, int H,
@@ -112,8 +121,15 @@ extern "C" int ezb_corr_pyramid_bwd(float* const* dlvl_ptrs, const float* fmap1,
                                                    g[l - 1].pitch, g[l - 1].qstride);
     EZB_LAUNCH_OK();
   }
-  k1b::GView G{dlvl_ptrs[0], W, g[0].pitch, g[0].qstride};
   const float alpha = 1.0f / sqrtf((float)C);
+  if (corr_bwd_tc_supported(C, N, g[0].qstride) && getenv("EZB_BWD_SIMT") == nullptr) {
+    if (dfmap1)
+      if (int r = corr_bwd_tc_launch(0, dlvl_ptrs[0], g[0].qstride, fmap2, B, C, N, alpha, dfmap1, st)) return r;
+    if (dfmap2)
+      if (int r = corr_bwd_tc_launch(1, dlvl_ptrs[0], g[0].qstride, fmap1, B, C, N, alpha, dfmap2, st)) return r;
+    return EZB_OK;
+  }
+  k1b::GView G{dlvl_ptrs[0], W, g[0].pitch, g[0].qstride};
   dim3 grid(cdiv(N, k1b::TN), cdiv(C, k1b::TM), B);
   if (dfmap1) {
     k1b::corr_bwd_gemm_kernel<true><<<grid, 256, 0, st>>>(fmap2, G, dfmap1, C, N, alpha);

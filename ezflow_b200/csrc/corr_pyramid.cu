@@ -28,6 +28,7 @@
 //            16-byte stores; a warp writes its 32 queries x 128-byte lines as contiguous 4 KB sections.
 #include "ezb_common.cuh"
 #include "ezb_ptx.cuh"
+#include "ezb_tma.cuh"
 
 #include <cstdlib>
 
@@ -461,33 +462,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 }
 
 // --------------------------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = []() -> EncodeTiledFn {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      return nullptr;
-    return reinterpret_cast<EncodeTiledFn>(f);
-  }();
-  return fn;
-}
-
-static int make_tmap(CUtensorMap* tm, CUtensorMapDataType dt, int rank, void* ptr, const cuuint64_t* dims,
-                     const cuuint64_t* strides_bytes /*rank-1*/, const cuuint32_t* box, CUtensorMapSwizzle swz) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return fail(EZB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(tm, dt, (cuuint32_t)rank, ptr, dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(EZB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-  return EZB_OK;
-}
-
 struct Workspace {
   unsigned int* amax;  // [2][B]
   float* bscale;       // [B]
@@ -586,6 +560,24 @@ static int launch_gemm(const Workspace& ws, int B, int C, const PyrLayout& lay, 
 }
 
 }  // namespace k1
+
+namespace prep {
+int launch_absmax(const float* t0, const float* t1, long long per_b, unsigned int* amax, int B, cudaStream_t st) {
+  EZB_REQUIRE(B <= 65535, "batch too large for one launch (split it)");
+  EZB_CUDA_OK(cudaMemsetAsync(amax, 0, (size_t)2 * B * 4, st));
+  int gx = (int)std::min<long long>(cdiv64(per_b, 256 * 64), 4096);  // 16 float4 per thread
+  if (gx < 1) gx = 1;
+  k1::absmax_kernel<<<dim3(gx, B, 2), 256, 0, st>>>(t0, t1, per_b, amax, B);
+  EZB_LAUNCH_OK();
+  return EZB_OK;
+}
+int launch_convert_kmajor(const float* src, __half* dst, const unsigned int* amax, int B, int C, int Cp, int N, cudaStream_t st) {
+  EZB_REQUIRE(B <= 65535 && Cp % 64 == 0, "bad arguments");
+  k1::convert_kmajor_kernel<<<dim3(cdiv(N, 32), Cp / 64, B), 256, 0, st>>>(src, dst, amax, C, Cp, N);
+  EZB_LAUNCH_OK();
+  return EZB_OK;
+}
+}  // namespace prep
 }  // namespace ezb
 
 using namespace ezb;
@@ -662,19 +654,10 @@ extern "C" int ezb_corr_pyramid_fwd_ex(const float* fmap1, const float* fmap2, i
   const size_t need = k1::ws_layout(B, C, lay, reinterpret_cast<void*>(wbase), &ws) + (wbase - reinterpret_cast<uintptr_t>(workspace));
   if (need > workspace_bytes) return fail(EZB_ERR_WORKSPACE, "workspace too small: need %zu, got %zu", need, workspace_bytes);
 
-  EZB_CUDA_OK(cudaMemsetAsync(ws.amax, 0, (size_t)2 * B * 4, st));
-  {
-    const long long per_b = (long long)C * N;
-    int gx = (int)std::min<long long>(cdiv64(per_b, 256 * 64), 4096);  // 16 float4 per thread
-    if (gx < 1) gx = 1;
-    k1::absmax_kernel<<<dim3(gx, B, 2), 256, 0, st>>>(fmap1, fmap2, per_b, ws.amax, B);
-    EZB_LAUNCH_OK();
-  }
+  if (int r = prep::launch_absmax(fmap1, fmap2, (long long)C * N, ws.amax, B, st)) return r;
   k1::scales_kernel<<<cdiv(B, 128), 128, 0, st>>>(ws.amax, B, C, dtype, ws.bscale, ws.epi, deq_scale);
   EZB_LAUNCH_OK();
-  EZB_REQUIRE(B <= 65535, "batch too large for one launch (split it)");
-  k1::convert_kmajor_kernel<<<dim3(cdiv(N, 32), Cp / 64, B), 256, 0, st>>>(fmap1, ws.f1h, ws.amax, C, Cp, N);
-  EZB_LAUNCH_OK();
+  if (int r = prep::launch_convert_kmajor(fmap1, ws.f1h, ws.amax, B, C, Cp, N, st)) return r;
   k1::PackParams pk;
   for (int l = 0; l < PYR_MAX_LEVELS; ++l) {
     pk.lvl[l] = l == 0 ? fmap2 : ws.f2l[l];

@@ -65,6 +65,14 @@ inline int num_sms() {
   return sms > 0 ? sms : 148;
 }
 
+// fp32 -> fp16 operand preparation shared by the tcgen05 kernels (defined in corr_pyramid.cu)
+namespace prep {
+// amax[which*B + b] = max |t_which[b, :]| as float bits (zeroes amax first); per_b elements per batch entry
+int launch_absmax(const float* t0, const float* t1, long long per_b, unsigned int* amax, int B, cudaStream_t st);
+// fp32 (B,C,N) -> fp16 (B,N,Cp) scaled by 2^-floor(log2(amax[b])) (into (-2,2)); channels >= C zero-filled
+int launch_convert_kmajor(const float* src, __half* dst, const unsigned int* amax, int B, int C, int Cp, int N, cudaStream_t st);
+}  // namespace prep
+
 // Pyramid level geometry shared by K1/K2/K3 (see ezb_corr_pyramid_layout in the header).
 struct LevelGeom {
   int h, w, pitch;
@@ -72,14 +80,16 @@ struct LevelGeom {
 };
 
 inline bool pyramid_geom(int H, int W, int L, int dtype, LevelGeom* g) {
+  // gradient levels: rows packed (pitch = w), per-query stride rounded up to 16 bytes so that a level can be
+  // described to TMA as a 2-D tensor (rows = queries, columns = y*w + x)
   const int es = dtype == EZB_F16 ? 2 : 4;
   const int align = 16 / es;
   for (int l = 0; l < L; ++l) {
     g[l].h = H >> l;
     g[l].w = W >> l;
     if (g[l].h < 1 || g[l].w < 1) return false;
-    g[l].pitch = round_up(g[l].w, align);
-    g[l].qstride = (int64_t)g[l].h * g[l].pitch;
+    g[l].pitch = g[l].w;
+    g[l].qstride = round_up(g[l].h * g[l].w, align);
   }
   return true;
 }

@@ -209,6 +209,15 @@ static int launch_fwd(Params& P, cudaStream_t st) {
 }  // namespace k4
 }  // namespace ezb
 
+namespace ezb {
+// local_corr_tc.cu
+bool local_corr_tc_supported(int C, int sh, int sw, int D);
+size_t local_corr_tc_workspace_bytes(int BG, int C, int H, int W);
+int local_corr_tc_launch(const float* in1, const float* in2, int BG, int G, int C, int H, int W, int Ph, int Pw, int sh, int sw,
+                         int padh, int padw, int D, const int* dph, const int* dpw, float scale, float slope, float* out,
+                         long long out_bstride, void* workspace, size_t workspace_bytes, cudaStream_t st);
+}  // namespace ezb
+
 using namespace ezb;
 
 static int check_local_args(int B, int C, int H, int W, int Ph, int Pw, int sh, int sw, int padh, int padw, int dph, int dpw) {
@@ -218,11 +227,23 @@ static int check_local_args(int B, int C, int H, int W, int Ph, int Pw, int sh, 
   return EZB_OK;
 }
 
+extern "C" int ezb_local_corr_workspace_bytes(int BG, int C, int H, int W, size_t* bytes) {
+  EZB_REQUIRE(BG > 0 && C > 0 && H > 0 && W > 0 && bytes, "bad arguments");
+  *bytes = local_corr_tc_workspace_bytes(BG, C, H, W);
+  return EZB_OK;
+}
+
 extern "C" int ezb_local_corr_fwd(const float* in1, const float* in2, int B, int C, int H, int W, int Ph, int Pw, int sh,
                                   int sw, int padh, int padw, int dph, int dpw, float scale, float slope, float* out,
-                                  int64_t out_batch_stride, void* stream) {
+                                  int64_t out_batch_stride, void* workspace, size_t workspace_bytes, void* stream) {
   EZB_REQUIRE(in1 && in2 && out, "null pointer");
   if (int r = check_local_args(B, C, H, W, Ph, Pw, sh, sw, padh, padw, dph, dpw)) return r;
+  if (workspace != nullptr && local_corr_tc_supported(C, sh, sw, 1)) {
+    const int oh = cdiv(H + 2 * padh, sh), ow = cdiv(W + 2 * padw, sw);
+    return local_corr_tc_launch(in1, in2, B, 1, C, H, W, Ph, Pw, sh, sw, padh, padw, 1, &dph, &dpw, scale, slope, out,
+                                out_batch_stride > 0 ? out_batch_stride : (int64_t)Ph * Pw * oh * ow, workspace, workspace_bytes,
+                                static_cast<cudaStream_t>(stream));
+  }
   k4::Params P;
   P.in1 = in1; P.in2 = in2; P.out = out;
   P.BG = B; P.G = 1; P.C = C; P.H = H; P.W = W;
@@ -235,10 +256,18 @@ extern "C" int ezb_local_corr_fwd(const float* in1, const float* in2, int B, int
 }
 
 extern "C" int ezb_matryoshka_fwd(const float* x1, const float* x2, int B, int G, int Cg, int H, int W, int P_, int stride,
-                                  const int* dil, int D, float slope, float* out, int64_t out_batch_stride, void* stream) {
+                                  const int* dil, int D, float slope, float* out, int64_t out_batch_stride, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
   EZB_REQUIRE(x1 && x2 && out && dil, "null pointer");
   EZB_REQUIRE(G > 0 && D > 0 && D <= k4::MAX_DIL, "bad group/dilation count G=%d D=%d (max %d dilations)", G, D, k4::MAX_DIL);
   if (int r = check_local_args(B, Cg, H, W, P_, P_, stride, stride, 0, 0, 1, 1)) return r;
+  for (int d = 0; d < D; ++d) EZB_REQUIRE(dil[d] > 0, "dilation must be positive");
+  if (workspace != nullptr && local_corr_tc_supported(Cg, stride, stride, D)) {
+    const int oh = cdiv(H, stride), ow = cdiv(W, stride);
+    return local_corr_tc_launch(x1, x2, B * G, G, Cg, H, W, P_, P_, stride, stride, 0, 0, D, dil, dil, 1.f, slope, out,
+                                out_batch_stride > 0 ? out_batch_stride : (int64_t)D * G * P_ * P_ * oh * ow, workspace,
+                                workspace_bytes, static_cast<cudaStream_t>(stream));
+  }
   k4::Params P;
   P.in1 = x1; P.in2 = x2; P.out = out;
   P.BG = B * G; P.G = G; P.C = Cg; P.H = H; P.W = W;

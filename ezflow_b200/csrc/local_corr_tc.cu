@@ -1,0 +1,355 @@
+// K4 / K6 on tensor cores: local displacement-window correlation as a windowed all-pairs tcgen05 GEMM.
+//
+// Replaces iter_spatial_correlation_sample (reference ezflow/similarity/correlation/sampler.py:29-129) and
+// MatryoshkaDilatedCostVolume.forward (ezflow/similarity/learnable_cost.py:306-325) for C <= 256 per group:
+//   out[b,d,g,pi,pj,y,x] = act( scale * sum_c in1p[bg,c,y*sh,x*sw] * in2p[bg,c, y*sh + pi*dph_d - mdh_d, x*sw + pj*dpw_d - mdw_d] )
+//
+// FlowNetC (C=256, 441 displacements) and DCVNet (C=256, 486 displacements) have 60 flop per byte of HBM
+// traffic, far above what CUDA cores sustain, so the contraction runs on tcgen05:
+//   prep    : per-(batch,group) absmax -> power-of-two pre-scale; fp32 (BG,C,H,W) -> fp16 K-major (BG,H,W,Cp)
+//   kernel  : one CTA per 8x16 tile of output pixels ("queries", UMMA M = 128).  The query operand (<= 64 KB)
+//             is TMA-loaded once (strided box for stride > 1, negative coordinates / OOB zero fill implement
+//             the zero padding).  The CTA then sweeps 8x16 tiles of in2 pixels ("targets", UMMA N = 128) over the
+//             bounding box of all displacements of all dilations, clipped to the image, through a 4-stage TMA
+//             ring; 4 TMEM accumulators decouple the MMA warp from the epilogue.
+//   epilogue: lane = query.  The 128 accumulator columns of a tile go TMEM -> registers -> a private row of
+//             shared memory (dynamic column indexing), then every (dilation, pi, pj) whose target falls into this
+//             tile is picked up and stored: for a fixed (pi,pj) the 16 queries of a tile row write 64
+//             contiguous bytes of the (B, D*G, Ph, Pw, oh, ow) output.  Displacements that point outside the
+//             image are written as zeros up front.  Every output element is written exactly once.
+// Only 1/5 to 1/40 of the computed products are kept (the window is a band of the all-pairs matrix), which is
+// still 20-40x faster than fp32 FMAs on CUDA cores for these shapes (profiles/r01_local_corr.md).
+#include "ezb_common.cuh"
+#include "ezb_ptx.cuh"
+#include "ezb_tma.cuh"
+
+#include <climits>
+
+namespace ezb {
+namespace k4tc {
+
+constexpr int QTH = 8, QTW = 16, BM = QTH * QTW;  // query tile  -> UMMA M = 128 (TMEM lanes)
+constexpr int TTH = 8, TTW = 16, BN = TTH * TTW;  // target tile -> UMMA N = 128 (TMEM columns)
+constexpr int BK = 64, KB_MAX = 4;                // C <= 256
+constexpr int STAGES = 4;
+constexpr int A_KB_BYTES = BM * BK * 2;           // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;        // 16 KB
+constexpr int S_STRIDE = BN + 1;                  // words; odd => lane = query accesses are conflict-free
+constexpr int NACC = 4, TMEM_COLS = NACC * BN;    // 512
+constexpr int EPI_WARPS = 8;                      // two per TMEM lane quadrant
+constexpr int NUM_THREADS = 128 + EPI_WARPS * 32;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue
+constexpr int MAX_DIL = 8;
+constexpr int SMEM_A = 0;
+constexpr int SMEM_B = SMEM_A + KB_MAX * A_KB_BYTES;
+constexpr int SMEM_S = SMEM_B + STAGES * B_STAGE_BYTES;
+constexpr int SMEM_BAR = SMEM_S + BM * S_STRIDE * 4;
+constexpr int SMEM_BYTES = SMEM_BAR + 256 + 1024;
+
+struct Params {
+  int G, H, W, oh, ow, Ph, Pw, sh, sw, padh, padw, D, KB;
+  int dph[MAX_DIL], dpw[MAX_DIL];
+  float slope;
+  const float* deq;  // [BG]: user scale * 2^(e1+e2)
+  float* out;
+  long long out_bstride;
+};
+
+__global__ void tc_scales_kernel(const unsigned int* __restrict__ amax, int BG, float scale, float* __restrict__ deq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= BG) return;
+  auto ex = [](unsigned int bits) {
+    const int e = (int)((bits >> 23) & 0xff);
+    return e == 0 ? 0 : e - 127;
+  };
+  int e = ex(amax[i]) + ex(amax[BG + i]);
+  e = max(-126, min(126, e));
+  deq[i] = scale * __uint_as_float((unsigned int)(e + 127) << 23);
+}
+
+__device__ __forceinline__ int floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }  // b > 0
+__device__ __forceinline__ int ceil_div(int a, int b) { return -floor_div(-a, b); }
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+    local_corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw_addr);
+  const uint32_t sA = base + SMEM_A, sB = base + SMEM_B, sBar = base + SMEM_BAR;
+  float* S = reinterpret_cast<float*>(base_ptr + SMEM_S);
+  auto full_bar = [&](int s) { return sBar + 8u * s; };
+  auto empty_bar = [&](int s) { return sBar + 8u * (STAGES + s); };
+  const uint32_t a_full = sBar + 8u * (2 * STAGES);
+  auto tmem_full = [&](int a) { return sBar + 8u * (2 * STAGES + 1 + a); };
+  auto tmem_empty = [&](int a) { return sBar + 8u * (2 * STAGES + 1 + NACC + a); };
+  volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + SMEM_BAR + 8 * (2 * STAGES + 1 + 2 * NACC));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qx0 = blockIdx.x * QTW, qy0 = blockIdx.y * QTH, bg = blockIdx.z;
+
+  // bounding box (in2 pixel coordinates, clipped to the image) of every target any query of this tile needs
+  int mdh_max = 0, mdw_max = 0;
+  for (int d = 0; d < P.D; ++d) {
+    mdh_max = max(mdh_max, P.dph[d] * (P.Ph - 1) / 2);
+    mdw_max = max(mdw_max, P.dpw[d] * (P.Pw - 1) / 2);
+  }
+  const int y_lo = max(0, qy0 * P.sh - P.padh - mdh_max);
+  const int y_hi = min(P.H - 1, (min(qy0 + QTH, P.oh) - 1) * P.sh - P.padh + mdh_max);
+  const int x_lo = max(0, qx0 * P.sw - P.padw - mdw_max);
+  const int x_hi = min(P.W - 1, (min(qx0 + QTW, P.ow) - 1) * P.sw - P.padw + mdw_max);
+  const int nty = y_hi >= y_lo ? (y_hi - y_lo) / TTH + 1 : 0;
+  const int ntx = x_hi >= x_lo ? (x_hi - x_lo) / TTW + 1 : 0;
+  const int ntiles = nty * ntx;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    ptx::mbar_init(a_full, 1);
+    for (int a = 0; a < NACC; ++a) {
+      ptx::mbar_init(tmem_full(a), 1);
+      ptx::mbar_init(tmem_empty(a), EPI_WARPS);  // one arrive per epilogue warp
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_ptr_slot)), TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    if (ntiles > 0) {
+      ptx::mbar_expect_tx(a_full, (uint32_t)(P.KB * A_KB_BYTES));
+      for (int kb = 0; kb < P.KB; ++kb)
+        ptx::tma_load_4d_hint(sA + kb * A_KB_BYTES, &tmA, a_full, kb * BK, qx0 * P.sw - P.padw, qy0 * P.sh - P.padh, bg,
+                              ptx::kEvictFirst);
+    }
+    uint32_t stage = 0, phase = 0;
+    for (int tt = 0; tt < ntiles; ++tt) {
+      const int ty0 = y_lo + (tt / ntx) * TTH, tx0 = x_lo + (tt % ntx) * TTW;
+      for (int kb = 0; kb < P.KB; ++kb) {
+        ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+        ptx::mbar_expect_tx(full_bar(stage), B_STAGE_BYTES);
+        // in2 windows of neighbouring query tiles overlap heavily: keep them in L2
+        ptx::tma_load_4d_hint(sB + stage * B_STAGE_BYTES, &tmB, full_bar(stage), kb * BK, tx0, ty0, bg, ptx::kEvictLast);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = ptx::umma_idesc(/*f16*/ 0, BM, BN);
+    uint32_t stage = 0, phase = 0;
+    if (ntiles > 0) {
+      ptx::mbar_wait(a_full, 0);
+      ptx::tc_fence_after();
+    }
+    for (int tt = 0; tt < ntiles; ++tt) {
+      const uint32_t acc = tt % NACC, aphase = (tt / NACC) & 1;
+      ptx::mbar_wait(tmem_empty(acc), aphase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < P.KB; ++kb) {
+        ptx::mbar_wait(full_bar(stage), phase);
+        ptx::tc_fence_after();
+        const uint64_t a_desc = ptx::umma_desc_kmajor_sw128(sA + kb * A_KB_BYTES);
+        const uint64_t b_desc = ptx::umma_desc_kmajor_sw128(sB + stage * B_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) ptx::umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+        ptx::umma_commit(empty_bar(stage));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      ptx::umma_commit(tmem_full(acc));
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: lane = query =====================
+    // Two warps share a TMEM lane quadrant (= 32 queries): each drains half of the accumulator columns into
+    // the queries' shared-memory rows, then they split the displacement rows (pi) between them.
+    const int quad = warp & 3, half = (warp - 4) >> 2;
+    const int q = quad * 32 + lane;
+    const int oy = qy0 + q / QTW, ox = qx0 + q % QTW;
+    const bool q_ok = oy < P.oh && ox < P.ow;
+    const int b = bg / P.G, g = bg - b * P.G;
+    const float deq = __ldg(P.deq + bg);
+    const long long plane = (long long)P.oh * P.ow;
+    float* out_q = P.out + (long long)b * P.out_bstride + (long long)oy * P.ow + ox;
+    float* Srow = S + q * S_STRIDE;
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory"); };
+
+    // displacements that point outside the image: zeros (act(0) = 0), written once, up front
+    if (q_ok) {
+      for (int d = 0; d < P.D; ++d) {
+        const int dph = P.dph[d], dpw = P.dpw[d];
+        const int y2_0 = oy * P.sh - P.padh - dph * (P.Ph - 1) / 2, x2_0 = ox * P.sw - P.padw - dpw * (P.Pw - 1) / 2;
+        float* o = out_q + (long long)(d * P.G + g) * P.Ph * P.Pw * plane;
+        for (int a = half; a < P.Ph; a += 2) {
+          const int y2 = y2_0 + a * dph;
+          const bool row_in = y2 >= 0 && y2 < P.H;
+          for (int bb = 0; bb < P.Pw; ++bb) {
+            const int x2 = x2_0 + bb * dpw;
+            if (!(row_in && x2 >= 0 && x2 < P.W)) o[(long long)(a * P.Pw + bb) * plane] = 0.f;
+          }
+        }
+      }
+    }
+
+    for (int tt = 0; tt < ntiles; ++tt) {
+      const int ty0 = y_lo + (tt / ntx) * TTH, tx0 = x_lo + (tt % ntx) * TTW;
+      const int ty1 = min(ty0 + TTH, P.H) - 1, tx1 = min(tx0 + TTW, P.W) - 1;  // last in-image row / column of the tile
+      const uint32_t acc = tt % NACC, aphase = (tt / NACC) & 1;
+      ptx::mbar_wait(tmem_full(acc), aphase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16) + half * (BN / 2);
+      {
+        uint32_t r0[32], r1[32];
+        ptx::tmem_ld_32x32b_x32(taddr, r0);
+        ptx::tmem_ld_32x32b_x32(taddr + 32, r1);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(tmem_empty(acc));  // the accumulator is in registers: release it early
+        float* dst = Srow + half * (BN / 2);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dst[j] = __uint_as_float(r0[j]);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dst[32 + j] = __uint_as_float(r1[j]);
+      }
+      pair_sync();  // both halves of the rows are in shared memory
+
+      for (int d = 0; d < P.D; ++d) {
+        const int dph = P.dph[d], dpw = P.dpw[d];
+        const int y2_0 = oy * P.sh - P.padh - dph * (P.Ph - 1) / 2, x2_0 = ox * P.sw - P.padw - dpw * (P.Pw - 1) / 2;
+        // this lane's displacement ranges whose target lies in the in-image part of the tile
+        int a_lo = max(0, ceil_div(ty0 - y2_0, dph)), a_hi = min(P.Ph - 1, floor_div(ty1 - y2_0, dph));
+        int b_lo = max(0, ceil_div(tx0 - x2_0, dpw)), b_hi = min(P.Pw - 1, floor_div(tx1 - x2_0, dpw));
+        if (!q_ok || a_lo > a_hi || b_lo > b_hi) { a_lo = b_lo = INT_MAX; a_hi = b_hi = INT_MIN; }
+        // all lanes walk the union so that a store instruction covers one (pi, pj): contiguous output pixels
+        const int ua_lo = __reduce_min_sync(0xffffffffu, a_lo), ua_hi = __reduce_max_sync(0xffffffffu, a_hi);
+        const int ub_lo = __reduce_min_sync(0xffffffffu, b_lo), ub_hi = __reduce_max_sync(0xffffffffu, b_hi);
+        if (ua_lo > ua_hi) continue;
+        float* o = out_q + (long long)(d * P.G + g) * P.Ph * P.Pw * plane;
+        for (int a = ua_lo + ((ua_lo ^ half) & 1); a <= ua_hi; a += 2) {  // rows with a % 2 == half
+          const bool row_ok = a >= a_lo && a <= a_hi;
+          const float* srow = Srow + (y2_0 + a * dph - ty0) * TTW + (x2_0 - tx0);
+          float* orow = o + (long long)a * P.Pw * plane;
+          for (int bb = ub_lo; bb <= ub_hi; bb += 4) {  // 4 independent load -> store chains in flight
+            float v[4];
+            bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              ok[u] = row_ok && bb + u >= b_lo && bb + u <= b_hi;
+              v[u] = ok[u] ? srow[(bb + u) * dpw] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float w = v[u] * deq;
+              w = w >= 0.f ? w : w * P.slope;
+              if (ok[u]) orow[(long long)(bb + u) * plane] = w;
+            }
+          }
+        }
+      }
+      pair_sync();  // both warps are done with the rows before the next tile overwrites them
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+struct Workspace {
+  unsigned int* amax;  // [2][BG]
+  float* deq;          // [BG]
+  __half* in1h;        // (BG, H, W, Cp)
+  __half* in2h;
+};
+
+static size_t ws_layout(int BG, int C, int H, int W, void* base, Workspace* ws) {
+  const int Cp = round_up(C, BK);
+  uintptr_t p = reinterpret_cast<uintptr_t>(base);
+  auto take = [&](size_t bytes, size_t align) {
+    p = (p + align - 1) / align * align;
+    uintptr_t r = p;
+    p += bytes;
+    return r;
+  };
+  const uintptr_t amax = take((size_t)2 * BG * 4, 256);
+  const uintptr_t deq = take((size_t)BG * 4, 256);
+  const uintptr_t a = take((size_t)BG * H * W * Cp * 2, 1024);
+  const uintptr_t b = take((size_t)BG * H * W * Cp * 2, 1024);
+  if (ws) {
+    ws->amax = reinterpret_cast<unsigned int*>(amax);
+    ws->deq = reinterpret_cast<float*>(deq);
+    ws->in1h = reinterpret_cast<__half*>(a);
+    ws->in2h = reinterpret_cast<__half*>(b);
+  }
+  return p - reinterpret_cast<uintptr_t>(base);
+}
+
+}  // namespace k4tc
+
+// true when the tensor-core kernel covers this problem (otherwise the exact fp32 SIMT kernel runs)
+bool local_corr_tc_supported(int C, int sh, int sw, int D) {
+  return C <= k4tc::KB_MAX * k4tc::BK && sh <= 8 && sw <= 8 && D <= k4tc::MAX_DIL;
+}
+
+size_t local_corr_tc_workspace_bytes(int BG, int C, int H, int W) { return k4tc::ws_layout(BG, C, H, W, nullptr, nullptr) + 1024; }
+
+int local_corr_tc_launch(const float* in1, const float* in2, int BG, int G, int C, int H, int W, int Ph, int Pw, int sh, int sw,
+                         int padh, int padw, int D, const int* dph, const int* dpw, float scale, float slope, float* out,
+                         long long out_bstride, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  using namespace k4tc;
+  const int Cp = round_up(C, BK), N = H * W;
+  uintptr_t wbase = (reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023);
+  Workspace ws;
+  const size_t need = ws_layout(BG, C, H, W, reinterpret_cast<void*>(wbase), &ws) + (wbase - reinterpret_cast<uintptr_t>(workspace));
+  if (need > workspace_bytes) return fail(EZB_ERR_WORKSPACE, "workspace too small: need %zu, got %zu", need, workspace_bytes);
+  EZB_REQUIRE(BG <= 65535, "batch too large for one launch (split it)");
+
+  if (int r = prep::launch_absmax(in1, in2, (long long)C * N, ws.amax, BG, st)) return r;
+  tc_scales_kernel<<<cdiv(BG, 128), 128, 0, st>>>(ws.amax, BG, scale, ws.deq);
+  EZB_LAUNCH_OK();
+  if (int r = prep::launch_convert_kmajor(in1, ws.in1h, ws.amax, BG, C, Cp, N, st)) return r;
+  if (int r = prep::launch_convert_kmajor(in2, ws.in2h, ws.amax + BG, BG, C, Cp, N, st)) return r;
+
+  CUtensorMap tmA, tmB;
+  cuuint64_t dims[4] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)BG};
+  cuuint64_t str[3] = {(cuuint64_t)Cp * 2, (cuuint64_t)W * Cp * 2, (cuuint64_t)H * W * Cp * 2};
+  {
+    cuuint32_t box[4] = {BK, (cuuint32_t)(QTW * sw), (cuuint32_t)(QTH * sh), 1};
+    cuuint32_t es[4] = {1, (cuuint32_t)sw, (cuuint32_t)sh, 1};
+    if (int r = make_tmap_ex(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, ws.in1h, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B)) return r;
+  }
+  {
+    cuuint32_t box[4] = {BK, TTW, TTH, 1};
+    if (int r = make_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, ws.in2h, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return r;
+  }
+  Params P;
+  P.G = G; P.H = H; P.W = W;
+  P.oh = cdiv(H + 2 * padh, sh); P.ow = cdiv(W + 2 * padw, sw);
+  P.Ph = Ph; P.Pw = Pw; P.sh = sh; P.sw = sw; P.padh = padh; P.padw = padw;
+  P.D = D; P.KB = Cp / BK;
+  for (int d = 0; d < D; ++d) { P.dph[d] = dph[d]; P.dpw[d] = dpw[d]; }
+  P.slope = slope;
+  P.deq = ws.deq;
+  P.out = out;
+  P.out_bstride = out_bstride;
+  dim3 grid(cdiv(P.ow, QTW), cdiv(P.oh, QTH), BG);
+  EZB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "output too large for one launch");
+  EZB_CUDA_OK(cudaFuncSetAttribute(local_corr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  local_corr_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, P);
+  EZB_LAUNCH_OK();
+  return EZB_OK;
+}
+
+}  // namespace ezb

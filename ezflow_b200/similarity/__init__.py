@@ -2,7 +2,7 @@ from ..registry import SIMILARITY_REGISTRY, build_similarity
 from .layer import CorrelationLayer
 from .matryoshka import MatryoshkaDilatedCostVolume, MatryoshkaDilatedCostVolumeList
 from .pairwise import MutliScalePairwise4DCorr, get_pyramid_dtype, set_pyramid_dtype
-from .sampler import IterSpatialCorrelationSampler, iter_spatial_correlation_sample
+from .sampler import IterSpatialCorrelationSampler, get_local_corr_mode, iter_spatial_correlation_sample, set_local_corr_mode
 
 __all__ = [
     "SIMILARITY_REGISTRY",
@@ -15,4 +15,6 @@ __all__ = [
     "iter_spatial_correlation_sample",
     "set_pyramid_dtype",
     "get_pyramid_dtype",
+    "set_local_corr_mode",
+    "get_local_corr_mode",
 ]

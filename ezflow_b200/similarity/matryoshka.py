@@ -17,7 +17,7 @@ from .. import _cabi
 from ..config import configurable
 from ..registry import SIMILARITY_REGISTRY
 from .sampler import IterSpatialCorrelationSampler as SpatialCorrelationSampler
-from .sampler import local_corr_backward
+from .sampler import local_corr_backward, local_corr_workspace
 
 
 def _matryoshka_forward(x1, x2, G, P, stride, dilations, slope, out=None, ch_offset=0):
@@ -29,10 +29,11 @@ def _matryoshka_forward(x1, x2, G, P, stride, dilations, slope, out=None, ch_off
     view = out[:, ch_offset : ch_offset + D * G]
     dil = (ctypes.c_int * D)(*[int(d) for d in dilations])
     with torch.cuda.device(x1.device):
+        ws, nws = local_corr_workspace(B * G, C // G, H, W, x1.device)
         _cabi.check(
             _cabi.lib().ezb_matryoshka_fwd(
                 _cabi.ptr(x1), _cabi.ptr(x2), B, G, C // G, H, W, P, stride, dil, D, float(slope),
-                ctypes.c_void_p(view.data_ptr()), int(out.stride(0)), _cabi.stream_ptr(x1.device),
+                ctypes.c_void_p(view.data_ptr()), int(out.stride(0)), _cabi.ptr(ws), nws, _cabi.stream_ptr(x1.device),
             )
         )
     return out

@@ -5,6 +5,8 @@ ezflow/similarity/correlation/sampler.py:29-209): same parameters, same ``NotImp
 kernel_size != 1, dilation != 1 and even patch sizes, output (B, P_h, P_w, h', w') contiguous fp32.
 """
 
+import ctypes
+import os
 from typing import Tuple, Union
 
 import torch
@@ -25,17 +27,44 @@ def _out_hw(H, W, stride, padding):
     return -(-(H + 2 * padding[0]) // stride[0]), -(-(W + 2 * padding[1]) // stride[1])
 
 
+_LOCAL_CORR_MODE = os.environ.get("EZB_LOCAL_CORR", "tc").lower()
+
+
+def set_local_corr_mode(name):
+    """'tc' (default): tcgen05 tensor cores, fp16 operands / fp32 accumulation, <= 1e-3 relative error;
+    'exact': fp32 CUDA-core kernel (bit-for-bit fp32 FMA sums)."""
+    global _LOCAL_CORR_MODE
+    name = str(name).lower()
+    if name not in ("tc", "exact"):
+        raise ValueError("local correlation mode must be 'tc' or 'exact'")
+    _LOCAL_CORR_MODE = name
+
+
+def get_local_corr_mode():
+    return _LOCAL_CORR_MODE
+
+
+def local_corr_workspace(BG, C, H, W, device):
+    """Scratch for the tensor-core path (fp16 K-major operand copies + scales), or (None, 0) in 'exact' mode."""
+    if _LOCAL_CORR_MODE != "tc":
+        return None, 0
+    n = ctypes.c_size_t(0)
+    _cabi.check(_cabi.lib().ezb_local_corr_workspace_bytes(BG, C, H, W, ctypes.byref(n)))
+    return torch.empty(n.value, dtype=torch.uint8, device=device), n.value
+
+
 def local_corr_forward(in1, in2, patch, stride, padding, dpatch, scale=1.0, slope=1.0, out=None, out_batch_stride=0):
     B, C, H, W = in1.shape
     oh, ow = _out_hw(H, W, stride, padding)
     if out is None:
         out = torch.empty((B, patch[0], patch[1], oh, ow), dtype=torch.float32, device=in1.device)
     with torch.cuda.device(in1.device):
+        ws, nws = local_corr_workspace(B, C, H, W, in1.device)
         _cabi.check(
             _cabi.lib().ezb_local_corr_fwd(
                 _cabi.ptr(in1), _cabi.ptr(in2), B, C, H, W, patch[0], patch[1], stride[0], stride[1], padding[0], padding[1],
                 dpatch[0], dpatch[1], float(scale), float(slope), _cabi.ptr(out), int(out_batch_stride),
-                _cabi.stream_ptr(in1.device),
+                _cabi.ptr(ws), nws, _cabi.stream_ptr(in1.device),
             )
         )
     return out

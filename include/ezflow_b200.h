@@ -104,9 +104,10 @@ int ezb_corr_lookup_fwd(const void* pyramid, const float* deq_scale /*[B]*/,
                         int B, int H, int W, int L, int radius, int dtype,
                         float* out, void* stream);
 
-/* Gradient levels are separate fp32 buffers, row-major per query with a 16-byte row pitch:
- * element (b,q,y,x) of level l at ((b*N+q)*h[l] + y)*pitch[l] + x, pitch[l] = w[l] rounded up to 4
- * (ezb_corr_grad_layout).  The lookup adjoint accumulates into them (+=). */
+/* Gradient levels are separate fp32 buffers, row-major per query: element (b,q,y,x) of level l at
+ * (b*N+q)*qstride[l] + y*pitch[l] + x with pitch[l] = w[l] and qstride[l] = h[l]*w[l] rounded up to 4 (a 16-byte
+ * aligned row per query, so TMA can read a level as a 2-D tensor) (ezb_corr_grad_layout).
+ * The lookup adjoint accumulates into them (+=). */
 int ezb_corr_grad_layout(int H, int W, int L, int* h, int* w, int* pitch, int64_t* qstride /*[L] host*/);
 int ezb_corr_lookup_bwd(const float* dout /* (B, L*(2r+1)^2, H, W) */, const float* coords,
                         int B, int H, int W, int L, int radius,
@@ -124,10 +125,17 @@ int ezb_corr_pyramid_bwd(float* const* dlvl_ptrs /*[L] host*/, const float* fmap
  *   in*p = inputs zero-padded by (padh,padw); md = dp*(P-1)/2; out (B,Ph,Pw,oh,ow),
  *   oh = ceil((H+2*padh)/sh), ow likewise.  act = leaky_relu(slope) (slope 1 = identity).
  *   `out_batch_stride` (elements) lets K6 write straight into a slice of the concatenated volume.
+ *   With a workspace of ezb_local_corr_workspace_bytes() (and C <= 256 per group, stride <= 8) the
+ *   contraction runs on tcgen05 tensor cores with fp16 operands / fp32 accumulation (<= 1e-3 relative,
+ *   the north_star tolerance for cost volumes); with workspace == NULL the exact fp32 CUDA-core kernel
+ *   runs (any C, any stride).
  * ------------------------------------------------------------------------------------------- */
+int ezb_local_corr_workspace_bytes(int BG /* batch * groups */, int C /* per group */, int H, int W, size_t* bytes /*host*/);
+
 int ezb_local_corr_fwd(const float* in1, const float* in2, int B, int C, int H, int W,
                        int Ph, int Pw, int sh, int sw, int padh, int padw, int dph, int dpw,
-                       float scale, float slope, float* out, int64_t out_batch_stride, void* stream);
+                       float scale, float slope, float* out, int64_t out_batch_stride,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 int ezb_local_corr_bwd(const float* in1, const float* in2, const float* dout, int B, int C, int H, int W,
                        int Ph, int Pw, int sh, int sw, int padh, int padw, int dph, int dpw,
@@ -142,7 +150,7 @@ int ezb_local_corr_bwd(const float* in1, const float* in2, const float* dout, in
  * ------------------------------------------------------------------------------------------- */
 int ezb_matryoshka_fwd(const float* x1, const float* x2, int B, int G, int Cg, int H, int W,
                        int P, int stride, const int* dil /*[D] host*/, int D, float slope,
-                       float* out, int64_t out_batch_stride, void* stream);
+                       float* out, int64_t out_batch_stride, void* workspace, size_t workspace_bytes, void* stream);
 
 /* x / (||x||_2 over channels + eps)   learnable_cost.py:426-428 */
 int ezb_l2_normalize_fwd(const float* x, int B, int C, int HW, float eps, float* out, void* stream);

@@ -81,7 +81,7 @@ def test_pyramid_layout(lib):
         assert len(pairs) == h * w and not (pairs & seen)
         seen |= pairs
     g = grad_layout(46, 62, 4)
-    assert [(h, w, p) for h, w, p, _ in g] == [(46, 62, 64), (23, 31, 32), (11, 15, 16), (5, 7, 8)]
+    assert [(h, w, p, qs) for h, w, p, qs in g] == [(46, 62, 62, 2852), (23, 31, 31, 716), (11, 15, 15, 168), (5, 7, 7, 36)]
 
 
 def test_argument_validation_without_gpu(lib):
@@ -91,7 +91,7 @@ def test_argument_validation_without_gpu(lib):
     assert lib.ezb_corr_lookup_fwd(None, None, None, 1, 8, 8, 1, 4, 0, None, None) == -1
     one = ctypes.c_void_p(16)
     # even patch size -> unsupported, same message as the reference (sampler.py:93-94)
-    rc = lib.ezb_local_corr_fwd(one, one, 1, 2, 4, 4, 4, 4, 1, 1, 0, 0, 1, 1, 1.0, 1.0, one, 0, None)
+    rc = lib.ezb_local_corr_fwd(one, one, 1, 2, 4, 4, 4, 4, 1, 1, 0, 0, 1, 1, 1.0, 1.0, one, 0, None, 0, None)
     assert rc == -2 and "odd patch sizes" in _cabi.last_error()
     with pytest.raises(NotImplementedError):
         _cabi.check(rc)
