@@ -4,8 +4,8 @@
 // pairwise.py:26-41, :78-88; closed forms SURVEY.md App. A7):
 //   fold   : dL_{l-1}[2y+a, 2x+b] += dL_l[y,x] / 4      (floor-pool adjoint; dropped rows/cols get 0)
 //   gemms  : df1[b,c,q] = sum_t g[q,t] f2[b,c,t] / sqrt(C),  df2[b,c,t] = sum_q g[q,t] f1[b,c,q] / sqrt(C)
-// The GEMMs run on tcgen05 (kind::tf32, corr_bwd_tc.cu) whenever TMA can describe the operands (C <= 256,
-// H*W a multiple of 4); the fp32 shared-memory-tiled SIMT GEMMs below cover the remaining shapes.
+// With a workspace, C <= 256 and H*W a multiple of 4 everything runs on tcgen05 (kind::tf32, corr_bwd_tc.cu) without
+// folding; the fold kernel and the fp32 shared-memory-tiled SIMT GEMMs below cover the remaining shapes.
 #include "ezb_common.cuh"
 
 #include <cstdlib>
@@ -96,15 +96,24 @@ __global__ void __launch_bounds__(256) corr_bwd_gemm_kernel(const float* __restr
 
 namespace ezb {
 // corr_bwd_tc.cu
-bool corr_bwd_tc_supported(int C, int N, long long g_qstride);
-int corr_bwd_tc_launch(int mode, const float* g, long long g_qstride, const float* F, int B, int C, int N, float alpha, float* out,
+bool corr_bwd_tc_supported(int C, int N);
+size_t corr_bwd_tc_workspace_bytes(int B, int C, int H, int W, int L);
+int corr_bwd_tc_launch(float* const* dlvl, const long long* qstride, const float* fmap1, const float* fmap2, int B, int C, int H,
+                       int W, int L, float alpha, float* dfmap1, float* dfmap2, void* workspace, size_t workspace_bytes,
                        cudaStream_t st);
 }  // namespace ezb
 
 using namespace ezb;
 
+extern "C" int ezb_corr_pyramid_bwd_workspace_bytes(int B, int C, int H, int W, int L, size_t* bytes) {
+  EZB_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && L >= 1 && L <= EZB_MAX_LEVELS && bytes, "bad arguments");
+  *bytes = (L <= 4 && corr_bwd_tc_supported(C, H * W)) ? corr_bwd_tc_workspace_bytes(B, C, H, W, L) : 0;
+  return EZB_OK;
+}
+
 extern "C" int ezb_corr_pyramid_bwd(float* const* dlvl_ptrs, const float* fmap1, const float* fmap2, int B, int C, int H,
-                                    int W, int L, float* dfmap1, float* dfmap2, void* stream) {
+                                    int W, int L, float* dfmap1, float* dfmap2, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
   EZB_REQUIRE(dlvl_ptrs && fmap1 && fmap2 && (dfmap1 || dfmap2), "null pointer");
   EZB_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && L >= 1 && L <= EZB_MAX_LEVELS, "bad shape B=%d C=%d H=%d W=%d L=%d", B, C,
               H, W, L);
@@ -114,20 +123,19 @@ extern "C" int ezb_corr_pyramid_bwd(float* const* dlvl_ptrs, const float* fmap1,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int N = H * W;
   const long long rows = (long long)B * N;
+  const float alpha = 1.0f / sqrtf((float)C);
+  if (workspace != nullptr && L <= 4 && corr_bwd_tc_supported(C, N) && getenv("EZB_BWD_SIMT") == nullptr) {
+    // tensor cores, no fold: the K loop of the df1 GEMM runs over the targets of all levels (corr_bwd_tc.cu)
+    long long qs[EZB_MAX_LEVELS];
+    for (int l = 0; l < L; ++l) qs[l] = g[l].qstride;
+    return corr_bwd_tc_launch(dlvl_ptrs, qs, fmap1, fmap2, B, C, H, W, L, alpha, dfmap1, dfmap2, workspace, workspace_bytes, st);
+  }
   for (int l = L - 1; l >= 1; --l) {
     const long long total = rows * g[l].h * g[l].w;
     const int blocks = (int)std::min<long long>(cdiv64(total, 256), 148 * 32);
     k1b::fold_level_kernel<<<blocks, 256, 0, st>>>(dlvl_ptrs[l], dlvl_ptrs[l - 1], rows, g[l].h, g[l].w, g[l].pitch, g[l].qstride,
                                                    g[l - 1].pitch, g[l - 1].qstride);
     EZB_LAUNCH_OK();
-  }
-  const float alpha = 1.0f / sqrtf((float)C);
-  if (corr_bwd_tc_supported(C, N, g[0].qstride) && getenv("EZB_BWD_SIMT") == nullptr) {
-    if (dfmap1)
-      if (int r = corr_bwd_tc_launch(0, dlvl_ptrs[0], g[0].qstride, fmap2, B, C, N, alpha, dfmap1, st)) return r;
-    if (dfmap2)
-      if (int r = corr_bwd_tc_launch(1, dlvl_ptrs[0], g[0].qstride, fmap1, B, C, N, alpha, dfmap2, st)) return r;
-    return EZB_OK;
   }
   k1b::GView G{dlvl_ptrs[0], W, g[0].pitch, g[0].qstride};
   dim3 grid(cdiv(N, k1b::TN), cdiv(C, k1b::TM), B);

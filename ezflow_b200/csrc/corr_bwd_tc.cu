@@ -2,9 +2,13 @@
 //
 // Autograd of MutliScalePairwise4DCorr.corr (reference ezflow/similarity/correlation/pairwise.py:78-88):
 //   df1[b,c,q] = sum_t g[b,q,t] f2[b,c,t] / sqrt(C)        df2[b,c,t] = sum_q g[b,q,t] f1[b,c,q] / sqrt(C)
-// g = level-0 gradient volume (fp32, 4.2 GB per 1080p pair) after the pooled levels have been folded into it.
+// (K2b is folded in by linearity: level l of the pyramid is f1^T pool_l(f2) / sqrt(C), so with g_l the gradient of level l
+//   df1 = sum_l g_l pool_l(f2)^T / sqrt(C),      df2 = sum_l unpool_l( g_l^T f1 ) / sqrt(C)
+//  i.e. the df1 GEMM simply runs its K loop over the targets of ALL levels against the pooled f2, and the df2 GEMM
+//  produces one small (C x N_l) matrix per level that a tiny kernel un-pools and adds; the 5.6 GB gradient pyramid is
+//  never folded level by level.)
 // Both GEMMs read g, f1 and f2 as they are in HBM — fp32, through TMA, consumed as tf32 — so there is no conversion
-// or transposition pass over the 4.2 GB volume:
+// or transposition pass over the gradient volume (4.2 GB for level 0 of a 1080p pair):
 //   df1:  D[q, c]  M = 256 queries (two 128-row accumulators), N = 256 channels, K = t
 //         A = g rows (K-major: t contiguous), B = f2 (K-major: (C, N) rows are channels)
 //   df2:  D[c, t]  M = 256 channels (two accumulators), N = 256 targets, K = q
@@ -29,11 +33,18 @@ constexpr int SMEM_BAR = STAGES * STAGE_BYTES;
 constexpr int SMEM_BYTES = SMEM_BAR + 256 + 1024;
 constexpr int TMEM_COLS = 512;
 
+constexpr int MAXL = 4;
+struct Maps {
+  CUtensorMap g[MAXL];  // gradient level l: 2-D (t_l, B*N rows); K-major boxes (mode 0) / MN-major boxes (mode 1)
+  CUtensorMap f[MAXL];  // mode 0: level l of (pooled) fmap2 as (N_l, C, B);  mode 1: f[0] = fmap1 (N, C, B)
+};
 struct Params {
-  int mode;  // 0: df1 (rows = queries, cols = channels)   1: df2 (rows = channels, cols = targets)
-  int C, N;
+  int mode;  // 0: df1 (rows = queries, cols = channels)   1: df2 (rows = channels, cols = targets of one level)
+  int C, N, L;
+  int Nl[MAXL];             // targets per level
+  int tile_base[MAXL + 1];  // mode 1: first grid tile of level l
   float alpha;
-  float* out;  // (B, C, N)
+  float* out[MAXL];         // mode 0: out[0] = dfmap1 (B,C,N);  mode 1: out[l] = (B, C, Nl[l]) (out[0] = dfmap2)
 };
 
 __device__ __forceinline__ uint64_t desc_mnmajor_sw128_base32(uint32_t smem_addr, uint32_t lbo_bytes) {
@@ -50,7 +61,7 @@ __device__ __forceinline__ uint64_t desc_mnmajor_sw128_base32(uint32_t smem_addr
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-    corr_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmF, const Params P) {
+    corr_bwd_tc_kernel(const __grid_constant__ Maps M, const Params P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -62,12 +73,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + SMEM_BAR + 8 * (2 * STAGES + 1));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
-  const int tile0 = blockIdx.x * 256;  // first query (mode 0) / first target (mode 1) of this tile
-  const int nk = (P.N + BK - 1) / BK;
+  int lvl = 0;  // mode 1: the level this tile belongs to
+  if (P.mode == 1)
+    while (lvl + 1 < P.L && (int)blockIdx.x >= P.tile_base[lvl + 1]) ++lvl;
+  const int tile0 = (P.mode == 0 ? blockIdx.x : blockIdx.x - P.tile_base[lvl]) * 256;  // first query / first target
+  // K loop: mode 0 walks the targets of every level, mode 1 the queries
+  const int l_begin = P.mode == 0 ? 0 : lvl, l_end = P.mode == 0 ? P.L : lvl + 1;
 
   if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tmG);
-    ptx::prefetch_tmap(&tmF);
+    ptx::prefetch_tmap(&M.g[lvl]);
+    ptx::prefetch_tmap(&M.f[0]);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -89,45 +104,52 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
     uint32_t stage = 0, phase = 0;
-    for (int k = 0; k < nk; ++k) {
-      ptx::mbar_wait(empty_bar(stage), phase ^ 1);
-      const uint32_t sA = base + stage * STAGE_BYTES, sB = sA + 2 * A_BYTES;
-      ptx::mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-      if (P.mode == 0) {
-        // A = g[b, tile0 + (0..255), k*32 ..]: two boxes of 128 query rows; B = f2[b, 0..255, k*32 ..]
-        ptx::tma_load_2d_hint(sA, &tmG, full_bar(stage), k * BK, b * P.N + tile0, ptx::kEvictFirst);
-        ptx::tma_load_2d_hint(sA + A_BYTES, &tmG, full_bar(stage), k * BK, b * P.N + tile0 + BM, ptx::kEvictFirst);
-        ptx::tma_load_3d_hint(sB, &tmF, full_bar(stage), k * BK, 0, b, ptx::kEvictLast);
-      } else {
-        // A = f1[b, 0..255, k*32 ..]: two boxes of 128 channel rows; B = g[b, k*32 + (0..31), tile0 + (0..255)] as eight
-        // MN-major atoms columns (32 targets x 32 query rows each)
-        ptx::tma_load_3d_hint(sA, &tmF, full_bar(stage), k * BK, 0, b, ptx::kEvictLast);
-        ptx::tma_load_3d_hint(sA + A_BYTES, &tmF, full_bar(stage), k * BK, BM, b, ptx::kEvictLast);
+    for (int l = l_begin; l < l_end; ++l) {
+      const int nk = ((P.mode == 0 ? P.Nl[l] : P.N) + BK - 1) / BK;
+      for (int k = 0; k < nk; ++k) {
+        ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+        const uint32_t sA = base + stage * STAGE_BYTES, sB = sA + 2 * A_BYTES;
+        ptx::mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+        if (P.mode == 0) {
+          // A = g_l[b, tile0 + (0..255), k*32 ..]: two boxes of 128 query rows; B = pool_l(f2)[b, 0..255, k*32 ..]
+          ptx::tma_load_2d_hint(sA, &M.g[l], full_bar(stage), k * BK, b * P.N + tile0, ptx::kEvictFirst);
+          ptx::tma_load_2d_hint(sA + A_BYTES, &M.g[l], full_bar(stage), k * BK, b * P.N + tile0 + BM, ptx::kEvictFirst);
+          ptx::tma_load_3d_hint(sB, &M.f[l], full_bar(stage), k * BK, 0, b, ptx::kEvictLast);
+        } else {
+          // A = f1[b, 0..255, k*32 ..]: two boxes of 128 channel rows; B = g_l[b, k*32 + (0..31), tile0 + (0..255)] as
+          // eight MN-major atom columns (32 targets x 32 query rows each)
+          ptx::tma_load_3d_hint(sA, &M.f[0], full_bar(stage), k * BK, 0, b, ptx::kEvictLast);
+          ptx::tma_load_3d_hint(sA + A_BYTES, &M.f[0], full_bar(stage), k * BK, BM, b, ptx::kEvictLast);
 #pragma unroll
-        for (int j = 0; j < BN / 32; ++j)
-          ptx::tma_load_2d_hint(sB + j * (BK * 128), &tmG, full_bar(stage), tile0 + 32 * j, b * P.N + k * BK, ptx::kEvictFirst);
+          for (int j = 0; j < BN / 32; ++j)
+            ptx::tma_load_2d_hint(sB + j * (BK * 128), &M.g[l], full_bar(stage), tile0 + 32 * j, b * P.N + k * BK, ptx::kEvictFirst);
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = ptx::umma_idesc(/*tf32*/ 2, BM, BN) | (P.mode == 1 ? (1u << 16) : 0u);  // bit 16: B is MN-major
-    uint32_t stage = 0, phase = 0;
-    for (int k = 0; k < nk; ++k) {
-      ptx::mbar_wait(full_bar(stage), phase);
-      ptx::tc_fence_after();
-      const uint32_t sA = base + stage * STAGE_BYTES, sB = sA + 2 * A_BYTES;
-      const uint64_t b_desc = P.mode == 0 ? ptx::umma_desc_kmajor_sw128(sB) : desc_mnmajor_sw128_base32(sB, BK * 128);
-      const uint32_t b_step = P.mode == 0 ? 2u : 64u;  // 8 tf32 of K: 32 bytes along a K-major row / one 1024-byte atom
+    uint32_t stage = 0, phase = 0, first = 1;
+    for (int l = l_begin; l < l_end; ++l) {
+      const int nk = ((P.mode == 0 ? P.Nl[l] : P.N) + BK - 1) / BK;
+      for (int k = 0; k < nk; ++k) {
+        ptx::mbar_wait(full_bar(stage), phase);
+        ptx::tc_fence_after();
+        const uint32_t sA = base + stage * STAGE_BYTES, sB = sA + 2 * A_BYTES;
+        const uint64_t b_desc = P.mode == 0 ? ptx::umma_desc_kmajor_sw128(sB) : desc_mnmajor_sw128_base32(sB, BK * 128);
+        const uint32_t b_step = P.mode == 0 ? 2u : 64u;  // 8 tf32 of K: 32 bytes along a K-major row / two 512-byte atoms
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const uint64_t a_desc = ptx::umma_desc_kmajor_sw128(sA + h * A_BYTES);
+        for (int h = 0; h < 2; ++h) {
+          const uint64_t a_desc = ptx::umma_desc_kmajor_sw128(sA + h * A_BYTES);
 #pragma unroll
-        for (int kk = 0; kk < BK / 8; ++kk)
-          ptx::umma_tf32(tmem_base + h * BN, a_desc + 2 * kk, b_desc + b_step * kk, idesc, (k | kk) != 0);
+          for (int kk = 0; kk < BK / 8; ++kk)
+            ptx::umma_tf32(tmem_base + h * BN, a_desc + 2 * kk, b_desc + b_step * kk, idesc, (first == 0) || kk != 0);
+        }
+        first = 0;
+        ptx::umma_commit(empty_bar(stage));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      ptx::umma_commit(empty_bar(stage));
-      if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
     ptx::umma_commit(done_bar);
   } else if (warp >= 4) {
@@ -135,7 +157,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     const int quad = warp & 3;
     ptx::mbar_wait(done_bar, 0);
     ptx::tc_fence_after();
-    float* out_b = P.out + (long long)b * P.C * P.N;
+    const int ncol = P.mode == 0 ? P.N : P.Nl[lvl];  // row length of the output matrix
+    float* out_b = P.out[lvl] + (long long)b * P.C * ncol;
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
       const int row = h * BM + quad * 32 + lane;
@@ -150,14 +173,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           if (q < P.N) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (c0 + j < P.C) out_b[(long long)(c0 + j) * P.N + q] = __uint_as_float(r[j]) * P.alpha;
+              if (c0 + j < P.C) out_b[(long long)(c0 + j) * ncol + q] = __uint_as_float(r[j]) * P.alpha;
           }
         } else {
           // row = channel, columns = targets: each lane writes 32 consecutive targets of its channel row
           const int t0 = tile0 + c0;
-          if (row < P.C && t0 < P.N) {
-            float* dst = out_b + (long long)row * P.N + t0;
-            if (t0 + 32 <= P.N && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+          if (row < P.C && t0 < ncol) {
+            float* dst = out_b + (long long)row * ncol + t0;
+            if (t0 + 32 <= ncol && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
                 *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]) * P.alpha, __uint_as_float(r[j + 1]) * P.alpha,
@@ -165,7 +188,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (t0 + j < P.N) dst[j] = __uint_as_float(r[j]) * P.alpha;
+                if (t0 + j < ncol) dst[j] = __uint_as_float(r[j]) * P.alpha;
             }
           }
         }
@@ -177,39 +200,122 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   if (warp == 2) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// dfmap2[b,c,y,x] += sum_{l>=1} dB_l[b,c,y>>l,x>>l] / 4^l   (adjoint of l floor 2x2 average pools; pixels outside the
+// pooled area of a level get nothing from it)
+struct UnpoolParams {
+  const float* dB[MAXL];
+  int h[MAXL], w[MAXL];
+  int L, H, W;
+  long long planes;
+};
+__global__ void __launch_bounds__(256) unpool_add_kernel(float* __restrict__ df2, const UnpoolParams U) {
+  const long long total = U.planes * U.H * U.W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % U.W);
+    const long long r = i / U.W;
+    const int y = (int)(r % U.H);
+    const long long pl = r / U.H;
+    float acc = 0.f, wgt = 0.25f;
+    for (int l = 1; l < U.L; ++l, wgt *= 0.25f) {
+      const int yl = y >> l, xl = x >> l;
+      if (yl < U.h[l] && xl < U.w[l]) acc += wgt * __ldg(U.dB[l] + (pl * U.h[l] + yl) * U.w[l] + xl);
+    }
+    df2[i] += acc;
+  }
+}
+
 }  // namespace k1btc
 
 // true when the tcgen05 path covers this problem (TMA needs 16-byte-aligned row strides)
-bool corr_bwd_tc_supported(int C, int N, long long g_qstride) { return C <= 256 && (N % 4) == 0 && (g_qstride % 4) == 0; }
+bool corr_bwd_tc_supported(int C, int N) { return C <= 256 && (N % 4) == 0; }
 
-// g: level-0 gradient volume, row (b*N + q) at g + row*g_qstride, t contiguous.  F: the other feature map (B,C,N).
-// mode 0: out = dfmap1 from F = fmap2;  mode 1: out = dfmap2 from F = fmap1.
-int corr_bwd_tc_launch(int mode, const float* g, long long g_qstride, const float* F, int B, int C, int N, float alpha, float* out,
+// scratch: pooled fmap2 levels (padded rows) and the per-level dB matrices
+size_t corr_bwd_tc_workspace_bytes(int B, int C, int H, int W, int L) {
+  size_t n = 1024;
+  for (int l = 1; l < L; ++l) {
+    const long long nl = (long long)(H >> l) * (W >> l);
+    n += (size_t)B * C * round_up((int)nl, 4) * 4 + 256;  // pool_l(f2)
+    n += (size_t)B * C * nl * 4 + 256;                     // dB_l
+  }
+  return n;
+}
+
+// dlvl[l]: gradient level l, row (b*N + q) at dlvl[l] + row*qstride[l], targets contiguous.  Computes dfmap1 and/or dfmap2.
+int corr_bwd_tc_launch(float* const* dlvl, const long long* qstride, const float* fmap1, const float* fmap2, int B, int C, int H,
+                       int W, int L, float alpha, float* dfmap1, float* dfmap2, void* workspace, size_t workspace_bytes,
                        cudaStream_t st) {
   using namespace k1btc;
+  const int N = H * W;
+  EZB_REQUIRE(L <= MAXL, "at most %d levels", MAXL);
   EZB_REQUIRE((long long)B * N < (1ll << 31), "batch too large for one launch (split it)");
-  CUtensorMap tmG, tmF;
-  {
-    cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)B * N};
-    cuuint64_t str[1] = {(cuuint64_t)g_qstride * 4};
-    cuuint32_t box[2] = {BK, (cuuint32_t)(mode == 0 ? BM : BK)};
-    if (int r = make_tmap(&tmG, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(g), dims, str, box,
-                          mode == 0 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
-      return r;
+  if (corr_bwd_tc_workspace_bytes(B, C, H, W, L) > workspace_bytes)
+    return fail(EZB_ERR_WORKSPACE, "workspace too small: need %zu, got %zu", corr_bwd_tc_workspace_bytes(B, C, H, W, L), workspace_bytes);
+  uintptr_t wp = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
+  auto take = [&](size_t bytes) {
+    uintptr_t r = wp;
+    wp = (wp + bytes + 255) & ~uintptr_t(255);
+    return reinterpret_cast<float*>(r);
+  };
+  int Nl[MAXL], hl[MAXL], wl[MAXL], Npad[MAXL];
+  const float* f2l[MAXL];
+  float* dB[MAXL];
+  for (int l = 0; l < L; ++l) {
+    hl[l] = H >> l; wl[l] = W >> l; Nl[l] = hl[l] * wl[l]; Npad[l] = round_up(Nl[l], 4);
   }
-  {
-    cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)C, (cuuint64_t)B};
-    cuuint64_t str[2] = {(cuuint64_t)N * 4, (cuuint64_t)C * N * 4};
-    cuuint32_t box[3] = {BK, (cuuint32_t)(mode == 0 ? BN : BM), 1};
-    if (int r = make_tmap(&tmF, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(F), dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return r;
+  f2l[0] = fmap2; Npad[0] = N; dB[0] = dfmap2;
+  for (int l = 1; l < L; ++l) {
+    float* p = take((size_t)B * C * Npad[l] * 4);
+    dB[l] = take((size_t)B * C * Nl[l] * 4);
+    if (dfmap1) {
+      if (int r = prep::launch_pool2x2(f2l[l - 1], p, (long long)B * C, hl[l - 1], wl[l - 1], Npad[l - 1], hl[l], wl[l], Npad[l], st)) return r;
+    }
+    f2l[l] = p;
   }
-  Params P;
-  P.mode = mode; P.C = C; P.N = N; P.alpha = alpha; P.out = out;
   EZB_CUDA_OK(cudaFuncSetAttribute(corr_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  dim3 grid(cdiv(N, 256), B);
-  EZB_REQUIRE(grid.y <= 65535, "batch too large for one launch (split it)");
-  corr_bwd_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmG, tmF, P);
-  EZB_LAUNCH_OK();
+  for (int mode = 0; mode < 2; ++mode) {
+    if (mode == 0 ? dfmap1 == nullptr : dfmap2 == nullptr) continue;
+    Maps M;
+    memset(&M, 0, sizeof(M));
+    Params P;
+    P.mode = mode; P.C = C; P.N = N; P.L = L; P.alpha = alpha;
+    int tiles = 0;
+    for (int l = 0; l < MAXL; ++l) {
+      P.Nl[l] = l < L ? Nl[l] : 0;
+      P.tile_base[l] = tiles;
+      if (l < L) tiles += cdiv(Nl[l], 256);
+      P.out[l] = mode == 0 ? dfmap1 : (l < L ? dB[l] : nullptr);
+    }
+    P.tile_base[MAXL] = tiles;
+    for (int l = 0; l < L; ++l) {
+      cuuint64_t dims[2] = {(cuuint64_t)Nl[l], (cuuint64_t)B * N};
+      cuuint64_t str[1] = {(cuuint64_t)qstride[l] * 4};
+      cuuint32_t box[2] = {BK, (cuuint32_t)(mode == 0 ? BM : BK)};
+      if (int r = make_tmap(&M.g[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dlvl[l], dims, str, box,
+                            mode == 0 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+        return r;
+    }
+    const int nf = mode == 0 ? L : 1;
+    for (int l = 0; l < nf; ++l) {
+      const float* F = mode == 0 ? f2l[l] : fmap1;
+      const int n = mode == 0 ? Nl[l] : N, npad = mode == 0 ? Npad[l] : N;
+      cuuint64_t dims[3] = {(cuuint64_t)n, (cuuint64_t)C, (cuuint64_t)B};
+      cuuint64_t str[2] = {(cuuint64_t)npad * 4, (cuuint64_t)C * npad * 4};
+      cuuint32_t box[3] = {BK, (cuuint32_t)(mode == 0 ? BN : BM), 1};
+      if (int r = make_tmap(&M.f[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(F), dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return r;
+    }
+    dim3 grid(mode == 0 ? cdiv(N, 256) : tiles, B);
+    EZB_REQUIRE(grid.y <= 65535, "batch too large for one launch (split it)");
+    corr_bwd_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(M, P);
+    EZB_LAUNCH_OK();
+    if (mode == 1 && L > 1) {
+      UnpoolParams U;
+      for (int l = 0; l < MAXL; ++l) { U.dB[l] = l < L ? dB[l] : nullptr; U.h[l] = l < L ? hl[l] : 0; U.w[l] = l < L ? wl[l] : 0; }
+      U.L = L; U.H = H; U.W = W; U.planes = (long long)B * C;
+      const long long total = U.planes * N;
+      unpool_add_kernel<<<(int)std::min<long long>(cdiv64(total, 256), 148 * 16), 256, 0, st>>>(dfmap2, U);
+      EZB_LAUNCH_OK();
+    }
+  }
   return EZB_OK;
 }
 

@@ -173,15 +173,15 @@ __global__ void __launch_bounds__(256) convert_kmajor_kernel(const float* __rest
 // fmap2 levels 1..L-1: successive floor 2x2 average pools (F.avg_pool2d(.., 2, stride=2), pairwise.py:40)
 // applied to the feature map instead of the 4-D volume.  planes = B*C.
 __global__ void __launch_bounds__(256) pool2x2_kernel(const float* __restrict__ src, float* __restrict__ dst, long long planes,
-                                                      int hs, int ws, int hd, int wd) {
+                                                      int hs, int ws, long long src_plane, int hd, int wd, long long dst_plane) {
   const long long total = planes * hd * wd;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(i % wd);
     const long long r = i / wd;
     const int y = (int)(r % hd);
     const long long pl = r / hd;
-    const float* s = src + (pl * hs + 2 * y) * ws + 2 * x;
-    dst[i] = 0.25f * ((__ldg(s) + __ldg(s + 1)) + (__ldg(s + ws) + __ldg(s + ws + 1)));
+    const float* s = src + pl * src_plane + (long long)(2 * y) * ws + 2 * x;
+    dst[pl * dst_plane + (long long)y * wd + x] = 0.25f * ((__ldg(s) + __ldg(s + 1)) + (__ldg(s + ws) + __ldg(s + ws + 1)));
   }
 }
 
@@ -577,6 +577,14 @@ int launch_convert_kmajor(const float* src, __half* dst, const unsigned int* ama
   EZB_LAUNCH_OK();
   return EZB_OK;
 }
+int launch_pool2x2(const float* src, float* dst, long long planes, int hs, int ws, long long src_plane, int hd, int wd,
+                   long long dst_plane, cudaStream_t st) {
+  const long long total = planes * hd * wd;
+  const int gx = (int)std::max<long long>(1, std::min<long long>(cdiv64(total, 256), 148 * 8));
+  k1::pool2x2_kernel<<<gx, 256, 0, st>>>(src, dst, planes, hs, ws, src_plane, hd, wd, dst_plane);
+  EZB_LAUNCH_OK();
+  return EZB_OK;
+}
 }  // namespace prep
 }  // namespace ezb
 
@@ -673,7 +681,8 @@ extern "C" int ezb_corr_pyramid_fwd_ex(const float* fmap1, const float* fmap2, i
   for (int l = 1; l < L; ++l) {
     const long long total = (long long)B * C * pk.h[l] * pk.w[l];
     const int gx = (int)std::min<long long>(cdiv64(total, 256), 148 * 8);
-    k1::pool2x2_kernel<<<gx, 256, 0, st>>>(pk.lvl[l - 1], ws.f2l[l], (long long)B * C, pk.h[l - 1], pk.w[l - 1], pk.h[l], pk.w[l]);
+    k1::pool2x2_kernel<<<gx, 256, 0, st>>>(pk.lvl[l - 1], ws.f2l[l], (long long)B * C, pk.h[l - 1], pk.w[l - 1],
+                                           (long long)pk.h[l - 1] * pk.w[l - 1], pk.h[l], pk.w[l], (long long)pk.h[l] * pk.w[l]);
     EZB_LAUNCH_OK();
   }
   k1::pack_record_operand_kernel<<<dim3(lay.n_tiles, Cp / k1::PACK_CH, B), 256, 0, st>>>(pk);

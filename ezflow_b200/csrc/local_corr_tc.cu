@@ -36,8 +36,9 @@ constexpr int A_KB_BYTES = BM * BK * 2;           // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;        // 16 KB
 constexpr int S_STRIDE = BN + 1;                  // words; odd => lane = query accesses are conflict-free
 constexpr int NACC = 4, TMEM_COLS = NACC * BN;    // 512
-constexpr int EPI_WARPS = 8;                      // two per TMEM lane quadrant
-constexpr int NUM_THREADS = 128 + EPI_WARPS * 32;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue
+constexpr int EPI_SPLIT = 4;                      // epilogue warps per TMEM lane quadrant
+constexpr int EPI_WARPS = 4 * EPI_SPLIT;
+constexpr int NUM_THREADS = 128 + EPI_WARPS * 32;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4.. epilogue
 constexpr int MAX_DIL = 8;
 constexpr int SMEM_A = 0;
 constexpr int SMEM_B = SMEM_A + KB_MAX * A_KB_BYTES;
@@ -172,9 +173,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     }
   } else if (warp >= 4) {
     // ===================== epilogue: lane = query =====================
-    // Two warps share a TMEM lane quadrant (= 32 queries): each drains half of the accumulator columns into
-    // the queries' shared-memory rows, then they split the displacement rows (pi) between them.
-    const int quad = warp & 3, half = (warp - 4) >> 2;
+    // EPI_SPLIT warps share a TMEM lane quadrant (= 32 queries): each drains its share of the accumulator columns
+    // into the queries' shared-memory rows, then they split the (pi, pj-chunk) work items between them.
+    const int quad = warp & 3, part = (warp - 4) >> 2;
     const int q = quad * 32 + lane;
     const int oy = qy0 + q / QTW, ox = qx0 + q % QTW;
     const bool q_ok = oy < P.oh && ox < P.ow;
@@ -183,7 +184,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     const long long plane = (long long)P.oh * P.ow;
     float* out_q = P.out + (long long)b * P.out_bstride + (long long)oy * P.ow + ox;
     float* Srow = S + q * S_STRIDE;
-    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory"); };
+    auto quad_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * EPI_SPLIT) : "memory"); };
+    constexpr int CPW = BN / EPI_SPLIT;  // accumulator columns per warp
 
     // displacements that point outside the image: zeros (act(0) = 0), written once, up front
     if (q_ok) {
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         const int dph = P.dph[d], dpw = P.dpw[d];
         const int y2_0 = oy * P.sh - P.padh - dph * (P.Ph - 1) / 2, x2_0 = ox * P.sw - P.padw - dpw * (P.Pw - 1) / 2;
         float* o = out_q + (long long)(d * P.G + g) * P.Ph * P.Pw * plane;
-        for (int a = half; a < P.Ph; a += 2) {
+        for (int a = part; a < P.Ph; a += EPI_SPLIT) {
           const int y2 = y2_0 + a * dph;
           const bool row_in = y2 >= 0 && y2 < P.H;
           for (int bb = 0; bb < P.Pw; ++bb) {
@@ -208,22 +210,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       const uint32_t acc = tt % NACC, aphase = (tt / NACC) & 1;
       ptx::mbar_wait(tmem_full(acc), aphase);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16) + half * (BN / 2);
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16) + part * CPW;
       {
-        uint32_t r0[32], r1[32];
-        ptx::tmem_ld_32x32b_x32(taddr, r0);
-        ptx::tmem_ld_32x32b_x32(taddr + 32, r1);
+        uint32_t r[CPW / 32][32];
+#pragma unroll
+        for (int c = 0; c < CPW / 32; ++c) ptx::tmem_ld_32x32b_x32(taddr + c * 32, r[c]);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(tmem_empty(acc));  // the accumulator is in registers: release it early
-        float* dst = Srow + half * (BN / 2);
+        float* dst = Srow + part * CPW;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) dst[j] = __uint_as_float(r0[j]);
+        for (int c = 0; c < CPW / 32; ++c)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) dst[32 + j] = __uint_as_float(r1[j]);
+          for (int j = 0; j < 32; ++j) dst[c * 32 + j] = __uint_as_float(r[c][j]);
       }
-      pair_sync();  // both halves of the rows are in shared memory
+      quad_sync();  // all column shares of the rows are in shared memory
 
       for (int d = 0; d < P.D; ++d) {
         const int dph = P.dph[d], dpw = P.dpw[d];
@@ -237,28 +239,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         const int ub_lo = __reduce_min_sync(0xffffffffu, b_lo), ub_hi = __reduce_max_sync(0xffffffffu, b_hi);
         if (ua_lo > ua_hi) continue;
         float* o = out_q + (long long)(d * P.G + g) * P.Ph * P.Pw * plane;
-        for (int a = ua_lo + ((ua_lo ^ half) & 1); a <= ua_hi; a += 2) {  // rows with a % 2 == half
+        // work items = (pi, chunk of 4 pj), dealt round-robin to the warps of the quadrant
+        const int nchunk = (ub_hi - ub_lo) / 4 + 1, nitems = (ua_hi - ua_lo + 1) * nchunk;
+        for (int it = part; it < nitems; it += EPI_SPLIT) {
+          const int ai = it / nchunk, a = ua_lo + ai, bb = ub_lo + (it - ai * nchunk) * 4;
           const bool row_ok = a >= a_lo && a <= a_hi;
           const float* srow = Srow + (y2_0 + a * dph - ty0) * TTW + (x2_0 - tx0);
           float* orow = o + (long long)a * P.Pw * plane;
-          for (int bb = ub_lo; bb <= ub_hi; bb += 4) {  // 4 independent load -> store chains in flight
-            float v[4];
-            bool ok[4];
+          float v[4];
+          bool ok[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              ok[u] = row_ok && bb + u >= b_lo && bb + u <= b_hi;
-              v[u] = ok[u] ? srow[(bb + u) * dpw] : 0.f;
-            }
+          for (int u = 0; u < 4; ++u) {  // 4 independent load -> store chains in flight
+            ok[u] = row_ok && bb + u >= b_lo && bb + u <= b_hi;
+            v[u] = ok[u] ? srow[(bb + u) * dpw] : 0.f;
+          }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              float w = v[u] * deq;
-              w = w >= 0.f ? w : w * P.slope;
-              if (ok[u]) orow[(long long)(bb + u) * plane] = w;
-            }
+          for (int u = 0; u < 4; ++u) {
+            float w = v[u] * deq;
+            w = w >= 0.f ? w : w * P.slope;
+            if (ok[u]) orow[(long long)(bb + u) * plane] = w;
           }
         }
       }
-      pair_sync();  // both warps are done with the rows before the next tile overwrites them
+      quad_sync();  // every warp is done with the rows before the next tile overwrites them
     }
   }
 

@@ -181,13 +181,17 @@ class _BuildFn(torch.autograd.Function):
         df1 = torch.empty_like(st.fmap1)
         df2 = torch.empty_like(st.fmap2)
         with torch.cuda.device(st.device):
+            lib = _cabi.lib()
+            nws = ctypes.c_size_t(0)
+            _cabi.check(lib.ezb_corr_pyramid_bwd_workspace_bytes(st.B, st.C, st.H, st.W, st.L, ctypes.byref(nws)))
+            ws = torch.empty(nws.value, dtype=torch.uint8, device=st.device) if nws.value else None
             _cabi.check(
-                _cabi.lib().ezb_corr_pyramid_bwd(
+                lib.ezb_corr_pyramid_bwd(
                     _cabi.ptr_array(st.grad_levels), _cabi.ptr(st.fmap1), _cabi.ptr(st.fmap2), st.B, st.C, st.H, st.W, st.L,
-                    _cabi.ptr(df1), _cabi.ptr(df2), _cabi.stream_ptr(st.device),
+                    _cabi.ptr(df1), _cabi.ptr(df2), _cabi.ptr(ws), nws.value, _cabi.stream_ptr(st.device),
                 )
             )
-        st.grad_levels = None  # consumed (folded in place)
+        st.grad_levels = None  # consumed
         return df1, df2, None
 
 

@@ -113,10 +113,15 @@ int ezb_corr_lookup_bwd(const float* dout /* (B, L*(2r+1)^2, H, W) */, const flo
                         int B, int H, int W, int L, int radius,
                         float* const* dlvl_ptrs /*[L] host*/, void* stream);
 
-/* Adjoint of the pyramid build (K2b + K1b): folds level gradients into level 0 (in place, dlvl[0]
- * is overwritten with the total) and computes dfmap1, dfmap2 (B,C,H,W) fp32. */
+/* Adjoint of the pyramid build (K2b + K1b): dfmap1, dfmap2 (B,C,H,W) fp32 from the gradient levels.
+ * With a workspace of ezb_corr_pyramid_bwd_workspace_bytes() (non-zero when C <= 256, L <= 4 and H*W % 4 == 0) both
+ * GEMMs run on tcgen05 (kind::tf32) over all levels at once and the gradient levels are left untouched; otherwise
+ * (workspace == NULL) the levels are folded into level 0 in place (dlvl[0] is overwritten with the total) and fp32
+ * CUDA-core GEMMs run. */
+int ezb_corr_pyramid_bwd_workspace_bytes(int B, int C, int H, int W, int L, size_t* bytes /*host*/);
 int ezb_corr_pyramid_bwd(float* const* dlvl_ptrs /*[L] host*/, const float* fmap1, const float* fmap2,
-                         int B, int C, int H, int W, int L, float* dfmap1, float* dfmap2, void* stream);
+                         int B, int C, int H, int W, int L, float* dfmap1, float* dfmap2,
+                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Local displacement-window correlation (K4 / K4b), also CorrelationLayer and the engine of K6
