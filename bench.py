@@ -33,7 +33,7 @@ LEVEL_ELEMS = 32400 + 8040 + 1980 + 480  # 135x240 + 67x120 + 33x60 + 16x30 per 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs-per-gpu", type=int, default=8, help="image pairs each rank processes per step")
@@ -154,49 +154,74 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock and throttle reasons sampled every 5 ms DURING the timed region through NVML (a thread in this
+    process; falls back to one nvidia-smi query when NVML is unavailable)."""
 
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = {
+        "hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+        "hw_power_brake_slowdown": 0x80,
+    }
 
     def __init__(self, index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        import threading
+
+        self.index = index
+        self.samples, self.mask, self.max_mhz = [], 0, None
+        self._stop = threading.Event()
+        self._nvml = None
         try:
-            self.p = subprocess.Popen(
-                ["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
-                stdout=self.f, stderr=subprocess.DEVNULL,
-            )
-        except OSError:
-            pass
+            import pynvml
+
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: map the CUDA ordinal through CUDA_VISIBLE_DEVICES when it is set
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._nvml = pynvml
+        except Exception:
+            self._nvml = None
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def _run(self):
+        nv = self._nvml
+        if nv is None:
+            return
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                try:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                except Exception:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+            except Exception:
+                break
+            time.sleep(0.005)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
+        self._stop.set()
+        self._t.join(timeout=2)
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": len(self.samples), "source": "nvml"}
+        if self.samples:
+            s = sorted(self.samples)
+            out["sm_mhz"] = s[len(s) // 2]
+            out["sm_min_mhz"] = s[0]
+            out["reasons"] = sorted(k for k, bit in self.REASONS.items() if self.mask & bit)
             return out
-        self.p.terminate()
+        # fallback: a single nvidia-smi query (after the region; reported as such)
+        out["source"] = "nvidia-smi (single query after the timed region)"
         try:
-            self.p.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-        self.f.flush()
-        rows = [r.strip().split(",") for r in open(self.f.name) if r.strip()]
-        os.unlink(self.f.name)
-        clocks, reasons = [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            try:
-                clocks.append(float(r[0]))
-                out["sm_max_mhz"] = float(r[1])
-            except (ValueError, IndexError):
-                continue
-            for nm, v in zip(names, r[2:6]):
-                if v.strip().lower().startswith("active"):
-                    reasons.add(nm)
-        if clocks:
-            clocks.sort()
-            out["sm_mhz"] = clocks[len(clocks) // 2]
-        out["reasons"] = sorted(reasons)
-        out["samples"] = len(clocks)
+            q = "clocks.sm,clocks.max.sm"
+            r = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                               capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+            out["sm_mhz"], out["sm_max_mhz"], out["samples"] = float(r[0]), float(r[1]), 1
+        except Exception:
+            pass
         return out
 
 

@@ -76,13 +76,14 @@ __global__ void __launch_bounds__(NTHREADS, 3) corr_lookup_fwd_kernel(const Look
   const float* cx_ptr = P.coords + (long long)b * 2 * P.N;
   const float* cy_ptr = cx_ptr + P.N;
   const char* pair_base = P.pyr + (long long)b * P.n_tiles * P.n_groups * P.group_bytes + (long long)grp * P.group_bytes;
-  const long long tile_stride = (long long)P.n_groups * P.group_bytes;
+  const unsigned int tile_stride = (unsigned int)(P.n_groups * P.group_bytes);  // < 2^32, checked by the host
   int2* items = reinterpret_cast<int2*>(sm_words + QB * qstride_words);
 
   // ---------------- phase 0: window origins ----------------
   // Every warp serves 4 queries of the block; lane k < 16 owns item (query k/4, level k%4) and keeps its
-  // window origin in registers (shuffled to the other lanes below) and in shared memory (phase 2).
-  int2 org_mine;
+  // window origin in a register (shuffled to the other lanes below) and in shared memory (phase 2).
+  using G = Gather<ES>;
+  int org_packed;  // (first chunk index << 16) | (first row & 0xffff), both small signed numbers
   {
     const int qi = (lane >> 2) & 3, l = lane & 3;
     const int q = min(q0 + warp * 4 + qi, P.N - 1);
@@ -90,8 +91,9 @@ __global__ void __launch_bounds__(NTHREADS, 3) corr_lookup_fwd_kernel(const Look
     const int x0 = float_floor_to_int_clamped(__ldg(cx_ptr + q) * inv, -(1 << 24), 1 << 24);
     const int y0 = float_floor_to_int_clamped(__ldg(cy_ptr + q) * inv, -(1 << 24), 1 << 24);
     // clamped so that a window entirely outside the level stays entirely outside
-    org_mine = make_int2(max(-D, min(P.W >> l, x0 - r)), max(-D, min(P.H >> l, y0 - r)));
-    if (lane < 16 && l < P.L) items[l * QB + warp * 4 + qi] = org_mine;
+    const int2 org = make_int2(max(-D, min(P.W >> l, x0 - r)), max(-D, min(P.H >> l, y0 - r)));
+    if (lane < 16 && l < P.L) items[l * QB + warp * 4 + qi] = org;
+    org_packed = (G::chunk_floor(org.x) << 16) | (org.y & 0xffff);
   }
 
   // ---------------- phase 1: gather windows ----------------
@@ -100,7 +102,6 @@ __global__ void __launch_bounds__(NTHREADS, 3) corr_lookup_fwd_kernel(const Look
   // round trip), so a warp has the windows of its 4 queries x all levels (16 x 480 bytes) in flight at once.
   // Everything outside a level's valid area is stored as zero by the GEMM (zero operand rows), and chunks
   // outside the level are zero-filled here (src-size 0), so no per-element masking is needed.
-  using G = Gather<ES>;
   const int ng = G::ng(D), row_el = G::row_el(D);
   const int tasks = D * ng, rounds = (tasks + 31) >> 5;
   const uint32_t sm_base = (uint32_t)__cvta_generic_to_shared(sm_words);
@@ -109,26 +110,25 @@ __global__ void __launch_bounds__(NTHREADS, 3) corr_lookup_fwd_kernel(const Look
     const int row = (ng == 3) ? div3(t) : (ng == 4) ? t >> 2 : t / ng;
     const int gi = t - row * ng;
     const bool task_ok = t < tasks;
-    const uint32_t dst_task = sm_base + (row * row_el + gi * G::VW) * ES;
+    const uint32_t dst_task = sm_base + (row * row_el + gi * G::VW) * ES + warp * 4 * (qstride_words * 4);
 #pragma unroll
     for (int qi = 0; qi < 4; ++qi) {
       const int ql = warp * 4 + qi;
 #pragma unroll
       for (int l = 0; l < PYR_MAX_LEVELS; ++l) {
-        const int ox = __shfl_sync(0xffffffffu, org_mine.x, qi * 4 + l);
-        const int oy = __shfl_sync(0xffffffffu, org_mine.y, qi * 4 + l);
+        const int pk = __shfl_sync(0xffffffffu, org_packed, qi * 4 + l);
         if (l < P.L && task_ok) {
-          const int y = oy + row;
-          const int xg = (G::chunk_floor(ox) + gi) * G::VW;  // first pixel of the chunk
+          const int y = (int)(short)(pk & 0xffff) + row;
+          const int xg = ((pk >> 16) + gi) * G::VW;  // first pixel of the chunk
           const char* src = pair_base;
           uint32_t nbytes = 0;
-          if (y >= 0 && y < (P.H >> l) && xg >= 0 && xg < (P.W >> l)) {
-            const int s = P.sub_base[l] + (y / PYR_SY) * P.sw[l] + xg / PYR_SX;
-            const int col = (s % PYR_SUBS_PER_TILE) * PYR_SUB + (y % PYR_SY) * PYR_SX + xg % PYR_SX;
-            src = pair_base + (long long)(s / PYR_SUBS_PER_TILE) * tile_stride + pyr_record_offset(ES, ql, col);
+          if ((unsigned)y < (unsigned)(P.H >> l) && (unsigned)xg < (unsigned)(P.W >> l)) {
+            const unsigned sidx = (unsigned)(P.sub_base[l] + (y / PYR_SY) * P.sw[l] + xg / PYR_SX);
+            const int col = (int)(sidx % PYR_SUBS_PER_TILE) * PYR_SUB + (y % PYR_SY) * PYR_SX + xg % PYR_SX;
+            src = pair_base + (unsigned long long)(sidx / PYR_SUBS_PER_TILE) * tile_stride + (unsigned)pyr_record_offset(ES, ql, col);
             nbytes = 16;
           }
-          cp_async_16(dst_task + ql * (qstride_words * 4) + l * D * row_el * ES, src, nbytes);
+          cp_async_16(dst_task + qi * (qstride_words * 4) + l * D * row_el * ES, src, nbytes);
         }
       }
     }
@@ -139,13 +139,19 @@ __global__ void __launch_bounds__(NTHREADS, 3) corr_lookup_fwd_kernel(const Look
   // ---------------- phase 2: bilinear taps, lane = query ----------------
   // work item = (level, i): the 2r+1 outputs with x-offset i, walked down the window so each new output
   // needs two fresh taps (the upper pair is the previous lower pair).  Stores are 128 contiguous bytes.
+  // Every warp takes a contiguous run of items, so the per-level setup is done once per warp (with 4 levels
+  // and 8 warps: two warps per level).
   const int q = q0 + lane;
   if (q >= P.N) return;
   const float deq = __ldg(P.deq + b);
   const float x = __ldg(cx_ptr + q), y = __ldg(cy_ptr + q);
   float* out = P.out + (long long)b * P.L * KK * P.N + q;
-  for (int item = warp; item < P.L * K; item += NTHREADS / 32) {
-    const int l = item / K, i = item - l * K;  // i offsets x (slow output index!), j offsets y   pairwise.py:53-61
+  const T* sm_q = reinterpret_cast<const T*>(sm_words + lane * qstride_words);
+  const int n_items = P.L * K, n_warps = NTHREADS / 32;
+  int item = n_items * warp / n_warps;
+  const int item_end = n_items * (warp + 1) / n_warps;
+  while (item < item_end) {
+    const int l = item / K, i0 = item - l * K, i1 = min(K, i0 + item_end - item);
     const float inv = 1.0f / (float)(1 << l);
     const float cx = x * inv, cy = y * inv;
     const float fx = cx - floorf(cx), fy = cy - floorf(cy);
@@ -153,15 +159,20 @@ __global__ void __launch_bounds__(NTHREADS, 3) corr_lookup_fwd_kernel(const Look
     const float wl0 = deq * (1.f - fx), wl1 = deq * fx;
     const int xs = items[l * QB + lane].x;
     const int off = xs - G::chunk_floor(xs) * G::VW;  // taps start `off` pixels into the fetched row
-    const T* p = reinterpret_cast<const T*>(sm_words + lane * qstride_words) + l * D * row_el + off + i;
-    float* o = out + (long long)(l * KK + i * K) * P.N;
-    float top = wl0 * (float)p[0] + wl1 * (float)p[1];  // horizontal lerp of row j
-    for (int j = 0; j < K; ++j) {
-      p += row_el;
-      const float bot = wl0 * (float)p[0] + wl1 * (float)p[1];
-      o[(long long)j * P.N] = top + fy * (bot - top);
-      top = bot;
+    const T* pl = sm_q + l * D * row_el + off;
+    float* o = out + (long long)(l * KK + i0 * K) * P.N;  // i offsets x (slow output index!), j offsets y   pairwise.py:53-61
+    for (int i = i0; i < i1; ++i) {
+      const T* p = pl + i;
+      float top = wl0 * (float)p[0] + wl1 * (float)p[1];  // horizontal lerp of row j
+      for (int j = 0; j < K; ++j) {
+        p += row_el;
+        const float bot = wl0 * (float)p[0] + wl1 * (float)p[1];
+        *o = top + fy * (bot - top);
+        o += P.N;
+        top = bot;
+      }
     }
+    item += i1 - i0;
   }
 }
 
@@ -254,6 +265,7 @@ extern "C" int ezb_corr_lookup_fwd(const void* pyramid, const float* deq_scale, 
   PyrLayout lay;
   EZB_REQUIRE(pyr_layout(H, W, L, dtype, &lay), "feature map %dx%d too small for %d pyramid levels", H, W, L);
   EZB_REQUIRE((reinterpret_cast<uintptr_t>(pyramid) & 127) == 0, "pyramid buffer must be 128-byte aligned");
+  EZB_REQUIRE((long long)lay.n_groups * lay.group_bytes < (1ll << 32), "feature map too large (H*W=%d)", H * W);
   k3::LookupParams P;
   const int N = H * W;
   P.H = H;
