@@ -24,8 +24,9 @@
 //            each CTA fetches half of every A stage and TMA-multicasts it to both, which halves the L2
 //            read traffic of the re-streamed A operand (the kernel is L2-fabric bound otherwise:
 //            profiles/r01_gemm_experiments.md).
-//   epilogue: TMEM -> registers -> (scale) -> fp16/fp32 -> swizzled staging -> coalesced streaming
-//            16-byte stores; a warp writes its 32 queries x 128-byte lines as contiguous 4 KB sections.
+//   epilogue: TMEM -> registers (tcgen05.ld.16x256b) -> (scale) -> fp16/fp32 -> 256-bit streaming stores straight
+//            from registers: the operand rows are ordered so that a quad of threads owns one query's 128-byte
+//            line, i.e. every store instruction writes 8 complete lines; no shared-memory staging.
 #include "ezb_common.cuh"
 #include "ezb_ptx.cuh"
 #include "ezb_tma.cuh"
@@ -40,26 +41,22 @@ constexpr int BN = PYR_REC;       // record elements   (UMMA N = 256, TMEM colum
 constexpr int BK = 64;            // fp16 elements per 128-byte swizzle row
 constexpr int KB_MAX = 4;         // resident B k-blocks  (C <= 256)
 #ifndef EZB_GEMM_STAGES
-#define EZB_GEMM_STAGES 5
-#endif
-#ifndef EZB_GEMM_EPI_WARPS
-#define EZB_GEMM_EPI_WARPS 4
+#define EZB_GEMM_STAGES 6
 #endif
 constexpr int STAGES = EZB_GEMM_STAGES;  // A ring
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 constexpr int CLUSTER = 2;                   // CTAs sharing one A stream
 constexpr int A_SLICE_ROWS = BM / CLUSTER;   // rows of an A stage each CTA of the cluster fetches (and multicasts)
 constexpr int B_KB_BYTES = BN * BK * 2;      // 32 KB
-constexpr int SLOT_BYTES = 4096;             // one staged section: 32 queries x 128 B
-constexpr int SLOTS_PER_WARP = 1;
-constexpr int EPI_WARPS = EZB_GEMM_EPI_WARPS;  // EPI_SPLIT warps per TMEM lane quadrant, each takes 1/EPI_SPLIT of the record
-constexpr int EPI_SPLIT = EPI_WARPS / 4;
-static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "one or two epilogue warps per TMEM lane quadrant");
+#ifndef EZB_GEMM_EPI_SPLIT
+#define EZB_GEMM_EPI_SPLIT 1
+#endif
+constexpr int EPI_SPLIT = EZB_GEMM_EPI_SPLIT;  // epilogue warps per TMEM lane quadrant (each takes 1/EPI_SPLIT of the record)
+constexpr int EPI_WARPS = 4 * EPI_SPLIT;
 constexpr int NUM_THREADS = 128 + EPI_WARPS * 32;
 constexpr int SMEM_B = 0;
 constexpr int SMEM_A = SMEM_B + KB_MAX * B_KB_BYTES;
-constexpr int SMEM_STG = SMEM_A + STAGES * A_STAGE_BYTES;
-constexpr int SMEM_BAR = SMEM_STG + EPI_WARPS * SLOTS_PER_WARP * SLOT_BYTES;
+constexpr int SMEM_BAR = SMEM_A + STAGES * A_STAGE_BYTES;
 constexpr int SMEM_BYTES = SMEM_BAR + 256 + 1024;  // + barrier block + alignment slack
 constexpr int TMEM_COLS = 512;                     // two 256-column accumulators
 
@@ -69,8 +66,8 @@ struct GemmParams {
   long long group_bytes;
   const float* epi_scale;  // [B]
   char* pyr;               // pyramid buffer, group blocks ordered [pair][record tile][group]
-  int dbg;                 // profiling experiments only (EZB_GEMM_DEBUG env): 1 no global stores, 2 no staging either,
-                           // 4 no MMA issue, 8 no A loads
+  int dbg;                 // profiling experiments only (EZB_GEMM_DEBUG env): 1 no global stores, 4 no MMA issue,
+                           // 8 no A loads, 16 no TMEM reads, 64 no MMA for the last 15 % of the records
 };
 
 // ------------------------------------------------------------------------------ prep kernels
@@ -187,20 +184,23 @@ __global__ void __launch_bounds__(256) pool2x2_kernel(const float* __restrict__ 
 
 // B operand: for every (pair, record tile) a [256 rows][Cp] fp16 tile; row n holds the level-l pixel of
 // (pooled) f2 that record column n stands for (zero outside the level).
-// Block = (record tile, 32-channel chunk, pair); thread n gathers its pixel over the chunk's channels (a
-// warp reads one 4x8 subtile of one channel: four full 32-byte sectors), then rows are written K-major.
+// Block = (record tile, 32-channel chunk, pair); every thread gathers its pixel over the chunk's channels, then
+// rows are written K-major.
 constexpr int PACK_CH = 32;
 struct PackParams {
   const float* lvl[PYR_MAX_LEVELS];  // level l of f2: (B, C, h[l], w[l]) fp32
   int h[PYR_MAX_LEVELS], w[PYR_MAX_LEVELS], sw[PYR_MAX_LEVELS], sub_base[PYR_MAX_LEVELS + 1];
-  int L, C, Cp, n_recs;
+  int L, C, Cp, n_recs, epl;  // epl: record elements per 128-byte line of the pyramid (64 fp16 / 32 fp32)
   const float* bscale;  // [B]
   __half* bp;           // (B, n_recs, 256, Cp)
 };
 __global__ void __launch_bounds__(256) pack_record_operand_kernel(const PackParams P) {
   __shared__ float tile[PACK_CH][PYR_REC + 1];
   const int rec = blockIdx.x, c0 = blockIdx.y * PACK_CH, b = blockIdx.z;
-  const int n = threadIdx.x;
+  // operand row (= accumulator column) threadIdx.x holds record element n (ezb_common.cuh: the epilogue's
+  // tcgen05.ld.16x256b hands every thread 32 contiguous bytes of a line)
+  const int col = threadIdx.x;
+  const int n = col / P.epl * P.epl + pyr_line_element_of_column(P.epl, col % P.epl);
   const int s = rec * PYR_SUBS_PER_TILE + n / PYR_SUB;
   int l = 0;
   while (l + 1 < P.L && s >= P.sub_base[l + 1]) ++l;
@@ -218,94 +218,77 @@ __global__ void __launch_bounds__(256) pack_record_operand_kernel(const PackPara
   const float sc = __ldg(P.bscale + b);
   const int cmax = min(PACK_CH, P.C - c0);  // channels >= C are zero-filled
 #pragma unroll 8
-  for (int c = 0; c < PACK_CH; ++c) tile[c][n] = (src != nullptr && c < cmax) ? __ldg(src + c * cstride) * sc : 0.f;
+  for (int c = 0; c < PACK_CH; ++c) tile[c][col] = (src != nullptr && c < cmax) ? __ldg(src + c * cstride) * sc : 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __half* dst = P.bp + ((long long)b * P.n_recs + rec) * PYR_REC * P.Cp + c0 + lane;
   for (int row = warp; row < PYR_REC; row += 8) dst[(long long)row * P.Cp] = __float2half_rn(tile[lane][row]);
 }
 
-// ----------------------------------------------------------------------------- epilogue helpers
-__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
+// ----------------------------------------------------------------------------- epilogue
+__device__ __forceinline__ uint32_t pack_half2(uint32_t a_bits, uint32_t b_bits) {
+  __half2 h = __floats2half2_rn(__uint_as_float(a_bits), __uint_as_float(b_bits));
   return *reinterpret_cast<uint32_t*>(&h);
 }
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
-  uint4 r;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
-  return r;
-}
-__device__ __forceinline__ void st_global_stream_v4(void* p, const uint4& v) {
-  // .cs: streaming / evict-first — the pyramid is written once and must not evict the GEMM operands from L2
-  asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
 
-// One section of a group block (32 lines of 128 bytes, one per lane).  Every lane writes its own line
-// into the warp's staging slot with the layout's XOR chunk swizzle (bank-conflict free); the slot is then
-// byte-identical to the section in global memory, and the warp streams it out with fully coalesced
-// 16-byte stores: each store instruction writes 512 contiguous bytes.
-__device__ __forceinline__ void staged_section_store(uint32_t slot, int lane, const uint32_t (&w)[32], char* gdst, int dbg) {
-  if (dbg & 2) return;
-  __syncwarp();  // the previous section's reads of this slot are done (shared-memory ops of a warp stay in order)
-#pragma unroll
-  for (int c = 0; c < 8; ++c)
-    st_shared_v4(slot + lane * 128 + ((c ^ (lane & 7)) << 4), w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
-  __syncwarp();
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const uint4 v = ld_shared_v4(slot + c * 512 + lane * 16);
-    if (!(dbg & 1)) st_global_stream_v4(gdst + c * 512 + lane * 16, v);
-  }
-}
-
-// Epilogue of one tile for one warp: 32 queries (one per lane) x HALF of a 256-element record (the two
-// warps of a TMEM lane quadrant split the record's sections) -> half of one group block.
-// TMEM loads are software-pipelined: the load of section s+1 is in flight while section s is converted,
-// staged and stored (tcgen05.wait::ld waits for everything outstanding, so it is issued right before the
-// next load).
+// Epilogue of one tile for one warp: 32 queries x one 256-element record -> one group block, no shared memory.
+// tcgen05.ld.16x256b gives thread t, for the two queries (t/4) and (t/4)+8 of a 16-lane half, the accumulator
+// columns 8i + 2(t%4) + {0,1}; the B operand is packed so that these are 32 CONTIGUOUS bytes of the query's
+// 128-byte line (ezb_common.cuh), so the four threads of a quad write one complete line and a warp-wide 256-bit
+// store writes 8 complete lines.  Loads are software-pipelined one step ahead of the convert + store.
 template <typename OutT>
-__device__ __forceinline__ void epilogue_tile(uint32_t t_base, uint32_t slot, int half, int lane, float scale,
-                                              uint32_t tmem_empty_bar, char* gblock, int dbg) {
+__device__ __forceinline__ void epilogue_tile(uint32_t t_base /* lane = first lane of the quadrant */, int part, int lane,
+                                              float scale, uint32_t tmem_empty_bar, char* gblock, int dbg) {
   constexpr bool kHalf = sizeof(OutT) == 2;
-  constexpr int kSections = (kHalf ? 4 : 8) / EPI_SPLIT;  // sections per warp; 64 / 32 record elements per 128-byte line
-  constexpr int kLoads = kHalf ? 2 : 1;           // x32 TMEM loads per section
-  const int s0 = half * kSections;
-  uint32_t r[2][kLoads][32];                      // double-buffered raw accumulator columns
-  if (dbg & 16) {  // profiling experiment: no TMEM reads at all
+  constexpr int kSections = kHalf ? 4 : 8;  // 128-byte lines per record: 64 / 32 record elements each
+  constexpr int kCols = kHalf ? 64 : 32;    // accumulator columns per section
+  constexpr int kRegs = kCols / 2;          // registers per load: 2 queries x kCols/4 columns per thread
+  constexpr int kSteps = kSections * 2 / EPI_SPLIT;  // (section, 16-lane half) steps of this warp
+  const int step0 = part * kSteps;
+  if ((dbg & 16) || gblock == nullptr) {    // nothing to write (profiling switch / query group beyond N)
     ptx::tc_fence_before();
     __syncwarp();
     if (lane == 0) ptx::mbar_arrive(tmem_empty_bar);
     return;
   }
+  const int qrow = lane >> 2, j = lane & 3;
+  auto load = [&](int lstep, uint32_t (&r)[kRegs]) {
+    const int step = step0 + lstep;
+    const uint32_t taddr = t_base + ((uint32_t)((step & 1) * 16) << 16) + (step >> 1) * kCols;
+    if constexpr (kHalf) ptx::tmem_ld_16x256b_x8(taddr, r); else ptx::tmem_ld_16x256b_x4(taddr, r);
+  };
+  uint32_t r[2][kRegs];
+  load(0, r[0]);
 #pragma unroll
-  for (int k = 0; k < kLoads; ++k) ptx::tmem_ld_32x32b_x32(t_base + (s0 * kLoads + k) * 32, r[0][k]);
-#pragma unroll
-  for (int s = 0; s < kSections; ++s) {
-    ptx::tmem_ld_wait();  // section s has landed
-    if (s + 1 < kSections) {
-#pragma unroll
-      for (int k = 0; k < kLoads; ++k) ptx::tmem_ld_32x32b_x32(t_base + ((s0 + s + 1) * kLoads + k) * 32, r[(s + 1) & 1][k]);
-    } else {  // this warp's part of the accumulator is in registers: hand the TMEM buffer back to the MMA warp
+  for (int step = 0; step < kSteps; ++step) {
+    ptx::tmem_ld_wait();  // `step` has landed
+    if (step + 1 < kSteps) {
+      load(step + 1, r[(step + 1) & 1]);
+    } else {  // accumulator fully drained into registers: hand the TMEM buffer back to the MMA warp
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tmem_empty_bar);
     }
-    uint32_t w[32];
+    const uint32_t(&v)[kRegs] = r[step & 1];
+    const int gs = step0 + step;
+    char* line0 = gblock + (gs >> 1) * 4096 + ((gs & 1) * 16 + qrow) * 128 + j * 32;  // query (t/4); +8 queries = +1024 B
+    if (dbg & 1) continue;
     if constexpr (kHalf) {
       // fp16 storage: the store factor is folded into the B operand, the accumulator is the stored value
+      uint32_t w0[8], w1[8];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        w[j] = pack_half2(__uint_as_float(r[s & 1][0][2 * j]), __uint_as_float(r[s & 1][0][2 * j + 1]));
-        w[16 + j] = pack_half2(__uint_as_float(r[s & 1][1][2 * j]), __uint_as_float(r[s & 1][1][2 * j + 1]));
+      for (int i = 0; i < 8; ++i) {
+        w0[i] = pack_half2(v[4 * i], v[4 * i + 1]);
+        w1[i] = pack_half2(v[4 * i + 2], v[4 * i + 3]);
       }
+      ptx::st_global_v8_hint(line0, w0[0], w0[1], w0[2], w0[3], w0[4], w0[5], w0[6], w0[7], ptx::kEvictFirst);
+      ptx::st_global_v8_hint(line0 + 1024, w1[0], w1[1], w1[2], w1[3], w1[4], w1[5], w1[6], w1[7], ptx::kEvictFirst);
     } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(__uint_as_float(r[s & 1][0][j]) * scale);
+      auto sc = [&](uint32_t bits) { return __float_as_uint(__uint_as_float(bits) * scale); };
+      ptx::st_global_v8_hint(line0, sc(v[0]), sc(v[1]), sc(v[4]), sc(v[5]), sc(v[8]), sc(v[9]), sc(v[12]), sc(v[13]), ptx::kEvictFirst);
+      ptx::st_global_v8_hint(line0 + 1024, sc(v[2]), sc(v[3]), sc(v[6]), sc(v[7]), sc(v[10]), sc(v[11]), sc(v[14]), sc(v[15]),
+                             ptx::kEvictFirst);
     }
-    if (gblock != nullptr) staged_section_store(slot, lane, w, gblock + (s0 + s) * 4096, dbg);  // null: group beyond N
   }
 }
 
@@ -318,7 +301,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw_addr);
-  const uint32_t sB = base + SMEM_B, sA = base + SMEM_A, sStg = base + SMEM_STG, sBar = base + SMEM_BAR;
+  const uint32_t sB = base + SMEM_B, sA = base + SMEM_A, sBar = base + SMEM_BAR;
   auto full_bar = [&](int s) { return sBar + 8u * s; };
   auto empty_bar = [&](int s) { return sBar + 8u * (STAGES + s); };
   const uint32_t b_full = sBar + 8u * (2 * STAGES), b_empty = b_full + 8u;
@@ -421,7 +404,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           ptx::tc_fence_after();
           const uint64_t a_desc = ptx::umma_desc_kmajor_sw128(sA + stage * A_STAGE_BYTES);
           const uint64_t b_desc = ptx::umma_desc_kmajor_sw128(sB + kb * B_KB_BYTES);
-          if (!(p.dbg & 4)) {
+          // dbg 64: no MMA for the last 15.5 % of the records (what pooling level 1 in the epilogue would save)
+          const bool skip_mma = (p.dbg & 4) || ((p.dbg & 64) && (int)(t / p.n_qblocks) * CLUSTER >= p.n_recs * 147 / 174);
+          if (!skip_mma) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)  // UMMA_K = 16 fp16 = 32 B = +2 in the descriptor's 16-byte units
               ptx::umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
@@ -434,8 +419,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int quad = warp & 3;         // TMEM lane quadrant this warp may access
-    const int half = (warp - 4) >> 2;  // which half of the record's sections
-    const uint32_t slot = sStg + (warp - 4) * (SLOTS_PER_WARP * SLOT_BYTES);
+    const int part = (warp - 4) >> 2;  // which share of the record's (section, half) steps
     uint32_t tile = 0;
     for (int b = 0; b < p.B; ++b) {
       const float scale = __ldg(p.epi_scale + b);
@@ -450,7 +434,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         const uint32_t t_base = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
         const int grp = qb * (BM / 32) + quad;  // query group of this warp; blocks are ordered [pair][patch][group]
         char* gblock = (grp < p.n_groups && rec < p.n_recs) ? p.pyr + (bp * p.n_groups + grp) * p.group_bytes : nullptr;
-        epilogue_tile<OutT>(t_base, slot, half, lane, scale, tmem_empty(acc), gblock, p.dbg);
+        epilogue_tile<OutT>(t_base, part, lane, scale, tmem_empty(acc), gblock, p.dbg);
       }
     }
   }
@@ -675,7 +659,7 @@ extern "C" int ezb_corr_pyramid_fwd_ex(const float* fmap1, const float* fmap2, i
     pk.sub_base[l] = lay.sub_base[l];
   }
   pk.sub_base[PYR_MAX_LEVELS] = lay.sub_base[PYR_MAX_LEVELS];
-  pk.L = L; pk.C = C; pk.Cp = Cp; pk.n_recs = lay.n_tiles;
+  pk.L = L; pk.C = C; pk.Cp = Cp; pk.n_recs = lay.n_tiles; pk.epl = 128 / lay.es;
   pk.bscale = ws.bscale;
   pk.bp = ws.f2p;
   for (int l = 1; l < L; ++l) {

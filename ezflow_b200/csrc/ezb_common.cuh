@@ -109,11 +109,11 @@ inline bool pyramid_geom(int H, int W, int L, int dtype, LevelGeom* g) {
 // avg-pooling is linear, so level l is the correlation with the l-times pooled fmap2.
 // Queries are taken 32 at a time (one epilogue warp).  For one (pair, tile, query group) the 32 records
 // form a contiguous *group block* of sections; section j holds, for each of the 32 queries, a 128-byte
-// line with record elements [j*EPL, (j+1)*EPL), EPL = 64 (fp16) or 32 (fp32).  Inside a line the 16-byte
-// chunks are XOR-swizzled with the lane index so that the epilogue's shared-memory staging (byte-identical
-// to the global section) is bank-conflict free; 32-byte sectors and 64-byte subtiles are preserved by the
-// XOR (as sets), and a subtile is one 128-byte line in fp16 (two in fp32).  Blocks are ordered [pair][tile][group]: one GEMM tile (128 queries x one record) writes 4
-// consecutive blocks = 64 KB (fp16) of contiguous memory.  Pixels outside a level's valid area (and
+// line with record elements [j*EPL, (j+1)*EPL), EPL = 64 (fp16) or 32 (fp32); a subtile is one 128-byte line in
+// fp16 (two in fp32).  The GEMM epilogue writes lines straight from registers: four threads hold the four 32-byte
+// quarters of a query's line, so one 256-bit store instruction of a warp writes 8 complete 128-byte lines.
+// Blocks are ordered [pair][tile][group]: one GEMM tile (128 queries x one record) writes 4 consecutive blocks =
+// 64 KB (fp16) of contiguous memory.  Pixels outside a level's valid area (and
 // levels >= L) are exact zeros.
 // --------------------------------------------------------------------------------------------
 constexpr int PYR_SY = 8, PYR_SX = 8, PYR_SUB = PYR_SY * PYR_SX, PYR_QG = 32, PYR_MAX_LEVELS = 4, PYR_REC = 256;
@@ -150,8 +150,13 @@ inline bool pyr_layout(int H, int W, int L, int dtype, PyrLayout* p) {
 // byte offset, inside a group block, of record element n (0..255) of query `lane` of the group
 __host__ __device__ inline int pyr_record_offset(int es, int lane, int n) {
   const int epl = 128 / es;  // record elements per 128-byte line
-  const int sec = n / epl, inl = (n - sec * epl) * es;
-  return sec * 4096 + lane * 128 + (((inl >> 4) ^ (lane & 7)) << 4) + (inl & 15);
+  const int sec = n / epl;
+  return sec * 4096 + lane * 128 + (n - sec * epl) * es;
 }
+// The GEMM epilogue reads the accumulator with tcgen05.ld.16x256b, which hands thread t the columns 8i + 2(t%4) + {0,1};
+// for a thread's values to be 32 contiguous bytes of its query's line, accumulator column c of a line holds line element
+//   m(c) = ((c%8)/2 * (epl/8) + c/8) * 2 + c%2,
+// i.e. row c of the packed B operand is the f2 pixel of record element m(c) (pack_record_operand_kernel).
+__host__ __device__ inline int pyr_line_element_of_column(int epl, int c) { return (((c & 7) >> 1) * (epl >> 3) + (c >> 3)) * 2 + (c & 1); }
 
 }  // namespace ezb
