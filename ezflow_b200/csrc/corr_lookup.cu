@@ -186,15 +186,16 @@ struct LookupBwdParams {
   int B, N, L, r;
 };
 
-// dpyr[l][b,q,y,x] += sum over window taps of weight * dout.  A query's gradient patch is private to
-// that query, so the block first builds the (2r+2)^2 patch in shared memory (each element gathers <= 4
-// taps) and then adds it to HBM with coalesced row-segment reductions (no inter-query conflicts).
+// dpyr[l][b,q,y,x] += sum over window taps of weight * dout.  A query's gradient window is private to that query (no
+// inter-query conflicts).  The block stages dout for its 32 queries in shared memory (coalesced loads, lane = query);
+// then a thread owns one window ROW of one (query, level): it slides along x keeping the vertically-combined value of
+// the previous window column, so every gradient element costs two shared-memory reads, and adds the row to HBM as
+// 8-byte-aligned pairs (red.global.add.v2.f32) with scalar ends.
 __global__ void __launch_bounds__(NTHREADS) corr_lookup_bwd_kernel(const LookupBwdParams P) {
   extern __shared__ float sm[];
-  const int r = P.r, D = 2 * r + 2, DD = D * D, K = 2 * r + 1, KK = K * K;
+  const int r = P.r, D = 2 * r + 2, K = 2 * r + 1, KK = K * K;
   const int dstride = (P.L * KK) | 1;  // dout values per query (odd stride)
   float* s_d = sm;                     // [QB][dstride]
-  float* s_g = sm + QB * dstride;      // [QB][L*DD]
   const int b = blockIdx.y, q0 = blockIdx.x * QB;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* cx_ptr = P.coords + (long long)b * 2 * P.N;
@@ -204,48 +205,69 @@ __global__ void __launch_bounds__(NTHREADS) corr_lookup_bwd_kernel(const LookupB
   {
     const int q = q0 + lane;
     const float* src = P.dout + (long long)b * P.L * KK * P.N + q;
-    for (int c = warp; c < P.L * KK; c += NTHREADS / 32) s_d[lane * dstride + c] = (q < P.N) ? __ldg(src + (long long)c * P.N) : 0.f;
+    const int nch = P.L * KK, nw = NTHREADS / 32;
+    for (int c0 = warp; c0 < nch; c0 += 8 * nw) {  // 8 independent loads in flight per thread
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int c = c0 + u * nw;
+        v[u] = (q < P.N && c < nch) ? __ldg(src + (long long)c * P.N) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int c = c0 + u * nw;
+        if (c < nch) s_d[lane * dstride + c] = v[u];
+      }
+    }
   }
   __syncthreads();
-  // gradient patches: thread -> (query, level, Y, X)
-  for (int idx = threadIdx.x; idx < QB * P.L * DD; idx += NTHREADS) {
-    const int ql = idx / (P.L * DD);
-    int rem = idx - ql * (P.L * DD);
-    const int l = rem / DD;
-    rem -= l * DD;
-    const int Y = rem / D, X = rem - Y * D;
-    const int q = min(q0 + ql, P.N - 1);
+
+  // thread -> (level, window row Y, query): consecutive threads take consecutive queries (conflict-free s_d reads)
+  for (int idx = threadIdx.x; idx < QB * P.L * D; idx += NTHREADS) {
+    const int ql = idx % QB, ly = idx / QB, l = ly / D, Y = ly - l * D;
+    const int q = q0 + ql;
+    if (q >= P.N) continue;
     const float inv = 1.0f / (float)(1 << l);
     const float cx = __ldg(cx_ptr + q) * inv, cy = __ldg(cy_ptr + q) * inv;
     const float fx = cx - floorf(cx), fy = cy - floorf(cy);
-    const float* d = s_d + ql * dstride + l * KK;
-    // out(i,j) touches patch (row j+a, col i+c) with weight wy[a]*wx[c]; invert: i = X-c, j = Y-a
-    float g = 0.f;
-#pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int i = X - c, j = Y - a;
-        if (i >= 0 && i < K && j >= 0 && j < K) g += (a ? fy : 1.f - fy) * (c ? fx : 1.f - fx) * d[i * K + j];
-      }
-    s_g[ql * (P.L * DD) + l * DD + Y * D + X] = g;
-  }
-  __syncthreads();
-  // add to HBM: warp per (query, level), lanes sweep the patch row-major (row segments are contiguous)
-  for (int item = warp; item < QB * P.L; item += NTHREADS / 32) {
-    const int l = item / QB, ql = item - l * QB, q = q0 + ql;
-    if (q >= P.N) continue;
-    const float inv = 1.0f / (float)(1 << l);
     const int hl = P.h[l], wl = P.w[l];
-    const int x0 = float_floor_to_int_clamped(__ldg(cx_ptr + q) * inv, -(1 << 24), 1 << 24);
-    const int y0 = float_floor_to_int_clamped(__ldg(cy_ptr + q) * inv, -(1 << 24), 1 << 24);
-    const int xs = max(-D, min(wl, x0 - r)), ys = max(-D, min(hl, y0 - r));
-    float* dst = P.dlvl[l] + ((long long)b * P.N + q) * P.qstride[l];
-    const float* g = s_g + ql * (P.L * DD) + l * DD;
-    for (int e = lane; e < DD; e += 32) {
-      const int Y = e / D, X = e - Y * D;
-      const int yy = ys + Y, xx = xs + X;
-      if (yy >= 0 && yy < hl && xx >= 0 && xx < wl) atomicAdd(dst + (long long)yy * P.pitch[l] + xx, g[e]);
+    const int xs = max(-D, min(wl, float_floor_to_int_clamped(cx, -(1 << 24), 1 << 24) - r));
+    const int ys = max(-D, min(hl, float_floor_to_int_clamped(cy, -(1 << 24), 1 << 24) - r));
+    const int yy = ys + Y;
+    if (yy < 0 || yy >= hl) continue;
+    // out(i,j) touches window (row j+a, col i+c) with weight wy[a]*wx[c]  =>  row Y collects j = Y (a=0) and j = Y-1 (a=1)
+    const float wy0 = (Y < K) ? 1.f - fy : 0.f, wy1 = (Y >= 1) ? fy : 0.f;
+    const float* d0 = s_d + ql * dstride + l * KK + min(Y, K - 1);  // + i*K: dout(i, j=Y)
+    const float* d1 = s_d + ql * dstride + l * KK + max(Y - 1, 0);  // + i*K: dout(i, j=Y-1)
+    float* row = P.dlvl[l] + ((long long)b * P.N + q) * P.qstride[l] + (long long)yy * P.pitch[l] + xs;
+    float prev = 0.f;  // vertically combined dout of window column X-1
+    auto next = [&](int X) {  // gradient of window element (Y, X); X must advance by one per call
+      const float cur = (X < K) ? wy0 * d0[X * K] + wy1 * d1[X * K] : 0.f;
+      const float g = (1.f - fx) * cur + fx * prev;
+      prev = cur;
+      return g;
+    };
+    int X = 0;
+    if ((reinterpret_cast<uintptr_t>(row) >> 2) & 1) {  // first address 8-byte misaligned: scalar head
+      const float g = next(0);
+      if (xs >= 0 && xs < wl) atomicAdd(row, g);
+      X = 1;
+    }
+    for (; X + 1 < D; X += 2) {
+      const float g0 = next(X), g1 = next(X + 1);
+      const int xx = xs + X;
+      const bool v0 = xx >= 0 && xx < wl, v1 = xx + 1 >= 0 && xx + 1 < wl;
+      if (v0 && v1) {
+        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(row + X), "f"(g0), "f"(g1) : "memory");
+      } else if (v0) {
+        atomicAdd(row + X, g0);
+      } else if (v1) {
+        atomicAdd(row + X + 1, g1);
+      }
+    }
+    if (X < D) {
+      const float g = next(X);
+      if (xs + X >= 0 && xs + X < wl) atomicAdd(row + X, g);
     }
   }
 }
@@ -346,7 +368,7 @@ extern "C" int ezb_corr_lookup_bwd(const float* dout, const float* coords, int B
   P.L = L;
   P.r = radius;
   const int D = 2 * radius + 2, K = 2 * radius + 1;
-  const size_t smem = (size_t)k3::QB * (((L * K * K) | 1) + L * D * D) * sizeof(float);
+  const size_t smem = (size_t)k3::QB * ((L * K * K) | 1) * sizeof(float);
   if (smem > 200 * 1024) return fail(EZB_ERR_UNSUPPORTED, "lookup window too large (L=%d, r=%d)", L, radius);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   EZB_CUDA_OK(cudaFuncSetAttribute(k3::corr_lookup_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
