@@ -48,6 +48,7 @@ constexpr int SMEM_BYTES = SMEM_BAR + 256 + 1024;
 
 struct Params {
   int G, H, W, oh, ow, Ph, Pw, sh, sw, padh, padw, D, KB;
+  int nsplit;  // CTAs sharing one query tile (each sweeps a slice of its target tiles): balances the last wave
   int dph[MAX_DIL], dpw[MAX_DIL];
   float slope;
   const float* deq;  // [BG]: user scale * 2^(e1+e2)
@@ -86,7 +87,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + SMEM_BAR + 8 * (2 * STAGES + 1 + 2 * NACC));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qx0 = blockIdx.x * QTW, qy0 = blockIdx.y * QTH, bg = blockIdx.z;
+  const int qx0 = blockIdx.x * QTW, qy0 = blockIdx.y * QTH;
+  const int bg = blockIdx.z / P.nsplit, split = blockIdx.z - bg * P.nsplit;
 
   // bounding box (in2 pixel coordinates, clipped to the image) of every target any query of this tile needs
   int mdh_max = 0, mdw_max = 0;
@@ -100,7 +102,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   const int x_hi = min(P.W - 1, (min(qx0 + QTW, P.ow) - 1) * P.sw - P.padw + mdw_max);
   const int nty = y_hi >= y_lo ? (y_hi - y_lo) / TTH + 1 : 0;
   const int ntx = x_hi >= x_lo ? (x_hi - x_lo) / TTW + 1 : 0;
-  const int ntiles = nty * ntx;
+  const int ntiles_all = nty * ntx;
+  const int tt_begin = ntiles_all * split / P.nsplit, tt_end = ntiles_all * (split + 1) / P.nsplit;
+  const int ntiles = tt_end - tt_begin;  // this CTA sweeps target tiles [tt_begin, tt_end)
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -137,7 +141,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     }
     uint32_t stage = 0, phase = 0;
     for (int tt = 0; tt < ntiles; ++tt) {
-      const int ty0 = y_lo + (tt / ntx) * TTH, tx0 = x_lo + (tt % ntx) * TTW;
+      const int ty0 = y_lo + ((tt_begin + tt) / ntx) * TTH, tx0 = x_lo + ((tt_begin + tt) % ntx) * TTW;
       for (int kb = 0; kb < P.KB; ++kb) {
         ptx::mbar_wait(empty_bar(stage), phase ^ 1);
         ptx::mbar_expect_tx(full_bar(stage), B_STAGE_BYTES);
@@ -188,7 +192,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     constexpr int CPW = BN / EPI_SPLIT;  // accumulator columns per warp
 
     // displacements that point outside the image: zeros (act(0) = 0), written once, up front
-    if (q_ok) {
+    if (q_ok && split == 0) {
       for (int d = 0; d < P.D; ++d) {
         const int dph = P.dph[d], dpw = P.dpw[d];
         const int y2_0 = oy * P.sh - P.padh - dph * (P.Ph - 1) / 2, x2_0 = ox * P.sw - P.padw - dpw * (P.Pw - 1) / 2;
@@ -205,7 +209,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     }
 
     for (int tt = 0; tt < ntiles; ++tt) {
-      const int ty0 = y_lo + (tt / ntx) * TTH, tx0 = x_lo + (tt % ntx) * TTW;
+      const int ty0 = y_lo + ((tt_begin + tt) / ntx) * TTH, tx0 = x_lo + ((tt_begin + tt) % ntx) * TTW;
       const int ty1 = min(ty0 + TTH, P.H) - 1, tx1 = min(tx0 + TTW, P.W) - 1;  // last in-image row / column of the tile
       const uint32_t acc = tt % NACC, aphase = (tt / NACC) & 1;
       ptx::mbar_wait(tmem_full(acc), aphase);
@@ -347,7 +351,23 @@ int local_corr_tc_launch(const float* in1, const float* in2, int BG, int G, int 
   P.deq = ws.deq;
   P.out = out;
   P.out_bstride = out_bstride;
-  dim3 grid(cdiv(P.ow, QTW), cdiv(P.oh, QTH), BG);
+  // split the target sweep of a query tile over several CTAs when there are too few query tiles to fill the GPU evenly
+  const int n_qtiles = cdiv(P.ow, QTW) * cdiv(P.oh, QTH) * BG;
+  int dmax_h = 1, dmax_w = 1;
+  for (int d = 0; d < D; ++d) { dmax_h = std::max(dmax_h, dph[d]); dmax_w = std::max(dmax_w, dpw[d]); }
+  const int max_tiles = std::min(cdiv(H, TTH) + 1, cdiv((Ph - 1) * dmax_h + QTH * sh, TTH) + 1) *
+                        std::min(cdiv(W, TTW) + 1, cdiv((Pw - 1) * dmax_w + QTW * sw, TTW) + 1);
+  // cost model: CTAs run in waves of one per SM; a CTA costs its share of the target tiles plus ~2 tiles of fixed work
+  P.nsplit = 1;
+  {
+    const int sms = num_sms();
+    long long best = (long long)cdiv(n_qtiles, sms) * (max_tiles + 2);
+    for (int k = 2; k <= 8 && max_tiles / k >= 4; ++k) {
+      const long long c = (long long)cdiv(n_qtiles * k, sms) * (cdiv(max_tiles, k) + 2);
+      if (c < best) { best = c; P.nsplit = k; }
+    }
+  }
+  dim3 grid(cdiv(P.ow, QTW), cdiv(P.oh, QTH), BG * P.nsplit);
   EZB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "output too large for one launch");
   EZB_CUDA_OK(cudaFuncSetAttribute(local_corr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   local_corr_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, P);
