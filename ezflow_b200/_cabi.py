@@ -12,7 +12,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(_HERE, "_lib", "libezflow_b200.so")
+LIBPATH = os.environ.get("EZB_LIBRARY") or os.path.join(_HERE, "_lib", "libezflow_b200.so")  # env override: experiment builds
 
 EZB_F32, EZB_F16 = 0, 1
 EZB_MAX_LEVELS = 8

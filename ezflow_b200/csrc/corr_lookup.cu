@@ -367,7 +367,7 @@ extern "C" int ezb_corr_lookup_bwd(const float* dout, const float* coords, int B
   P.N = N;
   P.L = L;
   P.r = radius;
-  const int D = 2 * radius + 2, K = 2 * radius + 1;
+  const int K = 2 * radius + 1;
   const size_t smem = (size_t)k3::QB * ((L * K * K) | 1) * sizeof(float);
   if (smem > 200 * 1024) return fail(EZB_ERR_UNSUPPORTED, "lookup window too large (L=%d, r=%d)", L, radius);
   cudaStream_t st = static_cast<cudaStream_t>(stream);

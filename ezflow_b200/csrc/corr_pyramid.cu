@@ -45,7 +45,10 @@ constexpr int KB_MAX = 4;         // resident B k-blocks  (C <= 256)
 #endif
 constexpr int STAGES = EZB_GEMM_STAGES;  // A ring
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
-constexpr int CLUSTER = 2;                   // CTAs sharing one A stream
+#ifndef EZB_GEMM_CLUSTER
+#define EZB_GEMM_CLUSTER 2
+#endif
+constexpr int CLUSTER = EZB_GEMM_CLUSTER;    // CTAs sharing one A stream
 constexpr int A_SLICE_ROWS = BM / CLUSTER;   // rows of an A stage each CTA of the cluster fetches (and multicasts)
 constexpr int B_KB_BYTES = BN * BK * 2;      // 32 KB
 #ifndef EZB_GEMM_EPI_SPLIT
