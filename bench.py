@@ -90,6 +90,10 @@ def cpu_port_pairs_per_sec(rows_per_worker, workers=None, repeats=1):
     band of `rows_per_worker` query rows.  Returns (pairs/s, cores, sample description)."""
     import multiprocessing as mp
 
+    try:  # the GPU leg may have pinned this process next to its GPU: the CPU baseline gets every host core
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))
+    except (AttributeError, OSError):
+        pass
     workers = workers or os.cpu_count() or 1
     ctx = mp.get_context("fork")
     best = None
@@ -225,6 +229,23 @@ class ClockSampler:
         return out
 
 
+def _bind_to_gpu_numa_node(index):
+    """Pins this process to the CPUs NVML reports as closest to GPU `index` (no-op when NVML cannot tell)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = index
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if index < len(ids) and ids[index].isdigit():
+                phys = int(ids[index])
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys))
+    except Exception:
+        pass
+
+
 def run_b200(args):
     import torch
 
@@ -239,9 +260,11 @@ def run_b200(args):
         raise RuntimeError("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    _bind_to_gpu_numa_node(local_rank)  # pinned host buffers are then first-touched next to this GPU's PCIe root
     if world > 1:
         import torch.distributed as dist
 
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     E.set_pyramid_dtype(args.pyramid_dtype)
     lib = _cabi.lib()
