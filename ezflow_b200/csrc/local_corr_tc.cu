@@ -68,8 +68,10 @@ __global__ void tc_scales_kernel(const unsigned int* __restrict__ amax, int BG, 
   deq[i] = scale * __uint_as_float((unsigned int)(e + 127) << 23);
 }
 
-__device__ __forceinline__ int floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }  // b > 0
-__device__ __forceinline__ int ceil_div(int a, int b) { return -floor_div(-a, b); }
+// floor(a / b) and ceil(a / b) for small |a| and b > 0 through a reciprocal: (a + 0.5) / b is never within 0.5/b >= 2^-5 of an
+// integer, far more than the rounding error of the float product, so the floor is exact (|a| < 2^15)
+__device__ __forceinline__ int floor_div(int a, float inv_b) { return __float2int_rd(((float)a + 0.5f) * inv_b); }
+__device__ __forceinline__ int ceil_div(int a, float inv_b) { return -floor_div(-a, inv_b); }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     local_corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params P) {
@@ -235,8 +237,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         const int dph = P.dph[d], dpw = P.dpw[d];
         const int y2_0 = oy * P.sh - P.padh - dph * (P.Ph - 1) / 2, x2_0 = ox * P.sw - P.padw - dpw * (P.Pw - 1) / 2;
         // this lane's displacement ranges whose target lies in the in-image part of the tile
-        int a_lo = max(0, ceil_div(ty0 - y2_0, dph)), a_hi = min(P.Ph - 1, floor_div(ty1 - y2_0, dph));
-        int b_lo = max(0, ceil_div(tx0 - x2_0, dpw)), b_hi = min(P.Pw - 1, floor_div(tx1 - x2_0, dpw));
+        const float inv_dph = __frcp_rn((float)dph), inv_dpw = __frcp_rn((float)dpw);
+        int a_lo = max(0, ceil_div(ty0 - y2_0, inv_dph)), a_hi = min(P.Ph - 1, floor_div(ty1 - y2_0, inv_dph));
+        int b_lo = max(0, ceil_div(tx0 - x2_0, inv_dpw)), b_hi = min(P.Pw - 1, floor_div(tx1 - x2_0, inv_dpw));
         if (!q_ok || a_lo > a_hi || b_lo > b_hi) { a_lo = b_lo = INT_MAX; a_hi = b_hi = INT_MIN; }
         // all lanes walk the union so that a store instruction covers one (pi, pj): contiguous output pixels
         const int ua_lo = __reduce_min_sync(0xffffffffu, a_lo), ua_hi = __reduce_max_sync(0xffffffffu, a_hi);
