@@ -145,13 +145,15 @@ __global__ void scales_kernel(const unsigned int* __restrict__ amax, int B, int 
 }
 
 // A operand: fp32 (B,C,N) -> fp16 (B,N,Cp) scaled by 2^-e1 (per pair); channels >= C zero-filled.
+// With a second tensor (src1/dst1), blockIdx.z in [B, 2B) converts it with the scales amax[B + b].
 __global__ void __launch_bounds__(256) convert_kmajor_kernel(const float* __restrict__ f1, __half* __restrict__ o1,
-                                                             const unsigned int* __restrict__ amax, int C, int Cp, int N) {
+                                                             const float* __restrict__ src1, __half* __restrict__ dst1,
+                                                             const unsigned int* __restrict__ amax, int B, int C, int Cp, int N) {
   __shared__ float tile[64][33];
-  const int b = blockIdx.z;
-  const float* src = f1 + (long long)b * C * N;
-  __half* dst = o1 + (long long)b * N * Cp;
-  const float s = pow2f(-pow2_exponent(amax[b]));
+  const int which = blockIdx.z >= B, b = blockIdx.z - which * B;
+  const float* src = (which ? src1 : f1) + (long long)b * C * N;
+  __half* dst = (which ? dst1 : o1) + (long long)b * N * Cp;
+  const float s = pow2f(-pow2_exponent(amax[blockIdx.z]));
   const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -560,7 +562,14 @@ int launch_absmax(const float* t0, const float* t1, long long per_b, unsigned in
 }
 int launch_convert_kmajor(const float* src, __half* dst, const unsigned int* amax, int B, int C, int Cp, int N, cudaStream_t st) {
   EZB_REQUIRE(B <= 65535 && Cp % 64 == 0, "bad arguments");
-  k1::convert_kmajor_kernel<<<dim3(cdiv(N, 32), Cp / 64, B), 256, 0, st>>>(src, dst, amax, C, Cp, N);
+  k1::convert_kmajor_kernel<<<dim3(cdiv(N, 32), Cp / 64, B), 256, 0, st>>>(src, dst, nullptr, nullptr, amax, B, C, Cp, N);
+  EZB_LAUNCH_OK();
+  return EZB_OK;
+}
+int launch_convert_kmajor2(const float* src0, __half* dst0, const float* src1, __half* dst1, const unsigned int* amax, int B, int C,
+                           int Cp, int N, cudaStream_t st) {
+  EZB_REQUIRE(2 * B <= 65535 && Cp % 64 == 0, "bad arguments");
+  k1::convert_kmajor_kernel<<<dim3(cdiv(N, 32), Cp / 64, 2 * B), 256, 0, st>>>(src0, dst0, src1, dst1, amax, B, C, Cp, N);
   EZB_LAUNCH_OK();
   return EZB_OK;
 }

@@ -71,6 +71,9 @@ namespace prep {
 int launch_absmax(const float* t0, const float* t1, long long per_b, unsigned int* amax, int B, cudaStream_t st);
 // fp32 (B,C,N) -> fp16 (B,N,Cp) scaled by 2^-floor(log2(amax[b])) (into (-2,2)); channels >= C zero-filled
 int launch_convert_kmajor(const float* src, __half* dst, const unsigned int* amax, int B, int C, int Cp, int N, cudaStream_t st);
+// both tensors in one launch: src0 with amax[b], src1 with amax[B + b]
+int launch_convert_kmajor2(const float* src0, __half* dst0, const float* src1, __half* dst1, const unsigned int* amax, int B, int C,
+                           int Cp, int N, cudaStream_t st);
 // floor 2x2 average pool of `planes` images (hs x ws, plane stride src_plane) into (hd x wd, plane stride dst_plane)
 int launch_pool2x2(const float* src, float* dst, long long planes, int hs, int ws, long long src_plane, int hd, int wd,
                    long long dst_plane, cudaStream_t st);

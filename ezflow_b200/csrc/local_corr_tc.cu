@@ -51,21 +51,20 @@ struct Params {
   int nsplit;  // CTAs sharing one query tile (each sweeps a slice of its target tiles): balances the last wave
   int dph[MAX_DIL], dpw[MAX_DIL];
   float slope;
-  const float* deq;  // [BG]: user scale * 2^(e1+e2)
+  const unsigned int* amax;  // [2][BG] float bits of max|in1|, max|in2| per (batch, group): operands were scaled by 2^-e
+  float scale;               // user scale (CorrelationLayer: 1/C)
   float* out;
   long long out_bstride;
 };
 
-__global__ void tc_scales_kernel(const unsigned int* __restrict__ amax, int BG, float scale, float* __restrict__ deq) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= BG) return;
+// 2^(e1+e2): undoes the power-of-two pre-scales of the two operands (e = floor(log2(absmax)), 0 for an all-zero tensor)
+__device__ __forceinline__ float dequant_factor(unsigned int amax1_bits, unsigned int amax2_bits) {
   auto ex = [](unsigned int bits) {
     const int e = (int)((bits >> 23) & 0xff);
     return e == 0 ? 0 : e - 127;
   };
-  int e = ex(amax[i]) + ex(amax[BG + i]);
-  e = max(-126, min(126, e));
-  deq[i] = scale * __uint_as_float((unsigned int)(e + 127) << 23);
+  const int e = max(-126, min(126, ex(amax1_bits) + ex(amax2_bits)));
+  return __uint_as_float((unsigned int)(e + 127) << 23);
 }
 
 // floor(a / b) and ceil(a / b) for small |a| and b > 0 through a reciprocal: (a + 0.5) / b is never within 0.5/b >= 2^-5 of an
@@ -186,7 +185,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     const int oy = qy0 + q / QTW, ox = qx0 + q % QTW;
     const bool q_ok = oy < P.oh && ox < P.ow;
     const int b = bg / P.G, g = bg - b * P.G;
-    const float deq = __ldg(P.deq + bg);
+    const float deq = P.scale * dequant_factor(__ldg(P.amax + bg), __ldg(P.amax + gridDim.z / P.nsplit + bg));
     const long long plane = (long long)P.oh * P.ow;
     float* out_q = P.out + (long long)b * P.out_bstride + (long long)oy * P.ow + ox;
     float* Srow = S + q * S_STRIDE;
@@ -279,7 +278,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 
 struct Workspace {
   unsigned int* amax;  // [2][BG]
-  float* deq;          // [BG]
   __half* in1h;        // (BG, H, W, Cp)
   __half* in2h;
 };
@@ -294,12 +292,10 @@ static size_t ws_layout(int BG, int C, int H, int W, void* base, Workspace* ws) 
     return r;
   };
   const uintptr_t amax = take((size_t)2 * BG * 4, 256);
-  const uintptr_t deq = take((size_t)BG * 4, 256);
   const uintptr_t a = take((size_t)BG * H * W * Cp * 2, 1024);
   const uintptr_t b = take((size_t)BG * H * W * Cp * 2, 1024);
   if (ws) {
     ws->amax = reinterpret_cast<unsigned int*>(amax);
-    ws->deq = reinterpret_cast<float*>(deq);
     ws->in1h = reinterpret_cast<__half*>(a);
     ws->in2h = reinterpret_cast<__half*>(b);
   }
@@ -327,10 +323,7 @@ int local_corr_tc_launch(const float* in1, const float* in2, int BG, int G, int 
   EZB_REQUIRE(BG <= 65535, "batch too large for one launch (split it)");
 
   if (int r = prep::launch_absmax(in1, in2, (long long)C * N, ws.amax, BG, st)) return r;
-  tc_scales_kernel<<<cdiv(BG, 128), 128, 0, st>>>(ws.amax, BG, scale, ws.deq);
-  EZB_LAUNCH_OK();
-  if (int r = prep::launch_convert_kmajor(in1, ws.in1h, ws.amax, BG, C, Cp, N, st)) return r;
-  if (int r = prep::launch_convert_kmajor(in2, ws.in2h, ws.amax + BG, BG, C, Cp, N, st)) return r;
+  if (int r = prep::launch_convert_kmajor2(in1, ws.in1h, in2, ws.in2h, ws.amax, BG, C, Cp, N, st)) return r;
 
   CUtensorMap tmA, tmB;
   cuuint64_t dims[4] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)BG};
@@ -351,7 +344,8 @@ int local_corr_tc_launch(const float* in1, const float* in2, int BG, int G, int 
   P.D = D; P.KB = Cp / BK;
   for (int d = 0; d < D; ++d) { P.dph[d] = dph[d]; P.dpw[d] = dpw[d]; }
   P.slope = slope;
-  P.deq = ws.deq;
+  P.amax = ws.amax;
+  P.scale = scale;
   P.out = out;
   P.out_bstride = out_bstride;
   // split the target sweep of a query tile over several CTAs when there are too few query tiles to fill the GPU evenly
