@@ -73,6 +73,30 @@ def test_backward_vs_reference_golden(golden, name):
     assert_close(f2.grad, g["df2"], GRAD_TOL, f"{name} dfmap2")
 
 
+@pytest.mark.parametrize("shape", [(2, 40, 9, 11), (2, 256, 12, 20), (1, 256, 11, 13)])
+def test_backward_vs_oracle_shapes(shape):
+    """Adjoints vs the numpy oracle on shapes the golden fixtures do not hold: H*W % 4 != 0 (TMA cannot describe the
+    operands: fold + fp32 CUDA-core GEMMs) and H*W % 4 == 0 with C = 256 (tf32 tcgen05 GEMMs over all levels), B = 2."""
+    import ezflow_b200 as E
+    from oracle import similarity_oracle as O
+
+    rng = np.random.default_rng(21)
+    B, C, H, W = shape
+    L, r = 3, 2
+    f1n = rng.standard_normal(shape).astype(np.float32)
+    f2n = rng.standard_normal(shape).astype(np.float32)
+    coords = O.coords_grid(B, H, W) + rng.uniform(-3, 3, (B, 2, H, W)).astype(np.float32)
+    dout = rng.standard_normal((B, L * (2 * r + 1) ** 2, H, W)).astype(np.float32)
+    shapes = [(H >> l, W >> l) for l in range(L)]
+    dpyr = O.corr_lookup_bwd(shapes, coords, dout, r)
+    df1, df2 = O.corr_pyramid_bwd(f1n, f2n, dpyr)
+    f1, f2 = to_gpu(f1n, True), to_gpu(f2n, True)
+    obj = E.MutliScalePairwise4DCorr(f1, f2, num_levels=L, corr_radius=r)
+    (obj(to_gpu(coords)) * to_gpu(dout)).sum().backward()
+    assert_close(f1.grad, df1, GRAD_TOL, f"{shape} dfmap1")
+    assert_close(f2.grad, df2, GRAD_TOL, f"{shape} dfmap2")
+
+
 def test_backward_two_lookups_accumulate(golden):
     """Two lookups through one pyramid: gradients add (RAFT calls the object 12x, models/raft.py:116)."""
     import ezflow_b200 as E
