@@ -29,22 +29,34 @@ namespace ezb {
 namespace k4tc {
 
 constexpr int QTH = 8, QTW = 16, BM = QTH * QTW;  // query tile  -> UMMA M = 128 (TMEM lanes)
-constexpr int TTH = 8, TTW = 16, BN = TTH * TTW;  // target tile -> UMMA N = 128 (TMEM columns)
+constexpr int TTH = 8;                            // target tile rows
 constexpr int BK = 64, KB_MAX = 4;                // C <= 256
-constexpr int STAGES = 4;
 constexpr int A_KB_BYTES = BM * BK * 2;           // 16 KB
-constexpr int B_STAGE_BYTES = BN * BK * 2;        // 16 KB
-constexpr int S_STRIDE = BN + 1;                  // words; odd => lane = query accesses are conflict-free
-constexpr int NACC = 4, TMEM_COLS = NACC * BN;    // 512
 constexpr int EPI_SPLIT = 4;                      // epilogue warps per TMEM lane quadrant
 constexpr int EPI_WARPS = 4 * EPI_SPLIT;
 constexpr int NUM_THREADS = 128 + EPI_WARPS * 32;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4.. epilogue
 constexpr int MAX_DIL = 8;
-constexpr int SMEM_A = 0;
-constexpr int SMEM_B = SMEM_A + KB_MAX * A_KB_BYTES;
-constexpr int SMEM_S = SMEM_B + STAGES * B_STAGE_BYTES;
-constexpr int SMEM_BAR = SMEM_S + BM * S_STRIDE * 4;
-constexpr int SMEM_BYTES = SMEM_BAR + 256 + 1024;
+constexpr int TMEM_COLS = 512;
+
+// Target-tile geometry.  TTW = 16: the general 8x16 tile (UMMA N = 128).  TTW = 24: for small windows (the x-extent of a
+// query tile's bounding box fits 24 columns, e.g. PWC-Net's 9x9 at stride 1) the tile spans the whole box width, so no
+// displacement straddles two tiles in x and a CTA needs half as many tiles (UMMA N = 192).
+template <int TTW_>
+struct Geo {
+  static constexpr int TTW = TTW_, BN = TTH * TTW;
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGES = BN <= 128 ? 4 : 2;
+  static constexpr int ACC_STRIDE = BN <= 128 ? 128 : 256;  // TMEM columns between accumulators
+  static constexpr int NACC = TMEM_COLS / ACC_STRIDE;
+  static constexpr int S_STRIDE = BN + 1;  // words; odd => lane = query accesses are conflict-free
+  static constexpr int CPW = BN / EPI_SPLIT;  // accumulator columns each epilogue warp stages
+  static constexpr int SMEM_A = 0;
+  static constexpr int SMEM_B = SMEM_A + KB_MAX * A_KB_BYTES;
+  static constexpr int SMEM_S = SMEM_B + STAGES * B_STAGE_BYTES;
+  static constexpr int SMEM_BAR = SMEM_S + BM * S_STRIDE * 4;
+  static constexpr int SMEM_BYTES = SMEM_BAR + 256 + 1024;
+  static_assert(CPW % 16 == 0 && SMEM_BYTES <= 232448 && (2 * STAGES + 2 + 2 * NACC) * 8 + 4 <= 256, "tile geometry");
+};
 
 struct Params {
   int G, H, W, oh, ow, Ph, Pw, sh, sw, padh, padw, D, KB;
@@ -72,8 +84,13 @@ __device__ __forceinline__ float dequant_factor(unsigned int amax1_bits, unsigne
 __device__ __forceinline__ int floor_div(int a, float inv_b) { return __float2int_rd(((float)a + 0.5f) * inv_b); }
 __device__ __forceinline__ int ceil_div(int a, float inv_b) { return -floor_div(-a, inv_b); }
 
+template <int TTW_>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     local_corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params P) {
+  using G = Geo<TTW_>;
+  constexpr int TTW = G::TTW, BN = G::BN, STAGES = G::STAGES, NACC = G::NACC, B_STAGE_BYTES = G::B_STAGE_BYTES;
+  constexpr int S_STRIDE = G::S_STRIDE, CPW = G::CPW, ACC_STRIDE = G::ACC_STRIDE;
+  constexpr int SMEM_A = G::SMEM_A, SMEM_B = G::SMEM_B, SMEM_S = G::SMEM_S, SMEM_BAR = G::SMEM_BAR;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -163,7 +180,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       const uint32_t acc = tt % NACC, aphase = (tt / NACC) & 1;
       ptx::mbar_wait(tmem_empty(acc), aphase ^ 1);
       ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
+      const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
       for (int kb = 0; kb < P.KB; ++kb) {
         ptx::mbar_wait(full_bar(stage), phase);
         ptx::tc_fence_after();
@@ -190,7 +207,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     float* out_q = P.out + (long long)b * P.out_bstride + (long long)oy * P.ow + ox;
     float* Srow = S + q * S_STRIDE;
     auto quad_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * EPI_SPLIT) : "memory"); };
-    constexpr int CPW = BN / EPI_SPLIT;  // accumulator columns per warp
 
     // displacements that point outside the image: zeros (act(0) = 0), written once, up front
     if (q_ok && split == 0) {
@@ -215,20 +231,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       const uint32_t acc = tt % NACC, aphase = (tt / NACC) & 1;
       ptx::mbar_wait(tmem_full(acc), aphase);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16) + part * CPW;
+      const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quad * 32) << 16) + part * CPW;
       {
-        uint32_t r[CPW / 32][32];
-#pragma unroll
-        for (int c = 0; c < CPW / 32; ++c) ptx::tmem_ld_32x32b_x32(taddr + c * 32, r[c]);
+        uint32_t r0[32], r1[16];
+        ptx::tmem_ld_32x32b_x32(taddr, r0);
+        if constexpr (CPW == 48) ptx::tmem_ld_32x32b_x16(taddr + 32, r1);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(tmem_empty(acc));  // the accumulator is in registers: release it early
         float* dst = Srow + part * CPW;
 #pragma unroll
-        for (int c = 0; c < CPW / 32; ++c)
+        for (int j = 0; j < 32; ++j) dst[j] = __uint_as_float(r0[j]);
+        if constexpr (CPW == 48) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) dst[c * 32 + j] = __uint_as_float(r[c][j]);
+          for (int j = 0; j < 16; ++j) dst[32 + j] = __uint_as_float(r1[j]);
+        }
       }
       quad_sync();  // all column shares of the rows are in shared memory
 
@@ -333,8 +351,13 @@ int local_corr_tc_launch(const float* in1, const float* in2, int BG, int G, int 
     cuuint32_t es[4] = {1, (cuuint32_t)sw, (cuuint32_t)sh, 1};
     if (int r = make_tmap_ex(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, ws.in1h, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B)) return r;
   }
+  int dmax_h = 1, dmax_w = 1;
+  for (int d = 0; d < D; ++d) { dmax_h = std::max(dmax_h, dph[d]); dmax_w = std::max(dmax_w, dpw[d]); }
+  // x-extent of a query tile's bounding box: if it fits 24 columns, 8x24 target tiles span it (Geo<24>)
+  const bool wide = (QTW - 1) * sw + (Pw - 1) * dmax_w + 1 <= 24;
+  const int TTW = wide ? 24 : 16;
   {
-    cuuint32_t box[4] = {BK, TTW, TTH, 1};
+    cuuint32_t box[4] = {BK, (cuuint32_t)TTW, TTH, 1};
     if (int r = make_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, ws.in2h, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return r;
   }
   Params P;
@@ -350,8 +373,6 @@ int local_corr_tc_launch(const float* in1, const float* in2, int BG, int G, int 
   P.out_bstride = out_bstride;
   // split the target sweep of a query tile over several CTAs when there are too few query tiles to fill the GPU evenly
   const int n_qtiles = cdiv(P.ow, QTW) * cdiv(P.oh, QTH) * BG;
-  int dmax_h = 1, dmax_w = 1;
-  for (int d = 0; d < D; ++d) { dmax_h = std::max(dmax_h, dph[d]); dmax_w = std::max(dmax_w, dpw[d]); }
   const int max_tiles = std::min(cdiv(H, TTH) + 1, cdiv((Ph - 1) * dmax_h + QTH * sh, TTH) + 1) *
                         std::min(cdiv(W, TTW) + 1, cdiv((Pw - 1) * dmax_w + QTW * sw, TTW) + 1);
   // cost model: CTAs run in waves of one per SM; a CTA costs its share of the target tiles plus ~2 tiles of fixed work
@@ -366,8 +387,13 @@ int local_corr_tc_launch(const float* in1, const float* in2, int BG, int G, int 
   }
   dim3 grid(cdiv(P.ow, QTW), cdiv(P.oh, QTH), BG * P.nsplit);
   EZB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "output too large for one launch");
-  EZB_CUDA_OK(cudaFuncSetAttribute(local_corr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  local_corr_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, P);
+  if (wide) {
+    EZB_CUDA_OK(cudaFuncSetAttribute(local_corr_tc_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<24>::SMEM_BYTES));
+    local_corr_tc_kernel<24><<<grid, NUM_THREADS, Geo<24>::SMEM_BYTES, st>>>(tmA, tmB, P);
+  } else {
+    EZB_CUDA_OK(cudaFuncSetAttribute(local_corr_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<16>::SMEM_BYTES));
+    local_corr_tc_kernel<16><<<grid, NUM_THREADS, Geo<16>::SMEM_BYTES, st>>>(tmA, tmB, P);
+  }
   EZB_LAUNCH_OK();
   return EZB_OK;
 }
