@@ -212,7 +212,7 @@ static int launch_fwd(Params& P, cudaStream_t st) {
 namespace ezb {
 // local_corr_tc.cu
 bool local_corr_tc_supported(int C, int sh, int sw, int D);
-size_t local_corr_tc_workspace_bytes(int BG, int C, int H, int W);
+size_t local_corr_tc_workspace_bytes(int BG, int C, int H, int W, int padh, int padw);
 int local_corr_tc_launch(const float* in1, const float* in2, int BG, int G, int C, int H, int W, int Ph, int Pw, int sh, int sw,
                          int padh, int padw, int D, const int* dph, const int* dpw, float scale, float slope, float* out,
                          long long out_bstride, void* workspace, size_t workspace_bytes, cudaStream_t st);
@@ -227,9 +227,9 @@ static int check_local_args(int B, int C, int H, int W, int Ph, int Pw, int sh, 
   return EZB_OK;
 }
 
-extern "C" int ezb_local_corr_workspace_bytes(int BG, int C, int H, int W, size_t* bytes) {
-  EZB_REQUIRE(BG > 0 && C > 0 && H > 0 && W > 0 && bytes, "bad arguments");
-  *bytes = local_corr_tc_workspace_bytes(BG, C, H, W);
+extern "C" int ezb_local_corr_workspace_bytes(int BG, int C, int H, int W, int padh, int padw, size_t* bytes) {
+  EZB_REQUIRE(BG > 0 && C > 0 && H > 0 && W > 0 && padh >= 0 && padw >= 0 && bytes, "bad arguments");
+  *bytes = local_corr_tc_workspace_bytes(BG, C, H, W, padh, padw);
   return EZB_OK;
 }
 

@@ -7,9 +7,10 @@
 // FlowNetC (C=256, 441 displacements) and DCVNet (C=256, 486 displacements) have 60 flop per byte of HBM
 // traffic, far above what CUDA cores sustain, so the contraction runs on tcgen05:
 //   prep    : per-(batch,group) absmax -> power-of-two pre-scale; fp32 (BG,C,H,W) -> fp16 K-major (BG,H,W,Cp)
+//             (for stride > 1 / padding > 0 only the query pixels of in1 are gathered: (BG,oh,ow,Cp))
 //   kernel  : one CTA per 8x16 tile of output pixels ("queries", UMMA M = 128).  The query operand (<= 64 KB)
-//             is TMA-loaded once (strided box for stride > 1, negative coordinates / OOB zero fill implement
-//             the zero padding).  The CTA then sweeps 8x16 tiles of in2 pixels ("targets", UMMA N = 128) over the
+//             is TMA-loaded once; negative box coordinates / OOB zero fill of the target loads implement the
+//             zero padding and the image border.  The CTA then sweeps 8x16 tiles of in2 pixels ("targets", UMMA N = 128) over the
 //             bounding box of all displacements of all dilations, clipped to the image, through a 4-stage TMA
 //             ring; 4 TMEM accumulators decouple the MMA warp from the epilogue.
 //   epilogue: lane = query.  The 128 accumulator columns of a tile go TMEM -> registers -> a private row of
@@ -77,6 +78,38 @@ __device__ __forceinline__ float dequant_factor(unsigned int amax1_bits, unsigne
   };
   const int e = max(-126, min(126, ex(amax1_bits) + ex(amax2_bits)));
   return __uint_as_float((unsigned int)(e + 127) << 23);
+}
+
+// Query operand for stride > 1 or padding > 0: only the pixels that are queries, (BG, oh, ow, Cp) fp16 K-major,
+//   dst[bg, oy, ox, c] = 2^-e1 * in1[bg, c, oy*sh - padh, ox*sw - padw]   (0 outside the image / for c >= C),
+// so the conversion touches 1/(sh*sw) of in1 and the A tiles are plain dense TMA boxes.
+__global__ void __launch_bounds__(256) gather_queries_kmajor_kernel(const float* __restrict__ in1, __half* __restrict__ dst,
+                                                                    const unsigned int* __restrict__ amax, int C, int Cp, int H,
+                                                                    int W, int oh, int ow, int sh, int sw, int padh, int padw) {
+  __shared__ float tile[64][33];
+  const int bg = blockIdx.z;
+  const float* src = in1 + (long long)bg * C * H * W;
+  const int e = (int)((amax[bg] >> 23) & 0xff);
+  const float sc = __uint_as_float((unsigned int)(127 - (e == 0 ? 0 : max(-126, min(126, e - 127)))) << 23);  // 2^-e1
+  const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 64, NQ = oh * ow;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = n0 + lane;
+  const int oy = n / ow, ox = n - oy * ow;
+  const int y = oy * sh - padh, x = ox * sw - padw;
+  const bool in_img = n < NQ && y >= 0 && y < H && x >= 0 && x < W;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + warp * 8 + i;
+    tile[warp * 8 + i][lane] = (in_img && c < C) ? __ldg(src + ((long long)c * H + y) * W + x) * sc : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int nl = warp * 4 + i, nn = n0 + nl;
+    if (nn < NQ)
+      *reinterpret_cast<__half2*>(dst + ((long long)bg * NQ + nn) * Cp + c0 + 2 * lane) =
+          __floats2half2_rn(tile[2 * lane][nl], tile[2 * lane + 1][nl]);
+  }
 }
 
 // floor(a / b) and ceil(a / b) for small |a| and b > 0 through a reciprocal: (a + 0.5) / b is never within 0.5/b >= 2^-5 of an
@@ -154,8 +187,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     if (ntiles > 0) {
       ptx::mbar_expect_tx(a_full, (uint32_t)(P.KB * A_KB_BYTES));
       for (int kb = 0; kb < P.KB; ++kb)
-        ptx::tma_load_4d_hint(sA + kb * A_KB_BYTES, &tmA, a_full, kb * BK, qx0 * P.sw - P.padw, qy0 * P.sh - P.padh, bg,
-                              ptx::kEvictFirst);
+        ptx::tma_load_4d_hint(sA + kb * A_KB_BYTES, &tmA, a_full, kb * BK, qx0, qy0, bg, ptx::kEvictFirst);  // (oy, ox) space
     }
     uint32_t stage = 0, phase = 0;
     for (int tt = 0; tt < ntiles; ++tt) {
@@ -252,6 +284,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 
       for (int d = 0; d < P.D; ++d) {
         const int dph = P.dph[d], dpw = P.dpw[d];
+        {  // CTA-uniform early out: this dilation's box around the query tile does not reach the target tile
+          const int mh = dph * (P.Ph - 1) / 2, mw = dpw * (P.Pw - 1) / 2;
+          if (ty1 < qy0 * P.sh - P.padh - mh || ty0 > (qy0 + QTH - 1) * P.sh - P.padh + mh ||
+              tx1 < qx0 * P.sw - P.padw - mw || tx0 > (qx0 + QTW - 1) * P.sw - P.padw + mw)
+            continue;
+        }
         const int y2_0 = oy * P.sh - P.padh - dph * (P.Ph - 1) / 2, x2_0 = ox * P.sw - P.padw - dpw * (P.Pw - 1) / 2;
         // this lane's displacement ranges whose target lies in the in-image part of the tile
         const float inv_dph = __frcp_rn((float)dph), inv_dpw = __frcp_rn((float)dpw);
@@ -296,11 +334,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 
 struct Workspace {
   unsigned int* amax;  // [2][BG]
-  __half* in1h;        // (BG, H, W, Cp)
+  __half* in1h;        // queries: (BG, oh, ow, Cp)
   __half* in2h;
 };
 
-static size_t ws_layout(int BG, int C, int H, int W, void* base, Workspace* ws) {
+static size_t ws_layout(int BG, int C, int H, int W, int padh, int padw, void* base, Workspace* ws) {
   const int Cp = round_up(C, BK);
   uintptr_t p = reinterpret_cast<uintptr_t>(base);
   auto take = [&](size_t bytes, size_t align) {
@@ -310,7 +348,8 @@ static size_t ws_layout(int BG, int C, int H, int W, void* base, Workspace* ws) 
     return r;
   };
   const uintptr_t amax = take((size_t)2 * BG * 4, 256);
-  const uintptr_t a = take((size_t)BG * H * W * Cp * 2, 1024);
+  // queries: (oh, ow) <= (H + 2 padh, W + 2 padw) pixels per map (stride only shrinks it)
+  const uintptr_t a = take((size_t)BG * (H + 2 * padh) * (W + 2 * padw) * Cp * 2, 1024);
   const uintptr_t b = take((size_t)BG * H * W * Cp * 2, 1024);
   if (ws) {
     ws->amax = reinterpret_cast<unsigned int*>(amax);
@@ -324,10 +363,13 @@ static size_t ws_layout(int BG, int C, int H, int W, void* base, Workspace* ws) 
 
 // true when the tensor-core kernel covers this problem (otherwise the exact fp32 SIMT kernel runs)
 bool local_corr_tc_supported(int C, int sh, int sw, int D) {
-  return C <= k4tc::KB_MAX * k4tc::BK && sh <= 8 && sw <= 8 && D <= k4tc::MAX_DIL;
+  (void)sh; (void)sw;  // any stride: the query operand is gathered compactly
+  return C <= k4tc::KB_MAX * k4tc::BK && D <= k4tc::MAX_DIL;
 }
 
-size_t local_corr_tc_workspace_bytes(int BG, int C, int H, int W) { return k4tc::ws_layout(BG, C, H, W, nullptr, nullptr) + 1024; }
+size_t local_corr_tc_workspace_bytes(int BG, int C, int H, int W, int padh, int padw) {
+  return k4tc::ws_layout(BG, C, H, W, padh, padw, nullptr, nullptr) + 1024;
+}
 
 int local_corr_tc_launch(const float* in1, const float* in2, int BG, int G, int C, int H, int W, int Ph, int Pw, int sh, int sw,
                          int padh, int padw, int D, const int* dph, const int* dpw, float scale, float slope, float* out,
@@ -336,20 +378,29 @@ int local_corr_tc_launch(const float* in1, const float* in2, int BG, int G, int 
   const int Cp = round_up(C, BK), N = H * W;
   uintptr_t wbase = (reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023);
   Workspace ws;
-  const size_t need = ws_layout(BG, C, H, W, reinterpret_cast<void*>(wbase), &ws) + (wbase - reinterpret_cast<uintptr_t>(workspace));
+  const size_t need = ws_layout(BG, C, H, W, padh, padw, reinterpret_cast<void*>(wbase), &ws) + (wbase - reinterpret_cast<uintptr_t>(workspace));
   if (need > workspace_bytes) return fail(EZB_ERR_WORKSPACE, "workspace too small: need %zu, got %zu", need, workspace_bytes);
   EZB_REQUIRE(BG <= 65535, "batch too large for one launch (split it)");
 
   if (int r = prep::launch_absmax(in1, in2, (long long)C * N, ws.amax, BG, st)) return r;
-  if (int r = prep::launch_convert_kmajor2(in1, ws.in1h, in2, ws.in2h, ws.amax, BG, C, Cp, N, st)) return r;
+  const int oh = cdiv(H + 2 * padh, sh), ow = cdiv(W + 2 * padw, sw);
+  if (sh == 1 && sw == 1 && padh == 0 && padw == 0) {  // queries = all pixels of in1: one launch converts both tensors
+    if (int r = prep::launch_convert_kmajor2(in1, ws.in1h, in2, ws.in2h, ws.amax, BG, C, Cp, N, st)) return r;
+  } else {  // strided / padded queries: gather only the query pixels of in1
+    if (int r = prep::launch_convert_kmajor(in2, ws.in2h, ws.amax + BG, BG, C, Cp, N, st)) return r;
+    gather_queries_kmajor_kernel<<<dim3(cdiv(oh * ow, 32), Cp / 64, BG), 256, 0, st>>>(in1, ws.in1h, ws.amax, C, Cp, H, W, oh, ow, sh,
+                                                                                      sw, padh, padw);
+    EZB_LAUNCH_OK();
+  }
 
   CUtensorMap tmA, tmB;
   cuuint64_t dims[4] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)BG};
   cuuint64_t str[3] = {(cuuint64_t)Cp * 2, (cuuint64_t)W * Cp * 2, (cuuint64_t)H * W * Cp * 2};
   {
-    cuuint32_t box[4] = {BK, (cuuint32_t)(QTW * sw), (cuuint32_t)(QTH * sh), 1};
-    cuuint32_t es[4] = {1, (cuuint32_t)sw, (cuuint32_t)sh, 1};
-    if (int r = make_tmap_ex(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, ws.in1h, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B)) return r;
+    cuuint64_t qdims[4] = {(cuuint64_t)Cp, (cuuint64_t)ow, (cuuint64_t)oh, (cuuint64_t)BG};
+    cuuint64_t qstr[3] = {(cuuint64_t)Cp * 2, (cuuint64_t)ow * Cp * 2, (cuuint64_t)oh * ow * Cp * 2};
+    cuuint32_t box[4] = {BK, QTW, QTH, 1};
+    if (int r = make_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, ws.in1h, qdims, qstr, box, CU_TENSOR_MAP_SWIZZLE_128B)) return r;
   }
   int dmax_h = 1, dmax_w = 1;
   for (int d = 0; d < D; ++d) { dmax_h = std::max(dmax_h, dph[d]); dmax_w = std::max(dmax_w, dpw[d]); }
@@ -362,7 +413,7 @@ int local_corr_tc_launch(const float* in1, const float* in2, int BG, int G, int 
   }
   Params P;
   P.G = G; P.H = H; P.W = W;
-  P.oh = cdiv(H + 2 * padh, sh); P.ow = cdiv(W + 2 * padw, sw);
+  P.oh = oh; P.ow = ow;
   P.Ph = Ph; P.Pw = Pw; P.sh = sh; P.sw = sw; P.padh = padh; P.padw = padw;
   P.D = D; P.KB = Cp / BK;
   for (int d = 0; d < D; ++d) { P.dph[d] = dph[d]; P.dpw[d] = dpw[d]; }

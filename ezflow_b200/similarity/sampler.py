@@ -44,12 +44,12 @@ def get_local_corr_mode():
     return _LOCAL_CORR_MODE
 
 
-def local_corr_workspace(BG, C, H, W, device):
+def local_corr_workspace(BG, C, H, W, device, padding=(0, 0)):
     """Scratch for the tensor-core path (fp16 K-major operand copies + scales), or (None, 0) in 'exact' mode."""
     if _LOCAL_CORR_MODE != "tc":
         return None, 0
     n = ctypes.c_size_t(0)
-    _cabi.check(_cabi.lib().ezb_local_corr_workspace_bytes(BG, C, H, W, ctypes.byref(n)))
+    _cabi.check(_cabi.lib().ezb_local_corr_workspace_bytes(BG, C, H, W, int(padding[0]), int(padding[1]), ctypes.byref(n)))
     return torch.empty(n.value, dtype=torch.uint8, device=device), n.value
 
 
@@ -59,7 +59,7 @@ def local_corr_forward(in1, in2, patch, stride, padding, dpatch, scale=1.0, slop
     if out is None:
         out = torch.empty((B, patch[0], patch[1], oh, ow), dtype=torch.float32, device=in1.device)
     with torch.cuda.device(in1.device):
-        ws, nws = local_corr_workspace(B, C, H, W, in1.device)
+        ws, nws = local_corr_workspace(B, C, H, W, in1.device, padding)
         _cabi.check(
             _cabi.lib().ezb_local_corr_fwd(
                 _cabi.ptr(in1), _cabi.ptr(in2), B, C, H, W, patch[0], patch[1], stride[0], stride[1], padding[0], padding[1],

@@ -130,12 +130,13 @@ int ezb_corr_pyramid_bwd(float* const* dlvl_ptrs /*[L] host*/, const float* fmap
  *   in*p = inputs zero-padded by (padh,padw); md = dp*(P-1)/2; out (B,Ph,Pw,oh,ow),
  *   oh = ceil((H+2*padh)/sh), ow likewise.  act = leaky_relu(slope) (slope 1 = identity).
  *   `out_batch_stride` (elements) lets K6 write straight into a slice of the concatenated volume.
- *   With a workspace of ezb_local_corr_workspace_bytes() (and C <= 256 per group, stride <= 8) the
+ *   With a workspace of ezb_local_corr_workspace_bytes() (and C <= 256 per group) the
  *   contraction runs on tcgen05 tensor cores with fp16 operands / fp32 accumulation (<= 1e-3 relative,
  *   the north_star tolerance for cost volumes); with workspace == NULL the exact fp32 CUDA-core kernel
- *   runs (any C, any stride).
+ *   runs (any C).
  * ------------------------------------------------------------------------------------------- */
-int ezb_local_corr_workspace_bytes(int BG /* batch * groups */, int C /* per group */, int H, int W, size_t* bytes /*host*/);
+int ezb_local_corr_workspace_bytes(int BG /* batch * groups */, int C /* per group */, int H, int W, int padh, int padw,
+                                   size_t* bytes /*host*/);
 
 int ezb_local_corr_fwd(const float* in1, const float* in2, int B, int C, int H, int W,
                        int Ph, int Pw, int sh, int sw, int padh, int padw, int dph, int dpw,
