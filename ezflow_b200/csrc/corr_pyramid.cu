@@ -576,7 +576,7 @@ int launch_convert_kmajor2(const float* src0, __half* dst0, const float* src1, _
 int launch_pool2x2(const float* src, float* dst, long long planes, int hs, int ws, long long src_plane, int hd, int wd,
                    long long dst_plane, cudaStream_t st) {
   const long long total = planes * hd * wd;
-  const int gx = (int)std::max<long long>(1, std::min<long long>(cdiv64(total, 256), 148 * 8));
+  const int gx = (int)std::max<long long>(1, std::min<long long>(cdiv64(total, 256), 148 * 64));
   k1::pool2x2_kernel<<<gx, 256, 0, st>>>(src, dst, planes, hs, ws, src_plane, hd, wd, dst_plane);
   EZB_LAUNCH_OK();
   return EZB_OK;
@@ -676,7 +676,7 @@ extern "C" int ezb_corr_pyramid_fwd_ex(const float* fmap1, const float* fmap2, i
   pk.bp = ws.f2p;
   for (int l = 1; l < L; ++l) {
     const long long total = (long long)B * C * pk.h[l] * pk.w[l];
-    const int gx = (int)std::min<long long>(cdiv64(total, 256), 148 * 8);
+    const int gx = (int)std::min<long long>(cdiv64(total, 256), 148 * 64);
     k1::pool2x2_kernel<<<gx, 256, 0, st>>>(pk.lvl[l - 1], ws.f2l[l], (long long)B * C, pk.h[l - 1], pk.w[l - 1],
                                            (long long)pk.h[l - 1] * pk.w[l - 1], pk.h[l], pk.w[l], (long long)pk.h[l] * pk.w[l]);
     EZB_LAUNCH_OK();
