@@ -183,3 +183,19 @@ def test_baseline_config_shapes_vs_oracle(cfg, mode):
         assert tuple(out.shape) == (1, 7, 9, 9, 48, 96)
         ref = O.matryoshka_cost_volume_list(xa, xb)
         assert_close(out, ref, FWD_TOL[mode], "cfg4")
+
+
+@pytest.mark.parametrize("cfg", [(1, 4, 3, 3, 3, 1, 0, 1), (1, 7, 5, 9, 5, 2, 1, 2), (2, 130, 6, 6, 9, 1, 4, 1), (1, 16, 20, 30, 3, 9, 0, 1)])
+def test_tiny_and_ragged_shapes_vs_oracle(cfg, mode):
+    """Maps smaller than one query tile, odd channel counts (padded to 64), padding with stride, stride > 8."""
+    import ezflow_b200 as E
+    from oracle import similarity_oracle as O
+
+    B, C, H, W, P, s, pad, dp = cfg
+    rng = np.random.default_rng(200 + C)
+    x1 = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    x2 = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    ref = O.iter_spatial_correlation_sample(x1, x2, patch_size=P, stride=s, padding=pad, dilation_patch=dp)
+    out = E.IterSpatialCorrelationSampler(kernel_size=1, patch_size=P, stride=s, padding=pad, dilation_patch=dp)(to_gpu(x1), to_gpu(x2))
+    assert tuple(out.shape) == ref.shape
+    assert_close(out, ref, FWD_TOL[mode], f"{cfg} ({mode})")

@@ -251,3 +251,21 @@ def test_full_size_1080p_properties():
     # (d) linearity: scaling fmap1 by 3 scales every lookup by 3 (power-of-two pre-scale makes this near-exact)
     out3 = E.MutliScalePairwise4DCorr(3.0 * f1, f2)(coords)
     assert rel_fro(out3.cpu().numpy(), (3.0 * out).cpu().numpy()) <= 5e-4
+
+
+@pytest.mark.parametrize("store", ["fp16", "fp32"])
+@pytest.mark.parametrize("cfg", [(1, 8, 4, 4, 1, 1), (1, 16, 5, 7, 2, 2), (2, 3, 2, 9, 1, 4), (1, 256, 3, 3, 1, 4), (1, 1, 16, 16, 4, 4)])
+def test_tiny_and_ragged_shapes_vs_oracle(cfg, store):
+    """Feature maps smaller than one GEMM tile / one query group, single channel, one pyramid level: CUDA path vs oracle."""
+    import ezflow_b200 as E
+    from oracle import similarity_oracle as O
+
+    B, C, H, W, L, r = cfg
+    rng = np.random.default_rng(100 + H * W)
+    f1 = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    f2 = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    coords = O.coords_grid(B, H, W) + rng.uniform(-2, 2, (B, 2, H, W)).astype(np.float32)
+    ref = O.corr_lookup(O.corr_pyramid(f1, f2, L), coords, r)
+    E.set_pyramid_dtype(store)
+    out = E.MutliScalePairwise4DCorr(to_gpu(f1), to_gpu(f2), num_levels=L, corr_radius=r)(to_gpu(coords))
+    assert_close(out, ref, LOOK_TOL, f"{cfg} ({store})")
