@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""Randomised parity sweep (GPU): CUDA path vs the numpy oracle over random shapes / parameters.
+    python tools/fuzz_parity.py [n_cases] [seed]
+Prints one line per failure and a summary; exit code 1 on any failure."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import ezflow_b200 as E
+from oracle import similarity_oracle as O
+
+n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+dev = torch.device("cuda:0")
+g = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+fails = 0
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b), 1e-30)), float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+for i in range(n_cases):
+    # ---- all-pairs pyramid + lookup (+ backward on every third case)
+    B = int(rng.integers(1, 4)); C = int(rng.choice([1, 3, 17, 64, 100, 256])); L = int(rng.integers(1, 5)); r = int(rng.integers(0, 6))
+    H = int(rng.integers(2 << (L - 1), 40)); W = int(rng.integers(2 << (L - 1), 56))
+    scale = float(10.0 ** rng.uniform(-3, 3))
+    f1 = (rng.standard_normal((B, C, H, W)) * scale).astype(np.float32); f2 = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    coords = O.coords_grid(B, H, W) + rng.uniform(-1.5 * r - 2, 1.5 * r + 2, (B, 2, H, W)).astype(np.float32)
+    store = "fp16" if rng.random() < 0.7 else "fp32"
+    E.set_pyramid_dtype(store)
+    ref = O.corr_lookup(O.corr_pyramid(f1, f2, L), coords, r)
+    t1, t2 = g(f1).requires_grad_(i % 3 == 0), g(f2).requires_grad_(i % 3 == 0)
+    out_t = E.MutliScalePairwise4DCorr(t1, t2, num_levels=L, corr_radius=r)(g(coords))
+    rf, mr = rel(out_t.detach().cpu().numpy(), ref)
+    ok = rf <= 1e-3 and mr <= 1e-3
+    if i % 3 == 0:
+        dout = rng.standard_normal(ref.shape).astype(np.float32)
+        (out_t * g(dout)).sum().backward()
+        dpyr = O.corr_lookup_bwd([(H >> l, W >> l) for l in range(L)], coords, dout, r)
+        d1, d2 = O.corr_pyramid_bwd(f1, f2, dpyr)
+        e1, e2 = rel(t1.grad.cpu().numpy(), d1), rel(t2.grad.cpu().numpy(), d2)
+        ok = ok and max(e1 + e2) <= 2e-3
+    if not ok:
+        fails += 1
+        print("FAIL pairwise", (B, C, H, W, L, r, store, scale), rf, mr)
+    # ---- local correlation
+    B = int(rng.integers(1, 3)); C = int(rng.choice([2, 32, 96, 130, 256])); H = int(rng.integers(3, 30)); W = int(rng.integers(3, 40))
+    P = int(rng.choice([1, 3, 5, 9, 21])); s = int(rng.choice([1, 1, 2, 3, 4])); pad = int(rng.choice([0, 0, 1, 4])); dp = int(rng.choice([1, 1, 2, 3, 5]))
+    x1 = rng.standard_normal((B, C, H, W)).astype(np.float32); x2 = (rng.standard_normal((B, C, H, W)) * 10.0 ** rng.uniform(-2, 2)).astype(np.float32)
+    ref = O.iter_spatial_correlation_sample(x1, x2, patch_size=P, stride=s, padding=pad, dilation_patch=dp)
+    for mode, tol in (("tc", 1e-3), ("exact", 2e-5)):
+        E.set_local_corr_mode(mode)
+        out = E.IterSpatialCorrelationSampler(kernel_size=1, patch_size=P, stride=s, padding=pad, dilation_patch=dp)(g(x1), g(x2)).cpu().numpy()
+        rf, mr = rel(out, ref) if out.shape == ref.shape else (9, 9)
+        if mode == "tc" and out.size < 200:
+            tol *= 8  # a handful of random-sign dot products: error relative to the result is not a stable statistic
+        if not (rf <= tol and mr <= tol):
+            fails += 1
+            print("FAIL local", mode, (B, C, H, W, P, s, pad, dp), rf, mr)
+E.set_local_corr_mode("tc"); E.set_pyramid_dtype("fp16")
+torch.cuda.synchronize()
+print(f"fuzz: {n_cases} cases x (pairwise + local tc/exact), failures: {fails}")
+sys.exit(1 if fails else 0)
