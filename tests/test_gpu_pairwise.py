@@ -269,3 +269,16 @@ def test_tiny_and_ragged_shapes_vs_oracle(cfg, store):
     E.set_pyramid_dtype(store)
     out = E.MutliScalePairwise4DCorr(to_gpu(f1), to_gpu(f2), num_levels=L, corr_radius=r)(to_gpu(coords))
     assert_close(out, ref, LOOK_TOL, f"{cfg} ({store})")
+
+
+def test_full_size_is_deterministic():
+    """Headline size, two pairs: repeated builds + lookups are bit-identical (no races in the TMA / tcgen05 pipelines)."""
+    import ezflow_b200 as E
+
+    g = torch.Generator(device="cpu").manual_seed(5)
+    f1 = torch.randn(2, 256, 135, 240, generator=g).to(dev())
+    f2 = torch.randn(2, 256, 135, 240, generator=g).to(dev())
+    c = E.coords_grid(2, 135, 240, device=dev()) + torch.randn(2, 2, 135, 240, generator=g).to(dev()) * 5
+    ref = E.MutliScalePairwise4DCorr(f1, f2)(c)
+    for _ in range(3):
+        assert torch.equal(E.MutliScalePairwise4DCorr(f1, f2)(c), ref)
