@@ -25,6 +25,7 @@
 #include "ezb_tma.cuh"
 
 #include <climits>
+#include <cstdlib>
 
 namespace ezb {
 namespace k4tc {
@@ -62,6 +63,12 @@ struct Geo {
 struct Params {
   int G, H, W, oh, ow, Ph, Pw, sh, sw, padh, padw, D, KB;
   int nsplit;  // CTAs sharing one query tile (each sweeps a slice of its target tiles): balances the last wave
+  // Lattice mode (lat > 1; one dilation = lat, stride 1, no padding): queries and targets with the same residues
+  // (cy, cx) mod lat only ever meet each other, so every residue class is an independent dilation-1 problem on the
+  // sub-lattice  pixel = (cy, cx) + lat * (y, x);  H, W, oh, ow, dph, dpw below are then in lattice units of class (0,0).
+  int lat, BG;
+  int Hf, Wf;        // full-resolution input size (lattice mode)
+  int out_h, out_w;  // full output plane
   int dph[MAX_DIL], dpw[MAX_DIL];
   float slope;
   const unsigned int* amax;  // [2][BG] float bits of max|in1|, max|in2| per (batch, group): operands were scaled by 2^-e
@@ -85,9 +92,12 @@ __device__ __forceinline__ float dequant_factor(unsigned int amax1_bits, unsigne
 // so the conversion touches 1/(sh*sw) of in1 and the A tiles are plain dense TMA boxes.
 __global__ void __launch_bounds__(256) gather_queries_kmajor_kernel(const float* __restrict__ in1, __half* __restrict__ dst,
                                                                     const unsigned int* __restrict__ amax, int C, int Cp, int H,
-                                                                    int W, int oh, int ow, int sh, int sw, int padh, int padw) {
+                                                                    int W, int oh, int ow, int sh, int sw, int padh, int padw,
+                                                                    int lat) {
   __shared__ float tile[64][33];
-  const int bg = blockIdx.z;
+  // lattice mode: blockIdx.z = bg * lat^2 + class; the class (cy, cx) acts as a negative padding with stride lat
+  const int ncls = lat * lat, bg = blockIdx.z / ncls, cls = blockIdx.z - bg * ncls;
+  if (lat > 1) { sh = sw = lat; padh = -(cls / lat); padw = -(cls % lat); }
   const float* src = in1 + (long long)bg * C * H * W;
   const int e = (int)((amax[bg] >> 23) & 0xff);
   const float sc = __uint_as_float((unsigned int)(127 - (e == 0 ? 0 : max(-126, min(126, e - 127)))) << 23);  // 2^-e1
@@ -107,7 +117,7 @@ __global__ void __launch_bounds__(256) gather_queries_kmajor_kernel(const float*
   for (int i = 0; i < 4; ++i) {
     const int nl = warp * 4 + i, nn = n0 + nl;
     if (nn < NQ)
-      *reinterpret_cast<__half2*>(dst + ((long long)bg * NQ + nn) * Cp + c0 + 2 * lane) =
+      *reinterpret_cast<__half2*>(dst + ((long long)blockIdx.z * NQ + nn) * Cp + c0 + 2 * lane) =
           __floats2half2_rn(tile[2 * lane][nl], tile[2 * lane + 1][nl]);
   }
 }
@@ -139,7 +149,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qx0 = blockIdx.x * QTW, qy0 = blockIdx.y * QTH;
-  const int bg = blockIdx.z / P.nsplit, split = blockIdx.z - bg * P.nsplit;
+  const int zq = blockIdx.z / P.nsplit, split = blockIdx.z - zq * P.nsplit;  // zq = bg * lat^2 + class
+  const int ncls = P.lat * P.lat, bg = zq / ncls, cls = zq - bg * ncls;
+  const int cy = cls / P.lat, cx = cls - cy * P.lat;
+  // image / output size in the units the tiles are laid out in (lattice mode: the lattice of this residue class)
+  const int H_ = P.lat > 1 ? (P.Hf - cy + P.lat - 1) / P.lat : P.H, W_ = P.lat > 1 ? (P.Wf - cx + P.lat - 1) / P.lat : P.W;
+  const int oh_ = P.lat > 1 ? H_ : P.oh, ow_ = P.lat > 1 ? W_ : P.ow;
+  if (qy0 >= oh_ || qx0 >= ow_) return;  // (lattice mode) this class is smaller than class (0,0): nothing here
 
   // bounding box (in2 pixel coordinates, clipped to the image) of every target any query of this tile needs
   int mdh_max = 0, mdw_max = 0;
@@ -148,9 +164,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     mdw_max = max(mdw_max, P.dpw[d] * (P.Pw - 1) / 2);
   }
   const int y_lo = max(0, qy0 * P.sh - P.padh - mdh_max);
-  const int y_hi = min(P.H - 1, (min(qy0 + QTH, P.oh) - 1) * P.sh - P.padh + mdh_max);
+  const int y_hi = min(H_ - 1, (min(qy0 + QTH, oh_) - 1) * P.sh - P.padh + mdh_max);
   const int x_lo = max(0, qx0 * P.sw - P.padw - mdw_max);
-  const int x_hi = min(P.W - 1, (min(qx0 + QTW, P.ow) - 1) * P.sw - P.padw + mdw_max);
+  const int x_hi = min(W_ - 1, (min(qx0 + QTW, ow_) - 1) * P.sw - P.padw + mdw_max);
   const int nty = y_hi >= y_lo ? (y_hi - y_lo) / TTH + 1 : 0;
   const int ntx = x_hi >= x_lo ? (x_hi - x_lo) / TTW + 1 : 0;
   const int ntiles_all = nty * ntx;
@@ -187,7 +203,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     if (ntiles > 0) {
       ptx::mbar_expect_tx(a_full, (uint32_t)(P.KB * A_KB_BYTES));
       for (int kb = 0; kb < P.KB; ++kb)
-        ptx::tma_load_4d_hint(sA + kb * A_KB_BYTES, &tmA, a_full, kb * BK, qx0, qy0, bg, ptx::kEvictFirst);  // (oy, ox) space
+        ptx::tma_load_4d_hint(sA + kb * A_KB_BYTES, &tmA, a_full, kb * BK, qx0, qy0, zq, ptx::kEvictFirst);  // (oy, ox) space
     }
     uint32_t stage = 0, phase = 0;
     for (int tt = 0; tt < ntiles; ++tt) {
@@ -196,7 +212,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         ptx::mbar_wait(empty_bar(stage), phase ^ 1);
         ptx::mbar_expect_tx(full_bar(stage), B_STAGE_BYTES);
         // in2 windows of neighbouring query tiles overlap heavily: keep them in L2
-        ptx::tma_load_4d_hint(sB + stage * B_STAGE_BYTES, &tmB, full_bar(stage), kb * BK, tx0, ty0, bg, ptx::kEvictLast);
+        ptx::tma_load_4d_hint(sB + stage * B_STAGE_BYTES, &tmB, full_bar(stage), kb * BK, cx + P.lat * tx0, cy + P.lat * ty0, bg,
+                              ptx::kEvictLast);  // lattice -> pixel coordinates
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -232,11 +249,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     const int quad = warp & 3, part = (warp - 4) >> 2;
     const int q = quad * 32 + lane;
     const int oy = qy0 + q / QTW, ox = qx0 + q % QTW;
-    const bool q_ok = oy < P.oh && ox < P.ow;
+    const bool q_ok = oy < oh_ && ox < ow_;
     const int b = bg / P.G, g = bg - b * P.G;
-    const float deq = P.scale * dequant_factor(__ldg(P.amax + bg), __ldg(P.amax + gridDim.z / P.nsplit + bg));
-    const long long plane = (long long)P.oh * P.ow;
-    float* out_q = P.out + (long long)b * P.out_bstride + (long long)oy * P.ow + ox;
+    const float deq = P.scale * dequant_factor(__ldg(P.amax + bg), __ldg(P.amax + P.BG + bg));
+    const long long plane = (long long)P.out_h * P.out_w;
+    float* out_q = P.out + (long long)b * P.out_bstride + (long long)(cy + P.lat * oy) * P.out_w + (cx + P.lat * ox);
     float* Srow = S + q * S_STRIDE;
     auto quad_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * EPI_SPLIT) : "memory"); };
 
@@ -248,10 +265,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         float* o = out_q + (long long)(d * P.G + g) * P.Ph * P.Pw * plane;
         for (int a = part; a < P.Ph; a += EPI_SPLIT) {
           const int y2 = y2_0 + a * dph;
-          const bool row_in = y2 >= 0 && y2 < P.H;
+          const bool row_in = y2 >= 0 && y2 < H_;
           for (int bb = 0; bb < P.Pw; ++bb) {
             const int x2 = x2_0 + bb * dpw;
-            if (!(row_in && x2 >= 0 && x2 < P.W)) o[(long long)(a * P.Pw + bb) * plane] = 0.f;
+            if (!(row_in && x2 >= 0 && x2 < W_)) o[(long long)(a * P.Pw + bb) * plane] = 0.f;
           }
         }
       }
@@ -259,7 +276,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 
     for (int tt = 0; tt < ntiles; ++tt) {
       const int ty0 = y_lo + ((tt_begin + tt) / ntx) * TTH, tx0 = x_lo + ((tt_begin + tt) % ntx) * TTW;
-      const int ty1 = min(ty0 + TTH, P.H) - 1, tx1 = min(tx0 + TTW, P.W) - 1;  // last in-image row / column of the tile
+      const int ty1 = min(ty0 + TTH, H_) - 1, tx1 = min(tx0 + TTW, W_) - 1;  // last in-image row / column of the tile
       const uint32_t acc = tt % NACC, aphase = (tt / NACC) & 1;
       ptx::mbar_wait(tmem_full(acc), aphase);
       ptx::tc_fence_after();
@@ -349,7 +366,8 @@ static size_t ws_layout(int BG, int C, int H, int W, int padh, int padw, void* b
   };
   const uintptr_t amax = take((size_t)2 * BG * 4, 256);
   // queries: (oh, ow) <= (H + 2 padh, W + 2 padw) pixels per map (stride only shrinks it)
-  const uintptr_t a = take((size_t)BG * (H + 2 * padh) * (W + 2 * padw) * Cp * 2, 1024);
+  // (+8: in lattice mode every residue class is rounded up to the size of class (0,0))
+  const uintptr_t a = take((size_t)BG * (H + 2 * padh + 8) * (W + 2 * padw + 8) * Cp * 2, 1024);
   const uintptr_t b = take((size_t)BG * H * W * Cp * 2, 1024);
   if (ws) {
     ws->amax = reinterpret_cast<unsigned int*>(amax);
@@ -383,49 +401,67 @@ int local_corr_tc_launch(const float* in1, const float* in2, int BG, int G, int 
   EZB_REQUIRE(BG <= 65535, "batch too large for one launch (split it)");
 
   if (int r = prep::launch_absmax(in1, in2, (long long)C * N, ws.amax, BG, st)) return r;
-  const int oh = cdiv(H + 2 * padh, sh), ow = cdiv(W + 2 * padw, sw);
-  if (sh == 1 && sw == 1 && padh == 0 && padw == 0) {  // queries = all pixels of in1: one launch converts both tensors
+  const int out_h = cdiv(H + 2 * padh, sh), out_w = cdiv(W + 2 * padw, sw);
+  // Lattice mode: one dilation lat > 1 at stride 1 without padding splits into lat^2 independent dilation-1 problems on
+  // sub-lattices (4x fewer wasted products for FlowNetC's dilation_patch = 2); classes must still fill a query tile.
+  int lat = 1;
+  if (D == 1 && sh == 1 && sw == 1 && padh == 0 && padw == 0 && dph[0] == dpw[0] && dph[0] >= 2 && dph[0] <= 8 &&
+      cdiv(H, dph[0]) >= QTH && cdiv(W, dph[0]) >= QTW && getenv("EZB_LOCAL_CORR_NO_LATTICE") == nullptr)
+    lat = dph[0];
+  const int ncls = lat * lat;
+  // sizes in the units the tiles are laid out in (lattice mode: the lattice of residue class (0,0), the largest one)
+  const int Hu = lat > 1 ? cdiv(H, lat) : H, Wu = lat > 1 ? cdiv(W, lat) : W;
+  const int oh = lat > 1 ? Hu : out_h, ow = lat > 1 ? Wu : out_w;
+  const int one = 1;
+  const int* dph_u = lat > 1 ? &one : dph;
+  const int* dpw_u = lat > 1 ? &one : dpw;
+  EZB_REQUIRE((long long)BG * ncls <= 65535, "batch too large for one launch (split it)");
+
+  if (lat == 1 && sh == 1 && sw == 1 && padh == 0 && padw == 0) {  // queries = all pixels of in1: one launch converts both tensors
     if (int r = prep::launch_convert_kmajor2(in1, ws.in1h, in2, ws.in2h, ws.amax, BG, C, Cp, N, st)) return r;
-  } else {  // strided / padded queries: gather only the query pixels of in1
+  } else {  // strided / padded / per-class queries: gather only the query pixels of in1, (BG * ncls, oh, ow, Cp)
     if (int r = prep::launch_convert_kmajor(in2, ws.in2h, ws.amax + BG, BG, C, Cp, N, st)) return r;
-    gather_queries_kmajor_kernel<<<dim3(cdiv(oh * ow, 32), Cp / 64, BG), 256, 0, st>>>(in1, ws.in1h, ws.amax, C, Cp, H, W, oh, ow, sh,
-                                                                                      sw, padh, padw);
+    gather_queries_kmajor_kernel<<<dim3(cdiv(oh * ow, 32), Cp / 64, BG * ncls), 256, 0, st>>>(in1, ws.in1h, ws.amax, C, Cp, H, W, oh, ow,
+                                                                                             sh, sw, padh, padw, lat);
     EZB_LAUNCH_OK();
   }
 
   CUtensorMap tmA, tmB;
-  cuuint64_t dims[4] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)BG};
-  cuuint64_t str[3] = {(cuuint64_t)Cp * 2, (cuuint64_t)W * Cp * 2, (cuuint64_t)H * W * Cp * 2};
   {
-    cuuint64_t qdims[4] = {(cuuint64_t)Cp, (cuuint64_t)ow, (cuuint64_t)oh, (cuuint64_t)BG};
+    cuuint64_t qdims[4] = {(cuuint64_t)Cp, (cuuint64_t)ow, (cuuint64_t)oh, (cuuint64_t)BG * ncls};
     cuuint64_t qstr[3] = {(cuuint64_t)Cp * 2, (cuuint64_t)ow * Cp * 2, (cuuint64_t)oh * ow * Cp * 2};
     cuuint32_t box[4] = {BK, QTW, QTH, 1};
     if (int r = make_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, ws.in1h, qdims, qstr, box, CU_TENSOR_MAP_SWIZZLE_128B)) return r;
   }
   int dmax_h = 1, dmax_w = 1;
-  for (int d = 0; d < D; ++d) { dmax_h = std::max(dmax_h, dph[d]); dmax_w = std::max(dmax_w, dpw[d]); }
+  for (int d = 0; d < D; ++d) { dmax_h = std::max(dmax_h, dph_u[d]); dmax_w = std::max(dmax_w, dpw_u[d]); }
   // x-extent of a query tile's bounding box: if it fits 24 columns, 8x24 target tiles span it (Geo<24>)
   const bool wide = (QTW - 1) * sw + (Pw - 1) * dmax_w + 1 <= 24;
   const int TTW = wide ? 24 : 16;
   {
-    cuuint32_t box[4] = {BK, (cuuint32_t)TTW, TTH, 1};
-    if (int r = make_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, ws.in2h, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return r;
+    // targets: the full-resolution in2; in lattice mode a box takes every lat-th pixel (TMA element strides)
+    cuuint64_t dims[4] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)BG};
+    cuuint64_t str[3] = {(cuuint64_t)Cp * 2, (cuuint64_t)W * Cp * 2, (cuuint64_t)H * W * Cp * 2};
+    cuuint32_t box[4] = {BK, (cuuint32_t)(TTW * lat), (cuuint32_t)(TTH * lat), 1};
+    cuuint32_t es[4] = {1, (cuuint32_t)lat, (cuuint32_t)lat, 1};
+    if (int r = make_tmap_ex(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, ws.in2h, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_128B)) return r;
   }
   Params P;
-  P.G = G; P.H = H; P.W = W;
+  P.G = G; P.H = Hu; P.W = Wu;
   P.oh = oh; P.ow = ow;
   P.Ph = Ph; P.Pw = Pw; P.sh = sh; P.sw = sw; P.padh = padh; P.padw = padw;
   P.D = D; P.KB = Cp / BK;
-  for (int d = 0; d < D; ++d) { P.dph[d] = dph[d]; P.dpw[d] = dpw[d]; }
+  for (int d = 0; d < D; ++d) { P.dph[d] = dph_u[d]; P.dpw[d] = dpw_u[d]; }
+  P.lat = lat; P.BG = BG; P.Hf = H; P.Wf = W; P.out_h = out_h; P.out_w = out_w;
   P.slope = slope;
   P.amax = ws.amax;
   P.scale = scale;
   P.out = out;
   P.out_bstride = out_bstride;
   // split the target sweep of a query tile over several CTAs when there are too few query tiles to fill the GPU evenly
-  const int n_qtiles = cdiv(P.ow, QTW) * cdiv(P.oh, QTH) * BG;
-  const int max_tiles = std::min(cdiv(H, TTH) + 1, cdiv((Ph - 1) * dmax_h + QTH * sh, TTH) + 1) *
-                        std::min(cdiv(W, TTW) + 1, cdiv((Pw - 1) * dmax_w + QTW * sw, TTW) + 1);
+  const int n_qtiles = cdiv(ow, QTW) * cdiv(oh, QTH) * BG * ncls;
+  const int max_tiles = std::min(cdiv(Hu, TTH) + 1, cdiv((Ph - 1) * dmax_h + QTH * sh, TTH) + 1) *
+                        std::min(cdiv(Wu, TTW) + 1, cdiv((Pw - 1) * dmax_w + QTW * sw, TTW) + 1);
   // cost model: CTAs run in waves of one per SM; a CTA costs its share of the target tiles plus ~2 tiles of fixed work
   P.nsplit = 1;
   {
@@ -436,7 +472,7 @@ int local_corr_tc_launch(const float* in1, const float* in2, int BG, int G, int 
       if (c < best) { best = c; P.nsplit = k; }
     }
   }
-  dim3 grid(cdiv(P.ow, QTW), cdiv(P.oh, QTH), BG * P.nsplit);
+  dim3 grid(cdiv(ow, QTW), cdiv(oh, QTH), BG * ncls * P.nsplit);
   EZB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "output too large for one launch");
   if (wide) {
     EZB_CUDA_OK(cudaFuncSetAttribute(local_corr_tc_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<24>::SMEM_BYTES));
