@@ -37,7 +37,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs-per-gpu", type=int, default=8, help="image pairs each rank processes per step")
-    ap.add_argument("--micro", type=int, default=4, help="pairs per pyramid build (micro-batch)")
+    ap.add_argument("--micro", type=int, default=8, help="pairs per pyramid build (micro-batch)")
     ap.add_argument("--pyramid-dtype", default="fp16", choices=["fp16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
