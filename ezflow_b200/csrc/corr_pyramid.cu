@@ -15,15 +15,16 @@
 //            f1: fp32 (B,C,N) -> fp16 K-major (B,N,Cp)                                   [A operand]
 //            f2: fp32 2x2 pools -> levels 1..L-1; then for every record tile a 256 x Cp fp16
 //                operand tile whose row n is the (pooled) f2 pixel of record column n     [B operand]
-//                (ezb_common.cuh: 8 subtiles of 4x8 pixels, all levels in one sequence)
+//                (ezb_common.cuh: 4 subtiles of 8x8 pixels, all levels in one sequence;
+//                rows permuted inside each 128-byte line for the epilogue, pyr_line_element_of_column)
 //   gemm   : persistent, warp-specialised tcgen05 kernel.  One CTA tile = 128 queries (TMEM lanes) x
 //            one record (256 TMEM columns).  The record operand (128 KB for C=256) stays resident in
-//            shared memory while the CTA sweeps query blocks (A streamed through a 4-stage TMA ring);
+//            shared memory while the CTA sweeps query blocks (A streamed through a 6-stage TMA ring);
 //            two 256-column accumulators double-buffer MMA against the epilogue.
 //            CTAs run as clusters of 2 that sweep the SAME query blocks against two different records:
 //            each CTA fetches half of every A stage and TMA-multicasts it to both, which halves the L2
-//            read traffic of the re-streamed A operand (the kernel is L2-fabric bound otherwise:
-//            profiles/r01_gemm_experiments.md).
+//            read traffic of the re-streamed A operand (the kernel is energy-bound at the board power cap; every
+//            byte that does not move helps: profiles/r01_gemm_experiments.md).
 //   epilogue: TMEM -> registers (tcgen05.ld.16x256b) -> (scale) -> fp16/fp32 -> 256-bit streaming stores straight
 //            from registers: the operand rows are ordered so that a quad of threads owns one query's 128-byte
 //            line, i.e. every store instruction writes 8 complete lines; no shared-memory staging.
