@@ -182,6 +182,13 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
       : "r"(taddr)
       : "memory");
 }
+// TMEM -> registers: 32 lanes x 8 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 // TMEM -> registers, 16 lanes x 256 bits repeated N times along the columns.  Thread t gets, for repetition i:
 //   r[4i+0], r[4i+1] = lane (t/4),     columns 8i + 2(t%4), +1
 //   r[4i+2], r[4i+3] = lane (t/4) + 8, same columns

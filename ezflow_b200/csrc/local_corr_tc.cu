@@ -31,7 +31,6 @@ namespace ezb {
 namespace k4tc {
 
 constexpr int QTH = 8, QTW = 16, BM = QTH * QTW;  // query tile  -> UMMA M = 128 (TMEM lanes)
-constexpr int TTH = 8;                            // target tile rows
 constexpr int BK = 64, KB_MAX = 4;                // C <= 256
 constexpr int A_KB_BYTES = BM * BK * 2;           // 16 KB
 constexpr int EPI_SPLIT = 4;                      // epilogue warps per TMEM lane quadrant
@@ -40,14 +39,15 @@ constexpr int NUM_THREADS = 128 + EPI_WARPS * 32;  // warp 0 TMA, 1 MMA, 2 TMEM 
 constexpr int MAX_DIL = 8;
 constexpr int TMEM_COLS = 512;
 
-// Target-tile geometry.  TTW = 16: the general 8x16 tile (UMMA N = 128).  TTW = 24: for small windows (the x-extent of a
-// query tile's bounding box fits 24 columns, e.g. PWC-Net's 9x9 at stride 1) the tile spans the whole box width, so no
-// displacement straddles two tiles in x and a CTA needs half as many tiles (UMMA N = 192).
-template <int TTW_>
+// Target-tile geometry (rows x columns of in2 pixels = UMMA N).  8x16 (N = 128) is the general tile.  When the x-extent of a
+// query tile's bounding box is small, the tile spans the whole box width instead, so that no displacement straddles two
+// tiles in x and fewer extraction slots are wasted: 8x24 (N = 192; PWC-Net's 9x9 window), 4x40 (N = 160; FlowNetC's 21x21
+// window in lattice mode).
+template <int TTW_, int TTH_>
 struct Geo {
-  static constexpr int TTW = TTW_, BN = TTH * TTW;
+  static constexpr int TTW = TTW_, TTH = TTH_, BN = TTH * TTW;
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
-  static constexpr int STAGES = BN <= 128 ? 4 : 2;
+  static constexpr int STAGES = BN <= 128 ? 4 : BN <= 160 ? 3 : 2;
   static constexpr int ACC_STRIDE = BN <= 128 ? 128 : 256;  // TMEM columns between accumulators
   static constexpr int NACC = TMEM_COLS / ACC_STRIDE;
   static constexpr int S_STRIDE = BN + 1;  // words; odd => lane = query accesses are conflict-free
@@ -57,7 +57,7 @@ struct Geo {
   static constexpr int SMEM_S = SMEM_B + STAGES * B_STAGE_BYTES;
   static constexpr int SMEM_BAR = SMEM_S + BM * S_STRIDE * 4;
   static constexpr int SMEM_BYTES = SMEM_BAR + 256 + 1024;
-  static_assert(CPW % 16 == 0 && SMEM_BYTES <= 232448 && (2 * STAGES + 2 + 2 * NACC) * 8 + 4 <= 256, "tile geometry");
+  static_assert(CPW % 8 == 0 && CPW <= 56 && BN % 16 == 0 && SMEM_BYTES <= 232448 && (2 * STAGES + 2 + 2 * NACC) * 8 + 4 <= 256, "tile geometry");
 };
 
 struct Params {
@@ -127,11 +127,11 @@ __global__ void __launch_bounds__(256) gather_queries_kmajor_kernel(const float*
 __device__ __forceinline__ int floor_div(int a, float inv_b) { return __float2int_rd(((float)a + 0.5f) * inv_b); }
 __device__ __forceinline__ int ceil_div(int a, float inv_b) { return -floor_div(-a, inv_b); }
 
-template <int TTW_>
+template <int TTW_, int TTH_>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     local_corr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params P) {
-  using G = Geo<TTW_>;
-  constexpr int TTW = G::TTW, BN = G::BN, STAGES = G::STAGES, NACC = G::NACC, B_STAGE_BYTES = G::B_STAGE_BYTES;
+  using G = Geo<TTW_, TTH_>;
+  constexpr int TTW = G::TTW, TTH = G::TTH, BN = G::BN, STAGES = G::STAGES, NACC = G::NACC, B_STAGE_BYTES = G::B_STAGE_BYTES;
   constexpr int S_STRIDE = G::S_STRIDE, CPW = G::CPW, ACC_STRIDE = G::ACC_STRIDE;
   constexpr int SMEM_A = G::SMEM_A, SMEM_B = G::SMEM_B, SMEM_S = G::SMEM_S, SMEM_BAR = G::SMEM_BAR;
   extern __shared__ uint8_t smem_raw[];
@@ -282,19 +282,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quad * 32) << 16) + part * CPW;
       {
-        uint32_t r0[32], r1[16];
-        ptx::tmem_ld_32x32b_x32(taddr, r0);
-        if constexpr (CPW == 48) ptx::tmem_ld_32x32b_x16(taddr + 32, r1);
+        // CPW = 32 (+16) (+8) columns of this warp's share
+        constexpr bool k32 = CPW >= 32, k16 = (CPW % 32) >= 16, k8 = (CPW % 16) >= 8;
+        uint32_t r0[32], r1[16], r2[8];
+        if constexpr (k32) ptx::tmem_ld_32x32b_x32(taddr, r0);
+        if constexpr (k16) ptx::tmem_ld_32x32b_x16(taddr + (k32 ? 32 : 0), r1);
+        if constexpr (k8) ptx::tmem_ld_32x32b_x8(taddr + (k32 ? 32 : 0) + (k16 ? 16 : 0), r2);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(tmem_empty(acc));  // the accumulator is in registers: release it early
         float* dst = Srow + part * CPW;
+        if constexpr (k32) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) dst[j] = __uint_as_float(r0[j]);
-        if constexpr (CPW == 48) {
+          for (int j = 0; j < 32; ++j) dst[j] = __uint_as_float(r0[j]);
+        }
+        if constexpr (k16) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) dst[32 + j] = __uint_as_float(r1[j]);
+          for (int j = 0; j < 16; ++j) dst[(k32 ? 32 : 0) + j] = __uint_as_float(r1[j]);
+        }
+        if constexpr (k8) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[(k32 ? 32 : 0) + (k16 ? 16 : 0) + j] = __uint_as_float(r2[j]);
         }
       }
       quad_sync();  // all column shares of the rows are in shared memory
@@ -435,9 +444,9 @@ int local_corr_tc_launch(const float* in1, const float* in2, int BG, int G, int 
   }
   int dmax_h = 1, dmax_w = 1;
   for (int d = 0; d < D; ++d) { dmax_h = std::max(dmax_h, dph_u[d]); dmax_w = std::max(dmax_w, dpw_u[d]); }
-  // x-extent of a query tile's bounding box: if it fits 24 columns, 8x24 target tiles span it (Geo<24>)
-  const bool wide = (QTW - 1) * sw + (Pw - 1) * dmax_w + 1 <= 24;
-  const int TTW = wide ? 24 : 16;
+  // x-extent of a query tile's bounding box (layout units): if it fits, the target tile spans it (8x24 / 4x40)
+  const int xext = (QTW - 1) * sw + (Pw - 1) * dmax_w + 1;
+  const int TTW = xext <= 24 ? 24 : xext <= 40 ? 40 : 16, TTH = TTW == 40 ? 4 : 8;
   {
     // targets: the full-resolution in2; in lattice mode a box takes every lat-th pixel (TMA element strides)
     cuuint64_t dims[4] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)BG};
@@ -474,12 +483,15 @@ int local_corr_tc_launch(const float* in1, const float* in2, int BG, int G, int 
   }
   dim3 grid(cdiv(ow, QTW), cdiv(oh, QTH), BG * ncls * P.nsplit);
   EZB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "output too large for one launch");
-  if (wide) {
-    EZB_CUDA_OK(cudaFuncSetAttribute(local_corr_tc_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<24>::SMEM_BYTES));
-    local_corr_tc_kernel<24><<<grid, NUM_THREADS, Geo<24>::SMEM_BYTES, st>>>(tmA, tmB, P);
+  if (TTW == 24) {
+    EZB_CUDA_OK(cudaFuncSetAttribute(local_corr_tc_kernel<24, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<24, 8>::SMEM_BYTES));
+    local_corr_tc_kernel<24, 8><<<grid, NUM_THREADS, Geo<24, 8>::SMEM_BYTES, st>>>(tmA, tmB, P);
+  } else if (TTW == 40) {
+    EZB_CUDA_OK(cudaFuncSetAttribute(local_corr_tc_kernel<40, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<40, 4>::SMEM_BYTES));
+    local_corr_tc_kernel<40, 4><<<grid, NUM_THREADS, Geo<40, 4>::SMEM_BYTES, st>>>(tmA, tmB, P);
   } else {
-    EZB_CUDA_OK(cudaFuncSetAttribute(local_corr_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<16>::SMEM_BYTES));
-    local_corr_tc_kernel<16><<<grid, NUM_THREADS, Geo<16>::SMEM_BYTES, st>>>(tmA, tmB, P);
+    EZB_CUDA_OK(cudaFuncSetAttribute(local_corr_tc_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<16, 8>::SMEM_BYTES));
+    local_corr_tc_kernel<16, 8><<<grid, NUM_THREADS, Geo<16, 8>::SMEM_BYTES, st>>>(tmA, tmB, P);
   }
   EZB_LAUNCH_OK();
   return EZB_OK;
