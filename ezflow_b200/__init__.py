@@ -20,7 +20,7 @@ from .similarity import (
     set_local_corr_mode,
     set_pyramid_dtype,
 )
-from .utils import coords_grid, warp
+from .utils import convex_upsample_flow, coords_grid, warp
 
 __version__ = "0.1.0"
 

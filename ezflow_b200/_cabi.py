@@ -56,6 +56,9 @@ _SIGNATURES = {
     "ezb_l2_normalize_fwd": ([c_vp, c_int, c_int, c_int, c_f32, c_vp, c_vp], c_int),
     "ezb_warp_fwd": ([c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp], c_int),
     "ezb_warp_bwd": ([c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp], c_int),
+    "ezb_convex_upsample_fwd": ([c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp], c_int),
+    "ezb_convex_upsample_bwd_workspace_bytes": ([c_int, c_int, c_int, c_int, _P(c_sz)], c_int),
+    "ezb_convex_upsample_bwd": ([c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_sz, c_vp], c_int),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

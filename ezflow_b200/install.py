@@ -5,7 +5,8 @@ The reference's ``Registry`` asserts on duplicate names (ezflow/utils/registry.p
 entries are overwritten in ``_obj_map``.  FlowNetC and PWC-Net bypass the registry and import the
 sampler by name (ezflow/models/flownet_c.py:9, ezflow/decoder/pyramid.py:6), and
 ``learnable_cost`` binds a module-global alias (ezflow/similarity/learnable_cost.py:6-9); those
-globals are rebound too, as is ``warp`` in the PWC decoder (ezflow/decoder/pyramid.py:138).
+globals are rebound too, as are ``warp`` in the PWC decoder (ezflow/decoder/pyramid.py:138) and
+``convex_upsample_flow`` in RAFT and DCVNet's decoder (ezflow/models/raft.py:127, decoder/dilated_flow_stack_filter.py:219).
 All of them are read at model-construction / call time, so ``install()`` must run before ``build_model``.
 """
 
@@ -33,7 +34,7 @@ def _rebind(modname, attr, value):
     setattr(mod, attr, value)
 
 
-def install(patch_warp=True):
+def install(patch_warp=True, patch_upsample=True):
     """Returns the list of (module, attribute) pairs that were rebound."""
     ez_sim = importlib.import_module("ezflow.similarity")
     reg = ez_sim.SIMILARITY_REGISTRY
@@ -56,6 +57,10 @@ def install(patch_warp=True):
         _rebind("ezflow.decoder.pyramid", "warp", U.warp)
         _rebind("ezflow.utils.warp", "warp", U.warp)
         _rebind("ezflow.utils", "warp", U.warp)
+    if patch_upsample:
+        # convex upsampling of every iteration's flow (ezflow/models/raft.py:9,127; decoder/dilated_flow_stack_filter.py:8,219)
+        for modname in ("ezflow.utils.resampling", "ezflow.utils", "ezflow.models.raft", "ezflow.decoder.dilated_flow_stack_filter"):
+            _rebind(modname, "convex_upsample_flow", U.convex_upsample_flow)
     return [k for k in _saved if k[0] != "<registry>"]
 
 

@@ -169,6 +169,23 @@ int ezb_warp_fwd(const float* x, const float* flow, int B, int C, int H, int W, 
 int ezb_warp_bwd(const float* x, const float* flow, const float* dout, int B, int C, int H, int W,
                  float* dx, float* dflow, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Convex flow upsampling (K7)   replaces convex_upsample_flow  ezflow/utils/resampling.py:112-141
+ * (called after every RAFT iteration, models/raft.py:127, and by DCVNet,
+ * decoder/dilated_flow_stack_filter.py:219)
+ *   flow (N,C,H,W) fp32, C in 1..4; mask_logits (N, 9*s*s, H, W) fp32 viewed (N,1,9,s,s,H,W);
+ *   out (N,C,s*H,s*W) = sum_k softmax_k(mask_logits) * unfold3x3(flow)       (zero padded)
+ * Backward: dflow (N,C,H,W) and / or dmask_logits (same shape as mask_logits); either may be NULL.
+ * dflow needs a workspace of ezb_convex_upsample_bwd_workspace_bytes (per-tap partial sums that a
+ * second pass gathers, so the result does not depend on atomics ordering).
+ * ------------------------------------------------------------------------------------------- */
+int ezb_convex_upsample_fwd(const float* flow, const float* mask_logits, int N, int C, int H, int W,
+                            int out_stride, float* out, void* stream);
+int ezb_convex_upsample_bwd_workspace_bytes(int N, int C, int H, int W, size_t* bytes);
+int ezb_convex_upsample_bwd(const float* flow, const float* mask_logits, const float* dout, int N, int C,
+                            int H, int W, int out_stride, float* dflow, float* dmask_logits,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -383,3 +383,45 @@ def warp(x: np.ndarray, flow: np.ndarray) -> np.ndarray:
     mask = np.where(mask < dt(0.9999), dt(0), mask)
     mask = np.where(mask > 0, dt(1), mask)
     return (out * mask).astype(x.dtype)
+
+
+# --------------------------------------------------------------------------
+# K7: convex flow upsampling      ezflow/utils/resampling.py:112-141
+# --------------------------------------------------------------------------
+def _unfold3x3(flow: np.ndarray) -> np.ndarray:
+    """F.unfold(flow, [3,3], padding=1) viewed (N, C, 9, H, W): tap k = ky*3+kx reads flow[h+ky-1, w+kx-1] (zero padded)."""
+    n, c, h, w = flow.shape
+    padded = np.pad(flow, ((0, 0), (0, 0), (1, 1), (1, 1)))
+    return np.stack([padded[:, :, ky : ky + h, kx : kx + w] for ky in range(3) for kx in range(3)], axis=2)
+
+
+def _softmax(x: np.ndarray, axis: int) -> np.ndarray:
+    e = np.exp(x - x.max(axis=axis, keepdims=True))
+    return e / e.sum(axis=axis, keepdims=True)
+
+
+def convex_upsample_flow(flow: np.ndarray, mask_logits: np.ndarray, out_stride: int) -> np.ndarray:
+    """resampling.py:131-141: softmax over the 9 taps, weighted 3x3 unfold, pixel-shuffle to (N, C, s*H, s*W)."""
+    n, c, h, w = flow.shape
+    s = int(out_stride)
+    probs = _softmax(mask_logits.reshape(n, 1, 9, s, s, h, w), axis=2)
+    taps = _unfold3x3(flow).reshape(n, c, 9, 1, 1, h, w)
+    up = (probs * taps).sum(axis=2)  # (n, c, s, s, h, w)
+    return up.transpose(0, 1, 4, 2, 5, 3).reshape(n, c, s * h, s * w).astype(flow.dtype)
+
+
+def convex_upsample_flow_bwd(flow: np.ndarray, mask_logits: np.ndarray, out_stride: int, dout: np.ndarray):
+    """Adjoint of convex_upsample_flow (autograd of resampling.py:131-141): returns (dflow, dmask_logits)."""
+    n, c, h, w = flow.shape
+    s = int(out_stride)
+    probs = _softmax(mask_logits.reshape(n, 1, 9, s, s, h, w), axis=2)
+    taps = _unfold3x3(flow).reshape(n, c, 9, 1, 1, h, w)
+    dup = dout.reshape(n, c, h, s, w, s).transpose(0, 1, 3, 5, 2, 4)[:, :, None]  # (n, c, 1, s, s, h, w)
+    g = (dup * taps).sum(axis=1, keepdims=True)  # (n, 1, 9, s, s, h, w)
+    dlogits = probs * (g - (probs * g).sum(axis=2, keepdims=True))
+    dtaps = (probs * dup).sum(axis=(3, 4))  # (n, c, 9, h, w)
+    dpad = np.zeros((n, c, h + 2, w + 2), dtype=flow.dtype)
+    for ky in range(3):
+        for kx in range(3):
+            dpad[:, :, ky : ky + h, kx : kx + w] += dtaps[:, :, ky * 3 + kx]
+    return dpad[:, :, 1:-1, 1:-1].astype(flow.dtype), dlogits.reshape(mask_logits.shape).astype(flow.dtype)

@@ -64,6 +64,8 @@ def test_no_cpu_fallback():
         E.MatryoshkaDilatedCostVolume()(x, x)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         E.warp(x, torch.zeros(1, 2, 8, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        E.convex_upsample_flow(torch.zeros(1, 2, 8, 8), torch.zeros(1, 9 * 64, 8, 8), 8)
     # parameter errors come before device errors, as in the reference (sampler.py:89-94)
     with pytest.raises(NotImplementedError):
         E.iter_spatial_correlation_sample(x, x, kernel_size=3)
@@ -101,6 +103,9 @@ def test_install_into_reference_and_yaml_models():
         assert R.get("MutliScalePairwise4DCorr") is E.MutliScalePairwise4DCorr
         raft = build_model("RAFT", cfg_path=refshim.reference_config_path("raft.yaml"), custom_cfg=True)
         assert raft.similarity_fn is E.MutliScalePairwise4DCorr
+        import ezflow.models.raft as ref_raft
+
+        assert ref_raft.convex_upsample_flow is E.convex_upsample_flow
         fnc = build_model("FlowNetC", cfg_path=refshim.reference_config_path("flownet_c.yaml"), custom_cfg=True)
         assert isinstance(fnc.correlation_layer, E.IterSpatialCorrelationSampler)
         assert (fnc.correlation_layer.patch_size, fnc.correlation_layer.dilation_patch) == (21, 2)

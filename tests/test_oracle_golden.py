@@ -133,3 +133,13 @@ def test_pool_floor_and_adjoint():
     dx = O.avg_pool2x2_bwd(dy, (7, 9))
     assert np.all(dx[..., 6, :] == 0) and np.all(dx[..., :, 8] == 0)
     np.testing.assert_allclose((y * dy).sum(), (x * dx).sum(), rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["convex_up_s8", "convex_up_s4"])
+def test_convex_upsample(golden, name):
+    g = golden(name)
+    s = int(g["out_stride"])
+    close(O.convex_upsample_flow(g["flow"], g["logits"], s), g["out"])
+    dflow, dlogits = O.convex_upsample_flow_bwd(g["flow"], g["logits"], s, g["dout"])
+    close(dflow, g["dflow"], rtol=5e-5)
+    close(dlogits, g["dlogits"], rtol=5e-5)

@@ -98,7 +98,33 @@ def cfg5():
     report("cfg5 RAFT 1080p fwd+bwd, 1 pair (build, 12 lookups, 12 lookup-bwd, pyramid-bwd)", ms, nb, 3 * 2.0 * N * N * 256)
 
 
+def upsample():
+    """Convex flow upsampling at the headline size: 4 pairs, 135x240 -> 1080x1920 (called once per RAFT iteration);
+    the reference's PyTorch ops (softmax + unfold + mul + sum + permute) beside it."""
+    n, h, w, s = 4, 135, 240, 8
+    flow = torch.randn(n, 2, h, w, device=dev) * 8
+    logits = torch.randn(n, 9 * s * s, h, w, device=dev)
+    nb = (logits.numel() + flow.numel() + n * 2 * s * s * h * w) * 4
+    with torch.no_grad():
+        report("convex upsample fwd B4 135x240 s8", timed(lambda: E.convex_upsample_flow(flow, logits, s)), nb, 0)
+
+        def torch_ref():
+            probs = torch.softmax(logits.view(n, 1, 9, s, s, h, w), dim=2)
+            up = torch.nn.functional.unfold(flow, [3, 3], padding=1).view(n, 2, 9, 1, 1, h, w)
+            return torch.sum(probs * up, dim=2).permute(0, 1, 4, 2, 5, 3).reshape(n, 2, s * h, s * w)
+
+        report("  same, reference PyTorch ops on this GPU", timed(torch_ref), nb, 0)
+    fl, lg = flow.clone().requires_grad_(True), logits.clone().requires_grad_(True)
+    dout = torch.randn(n, 2, s * h, s * w, device=dev)
+
+    def fb():
+        fl.grad = lg.grad = None
+        (E.convex_upsample_flow(fl, lg, s) * dout).sum().backward()
+
+    report("convex upsample fwd+bwd B4 (incl. autograd glue)", timed(fb), 3 * nb, 0)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["cfg2", "cfg3", "cfg4", "cfg5"]
+    which = sys.argv[1:] or ["cfg2", "cfg3", "cfg4", "cfg5", "upsample"]
     for w in which:
         globals()[w]()

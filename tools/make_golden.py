@@ -3,7 +3,7 @@
 imported from /root/reference through tests/refshim.py) on seeded inputs.
 
 The reference cannot travel to the GPU box, so its outputs are committed as small
-fixtures.  Re-run with:  python tools/make_golden.py
+fixtures.  Re-run with:  python tools/make_golden.py [name-prefix ...]
 Every fixture stores its inputs, so tests never depend on RNG reproducibility.
 """
 
@@ -23,6 +23,7 @@ assert ez is not None and refshim.reference_root() == "/root/reference", "needs 
 from ezflow.similarity import SIMILARITY_REGISTRY  # noqa: E402
 from ezflow.similarity.correlation.sampler import iter_spatial_correlation_sample  # noqa: E402
 from ezflow.utils import coords_grid  # noqa: E402
+from ezflow.utils.resampling import convex_upsample_flow  # noqa: E402
 from ezflow.utils.warp import warp  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
@@ -34,7 +35,12 @@ def npy(t):
     return t.detach().cpu().numpy()
 
 
+ONLY = [a for a in sys.argv[1:] if not a.startswith("-")]  # optional fixture-name prefixes: regenerate only those
+
+
 def save(name, **arrs):
+    if ONLY and not any(name.startswith(p) for p in ONLY):
+        return
     path = os.path.join(OUT, name + ".npz")
     np.savez_compressed(path, **{k: (npy(v) if torch.is_tensor(v) else np.asarray(v)) for k, v in arrs.items()})
     print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB")
@@ -122,6 +128,16 @@ def main():
     dout = torch.randn(out.shape, generator=g)
     (out * dout).sum().backward()
     save("warp", x=x, flow=flow, out=out, dout=dout, dx=x.grad, dflow=flow.grad)
+
+    # ---- convex flow upsampling (K7) ----
+    g = torch.Generator().manual_seed(51)
+    for name, (n, c, h, w, st) in {"convex_up_s8": (1, 2, 4, 35, 8), "convex_up_s4": (2, 3, 5, 33, 4)}.items():
+        flow = (torch.randn(n, c, h, w, generator=g) * 4.0).requires_grad_(True)
+        logits = (torch.randn(n, 9 * st * st, h, w, generator=g) * 2.0).requires_grad_(True)
+        out = convex_upsample_flow(flow, logits, st)
+        dout = torch.randn(out.shape, generator=g)
+        (out * dout).sum().backward()
+        save(name, flow=flow, logits=logits, out=out, dout=dout, dflow=flow.grad, dlogits=logits.grad, out_stride=st)
 
 
 if __name__ == "__main__":
