@@ -6,7 +6,7 @@ Host side: Python classes mirroring ``ezflow.similarity`` (same names, construct
 """
 
 from . import _cabi
-from .install import install, uninstall
+from .install import fuse_model, install, uninstall
 from .registry import SIMILARITY_REGISTRY, build_similarity
 from .similarity import (
     CorrelationLayer,
@@ -14,9 +14,11 @@ from .similarity import (
     MatryoshkaDilatedCostVolume,
     MatryoshkaDilatedCostVolumeList,
     MutliScalePairwise4DCorr,
+    WarpedFeatures,
     get_local_corr_mode,
     get_pyramid_dtype,
     iter_spatial_correlation_sample,
+    lazy_warp,
     set_local_corr_mode,
     set_pyramid_dtype,
 )

@@ -213,7 +213,7 @@ namespace ezb {
 // local_corr_tc.cu
 bool local_corr_tc_supported(int C, int sh, int sw, int D);
 size_t local_corr_tc_workspace_bytes(int BG, int C, int H, int W, int padh, int padw);
-int local_corr_tc_launch(const float* in1, const float* in2, int BG, int G, int C, int H, int W, int Ph, int Pw, int sh, int sw,
+int local_corr_tc_launch(const float* in1, const float* in2, const float* flow2, int BG, int G, int C, int H, int W, int Ph, int Pw, int sh, int sw,
                          int padh, int padw, int D, const int* dph, const int* dpw, float scale, float slope, float* out,
                          long long out_bstride, void* workspace, size_t workspace_bytes, cudaStream_t st);
 }  // namespace ezb
@@ -240,7 +240,7 @@ extern "C" int ezb_local_corr_fwd(const float* in1, const float* in2, int B, int
   if (int r = check_local_args(B, C, H, W, Ph, Pw, sh, sw, padh, padw, dph, dpw)) return r;
   if (workspace != nullptr && local_corr_tc_supported(C, sh, sw, 1)) {
     const int oh = cdiv(H + 2 * padh, sh), ow = cdiv(W + 2 * padw, sw);
-    return local_corr_tc_launch(in1, in2, B, 1, C, H, W, Ph, Pw, sh, sw, padh, padw, 1, &dph, &dpw, scale, slope, out,
+    return local_corr_tc_launch(in1, in2, nullptr, B, 1, C, H, W, Ph, Pw, sh, sw, padh, padw, 1, &dph, &dpw, scale, slope, out,
                                 out_batch_stride > 0 ? out_batch_stride : (int64_t)Ph * Pw * oh * ow, workspace, workspace_bytes,
                                 static_cast<cudaStream_t>(stream));
   }
@@ -264,7 +264,7 @@ extern "C" int ezb_matryoshka_fwd(const float* x1, const float* x2, int B, int G
   for (int d = 0; d < D; ++d) EZB_REQUIRE(dil[d] > 0, "dilation must be positive");
   if (workspace != nullptr && local_corr_tc_supported(Cg, stride, stride, D)) {
     const int oh = cdiv(H, stride), ow = cdiv(W, stride);
-    return local_corr_tc_launch(x1, x2, B * G, G, Cg, H, W, P_, P_, stride, stride, 0, 0, D, dil, dil, 1.f, slope, out,
+    return local_corr_tc_launch(x1, x2, nullptr, B * G, G, Cg, H, W, P_, P_, stride, stride, 0, 0, D, dil, dil, 1.f, slope, out,
                                 out_batch_stride > 0 ? out_batch_stride : (int64_t)D * G * P_ * P_ * oh * ow, workspace,
                                 workspace_bytes, static_cast<cudaStream_t>(stream));
   }
@@ -282,6 +282,21 @@ extern "C" int ezb_matryoshka_fwd(const float* x1, const float* x2, int B, int G
   P.scale = 1.f; P.slope = slope;
   P.out_bstride = out_batch_stride > 0 ? out_batch_stride : (int64_t)D * G * P_ * P_ * P.oh * P.ow;
   return k4::launch_fwd(P, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ezb_warp_local_corr_fwd(const float* in1, const float* in2, const float* flow, int B, int C, int H, int W, int Ph,
+                                       int Pw, int sh, int sw, int padh, int padw, int dph, int dpw, float scale, float slope,
+                                       float* out, int64_t out_batch_stride, void* workspace, size_t workspace_bytes,
+                                       void* stream) {
+  EZB_REQUIRE(in1 && in2 && flow && out, "null pointer");
+  if (int r = check_local_args(B, C, H, W, Ph, Pw, sh, sw, padh, padw, dph, dpw)) return r;
+  if (workspace == nullptr || !local_corr_tc_supported(C, sh, sw, 1))
+    return fail(EZB_ERR_UNSUPPORTED, "the warp-fused correlation runs on the tensor-core path only (needs a workspace and C <= 256); "
+                                     "call ezb_warp_fwd and ezb_local_corr_fwd instead");
+  const int oh = cdiv(H + 2 * padh, sh), ow = cdiv(W + 2 * padw, sw);
+  return local_corr_tc_launch(in1, in2, flow, B, 1, C, H, W, Ph, Pw, sh, sw, padh, padw, 1, &dph, &dpw, scale, slope, out,
+                              out_batch_stride > 0 ? out_batch_stride : (int64_t)Ph * Pw * oh * ow, workspace, workspace_bytes,
+                              static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int ezb_local_corr_bwd(const float* in1, const float* in2, const float* dout, int B, int C, int H, int W, int Ph,

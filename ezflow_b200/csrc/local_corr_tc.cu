@@ -23,6 +23,7 @@
 #include "ezb_common.cuh"
 #include "ezb_ptx.cuh"
 #include "ezb_tma.cuh"
+#include "ezb_warp.cuh"
 
 #include <climits>
 #include <cstdlib>
@@ -118,6 +119,58 @@ __global__ void __launch_bounds__(256) gather_queries_kmajor_kernel(const float*
     const int nl = warp * 4 + i, nn = n0 + nl;
     if (nn < NQ)
       *reinterpret_cast<__half2*>(dst + ((long long)blockIdx.z * NQ + nn) * Cp + c0 + 2 * lane) =
+          __floats2half2_rn(tile[2 * lane][nl], tile[2 * lane + 1][nl]);
+  }
+}
+
+// Target operand of the warp-fused correlation (PWC-Net: warp(features2, flow) feeds the sampler, reference
+// decoder/pyramid.py:138-141): dst[bg, y, x, c] = 2^-e2 * warp(in2, flow)[bg, c, y, x] — the bilinear warp of K5 (warp.cu)
+// evaluated while the operand is converted, so the warped fp32 tensor is never written or re-read.  e2 comes from
+// absmax(in2), an upper bound of the warped tensor's absmax (every warped value is a convex combination times a 0/1 mask).
+// blockIdx.z in [BG, 2 BG) (when in1 != nullptr) converts the query tensor in1 plainly in the same launch.
+__global__ void __launch_bounds__(256) warp_convert_kmajor_kernel(const float* __restrict__ in2, const float* __restrict__ flow,
+                                                                  __half* __restrict__ dst2, const float* __restrict__ in1,
+                                                                  __half* __restrict__ dst1, const unsigned int* __restrict__ amax,
+                                                                  int BG, int G, int C, int Cp, int H, int W) {
+  __shared__ float tile[64][33];
+  const bool plain = blockIdx.z >= BG;
+  const int bg = plain ? blockIdx.z - BG : blockIdx.z, N = H * W;
+  const float* src = (plain ? in1 : in2) + (long long)bg * C * N;
+  __half* dst = plain ? dst1 : dst2;
+  const int e = (int)((amax[plain ? bg : BG + bg] >> 23) & 0xff);
+  const float sc = __uint_as_float((unsigned int)(127 - (e == 0 ? 0 : max(-126, min(126, e - 127)))) << 23);  // 2^-e
+  const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = min(n0 + lane, N - 1);
+  if (plain) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + warp * 8 + i;
+      tile[warp * 8 + i][lane] = c < C ? __ldg(src + (long long)c * N + n) * sc : 0.f;
+    }
+  } else {
+    const float* fl = flow + (long long)(bg / G) * 2 * N;
+    const int py = n / W, px = n - py * W;
+    const k5::Taps t = k5::make_taps(__ldg(fl + n), __ldg(fl + N + n), px, py, H, W);
+    k5::Gather g = k5::make_gather(t, W);
+    if (g.zero) g.w00 = g.w01 = g.w10 = g.w11 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + warp * 8 + i;
+      float v = 0.f;
+      if (c < C) {
+        const float* sp = src + (long long)c * N;
+        v = ((g.w00 * __ldg(sp + g.oaa) + g.w01 * __ldg(sp + g.oab)) + (g.w10 * __ldg(sp + g.oba) + g.w11 * __ldg(sp + g.obb))) * sc;
+      }
+      tile[warp * 8 + i][lane] = v;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int nl = warp * 4 + i, nn = n0 + nl;
+    if (nn < N)
+      *reinterpret_cast<__half2*>(dst + ((long long)bg * N + nn) * Cp + c0 + 2 * lane) =
           __floats2half2_rn(tile[2 * lane][nl], tile[2 * lane + 1][nl]);
   }
 }
@@ -398,9 +451,9 @@ size_t local_corr_tc_workspace_bytes(int BG, int C, int H, int W, int padh, int 
   return k4tc::ws_layout(BG, C, H, W, padh, padw, nullptr, nullptr) + 1024;
 }
 
-int local_corr_tc_launch(const float* in1, const float* in2, int BG, int G, int C, int H, int W, int Ph, int Pw, int sh, int sw,
-                         int padh, int padw, int D, const int* dph, const int* dpw, float scale, float slope, float* out,
-                         long long out_bstride, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+int local_corr_tc_launch(const float* in1, const float* in2, const float* flow2, int BG, int G, int C, int H, int W, int Ph, int Pw,
+                         int sh, int sw, int padh, int padw, int D, const int* dph, const int* dpw, float scale, float slope,
+                         float* out, long long out_bstride, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   using namespace k4tc;
   const int Cp = round_up(C, BK), N = H * W;
   uintptr_t wbase = (reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023);
@@ -426,10 +479,18 @@ int local_corr_tc_launch(const float* in1, const float* in2, int BG, int G, int 
   const int* dpw_u = lat > 1 ? &one : dpw;
   EZB_REQUIRE((long long)BG * ncls <= 65535, "batch too large for one launch (split it)");
 
-  if (lat == 1 && sh == 1 && sw == 1 && padh == 0 && padw == 0) {  // queries = all pixels of in1: one launch converts both tensors
+  const bool dense_queries = lat == 1 && sh == 1 && sw == 1 && padh == 0 && padw == 0;  // queries = all pixels of in1
+  if (flow2) {  // targets = warp(in2, flow2), evaluated during the conversion
+    EZB_REQUIRE(2 * BG <= 65535, "batch too large for one launch (split it)");
+    warp_convert_kmajor_kernel<<<dim3(cdiv(N, 32), Cp / 64, dense_queries ? 2 * BG : BG), 256, 0, st>>>(
+        in2, flow2, ws.in2h, dense_queries ? in1 : nullptr, ws.in1h, ws.amax, BG, G, C, Cp, H, W);
+    EZB_LAUNCH_OK();
+  } else if (dense_queries) {  // one launch converts both tensors
     if (int r = prep::launch_convert_kmajor2(in1, ws.in1h, in2, ws.in2h, ws.amax, BG, C, Cp, N, st)) return r;
-  } else {  // strided / padded / per-class queries: gather only the query pixels of in1, (BG * ncls, oh, ow, Cp)
+  } else {
     if (int r = prep::launch_convert_kmajor(in2, ws.in2h, ws.amax + BG, BG, C, Cp, N, st)) return r;
+  }
+  if (!dense_queries) {  // strided / padded / per-class queries: gather only the query pixels of in1, (BG * ncls, oh, ow, Cp)
     gather_queries_kmajor_kernel<<<dim3(cdiv(oh * ow, 32), Cp / 64, BG * ncls), 256, 0, st>>>(in1, ws.in1h, ws.amax, C, Cp, H, W, oh, ow,
                                                                                              sh, sw, padh, padw, lat);
     EZB_LAUNCH_OK();

@@ -6,44 +6,10 @@
 // One thread per output pixel computes the four taps once and sweeps the channels (reads and writes
 // are coalesced along x).  HBM-bound: C*(4 B read + 4 B write) + 8 B of flow per pixel.
 #include "ezb_common.cuh"
+#include "ezb_warp.cuh"
 
 namespace ezb {
 namespace k5 {
-
-struct Taps {
-  int x0, y0;
-  float wx0, wx1, wy0, wy1;
-  bool vx0, vx1, vy0, vy1;
-  float mask;
-};
-
-__device__ __forceinline__ Taps make_taps(float fx, float fy, int x, int y, int H, int W) {
-  // follow the reference's normalise -> grid_sample un-normalise round trip (warp.py:32-33)
-  const float gx = 2.0f * ((float)x + fx) / (float)max(W - 1, 1) - 1.0f;
-  const float gy = 2.0f * ((float)y + fy) / (float)max(H - 1, 1) - 1.0f;
-  const float ix = ((gx + 1.f) / 2.f) * (float)(W - 1);
-  const float iy = ((gy + 1.f) / 2.f) * (float)(H - 1);
-  Taps t;
-  const float x0f = floorf(ix), y0f = floorf(iy);
-  t.wx1 = ix - x0f;
-  t.wx0 = 1.f - t.wx1;
-  t.wy1 = iy - y0f;
-  t.wy0 = 1.f - t.wy1;
-  const float xc = fminf(fmaxf(x0f, -2.f), (float)W), yc = fminf(fmaxf(y0f, -2.f), (float)H);
-  t.x0 = (xc == xc) ? (int)xc : -2;
-  t.y0 = (yc == yc) ? (int)yc : -2;
-  t.vx0 = t.x0 >= 0 && t.x0 < W;
-  t.vx1 = t.x0 + 1 >= 0 && t.x0 + 1 < W;
-  t.vy0 = t.y0 >= 0 && t.y0 < H;
-  t.vy1 = t.y0 + 1 >= 0 && t.y0 + 1 < H;
-  float m = 0.f;
-  if (t.vy0 && t.vx0) m += t.wy0 * t.wx0;
-  if (t.vy0 && t.vx1) m += t.wy0 * t.wx1;
-  if (t.vy1 && t.vx0) m += t.wy1 * t.wx0;
-  if (t.vy1 && t.vx1) m += t.wy1 * t.wx1;
-  t.mask = (m < 0.9999f) ? 0.f : 1.f;  // mask<0.9999 -> 0 ; mask>0 -> 1   (warp.py:39-40)
-  return t;
-}
 
 // thread = pixel, blockIdx.y = chunk of CCH channels: the taps (weights folded with validity and the mask, addresses
 // clamped into the image) are computed once per thread, then the channel loop is 4 loads + 4 FMAs + 1 store, unrolled so
@@ -64,15 +30,11 @@ __global__ void __launch_bounds__(128) warp_fwd_kernel(const float* __restrict__
     for (int c = c0; c < c1; ++c, dst += HW) *dst = 0.f;
     return;
   }
-  const float w00 = (t.vy0 && t.vx0) ? t.wy0 * t.wx0 : 0.f, w01 = (t.vy0 && t.vx1) ? t.wy0 * t.wx1 : 0.f;
-  const float w10 = (t.vy1 && t.vx0) ? t.wy1 * t.wx0 : 0.f, w11 = (t.vy1 && t.vx1) ? t.wy1 * t.wx1 : 0.f;
-  const int ya = t.vy0 ? t.y0 : t.y0 + 1, yb = t.vy1 ? t.y0 + 1 : t.y0;  // invalid taps read a valid neighbour (weight 0)
-  const int xa = t.vx0 ? t.x0 : t.x0 + 1, xb = t.vx1 ? t.x0 + 1 : t.x0;
+  const Gather g = make_gather(t, W);
   const float* s = x + ((long long)b * C + c0) * HW;
-  const long long oaa = (long long)ya * W + xa, oab = (long long)ya * W + xb, oba = (long long)yb * W + xa, obb = (long long)yb * W + xb;
 #pragma unroll 4
   for (int c = c0; c < c1; ++c, s += HW, dst += HW)
-    *dst = (w00 * __ldg(s + oaa) + w01 * __ldg(s + oab)) + (w10 * __ldg(s + oba) + w11 * __ldg(s + obb));
+    *dst = (g.w00 * __ldg(s + g.oaa) + g.w01 * __ldg(s + g.oab)) + (g.w10 * __ldg(s + g.oba) + g.w11 * __ldg(s + g.obb));
 }
 
 // dx (pre-zeroed) += scatter of dout*mask through the bilinear taps; dflow = d(sample)/d(position).

@@ -34,8 +34,11 @@ def _rebind(modname, attr, value):
     setattr(mod, attr, value)
 
 
-def install(patch_warp=True, patch_upsample=True):
-    """Returns the list of (module, attribute) pairs that were rebound."""
+def install(patch_warp=True, patch_upsample=True, fuse_warp=True):
+    """Returns the list of (module, attribute) pairs that were rebound.
+
+    fuse_warp: the PWC decoder's ``warp`` (whose only consumer is the correlation sampler, ezflow/decoder/pyramid.py:138-141)
+    returns a ``WarpedFeatures`` handle, so the sampler evaluates the warp inside its own kernel."""
     ez_sim = importlib.import_module("ezflow.similarity")
     reg = ez_sim.SIMILARITY_REGISTRY
     for name in _REGISTRY_NAMES:
@@ -54,7 +57,7 @@ def install(patch_warp=True, patch_upsample=True):
     _rebind("ezflow.decoder.pyramid", "SpatialCorrelationSampler", S.IterSpatialCorrelationSampler)
     _rebind("ezflow.similarity.learnable_cost", "SpatialCorrelationSampler", S.IterSpatialCorrelationSampler)
     if patch_warp:
-        _rebind("ezflow.decoder.pyramid", "warp", U.warp)
+        _rebind("ezflow.decoder.pyramid", "warp", S.lazy_warp if fuse_warp else U.warp)
         _rebind("ezflow.utils.warp", "warp", U.warp)
         _rebind("ezflow.utils", "warp", U.warp)
     if patch_upsample:
@@ -62,6 +65,28 @@ def install(patch_warp=True, patch_upsample=True):
         for modname in ("ezflow.utils.resampling", "ezflow.utils", "ezflow.models.raft", "ezflow.decoder.dilated_flow_stack_filter"):
             _rebind(modname, "convex_upsample_flow", U.convex_upsample_flow)
     return [k for k in _saved if k[0] != "<registry>"]
+
+
+def fuse_model(model):
+    """Post-build surgery: wherever a B200 correlation sampler is directly followed by a LeakyReLU — FlowNetC
+    (``corr_activation``, ezflow/models/flownet_c.py:42,86-90) and the PWC decoder (``leaky_relu``,
+    ezflow/decoder/pyramid.py:49,98-102), neither of which uses that activation anywhere else — the activation is folded into
+    the sampler's epilogue and replaced by ``nn.Identity``.  Returns the number of samplers fused."""
+    import torch.nn as nn
+
+    fused = 0
+    for m in model.modules():
+        corr = getattr(m, "correlation_layer", None)
+        if not isinstance(corr, S.IterSpatialCorrelationSampler) or corr.fused_negative_slope is not None:
+            continue
+        for attr in ("leaky_relu", "corr_activation"):
+            act = getattr(m, attr, None)
+            if isinstance(act, nn.LeakyReLU) and act.negative_slope > 0:
+                corr.fused_negative_slope = float(act.negative_slope)
+                setattr(m, attr, nn.Identity())
+                fused += 1
+                break
+    return fused
 
 
 def uninstall():

@@ -2,7 +2,14 @@ from ..registry import SIMILARITY_REGISTRY, build_similarity
 from .layer import CorrelationLayer
 from .matryoshka import MatryoshkaDilatedCostVolume, MatryoshkaDilatedCostVolumeList
 from .pairwise import MutliScalePairwise4DCorr, get_pyramid_dtype, set_pyramid_dtype
-from .sampler import IterSpatialCorrelationSampler, get_local_corr_mode, iter_spatial_correlation_sample, set_local_corr_mode
+from .sampler import (
+    IterSpatialCorrelationSampler,
+    WarpedFeatures,
+    get_local_corr_mode,
+    iter_spatial_correlation_sample,
+    lazy_warp,
+    set_local_corr_mode,
+)
 
 __all__ = [
     "SIMILARITY_REGISTRY",
@@ -17,4 +24,6 @@ __all__ = [
     "get_pyramid_dtype",
     "set_local_corr_mode",
     "get_local_corr_mode",
+    "WarpedFeatures",
+    "lazy_warp",
 ]

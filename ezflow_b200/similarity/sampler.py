@@ -53,20 +53,29 @@ def local_corr_workspace(BG, C, H, W, device, padding=(0, 0)):
     return torch.empty(n.value, dtype=torch.uint8, device=device), n.value
 
 
-def local_corr_forward(in1, in2, patch, stride, padding, dpatch, scale=1.0, slope=1.0, out=None, out_batch_stride=0):
+TC_MAX_CHANNELS = 256  # per group; above it (or in 'exact' mode) the fp32 CUDA-core kernel runs
+
+
+def warp_fusable(C):
+    """True when ``corr(in1, warp(in2, flow))`` can run as one fused pass (tensor-core path only)."""
+    return _LOCAL_CORR_MODE == "tc" and C <= TC_MAX_CHANNELS
+
+
+def local_corr_forward(in1, in2, patch, stride, padding, dpatch, scale=1.0, slope=1.0, out=None, out_batch_stride=0, flow2=None):
+    """out = act(scale * corr(in1, in2)); with ``flow2`` (B,2,H,W) the targets are warp(in2, flow2), evaluated on the fly."""
     B, C, H, W = in1.shape
     oh, ow = _out_hw(H, W, stride, padding)
     if out is None:
         out = torch.empty((B, patch[0], patch[1], oh, ow), dtype=torch.float32, device=in1.device)
+    lib = _cabi.lib()
     with torch.cuda.device(in1.device):
         ws, nws = local_corr_workspace(B, C, H, W, in1.device, padding)
-        _cabi.check(
-            _cabi.lib().ezb_local_corr_fwd(
-                _cabi.ptr(in1), _cabi.ptr(in2), B, C, H, W, patch[0], patch[1], stride[0], stride[1], padding[0], padding[1],
-                dpatch[0], dpatch[1], float(scale), float(slope), _cabi.ptr(out), int(out_batch_stride),
-                _cabi.ptr(ws), nws, _cabi.stream_ptr(in1.device),
-            )
-        )
+        geom = (B, C, H, W, patch[0], patch[1], stride[0], stride[1], padding[0], padding[1], dpatch[0], dpatch[1])
+        tail = (float(scale), float(slope), _cabi.ptr(out), int(out_batch_stride), _cabi.ptr(ws), nws, _cabi.stream_ptr(in1.device))
+        if flow2 is not None:
+            _cabi.check(lib.ezb_warp_local_corr_fwd(_cabi.ptr(in1), _cabi.ptr(in2), _cabi.ptr(flow2), *geom, *tail))
+        else:
+            _cabi.check(lib.ezb_local_corr_fwd(_cabi.ptr(in1), _cabi.ptr(in2), *geom, *tail))
     return out
 
 
@@ -102,6 +111,71 @@ class _LocalCorrFn(torch.autograd.Function):
         return d1, d2, None, None, None, None, None
 
 
+class _FusedLocalCorrFn(torch.autograd.Function):
+    """act(scale * corr(in1, warp(in2, flow))) with the warp (optional) and the LeakyReLU folded into the forward kernel.
+    The backward chains the existing adjoints: activation mask -> K4b -> warp backward (the warped tensor is
+    re-materialised there; the forward never writes it)."""
+
+    @staticmethod
+    def forward(ctx, in1, in2, flow, patch, stride, padding, dpatch, scale, slope):
+        ctx.cfg = (patch, stride, padding, dpatch, scale, slope)
+        out = local_corr_forward(in1, in2, patch, stride, padding, dpatch, scale, slope, flow2=flow)
+        ctx.has_flow = flow is not None
+        saved = [in1, in2] + ([flow] if ctx.has_flow else []) + ([out] if slope != 1.0 else [])
+        ctx.save_for_backward(*saved)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from ..utils import _warp_backward, _warp_forward
+
+        patch, stride, padding, dpatch, scale, slope = ctx.cfg
+        saved = list(ctx.saved_tensors)
+        in1, in2 = saved[0], saved[1]
+        flow = saved[2] if ctx.has_flow else None
+        dout = dout.contiguous().float()
+        if slope != 1.0:  # slope > 0, so the sign of the activated output is the sign of the pre-activation
+            out = saved[-1]
+            dout = torch.where(out > 0, dout, dout * slope)
+        need1, need2, needf = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_flow and ctx.needs_input_grad[2]
+        tgt = _warp_forward(in2, flow) if ctx.has_flow else in2
+        d1, dt = local_corr_backward(in1, tgt, dout, patch, stride, padding, dpatch, scale, need1, need2 or needf)
+        d2, dflow = dt, None
+        if ctx.has_flow and dt is not None:
+            d2, dflow = _warp_backward(in2, flow, dt, need2, needf)
+        return d1, d2, dflow, None, None, None, None, None, None
+
+
+class WarpedFeatures:
+    """Deferred ``warp(x, flow)`` (reference ezflow/utils/warp.py:5-42).  The PWC-Net decoder warps features2 only to hand
+    them to the correlation sampler (reference ezflow/decoder/pyramid.py:138-141); passing this handle as ``input2`` lets the
+    sampler evaluate the warp inside its operand conversion.  ``materialize()`` gives the ordinary warped tensor."""
+
+    def __init__(self, x, flow):
+        self.x = _cabi.require_cuda_f32(x, "x")
+        self.flow = _cabi.require_cuda_f32(flow, "flow")
+        f, a = self.flow, self.x
+        if a.dim() != 4 or f.dim() != 4 or f.shape[1] != 2 or f.shape[0] != a.shape[0] or f.shape[2:] != a.shape[2:]:
+            raise ValueError(f"warp expects x (B,C,H,W) and flow (B,2,H,W); got {tuple(x.shape)} and {tuple(flow.shape)}")
+
+    shape = property(lambda self: self.x.shape)
+    device = property(lambda self: self.x.device)
+    dtype = property(lambda self: self.x.dtype)
+
+    def dim(self):
+        return self.x.dim()
+
+    def materialize(self):
+        from ..utils import warp
+
+        return warp(self.x, self.flow)
+
+
+def lazy_warp(x, flow):
+    """Same signature as ``warp``; returns a ``WarpedFeatures`` handle for the sampler to consume."""
+    return WarpedFeatures(x, flow)
+
+
 def _validate(kernel_size, patch_size, dilation):
     # same checks, same messages as sampler.py:89-94
     if kernel_size[0] != 1 or kernel_size[1] != 1:
@@ -122,18 +196,37 @@ def iter_spatial_correlation_sample(
     dilation: IntOrPair = 1,
     dilation_patch: IntOrPair = 1,
     _scale: float = 1.0,
+    _negative_slope: float = None,
 ) -> torch.Tensor:
-    """Spatial correlation sampling from input1 to input2 (one fused CUDA kernel instead of P^2 slices)."""
+    """Spatial correlation sampling from input1 to input2 (one fused CUDA kernel instead of P^2 slices).
+
+    Extensions over the reference (both optional): ``input2`` may be a ``WarpedFeatures`` handle (the warp is fused
+    into the kernel's operand conversion) and ``_negative_slope`` folds a following LeakyReLU into the epilogue."""
     kernel_size, patch_size, stride = _pair(kernel_size), _pair(patch_size), _pair(stride)
     padding, dilation, dilation_patch = _pair(padding), _pair(dilation), _pair(dilation_patch)
     _validate(kernel_size, patch_size, dilation)
     a = _cabi.require_cuda_f32(input1, "input1")
-    b = _cabi.require_cuda_f32(input2, "input2")
+    flow = None
+    if isinstance(input2, WarpedFeatures):
+        if warp_fusable(a.shape[1] if a.dim() == 4 else 0):
+            b, flow = input2.x, input2.flow
+        else:
+            b = input2.materialize()
+    else:
+        b = _cabi.require_cuda_f32(input2, "input2")
     if a.dim() != 4 or a.shape != b.shape:
         raise ValueError(f"input1/input2 must both be (B,C,H,W); got {tuple(input1.shape)} and {tuple(input2.shape)}")
-    if torch.is_grad_enabled() and (a.requires_grad or b.requires_grad):
-        return _LocalCorrFn.apply(a, b, patch_size, stride, padding, dilation_patch, _scale)
-    return local_corr_forward(a, b, patch_size, stride, padding, dilation_patch, _scale)
+    slope = 1.0 if _negative_slope is None else float(_negative_slope)
+    if slope <= 0.0:
+        raise ValueError("a fused LeakyReLU needs a positive negative_slope")
+    needs_grad = torch.is_grad_enabled() and (a.requires_grad or b.requires_grad or (flow is not None and flow.requires_grad))
+    if flow is None and slope == 1.0:
+        if needs_grad:
+            return _LocalCorrFn.apply(a, b, patch_size, stride, padding, dilation_patch, _scale)
+        return local_corr_forward(a, b, patch_size, stride, padding, dilation_patch, _scale)
+    if needs_grad:
+        return _FusedLocalCorrFn.apply(a, b, flow, patch_size, stride, padding, dilation_patch, _scale, slope)
+    return local_corr_forward(a, b, patch_size, stride, padding, dilation_patch, _scale, slope, flow2=flow)
 
 
 @SIMILARITY_REGISTRY.register()
@@ -164,6 +257,8 @@ class IterSpatialCorrelationSampler(nn.Module):
         self.padding = padding
         self.dilation = dilation
         self.dilation_patch = dilation_patch
+        # set by ezflow_b200.fuse_model(): slope of the LeakyReLU that followed this sampler, now applied in its epilogue
+        self.fused_negative_slope = None
 
     @classmethod
     def from_config(cls, cfg):
@@ -186,4 +281,5 @@ class IterSpatialCorrelationSampler(nn.Module):
             padding=self.padding,
             dilation=self.dilation,
             dilation_patch=self.dilation_patch,
+            _negative_slope=self.fused_negative_slope,
         )

@@ -20,18 +20,23 @@ class _WarpFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         x, flow = ctx.saved_tensors
-        B, C, H, W = x.shape
-        dout = dout.contiguous().float()
-        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        dflow = torch.empty_like(flow) if ctx.needs_input_grad[1] else None
-        with torch.cuda.device(x.device):
-            _cabi.check(
-                _cabi.lib().ezb_warp_bwd(
-                    _cabi.ptr(x), _cabi.ptr(flow), _cabi.ptr(dout), B, C, H, W, _cabi.ptr(dx), _cabi.ptr(dflow),
-                    _cabi.stream_ptr(x.device),
-                )
+        return _warp_backward(x, flow, dout.contiguous().float(), ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+
+
+def _warp_backward(x, flow, dout, need_x=True, need_flow=True):
+    B, C, H, W = x.shape
+    dx = torch.empty_like(x) if need_x else None
+    dflow = torch.empty_like(flow) if need_flow else None
+    if dx is None and dflow is None:
+        return None, None
+    with torch.cuda.device(x.device):
+        _cabi.check(
+            _cabi.lib().ezb_warp_bwd(
+                _cabi.ptr(x), _cabi.ptr(flow), _cabi.ptr(dout), B, C, H, W, _cabi.ptr(dx), _cabi.ptr(dflow),
+                _cabi.stream_ptr(x.device),
             )
-        return dx, dflow
+        )
+    return dx, dflow
 
 
 def _warp_forward(x, flow):

@@ -143,6 +143,16 @@ int ezb_local_corr_fwd(const float* in1, const float* in2, int B, int C, int H, 
                        float scale, float slope, float* out, int64_t out_batch_stride,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* Warp-fused forward (section 8f-2): out = act(scale * corr(in1, warp(in2, flow))) where warp is ezb_warp_fwd's
+ * (ezflow/utils/warp.py:5-42) — PWC-Net's decoder warps features2 by the up-sampled flow right before every
+ * correlation (ezflow/decoder/pyramid.py:138-141) and applies LeakyReLU(0.1) right after it (:98-102).  The warp is
+ * evaluated while the target operand is converted to fp16, so the warped tensor never exists in HBM.  Tensor-core
+ * path only: EZB_ERR_UNSUPPORTED when workspace == NULL or C > 256 (callers then run the two kernels). */
+int ezb_warp_local_corr_fwd(const float* in1, const float* in2, const float* flow /* (B,2,H,W) */, int B, int C, int H, int W,
+                            int Ph, int Pw, int sh, int sw, int padh, int padw, int dph, int dpw,
+                            float scale, float slope, float* out, int64_t out_batch_stride,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
 int ezb_local_corr_bwd(const float* in1, const float* in2, const float* dout, int B, int C, int H, int W,
                        int Ph, int Pw, int sh, int sw, int padh, int padw, int dph, int dpw,
                        float scale, int64_t dout_batch_stride,

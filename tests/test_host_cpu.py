@@ -111,6 +111,13 @@ def test_install_into_reference_and_yaml_models():
         assert (fnc.correlation_layer.patch_size, fnc.correlation_layer.dilation_patch) == (21, 2)
         pwc = build_model("PWCNet", cfg_path=refshim.reference_config_path("pwcnet.yaml"), custom_cfg=True)
         assert isinstance(pwc.decoder.correlation_layer, E.IterSpatialCorrelationSampler)
+        # fusions of the sampler's neighbours: lazy warp in the PWC decoder, LeakyReLU folded into the sampler
+        import ezflow.decoder.pyramid as ref_pyramid
+
+        assert ref_pyramid.warp is E.lazy_warp
+        assert E.fuse_model(pwc) == 1 and isinstance(pwc.decoder.leaky_relu, torch.nn.Identity)
+        assert pwc.decoder.correlation_layer.fused_negative_slope == pytest.approx(0.1)
+        assert E.fuse_model(fnc) == 1 and isinstance(fnc.corr_activation, torch.nn.Identity)
         dcv = build_model("DCVNet", cfg_path=refshim.reference_config_path("dcvnet.yaml"), custom_cfg=True)
         assert isinstance(dcv.cost_volume_list, E.MatryoshkaDilatedCostVolumeList)
         ref_keys = {k for k in dcv.state_dict() if "offsets" in k}

@@ -66,6 +66,24 @@ def cfg3():
         nbw = nb + sum(2 * a.numel() * 4 + f.numel() * 4 for a, _, f in xs[1:])
         report("cfg3 PWC 5-level warp+corr B8", timed(lambda: run(True)), nbw, fl)
 
+        # the decoder step as the reference runs it (pyramid.py:98-102,138-141): warp -> corr -> view -> LeakyReLU(0.1)
+        def unfused():
+            for i, (a, b, f) in enumerate(xs):
+                c = m(a, E.warp(b, f) if i > 0 else b)
+                torch.nn.functional.leaky_relu(c.view(c.shape[0], -1, c.shape[3], c.shape[4]), 0.1)
+
+        mf = E.IterSpatialCorrelationSampler(kernel_size=1, patch_size=9, padding=0)
+        mf.fused_negative_slope = 0.1
+
+        def fused():
+            for i, (a, b, f) in enumerate(xs):
+                c = mf(a, E.lazy_warp(b, f) if i > 0 else b)
+                c.view(c.shape[0], -1, c.shape[3], c.shape[4])
+
+        nbf = nb + sum(f.numel() * 4 for _, _, f in xs[1:])  # fused: the warped tensor is never written or re-read
+        report("cfg3 PWC warp+corr+LeakyReLU B8, separate kernels", timed(unfused), nbw + 2 * (nb - sum(2 * a.numel() * 4 for a, _, _ in xs)), fl)
+        report("cfg3 PWC warp+corr+LeakyReLU B8, fused (lazy_warp + fuse_model)", timed(fused), nbf, fl)
+
 
 def cfg4():
     xa = [torch.randn(4, 128, 192, 384, device=dev), torch.randn(4, 256, 48, 96, device=dev)]
