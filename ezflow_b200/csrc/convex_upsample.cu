@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(NTHREADS, C <= 2 ? 4 : 2) convex_upsample_fwd_
 //   dnb[c][k] (h, w) = sum_{i,j} p_k * dout_c           -> part[n][c][k][h][w]   (deterministic block-level reduction)
 // and a second pass gathers dflow[c][y][x] = sum_k part[c][k][y - ky + 1][x - kx + 1].
 template <int C, int S>
-__global__ void __launch_bounds__(NTHREADS) convex_upsample_bwd_kernel(const float* __restrict__ flow,
+__global__ void __launch_bounds__(NTHREADS, C <= 2 ? 3 : 1) convex_upsample_bwd_kernel(const float* __restrict__ flow,
                                                                        const float* __restrict__ logits,
                                                                        const float* __restrict__ dout, float* __restrict__ dlogits,
                                                                        float* __restrict__ part, int N, int H, int W, int s_rt,
