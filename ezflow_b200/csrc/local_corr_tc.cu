@@ -58,12 +58,15 @@ struct Geo {
   static constexpr int SMEM_S = SMEM_B + STAGES * B_STAGE_BYTES;
   static constexpr int SMEM_BAR = SMEM_S + BM * S_STRIDE * 4;
   static constexpr int SMEM_BYTES = SMEM_BAR + 256 + 1024;
-  static_assert(CPW % 8 == 0 && CPW <= 56 && BN % 16 == 0 && SMEM_BYTES <= 232448 && (2 * STAGES + 2 + 2 * NACC) * 8 + 4 <= 256, "tile geometry");
+  static_assert(CPW % 8 == 0 && CPW <= 56 && BN % 16 == 0 && SMEM_BYTES <= 232448 && (2 * STAGES + 4 + 2 * NACC) * 8 + 4 <= 256, "tile geometry");
 };
 
 struct Params {
   int G, H, W, oh, ow, Ph, Pw, sh, sw, padh, padw, D, KB;
-  int nsplit;  // CTAs sharing one query tile (each sweeps a slice of its target tiles): balances the last wave
+  int nsplit;  // work items sharing one query tile (each sweeps a slice of its target tiles): balances the load
+  // Persistent CTAs: work item = (query tile x, query tile y, z = (bg * lat^2 + class) * nsplit + split), item index
+  // x-fastest; CTA c takes items c, c + gridDim.x, ...
+  int qtx, qty, n_items;
   // Lattice mode (lat > 1; one dilation = lat, stride 1, no padding): queries and targets with the same residues
   // (cy, cx) mod lat only ever meet each other, so every residue class is an independent dilation-1 problem on the
   // sub-lattice  pixel = (cy, cx) + lat * (y, x);  H, W, oh, ow, dph, dpw below are then in lattice units of class (0,0).
@@ -152,13 +155,12 @@ __global__ void __launch_bounds__(256) warp_convert_kmajor_kernel(const float* _
     const float* fl = flow + (long long)(bg / G) * 2 * N;
     const int py = n / W, px = n - py * W;
     const k5::Taps t = k5::make_taps(__ldg(fl + n), __ldg(fl + N + n), px, py, H, W);
-    k5::Gather g = k5::make_gather(t, W);
-    if (g.zero) g.w00 = g.w01 = g.w10 = g.w11 = 0.f;
+    const k5::Gather g = k5::make_gather(t, W);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int c = c0 + warp * 8 + i;
       float v = 0.f;
-      if (c < C) {
+      if (c < C && !g.zero) {  // mask == 0 (e.g. every tap outside the image: the clamped addresses are not valid then)
         const float* sp = src + (long long)c * N;
         v = ((g.w00 * __ldg(sp + g.oaa) + g.w01 * __ldg(sp + g.oab)) + (g.w10 * __ldg(sp + g.oba) + g.w11 * __ldg(sp + g.obb))) * sc;
       }
@@ -195,36 +197,56 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   float* S = reinterpret_cast<float*>(base_ptr + SMEM_S);
   auto full_bar = [&](int s) { return sBar + 8u * s; };
   auto empty_bar = [&](int s) { return sBar + 8u * (STAGES + s); };
-  const uint32_t a_full = sBar + 8u * (2 * STAGES);
-  auto tmem_full = [&](int a) { return sBar + 8u * (2 * STAGES + 1 + a); };
-  auto tmem_empty = [&](int a) { return sBar + 8u * (2 * STAGES + 1 + NACC + a); };
-  volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + SMEM_BAR + 8 * (2 * STAGES + 1 + 2 * NACC));
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qx0 = blockIdx.x * QTW, qy0 = blockIdx.y * QTH;
-  const int zq = blockIdx.z / P.nsplit, split = blockIdx.z - zq * P.nsplit;  // zq = bg * lat^2 + class
-  const int ncls = P.lat * P.lat, bg = zq / ncls, cls = zq - bg * ncls;
-  const int cy = cls / P.lat, cx = cls - cy * P.lat;
-  // image / output size in the units the tiles are laid out in (lattice mode: the lattice of this residue class)
-  const int H_ = P.lat > 1 ? (P.Hf - cy + P.lat - 1) / P.lat : P.H, W_ = P.lat > 1 ? (P.Wf - cx + P.lat - 1) / P.lat : P.W;
-  const int oh_ = P.lat > 1 ? H_ : P.oh, ow_ = P.lat > 1 ? W_ : P.ow;
-  if (qy0 >= oh_ || qx0 >= ow_) return;  // (lattice mode) this class is smaller than class (0,0): nothing here
+  // the query operand is double-buffered when it takes at most half of its shared-memory area (C <= 128)
+  const int na = P.KB <= KB_MAX / 2 ? 2 : 1;
+  auto a_full = [&](int s) { return sBar + 8u * (2 * STAGES + s); };
+  auto a_empty = [&](int s) { return sBar + 8u * (2 * STAGES + 2 + s); };
+  auto tmem_full = [&](int a) { return sBar + 8u * (2 * STAGES + 4 + a); };
+  auto tmem_empty = [&](int a) { return sBar + 8u * (2 * STAGES + 4 + NACC + a); };
+  volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + SMEM_BAR + 8 * (2 * STAGES + 4 + 2 * NACC));
 
-  // bounding box (in2 pixel coordinates, clipped to the image) of every target any query of this tile needs
   int mdh_max = 0, mdw_max = 0;
   for (int d = 0; d < P.D; ++d) {
     mdh_max = max(mdh_max, P.dph[d] * (P.Ph - 1) / 2);
     mdw_max = max(mdw_max, P.dpw[d] * (P.Pw - 1) / 2);
   }
-  const int y_lo = max(0, qy0 * P.sh - P.padh - mdh_max);
-  const int y_hi = min(H_ - 1, (min(qy0 + QTH, oh_) - 1) * P.sh - P.padh + mdh_max);
-  const int x_lo = max(0, qx0 * P.sw - P.padw - mdw_max);
-  const int x_hi = min(W_ - 1, (min(qx0 + QTW, ow_) - 1) * P.sw - P.padw + mdw_max);
-  const int nty = y_hi >= y_lo ? (y_hi - y_lo) / TTH + 1 : 0;
-  const int ntx = x_hi >= x_lo ? (x_hi - x_lo) / TTW + 1 : 0;
-  const int ntiles_all = nty * ntx;
-  const int tt_begin = ntiles_all * split / P.nsplit, tt_end = ntiles_all * (split + 1) / P.nsplit;
-  const int ntiles = tt_end - tt_begin;  // this CTA sweeps target tiles [tt_begin, tt_end)
+  const int ncls = P.lat * P.lat;
+
+  // geometry of a work item (every role walks the same item sequence and derives the same numbers)
+  struct Item {
+    int qx0, qy0, zq, split, bg, cy, cx, H_, W_, oh_, ow_, y_lo, x_lo, ntx, tt_begin, ntiles;
+    bool valid;
+  };
+  auto item_geometry = [&](int item) {
+    Item it;
+    const int bx = item % P.qtx, rest = item / P.qtx, by = rest % P.qty, bz = rest / P.qty;
+    it.qx0 = bx * QTW;
+    it.qy0 = by * QTH;
+    it.zq = bz / P.nsplit;  // bg * lat^2 + class
+    it.split = bz - it.zq * P.nsplit;
+    it.bg = it.zq / ncls;
+    const int cls = it.zq - it.bg * ncls;
+    it.cy = cls / P.lat;
+    it.cx = cls - it.cy * P.lat;
+    // image / output size in the units the tiles are laid out in (lattice mode: the lattice of this residue class)
+    it.H_ = P.lat > 1 ? (P.Hf - it.cy + P.lat - 1) / P.lat : P.H;
+    it.W_ = P.lat > 1 ? (P.Wf - it.cx + P.lat - 1) / P.lat : P.W;
+    it.oh_ = P.lat > 1 ? it.H_ : P.oh;
+    it.ow_ = P.lat > 1 ? it.W_ : P.ow;
+    it.valid = it.qy0 < it.oh_ && it.qx0 < it.ow_;  // (lattice mode) a class smaller than class (0,0) has fewer tiles
+    // bounding box (in2 pixel coordinates, clipped to the image) of every target any query of this tile needs
+    it.y_lo = max(0, it.qy0 * P.sh - P.padh - mdh_max);
+    const int y_hi = min(it.H_ - 1, (min(it.qy0 + QTH, it.oh_) - 1) * P.sh - P.padh + mdh_max);
+    it.x_lo = max(0, it.qx0 * P.sw - P.padw - mdw_max);
+    const int x_hi = min(it.W_ - 1, (min(it.qx0 + QTW, it.ow_) - 1) * P.sw - P.padw + mdw_max);
+    const int nty = y_hi >= it.y_lo ? (y_hi - it.y_lo) / TTH + 1 : 0;
+    it.ntx = x_hi >= it.x_lo ? (x_hi - it.x_lo) / TTW + 1 : 0;
+    const int ntiles_all = it.valid ? nty * it.ntx : 0;
+    it.tt_begin = ntiles_all * it.split / P.nsplit;
+    it.ntiles = ntiles_all * (it.split + 1) / P.nsplit - it.tt_begin;  // this item sweeps target tiles [tt_begin, tt_begin + ntiles)
+    return it;
+  };
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -235,7 +257,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       ptx::mbar_init(full_bar(s), 1);
       ptx::mbar_init(empty_bar(s), 1);
     }
-    ptx::mbar_init(a_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(a_full(s), 1);
+      ptx::mbar_init(a_empty(s), 1);
+    }
     for (int a = 0; a < NACC; ++a) {
       ptx::mbar_init(tmem_full(a), 1);
       ptx::mbar_init(tmem_empty(a), EPI_WARPS);  // one arrive per epilogue warp
@@ -250,50 +275,68 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_slot;
+  const uint32_t a_slot_bytes = (uint32_t)(KB_MAX / 2) * A_KB_BYTES;
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
-    if (ntiles > 0) {
-      ptx::mbar_expect_tx(a_full, (uint32_t)(P.KB * A_KB_BYTES));
-      for (int kb = 0; kb < P.KB; ++kb)
-        ptx::tma_load_4d_hint(sA + kb * A_KB_BYTES, &tmA, a_full, kb * BK, qx0, qy0, zq, ptx::kEvictFirst);  // (oy, ox) space
-    }
     uint32_t stage = 0, phase = 0;
-    for (int tt = 0; tt < ntiles; ++tt) {
-      const int ty0 = y_lo + ((tt_begin + tt) / ntx) * TTH, tx0 = x_lo + ((tt_begin + tt) % ntx) * TTW;
-      for (int kb = 0; kb < P.KB; ++kb) {
-        ptx::mbar_wait(empty_bar(stage), phase ^ 1);
-        ptx::mbar_expect_tx(full_bar(stage), B_STAGE_BYTES);
-        // in2 windows of neighbouring query tiles overlap heavily: keep them in L2
-        ptx::tma_load_4d_hint(sB + stage * B_STAGE_BYTES, &tmB, full_bar(stage), kb * BK, cx + P.lat * tx0, cy + P.lat * ty0, bg,
-                              ptx::kEvictLast);  // lattice -> pixel coordinates
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    int acount = 0;  // items with a query operand so far
+    for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+      const Item it = item_geometry(item);
+      if (it.ntiles <= 0) continue;
+      {
+        const int slot = acount % na;
+        const uint32_t aph = (uint32_t)(acount / na) & 1u;
+        ++acount;
+        ptx::mbar_wait(a_empty(slot), aph ^ 1);  // the MMAs of the item that used this slot before have completed
+        ptx::mbar_expect_tx(a_full(slot), (uint32_t)(P.KB * A_KB_BYTES));
+        for (int kb = 0; kb < P.KB; ++kb)
+          ptx::tma_load_4d_hint(sA + slot * a_slot_bytes + kb * A_KB_BYTES, &tmA, a_full(slot), kb * BK, it.qx0, it.qy0, it.zq,
+                                ptx::kEvictFirst);  // (oy, ox) space
+      }
+      for (int tt = 0; tt < it.ntiles; ++tt) {
+        const int ty0 = it.y_lo + ((it.tt_begin + tt) / it.ntx) * TTH, tx0 = it.x_lo + ((it.tt_begin + tt) % it.ntx) * TTW;
+        for (int kb = 0; kb < P.KB; ++kb) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+          ptx::mbar_expect_tx(full_bar(stage), B_STAGE_BYTES);
+          // in2 windows of neighbouring query tiles overlap heavily: keep them in L2
+          ptx::tma_load_4d_hint(sB + stage * B_STAGE_BYTES, &tmB, full_bar(stage), kb * BK, it.cx + P.lat * tx0, it.cy + P.lat * ty0,
+                                it.bg, ptx::kEvictLast);  // lattice -> pixel coordinates
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = ptx::umma_idesc(/*f16*/ 0, BM, BN);
     uint32_t stage = 0, phase = 0;
-    if (ntiles > 0) {
-      ptx::mbar_wait(a_full, 0);
+    int acount = 0, tcount = 0;  // running counts of query operands / target tiles (accumulators rotate across items)
+    for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+      const Item it = item_geometry(item);
+      if (it.ntiles <= 0) continue;
+      const int slot = acount % na;
+      const uint32_t aph = (uint32_t)(acount / na) & 1u;
+      ++acount;
+      ptx::mbar_wait(a_full(slot), aph);
       ptx::tc_fence_after();
-    }
-    for (int tt = 0; tt < ntiles; ++tt) {
-      const uint32_t acc = tt % NACC, aphase = (tt / NACC) & 1;
-      ptx::mbar_wait(tmem_empty(acc), aphase ^ 1);
-      ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
-      for (int kb = 0; kb < P.KB; ++kb) {
-        ptx::mbar_wait(full_bar(stage), phase);
+      for (int tt = 0; tt < it.ntiles; ++tt, ++tcount) {
+        const uint32_t acc = tcount % NACC, aphase = (tcount / NACC) & 1;
+        ptx::mbar_wait(tmem_empty(acc), aphase ^ 1);
         ptx::tc_fence_after();
-        const uint64_t a_desc = ptx::umma_desc_kmajor_sw128(sA + kb * A_KB_BYTES);
-        const uint64_t b_desc = ptx::umma_desc_kmajor_sw128(sB + stage * B_STAGE_BYTES);
+        const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+        for (int kb = 0; kb < P.KB; ++kb) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint64_t a_desc = ptx::umma_desc_kmajor_sw128(sA + slot * a_slot_bytes + kb * A_KB_BYTES);
+          const uint64_t b_desc = ptx::umma_desc_kmajor_sw128(sB + stage * B_STAGE_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) ptx::umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-        ptx::umma_commit(empty_bar(stage));
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          for (int k = 0; k < BK / 16; ++k) ptx::umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          ptx::umma_commit(empty_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(tmem_full(acc));
       }
-      ptx::umma_commit(tmem_full(acc));
+      ptx::umma_commit(a_empty(slot));  // arrives once every MMA that read this query operand is done
     }
   } else if (warp >= 4) {
     // ===================== epilogue: lane = query =====================
@@ -301,108 +344,114 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     // into the queries' shared-memory rows, then they split the (pi, pj-chunk) work items between them.
     const int quad = warp & 3, part = (warp - 4) >> 2;
     const int q = quad * 32 + lane;
-    const int oy = qy0 + q / QTW, ox = qx0 + q % QTW;
-    const bool q_ok = oy < oh_ && ox < ow_;
-    const int b = bg / P.G, g = bg - b * P.G;
-    const float deq = P.scale * dequant_factor(__ldg(P.amax + bg), __ldg(P.amax + P.BG + bg));
     const long long plane = (long long)P.out_h * P.out_w;
-    float* out_q = P.out + (long long)b * P.out_bstride + (long long)(cy + P.lat * oy) * P.out_w + (cx + P.lat * ox);
     float* Srow = S + q * S_STRIDE;
     auto quad_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * EPI_SPLIT) : "memory"); };
+    int tcount = 0;
+    for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+      const Item it = item_geometry(item);
+      if (!it.valid) continue;
+      const int qx0 = it.qx0, qy0 = it.qy0, H_ = it.H_, W_ = it.W_;
+      const int oy = qy0 + q / QTW, ox = qx0 + q % QTW;
+      const bool q_ok = oy < it.oh_ && ox < it.ow_;
+      const int b = it.bg / P.G, g = it.bg - b * P.G;
+      const float deq = P.scale * dequant_factor(__ldg(P.amax + it.bg), __ldg(P.amax + P.BG + it.bg));
+      float* out_q = P.out + (long long)b * P.out_bstride + (long long)(it.cy + P.lat * oy) * P.out_w + (it.cx + P.lat * ox);
 
-    // displacements that point outside the image: zeros (act(0) = 0), written once, up front
-    if (q_ok && split == 0) {
-      for (int d = 0; d < P.D; ++d) {
-        const int dph = P.dph[d], dpw = P.dpw[d];
-        const int y2_0 = oy * P.sh - P.padh - dph * (P.Ph - 1) / 2, x2_0 = ox * P.sw - P.padw - dpw * (P.Pw - 1) / 2;
-        float* o = out_q + (long long)(d * P.G + g) * P.Ph * P.Pw * plane;
-        for (int a = part; a < P.Ph; a += EPI_SPLIT) {
-          const int y2 = y2_0 + a * dph;
-          const bool row_in = y2 >= 0 && y2 < H_;
-          for (int bb = 0; bb < P.Pw; ++bb) {
-            const int x2 = x2_0 + bb * dpw;
-            if (!(row_in && x2 >= 0 && x2 < W_)) o[(long long)(a * P.Pw + bb) * plane] = 0.f;
+      // displacements that point outside the image: zeros (act(0) = 0), written once, up front
+      if (q_ok && it.split == 0) {
+        for (int d = 0; d < P.D; ++d) {
+          const int dph = P.dph[d], dpw = P.dpw[d];
+          const int y2_0 = oy * P.sh - P.padh - dph * (P.Ph - 1) / 2, x2_0 = ox * P.sw - P.padw - dpw * (P.Pw - 1) / 2;
+          float* o = out_q + (long long)(d * P.G + g) * P.Ph * P.Pw * plane;
+          for (int a = part; a < P.Ph; a += EPI_SPLIT) {
+            const int y2 = y2_0 + a * dph;
+            const bool row_in = y2 >= 0 && y2 < H_;
+            for (int bb = 0; bb < P.Pw; ++bb) {
+              const int x2 = x2_0 + bb * dpw;
+              if (!(row_in && x2 >= 0 && x2 < W_)) o[(long long)(a * P.Pw + bb) * plane] = 0.f;
+            }
           }
         }
       }
-    }
 
-    for (int tt = 0; tt < ntiles; ++tt) {
-      const int ty0 = y_lo + ((tt_begin + tt) / ntx) * TTH, tx0 = x_lo + ((tt_begin + tt) % ntx) * TTW;
-      const int ty1 = min(ty0 + TTH, H_) - 1, tx1 = min(tx0 + TTW, W_) - 1;  // last in-image row / column of the tile
-      const uint32_t acc = tt % NACC, aphase = (tt / NACC) & 1;
-      ptx::mbar_wait(tmem_full(acc), aphase);
-      ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quad * 32) << 16) + part * CPW;
-      {
-        // CPW = 32 (+16) (+8) columns of this warp's share
-        constexpr bool k32 = CPW >= 32, k16 = (CPW % 32) >= 16, k8 = (CPW % 16) >= 8;
-        uint32_t r0[32], r1[16], r2[8];
-        if constexpr (k32) ptx::tmem_ld_32x32b_x32(taddr, r0);
-        if constexpr (k16) ptx::tmem_ld_32x32b_x16(taddr + (k32 ? 32 : 0), r1);
-        if constexpr (k8) ptx::tmem_ld_32x32b_x8(taddr + (k32 ? 32 : 0) + (k16 ? 16 : 0), r2);
-        ptx::tmem_ld_wait();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(tmem_empty(acc));  // the accumulator is in registers: release it early
-        float* dst = Srow + part * CPW;
-        if constexpr (k32) {
+      for (int tt = 0; tt < it.ntiles; ++tt, ++tcount) {
+        const int ty0 = it.y_lo + ((it.tt_begin + tt) / it.ntx) * TTH, tx0 = it.x_lo + ((it.tt_begin + tt) % it.ntx) * TTW;
+        const int ty1 = min(ty0 + TTH, H_) - 1, tx1 = min(tx0 + TTW, W_) - 1;  // last in-image row / column of the tile
+        const uint32_t acc = tcount % NACC, aphase = (tcount / NACC) & 1;
+        ptx::mbar_wait(tmem_full(acc), aphase);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quad * 32) << 16) + part * CPW;
+        {
+          // CPW = 32 (+16) (+8) columns of this warp's share
+          constexpr bool k32 = CPW >= 32, k16 = (CPW % 32) >= 16, k8 = (CPW % 16) >= 8;
+          uint32_t r0[32], r1[16], r2[8];
+          if constexpr (k32) ptx::tmem_ld_32x32b_x32(taddr, r0);
+          if constexpr (k16) ptx::tmem_ld_32x32b_x16(taddr + (k32 ? 32 : 0), r1);
+          if constexpr (k8) ptx::tmem_ld_32x32b_x8(taddr + (k32 ? 32 : 0) + (k16 ? 16 : 0), r2);
+          ptx::tmem_ld_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(tmem_empty(acc));  // the accumulator is in registers: release it early
+          float* dst = Srow + part * CPW;
+          if constexpr (k32) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) dst[j] = __uint_as_float(r0[j]);
-        }
-        if constexpr (k16) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) dst[(k32 ? 32 : 0) + j] = __uint_as_float(r1[j]);
-        }
-        if constexpr (k8) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) dst[(k32 ? 32 : 0) + (k16 ? 16 : 0) + j] = __uint_as_float(r2[j]);
-        }
-      }
-      quad_sync();  // all column shares of the rows are in shared memory
-
-      for (int d = 0; d < P.D; ++d) {
-        const int dph = P.dph[d], dpw = P.dpw[d];
-        {  // CTA-uniform early out: this dilation's box around the query tile does not reach the target tile
-          const int mh = dph * (P.Ph - 1) / 2, mw = dpw * (P.Pw - 1) / 2;
-          if (ty1 < qy0 * P.sh - P.padh - mh || ty0 > (qy0 + QTH - 1) * P.sh - P.padh + mh ||
-              tx1 < qx0 * P.sw - P.padw - mw || tx0 > (qx0 + QTW - 1) * P.sw - P.padw + mw)
-            continue;
-        }
-        const int y2_0 = oy * P.sh - P.padh - dph * (P.Ph - 1) / 2, x2_0 = ox * P.sw - P.padw - dpw * (P.Pw - 1) / 2;
-        // this lane's displacement ranges whose target lies in the in-image part of the tile
-        const float inv_dph = __frcp_rn((float)dph), inv_dpw = __frcp_rn((float)dpw);
-        int a_lo = max(0, ceil_div(ty0 - y2_0, inv_dph)), a_hi = min(P.Ph - 1, floor_div(ty1 - y2_0, inv_dph));
-        int b_lo = max(0, ceil_div(tx0 - x2_0, inv_dpw)), b_hi = min(P.Pw - 1, floor_div(tx1 - x2_0, inv_dpw));
-        if (!q_ok || a_lo > a_hi || b_lo > b_hi) { a_lo = b_lo = INT_MAX; a_hi = b_hi = INT_MIN; }
-        // all lanes walk the union so that a store instruction covers one (pi, pj): contiguous output pixels
-        const int ua_lo = __reduce_min_sync(0xffffffffu, a_lo), ua_hi = __reduce_max_sync(0xffffffffu, a_hi);
-        const int ub_lo = __reduce_min_sync(0xffffffffu, b_lo), ub_hi = __reduce_max_sync(0xffffffffu, b_hi);
-        if (ua_lo > ua_hi) continue;
-        float* o = out_q + (long long)(d * P.G + g) * P.Ph * P.Pw * plane;
-        // work items = (pi, chunk of 4 pj), dealt round-robin to the warps of the quadrant
-        const int nchunk = (ub_hi - ub_lo) / 4 + 1, nitems = (ua_hi - ua_lo + 1) * nchunk;
-        for (int it = part; it < nitems; it += EPI_SPLIT) {
-          const int ai = it / nchunk, a = ua_lo + ai, bb = ub_lo + (it - ai * nchunk) * 4;
-          const bool row_ok = a >= a_lo && a <= a_hi;
-          const float* srow = Srow + (y2_0 + a * dph - ty0) * TTW + (x2_0 - tx0);
-          float* orow = o + (long long)a * P.Pw * plane;
-          float v[4];
-          bool ok[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {  // 4 independent load -> store chains in flight
-            ok[u] = row_ok && bb + u >= b_lo && bb + u <= b_hi;
-            v[u] = ok[u] ? srow[(bb + u) * dpw] : 0.f;
+            for (int j = 0; j < 32; ++j) dst[j] = __uint_as_float(r0[j]);
           }
+          if constexpr (k16) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            float w = v[u] * deq;
-            w = w >= 0.f ? w : w * P.slope;
-            if (ok[u]) orow[(long long)(bb + u) * plane] = w;
+            for (int j = 0; j < 16; ++j) dst[(k32 ? 32 : 0) + j] = __uint_as_float(r1[j]);
+          }
+          if constexpr (k8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[(k32 ? 32 : 0) + (k16 ? 16 : 0) + j] = __uint_as_float(r2[j]);
           }
         }
+        quad_sync();  // all column shares of the rows are in shared memory
+
+        for (int d = 0; d < P.D; ++d) {
+          const int dph = P.dph[d], dpw = P.dpw[d];
+          {  // CTA-uniform early out: this dilation's box around the query tile does not reach the target tile
+            const int mh = dph * (P.Ph - 1) / 2, mw = dpw * (P.Pw - 1) / 2;
+            if (ty1 < qy0 * P.sh - P.padh - mh || ty0 > (qy0 + QTH - 1) * P.sh - P.padh + mh ||
+                tx1 < qx0 * P.sw - P.padw - mw || tx0 > (qx0 + QTW - 1) * P.sw - P.padw + mw)
+              continue;
+          }
+          const int y2_0 = oy * P.sh - P.padh - dph * (P.Ph - 1) / 2, x2_0 = ox * P.sw - P.padw - dpw * (P.Pw - 1) / 2;
+          // this lane's displacement ranges whose target lies in the in-image part of the tile
+          const float inv_dph = __frcp_rn((float)dph), inv_dpw = __frcp_rn((float)dpw);
+          int a_lo = max(0, ceil_div(ty0 - y2_0, inv_dph)), a_hi = min(P.Ph - 1, floor_div(ty1 - y2_0, inv_dph));
+          int b_lo = max(0, ceil_div(tx0 - x2_0, inv_dpw)), b_hi = min(P.Pw - 1, floor_div(tx1 - x2_0, inv_dpw));
+          if (!q_ok || a_lo > a_hi || b_lo > b_hi) { a_lo = b_lo = INT_MAX; a_hi = b_hi = INT_MIN; }
+          // all lanes walk the union so that a store instruction covers one (pi, pj): contiguous output pixels
+          const int ua_lo = __reduce_min_sync(0xffffffffu, a_lo), ua_hi = __reduce_max_sync(0xffffffffu, a_hi);
+          const int ub_lo = __reduce_min_sync(0xffffffffu, b_lo), ub_hi = __reduce_max_sync(0xffffffffu, b_hi);
+          if (ua_lo > ua_hi) continue;
+          float* o = out_q + (long long)(d * P.G + g) * P.Ph * P.Pw * plane;
+          // work items = (pi, chunk of 4 pj), dealt round-robin to the warps of the quadrant
+          const int nchunk = (ub_hi - ub_lo) / 4 + 1, nitems = (ua_hi - ua_lo + 1) * nchunk;
+          for (int wi = part; wi < nitems; wi += EPI_SPLIT) {
+            const int ai = wi / nchunk, a = ua_lo + ai, bb = ub_lo + (wi - ai * nchunk) * 4;
+            const bool row_ok = a >= a_lo && a <= a_hi;
+            const float* srow = Srow + (y2_0 + a * dph - ty0) * TTW + (x2_0 - tx0);
+            float* orow = o + (long long)a * P.Pw * plane;
+            float v[4];
+            bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {  // 4 independent load -> store chains in flight
+              ok[u] = row_ok && bb + u >= b_lo && bb + u <= b_hi;
+              v[u] = ok[u] ? srow[(bb + u) * dpw] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float w = v[u] * deq;
+              w = w >= 0.f ? w : w * P.slope;
+              if (ok[u]) orow[(long long)(bb + u) * plane] = w;
+            }
+          }
+        }
+        quad_sync();  // every warp is done with the rows before the next tile overwrites them
       }
-      quad_sync();  // every warp is done with the rows before the next tile overwrites them
     }
   }
 
@@ -542,8 +591,14 @@ int local_corr_tc_launch(const float* in1, const float* in2, const float* flow2,
       if (c < best) { best = c; P.nsplit = k; }
     }
   }
-  dim3 grid(cdiv(ow, QTW), cdiv(oh, QTH), BG * ncls * P.nsplit);
-  EZB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "output too large for one launch");
+  P.qtx = cdiv(ow, QTW);
+  P.qty = cdiv(oh, QTH);
+  const long long n_items = (long long)P.qtx * P.qty * BG * ncls * P.nsplit;
+  EZB_REQUIRE(n_items < (1ll << 31), "output too large for one launch");
+  P.n_items = (int)n_items;
+  // persistent CTAs (one per SM: the kernel uses most of the shared memory) walk the items round-robin, so that the query
+  // load + MMAs of the next item overlap the extraction of the current one and the per-CTA set-up is paid once
+  const int grid = getenv("EZB_LOCAL_CORR_NONPERSISTENT") ? P.n_items : std::min(P.n_items, num_sms());
   if (TTW == 24) {
     EZB_CUDA_OK(cudaFuncSetAttribute(local_corr_tc_kernel<24, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<24, 8>::SMEM_BYTES));
     local_corr_tc_kernel<24, 8><<<grid, NUM_THREADS, Geo<24, 8>::SMEM_BYTES, st>>>(tmA, tmB, P);
