@@ -61,7 +61,30 @@ for i in range(n_cases):
         if not (rf <= tol and mr <= tol):
             fails += 1
             print("FAIL local", mode, (B, C, H, W, P, s, pad, dp), rf, mr)
+    # ---- fused decoder step: warp -> correlation -> LeakyReLU (flows large enough to push taps outside the image)
+    flow = (rng.standard_normal((B, 2, H, W)) * rng.choice([0.5, 3.0, 40.0])).astype(np.float32)
+    slope = float(rng.choice([0.1, 0.01, 1.0]))
+    ref = O.leaky_relu(O.iter_spatial_correlation_sample(x1, O.warp(x2, flow), patch_size=P, stride=s, padding=pad, dilation_patch=dp), slope)
+    for mode, tol in (("tc", 1e-3), ("exact", 5e-5)):
+        E.set_local_corr_mode(mode)
+        m = E.IterSpatialCorrelationSampler(kernel_size=1, patch_size=P, stride=s, padding=pad, dilation_patch=dp)
+        m.fused_negative_slope = None if slope == 1.0 else slope
+        out = m(g(x1), E.lazy_warp(g(x2), g(flow))).cpu().numpy()
+        rf, mr = rel(out, ref) if out.shape == ref.shape else (9, 9)
+        if mode == "tc" and np.count_nonzero(ref) < 200:
+            tol *= 8  # as above; pixels the warp masks out are exact zeros and do not average the statistic down
+        if not (rf <= tol and mr <= tol) and np.abs(ref).max() > 0:
+            fails += 1
+            print("FAIL fused", mode, (B, C, H, W, P, s, pad, dp, slope), rf, mr)
+    # ---- convex flow upsampling
+    N = int(rng.integers(1, 3)); Cf = int(rng.integers(1, 5)); h = int(rng.integers(1, 12)); w = int(rng.integers(1, 80)); st = int(rng.choice([1, 2, 3, 4, 8, 8]))
+    fl = (rng.standard_normal((N, Cf, h, w)) * 10).astype(np.float32); lg = (rng.standard_normal((N, 9 * st * st, h, w)) * 10.0 ** rng.uniform(-1, 1)).astype(np.float32)
+    out = E.convex_upsample_flow(g(fl), g(lg), st).cpu().numpy()
+    rf, mr = rel(out, O.convex_upsample_flow(fl, lg, st))
+    if not (rf <= 2e-5 and mr <= 2e-5):
+        fails += 1
+        print("FAIL upsample", (N, Cf, h, w, st), rf, mr)
 E.set_local_corr_mode("tc"); E.set_pyramid_dtype("fp16")
 torch.cuda.synchronize()
-print(f"fuzz: {n_cases} cases x (pairwise + local tc/exact), failures: {fails}")
+print(f"fuzz: {n_cases} cases x (pairwise + local tc/exact + fused warp/activation + convex upsampling), failures: {fails}")
 sys.exit(1 if fails else 0)
