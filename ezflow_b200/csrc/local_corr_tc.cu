@@ -61,8 +61,28 @@ struct Geo {
   static_assert(CPW % 8 == 0 && CPW <= 56 && BN % 16 == 0 && SMEM_BYTES <= 232448 && (2 * STAGES + 4 + 2 * NACC) * 8 + 4 <= 256, "tile geometry");
 };
 
+// n / d for 0 <= n < 2^31 as a multiply-high and a shift (the divisors are launch constants: the item decode would
+// otherwise cost every warp half a dozen integer divisions per work item)
+struct FastDiv {
+  unsigned mul, shr;
+  int d;
+};
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f{0u, 0u, d};
+  if (d > 1) {
+    int lg = 31 - __builtin_clz((unsigned)d);
+    if (d & (d - 1)) ++lg;  // ceil(log2 d)
+    const int p = 31 + lg;
+    f.mul = (unsigned)(((1ull << p) + (unsigned)d - 1) / (unsigned)d);
+    f.shr = (unsigned)(p - 32);
+  }
+  return f;
+}
+__device__ __forceinline__ int fdiv(int n, const FastDiv& f) { return f.d == 1 ? n : (int)(__umulhi((unsigned)n, f.mul) >> f.shr); }
+
 struct Params {
   int G, H, W, oh, ow, Ph, Pw, sh, sw, padh, padw, D, KB;
+  FastDiv d_qtx, d_qty, d_nsplit, d_ncls, d_lat, d_G;
   int nsplit;  // work items sharing one query tile (each sweeps a slice of its target tiles): balances the load
   // Persistent CTAs: work item = (query tile x, query tile y, z = (bg * lat^2 + class) * nsplit + split), item index
   // x-fastest; CTA c takes items c, c + gridDim.x, ...
@@ -220,18 +240,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   };
   auto item_geometry = [&](int item) {
     Item it;
-    const int bx = item % P.qtx, rest = item / P.qtx, by = rest % P.qty, bz = rest / P.qty;
+    const int rest = fdiv(item, P.d_qtx), bx = item - rest * P.qtx, bz = fdiv(rest, P.d_qty), by = rest - bz * P.qty;
     it.qx0 = bx * QTW;
     it.qy0 = by * QTH;
-    it.zq = bz / P.nsplit;  // bg * lat^2 + class
+    it.zq = fdiv(bz, P.d_nsplit);  // bg * lat^2 + class
     it.split = bz - it.zq * P.nsplit;
-    it.bg = it.zq / ncls;
+    it.bg = fdiv(it.zq, P.d_ncls);
     const int cls = it.zq - it.bg * ncls;
-    it.cy = cls / P.lat;
+    it.cy = fdiv(cls, P.d_lat);
     it.cx = cls - it.cy * P.lat;
     // image / output size in the units the tiles are laid out in (lattice mode: the lattice of this residue class)
-    it.H_ = P.lat > 1 ? (P.Hf - it.cy + P.lat - 1) / P.lat : P.H;
-    it.W_ = P.lat > 1 ? (P.Wf - it.cx + P.lat - 1) / P.lat : P.W;
+    it.H_ = P.lat > 1 ? fdiv(P.Hf - it.cy + P.lat - 1, P.d_lat) : P.H;
+    it.W_ = P.lat > 1 ? fdiv(P.Wf - it.cx + P.lat - 1, P.d_lat) : P.W;
     it.oh_ = P.lat > 1 ? it.H_ : P.oh;
     it.ow_ = P.lat > 1 ? it.W_ : P.ow;
     it.valid = it.qy0 < it.oh_ && it.qx0 < it.ow_;  // (lattice mode) a class smaller than class (0,0) has fewer tiles
@@ -243,8 +263,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     const int nty = y_hi >= it.y_lo ? (y_hi - it.y_lo) / TTH + 1 : 0;
     it.ntx = x_hi >= it.x_lo ? (x_hi - it.x_lo) / TTW + 1 : 0;
     const int ntiles_all = it.valid ? nty * it.ntx : 0;
-    it.tt_begin = ntiles_all * it.split / P.nsplit;
-    it.ntiles = ntiles_all * (it.split + 1) / P.nsplit - it.tt_begin;  // this item sweeps target tiles [tt_begin, tt_begin + ntiles)
+    it.tt_begin = fdiv(ntiles_all * it.split, P.d_nsplit);
+    it.ntiles = fdiv(ntiles_all * (it.split + 1), P.d_nsplit) - it.tt_begin;  // this item sweeps target tiles [tt_begin, tt_begin + ntiles)
     return it;
   };
 
@@ -294,8 +314,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           ptx::tma_load_4d_hint(sA + slot * a_slot_bytes + kb * A_KB_BYTES, &tmA, a_full(slot), kb * BK, it.qx0, it.qy0, it.zq,
                                 ptx::kEvictFirst);  // (oy, ox) space
       }
+      int tyi = it.tt_begin / it.ntx, txi = it.tt_begin - tyi * it.ntx;  // tile row / column inside the bounding box
       for (int tt = 0; tt < it.ntiles; ++tt) {
-        const int ty0 = it.y_lo + ((it.tt_begin + tt) / it.ntx) * TTH, tx0 = it.x_lo + ((it.tt_begin + tt) % it.ntx) * TTW;
+        const int ty0 = it.y_lo + tyi * TTH, tx0 = it.x_lo + txi * TTW;
+        if (++txi == it.ntx) { txi = 0; ++tyi; }
         for (int kb = 0; kb < P.KB; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1);
           ptx::mbar_expect_tx(full_bar(stage), B_STAGE_BYTES);
@@ -354,12 +376,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       const int qx0 = it.qx0, qy0 = it.qy0, H_ = it.H_, W_ = it.W_;
       const int oy = qy0 + q / QTW, ox = qx0 + q % QTW;
       const bool q_ok = oy < it.oh_ && ox < it.ow_;
-      const int b = it.bg / P.G, g = it.bg - b * P.G;
+      const int b = fdiv(it.bg, P.d_G), g = it.bg - b * P.G;
       const float deq = P.scale * dequant_factor(__ldg(P.amax + it.bg), __ldg(P.amax + P.BG + it.bg));
+      // offsets inside one batch entry of the output fit 32 bits (checked by the launcher): one IMAD per store address
       float* out_q = P.out + (long long)b * P.out_bstride + (long long)(it.cy + P.lat * oy) * P.out_w + (it.cx + P.lat * ox);
+      const unsigned uplane = (unsigned)plane;
 
-      // displacements that point outside the image: zeros (act(0) = 0), written once, up front
-      if (q_ok && it.split == 0) {
+      // displacements that point outside the image: zeros (act(0) = 0), written once, up front; a tile whose whole
+      // displacement box lies inside the image has none
+      const bool box_inside = qy0 * P.sh - P.padh - mdh_max >= 0 && (min(qy0 + QTH, it.oh_) - 1) * P.sh - P.padh + mdh_max < H_ &&
+                              qx0 * P.sw - P.padw - mdw_max >= 0 && (min(qx0 + QTW, it.ow_) - 1) * P.sw - P.padw + mdw_max < W_;
+      if (q_ok && it.split == 0 && !box_inside) {
         for (int d = 0; d < P.D; ++d) {
           const int dph = P.dph[d], dpw = P.dpw[d];
           const int y2_0 = oy * P.sh - P.padh - dph * (P.Ph - 1) / 2, x2_0 = ox * P.sw - P.padw - dpw * (P.Pw - 1) / 2;
@@ -375,8 +402,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         }
       }
 
+      int tyi = it.ntiles > 0 ? it.tt_begin / it.ntx : 0, txi = it.tt_begin - tyi * it.ntx;
       for (int tt = 0; tt < it.ntiles; ++tt, ++tcount) {
-        const int ty0 = it.y_lo + ((it.tt_begin + tt) / it.ntx) * TTH, tx0 = it.x_lo + ((it.tt_begin + tt) % it.ntx) * TTW;
+        const int ty0 = it.y_lo + tyi * TTH, tx0 = it.x_lo + txi * TTW;
+        if (++txi == it.ntx) { txi = 0; ++tyi; }
         const int ty1 = min(ty0 + TTH, H_) - 1, tx1 = min(tx0 + TTW, W_) - 1;  // last in-image row / column of the tile
         const uint32_t acc = tcount % NACC, aphase = (tcount / NACC) & 1;
         ptx::mbar_wait(tmem_full(acc), aphase);
@@ -411,7 +440,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 
         for (int d = 0; d < P.D; ++d) {
           const int dph = P.dph[d], dpw = P.dpw[d];
-          {  // CTA-uniform early out: this dilation's box around the query tile does not reach the target tile
+          if (P.D > 1) {  // CTA-uniform early out: this dilation's box around the query tile does not reach the target tile
             const int mh = dph * (P.Ph - 1) / 2, mw = dpw * (P.Pw - 1) / 2;
             if (ty1 < qy0 * P.sh - P.padh - mh || ty0 > (qy0 + QTH - 1) * P.sh - P.padh + mh ||
                 tx1 < qx0 * P.sw - P.padw - mw || tx0 > (qx0 + QTW - 1) * P.sw - P.padw + mw)
@@ -427,26 +456,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           const int ua_lo = __reduce_min_sync(0xffffffffu, a_lo), ua_hi = __reduce_max_sync(0xffffffffu, a_hi);
           const int ub_lo = __reduce_min_sync(0xffffffffu, b_lo), ub_hi = __reduce_max_sync(0xffffffffu, b_hi);
           if (ua_lo > ua_hi) continue;
-          float* o = out_q + (long long)(d * P.G + g) * P.Ph * P.Pw * plane;
+          const unsigned o_d = (unsigned)((d * P.G + g) * P.Ph * P.Pw) * uplane;
           // work items = (pi, chunk of 4 pj), dealt round-robin to the warps of the quadrant
           const int nchunk = (ub_hi - ub_lo) / 4 + 1, nitems = (ua_hi - ua_lo + 1) * nchunk;
+          int ai = 0, ci = part;  // work item wi = ai * nchunk + ci, kept incrementally (no division per item)
+          while (ci >= nchunk) { ci -= nchunk; ++ai; }
           for (int wi = part; wi < nitems; wi += EPI_SPLIT) {
-            const int ai = wi / nchunk, a = ua_lo + ai, bb = ub_lo + (wi - ai * nchunk) * 4;
+            const int a = ua_lo + ai, bb = ub_lo + ci * 4;
+            ci += EPI_SPLIT;
+            while (ci >= nchunk) { ci -= nchunk; ++ai; }
             const bool row_ok = a >= a_lo && a <= a_hi;
-            const float* srow = Srow + (y2_0 + a * dph - ty0) * TTW + (x2_0 - tx0);
-            float* orow = o + (long long)a * P.Pw * plane;
+            const float* srow = Srow + (y2_0 + a * dph - ty0) * TTW + (x2_0 - tx0) + bb * dpw;
+            const unsigned o_ab = o_d + (unsigned)(a * P.Pw + bb) * uplane;
             float v[4];
             bool ok[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {  // 4 independent load -> store chains in flight
               ok[u] = row_ok && bb + u >= b_lo && bb + u <= b_hi;
-              v[u] = ok[u] ? srow[(bb + u) * dpw] : 0.f;
+              v[u] = ok[u] ? srow[u * dpw] : 0.f;
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               float w = v[u] * deq;
               w = w >= 0.f ? w : w * P.slope;
-              if (ok[u]) orow[(long long)(bb + u) * plane] = w;
+              if (ok[u]) out_q[o_ab + u * uplane] = w;
             }
           }
         }
@@ -593,6 +626,9 @@ int local_corr_tc_launch(const float* in1, const float* in2, const float* flow2,
   }
   P.qtx = cdiv(ow, QTW);
   P.qty = cdiv(oh, QTH);
+  P.d_qtx = make_fastdiv(P.qtx); P.d_qty = make_fastdiv(P.qty); P.d_nsplit = make_fastdiv(P.nsplit);
+  P.d_ncls = make_fastdiv(ncls); P.d_lat = make_fastdiv(lat); P.d_G = make_fastdiv(G);
+  EZB_REQUIRE((long long)D * G * Ph * Pw * out_h * out_w < (1ll << 31), "output per batch entry too large for the tensor-core path");
   const long long n_items = (long long)P.qtx * P.qty * BG * ncls * P.nsplit;
   EZB_REQUIRE(n_items < (1ll << 31), "output too large for one launch");
   P.n_items = (int)n_items;
