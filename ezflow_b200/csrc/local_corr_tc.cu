@@ -26,6 +26,7 @@
 #include "ezb_warp.cuh"
 
 #include <climits>
+#include <type_traits>
 #include <cstdlib>
 
 namespace ezb {
@@ -457,30 +458,45 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           const int ub_lo = __reduce_min_sync(0xffffffffu, b_lo), ub_hi = __reduce_max_sync(0xffffffffu, b_hi);
           if (ua_lo > ua_hi) continue;
           const unsigned o_d = (unsigned)((d * P.G + g) * P.Ph * P.Pw) * uplane;
-          // work items = (pi, chunk of 4 pj), dealt round-robin to the warps of the quadrant
-          const int nchunk = (ub_hi - ub_lo) / 4 + 1, nitems = (ua_hi - ua_lo + 1) * nchunk;
-          int ai = 0, ci = part;  // work item wi = ai * nchunk + ci, kept incrementally (no division per item)
-          while (ci >= nchunk) { ci -= nchunk; ++ai; }
-          for (int wi = part; wi < nitems; wi += EPI_SPLIT) {
-            const int a = ua_lo + ai, bb = ub_lo + ci * 4;
-            ci += EPI_SPLIT;
+          // work items = (pi, chunk of CH pj), dealt round-robin to the warps of the quadrant.  CH (3 or 4) is whichever
+          // wastes fewer slots on this row width (a 9- or 21-wide window splits into chunks of 3 without remainder);
+          // ACT: LeakyReLU fused (slope != 1).
+          auto extract = [&](auto ch_tag, auto act_tag) {
+            constexpr int CH = decltype(ch_tag)::value;
+            constexpr bool ACT = decltype(act_tag)::value;
+            const int nchunk = (ub_hi - ub_lo) / CH + 1, nitems = (ua_hi - ua_lo + 1) * nchunk;
+            int ai = 0, ci = part;  // work item wi = ai * nchunk + ci, kept incrementally (no division per item)
             while (ci >= nchunk) { ci -= nchunk; ++ai; }
-            const bool row_ok = a >= a_lo && a <= a_hi;
-            const float* srow = Srow + (y2_0 + a * dph - ty0) * TTW + (x2_0 - tx0) + bb * dpw;
-            const unsigned o_ab = o_d + (unsigned)(a * P.Pw + bb) * uplane;
-            float v[4];
-            bool ok[4];
+            for (int wi = part; wi < nitems; wi += EPI_SPLIT) {
+              const int a = ua_lo + ai, bb = ub_lo + ci * CH;
+              ci += EPI_SPLIT;
+              while (ci >= nchunk) { ci -= nchunk; ++ai; }
+              const bool row_ok = a >= a_lo && a <= a_hi;
+              const float* srow = Srow + (y2_0 + a * dph - ty0) * TTW + (x2_0 - tx0) + bb * dpw;
+              const unsigned o_ab = o_d + (unsigned)(a * P.Pw + bb) * uplane;
+              float v[CH];
+              bool ok[CH];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {  // 4 independent load -> store chains in flight
-              ok[u] = row_ok && bb + u >= b_lo && bb + u <= b_hi;
-              v[u] = ok[u] ? srow[u * dpw] : 0.f;
-            }
+              for (int u = 0; u < CH; ++u) {  // CH independent load -> store chains in flight
+                ok[u] = row_ok && bb + u >= b_lo && bb + u <= b_hi;
+                v[u] = ok[u] ? srow[u * dpw] : 0.f;
+              }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              float w = v[u] * deq;
-              w = w >= 0.f ? w : w * P.slope;
-              if (ok[u]) out_q[o_ab + u * uplane] = w;
+              for (int u = 0; u < CH; ++u) {
+                float w = v[u] * deq;
+                if (ACT) w = w >= 0.f ? w : w * P.slope;
+                if (ok[u]) out_q[o_ab + u * uplane] = w;
+              }
             }
+          };
+          const int nb = ub_hi - ub_lo + 1;
+          const bool ch3 = (nb + 2) / 3 * 3 < (nb + 3) / 4 * 4, act = P.slope != 1.f;
+          if (ch3) {
+            if (act) extract(std::integral_constant<int, 3>{}, std::true_type{});
+            else extract(std::integral_constant<int, 3>{}, std::false_type{});
+          } else {
+            if (act) extract(std::integral_constant<int, 4>{}, std::true_type{});
+            else extract(std::integral_constant<int, 4>{}, std::false_type{});
           }
         }
         quad_sync();  // every warp is done with the rows before the next tile overwrites them
