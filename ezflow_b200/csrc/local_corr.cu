@@ -13,6 +13,8 @@
 // into the (possibly concatenated, K6) destination; scale and LeakyReLU are fused.
 #include "ezb_common.cuh"
 
+#include <cstdlib>
+
 namespace ezb {
 namespace k4 {
 
@@ -173,6 +175,83 @@ __global__ void local_corr_bwd_in2_kernel(const BwdParams P) {
   }
 }
 
+// Stride-1 adjoints, tiled (FlowNetC, PWC-Net, CorrelationLayer, DCVNet's stride-1 scales).  A block owns an 8 x 32 tile of
+// gradient pixels and a chunk of 16 channels; thread = pixel (lane = x: every shared-memory access below is
+// conflict-free and every global access coalesced), 16 accumulators per thread.  Per displacement row pi the block stages
+//   dsh[pj][ty][x]   the upstream gradient of displacement (pi, pj) at the pixel that pairs with (ty, x)
+//   osh[c][ty][j]    the other operand's row for that pi with a halo of (Pw - 1) * dpw columns (zero outside the image)
+// and every thread accumulates  acc[c] += dsh[pj] * osh[c][x + offset(pj)].
+//   SECOND = false: din1[c,y1,x1] = sum dout[pi,pj,y1+padh,x1+padw] * in2[c, y1 + pi*dph - mdh, x1 + pj*dpw - mdw]
+//   SECOND = true : din2[c,y2,x2] = sum dout[pi,pj,y1+padh,x1+padw] * in1[c,y1,x1],  (y1,x1) = (y2 - pi*dph + mdh, x2 - pj*dpw + mdw)
+// The gather kernels above cost P^2 uncached-pattern loads per output element (9.7 ms for FlowNetC's 21 x 21 window at
+// batch 8); here the P^2 products come out of shared memory.
+constexpr int BT_Y = 8, BT_X = 32, BT_C = 16;
+template <bool SECOND>
+__global__ void __launch_bounds__(BT_Y * BT_X) local_corr_bwd_tiled_kernel(const BwdParams P) {
+  extern __shared__ float smem_bt[];
+  const int halo = (P.Pw - 1) * P.dpw, ow_s = BT_X + halo;  // staged row width
+  float* dsh = smem_bt;                           // [Pw][BT_Y][BT_X]
+  float* osh = smem_bt + P.Pw * BT_Y * BT_X;      // [BT_C][BT_Y][ow_s]
+  const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int xtiles = (P.W + BT_X - 1) / BT_X;
+  const int x0 = (blockIdx.x % xtiles) * BT_X, y0 = (blockIdx.x / xtiles) * BT_Y;
+  const int c0 = blockIdx.y * BT_C, b = blockIdx.z;
+  const int mdh = P.dph * (P.Ph - 1) / 2, mdw = P.dpw * (P.Pw - 1) / 2;
+  const long long HW = (long long)P.H * P.W, ohw = (long long)P.oh * P.ow;
+  const float* other = (SECOND ? P.in1 : P.in2) + ((long long)b * P.C + c0) * HW;
+  const float* dout = P.dout + (long long)b * P.dout_bstride;
+  float acc[BT_C];
+#pragma unroll
+  for (int c = 0; c < BT_C; ++c) acc[c] = 0.f;
+  const int nch = min(BT_C, P.C - c0);
+  // first staged column of the other operand: din1 reads x1 + pj*dpw - mdw, din2 reads x2 - pj*dpw + mdw
+  const int xb = SECOND ? x0 + mdw - halo : x0 - mdw;
+
+  for (int pi = 0; pi < P.Ph; ++pi) {
+    const int dy = SECOND ? mdh - pi * P.dph : pi * P.dph - mdh;  // row of the other operand = tile row + dy
+    __syncthreads();  // the previous iteration's reads are done
+    // ---- stage the other operand's rows (zero outside the image / beyond C)
+    for (int r = ty; r < BT_C * BT_Y; r += BT_Y) {  // warp = staged row (c, yy), lanes sweep its columns
+      const int yy = r % BT_Y, c = r / BT_Y;
+      const int ys = y0 + yy + dy;
+      const bool row_ok = c < nch && ys >= 0 && ys < P.H;
+      const float* src = other + (long long)c * HW + (long long)ys * P.W;
+      for (int j = lane; j < ow_s; j += 32) {
+        const int xs = xb + j;
+        osh[r * ow_s + j] = (row_ok && xs >= 0 && xs < P.W) ? __ldg(src + xs) : 0.f;
+      }
+    }
+    // ---- stage the upstream gradient of this displacement row
+    for (int idx = threadIdx.x; idx < P.Pw * BT_Y * BT_X; idx += BT_Y * BT_X) {
+      const int xx = idx % BT_X, r = idx / BT_X, yy = r % BT_Y, pj = r / BT_Y;
+      // the in1 pixel (= query) this gradient element belongs to
+      const int y1 = SECOND ? y0 + yy + dy : y0 + yy;
+      const int x1 = SECOND ? x0 + xx - pj * P.dpw + mdw : x0 + xx;
+      float v = 0.f;
+      if (y1 >= 0 && y1 < P.H && x1 >= 0 && x1 < P.W)
+        v = __ldg(dout + (long long)(pi * P.Pw + pj) * ohw + (long long)(y1 + P.padh) * P.ow + (x1 + P.padw));
+      dsh[idx] = v;
+    }
+    __syncthreads();
+    const float* drow = dsh + ty * BT_X + lane;
+    const float* orow = osh + ty * ow_s + lane + (SECOND ? halo : 0);
+    const int ostep = SECOND ? -P.dpw : P.dpw;
+    for (int pj = 0; pj < P.Pw; ++pj) {
+      const float d = drow[pj * BT_Y * BT_X];
+      const float* o = orow + pj * ostep;
+#pragma unroll
+      for (int c = 0; c < BT_C; ++c) acc[c] = fmaf(d, o[c * BT_Y * ow_s], acc[c]);
+    }
+  }
+  const int y = y0 + ty, x = x0 + lane;
+  if (y < P.H && x < P.W) {
+    float* dst = (SECOND ? P.din2 : P.din1) + ((long long)b * P.C + c0) * HW + (long long)y * P.W + x;
+#pragma unroll
+    for (int c = 0; c < BT_C; ++c)
+      if (c < nch) dst[(long long)c * HW] = acc[c] * P.scale;
+  }
+}
+
 // x / (||x||_2 over channels + eps)        learnable_cost.py:426-428
 __global__ void l2_normalize_kernel(const float* __restrict__ x, float* __restrict__ out, int C, long long HW, long long total_px,
                                     float eps) {
@@ -314,6 +393,24 @@ extern "C" int ezb_local_corr_bwd(const float* in1, const float* in2, const floa
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long total = (long long)B * C * H * W;
   const int blocks = (int)std::min<long long>(cdiv64(total, 256), 148 * 32);
+  // stride 1: tiled kernels (products out of shared memory); otherwise the gather kernels
+  const size_t tiled_smem = ((size_t)Pw * k4::BT_Y * k4::BT_X + (size_t)k4::BT_C * k4::BT_Y * (k4::BT_X + (Pw - 1) * dpw)) * sizeof(float);
+  const long long tiles = (long long)cdiv(W, k4::BT_X) * cdiv(H, k4::BT_Y);
+  if (sh == 1 && sw == 1 && tiled_smem <= 200 * 1024 && tiles < (1ll << 31) && cdiv(C, k4::BT_C) <= 65535 && B <= 65535 &&
+      getenv("EZB_LOCAL_CORR_BWD_GATHER") == nullptr) {
+    const dim3 grid((unsigned)tiles, cdiv(C, k4::BT_C), B);
+    if (din1) {
+      EZB_CUDA_OK(cudaFuncSetAttribute(k4::local_corr_bwd_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled_smem));
+      k4::local_corr_bwd_tiled_kernel<false><<<grid, k4::BT_Y * k4::BT_X, tiled_smem, st>>>(P);
+      EZB_LAUNCH_OK();
+    }
+    if (din2) {
+      EZB_CUDA_OK(cudaFuncSetAttribute(k4::local_corr_bwd_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiled_smem));
+      k4::local_corr_bwd_tiled_kernel<true><<<grid, k4::BT_Y * k4::BT_X, tiled_smem, st>>>(P);
+      EZB_LAUNCH_OK();
+    }
+    return EZB_OK;
+  }
   if (din1) { k4::local_corr_bwd_in1_kernel<<<blocks, 256, 0, st>>>(P); EZB_LAUNCH_OK(); }
   if (din2) { k4::local_corr_bwd_in2_kernel<<<blocks, 256, 0, st>>>(P); EZB_LAUNCH_OK(); }
   return EZB_OK;

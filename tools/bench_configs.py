@@ -3,7 +3,7 @@
 (config 5: lookup backward + pyramid backward for one pair) on one GPU with CUDA events; prints achieved GB/s
 against the algorithmic bytes of BASELINE.md §3.  Parity for the same shapes is in tests/test_gpu_local.py.
 
-    python tools/bench_configs.py [cfg2 cfg3 cfg4 cfg5]
+    python tools/bench_configs.py [cfg2 cfg3 cfg4 cfg5 upsample bwd]
 """
 import json
 import os
@@ -114,6 +114,30 @@ def cfg5():
     N = 32400
     nb = N * 42900 * 2 + 12 * 68.2e6 + 12 * 145.7e6 + 2 * N * 42900 * 4
     report("cfg5 RAFT 1080p fwd+bwd, 1 pair (build, 12 lookups, 12 lookup-bwd, pyramid-bwd)", ms, nb, 3 * 2.0 * N * N * 256)
+
+
+def bwd():
+    """Local-correlation adjoints (K4b) at the config 2 / config 3 shapes: forward + backward through autograd minus
+    the forward alone (the loss glue is a single out.backward(dout))."""
+    cases = [("cfg2 FlowNetC B8 256x48x64 P21 dp2", (8, 256, 48, 64), dict(patch_size=21, dilation_patch=2)),
+             ("cfg3 finest PWC level B8 32x112x256 P9", (8, 32, 112, 256), dict(patch_size=9)),
+             ("cfg3 PWC level B8 96x28x64 P9", (8, 96, 28, 64), dict(patch_size=9))]
+    for name, shape, kw in cases:
+        x1 = torch.randn(shape, device=dev, requires_grad=True)
+        x2 = torch.randn(shape, device=dev, requires_grad=True)
+        m = E.IterSpatialCorrelationSampler(kernel_size=1, padding=0, **kw)
+        out = m(x1, x2)
+        dout = torch.randn_like(out)
+        with torch.no_grad():
+            t_f = timed(lambda: m(x1.detach(), x2.detach()))
+
+        def fb():
+            x1.grad = x2.grad = None
+            m(x1, x2).backward(dout)
+
+        t_fb = timed(fb)
+        nb = 2 * x1.numel() * 4 * 2 + out.numel() * 4
+        report(f"K4b {name}: backward only (fwd {t_f:.3f} ms)", t_fb - t_f, nb, 2 * 2.0 * out.numel() * shape[1])
 
 
 def upsample():
