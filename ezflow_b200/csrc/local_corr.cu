@@ -179,19 +179,20 @@ __global__ void local_corr_bwd_in2_kernel(const BwdParams P) {
 // gradient pixels and a chunk of 16 channels; thread = pixel (lane = x: every shared-memory access below is
 // conflict-free and every global access coalesced), 16 accumulators per thread.  Per displacement row pi the block stages
 //   dsh[pj][ty][x]   the upstream gradient of displacement (pi, pj) at the pixel that pairs with (ty, x)
-//   osh[c][ty][j]    the other operand's row for that pi with a halo of (Pw - 1) * dpw columns (zero outside the image)
-// and every thread accumulates  acc[c] += dsh[pj] * osh[c][x + offset(pj)].
+//   osh[ty][j][c]    the other operand's row for that pi with a halo of (Pw - 1) * dpw columns (zero outside the image),
+//                    channel-innermost with a pitch of 20 floats: the 16 channels of a pixel are four conflict-free LDS.128
+// and every thread accumulates  acc[c] += dsh[pj] * osh[x + offset(pj)][c].
 //   SECOND = false: din1[c,y1,x1] = sum dout[pi,pj,y1+padh,x1+padw] * in2[c, y1 + pi*dph - mdh, x1 + pj*dpw - mdw]
 //   SECOND = true : din2[c,y2,x2] = sum dout[pi,pj,y1+padh,x1+padw] * in1[c,y1,x1],  (y1,x1) = (y2 - pi*dph + mdh, x2 - pj*dpw + mdw)
 // The gather kernels above cost P^2 uncached-pattern loads per output element (9.7 ms for FlowNetC's 21 x 21 window at
 // batch 8); here the P^2 products come out of shared memory.
-constexpr int BT_Y = 8, BT_X = 32, BT_C = 16;
+constexpr int BT_Y = 8, BT_X = 32, BT_C = 16, BT_CP = 20;  // BT_CP: channel pitch of a staged pixel (floats)
 template <bool SECOND>
 __global__ void __launch_bounds__(BT_Y * BT_X) local_corr_bwd_tiled_kernel(const BwdParams P) {
   extern __shared__ float smem_bt[];
   const int halo = (P.Pw - 1) * P.dpw, ow_s = BT_X + halo;  // staged row width
   float* dsh = smem_bt;                           // [Pw][BT_Y][BT_X]
-  float* osh = smem_bt + P.Pw * BT_Y * BT_X;      // [BT_C][BT_Y][ow_s]
+  float* osh = smem_bt + P.Pw * BT_Y * BT_X;      // [BT_Y][ow_s][BT_CP]
   const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int xtiles = (P.W + BT_X - 1) / BT_X;
   const int x0 = (blockIdx.x % xtiles) * BT_X, y0 = (blockIdx.x / xtiles) * BT_Y;
@@ -211,36 +212,56 @@ __global__ void __launch_bounds__(BT_Y * BT_X) local_corr_bwd_tiled_kernel(const
     const int dy = SECOND ? mdh - pi * P.dph : pi * P.dph - mdh;  // row of the other operand = tile row + dy
     __syncthreads();  // the previous iteration's reads are done
     // ---- stage the other operand's rows (zero outside the image / beyond C)
-    for (int r = ty; r < BT_C * BT_Y; r += BT_Y) {  // warp = staged row (c, yy), lanes sweep its columns
-      const int yy = r % BT_Y, c = r / BT_Y;
+    // (four independent loads per thread are issued before the first store: the staging is latency-bound otherwise)
+    for (int r = ty; r < (BT_C / 4) * BT_Y; r += BT_Y) {  // warp = (group of 4 channels, staged row), lanes sweep the columns
+      const int yy = r % BT_Y, cg = r / BT_Y;
       const int ys = y0 + yy + dy;
-      const bool row_ok = c < nch && ys >= 0 && ys < P.H;
-      const float* src = other + (long long)c * HW + (long long)ys * P.W;
+      const bool row_in = ys >= 0 && ys < P.H;
+      const float* src = other + (long long)(cg * 4) * HW + (long long)ys * P.W;
       for (int j = lane; j < ow_s; j += 32) {
         const int xs = xb + j;
-        osh[r * ow_s + j] = (row_ok && xs >= 0 && xs < P.W) ? __ldg(src + xs) : 0.f;
+        const bool ok = row_in && xs >= 0 && xs < P.W;
+        float4 v;
+        v.x = (ok && cg * 4 + 0 < nch) ? __ldg(src + xs) : 0.f;
+        v.y = (ok && cg * 4 + 1 < nch) ? __ldg(src + HW + xs) : 0.f;
+        v.z = (ok && cg * 4 + 2 < nch) ? __ldg(src + 2 * HW + xs) : 0.f;
+        v.w = (ok && cg * 4 + 3 < nch) ? __ldg(src + 3 * HW + xs) : 0.f;
+        *reinterpret_cast<float4*>(osh + (yy * ow_s + j) * BT_CP + cg * 4) = v;
       }
     }
-    // ---- stage the upstream gradient of this displacement row
-    for (int idx = threadIdx.x; idx < P.Pw * BT_Y * BT_X; idx += BT_Y * BT_X) {
-      const int xx = idx % BT_X, r = idx / BT_X, yy = r % BT_Y, pj = r / BT_Y;
-      // the in1 pixel (= query) this gradient element belongs to
-      const int y1 = SECOND ? y0 + yy + dy : y0 + yy;
-      const int x1 = SECOND ? x0 + xx - pj * P.dpw + mdw : x0 + xx;
-      float v = 0.f;
-      if (y1 >= 0 && y1 < P.H && x1 >= 0 && x1 < P.W)
-        v = __ldg(dout + (long long)(pi * P.Pw + pj) * ohw + (long long)(y1 + P.padh) * P.ow + (x1 + P.padw));
-      dsh[idx] = v;
+    // ---- stage the upstream gradient of this displacement row: thread = tile pixel, loop over pj
+    {
+      const int y1 = SECOND ? y0 + ty + dy : y0 + ty;  // the in1 pixel (= query) row this gradient element belongs to
+      const bool y_ok = y1 >= 0 && y1 < P.H;
+      const float* drow_g = dout + (long long)pi * P.Pw * ohw + (long long)(y1 + P.padh) * P.ow + P.padw;
+      for (int pj0 = 0; pj0 < P.Pw; pj0 += 4) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int pj = pj0 + u;
+          const int x1 = SECOND ? x0 + lane - pj * P.dpw + mdw : x0 + lane;
+          v[u] = (pj < P.Pw && y_ok && x1 >= 0 && x1 < P.W) ? __ldg(drow_g + (long long)pj * ohw + x1) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (pj0 + u < P.Pw) dsh[((pj0 + u) * BT_Y + ty) * BT_X + lane] = v[u];
+      }
     }
     __syncthreads();
     const float* drow = dsh + ty * BT_X + lane;
-    const float* orow = osh + ty * ow_s + lane + (SECOND ? halo : 0);
-    const int ostep = SECOND ? -P.dpw : P.dpw;
+    const float4* orow = reinterpret_cast<const float4*>(osh + (ty * ow_s + lane + (SECOND ? halo : 0)) * BT_CP);
+    const int ostep = (SECOND ? -P.dpw : P.dpw) * (BT_CP / 4);
     for (int pj = 0; pj < P.Pw; ++pj) {
       const float d = drow[pj * BT_Y * BT_X];
-      const float* o = orow + pj * ostep;
+      const float4* o = orow + pj * ostep;
 #pragma unroll
-      for (int c = 0; c < BT_C; ++c) acc[c] = fmaf(d, o[c * BT_Y * ow_s], acc[c]);
+      for (int g = 0; g < BT_C / 4; ++g) {
+        const float4 v = o[g];
+        acc[4 * g + 0] = fmaf(d, v.x, acc[4 * g + 0]);
+        acc[4 * g + 1] = fmaf(d, v.y, acc[4 * g + 1]);
+        acc[4 * g + 2] = fmaf(d, v.z, acc[4 * g + 2]);
+        acc[4 * g + 3] = fmaf(d, v.w, acc[4 * g + 3]);
+      }
     }
   }
   const int y = y0 + ty, x = x0 + lane;
@@ -394,7 +415,7 @@ extern "C" int ezb_local_corr_bwd(const float* in1, const float* in2, const floa
   const long long total = (long long)B * C * H * W;
   const int blocks = (int)std::min<long long>(cdiv64(total, 256), 148 * 32);
   // stride 1: tiled kernels (products out of shared memory); otherwise the gather kernels
-  const size_t tiled_smem = ((size_t)Pw * k4::BT_Y * k4::BT_X + (size_t)k4::BT_C * k4::BT_Y * (k4::BT_X + (Pw - 1) * dpw)) * sizeof(float);
+  const size_t tiled_smem = ((size_t)Pw * k4::BT_Y * k4::BT_X + (size_t)k4::BT_CP * k4::BT_Y * (k4::BT_X + (Pw - 1) * dpw)) * sizeof(float);
   const long long tiles = (long long)cdiv(W, k4::BT_X) * cdiv(H, k4::BT_Y);
   if (sh == 1 && sw == 1 && tiled_smem <= 200 * 1024 && tiles < (1ll << 31) && cdiv(C, k4::BT_C) <= 65535 && B <= 65535 &&
       getenv("EZB_LOCAL_CORR_BWD_GATHER") == nullptr) {
