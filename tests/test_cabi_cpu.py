@@ -114,3 +114,23 @@ def test_sass_is_blackwell_native():
     for mnem in ("UTCHMMA", "LDTM", "UTMALDG"):
         assert mnem in sass, f"{mnem} missing from SASS"
     assert "HMMA." not in sass.replace("UTCHMMA", "")
+
+
+def test_header_is_c99_and_library_links_from_plain_c(lib, tmp_path):
+    """The boundary is a C ABI: a C99 program includes the header, links the .so and calls host-only entry points."""
+    import shutil
+    import subprocess
+
+    from ezflow_b200 import _cabi
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    exe = str(tmp_path / "cabi_link")
+    libdir = os.path.dirname(_cabi.LIBPATH)
+    cmd = [gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "c", "cabi_link.c"), "-o", exe, "-L", libdir, "-lezflow_b200", f"-Wl,-rpath,{libdir}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "cabi_link ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
