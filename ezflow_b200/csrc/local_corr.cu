@@ -34,6 +34,7 @@ struct Params {
   int dph[MAX_DIL], dpw[MAX_DIL];
   int oh, ow;
   int rx_max;          // shared-memory row length of the in2 window
+  int pi_split;        // 1: a block walks all displacement rows; Ph: blockIdx.z also indexes the displacement row
   float scale, slope;
   long long out_bstride;
 };
@@ -43,7 +44,10 @@ __global__ void __launch_bounds__(NT) local_corr_fwd_kernel(const Params P) {
   float* sA = sm;                 // [CC][TX]
   float* sB = sm + CC * TX;       // [CC][rx_max]
   const int x0 = blockIdx.x * TX, y = blockIdx.y;
-  const int bg = blockIdx.z / P.D, d = blockIdx.z - bg * P.D;
+  // displacement rows are independent: with pi in the grid a small map still fills the GPU (a block per output row
+  // walking all P rows was latency-bound: 285 us for a 7x16 map)
+  const int zz = blockIdx.z / P.pi_split, pi_only = blockIdx.z - zz * P.pi_split;
+  const int bg = zz / P.D, d = zz - bg * P.D;
   const int b = bg / P.G, g = bg - b * P.G;
   const int dph = P.dph[d], dpw = P.dpw[d];
   const int mdh = dph * (P.Ph - 1) / 2, mdw = dpw * (P.Pw - 1) / 2;
@@ -59,7 +63,8 @@ __global__ void __launch_bounds__(NT) local_corr_fwd_kernel(const Params P) {
   float* out = P.out + (long long)b * P.out_bstride + ((long long)(d * P.G + g) * P.Ph * P.Pw) * ohw + (long long)y * P.ow;
   const bool x_ok = x0 + xl < P.ow;
 
-  for (int pi = 0; pi < P.Ph; ++pi) {
+  const int pi_begin = P.pi_split > 1 ? pi_only : 0, pi_end = P.pi_split > 1 ? pi_only + 1 : P.Ph;
+  for (int pi = pi_begin; pi < pi_end; ++pi) {
     const int y2 = y * P.sh + pi * dph - mdh - P.padh;
     const bool rows_ok = y1_ok && y2 >= 0 && y2 < P.H;
     for (int jbase = 0; jbase < P.Pw; jbase += 4 * NJ) {
@@ -299,7 +304,10 @@ static int launch_fwd(Params& P, cudaStream_t st) {
     return fail(EZB_ERR_UNSUPPORTED, "displacement window too wide for the shared-memory tile (patch %d, dilation_patch up to %d, stride %d)",
                 P.Pw, P.dpw[0], P.sw);
   EZB_CUDA_OK(cudaFuncSetAttribute(local_corr_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(cdiv(P.ow, TX), P.oh, P.BG * P.D);
+  // small maps only: with enough row blocks to fill the GPU, splitting just re-stages the in1 row P times more often
+  const long long row_blocks = (long long)cdiv(P.ow, TX) * P.oh * P.BG * P.D;
+  P.pi_split = (row_blocks < 2000 && (long long)P.BG * P.D * P.Ph <= 65535) ? P.Ph : 1;
+  dim3 grid(cdiv(P.ow, TX), P.oh, P.BG * P.D * P.pi_split);
   EZB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "output too large for one launch");
   local_corr_fwd_kernel<<<grid, NT, smem, st>>>(P);
   EZB_LAUNCH_OK();
