@@ -153,7 +153,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -477,7 +477,7 @@ def run_b200(args):
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample = cpu_port_pairs_per_sec(args.cpu_sample_rows)
             line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         import torch.distributed as dist
 
@@ -485,8 +485,31 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def _reserve_stdout():
+    """stdout carries exactly one JSON line: file descriptor 1 is pointed at stderr for the rest of the process (NCCL and
+    other native libraries print their banners with printf), and the JSON line is written to the saved descriptor."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
+
+
 def main():
     args = parse_args()
+    _reserve_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
