@@ -26,6 +26,8 @@ def _matryoshka_forward(x1, x2, G, P, stride, dilations, slope, out=None, ch_off
     oh, ow = -(-H // stride), -(-W // stride)
     if out is None:
         out = torch.empty((B, D * G, P, P, oh, ow), dtype=torch.float32, device=x1.device)
+    if B == 0:
+        return out
     view = out[:, ch_offset : ch_offset + D * G]
     dil = (ctypes.c_int * D)(*[int(d) for d in dilations])
     with torch.cuda.device(x1.device):

@@ -258,6 +258,10 @@ class MutliScalePairwise4DCorr:
             raise ValueError(f"fmap1/fmap2 must both be (B,C,H,W); got {tuple(fmap1.shape)} and {tuple(fmap2.shape)}")
         if int(num_levels) < 1:
             raise ValueError("num_levels must be >= 1")
+        self._empty = f1.shape[0] == 0  # an empty batch yields empty lookups, as the reference's ops do
+        if self._empty:
+            self._state, self._token, self._shape = None, None, tuple(f1.shape)
+            return
         self._state = _PyramidState(f1.detach(), f2.detach(), num_levels, _PYRAMID_DTYPE)
         if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
             self._token = _BuildFn.apply(f1, f2, self._state)
@@ -277,6 +281,9 @@ class MutliScalePairwise4DCorr:
 
     def __call__(self, coords):
         c = _cabi.require_cuda_f32(coords, "coords")
+        if self._empty:
+            _, _, H, W = self._shape
+            return c.new_zeros((0, self.num_levels * (2 * self.corr_radius + 1) ** 2, H, W))
         st = self._state
         if c.dim() != 4 or c.shape[0] != st.B or c.shape[1] != 2 or c.shape[2] != st.H or c.shape[3] != st.W:
             raise ValueError(f"coords must be ({st.B},2,{st.H},{st.W}); got {tuple(coords.shape)}")

@@ -67,6 +67,8 @@ def local_corr_forward(in1, in2, patch, stride, padding, dpatch, scale=1.0, slop
     oh, ow = _out_hw(H, W, stride, padding)
     if out is None:
         out = torch.empty((B, patch[0], patch[1], oh, ow), dtype=torch.float32, device=in1.device)
+    if B == 0:
+        return out
     lib = _cabi.lib()
     with torch.cuda.device(in1.device):
         ws, nws = local_corr_workspace(B, C, H, W, in1.device, padding)
@@ -83,6 +85,8 @@ def local_corr_backward(in1, in2, dout, patch, stride, padding, dpatch, scale=1.
     B, C, H, W = in1.shape
     d1 = torch.empty_like(in1) if need1 else None
     d2 = torch.empty_like(in2) if need2 else None
+    if B == 0 or (d1 is None and d2 is None):
+        return d1, d2
     with torch.cuda.device(in1.device):
         _cabi.check(
             _cabi.lib().ezb_local_corr_bwd(

@@ -42,6 +42,8 @@ def _warp_backward(x, flow, dout, need_x=True, need_flow=True):
 def _warp_forward(x, flow):
     B, C, H, W = x.shape
     out = torch.empty_like(x)
+    if B == 0:
+        return out
     with torch.cuda.device(x.device):
         _cabi.check(_cabi.lib().ezb_warp_fwd(_cabi.ptr(x), _cabi.ptr(flow), B, C, H, W, _cabi.ptr(out), _cabi.stream_ptr(x.device)))
     return out
@@ -99,6 +101,8 @@ class _ConvexUpsampleFn(torch.autograd.Function):
 def _convex_upsample_forward(flow, mask_logits, out_stride):
     N, C, H, W = flow.shape
     out = torch.empty((N, C, out_stride * H, out_stride * W), dtype=torch.float32, device=flow.device)
+    if N == 0:
+        return out
     with torch.cuda.device(flow.device):
         _cabi.check(
             _cabi.lib().ezb_convex_upsample_fwd(

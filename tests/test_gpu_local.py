@@ -199,3 +199,18 @@ def test_tiny_and_ragged_shapes_vs_oracle(cfg, mode):
     out = E.IterSpatialCorrelationSampler(kernel_size=1, patch_size=P, stride=s, padding=pad, dilation_patch=dp)(to_gpu(x1), to_gpu(x2))
     assert tuple(out.shape) == ref.shape
     assert_close(out, ref, FWD_TOL[mode], f"{cfg} ({mode})")
+
+
+def test_empty_batch_returns_empty_outputs():
+    """B = 0 (e.g. the tail of a DataParallel scatter): every op returns an empty tensor of the reference's shape."""
+    import ezflow_b200 as E
+
+    z = torch.zeros(0, 16, 12, 20, device=dev())
+    fl = torch.zeros(0, 2, 12, 20, device=dev())
+    assert tuple(E.IterSpatialCorrelationSampler(patch_size=9)(z, z).shape) == (0, 9, 9, 12, 20)
+    assert tuple(E.CorrelationLayer()(z, z).shape) == (0, 81, 12, 20)
+    assert tuple(E.MatryoshkaDilatedCostVolume()(z, z).shape) == (0, 6, 9, 9, 12, 20)
+    assert tuple(E.warp(z, fl).shape) == (0, 16, 12, 20)
+    assert tuple(E.convex_upsample_flow(fl, torch.zeros(0, 576, 12, 20, device=dev()), 8).shape) == (0, 2, 96, 160)
+    fn = E.MutliScalePairwise4DCorr(z, z, num_levels=2, corr_radius=3)
+    assert tuple(fn(fl).shape) == (0, 2 * 49, 12, 20)
