@@ -213,14 +213,22 @@ __global__ void __launch_bounds__(BT_Y * BT_X) local_corr_bwd_tiled_kernel(const
   // first staged column of the other operand: din1 reads x1 + pj*dpw - mdw, din2 reads x2 - pj*dpw + mdw
   const int xb = SECOND ? x0 + mdw - halo : x0 - mdw;
 
-  for (int pi = 0; pi < P.Ph; ++pi) {
+  // Displacement rows are walked so that the other operand's rows only ever move down: step `it` needs the image rows
+  // ybase + a for a in [it*dph, it*dph + BT_Y) (din2 walks pi backwards for that), kept in a ring of BT_Y row slots
+  // (slot = a mod BT_Y), so a step stages only the min(dph, BT_Y) rows its predecessor did not have.
+  const int ybase = SECOND ? y0 + mdh - (P.Ph - 1) * P.dph : y0 - mdh;
+  const int rows_new = min(P.dph, BT_Y);
+  for (int it = 0; it < P.Ph; ++it) {
+    const int pi = SECOND ? P.Ph - 1 - it : it;
     const int dy = SECOND ? mdh - pi * P.dph : pi * P.dph - mdh;  // row of the other operand = tile row + dy
+    const int a0 = it * P.dph;
+    const int a_first = it == 0 ? a0 : a0 + BT_Y - rows_new, n_rows = it == 0 ? BT_Y : rows_new;
     __syncthreads();  // the previous iteration's reads are done
-    // ---- stage the other operand's rows (zero outside the image / beyond C)
+    // ---- stage the other operand's new rows (zero outside the image / beyond C)
     // (four independent loads per thread are issued before the first store: the staging is latency-bound otherwise)
-    for (int r = ty; r < (BT_C / 4) * BT_Y; r += BT_Y) {  // warp = (group of 4 channels, staged row), lanes sweep the columns
-      const int yy = r % BT_Y, cg = r / BT_Y;
-      const int ys = y0 + yy + dy;
+    for (int r = ty; r < (BT_C / 4) * n_rows; r += BT_Y) {  // warp = (group of 4 channels, new row), lanes sweep the columns
+      const int cg = r / n_rows, a = a_first + (r - cg * n_rows);
+      const int ys = ybase + a, slot = a & (BT_Y - 1);
       const bool row_in = ys >= 0 && ys < P.H;
       const float* src = other + (long long)(cg * 4) * HW + (long long)ys * P.W;
       for (int j = lane; j < ow_s; j += 32) {
@@ -231,7 +239,7 @@ __global__ void __launch_bounds__(BT_Y * BT_X) local_corr_bwd_tiled_kernel(const
         v.y = (ok && cg * 4 + 1 < nch) ? __ldg(src + HW + xs) : 0.f;
         v.z = (ok && cg * 4 + 2 < nch) ? __ldg(src + 2 * HW + xs) : 0.f;
         v.w = (ok && cg * 4 + 3 < nch) ? __ldg(src + 3 * HW + xs) : 0.f;
-        *reinterpret_cast<float4*>(osh + (yy * ow_s + j) * BT_CP + cg * 4) = v;
+        *reinterpret_cast<float4*>(osh + (slot * ow_s + j) * BT_CP + cg * 4) = v;
       }
     }
     // ---- stage the upstream gradient of this displacement row: thread = tile pixel, loop over pj
@@ -254,7 +262,7 @@ __global__ void __launch_bounds__(BT_Y * BT_X) local_corr_bwd_tiled_kernel(const
     }
     __syncthreads();
     const float* drow = dsh + ty * BT_X + lane;
-    const float4* orow = reinterpret_cast<const float4*>(osh + (ty * ow_s + lane + (SECOND ? halo : 0)) * BT_CP);
+    const float4* orow = reinterpret_cast<const float4*>(osh + (((a0 + ty) & (BT_Y - 1)) * ow_s + lane + (SECOND ? halo : 0)) * BT_CP);
     const int ostep = (SECOND ? -P.dpw : P.dpw) * (BT_CP / 4);
     for (int pj = 0; pj < P.Pw; ++pj) {
       const float d = drow[pj * BT_Y * BT_X];
