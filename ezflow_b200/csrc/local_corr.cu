@@ -183,10 +183,10 @@ __global__ void local_corr_bwd_in2_kernel(const BwdParams P) {
 // Stride-1 adjoints, tiled (FlowNetC, PWC-Net, CorrelationLayer, DCVNet's stride-1 scales).  A block owns an 8 x 32 tile of
 // gradient pixels and a chunk of 16 channels; thread = pixel (lane = x: every shared-memory access below is
 // conflict-free and every global access coalesced), 16 accumulators per thread.  Per displacement row pi the block stages
-//   dsh[pj][ty][x]   the upstream gradient of displacement (pi, pj) at the pixel that pairs with (ty, x)
 //   osh[ty][j][c]    the other operand's row for that pi with a halo of (Pw - 1) * dpw columns (zero outside the image),
 //                    channel-innermost with a pitch of 20 floats: the 16 channels of a pixel are four conflict-free LDS.128
-// and every thread accumulates  acc[c] += dsh[pj] * osh[x + offset(pj)][c].
+// and every thread accumulates  acc[c] += d[pj] * osh[x + offset(pj)][c], d[pj] = the upstream gradient of displacement (pi, pj) at
+// the pixel that pairs with (ty, x) — private to the thread, read from global memory a few displacements ahead.
 //   SECOND = false: din1[c,y1,x1] = sum dout[pi,pj,y1+padh,x1+padw] * in2[c, y1 + pi*dph - mdh, x1 + pj*dpw - mdw]
 //   SECOND = true : din2[c,y2,x2] = sum dout[pi,pj,y1+padh,x1+padw] * in1[c,y1,x1],  (y1,x1) = (y2 - pi*dph + mdh, x2 - pj*dpw + mdw)
 // The gather kernels above cost P^2 uncached-pattern loads per output element (9.7 ms for FlowNetC's 21 x 21 window at
@@ -196,8 +196,7 @@ template <bool SECOND>
 __global__ void __launch_bounds__(BT_Y * BT_X) local_corr_bwd_tiled_kernel(const BwdParams P) {
   extern __shared__ float smem_bt[];
   const int halo = (P.Pw - 1) * P.dpw, ow_s = BT_X + halo;  // staged row width
-  float* dsh = smem_bt;                           // [Pw][BT_Y][BT_X]
-  float* osh = smem_bt + P.Pw * BT_Y * BT_X;      // [BT_Y][ow_s][BT_CP]
+  float* osh = smem_bt;                           // [BT_Y][ow_s][BT_CP]
   const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int xtiles = (P.W + BT_X - 1) / BT_X;
   const int x0 = (blockIdx.x % xtiles) * BT_X, y0 = (blockIdx.x / xtiles) * BT_Y;
@@ -242,38 +241,43 @@ __global__ void __launch_bounds__(BT_Y * BT_X) local_corr_bwd_tiled_kernel(const
         *reinterpret_cast<float4*>(osh + (slot * ow_s + j) * BT_CP + cg * 4) = v;
       }
     }
-    // ---- stage the upstream gradient of this displacement row: thread = tile pixel, loop over pj
-    {
-      const int y1 = SECOND ? y0 + ty + dy : y0 + ty;  // the in1 pixel (= query) row this gradient element belongs to
-      const bool y_ok = y1 >= 0 && y1 < P.H;
-      const float* drow_g = dout + (long long)pi * P.Pw * ohw + (long long)(y1 + P.padh) * P.ow + P.padw;
-      for (int pj0 = 0; pj0 < P.Pw; pj0 += 4) {
-        float v[4];
+    // ---- the upstream gradient dout[pi, pj] at the pixel that pairs with (ty, lane) is private to this thread: it comes
+    // straight from global memory (L2) into registers, four displacements ahead of their use
+    const int y1 = SECOND ? y0 + ty + dy : y0 + ty;  // the in1 pixel (= query) row this gradient element belongs to
+    const bool y_ok = y1 >= 0 && y1 < P.H;
+    const float* drow_g = dout + (long long)pi * P.Pw * ohw + (long long)(y1 + P.padh) * P.ow + P.padw;
+    const int xq = SECOND ? x0 + lane + mdw : x0 + lane;
+    auto load_d = [&](int pj) {
+      const int x1 = SECOND ? xq - pj * P.dpw : xq;
+      return (pj < P.Pw && y_ok && x1 >= 0 && x1 < P.W) ? __ldg(drow_g + (long long)pj * ohw + x1) : 0.f;
+    };
+    float dn[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int pj = pj0 + u;
-          const int x1 = SECOND ? x0 + lane - pj * P.dpw + mdw : x0 + lane;
-          v[u] = (pj < P.Pw && y_ok && x1 >= 0 && x1 < P.W) ? __ldg(drow_g + (long long)pj * ohw + x1) : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (pj0 + u < P.Pw) dsh[((pj0 + u) * BT_Y + ty) * BT_X + lane] = v[u];
-      }
-    }
+    for (int u = 0; u < 4; ++u) dn[u] = load_d(u);
     __syncthreads();
-    const float* drow = dsh + ty * BT_X + lane;
     const float4* orow = reinterpret_cast<const float4*>(osh + (((a0 + ty) & (BT_Y - 1)) * ow_s + lane + (SECOND ? halo : 0)) * BT_CP);
     const int ostep = (SECOND ? -P.dpw : P.dpw) * (BT_CP / 4);
-    for (int pj = 0; pj < P.Pw; ++pj) {
-      const float d = drow[pj * BT_Y * BT_X];
-      const float4* o = orow + pj * ostep;
+    for (int pj0 = 0; pj0 < P.Pw; pj0 += 4) {
+      float dc[4];
 #pragma unroll
-      for (int g = 0; g < BT_C / 4; ++g) {
-        const float4 v = o[g];
-        acc[4 * g + 0] = fmaf(d, v.x, acc[4 * g + 0]);
-        acc[4 * g + 1] = fmaf(d, v.y, acc[4 * g + 1]);
-        acc[4 * g + 2] = fmaf(d, v.z, acc[4 * g + 2]);
-        acc[4 * g + 3] = fmaf(d, v.w, acc[4 * g + 3]);
+      for (int u = 0; u < 4; ++u) {
+        dc[u] = dn[u];
+        dn[u] = load_d(pj0 + 4 + u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (pj0 + u < P.Pw) {
+          const float d = dc[u];
+          const float4* o = orow + (pj0 + u) * ostep;
+#pragma unroll
+          for (int g = 0; g < BT_C / 4; ++g) {
+            const float4 v = o[g];
+            acc[4 * g + 0] = fmaf(d, v.x, acc[4 * g + 0]);
+            acc[4 * g + 1] = fmaf(d, v.y, acc[4 * g + 1]);
+            acc[4 * g + 2] = fmaf(d, v.z, acc[4 * g + 2]);
+            acc[4 * g + 3] = fmaf(d, v.w, acc[4 * g + 3]);
+          }
+        }
       }
     }
   }
@@ -431,7 +435,7 @@ extern "C" int ezb_local_corr_bwd(const float* in1, const float* in2, const floa
   const long long total = (long long)B * C * H * W;
   const int blocks = (int)std::min<long long>(cdiv64(total, 256), 148 * 32);
   // stride 1: tiled kernels (products out of shared memory); otherwise the gather kernels
-  const size_t tiled_smem = ((size_t)Pw * k4::BT_Y * k4::BT_X + (size_t)k4::BT_CP * k4::BT_Y * (k4::BT_X + (Pw - 1) * dpw)) * sizeof(float);
+  const size_t tiled_smem = (size_t)k4::BT_CP * k4::BT_Y * (k4::BT_X + (Pw - 1) * dpw) * sizeof(float);
   const long long tiles = (long long)cdiv(W, k4::BT_X) * cdiv(H, k4::BT_Y);
   if (sh == 1 && sw == 1 && tiled_smem <= 200 * 1024 && tiles < (1ll << 31) && cdiv(C, k4::BT_C) <= 65535 && B <= 65535 &&
       getenv("EZB_LOCAL_CORR_BWD_GATHER") == nullptr) {
