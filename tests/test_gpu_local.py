@@ -214,3 +214,52 @@ def test_empty_batch_returns_empty_outputs():
     assert tuple(E.convex_upsample_flow(fl, torch.zeros(0, 576, 12, 20, device=dev()), 8).shape) == (0, 2, 96, 160)
     fn = E.MutliScalePairwise4DCorr(z, z, num_levels=2, corr_radius=3)
     assert tuple(fn(fl).shape) == (0, 2 * 49, 12, 20)
+
+
+def _torch_sampler(x1, x2, patch, stride=1, padding=0, dp=1):
+    """fp32 PyTorch restatement of iter_spatial_correlation_sample (reference sampler.py:96-129: pad, one shifted slice per
+    displacement, multiply, sum over channels) — the full-size checker where the numpy oracle would take minutes."""
+    import torch.nn.functional as F
+
+    b, c, h, w = x1.shape
+    a = F.pad(x1, (padding, padding, padding, padding))
+    t = F.pad(x2, (padding, padding, padding, padding))
+    md = dp * (patch - 1) // 2
+    hp, wp = a.shape[2:]
+    t = F.pad(t, (md, md, md, md))
+    a = a[:, :, ::stride, ::stride]
+    out = torch.empty(b, patch, patch, a.shape[2], a.shape[3], device=x1.device)
+    for i in range(patch):
+        for j in range(patch):
+            out[:, i, j] = (a * t[:, :, i * dp : i * dp + hp : stride, j * dp : j * dp + wp : stride]).sum(1)
+    return out
+
+
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg3_fine", "cfg4_s8_dil", "cfg4_s2"])
+def test_baseline_configs_full_batch(cfg, mode):
+    """BASELINE configs 2-4 at their FULL batch sizes (many work items per persistent CTA, nsplit, lattice mode, stride 4)
+    against the PyTorch fp32 restatement on the same GPU."""
+    import ezflow_b200 as E
+
+    g = torch.Generator(device=dev()).manual_seed(23)
+    shape, kw = {
+        "cfg2": ((8, 256, 48, 64), dict(patch=21, dp=2)),
+        "cfg3_fine": ((8, 32, 112, 256), dict(patch=9)),
+        "cfg4_s8_dil": ((4, 256, 48, 96), dict(patch=9, dp=5)),
+        "cfg4_s2": ((4, 128, 192, 384), dict(patch=9, stride=4)),
+    }[cfg]
+    x1 = torch.randn(shape, device=dev(), generator=g)
+    x2 = torch.randn(shape, device=dev(), generator=g)
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = _torch_sampler(x1, x2, kw["patch"], kw.get("stride", 1), 0, kw.get("dp", 1))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    m = E.IterSpatialCorrelationSampler(kernel_size=1, patch_size=kw["patch"], stride=kw.get("stride", 1), padding=0,
+                                        dilation_patch=kw.get("dp", 1))
+    out = m(x1, x2)
+    assert tuple(out.shape) == tuple(ref.shape)
+    assert_close(out, ref, FWD_TOL[mode] if mode == "tc" else 5e-5, f"{cfg} full batch")
+    # run-to-run determinism at full size (persistent CTAs must not race on the shared rows / accumulators)
+    assert torch.equal(out, m(x1, x2))
