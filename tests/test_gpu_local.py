@@ -263,3 +263,27 @@ def test_baseline_configs_full_batch(cfg, mode):
     assert_close(out, ref, FWD_TOL[mode] if mode == "tc" else 5e-5, f"{cfg} full batch")
     # run-to-run determinism at full size (persistent CTAs must not race on the shared rows / accumulators)
     assert torch.equal(out, m(x1, x2))
+
+
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg3_fine", "pad_dil"])
+def test_adjoints_full_size_vs_torch_autograd(cfg):
+    """K4b at BASELINE shapes (tiled stride-1 kernels, many tiles / channel chunks) against autograd of the PyTorch restatement."""
+    import ezflow_b200 as E
+
+    g = torch.Generator(device=dev()).manual_seed(29)
+    shape, kw = {
+        "cfg2": ((4, 256, 48, 64), dict(patch=21, dp=2)),
+        "cfg3_fine": ((8, 32, 112, 256), dict(patch=9)),
+        "pad_dil": ((2, 40, 37, 45), dict(patch=5, dp=3, padding=4)),  # ragged tiles, 40 channels (2.5 chunks), padding
+    }[cfg]
+    x1 = torch.randn(shape, device=dev(), generator=g)
+    x2 = torch.randn(shape, device=dev(), generator=g)
+    a1, a2 = x1.clone().requires_grad_(True), x2.clone().requires_grad_(True)
+    ref = _torch_sampler(a1, a2, kw["patch"], 1, kw.get("padding", 0), kw.get("dp", 1))
+    dout = torch.randn(ref.shape, device=dev(), generator=g)
+    ref.backward(dout)
+    b1, b2 = x1.clone().requires_grad_(True), x2.clone().requires_grad_(True)
+    m = E.IterSpatialCorrelationSampler(kernel_size=1, patch_size=kw["patch"], padding=kw.get("padding", 0), dilation_patch=kw.get("dp", 1))
+    m(b1, b2).backward(dout)
+    assert_close(b1.grad, a1.grad, 5e-5, f"{cfg} d input1")
+    assert_close(b2.grad, a2.grad, 5e-5, f"{cfg} d input2")
