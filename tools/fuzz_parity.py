@@ -80,11 +80,20 @@ for i in range(n_cases):
         m.fused_negative_slope = None if slope == 1.0 else slope
         out = m(g(x1), E.lazy_warp(g(x2), g(flow))).cpu().numpy()
         rf, mr = rel(out, ref) if out.shape == ref.shape else (9, 9)
-        if mode == "tc" and np.count_nonzero(ref) < 200:
+        nnz = int(np.count_nonzero(ref))
+        if mode == "tc" and nnz < 200:
             tol *= 8  # as above; pixels the warp masks out are exact zeros and do not average the statistic down
+        if nnz < 20 and out.shape == ref.shape:
+            # a handful of surviving dot products may all be cancellation-dominated: measure the error against the scale of a
+            # C-term dot product of these inputs instead of against the (accidentally small) results
+            scale_dp = float(np.sqrt(C) * np.sqrt((x1.astype(np.float64) ** 2).mean()) * np.sqrt((x2.astype(np.float64) ** 2).mean()))
+            rf = mr = float(np.abs(out.astype(np.float64) - ref).max() / max(np.abs(ref).max(), scale_dp))
         if not (rf <= tol and mr <= tol) and np.abs(ref).max() > 0:
             fails += 1
-            print("FAIL fused", mode, (B, C, H, W, P, s, pad, dp, slope), rf, mr)
+            print("FAIL fused", mode, (B, C, H, W, P, s, pad, dp, slope), rf, mr, "nnz", int(np.count_nonzero(ref)),
+                  "max|ref|", float(np.abs(ref).max()), "max|flow|", float(np.abs(flow).max()))
+            if os.environ.get("EZB_FUZZ_DUMP"):
+                np.savez(os.environ["EZB_FUZZ_DUMP"], x1=x1, x2=x2, flow=flow, ref=ref, out=out, params=np.array([P, s, pad, dp]), slope=slope)
     # ---- convex flow upsampling
     N = int(rng.integers(1, 3)); Cf = int(rng.integers(1, 5)); h = int(rng.integers(1, 12)); w = int(rng.integers(1, 80)); st = int(rng.choice([1, 2, 3, 4, 8, 8]))
     fl = (rng.standard_normal((N, Cf, h, w)) * 10).astype(np.float32); lg = (rng.standard_normal((N, 9 * st * st, h, w)) * 10.0 ** rng.uniform(-1, 1)).astype(np.float32)
