@@ -42,18 +42,22 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, hooks=False):
+    """hooks=True builds libezflow_b200_hooks.so with -DEZB_PROFILING_HOOKS (the GEMM's EZB_GEMM_DEBUG experiment switches,
+    tools/gemm_dbg.py); the shipped library is built without them."""
     os.makedirs(LIBDIR, exist_ok=True)
-    stamp = os.path.join(LIBDIR, "build.sha256")
+    libpath = LIBPATH.replace(".so", "_hooks.so") if hooks else LIBPATH
+    stamp = os.path.join(LIBDIR, "build_hooks.sha256" if hooks else "build.sha256")
     dig = _digest()
-    if not force and os.path.exists(LIBPATH) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
-        return LIBPATH
+    if not force and os.path.exists(libpath) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+        return libpath
     nvcc = _nvcc()
     objs = []
     procs = []
+    extra = ["-DEZB_PROFILING_HOOKS"] if hooks else []
     for src in SOURCES:
-        obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(LIBDIR, src.replace(".cu", "_hooks.o" if hooks else ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:
@@ -62,12 +66,12 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
-    cmd = [nvcc, "-shared", "-o", LIBPATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "-o", libpath] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     subprocess.check_call(cmd)
     with open(stamp, "w") as f:
         f.write(dig)
-    return LIBPATH
+    return libpath
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, hooks="--hooks" in sys.argv))

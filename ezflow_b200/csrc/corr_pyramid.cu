@@ -518,8 +518,14 @@ static int launch_gemm(const Workspace& ws, int B, int C, const PyrLayout& lay, 
   p.group_bytes = lay.group_bytes;
   p.epi_scale = ws.epi;
   p.pyr = static_cast<char*>(pyr);
+  // The profiling switches exist only in builds made with -DEZB_PROFILING_HOOKS (tools/gemm_dbg.py builds one under
+  // gpurun_out/); the shipped library ignores the environment, so nothing outside can make the product skip work.
+#ifdef EZB_PROFILING_HOOKS
   const char* dbg_env = getenv("EZB_GEMM_DEBUG");
   p.dbg = dbg_env ? atoi(dbg_env) : 0;
+#else
+  p.dbg = 0;
+#endif
 
   auto kern = corr_pyramid_gemm_kernel<OutT>;
   EZB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

@@ -1,8 +1,12 @@
 #!/usr/bin/env python
 """Profiling experiments on the GEMM kernel: time it with parts disabled (EZB_GEMM_DEBUG bit mask,
-see GemmParams::dbg).  Results with dbg != 0 are WRONG on purpose; this is a diagnosis tool only."""
+see GemmParams::dbg).  Results with dbg != 0 are WRONG on purpose; this is a diagnosis tool only.
+The switches exist only in the hooks build (python -m ezflow_b200.build --hooks, done here before the GPU run: nvcc
+cross-compiles without a GPU); the shipped library ignores EZB_GEMM_DEBUG."""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ezflow_b200 import build as _build
+os.environ["EZB_LIBRARY"] = _build.build(hooks=True)
 import torch
 from ezflow_b200 import _cabi
 from ezflow_b200.similarity import pairwise as PW
