@@ -38,11 +38,15 @@ class CorrelationLayer(nn.Module):
         }
 
     def forward(self, features1, features2):
-        if self.pad_size != self.max_h_disp:
-            # the reference slices features2 padded by pad_size with offsets 0..2*max_displacement; only the
-            # symmetric case (its default, and the only one it can run without shape errors when pad < disp)
-            # is a centred window.
-            raise NotImplementedError("CorrelationLayer on B200 supports pad_size == max_displacement only.")
+        if self.pad_size < self.max_h_disp:
+            # the reference's slices of features2 padded by pad_size run out of range: it cannot run this either
+            raise NotImplementedError("CorrelationLayer needs pad_size >= max_displacement (as the reference does).")
+        if self.pad_size > self.max_h_disp:
+            # reference layer.py:44-60: offsets 0..2d into features2 padded by pad_size, i.e. displacements -pad..2d-pad —
+            # an off-centre window.  Shifting features2 by (pad - d) pixels (zeros shifted in) turns it into the centred one.
+            s = self.pad_size - self.max_h_disp
+            H, W = features2.shape[-2:]
+            features2 = nn.functional.pad(features2, (s, 0, s, 0))[:, :, :H, :W]
         p = 2 * self.max_h_disp + 1
         c = features1.shape[1]
         out = iter_spatial_correlation_sample(features1, features2, patch_size=p, _scale=1.0 / c)

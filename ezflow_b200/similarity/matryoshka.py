@@ -55,7 +55,7 @@ class _MatryoshkaFn(torch.autograd.Function):
         G, P, stride, dilations, slope = ctx.cfg
         dout = dout.contiguous().float()
         if slope != 1.0:
-            dout = torch.where(out >= 0, dout, dout * slope)
+            dout = torch.where(out > 0, dout, dout * slope)  # F.leaky_relu's backward: the slope applies at exactly 0
         B, C, H, W = x1.shape
         x1g = x1.view(B * G, C // G, H, W)
         x2g = x2.view(B * G, C // G, H, W)

@@ -114,6 +114,7 @@ class _PyramidState:
         self.deq = None
         self.grad_levels = None
         self.grad_layout = None
+        self.grad_task = None  # autograd graph-task id of the backward pass that is filling grad_levels
 
     def build(self, ev_gemm=None):
         """ev_gemm: optional (start, end) raw cudaEvent handles recorded around the GEMM launch (bench only)."""
@@ -157,6 +158,13 @@ class _PyramidState:
         return out.view(len(queries), 1, h, w)
 
     def ensure_grad(self):
+        # A backward pass that never reached _BuildFn.backward (it raised half-way) leaves its partial sums behind; they must
+        # not leak into the next pass.  Every engine run has its own graph-task id.
+        task = torch._C._current_graph_task_id() if hasattr(torch._C, "_current_graph_task_id") else None
+        if self.grad_levels is not None and task != self.grad_task:
+            for g in self.grad_levels:
+                g.zero_()
+        self.grad_task = task
         if self.grad_levels is None:
             self.grad_layout = grad_layout(self.H, self.W, self.L)
             rows = self.B * self.N
@@ -171,15 +179,17 @@ class _BuildFn(torch.autograd.Function):
     def forward(ctx, fmap1, fmap2, state):
         state.build()
         ctx.state = state
+        ctx.save_for_backward(fmap1, fmap2)  # autograd's version check catches in-place edits between forward and backward
         return torch.zeros((), dtype=torch.float32, device=fmap1.device)
 
     @staticmethod
     def backward(ctx, _gtoken):
         st = ctx.state
+        fmap1, fmap2 = ctx.saved_tensors
         if st.grad_levels is None:  # no lookup contributed a gradient
-            return torch.zeros_like(st.fmap1), torch.zeros_like(st.fmap2), None
-        df1 = torch.empty_like(st.fmap1)
-        df2 = torch.empty_like(st.fmap2)
+            return torch.zeros_like(fmap1), torch.zeros_like(fmap2), None
+        df1 = torch.empty_like(fmap1)
+        df2 = torch.empty_like(fmap2)
         with torch.cuda.device(st.device):
             lib = _cabi.lib()
             nws = ctypes.c_size_t(0)
@@ -187,11 +197,11 @@ class _BuildFn(torch.autograd.Function):
             ws = torch.empty(nws.value, dtype=torch.uint8, device=st.device) if nws.value else None
             _cabi.check(
                 lib.ezb_corr_pyramid_bwd(
-                    _cabi.ptr_array(st.grad_levels), _cabi.ptr(st.fmap1), _cabi.ptr(st.fmap2), st.B, st.C, st.H, st.W, st.L,
+                    _cabi.ptr_array(st.grad_levels), _cabi.ptr(fmap1), _cabi.ptr(fmap2), st.B, st.C, st.H, st.W, st.L,
                     _cabi.ptr(df1), _cabi.ptr(df2), _cabi.ptr(ws), nws.value, _cabi.stream_ptr(st.device),
                 )
             )
-        st.grad_levels = None  # consumed
+        st.grad_levels, st.grad_task = None, None  # consumed
         return df1, df2, None
 
 
@@ -260,7 +270,7 @@ class MutliScalePairwise4DCorr:
             raise ValueError("num_levels must be >= 1")
         self._empty = f1.shape[0] == 0  # an empty batch yields empty lookups, as the reference's ops do
         if self._empty:
-            self._state, self._token, self._shape = None, None, tuple(f1.shape)
+            self._state, self._token, self._shape, self._device = None, None, tuple(f1.shape), f1.device
             return
         self._state = _PyramidState(f1.detach(), f2.detach(), num_levels, _PYRAMID_DTYPE)
         if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
@@ -275,6 +285,9 @@ class MutliScalePairwise4DCorr:
 
         The kernels keep the pyramid in a tiled layout, so these are dequantised *copies* gathered on
         demand (diagnostics / tests); nothing on the lookup path uses them."""
+        if self._empty:  # the reference's ops return empty tensors for an empty batch
+            _, _, H, W = self._shape
+            return [torch.zeros((0, 1, H >> l, W >> l), dtype=torch.float32, device=self._device) for l in range(int(self.num_levels))]
         st = self._state
         scale = st.deq.repeat_interleave(st.N).view(-1, 1, 1, 1)
         return [st.level_tensor(l).float() * scale for l in range(st.L)]
@@ -300,7 +313,9 @@ class MutliScalePairwise4DCorr:
 
     @staticmethod
     def corr(fmap1, fmap2):
-        """All-pairs correlation volume (B, H, W, 1, H, W) fp32 (pairwise.py:78-88), computed on tcgen05."""
+        """All-pairs correlation volume (B, H, W, 1, H, W) (pairwise.py:78-88), computed on tcgen05: fp16 operands with fp32
+        accumulation and fp32 storage, i.e. ~3e-4 relative to the reference's fp32 matmul.  Inference-only:
+        the result carries no autograd graph (gradients flow through the class's build + lookup path instead)."""
         f1 = _cabi.require_cuda_f32(fmap1, "fmap1")
         f2 = _cabi.require_cuda_f32(fmap2, "fmap2")
         st = _PyramidState(f1.detach(), f2.detach(), 1, "fp32")

@@ -14,7 +14,9 @@ import types
 
 import yaml
 
-REF_CANDIDATES = ["/root/reference", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")]
+_VENDORED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+# EZB_REFERENCE_ROOT pins one location (e.g. the vendored copy, to exercise what the GPU box will see)
+REF_CANDIDATES = [os.environ["EZB_REFERENCE_ROOT"]] if os.environ.get("EZB_REFERENCE_ROOT") else ["/root/reference", _VENDORED]
 
 
 class CfgNode(dict):

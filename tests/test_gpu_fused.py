@@ -136,3 +136,32 @@ def test_fuse_model_folds_the_activation():
     after = dec._corr_relu(f1, E.lazy_warp(f2, flow))
     assert tuple(after.shape) == (1, 81, 16, 24)
     assert_close(after, before, 1e-3, "fused decoder step vs unfused")
+
+
+def test_cancellation_dominated_case_absolute_bound(golden):
+    """Fixed regression case kept from the randomised sweep (tools/fuzz_parity.py, round 1): after the warp's mask only ONE
+    dot product survives and it is cancellation-dominated (0.22 against a dot-product scale of sqrt(C)*rms(x1)*rms(x2) = 234),
+    so an error relative to the result is meaningless for fp16 operands.  The bound that is asserted instead, written out:
+    |out - ref| <= 1e-3 * sqrt(C) * rms(x1) * rms(x2)   ('tc'; measured 2.9e-5 absolute = 1.2e-7 of that scale)
+    and the usual 5e-5 relative in 'exact' mode.  Masked-out pixels must be exact zeros in both modes."""
+    import ezflow_b200 as E
+
+    g = golden("fused_cancellation_case")
+    x1, x2, flow, ref = g["x1"], g["x2"], g["flow"], g["ref"]
+    P, s, pad, dp = (int(v) for v in g["params"])
+    slope = float(g["slope"])
+    C = x1.shape[1]
+    scale_dp = float(np.sqrt(C) * np.sqrt((x1.astype(np.float64) ** 2).mean()) * np.sqrt((x2.astype(np.float64) ** 2).mean()))
+    want = O.leaky_relu(O.iter_spatial_correlation_sample(x1, O.warp(x2, flow), patch_size=P, stride=s, padding=pad, dilation_patch=dp), slope)
+    np.testing.assert_allclose(want, ref, rtol=0, atol=1e-6)  # the stored reference output is the oracle's
+    old = E.get_local_corr_mode()
+    try:
+        for mode, bound in (("tc", 1e-3 * scale_dp), ("exact", 5e-5 * float(np.abs(ref).max()))):
+            E.set_local_corr_mode(mode)
+            out = _sampler(slope, patch_size=P, stride=s, padding=pad, dilation_patch=dp)(to_gpu(x1), E.lazy_warp(to_gpu(x2), to_gpu(flow))).cpu().numpy()
+            assert out.shape == ref.shape
+            assert not np.any(out[ref == 0]), f"{mode}: masked-out pixels must be exact zeros"
+            err = float(np.abs(out.astype(np.float64) - ref).max())
+            assert err <= bound, f"{mode}: abs error {err:.3e} > {bound:.3e}"
+    finally:
+        E.set_local_corr_mode(old)

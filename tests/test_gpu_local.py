@@ -214,6 +214,58 @@ def test_empty_batch_returns_empty_outputs():
     assert tuple(E.convex_upsample_flow(fl, torch.zeros(0, 576, 12, 20, device=dev()), 8).shape) == (0, 2, 96, 160)
     fn = E.MutliScalePairwise4DCorr(z, z, num_levels=2, corr_radius=3)
     assert tuple(fn(fl).shape) == (0, 2 * 49, 12, 20)
+    assert [tuple(t.shape) for t in fn.corr_pyramid] == [(0, 1, 12, 20), (0, 1, 6, 10)]  # reference pairwise.py:31-41 on B = 0
+
+
+def test_matryoshka_relu_backward_at_exact_zero_costs():
+    """use_relu=True where in-image costs are EXACTLY zero (all-zero feature pixels): F.leaky_relu's backward applies the
+    slope at 0 (x > 0 selects the identity branch), reference learnable_cost.py:322-323."""
+    import ezflow_b200 as E
+    import torch.nn.functional as F
+
+    rng = np.random.default_rng(9)
+    x1 = rng.standard_normal((1, 8, 9, 11)).astype(np.float32)
+    x2 = rng.standard_normal((1, 8, 9, 11)).astype(np.float32)
+    x1[:, :, 2:5, 3:7] = 0.0  # every cost of these queries is exactly 0
+    x2[:, :, 6, :] = 0.0
+    m = E.MatryoshkaDilatedCostVolume(num_groups=2, max_displacement=1, dilations=[1, 2], use_relu=True).to(dev())
+    old = E.get_local_corr_mode()
+    E.set_local_corr_mode("exact")
+    try:
+        a, b = to_gpu(x1, True), to_gpu(x2, True)
+        out = m(a, b)
+        dout = to_gpu(rng.standard_normal(tuple(out.shape)).astype(np.float32))
+        (out * dout).sum().backward()
+        # comparator: the un-activated volume from the same kernels, then PyTorch's own leaky_relu (forward and backward)
+        m_lin = E.MatryoshkaDilatedCostVolume(num_groups=2, max_displacement=1, dilations=[1, 2], use_relu=False).to(dev())
+        a2, b2 = to_gpu(x1, True), to_gpu(x2, True)
+        ref = F.leaky_relu(m_lin(a2, b2), 0.1)
+        assert (ref == 0).sum().item() > 100
+        (ref * dout).sum().backward()
+        assert_close(out, ref, 2e-5, "matryoshka relu fwd")
+        assert_close(a.grad, a2.grad, 2e-5, "matryoshka relu dx1 at zero costs")
+        assert_close(b.grad, b2.grad, 2e-5, "matryoshka relu dx2 at zero costs")
+    finally:
+        E.set_local_corr_mode(old)
+
+
+def test_correlation_layer_pad_larger_than_displacement(mode):
+    """pad_size > max_displacement: the reference (layer.py:44-60) slices features2 padded by pad_size with offsets 0..2d,
+    an off-centre window; restated here with the same slices in PyTorch."""
+    import ezflow_b200 as E
+    import torch.nn.functional as F
+
+    rng = np.random.default_rng(4)
+    x1 = to_gpu(rng.standard_normal((2, 24, 10, 13)).astype(np.float32))
+    x2 = to_gpu(rng.standard_normal((2, 24, 10, 13)).astype(np.float32))
+    pad, d = 5, 2
+    H, W = x1.shape[-2:]
+    x2p = F.pad(x2, (pad, pad, pad, pad))
+    ref = torch.cat([(x1 * x2p[:, :, dy : dy + H, dx : dx + W]).mean(1, keepdim=True) for dy in range(2 * d + 1) for dx in range(2 * d + 1)], 1)
+    out = E.CorrelationLayer(pad_size=pad, max_displacement=d)(x1, x2)
+    assert_close(out, ref, FWD_TOL[mode], "CorrelationLayer pad 5 / displacement 2")
+    with pytest.raises(NotImplementedError):
+        E.CorrelationLayer(pad_size=1, max_displacement=2)(x1, x2)
 
 
 def _torch_sampler(x1, x2, patch, stride=1, padding=0, dp=1):

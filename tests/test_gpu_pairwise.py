@@ -282,3 +282,58 @@ def test_full_size_is_deterministic():
     ref = E.MutliScalePairwise4DCorr(f1, f2)(c)
     for _ in range(3):
         assert torch.equal(E.MutliScalePairwise4DCorr(f1, f2)(c), ref)
+
+
+def test_inplace_edit_between_forward_and_backward_raises():
+    """The feature maps are saved through autograd (save_for_backward), so modifying them in place before backward()
+    trips PyTorch's version check exactly as it does for the reference's matmul."""
+    import ezflow_b200 as E
+
+    rng = np.random.default_rng(2)
+    f1 = to_gpu(rng.standard_normal((1, 16, 8, 12)).astype(np.float32), True)
+    f2 = to_gpu(rng.standard_normal((1, 16, 8, 12)).astype(np.float32), True)
+    a, b = f1 * 1.0, f2 * 1.0  # non-leaf tensors that may be edited in place
+    fn = E.MutliScalePairwise4DCorr(a, b, num_levels=2, corr_radius=2)
+    out = fn(E.coords_grid(1, 8, 12).to(dev()))
+    a.add_(1.0)
+    with pytest.raises(RuntimeError, match="modified by an inplace operation"):
+        out.sum().backward()
+
+
+def test_aborted_backward_leaves_no_stale_gradient():
+    """A backward pass that raises after some lookup adjoints already accumulated must not leak into the next pass."""
+    import ezflow_b200 as E
+
+    rng = np.random.default_rng(3)
+    x1 = rng.standard_normal((1, 16, 8, 12)).astype(np.float32)
+    x2 = rng.standard_normal((1, 16, 8, 12)).astype(np.float32)
+    coords = E.coords_grid(1, 8, 12).to(dev()) + 0.3
+
+    class Boom(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, t):
+            return t.clone()
+
+        @staticmethod
+        def backward(ctx, g):
+            raise ValueError("boom")
+
+    def grads(with_abort):
+        f1, f2 = to_gpu(x1, True), to_gpu(x2, True)
+        fn = E.MutliScalePairwise4DCorr(f1, f2, num_levels=2, corr_radius=2)
+        if with_abort:
+            # the engine runs later-created nodes first: the lookup adjoint fills the accumulator, then Boom (created before
+            # the lookup) aborts the pass before the pyramid adjoint has consumed it
+            boom = Boom.apply(fn._token * 1.0)
+            out = fn(coords)
+            with pytest.raises(ValueError):
+                (out.sum() + boom).backward()
+            assert fn._state.grad_levels is not None  # the aborted pass did leave partial sums behind
+            f1.grad = f2.grad = None
+        fn(coords).sum().backward()
+        return f1.grad.clone(), f2.grad.clone()
+
+    g1, g2 = grads(False)
+    h1, h2 = grads(True)
+    assert_close(h1, g1, 1e-6, "df1 after an aborted pass")
+    assert_close(h2, g2, 1e-6, "df2 after an aborted pass")

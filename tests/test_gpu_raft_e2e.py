@@ -10,50 +10,19 @@ Here the 12-iteration loop (reference ezflow/models/raft.py:96-129) is run on th
   (b) the CUDA path through the drop-in class,
 so that conv-backend differences between the CPU run and the GPU cancel in (a) vs (b)."""
 
-import math
 import os
 
 import numpy as np
 import pytest
 import torch
-import torch.nn.functional as F
 
-from gpu_util import dev
+from gpu_util import TorchPairwiseRef, dev
 
 pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PARTS = os.path.join(ROOT, "oracle", "_ref", "raft_cfg1_parts.pt")
 EPE_TOL = 0.01  # px, mean end-point error of the final upsampled flow (north_star)
-
-
-class TorchPairwiseRef:
-    """fp32 PyTorch restatement of MutliScalePairwise4DCorr (reference pairwise.py:26-88, resampling.py:56-85)."""
-
-    def __init__(self, fmap1, fmap2, num_levels, corr_radius):
-        b, c, h, w = fmap1.shape
-        corr = torch.matmul(fmap1.view(b, c, h * w).transpose(1, 2), fmap2.view(b, c, h * w)) / math.sqrt(float(c))
-        corr = corr.reshape(b * h * w, 1, h, w)
-        self.levels = [corr]
-        for _ in range(num_levels - 1):
-            self.levels.append(F.avg_pool2d(self.levels[-1], 2, stride=2))
-        self.r = corr_radius
-
-    def __call__(self, coords):
-        b, _, h, w = coords.shape
-        r = self.r
-        c = coords.permute(0, 2, 3, 1).reshape(b * h * w, 1, 1, 2)
-        d = torch.linspace(-r, r, 2 * r + 1, device=coords.device)
-        delta = torch.stack(torch.meshgrid(d, d, indexing="ij"), dim=-1).view(1, 2 * r + 1, 2 * r + 1, 2)
-        out = []
-        for l, lvl in enumerate(self.levels):
-            hl, wl = lvl.shape[-2:]
-            pos = c / 2**l + delta  # first window index offsets x (reference quirk)
-            gx = 2 * pos[..., 0] / (wl - 1) - 1
-            gy = 2 * pos[..., 1] / (hl - 1) - 1
-            s = F.grid_sample(lvl, torch.stack([gx, gy], dim=-1), align_corners=True)
-            out.append(s.view(b, h, w, -1))
-        return torch.cat(out, dim=-1).permute(0, 3, 1, 2).contiguous().float()
 
 
 def _run(parts, corr_cls, img1, img2, levels, radius, iters):

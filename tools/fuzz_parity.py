@@ -88,7 +88,10 @@ for i in range(n_cases):
             # C-term dot product of these inputs instead of against the (accidentally small) results
             scale_dp = float(np.sqrt(C) * np.sqrt((x1.astype(np.float64) ** 2).mean()) * np.sqrt((x2.astype(np.float64) ** 2).mean()))
             rf = mr = float(np.abs(out.astype(np.float64) - ref).max() / max(np.abs(ref).max(), scale_dp))
-        if not (rf <= tol and mr <= tol) and np.abs(ref).max() > 0:
+        if np.abs(ref).max() == 0:
+            # the warp masks every pixel out: the fused kernel must write exact zeros, not just anything
+            rf = mr = 0.0 if (out.shape == ref.shape and not np.any(out)) else 9.0
+        if not (rf <= tol and mr <= tol):
             fails += 1
             print("FAIL fused", mode, (B, C, H, W, P, s, pad, dp, slope), rf, mr, "nnz", int(np.count_nonzero(ref)),
                   "max|ref|", float(np.abs(ref).max()), "max|flow|", float(np.abs(flow).max()))
