@@ -41,14 +41,16 @@ class CorrelationLayer(nn.Module):
         if self.pad_size < self.max_h_disp:
             # the reference's slices of features2 padded by pad_size run out of range: it cannot run this either
             raise NotImplementedError("CorrelationLayer needs pad_size >= max_displacement (as the reference does).")
-        if self.pad_size > self.max_h_disp:
+        shift = self.pad_size - self.max_h_disp
+        if shift > 0:
             # reference layer.py:44-60: offsets 0..2d into features2 padded by pad_size, i.e. displacements -pad..2d-pad —
-            # an off-centre window.  Shifting features2 by (pad - d) pixels (zeros shifted in) turns it into the centred one.
-            s = self.pad_size - self.max_h_disp
-            H, W = features2.shape[-2:]
-            features2 = nn.functional.pad(features2, (s, 0, s, 0))[:, :, :H, :W]
+            # an off-centre window.  On canvases grown by `shift` (features1 at the top-left, features2 at the bottom-right)
+            # it is the centred window; the extra output rows / columns are cropped below.
+            features1 = nn.functional.pad(features1, (0, shift, 0, shift))
+            features2 = nn.functional.pad(features2, (shift, 0, shift, 0))
         p = 2 * self.max_h_disp + 1
         c = features1.shape[1]
         out = iter_spatial_correlation_sample(features1, features2, patch_size=p, _scale=1.0 / c)
         b, _, _, h, w = out.shape
-        return out.view(b, p * p, h, w)
+        out = out.view(b, p * p, h, w)
+        return out[:, :, : h - shift, : w - shift].contiguous() if shift > 0 else out

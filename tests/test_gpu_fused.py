@@ -143,7 +143,9 @@ def test_cancellation_dominated_case_absolute_bound(golden):
     dot product survives and it is cancellation-dominated (0.22 against a dot-product scale of sqrt(C)*rms(x1)*rms(x2) = 234),
     so an error relative to the result is meaningless for fp16 operands.  The bound that is asserted instead, written out:
     |out - ref| <= 1e-3 * sqrt(C) * rms(x1) * rms(x2)   ('tc'; measured 2.9e-5 absolute = 1.2e-7 of that scale)
-    and the usual 5e-5 relative in 'exact' mode.  Masked-out pixels must be exact zeros in both modes."""
+    and 1e-6 of the same scale in 'exact' mode (fp32 rounding of a 130-term sum whose terms are ~20; measured 2.9e-5 absolute
+    there too: the difference to the float64 oracle is fp32 rounding in the warp and the sum, not the operand precision).
+    Masked-out pixels must be exact zeros in both modes."""
     import ezflow_b200 as E
 
     g = golden("fused_cancellation_case")
@@ -156,7 +158,7 @@ def test_cancellation_dominated_case_absolute_bound(golden):
     np.testing.assert_allclose(want, ref, rtol=0, atol=1e-6)  # the stored reference output is the oracle's
     old = E.get_local_corr_mode()
     try:
-        for mode, bound in (("tc", 1e-3 * scale_dp), ("exact", 5e-5 * float(np.abs(ref).max()))):
+        for mode, bound in (("tc", 1e-3 * scale_dp), ("exact", 1e-6 * scale_dp)):
             E.set_local_corr_mode(mode)
             out = _sampler(slope, patch_size=P, stride=s, padding=pad, dilation_patch=dp)(to_gpu(x1), E.lazy_warp(to_gpu(x2), to_gpu(flow))).cpu().numpy()
             assert out.shape == ref.shape

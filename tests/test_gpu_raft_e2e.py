@@ -68,3 +68,5 @@ def test_raft_cfg1_final_flow_epe(golden):
     # the GPU re-run of the reference pipeline itself differs from its CPU run only by conv/GEMM backend rounding;
     # the CUDA path must not be further from the reference's own output than that plus the tolerance
     assert epe_gold_new <= epe_gold_ref + EPE_TOL
+    # and directly (north_star): CUDA path on the GPU vs the reference's own CPU run, CPU-vs-GPU convolution rounding included
+    assert epe_gold_new <= EPE_TOL, f"mean EPE vs the reference's CPU run {epe_gold_new:.4f} px > {EPE_TOL}"

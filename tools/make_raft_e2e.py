@@ -110,7 +110,7 @@ def main():
     torch.jit.save(torch.jit.script(holder), parts)
     print("wrote", parts, "%.1f MB" % (os.path.getsize(parts) / 1e6))
     gold = os.path.join(ROOT, "tests", "golden", "raft_e2e.npz")
-    np.savez_compressed(gold, img1=u1.numpy(), img2=u2.numpy(), flow=flow.numpy().astype(np.float16),
+    np.savez_compressed(gold, img1=u1.numpy(), img2=u2.numpy(), flow=flow.numpy().astype(np.float32),
                         levels=model.corr_levels, radius=model.corr_radius, iters=ITERS)
     print("wrote", gold, "%.0f KiB" % (os.path.getsize(gold) / 1024))
 
