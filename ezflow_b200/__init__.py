@@ -11,6 +11,9 @@ from .registry import SIMILARITY_REGISTRY, build_similarity
 from .similarity import (
     CorrelationLayer,
     IterSpatialCorrelationSampler,
+    LazyLookup,
+    LazyLookupPairwise4DCorr,
+    LookupConv2d,
     MatryoshkaDilatedCostVolume,
     MatryoshkaDilatedCostVolumeList,
     MutliScalePairwise4DCorr,
@@ -19,6 +22,7 @@ from .similarity import (
     get_pyramid_dtype,
     iter_spatial_correlation_sample,
     lazy_warp,
+    lookup_conv1x1,
     set_local_corr_mode,
     set_pyramid_dtype,
 )

@@ -1,0 +1,417 @@
+// K3 + convc1 fused: radius-r pyramid lookup -> 1x1 convolution (+ bias, ReLU) in ONE kernel.
+//
+// Replaces, for RAFT's update block, the pair
+//   corr = MutliScalePairwise4DCorr.__call__(coords)      ezflow/similarity/correlation/pairwise.py:43-69
+//   cor  = F.relu(self.convc1(corr))                      ezflow/decoder/iterative/recurrent_lookup.py:182,204
+// (convc1 = Conv2d(L*(2r+1)^2, 256, 1); SmallMotionEncoder: 96 outputs, :153) so that the (B, L*(2r+1)^2, H, W) lookup
+// features — 42 MB per 1080p pair and iteration — are never written to HBM nor re-read by the convolution.
+//
+// A 1x1 convolution is a GEMM over the channel axis:  out[b, n, q] = act( sum_k Wt[n, k] * feat[b, k, q] + bias[n] ).
+// Per tile of 128 queries the lookup features are produced level by level straight into a shared-memory A operand
+// (fp16, K-major, SWIZZLE_64B; one level = 81 taps padded to 96 = 3 k-blocks of 32) and one tcgen05.mma chain per level
+// accumulates against that level's slice of the weights (TMA, L2-resident) into a 128 x Cout fp32 accumulator in
+// tensor memory.  The epilogue applies the scales, bias and ReLU and stores NCHW with 128-byte coalesced rows.
+//
+//   warps 0-7   gather (cp.async windows of the NEXT (tile, level) stage) + bilinear taps of the current stage -> A
+//   warps 8-11  epilogue (one TMEM lane quadrant each)
+//   warp  12    weight-slice TMA + MMA issue (one elected lane), TMEM allocation
+//
+// Values: A holds the STORED pyramid domain (fp16 storage scale), the weights are pre-scaled by a power of two into
+// (-2, 2); out = act(acc * deq_scale[b] * wscale + bias).  fp16 operands / fp32 accumulation: <= 1e-3 relative to the
+// fp32 chain (tests/test_gpu_lookup_conv.py).  fp16 pyramids only (the default); callers fall back to the two
+// kernels otherwise.
+#include "ezb_common.cuh"
+#include "ezb_ptx.cuh"
+#include "ezb_tma.cuh"
+
+namespace ezb {
+namespace k3c {
+
+constexpr int TQ = 128;                 // queries per tile = UMMA M = TMEM lanes
+constexpr int MAX_R = 4;                // (2r+1)^2 <= 81 taps per level
+constexpr int KL = 96;                  // K slots per level (81 padded to a multiple of UMMA_K = 16)
+constexpr int KB_EL = 32;               // fp16 elements per SWIZZLE_64B row
+constexpr int KBS = KL / KB_EL;         // k-blocks per level (3)
+constexpr int N_MAX = 256;              // output channels (UMMA N)
+constexpr int A_KB_BYTES = TQ * 64;     // 8 KB
+constexpr int B_KB_BYTES = N_MAX * 64;  // 16 KB
+constexpr int ROW_EL = 24;              // fetched pixels per window row: 3 chunks of 8 (covers 2r+2 <= 10 taps at any alignment)
+constexpr int QSTRIDE = 496;            // bytes per query in a staging buffer: 10 rows x 48 B = 480, odd number of 16-byte chunks
+constexpr int STG_BYTES = TQ * QSTRIDE; // 63488
+constexpr int COMPUTE_WARPS = 8, EPI_WARPS = 4;
+constexpr int NUM_THREADS = (COMPUTE_WARPS + EPI_WARPS + 1) * 32;  // 416
+constexpr int SMEM_STG = 0;
+constexpr int SMEM_A = SMEM_STG + 2 * STG_BYTES;           // 126976
+constexpr int SMEM_B = SMEM_A + 2 * KBS * A_KB_BYTES;      // + 49152
+constexpr int SMEM_BIAS = SMEM_B + KBS * B_KB_BYTES;       // + 49152
+constexpr int SMEM_BAR = SMEM_BIAS + N_MAX * 4;
+constexpr int SMEM_BYTES = SMEM_BAR + 128 + 1024;
+static_assert(SMEM_A % 1024 == 0 && SMEM_B % 1024 == 0 && SMEM_BYTES <= 232448, "shared-memory plan");
+
+struct Params {
+  const char* pyr;
+  int H, W, N, L, r, B;
+  int sw[PYR_MAX_LEVELS], sub_base[PYR_MAX_LEVELS];
+  int n_tiles, n_groups;
+  long long group_bytes;
+  const float* deq;     // [B]
+  const float* coords;  // (B,2,N)
+  const float* wscale;  // [1]
+  const float* bias;    // [Cout] or null
+  float* out;           // (B, Cout, N)
+  int Cout, Np;         // Np = Cout rounded up to 16 (UMMA N)
+  int relu;
+  int tiles_per_pair, n_work;
+};
+
+__device__ __forceinline__ int floor_clamped(float v) {
+  float f = floorf(v);
+  f = fminf(fmaxf(f, -16777216.f), 16777216.f);
+  return (f == f) ? (int)f : -(1 << 24);
+}
+__device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void compute_bar() { asm volatile("bar.sync 1, %0;" ::"n"(COMPUTE_WARPS * 32) : "memory"); }
+
+// K-major SWIZZLE_64B shared-memory matrix descriptor: rows of 64 B, 8-row groups 512 B apart
+__device__ __forceinline__ uint64_t umma_desc_kmajor_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;  // SWIZZLE_64B
+  return d;
+}
+// byte offset of element (row, k) inside one level's A operand (KBS k-blocks of [TQ rows][32 fp16], SWIZZLE_64B:
+// the 16-byte chunk index is XORed with address bits [7,9) = (row >> 1) & 3)
+__device__ __forceinline__ uint32_t a_offset(int row, int k) {
+  const int kb = k >> 5, kk = k & 31;
+  return (uint32_t)(kb * A_KB_BYTES + row * 64 + ((((kk >> 3) ^ (row >> 1)) & 3) << 4) + (kk & 7) * 2);
+}
+
+// weights (Cout, L*KK) fp32 -> (N_MAX rows, L*KL) fp16 scaled by 2^-e (e = floor(log2 max|W|)); k slot l*KL + t holds input
+// channel l*KK + t, everything else is zero.  One block; wscale[0] = 2^e.
+__global__ void __launch_bounds__(1024) pack_weights_kernel(const float* __restrict__ w, int Cout, int KK, int L, __half* __restrict__ wp,
+                                                            float* __restrict__ wscale) {
+  __shared__ float red[32];
+  const int cin = L * KK, total = Cout * cin;
+  float m = 0.f;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) m = fmaxf(m, fabsf(w[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, red[i]);
+  const int eb = (int)((__float_as_uint(m) >> 23) & 0xff);
+  const int e = (eb == 0 || eb == 255) ? 0 : max(-126, min(126, eb - 127));
+  const float s = __uint_as_float((unsigned int)(127 - e) << 23);
+  if (threadIdx.x == 0) wscale[0] = __uint_as_float((unsigned int)(127 + e) << 23);
+  const int kp = L * KL;
+  for (int i = threadIdx.x; i < N_MAX * kp; i += blockDim.x) {
+    const int n = i / kp, k = i - n * kp, l = k / KL, t = k - l * KL;
+    wp[i] = __float2half_rn((n < Cout && t < KK) ? w[(long long)n * cin + l * KK + t] * s : 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) lookup_conv1x1_kernel(const __grid_constant__ CUtensorMap tmW, const Params P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw_addr);
+  const uint32_t sStg = base + SMEM_STG, sA = base + SMEM_A, sB = base + SMEM_B, sBar = base + SMEM_BAR;
+  float* s_bias = reinterpret_cast<float*>(base_ptr + SMEM_BIAS);
+  auto a_full = [&](int i) { return sBar + 8u * i; };         // 2
+  auto a_empty = [&](int i) { return sBar + 8u * (2 + i); };  // 2
+  const uint32_t b_full = sBar + 8u * 4, b_empty = sBar + 8u * 5;
+  auto d_full = [&](int i) { return sBar + 8u * (6 + i); };   // 2
+  auto d_empty = [&](int i) { return sBar + 8u * (8 + i); };  // 2
+  volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + SMEM_BAR + 8 * 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = P.r, D = 2 * r + 2, K = 2 * r + 1;
+
+  if (warp == 12) {
+    if (lane == 0) {
+      ptx::prefetch_tmap(&tmW);
+      for (int i = 0; i < 2; ++i) {
+        ptx::mbar_init(a_full(i), COMPUTE_WARPS);
+        ptx::mbar_init(a_empty(i), 1);
+        ptx::mbar_init(d_full(i), 1);
+        ptx::mbar_init(d_empty(i), EPI_WARPS);
+      }
+      ptx::mbar_init(b_full, 1);
+      ptx::mbar_init(b_empty, 1);
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_ptr_slot)), 512);
+    ptx::tmem_relinquish();
+  }
+  // zero both A buffers once: the K slots [KK, KL) of every level are never written again
+  for (int i = threadIdx.x; i < 2 * KBS * A_KB_BYTES / 16; i += NUM_THREADS)
+    reinterpret_cast<uint4*>(base_ptr + SMEM_A)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < N_MAX; i += NUM_THREADS) s_bias[i] = (P.bias != nullptr && i < P.Cout) ? __ldg(P.bias + i) : 0.f;
+  fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_slot;
+
+  const int n_my = (P.n_work - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
+  const int n_stages = n_my * P.L;
+
+  if (warp < COMPUTE_WARPS) {
+    // ================================ gather + taps ================================
+    // stage s = (tile ti = s / L of this CTA, level l = s % L).  Iteration s: wait for stage s's windows, issue the
+    // copies of stage s + 1 into the other staging buffer, compute stage s into A[s & 1].
+    auto issue_gather = [&](int s) {
+      const int ti = s / P.L, l = s - ti * P.L;
+      const int work = (int)blockIdx.x + ti * (int)gridDim.x;
+      const int b = work / P.tiles_per_pair, q0 = (work - b * P.tiles_per_pair) * TQ;
+      const float* cx_ptr = P.coords + (long long)b * 2 * P.N;
+      const float* cy_ptr = cx_ptr + P.N;
+      const uint32_t stg = sStg + (uint32_t)(s & 1) * STG_BYTES;
+      const float inv = 1.0f / (float)(1 << l);
+      const int hl = P.H >> l, wl = P.W >> l;
+      // lanes 0..15: window origin of query warp*16 + lane of the tile
+      int org_packed;
+      {
+        const int q = min(q0 + warp * 16 + (lane & 15), P.N - 1);
+        const int x0 = floor_clamped(__ldg(cx_ptr + q) * inv), y0 = floor_clamped(__ldg(cy_ptr + q) * inv);
+        const int ox = max(-D, min(wl, x0 - r)), oy = max(-D, min(hl, y0 - r));
+        org_packed = ((((ox + 64) >> 3) - 8) << 16) | (oy & 0xffff);  // first 8-pixel chunk, first row
+      }
+      const int ng = (7 + D + 7) >> 3;  // chunks per window row (3 for r = 4)
+      const int row = lane / ng >= D ? 0 : lane / ng, gi = lane - (lane / ng) * ng;
+      const bool task_ok = lane < D * ng;
+      const unsigned int tile_stride = (unsigned int)(P.n_groups * P.group_bytes);
+      const char* pair_base = P.pyr + (long long)b * P.n_tiles * P.n_groups * P.group_bytes;
+#pragma unroll 4
+      for (int qi = 0; qi < 16; ++qi) {
+        const int pk = __shfl_sync(0xffffffffu, org_packed, qi);
+        if (task_ok) {
+          const int ql = warp * 16 + qi;  // query inside the tile
+          const int q = min(q0 + ql, P.N - 1);
+          const int y = (int)(short)(pk & 0xffff) + row;
+          const int xg = ((pk >> 16) + gi) * 8;
+          const char* src = pair_base;
+          uint32_t nbytes = 0;
+          if ((unsigned)y < (unsigned)hl && (unsigned)xg < (unsigned)wl) {
+            const unsigned sidx = (unsigned)(P.sub_base[l] + (y / PYR_SY) * P.sw[l] + xg / PYR_SX);
+            const int col = (int)(sidx % PYR_SUBS_PER_TILE) * PYR_SUB + (y % PYR_SY) * PYR_SX + xg % PYR_SX;
+            src = pair_base + (unsigned long long)(sidx / PYR_SUBS_PER_TILE) * tile_stride + (long long)(q >> 5) * P.group_bytes +
+                  (unsigned)pyr_record_offset(2, q & 31, col);
+            nbytes = 16;
+          }
+          cp_async_16(stg + ql * QSTRIDE + (row * ROW_EL + gi * 8) * 2, src, nbytes);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    if (n_stages > 0) issue_gather(0);
+    const int gq = warp & 3, half = warp >> 2;
+    const int qrow = gq * 32 + lane;  // A row / TMEM lane of this thread's query
+    for (int s = 0; s < n_stages; ++s) {
+      const int ti = s / P.L, l = s - ti * P.L;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      compute_bar();  // stage s has landed for every thread; everybody is done reading stage s - 1
+      if (s + 1 < n_stages) issue_gather(s + 1);
+
+      const int work = (int)blockIdx.x + ti * (int)gridDim.x;
+      const int b = work / P.tiles_per_pair, q0 = (work - b * P.tiles_per_pair) * TQ;
+      const int q = min(q0 + qrow, P.N - 1);
+      const float* cx_ptr = P.coords + (long long)b * 2 * P.N;
+      const float inv = 1.0f / (float)(1 << l);
+      const float cx = __ldg(cx_ptr + q) * inv, cy = __ldg(cx_ptr + P.N + q) * inv;
+      const float fx = cx - floorf(cx), fy = cy - floorf(cy);
+      const float wl0 = 1.f - fx, wl1 = fx;
+      const int xs = max(-D, min(P.W >> l, floor_clamped(cx) - r));
+      const int off = xs - ((((xs + 64) >> 3) - 8) << 3);  // taps start `off` pixels into the fetched row
+      const __half* pl = reinterpret_cast<const __half*>(base_ptr + SMEM_STG + (s & 1) * STG_BYTES + qrow * QSTRIDE) + off;
+      // this warp's share of the window columns i: the two halves alternate between ceil(K/2) and floor(K/2) by level
+      const int isplit = (K + ((l & 1) ? 0 : 1)) >> 1;
+      const int i0 = half ? isplit : 0, i1 = half ? K : isplit;
+
+      const int abuf = s & 1;
+      ptx::mbar_wait(a_empty(abuf), (((uint32_t)s >> 1) & 1u) ^ 1u);  // the MMAs that read this buffer two stages ago are done
+      uint8_t* arow = base_ptr + SMEM_A + abuf * (KBS * A_KB_BYTES);
+      int k = i0 * K;
+      float held = 0.f;  // value of an even k waiting for its odd partner (one 4-byte store per pair)
+      for (int i = i0; i < i1; ++i) {
+        const __half* p = pl + i;
+        float top = wl0 * __half2float(p[0]) + wl1 * __half2float(p[1]);
+        for (int j = 0; j < K; ++j, ++k) {
+          p += ROW_EL;
+          const float bot = wl0 * __half2float(p[0]) + wl1 * __half2float(p[1]);
+          const float v = top + fy * (bot - top);
+          top = bot;
+          if (k & 1) {
+            if (k == i0 * K) {  // the run starts on an odd k: lone element
+              *reinterpret_cast<__half*>(arow + a_offset(qrow, k)) = __float2half_rn(v);
+            } else {
+              *reinterpret_cast<__half2*>(arow + a_offset(qrow, k - 1)) = __floats2half2_rn(held, v);
+            }
+          } else {
+            held = v;
+          }
+        }
+      }
+      if (i1 > i0 && (k & 1)) *reinterpret_cast<__half*>(arow + a_offset(qrow, k - 1)) = __float2half_rn(held);  // the run ended on an even k
+      fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(a_full(abuf));
+    }
+  } else if (warp == 12) {
+    // ================================ weight TMA + MMA issue ================================
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc(/*f16*/ 0, TQ, (uint32_t)P.Np);
+      for (int s = 0; s < n_stages; ++s) {
+        const int ti = s / P.L, l = s - ti * P.L;
+        ptx::mbar_wait(b_empty, ((uint32_t)s & 1u) ^ 1u);  // MMAs of stage s - 1 (the previous user of the weight buffer) are done
+        ptx::mbar_expect_tx(b_full, (uint32_t)(KBS * B_KB_BYTES));
+        for (int kb = 0; kb < KBS; ++kb)
+          ptx::tma_load_2d_hint(sB + kb * B_KB_BYTES, &tmW, b_full, l * KL + kb * KB_EL, 0, ptx::kEvictLast);
+        const int dbuf = ti & 1;
+        if (l == 0) {
+          ptx::mbar_wait(d_empty(dbuf), (((uint32_t)ti >> 1) & 1u) ^ 1u);
+          ptx::tc_fence_after();
+        }
+        ptx::mbar_wait(b_full, (uint32_t)s & 1u);
+        ptx::mbar_wait(a_full(s & 1), ((uint32_t)s >> 1) & 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + dbuf * N_MAX;
+        const uint32_t a_base = sA + (s & 1) * (KBS * A_KB_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < KBS; ++kb) {
+          const uint64_t a_desc = umma_desc_kmajor_sw64(a_base + kb * A_KB_BYTES);
+          const uint64_t b_desc = umma_desc_kmajor_sw64(sB + kb * B_KB_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < KB_EL / 16; ++kk) ptx::umma_f16(d_tmem, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (l | kb | kk) != 0);
+        }
+        ptx::umma_commit(a_empty(s & 1));
+        ptx::umma_commit(b_empty);
+        if (l == P.L - 1) ptx::umma_commit(d_full(dbuf));
+      }
+    }
+  } else {
+    // ================================ epilogue: lane = query ================================
+    const int quad = warp - COMPUTE_WARPS;  // warps 8..11 -> TMEM lane quadrants 0..3 (warp % 4)
+    const float wscale = __ldg(P.wscale);
+    for (int ti = 0; ti < n_my; ++ti) {
+      const int work = (int)blockIdx.x + ti * (int)gridDim.x;
+      const int b = work / P.tiles_per_pair, q0 = (work - b * P.tiles_per_pair) * TQ;
+      const int q = q0 + quad * 32 + lane;
+      const float sc = __ldg(P.deq + b) * wscale;
+      const int dbuf = ti & 1;
+      ptx::mbar_wait(d_full(dbuf), ((uint32_t)ti >> 1) & 1u);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + dbuf * N_MAX + ((uint32_t)(quad * 32) << 16);
+      float* o = P.out + (long long)b * P.Cout * P.N + q;
+      for (int c0 = 0; c0 < P.Np; c0 += 32) {
+        uint32_t v[32];
+        if (c0 + 32 <= P.Np) {
+          ptx::tmem_ld_32x32b_x32(taddr + c0, v);
+        } else {  // Np is a multiple of 16
+          uint32_t v16[16];
+          ptx::tmem_ld_32x32b_x16(taddr + c0, v16);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = v16[j];
+#pragma unroll
+          for (int j = 16; j < 32; ++j) v[j] = 0u;
+        }
+        ptx::tmem_ld_wait();
+        if (c0 + 32 >= P.Np) {  // the accumulator is in registers: hand it back to the MMA warp
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(d_empty(dbuf));
+        }
+        if (q < P.N) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = c0 + j;
+            if (n < P.Cout) {
+              float y = fmaf(__uint_as_float(v[j]), sc, s_bias[n]);
+              if (P.relu) y = fmaxf(y, 0.f);
+              o[(long long)n * P.N] = y;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 12) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace k3c
+}  // namespace ezb
+
+using namespace ezb;
+
+extern "C" int ezb_lookup_conv_packed_weight_bytes(int L, size_t* bytes) {
+  EZB_REQUIRE(L >= 1 && L <= PYR_MAX_LEVELS && bytes, "bad arguments");
+  *bytes = (size_t)k3c::N_MAX * L * k3c::KL * 2;
+  return EZB_OK;
+}
+
+extern "C" int ezb_lookup_conv_pack_weights(const float* weight, int Cout, int L, int radius, void* packed, float* wscale, void* stream) {
+  EZB_REQUIRE(weight && packed && wscale, "null pointer");
+  EZB_REQUIRE(L >= 1 && radius >= 0, "bad arguments");
+  if (L > PYR_MAX_LEVELS || radius > k3c::MAX_R || Cout < 1 || Cout > k3c::N_MAX)
+    return fail(EZB_ERR_UNSUPPORTED, "fused lookup + 1x1 conv supports num_levels <= %d, corr_radius <= %d, 1 <= out_channels <= %d", PYR_MAX_LEVELS,
+                k3c::MAX_R, k3c::N_MAX);
+  EZB_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 127) == 0, "packed weight buffer must be 128-byte aligned");
+  const int K = 2 * radius + 1;
+  k3c::pack_weights_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(weight, Cout, K * K, L, static_cast<__half*>(packed), wscale);
+  EZB_LAUNCH_OK();
+  return EZB_OK;
+}
+
+extern "C" int ezb_corr_lookup_conv1x1_fwd(const void* pyramid, const float* deq_scale, const float* coords, int B, int H, int W, int L,
+                                           int radius, int dtype, const void* packed_weight, const float* wscale, const float* bias,
+                                           int Cout, int relu, float* out, void* stream) {
+  EZB_REQUIRE(pyramid && deq_scale && coords && packed_weight && wscale && out, "null pointer");
+  EZB_REQUIRE(B > 0 && H > 0 && W > 0 && L >= 1 && radius >= 0, "bad shape B=%d H=%d W=%d L=%d r=%d", B, H, W, L, radius);
+  if (dtype != EZB_F16) return fail(EZB_ERR_UNSUPPORTED, "fused lookup + 1x1 conv needs an fp16 pyramid");
+  if (L > PYR_MAX_LEVELS || radius > k3c::MAX_R || Cout < 1 || Cout > k3c::N_MAX)
+    return fail(EZB_ERR_UNSUPPORTED, "fused lookup + 1x1 conv supports num_levels <= %d, corr_radius <= %d, 1 <= out_channels <= %d", PYR_MAX_LEVELS,
+                k3c::MAX_R, k3c::N_MAX);
+  PyrLayout lay;
+  EZB_REQUIRE(pyr_layout(H, W, L, dtype, &lay), "feature map %dx%d too small for %d pyramid levels", H, W, L);
+  EZB_REQUIRE((reinterpret_cast<uintptr_t>(pyramid) & 127) == 0, "pyramid buffer must be 128-byte aligned");
+  EZB_REQUIRE((long long)lay.n_groups * lay.group_bytes < (1ll << 32), "feature map too large (H*W=%d)", H * W);
+  const int N = H * W;
+  k3c::Params P;
+  P.pyr = static_cast<const char*>(pyramid);
+  P.H = H; P.W = W; P.N = N; P.L = L; P.r = radius; P.B = B;
+  for (int l = 0; l < PYR_MAX_LEVELS; ++l) { P.sw[l] = lay.sw[l]; P.sub_base[l] = lay.sub_base[l]; }
+  P.n_tiles = lay.n_tiles; P.n_groups = lay.n_groups; P.group_bytes = lay.group_bytes;
+  P.deq = deq_scale; P.coords = coords; P.wscale = wscale; P.bias = bias; P.out = out;
+  P.Cout = Cout; P.Np = round_up(Cout, 16); P.relu = relu;
+  P.tiles_per_pair = cdiv(N, k3c::TQ);
+  const long long n_work = (long long)P.tiles_per_pair * B;
+  EZB_REQUIRE(n_work < (1ll << 31), "batch too large for one launch (split it)");
+  P.n_work = (int)n_work;
+
+  CUtensorMap tmW;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)L * k3c::KL, (cuuint64_t)k3c::N_MAX};
+    cuuint64_t str[1] = {(cuuint64_t)L * k3c::KL * 2};
+    cuuint32_t box[2] = {k3c::KB_EL, k3c::N_MAX};
+    if (int r = make_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(packed_weight), dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B))
+      return r;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  EZB_CUDA_OK(cudaFuncSetAttribute(k3c::lookup_conv1x1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k3c::SMEM_BYTES));
+  const int grid = (int)std::min<long long>(n_work, num_sms());
+  k3c::lookup_conv1x1_kernel<<<grid, k3c::NUM_THREADS, k3c::SMEM_BYTES, st>>>(tmW, P);
+  EZB_LAUNCH_OK();
+  return EZB_OK;
+}

@@ -71,10 +71,31 @@ def fuse_model(model):
     """Post-build surgery: wherever a B200 correlation sampler is directly followed by a LeakyReLU — FlowNetC
     (``corr_activation``, ezflow/models/flownet_c.py:42,86-90) and the PWC decoder (``leaky_relu``,
     ezflow/decoder/pyramid.py:49,98-102), neither of which uses that activation anywhere else — the activation is folded into
-    the sampler's epilogue and replaced by ``nn.Identity``.  Returns the number of samplers fused."""
+    the sampler's epilogue and replaced by ``nn.Identity``; in RAFT the lookup is fused with the update block's first 1x1
+    convolution.  Returns the number of fusions made."""
+    import types
+
     import torch.nn as nn
 
+    from .similarity.lookup_conv import LookupConv2d, fused_motion_encoder_forward
+    from .similarity.pairwise import LazyLookupPairwise4DCorr
+
     fused = 0
+    # RAFT: lookup -> convc1 (+ bias + ReLU) as one kernel (SURVEY §8f-1; reference models/raft.py:116-120,
+    # decoder/iterative/recurrent_lookup.py:153,182,204).  The 1x1 conv is re-classed in place (same parameters and
+    # state-dict keys), the encoder's forward skips the ReLU the kernel already applied, and the model's similarity class
+    # hands out LazyLookup handles.
+    enc = getattr(getattr(model, "update_block", None), "encoder", None)
+    conv = getattr(enc, "convc1", None)
+    if (
+        getattr(model, "similarity_fn", None) is S.MutliScalePairwise4DCorr
+        and type(conv) is nn.Conv2d and conv.kernel_size == (1, 1) and conv.stride == (1, 1) and conv.padding == (0, 0) and conv.groups == 1
+        and all(hasattr(enc, a) for a in ("convf1", "convf2", "conv"))
+    ):
+        conv.__class__ = LookupConv2d
+        enc.forward = types.MethodType(fused_motion_encoder_forward, enc)
+        model.similarity_fn = LazyLookupPairwise4DCorr
+        fused += 1
     for m in model.modules():
         corr = getattr(m, "correlation_layer", None)
         if not isinstance(corr, S.IterSpatialCorrelationSampler) or corr.fused_negative_slope is not None:

@@ -1,7 +1,8 @@
 from ..registry import SIMILARITY_REGISTRY, build_similarity
 from .layer import CorrelationLayer
 from .matryoshka import MatryoshkaDilatedCostVolume, MatryoshkaDilatedCostVolumeList
-from .pairwise import MutliScalePairwise4DCorr, get_pyramid_dtype, set_pyramid_dtype
+from .lookup_conv import LazyLookup, LookupConv2d, lookup_conv1x1
+from .pairwise import LazyLookupPairwise4DCorr, MutliScalePairwise4DCorr, get_pyramid_dtype, set_pyramid_dtype
 from .sampler import (
     IterSpatialCorrelationSampler,
     WarpedFeatures,
@@ -26,4 +27,8 @@ __all__ = [
     "get_local_corr_mode",
     "WarpedFeatures",
     "lazy_warp",
+    "LazyLookup",
+    "LookupConv2d",
+    "lookup_conv1x1",
+    "LazyLookupPairwise4DCorr",
 ]

@@ -258,6 +258,9 @@ class MutliScalePairwise4DCorr:
         Radius of the lookup window
     """
 
+    # True in the subclass fuse_model() gives to RAFT: lookups without autograd return a LazyLookup handle
+    _lazy_lookup = False
+
     @configurable
     def __init__(self, fmap1, fmap2, num_levels=4, corr_radius=4):
         self.num_levels = num_levels
@@ -302,7 +305,14 @@ class MutliScalePairwise4DCorr:
             raise ValueError(f"coords must be ({st.B},2,{st.H},{st.W}); got {tuple(coords.shape)}")
         if self._token is not None and torch.is_grad_enabled():
             return _LookupFn.apply(self._token, c.detach(), st, int(self.corr_radius))
+        if self._lazy_lookup:
+            from .lookup_conv import LazyLookup
+
+            return LazyLookup(self, c.detach())  # consumed by LookupConv2d (lookup -> convc1 fused), SURVEY §8f-1
         return _lookup_forward(st, c.detach(), int(self.corr_radius))
+
+    def _lookup(self, coords):
+        return _lookup_forward(self._state, coords, int(self.corr_radius))
 
     @classmethod
     def from_config(cls, cfg):
@@ -322,3 +332,10 @@ class MutliScalePairwise4DCorr:
         st.build()
         B, _, H, W = f1.shape
         return st.level_tensor(0).reshape(B, H, W, 1, H, W)
+
+
+class LazyLookupPairwise4DCorr(MutliScalePairwise4DCorr):
+    """The class ``fuse_model`` installs as ``RAFT.similarity_fn``: identical, except that a lookup outside autograd returns
+    a ``LazyLookup`` for the update block's ``LookupConv2d`` to evaluate inside its own kernel."""
+
+    _lazy_lookup = True

@@ -104,6 +104,22 @@ int ezb_corr_lookup_fwd(const void* pyramid, const float* deq_scale /*[B]*/,
                         int B, int H, int W, int L, int radius, int dtype,
                         float* out, void* stream);
 
+/* Lookup fused with the 1x1 convolution that consumes it in RAFT's update block:
+ *   replaces  corr = corr_fn(coords); cor = F.relu(self.convc1(corr))
+ *   ezflow/similarity/correlation/pairwise.py:43-69 + ezflow/decoder/iterative/recurrent_lookup.py:153,182,204
+ *   out (B, Cout, H, W) = act( conv1x1(lookup(coords), weight (Cout, L*(2r+1)^2), bias) ),  act = ReLU when relu != 0.
+ * The lookup features are produced straight into the A operand of a tcgen05 GEMM (fp16 operands, fp32 accumulation,
+ * <= 1e-3 relative) and never written to HBM.  fp16 pyramids, L <= 4, radius <= 4, Cout <= 256; anything else returns
+ * EZB_ERR_UNSUPPORTED and the caller runs the two separate ops.
+ * The weights are packed once (fp16, K-major, one 96-slot K block per level, scaled by a power of two) into a buffer of
+ * ezb_lookup_conv_packed_weight_bytes(); wscale[0] receives the factor that undoes the scaling. */
+int ezb_lookup_conv_packed_weight_bytes(int L, size_t* bytes /*host*/);
+int ezb_lookup_conv_pack_weights(const float* weight /* (Cout, L*(2r+1)^2) */, int Cout, int L, int radius,
+                                 void* packed /* 128-byte aligned, written */, float* wscale /*[1] device, written*/, void* stream);
+int ezb_corr_lookup_conv1x1_fwd(const void* pyramid, const float* deq_scale, const float* coords, int B, int H, int W, int L,
+                                int radius, int dtype, const void* packed_weight, const float* wscale,
+                                const float* bias /*[Cout] or NULL*/, int Cout, int relu, float* out, void* stream);
+
 /* Gradient levels are separate fp32 buffers, row-major per query: element (b,q,y,x) of level l at
  * (b*N+q)*qstride[l] + y*pitch[l] + x with pitch[l] = w[l] and qstride[l] = h[l]*w[l] rounded up to 4 (a 16-byte
  * aligned row per query, so TMA can read a level as a 2-D tensor) (ezb_corr_grad_layout).
