@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--no-secondary", action="store_true", help="skip the BASELINE config 2-5 records")
     ap.add_argument("--secondary", default="", help="comma-separated subset of secondary records to run (default: all)")
     ap.add_argument("--train-batch", type=int, default=64, help="global batch of the config-5 training step (sharded over ranks)")
+    ap.add_argument("--train-micro", type=int, default=4, help="pairs per pyramid build in the config-5 training step")
     ap.add_argument("--sustained-seconds", type=float, default=2.0, help="length of the sustained-clock headline record")
     return ap.parse_args()
 
@@ -441,24 +442,52 @@ def run_secondary(args, dev, world, rank, peaks, headline_step):
             del xa, xb
     torch.cuda.empty_cache()
 
+    if enabled("lookup_convc1_fused") or enabled("lookup_then_convc1_unfused"):
+        # one RAFT iteration's lookup + MotionEncoder.convc1 (1x1, 324 -> 256) + ReLU for 8 1080p pairs
+        with torch.no_grad():
+            Pn = args.micro
+            g = torch.Generator(device="cpu").manual_seed(77 + rank)
+            f1 = torch.randn(Pn, C, H, W, generator=g).to(dev)
+            f2 = torch.randn(Pn, C, H, W, generator=g).to(dev)
+            coords = (E.coords_grid(Pn, H, W) + torch.randn(Pn, 2, H, W, generator=g) * 4).clamp_(-16, W + 16).to(dev)
+            wgt = (torch.randn(256, L * (2 * R + 1) ** 2, 1, 1, generator=g) * 0.05).to(dev)
+            bias = torch.randn(256, generator=g).to(dev)
+            fn = E.LazyLookupPairwise4DCorr(f1, f2, num_levels=L, corr_radius=R)
+            lazy = fn(coords)
+            E.lookup_conv1x1(lazy, wgt, bias)  # packs the weights once
+            # algorithmic bytes: windows (2r+2)^2 fp16 per level + coords in, 256 fp32 channels out
+            nb = Pn * N * (L * (2 * R + 2) ** 2 * 2 + 8 + 256 * 4)
+            if enabled("lookup_convc1_fused"):
+                add("lookup_convc1_fused", timed(lambda: E.lookup_conv1x1(lazy, wgt, bias)), nb,
+                    "lookup -> convc1 (1x1, 324->256) + bias + ReLU as ONE tcgen05 kernel, %d 1080p pairs; the (B,324,H,W) features never reach HBM" % Pn)
+            if enabled("lookup_then_convc1_unfused"):
+                nb_un = nb + 2 * Pn * N * L * (2 * R + 1) ** 2 * 4  # + write and re-read of the lookup features
+                add("lookup_then_convc1_unfused", timed(lambda: torch.relu_(torch.nn.functional.conv2d(fn._lookup(coords), wgt, bias))), nb_un,
+                    "same result from this repo's lookup kernel + torch conv2d (cuDNN/cuBLAS, TF32 off) + in-place ReLU")
+            del fn, lazy, f1, f2
+        torch.cuda.empty_cache()
+
     if enabled("cfg5_raft_1080p_train_step"):
         # per pair: build (K1+K2), 12 lookups (K3), 12 lookup adjoints (K3b), pyramid adjoint (K1b+K2b); then the all-reduce
         lo, hi = shard_range(args.train_batch, world, rank)
         g = torch.Generator(device="cpu").manual_seed(99 + rank)
-        f1 = torch.randn(1, C, H, W, generator=g).to(dev).requires_grad_(True)
-        f2 = torch.randn(1, C, H, W, generator=g).to(dev).requires_grad_(True)
-        grid = E.coords_grid(1, H, W, device=dev)
-        coords = [(grid + torch.randn(1, 2, H, W, generator=g).to(dev) * (2 + k)).clamp_(-16, W + 16) for k in range(ITERS)]
-        douts = [torch.randn(1, L * (2 * R + 1) ** 2, H, W, generator=g).to(dev) for _ in range(ITERS)]
+        # the rank's pairs go through in micro-batches (pyramid + fp32 gradient pyramid: 8.5 GB per pair in flight)
+        TMB = max(1, min(args.train_micro, hi - lo))
+        f1 = torch.randn(TMB, C, H, W, generator=g).to(dev).requires_grad_(True)
+        f2 = torch.randn(TMB, C, H, W, generator=g).to(dev).requires_grad_(True)
+        grid = E.coords_grid(TMB, H, W, device=dev)
+        coords = [(grid + torch.randn(TMB, 2, H, W, generator=g).to(dev) * (2 + k)).clamp_(-16, W + 16) for k in range(ITERS)]
+        douts = [torch.randn(TMB, L * (2 * R + 1) ** 2, H, W, generator=g).to(dev) for _ in range(ITERS)]
         bucket = torch.randn(RAFT_PARAMS, device=dev)
 
         def train_step():
-            for _ in range(lo, hi):
+            for m in range(lo, hi, TMB):
+                n = min(TMB, hi - m)
                 f1.grad = f2.grad = None
-                fn = E.MutliScalePairwise4DCorr(f1, f2, num_levels=L, corr_radius=R)
+                fn = E.MutliScalePairwise4DCorr(f1[:n], f2[:n], num_levels=L, corr_radius=R)
                 loss = 0
                 for k in range(ITERS):
-                    loss = loss + (fn(coords[k]) * douts[k]).sum()
+                    loss = loss + (fn(coords[k][:n]) * douts[k][:n]).sum()
                 loss.backward()
                 del fn, loss
             if world > 1:
@@ -484,7 +513,7 @@ def run_secondary(args, dev, world, rank, peaks, headline_step):
         add("cfg5_raft_1080p_train_step", ms, int(per_pair * (hi - lo)),
             "RAFT 1080p correlation fwd+bwd training step, global batch sharded over the ranks, NCCL all-reduce(sum) of the "
             "RAFT-sized fp32 gradient bucket per step (BASELINE config 5); bytes = this rank's pairs",
-            global_batch=args.train_batch, pairs_per_rank=hi - lo, pairs_per_s=args.train_batch / (ms / 1e3),
+            global_batch=args.train_batch, pairs_per_rank=hi - lo, micro_batch=TMB, pairs_per_s=args.train_batch / (ms / 1e3),
             ms_per_pair=ms / max(hi - lo, 1), allreduce_elems=RAFT_PARAMS if world > 1 else 0, scaling="strong", steps=nsteps)
         del f1, f2, coords, douts, bucket
         torch.cuda.empty_cache()

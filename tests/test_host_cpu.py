@@ -106,6 +106,14 @@ def test_install_into_reference_and_yaml_models():
         import ezflow.models.raft as ref_raft
 
         assert ref_raft.convex_upsample_flow is E.convex_upsample_flow
+        # lookup -> convc1 fusion: the conv is re-classed in place, the state dict is untouched
+        keys = list(raft.state_dict())
+        assert E.fuse_model(raft) == 1 and E.fuse_model(raft) == 0
+        assert isinstance(raft.update_block.encoder.convc1, E.LookupConv2d) and raft.similarity_fn is E.LazyLookupPairwise4DCorr
+        assert list(raft.state_dict()) == keys
+        x = torch.randn(1, 324, 6, 8)
+        conv = raft.update_block.encoder.convc1
+        assert torch.equal(conv(x), torch.nn.functional.conv2d(x, conv.weight, conv.bias))  # plain tensors: an ordinary Conv2d
         fnc = build_model("FlowNetC", cfg_path=refshim.reference_config_path("flownet_c.yaml"), custom_cfg=True)
         assert isinstance(fnc.correlation_layer, E.IterSpatialCorrelationSampler)
         assert (fnc.correlation_layer.patch_size, fnc.correlation_layer.dilation_patch) == (21, 2)
