@@ -12,9 +12,9 @@
 // accumulates against that level's slice of the weights (TMA, L2-resident) into a 128 x Cout fp32 accumulator in
 // tensor memory.  The epilogue applies the scales, bias and ReLU and stores NCHW with 128-byte coalesced rows.
 //
-//   warps 0-7   gather (cp.async windows of the NEXT (tile, level) stage) + bilinear taps of the current stage -> A
-//   warps 8-11  epilogue (one TMEM lane quadrant each)
-//   warp  12    weight-slice TMA + MMA issue (one elected lane), TMEM allocation
+//   warps 0-15  gather (cp.async windows, two (tile, level) stages ahead in flight) + bilinear taps of the current stage -> A
+//   warps 16-19 epilogue (one TMEM lane quadrant each)
+//   warp  20    weight-slice TMA + MMA issue (one elected lane), TMEM allocation
 //
 // Values: A holds the STORED pyramid domain (fp16 storage scale), the weights are pre-scaled by a power of two into
 // (-2, 2); out = act(acc * deq_scale[b] * wscale + bias).  fp16 operands / fp32 accumulation: <= 1e-3 relative to the
@@ -38,8 +38,10 @@ constexpr int B_KB_BYTES = N_MAX * 64;  // 16 KB
 constexpr int ROW_EL = 24;              // fetched pixels per window row: 3 chunks of 8 (covers 2r+2 <= 10 taps at any alignment)
 constexpr int QSTRIDE = 496;            // bytes per query in a staging buffer: 10 rows x 48 B = 480, odd number of 16-byte chunks
 constexpr int STG_BYTES = TQ * QSTRIDE; // 63488
-constexpr int COMPUTE_WARPS = 8, EPI_WARPS = 4;
-constexpr int NUM_THREADS = (COMPUTE_WARPS + EPI_WARPS + 1) * 32;  // 416
+constexpr int COMPUTE_WARPS = 16, EPI_WARPS = 4;  // 4 compute warps per scheduler hide the tap arithmetic's latencies
+constexpr int NUM_THREADS = (COMPUTE_WARPS + EPI_WARPS + 1) * 32;  // 672
+constexpr int MMA_WARP = COMPUTE_WARPS + EPI_WARPS;
+constexpr int QPW = TQ / COMPUTE_WARPS;  // queries whose windows one warp fetches per stage
 constexpr int SMEM_STG = 0;
 constexpr int SMEM_A = SMEM_STG + 2 * STG_BYTES;           // 126976
 constexpr int SMEM_B = SMEM_A + 2 * KBS * A_KB_BYTES;      // + 49152
@@ -73,6 +75,15 @@ __device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src, 
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// waits that normally last microseconds (a whole stage / tile): back off between polls so the spinning warp does not
+// compete with the compute warps for issue slots
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, unsigned ns) {
+  uint32_t spins = 0;
+  while (!ptx::mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (++spins > (1u << 24)) __trap();
+  }
+}
 __device__ __forceinline__ void compute_bar() { asm volatile("bar.sync 1, %0;" ::"n"(COMPUTE_WARPS * 32) : "memory"); }
 
 // K-major SWIZZLE_64B shared-memory matrix descriptor: rows of 64 B, 8-row groups 512 B apart
@@ -92,10 +103,15 @@ __device__ __forceinline__ uint32_t a_offset(int row, int k) {
   return (uint32_t)(kb * A_KB_BYTES + row * 64 + ((((kk >> 3) ^ (row >> 1)) & 3) << 4) + (kk & 7) * 2);
 }
 
-// weights (Cout, L*KK) fp32 -> (N_MAX rows, L*KL) fp16 scaled by 2^-e (e = floor(log2 max|W|)); k slot l*KL + t holds input
-// channel l*KK + t, everything else is zero.  One block; wscale[0] = 2^e.
-__global__ void __launch_bounds__(1024) pack_weights_kernel(const float* __restrict__ w, int Cout, int KK, int L, __half* __restrict__ wp,
+// K slot of window tap (i, j) inside a level's block: every window column i owns K + 1 slots (K is odd), so that the taps
+// (i, 2m), (i, 2m + 1) are an aligned fp16 pair = one 4-byte shared-memory store; the odd slot out stays zero.
+__host__ __device__ __forceinline__ int tap_slot(int K, int i, int j) { return i * (K + 1) + j; }
+
+// weights (Cout, L*K*K) fp32 -> (N_MAX rows, L*KL) fp16 scaled by 2^-e (e = floor(log2 max|W|)); k slot l*KL + tap_slot(i, j)
+// holds input channel l*K*K + i*K + j, everything else is zero.  One block; wscale[0] = 2^e.
+__global__ void __launch_bounds__(1024) pack_weights_kernel(const float* __restrict__ w, int Cout, int K, int L, __half* __restrict__ wp,
                                                             float* __restrict__ wscale) {
+  const int KK = K * K;
   __shared__ float red[32];
   const int cin = L * KK, total = Cout * cin;
   float m = 0.f;
@@ -113,7 +129,8 @@ __global__ void __launch_bounds__(1024) pack_weights_kernel(const float* __restr
   const int kp = L * KL;
   for (int i = threadIdx.x; i < N_MAX * kp; i += blockDim.x) {
     const int n = i / kp, k = i - n * kp, l = k / KL, t = k - l * KL;
-    wp[i] = __float2half_rn((n < Cout && t < KK) ? w[(long long)n * cin + l * KK + t] * s : 0.f);
+    const int wi = t / (K + 1), wj = t - wi * (K + 1);  // slot -> tap
+    wp[i] = __float2half_rn((n < Cout && wi < K && wj < K) ? w[(long long)n * cin + l * KK + wi * K + wj] * s : 0.f);
   }
 }
 
@@ -134,7 +151,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) lookup_conv1x1_kernel(const __
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = P.r, D = 2 * r + 2, K = 2 * r + 1;
 
-  if (warp == 12) {
+  if (warp == MMA_WARP) {
     if (lane == 0) {
       ptx::prefetch_tmap(&tmW);
       for (int i = 0; i < 2; ++i) {
@@ -177,10 +194,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) lookup_conv1x1_kernel(const __
       const uint32_t stg = sStg + (uint32_t)(s & 1) * STG_BYTES;
       const float inv = 1.0f / (float)(1 << l);
       const int hl = P.H >> l, wl = P.W >> l;
-      // lanes 0..15: window origin of query warp*16 + lane of the tile
+      // lanes 0..QPW-1: window origin of query warp*QPW + lane of the tile
       int org_packed;
       {
-        const int q = min(q0 + warp * 16 + (lane & 15), P.N - 1);
+        const int q = min(q0 + warp * QPW + (lane & (QPW - 1)), P.N - 1);
         const int x0 = floor_clamped(__ldg(cx_ptr + q) * inv), y0 = floor_clamped(__ldg(cy_ptr + q) * inv);
         const int ox = max(-D, min(wl, x0 - r)), oy = max(-D, min(hl, y0 - r));
         org_packed = ((((ox + 64) >> 3) - 8) << 16) | (oy & 0xffff);  // first 8-pixel chunk, first row
@@ -190,37 +207,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) lookup_conv1x1_kernel(const __
       const bool task_ok = lane < D * ng;
       const unsigned int tile_stride = (unsigned int)(P.n_groups * P.group_bytes);
       const char* pair_base = P.pyr + (long long)b * P.n_tiles * P.n_groups * P.group_bytes;
-#pragma unroll 4
-      for (int qi = 0; qi < 16; ++qi) {
+      const uint32_t dst_lane = stg + (uint32_t)(warp * QPW) * QSTRIDE + (row * ROW_EL + gi * 8) * 2;
+      const int sb = P.sub_base[l], swl = P.sw[l];
+#pragma unroll
+      for (int qi = 0; qi < QPW; ++qi) {
         const int pk = __shfl_sync(0xffffffffu, org_packed, qi);
         if (task_ok) {
-          const int ql = warp * 16 + qi;  // query inside the tile
-          const int q = min(q0 + ql, P.N - 1);
+          const int q = min(q0 + warp * QPW + qi, P.N - 1);
           const int y = (int)(short)(pk & 0xffff) + row;
-          const int xg = ((pk >> 16) + gi) * 8;
-          const char* src = pair_base;
-          uint32_t nbytes = 0;
-          if ((unsigned)y < (unsigned)hl && (unsigned)xg < (unsigned)wl) {
-            const unsigned sidx = (unsigned)(P.sub_base[l] + (y / PYR_SY) * P.sw[l] + xg / PYR_SX);
-            const int col = (int)(sidx % PYR_SUBS_PER_TILE) * PYR_SUB + (y % PYR_SY) * PYR_SX + xg % PYR_SX;
-            src = pair_base + (unsigned long long)(sidx / PYR_SUBS_PER_TILE) * tile_stride + (long long)(q >> 5) * P.group_bytes +
-                  (unsigned)pyr_record_offset(2, q & 31, col);
-            nbytes = 16;
-          }
-          cp_async_16(stg + ql * QSTRIDE + (row * ROW_EL + gi * 8) * 2, src, nbytes);
+          const int xc = (pk >> 16) + gi;  // 8-pixel chunk = subtile column
+          // a chunk is one row of one 8x8 subtile: record column (s % 4) * 64 + (y % 8) * 8, i.e. section s % 4 of the
+          // query's group block, 16 bytes at (y % 8) * 16 of its 128-byte line (ezb_common.cuh)
+          const unsigned sidx = (unsigned)(sb + (y >> 3) * swl + xc);
+          const bool ok = (unsigned)y < (unsigned)hl && xc >= 0 && xc * 8 < wl;
+          const char* src = pair_base + (unsigned long long)(sidx >> 2) * tile_stride + (long long)(q >> 5) * P.group_bytes +
+                            (((sidx & 3u) << 12) + ((unsigned)(q & 31) << 7) + ((unsigned)(y & 7) << 4));
+          cp_async_16(dst_lane + qi * QSTRIDE, ok ? src : pair_base, ok ? 16u : 0u);
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
     if (n_stages > 0) issue_gather(0);
-    const int gq = warp & 3, half = warp >> 2;
+    const int gq = warp & 3, part = warp >> 2;  // query group (= TMEM lane quadrant) and share of the window columns
     const int qrow = gq * 32 + lane;  // A row / TMEM lane of this thread's query
     for (int s = 0; s < n_stages; ++s) {
       const int ti = s / P.L, l = s - ti * P.L;
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      compute_bar();  // stage s has landed for every thread; everybody is done reading stage s - 1
+      // stage s + 1 goes into the buffer stage s - 1 was read from (everybody left it at the barrier that ended iteration
+      // s - 1), BEFORE waiting for stage s: two stages of windows are in flight while this one is awaited
       if (s + 1 < n_stages) issue_gather(s + 1);
+      else asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      compute_bar();  // stage s has landed for every thread
 
       const int work = (int)blockIdx.x + ti * (int)gridDim.x;
       const int b = work / P.tiles_per_pair, q0 = (work - b * P.tiles_per_pair) * TQ;
@@ -232,57 +250,74 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) lookup_conv1x1_kernel(const __
       const float wl0 = 1.f - fx, wl1 = fx;
       const int xs = max(-D, min(P.W >> l, floor_clamped(cx) - r));
       const int off = xs - ((((xs + 64) >> 3) - 8) << 3);  // taps start `off` pixels into the fetched row
-      const __half* pl = reinterpret_cast<const __half*>(base_ptr + SMEM_STG + (s & 1) * STG_BYTES + qrow * QSTRIDE) + off;
-      // this warp's share of the window columns i: the two halves alternate between ceil(K/2) and floor(K/2) by level
-      const int isplit = (K + ((l & 1) ? 0 : 1)) >> 1;
-      const int i0 = half ? isplit : 0, i1 = half ? K : isplit;
+      // this warp's share of the window columns i: K columns dealt to the 4 parts (at most 3 each for K <= 9), the
+      // remainder rotating with the level
+      const int pr = (part + l) & 3;
+      const int i0 = (K * pr) >> 2, ni = ((K * (pr + 1)) >> 2) - i0;
+      const __half* pl = reinterpret_cast<const __half*>(base_ptr + SMEM_STG + (s & 1) * STG_BYTES + qrow * QSTRIDE) + off + i0;
 
       const int abuf = s & 1;
       ptx::mbar_wait(a_empty(abuf), (((uint32_t)s >> 1) & 1u) ^ 1u);  // the MMAs that read this buffer two stages ago are done
-      uint8_t* arow = base_ptr + SMEM_A + abuf * (KBS * A_KB_BYTES);
-      int k = i0 * K;
-      float held = 0.f;  // value of an even k waiting for its odd partner (one 4-byte store per pair)
-      for (int i = i0; i < i1; ++i) {
-        const __half* p = pl + i;
-        float top = wl0 * __half2float(p[0]) + wl1 * __half2float(p[1]);
-        for (int j = 0; j < K; ++j, ++k) {
-          p += ROW_EL;
-          const float bot = wl0 * __half2float(p[0]) + wl1 * __half2float(p[1]);
-          const float v = top + fy * (bot - top);
-          top = bot;
-          if (k & 1) {
-            if (k == i0 * K) {  // the run starts on an odd k: lone element
-              *reinterpret_cast<__half*>(arow + a_offset(qrow, k)) = __float2half_rn(v);
-            } else {
-              *reinterpret_cast<__half2*>(arow + a_offset(qrow, k - 1)) = __floats2half2_rn(held, v);
-            }
-          } else {
-            held = v;
+      uint8_t* arow = base_ptr + SMEM_A + abuf * (KBS * A_KB_BYTES) + qrow * 64;
+      const int swz = (qrow >> 1) & 3;
+      // byte offset (inside the row's k-blocks) of the aligned slot pair starting at even slot t
+      auto pair_off = [&](int t) { return (uint32_t)((t >> 5) * A_KB_BYTES + ((((t >> 3) & 3) ^ swz) << 4) + (t & 7) * 2); };
+      // Walk down the window rows once: a row's ni + 1 pixels give the ni horizontally interpolated values, two
+      // consecutive rows give the taps (i, j); taps (i, 2m), (i, 2m + 1) leave as one half2.
+      float top[3], held[3];
+      auto hrow = [&](const __half* p, float (&h)[3]) {
+        float x[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) x[a] = (a <= ni) ? __half2float(p[a]) : 0.f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) h[a] = wl0 * x[a] + wl1 * x[a + 1];
+      };
+      hrow(pl, top);
+      const __half* p = pl;
+      auto body = [&](int j) {
+        p += ROW_EL;
+        float bot[3];
+        hrow(p, bot);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const float v = top[a] + fy * (bot[a] - top[a]);
+          top[a] = bot[a];
+          if (a < ni) {
+            const int t = tap_slot(K, i0 + a, j);
+            if (j & 1) *reinterpret_cast<__half2*>(arow + pair_off(t - 1)) = __floats2half2_rn(held[a], v);
+            else if (j == K - 1) *reinterpret_cast<__half*>(arow + pair_off(t)) = __float2half_rn(v);  // odd K: the last tap is alone
+            else held[a] = v;
           }
         }
+      };
+      if (K == 9) {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) body(j);
+      } else {
+        for (int j = 0; j < K; ++j) body(j);
       }
-      if (i1 > i0 && (k & 1)) *reinterpret_cast<__half*>(arow + a_offset(qrow, k - 1)) = __float2half_rn(held);  // the run ended on an even k
       fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(a_full(abuf));
+      compute_bar();  // everybody is done reading this stage's windows: the buffer may be refilled
     }
-  } else if (warp == 12) {
+  } else if (warp == MMA_WARP) {
     // ================================ weight TMA + MMA issue ================================
     if (lane == 0) {
       const uint32_t idesc = ptx::umma_idesc(/*f16*/ 0, TQ, (uint32_t)P.Np);
       for (int s = 0; s < n_stages; ++s) {
         const int ti = s / P.L, l = s - ti * P.L;
-        ptx::mbar_wait(b_empty, ((uint32_t)s & 1u) ^ 1u);  // MMAs of stage s - 1 (the previous user of the weight buffer) are done
+        mbar_wait_backoff(b_empty, ((uint32_t)s & 1u) ^ 1u, 32);  // MMAs of stage s - 1 (the previous user of the weight buffer) are done
         ptx::mbar_expect_tx(b_full, (uint32_t)(KBS * B_KB_BYTES));
         for (int kb = 0; kb < KBS; ++kb)
           ptx::tma_load_2d_hint(sB + kb * B_KB_BYTES, &tmW, b_full, l * KL + kb * KB_EL, 0, ptx::kEvictLast);
         const int dbuf = ti & 1;
         if (l == 0) {
-          ptx::mbar_wait(d_empty(dbuf), (((uint32_t)ti >> 1) & 1u) ^ 1u);
+          mbar_wait_backoff(d_empty(dbuf), (((uint32_t)ti >> 1) & 1u) ^ 1u, 32);
           ptx::tc_fence_after();
         }
-        ptx::mbar_wait(b_full, (uint32_t)s & 1u);
-        ptx::mbar_wait(a_full(s & 1), ((uint32_t)s >> 1) & 1u);
+        mbar_wait_backoff(b_full, (uint32_t)s & 1u, 32);
+        mbar_wait_backoff(a_full(s & 1), ((uint32_t)s >> 1) & 1u, 64);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + dbuf * N_MAX;
         const uint32_t a_base = sA + (s & 1) * (KBS * A_KB_BYTES);
@@ -300,7 +335,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) lookup_conv1x1_kernel(const __
     }
   } else {
     // ================================ epilogue: lane = query ================================
-    const int quad = warp - COMPUTE_WARPS;  // warps 8..11 -> TMEM lane quadrants 0..3 (warp % 4)
+    const int quad = warp - COMPUTE_WARPS;  // warps 16..19 -> TMEM lane quadrants 0..3 (= warp % 4)
     const float wscale = __ldg(P.wscale);
     for (int ti = 0; ti < n_my; ++ti) {
       const int work = (int)blockIdx.x + ti * (int)gridDim.x;
@@ -308,7 +343,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) lookup_conv1x1_kernel(const __
       const int q = q0 + quad * 32 + lane;
       const float sc = __ldg(P.deq + b) * wscale;
       const int dbuf = ti & 1;
-      ptx::mbar_wait(d_full(dbuf), ((uint32_t)ti >> 1) & 1u);
+      mbar_wait_backoff(d_full(dbuf), ((uint32_t)ti >> 1) & 1u, 256);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + dbuf * N_MAX + ((uint32_t)(quad * 32) << 16);
       float* o = P.out + (long long)b * P.Cout * P.N + q;
@@ -331,13 +366,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) lookup_conv1x1_kernel(const __
           if (lane == 0) ptx::mbar_arrive(d_empty(dbuf));
         }
         if (q < P.N) {
+          float* oc = o + (long long)c0 * P.N;
+          if (c0 + 32 <= P.Cout) {  // whole chunk: no per-channel predicate
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = c0 + j;
-            if (n < P.Cout) {
-              float y = fmaf(__uint_as_float(v[j]), sc, s_bias[n]);
+            for (int j = 0; j < 32; ++j) {
+              float y = fmaf(__uint_as_float(v[j]), sc, s_bias[c0 + j]);
               if (P.relu) y = fmaxf(y, 0.f);
-              o[(long long)n * P.N] = y;
+              *oc = y;
+              oc += P.N;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (c0 + j < P.Cout) {
+                float y = fmaf(__uint_as_float(v[j]), sc, s_bias[c0 + j]);
+                if (P.relu) y = fmaxf(y, 0.f);
+                oc[(long long)j * P.N] = y;
+              }
             }
           }
         }
@@ -347,7 +392,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) lookup_conv1x1_kernel(const __
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 12) ptx::tmem_dealloc(tmem_base, 512);
+  if (warp == MMA_WARP) ptx::tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace k3c
@@ -369,7 +414,7 @@ extern "C" int ezb_lookup_conv_pack_weights(const float* weight, int Cout, int L
                 k3c::MAX_R, k3c::N_MAX);
   EZB_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 127) == 0, "packed weight buffer must be 128-byte aligned");
   const int K = 2 * radius + 1;
-  k3c::pack_weights_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(weight, Cout, K * K, L, static_cast<__half*>(packed), wscale);
+  k3c::pack_weights_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(weight, Cout, K, L, static_cast<__half*>(packed), wscale);
   EZB_LAUNCH_OK();
   return EZB_OK;
 }
