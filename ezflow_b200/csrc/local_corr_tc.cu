@@ -6,8 +6,10 @@
 //
 // FlowNetC (C=256, 441 displacements) and DCVNet (C=256, 486 displacements) have 60 flop per byte of HBM
 // traffic, far above what CUDA cores sustain, so the contraction runs on tcgen05:
-//   prep    : per-(batch,group) absmax -> power-of-two pre-scale; fp32 (BG,C,H,W) -> fp16 K-major (BG,H,W,Cp)
-//             (for stride > 1 / padding > 0 only the query pixels of in1 are gathered: (BG,oh,ow,Cp))
+//   prep    : ONE launch converts both tensors: fp32 (BG,C,H,W) -> fp16 K-major (BG,H,W,Cp), every image ROW scaled by its own
+//             power of two (absmax of the row, found in a first sweep the second one re-reads from L2), so there is no
+//             separate absmax pass over the inputs; the epilogue multiplies by (query row scale) x (target row scale)
+//             (for stride > 1 / padding > 0 / lattice mode only the query pixels of in1 are gathered: (BG,oh,ow,Cp))
 //   kernel  : one CTA per 8x16 tile of output pixels ("queries", UMMA M = 128).  The query operand (<= 64 KB)
 //             is TMA-loaded once; negative box coordinates / OOB zero fill of the target loads implement the
 //             zero padding and the image border.  The CTA then sweeps 8x16 tiles of in2 pixels ("targets", UMMA N = 128) over the
@@ -84,6 +86,7 @@ __device__ __forceinline__ int fdiv(int n, const FastDiv& f) { return f.d == 1 ?
 struct Params {
   int G, H, W, oh, ow, Ph, Pw, sh, sw, padh, padw, D, KB;
   FastDiv d_qtx, d_qty, d_nsplit, d_ncls, d_lat, d_G;
+  int regular;  // D == 1, dilation 1 (layout units), stride 1, no padding, window x-extent inside ONE target tile: row-wise extraction
   int nsplit;  // work items sharing one query tile (each sweeps a slice of its target tiles): balances the load
   // Persistent CTAs: work item = (query tile x, query tile y, z = (bg * lat^2 + class) * nsplit + split), item index
   // x-fastest; CTA c takes items c, c + gridDim.x, ...
@@ -96,105 +99,122 @@ struct Params {
   int out_h, out_w;  // full output plane
   int dph[MAX_DIL], dpw[MAX_DIL];
   float slope;
-  const unsigned int* amax;  // [2][BG] float bits of max|in1|, max|in2| per (batch, group): operands were scaled by 2^-e
-  float scale;               // user scale (CorrelationLayer: 1/C)
+  const float* qscale;  // [BG * lat^2][oh] 2^e of every query row: the fp16 operand row was scaled by 2^-e
+  const float* tscale;  // [BG][Hf]       2^e of every in2 row
+  float scale;          // user scale (CorrelationLayer: 1/C)
   float* out;
   long long out_bstride;
 };
 
-// 2^(e1+e2): undoes the power-of-two pre-scales of the two operands (e = floor(log2(absmax)), 0 for an all-zero tensor)
-__device__ __forceinline__ float dequant_factor(unsigned int amax1_bits, unsigned int amax2_bits) {
-  auto ex = [](unsigned int bits) {
-    const int e = (int)((bits >> 23) & 0xff);
-    return e == 0 ? 0 : e - 127;
+// ---------------------------------------------------------------------------------------------------------------
+// Operand conversion: fp32 NCHW -> fp16 K-major, one block per destination image row, per-row power-of-two scale.
+//   dst[img, oy, ox, c] = 2^-e(img,oy) * value(c, oy, ox),   rowscale[img * oh + oy] = 2^e,  e = floor(log2 max_row |value|)
+//   value = src[bg, c, oy*sh - padh, ox*sw - padw]  (0 outside the image or for c >= C), or, with a flow field, the
+//   bilinear warp of K5 (ezflow/utils/warp.py:5-42) evaluated at that pixel — the warped fp32 tensor is never written.
+// In lattice mode (queries of a dilation-lat problem) img = bg * lat^2 + class and the class (cy, cx) acts as a negative
+// padding with stride lat.  Sweep 1 finds the row's absmax, sweep 2 (same addresses: L2 hits) converts 32-pixel x 64-channel
+// chunks through a shared-memory transpose.  Up to two jobs (targets, queries) share one launch (blockIdx.z ranges).
+struct ConvJob {
+  const float* src;
+  const float* flow;  // (B,2,H,W) or null
+  __half* dst;
+  float* rowscale;
+  int C, Cp, H, W, oh, ow, sh, sw, padh, padw, lat, nimg, G;
+};
+struct ConvJobs {
+  ConvJob j[2];
+};
+
+__global__ void __launch_bounds__(256) convert_rows_kmajor_kernel(const ConvJobs JJ) {
+  __shared__ float tile[64][33];
+  __shared__ float red[8];
+  const bool second = (int)blockIdx.z >= JJ.j[0].nimg;
+  const ConvJob& J = JJ.j[second ? 1 : 0];
+  const int img = (int)blockIdx.z - (second ? JJ.j[0].nimg : 0), oy = blockIdx.x;
+  if (oy >= J.oh) return;
+  int sh = J.sh, sw = J.sw, padh = J.padh, padw = J.padw, bg = img;
+  if (J.lat > 1) {
+    const int ncls = J.lat * J.lat, cls = img % ncls;
+    bg = img / ncls;
+    sh = sw = J.lat;
+    padh = -(cls / J.lat);
+    padw = -(cls % J.lat);
+  }
+  const int HW = J.H * J.W, y = oy * sh - padh;
+  const bool row_in = y >= 0 && y < J.H;
+  const float* src = J.src + (long long)bg * J.C * HW;
+  const float* fl = J.flow ? J.flow + (long long)(bg / J.G) * 2 * HW : nullptr;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  // value of channel c at destination column ox (plain gather); the warp path goes through gather_at
+  auto gather_at = [&](int x) {  // taps of the warped pixel (x, y)
+    const k5::Taps t = k5::make_taps(__ldg(fl + y * J.W + x), __ldg(fl + HW + y * J.W + x), x, y, J.H, J.W);
+    return k5::make_gather(t, J.W);
   };
-  const int e = max(-126, min(126, ex(amax1_bits) + ex(amax2_bits)));
-  return __uint_as_float((unsigned int)(e + 127) << 23);
-}
+  auto warped = [&](const k5::Gather& g, const float* sp) {
+    return g.zero ? 0.f : ((g.w00 * __ldg(sp + g.oaa) + g.w01 * __ldg(sp + g.oab)) + (g.w10 * __ldg(sp + g.oba) + g.w11 * __ldg(sp + g.obb)));
+  };
 
-// Query operand for stride > 1 or padding > 0: only the pixels that are queries, (BG, oh, ow, Cp) fp16 K-major,
-//   dst[bg, oy, ox, c] = 2^-e1 * in1[bg, c, oy*sh - padh, ox*sw - padw]   (0 outside the image / for c >= C),
-// so the conversion touches 1/(sh*sw) of in1 and the A tiles are plain dense TMA boxes.
-__global__ void __launch_bounds__(256) gather_queries_kmajor_kernel(const float* __restrict__ in1, __half* __restrict__ dst,
-                                                                    const unsigned int* __restrict__ amax, int C, int Cp, int H,
-                                                                    int W, int oh, int ow, int sh, int sw, int padh, int padw,
-                                                                    int lat) {
-  __shared__ float tile[64][33];
-  // lattice mode: blockIdx.z = bg * lat^2 + class; the class (cy, cx) acts as a negative padding with stride lat
-  const int ncls = lat * lat, bg = blockIdx.z / ncls, cls = blockIdx.z - bg * ncls;
-  if (lat > 1) { sh = sw = lat; padh = -(cls / lat); padw = -(cls % lat); }
-  const float* src = in1 + (long long)bg * C * H * W;
-  const int e = (int)((amax[bg] >> 23) & 0xff);
-  const float sc = __uint_as_float((unsigned int)(127 - (e == 0 ? 0 : max(-126, min(126, e - 127)))) << 23);  // 2^-e1
-  const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 64, NQ = oh * ow;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n = n0 + lane;
-  const int oy = n / ow, ox = n - oy * ow;
-  const int y = oy * sh - padh, x = ox * sw - padw;
-  const bool in_img = n < NQ && y >= 0 && y < H && x >= 0 && x < W;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = c0 + warp * 8 + i;
-    tile[warp * 8 + i][lane] = (in_img && c < C) ? __ldg(src + ((long long)c * H + y) * W + x) * sc : 0.f;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int nl = warp * 4 + i, nn = n0 + nl;
-    if (nn < NQ)
-      *reinterpret_cast<__half2*>(dst + ((long long)blockIdx.z * NQ + nn) * Cp + c0 + 2 * lane) =
-          __floats2half2_rn(tile[2 * lane][nl], tile[2 * lane + 1][nl]);
-  }
-}
-
-// Target operand of the warp-fused correlation (PWC-Net: warp(features2, flow) feeds the sampler, reference
-// decoder/pyramid.py:138-141): dst[bg, y, x, c] = 2^-e2 * warp(in2, flow)[bg, c, y, x] — the bilinear warp of K5 (warp.cu)
-// evaluated while the operand is converted, so the warped fp32 tensor is never written or re-read.  e2 comes from
-// absmax(in2), an upper bound of the warped tensor's absmax (every warped value is a convex combination times a 0/1 mask).
-// blockIdx.z in [BG, 2 BG) (when in1 != nullptr) converts the query tensor in1 plainly in the same launch.
-__global__ void __launch_bounds__(256) warp_convert_kmajor_kernel(const float* __restrict__ in2, const float* __restrict__ flow,
-                                                                  __half* __restrict__ dst2, const float* __restrict__ in1,
-                                                                  __half* __restrict__ dst1, const unsigned int* __restrict__ amax,
-                                                                  int BG, int G, int C, int Cp, int H, int W) {
-  __shared__ float tile[64][33];
-  const bool plain = blockIdx.z >= BG;
-  const int bg = plain ? blockIdx.z - BG : blockIdx.z, N = H * W;
-  const float* src = (plain ? in1 : in2) + (long long)bg * C * N;
-  __half* dst = plain ? dst1 : dst2;
-  const int e = (int)((amax[plain ? bg : BG + bg] >> 23) & 0xff);
-  const float sc = __uint_as_float((unsigned int)(127 - (e == 0 ? 0 : max(-126, min(126, e - 127)))) << 23);  // 2^-e
-  const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n = min(n0 + lane, N - 1);
-  if (plain) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = c0 + warp * 8 + i;
-      tile[warp * 8 + i][lane] = c < C ? __ldg(src + (long long)c * N + n) * sc : 0.f;
-    }
-  } else {
-    const float* fl = flow + (long long)(bg / G) * 2 * N;
-    const int py = n / W, px = n - py * W;
-    const k5::Taps t = k5::make_taps(__ldg(fl + n), __ldg(fl + N + n), px, py, H, W);
-    const k5::Gather g = k5::make_gather(t, W);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = c0 + warp * 8 + i;
-      float v = 0.f;
-      if (c < C && !g.zero) {  // mask == 0 (e.g. every tap outside the image: the clamped addresses are not valid then)
-        const float* sp = src + (long long)c * N;
-        v = ((g.w00 * __ldg(sp + g.oaa) + g.w01 * __ldg(sp + g.oab)) + (g.w10 * __ldg(sp + g.oba) + g.w11 * __ldg(sp + g.obb))) * sc;
+  // ---- sweep 1: absmax of the row.  Thread -> (column slot, channel slice): consecutive threads take consecutive columns
+  float m = 0.f;
+  if (row_in) {
+    int owp = 32;
+    while (owp < J.ow && owp < 256) owp <<= 1;
+    const int xs = threadIdx.x % owp, cs = threadIdx.x / owp, ncs = 256 / owp;
+    for (int ox = xs; ox < J.ow; ox += owp) {
+      const int x = ox * sw - padw;
+      if (x < 0 || x >= J.W) continue;
+      if (fl) {
+        const k5::Gather g = gather_at(x);
+        if (!g.zero)
+          for (int c = cs; c < J.C; c += ncs) m = fmaxf(m, fabsf(warped(g, src + (long long)c * HW)));
+      } else {
+        const float* sp = src + (long long)y * J.W + x;
+        int c = cs;
+        for (; c + 3 * ncs < J.C; c += 4 * ncs) {  // four independent loads in flight
+          const float a0 = __ldg(sp + (long long)c * HW), a1 = __ldg(sp + (long long)(c + ncs) * HW);
+          const float a2 = __ldg(sp + (long long)(c + 2 * ncs) * HW), a3 = __ldg(sp + (long long)(c + 3 * ncs) * HW);
+          m = fmaxf(m, fmaxf(fmaxf(fabsf(a0), fabsf(a1)), fmaxf(fabsf(a2), fabsf(a3))));
+        }
+        for (; c < J.C; c += ncs) m = fmaxf(m, fabsf(__ldg(sp + (long long)c * HW)));
       }
-      tile[warp * 8 + i][lane] = v;
     }
   }
-  __syncthreads();
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int nl = warp * 4 + i, nn = n0 + nl;
-    if (nn < N)
-      *reinterpret_cast<__half2*>(dst + ((long long)bg * N + nn) * Cp + c0 + 2 * lane) =
-          __floats2half2_rn(tile[2 * lane][nl], tile[2 * lane + 1][nl]);
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = fmaxf(fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])), fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7])));
+  const int eb = (int)((__float_as_uint(m) >> 23) & 0xff);
+  const int e = (eb == 0 || eb == 255) ? 0 : max(-126, min(126, eb - 127));  // 0 for an all-zero row
+  const float sc = __uint_as_float((unsigned int)(127 - e) << 23);
+  if (threadIdx.x == 0) J.rowscale[(long long)img * J.oh + oy] = __uint_as_float((unsigned int)(127 + e) << 23);
+
+  // ---- sweep 2: convert 32-pixel x 64-channel chunks
+  __half* drow = J.dst + ((long long)img * J.oh + oy) * J.ow * J.Cp;
+  for (int x0 = 0; x0 < J.ow; x0 += 32) {
+    const int ox = x0 + lane, x = ox * sw - padw;
+    const bool in_img = row_in && ox < J.ow && x >= 0 && x < J.W;
+    k5::Gather g;
+    g.zero = true;
+    if (fl && in_img) g = gather_at(x);
+    for (int c0 = 0; c0 < J.Cp; c0 += 64) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = c0 + warp * 8 + i;
+        float v = 0.f;
+        if (in_img && c < J.C) v = fl ? warped(g, src + (long long)c * HW) : __ldg(src + (long long)c * HW + (long long)y * J.W + x);
+        tile[warp * 8 + i][lane] = v * sc;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int nl = warp * 4 + i;
+        if (x0 + nl < J.ow)
+          *reinterpret_cast<__half2*>(drow + (long long)(x0 + nl) * J.Cp + c0 + 2 * lane) = __floats2half2_rn(tile[2 * lane][nl], tile[2 * lane + 1][nl]);
+      }
+      __syncthreads();
+    }
   }
 }
 
@@ -378,7 +398,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       const int oy = qy0 + q / QTW, ox = qx0 + q % QTW;
       const bool q_ok = oy < it.oh_ && ox < it.ow_;
       const int b = fdiv(it.bg, P.d_G), g = it.bg - b * P.G;
-      const float deq = P.scale * dequant_factor(__ldg(P.amax + it.bg), __ldg(P.amax + P.BG + it.bg));
+      // power-of-two factors of the operand rows: the query row's is folded into deq, the target rows' into the drain below
+      const float deq = P.scale * (q_ok ? __ldg(P.qscale + (long long)it.zq * P.oh + oy) : 0.f);
+      const float* trow_scale = P.tscale + (long long)it.bg * P.Hf;
       // offsets inside one batch entry of the output fit 32 bits (checked by the launcher): one IMAD per store address
       float* out_q = P.out + (long long)b * P.out_bstride + (long long)(it.cy + P.lat * oy) * P.out_w + (it.cx + P.lat * ox);
       const unsigned uplane = (unsigned)plane;
@@ -419,6 +441,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           if constexpr (k32) ptx::tmem_ld_32x32b_x32(taddr, r0);
           if constexpr (k16) ptx::tmem_ld_32x32b_x16(taddr + (k32 ? 32 : 0), r1);
           if constexpr (k8) ptx::tmem_ld_32x32b_x8(taddr + (k32 ? 32 : 0) + (k16 ? 16 : 0), r2);
+          // this warp's columns are the target-tile rows [part * RPW, (part + 1) * RPW): their in2 row scales
+          constexpr int RPW = CPW / TTW;
+          static_assert(CPW % TTW == 0 && RPW >= 1, "an epilogue warp's columns are whole target-tile rows");
+          float ts[RPW];
+#pragma unroll
+          for (int u = 0; u < RPW; ++u) ts[u] = __ldg(trow_scale + min(it.cy + P.lat * (ty0 + part * RPW + u), P.Hf - 1));
           ptx::tmem_ld_wait();
           ptx::tc_fence_before();
           __syncwarp();
@@ -426,19 +454,67 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           float* dst = Srow + part * CPW;
           if constexpr (k32) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) dst[j] = __uint_as_float(r0[j]);
+            for (int j = 0; j < 32; ++j) dst[j] = __uint_as_float(r0[j]) * ts[j / TTW];
           }
           if constexpr (k16) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) dst[(k32 ? 32 : 0) + j] = __uint_as_float(r1[j]);
+            for (int j = 0; j < 16; ++j) dst[(k32 ? 32 : 0) + j] = __uint_as_float(r1[j]) * ts[((k32 ? 32 : 0) + j) / TTW];
           }
           if constexpr (k8) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[(k32 ? 32 : 0) + (k16 ? 16 : 0) + j] = __uint_as_float(r2[j]);
+            for (int j = 0; j < 8; ++j) dst[(k32 ? 32 : 0) + (k16 ? 16 : 0) + j] = __uint_as_float(r2[j]) * ts[((k32 ? 32 : 0) + (k16 ? 16 : 0) + j) / TTW];
           }
         }
         quad_sync();  // all column shares of the rows are in shared memory
 
+        if (P.regular) {
+          // Regular case (PWC-Net, CorrelationLayer, FlowNetC in lattice mode): a tile row tr holds, for every query of this
+          // warp, the window row pi = ty0 + tr - (oy - md) as Pw consecutive accumulator columns starting at xoff.  The
+          // warps of a quadrant take tile rows round-robin; a store instruction covers one (pi, pj): 2 x 64 contiguous bytes.
+          const int mdh = (P.Ph - 1) >> 1, mdw = (P.Pw - 1) >> 1;
+          const int xoff = ox - mdw - tx0;
+          const int b_lo = max(0, mdw - ox), b_hi = min(P.Pw - 1, W_ - 1 - ox + mdw);  // window columns inside the image
+          const bool x_inside = qx0 - mdw >= 0 && qx0 + QTW - 1 + mdw < W_ && qx0 + QTW <= it.ow_;  // CTA-uniform: no clipping in x
+          const unsigned o_d = (unsigned)(g * P.Ph * P.Pw) * uplane;
+          auto rows = [&](auto act_tag) {
+            constexpr bool ACT = decltype(act_tag)::value;
+            for (int tr = part; tr < TTH && ty0 + tr <= ty1; tr += EPI_SPLIT) {
+              const int pi = ty0 + tr - oy + mdh;
+              if (!(q_ok && pi >= 0 && pi < P.Ph)) continue;
+              const float* srow = Srow + tr * TTW + xoff;
+              float* o = out_q + (o_d + (unsigned)(pi * P.Pw) * uplane);
+              if (x_inside) {
+                int pj = 0;
+                for (; pj + 3 <= P.Pw; pj += 3) {  // three independent load -> store chains in flight
+                  float w0 = srow[pj] * deq, w1 = srow[pj + 1] * deq, w2 = srow[pj + 2] * deq;
+                  if (ACT) {
+                    w0 = w0 >= 0.f ? w0 : w0 * P.slope;
+                    w1 = w1 >= 0.f ? w1 : w1 * P.slope;
+                    w2 = w2 >= 0.f ? w2 : w2 * P.slope;
+                  }
+                  o[0] = w0;
+                  o[uplane] = w1;
+                  o[2 * uplane] = w2;
+                  o += 3 * uplane;
+                }
+                for (; pj < P.Pw; ++pj) {
+                  float w = srow[pj] * deq;
+                  if (ACT) w = w >= 0.f ? w : w * P.slope;
+                  *o = w;
+                  o += uplane;
+                }
+              } else {
+                for (int pj = b_lo; pj <= b_hi; ++pj) {
+                  float w = srow[pj] * deq;
+                  if (ACT) w = w >= 0.f ? w : w * P.slope;
+                  o[(unsigned)pj * uplane] = w;
+                }
+              }
+            }
+          };
+          if (P.slope != 1.f) rows(std::true_type{});
+          else rows(std::false_type{});
+        } else
         for (int d = 0; d < P.D; ++d) {
           const int dph = P.dph[d], dpw = P.dpw[d];
           if (P.D > 1) {  // CTA-uniform early out: this dilation's box around the query tile does not reach the target tile
@@ -510,8 +586,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 }
 
 struct Workspace {
-  unsigned int* amax;  // [2][BG]
-  __half* in1h;        // queries: (BG, oh, ow, Cp)
+  float* qscale;  // [BG * lat^2][oh]
+  float* tscale;  // [BG][H]
+  __half* in1h;   // queries: (BG * lat^2, oh, ow, Cp)
   __half* in2h;
 };
 
@@ -524,13 +601,16 @@ static size_t ws_layout(int BG, int C, int H, int W, int padh, int padw, void* b
     p += bytes;
     return r;
   };
-  const uintptr_t amax = take((size_t)2 * BG * 4, 256);
+  // lattice mode: lat^2 classes of ceil(H / lat) <= (H + lat) / lat rows each, lat <= 8
+  const uintptr_t qsc = take((size_t)BG * 8 * (H + 2 * padh + 8) * 4, 256);
+  const uintptr_t tsc = take((size_t)BG * H * 4, 256);
   // queries: (oh, ow) <= (H + 2 padh, W + 2 padw) pixels per map (stride only shrinks it)
   // (+8: in lattice mode every residue class is rounded up to the size of class (0,0))
   const uintptr_t a = take((size_t)BG * (H + 2 * padh + 8) * (W + 2 * padw + 8) * Cp * 2, 1024);
   const uintptr_t b = take((size_t)BG * H * W * Cp * 2, 1024);
   if (ws) {
-    ws->amax = reinterpret_cast<unsigned int*>(amax);
+    ws->qscale = reinterpret_cast<float*>(qsc);
+    ws->tscale = reinterpret_cast<float*>(tsc);
     ws->in1h = reinterpret_cast<__half*>(a);
     ws->in2h = reinterpret_cast<__half*>(b);
   }
@@ -560,7 +640,6 @@ int local_corr_tc_launch(const float* in1, const float* in2, const float* flow2,
   if (need > workspace_bytes) return fail(EZB_ERR_WORKSPACE, "workspace too small: need %zu, got %zu", need, workspace_bytes);
   EZB_REQUIRE(BG <= 65535, "batch too large for one launch (split it)");
 
-  if (int r = prep::launch_absmax(in1, in2, (long long)C * N, ws.amax, BG, st)) return r;
   const int out_h = cdiv(H + 2 * padh, sh), out_w = cdiv(W + 2 * padw, sw);
   // Lattice mode: one dilation lat > 1 at stride 1 without padding splits into lat^2 independent dilation-1 problems on
   // sub-lattices (4x fewer wasted products for FlowNetC's dilation_patch = 2); classes must still fill a query tile.
@@ -577,20 +656,18 @@ int local_corr_tc_launch(const float* in1, const float* in2, const float* flow2,
   const int* dpw_u = lat > 1 ? &one : dpw;
   EZB_REQUIRE((long long)BG * ncls <= 65535, "batch too large for one launch (split it)");
 
-  const bool dense_queries = lat == 1 && sh == 1 && sw == 1 && padh == 0 && padw == 0;  // queries = all pixels of in1
-  if (flow2) {  // targets = warp(in2, flow2), evaluated during the conversion
-    EZB_REQUIRE(2 * BG <= 65535, "batch too large for one launch (split it)");
-    warp_convert_kmajor_kernel<<<dim3(cdiv(N, 32), Cp / 64, dense_queries ? 2 * BG : BG), 256, 0, st>>>(
-        in2, flow2, ws.in2h, dense_queries ? in1 : nullptr, ws.in1h, ws.amax, BG, G, C, Cp, H, W);
-    EZB_LAUNCH_OK();
-  } else if (dense_queries) {  // one launch converts both tensors
-    if (int r = prep::launch_convert_kmajor2(in1, ws.in1h, in2, ws.in2h, ws.amax, BG, C, Cp, N, st)) return r;
-  } else {
-    if (int r = prep::launch_convert_kmajor(in2, ws.in2h, ws.amax + BG, BG, C, Cp, N, st)) return r;
-  }
-  if (!dense_queries) {  // strided / padded / per-class queries: gather only the query pixels of in1, (BG * ncls, oh, ow, Cp)
-    gather_queries_kmajor_kernel<<<dim3(cdiv(oh * ow, 32), Cp / 64, BG * ncls), 256, 0, st>>>(in1, ws.in1h, ws.amax, C, Cp, H, W, oh, ow,
-                                                                                             sh, sw, padh, padw, lat);
+  // one launch converts the targets (all of in2, optionally warped by flow2) and the queries (the query pixels of in1)
+  {
+    ConvJobs JJ;
+    ConvJob& T = JJ.j[0];
+    T.src = in2; T.flow = flow2; T.dst = ws.in2h; T.rowscale = ws.tscale;
+    T.C = C; T.Cp = Cp; T.H = H; T.W = W; T.oh = H; T.ow = W; T.sh = T.sw = 1; T.padh = T.padw = 0; T.lat = 1; T.nimg = BG; T.G = G;
+    ConvJob& Q = JJ.j[1];
+    Q.src = in1; Q.flow = nullptr; Q.dst = ws.in1h; Q.rowscale = ws.qscale;
+    Q.C = C; Q.Cp = Cp; Q.H = H; Q.W = W; Q.oh = oh; Q.ow = ow; Q.sh = sh; Q.sw = sw; Q.padh = padh; Q.padw = padw; Q.lat = lat;
+    Q.nimg = BG * ncls; Q.G = G;
+    EZB_REQUIRE((long long)BG * (1 + ncls) <= 65535, "batch too large for one launch (split it)");
+    convert_rows_kmajor_kernel<<<dim3(std::max(H, oh), 1, BG * (1 + ncls)), 256, 0, st>>>(JJ);
     EZB_LAUNCH_OK();
   }
 
@@ -620,9 +697,12 @@ int local_corr_tc_launch(const float* in1, const float* in2, const float* flow2,
   P.Ph = Ph; P.Pw = Pw; P.sh = sh; P.sw = sw; P.padh = padh; P.padw = padw;
   P.D = D; P.KB = Cp / BK;
   for (int d = 0; d < D; ++d) { P.dph[d] = dph_u[d]; P.dpw[d] = dpw_u[d]; }
+  P.regular = (D == 1 && dph_u[0] == 1 && dpw_u[0] == 1 && sh == 1 && sw == 1 && padh == 0 && padw == 0 && TTW != 16 &&
+               getenv("EZB_LOCAL_CORR_GENERIC_EXTRACT") == nullptr) ? 1 : 0;
   P.lat = lat; P.BG = BG; P.Hf = H; P.Wf = W; P.out_h = out_h; P.out_w = out_w;
   P.slope = slope;
-  P.amax = ws.amax;
+  P.qscale = ws.qscale;
+  P.tscale = ws.tscale;
   P.scale = scale;
   P.out = out;
   P.out_bstride = out_bstride;
