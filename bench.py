@@ -374,11 +374,46 @@ def run_secondary(args, dev, world, rank, peaks, headline_step):
         (ms,) = max_over_ranks([ts[len(ts) // 2]], device=dev)
         return ms
 
+    def timed_graph(fn, iters=10):
+        """The same call sequence captured once into a CUDA graph and replayed: device time without the Python / ctypes launch
+        path, which dominates eager timings of ops that take tens of microseconds.  None when capture is not possible."""
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                fn()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            for _ in range(3):
+                g.replay()
+            ts = []
+            for _ in range(iters):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                g.replay()
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            ts.sort()
+            (ms,) = max_over_ranks([ts[len(ts) // 2]], device=dev)
+            del g
+            return ms
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write(f"bench: CUDA-graph capture failed ({e!r})\n")
+            torch.cuda.synchronize()
+            return None
+
     def add(name, ms, nbytes, note, **extra):
         rec = {"name": name, "ms": ms, "algorithmic_bytes": nbytes, "gbs": nbytes / ms / 1e6 if ms > 0 else None,
                "frac": (nbytes / ms / 1e6) / peaks["hbm_gbs"] if ms > 0 else None, "bound": "hbm", "traffic": traffic.get(name),
                "note": note}
         rec.update(extra)
+        if rec.get("ms_graph"):
+            rec["frac_graph"] = (nbytes / rec["ms_graph"] / 1e6) / peaks["hbm_gbs"]
         records.append(rec)
 
     def enabled(name):
@@ -391,7 +426,8 @@ def run_secondary(args, dev, world, rank, peaks, headline_step):
             nb_f = 2 * x1.numel() * 4 + 8 * 441 * 48 * 64 * 4
             t_f = timed(lambda: m(x1, x2))
             if enabled("cfg2_flownetc_corr_fwd"):
-                add("cfg2_flownetc_corr_fwd", t_f, nb_f, "IterSpatialCorrelationSampler P=21 dilation_patch=2 on (8,256,48,64) x2 (BASELINE config 2)")
+                add("cfg2_flownetc_corr_fwd", t_f, nb_f, "IterSpatialCorrelationSampler P=21 dilation_patch=2 on (8,256,48,64) x2 (BASELINE config 2)",
+                    ms_graph=timed_graph(lambda: m(x1, x2)))
             if enabled("cfg2_flownetc_corr_bwd"):
                 with torch.enable_grad():
                     a, b = x1.clone().requires_grad_(True), x2.clone().requires_grad_(True)
@@ -412,13 +448,15 @@ def run_secondary(args, dev, world, rank, peaks, headline_step):
             nb = sum(2 * a.numel() * 4 + 8 * 81 * a.shape[2] * a.shape[3] * 4 for a, _, _ in xs)
             if enabled("cfg3_pwc_corr_fwd"):
                 add("cfg3_pwc_corr_fwd", timed(lambda: [m(a, b) for a, b, _ in xs]), nb,
-                    "IterSpatialCorrelationSampler P=9 on the 5 PWC-Net levels, batch 8, 448x1024 input (BASELINE config 3, no warp)")
+                    "IterSpatialCorrelationSampler P=9 on the 5 PWC-Net levels, batch 8, 448x1024 input (BASELINE config 3, no warp)",
+                    ms_graph=timed_graph(lambda: [m(a, b) for a, b, _ in xs]))
             if enabled("cfg3_pwc_warp_corr_leaky_fused"):
                 mf = E.IterSpatialCorrelationSampler(kernel_size=1, patch_size=9, padding=0)
                 mf.fused_negative_slope = 0.1
                 add("cfg3_pwc_warp_corr_leaky_fused", timed(lambda: [mf(a, E.lazy_warp(b, f) if i > 0 else b) for i, (a, b, f) in enumerate(xs)]),
                     nb + sum(f.numel() * 4 for _, _, f in xs[1:]),
-                    "PWC decoder step as one kernel chain per level: warp -> correlation -> LeakyReLU(0.1) (reference decoder/pyramid.py:98-102,138-141)")
+                    "PWC decoder step as one kernel chain per level: warp -> correlation -> LeakyReLU(0.1) (reference decoder/pyramid.py:98-102,138-141)",
+                    ms_graph=timed_graph(lambda: [mf(a, E.lazy_warp(b, f) if i > 0 else b) for i, (a, b, f) in enumerate(xs)]))
             if enabled("cfg3_pwc_finest_bwd"):
                 a0, b0, _ = xs[-1]
                 t_f = timed(lambda: m(a0, b0))
@@ -438,7 +476,8 @@ def run_secondary(args, dev, world, rank, peaks, headline_step):
             xb = [torch.randn(4, 128, 192, 384, device=dev), torch.randn(4, 256, 48, 96, device=dev)]
             mm = E.MatryoshkaDilatedCostVolumeList().to(dev)
             add("cfg4_dcvnet_matryoshka_fwd", timed(lambda: mm(xa, xb)), int(240.0e6),
-                "MatryoshkaDilatedCostVolumeList on (4,128,192,384)+(4,256,48,96) feature pairs (BASELINE config 4)")
+                "MatryoshkaDilatedCostVolumeList on (4,128,192,384)+(4,256,48,96) feature pairs (BASELINE config 4)",
+                ms_graph=timed_graph(lambda: mm(xa, xb)))
             del xa, xb
     torch.cuda.empty_cache()
 

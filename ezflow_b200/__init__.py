@@ -17,7 +17,9 @@ from .similarity import (
     MatryoshkaDilatedCostVolume,
     MatryoshkaDilatedCostVolumeList,
     MutliScalePairwise4DCorr,
+    OnDemandPairwise4DCorr,
     WarpedFeatures,
+    dicl_cost_volume,
     get_local_corr_mode,
     get_pyramid_dtype,
     iter_spatial_correlation_sample,
@@ -25,6 +27,7 @@ from .similarity import (
     lookup_conv1x1,
     set_local_corr_mode,
     set_pyramid_dtype,
+    vcn_corr,
 )
 from .utils import convex_upsample_flow, coords_grid, warp
 

@@ -60,6 +60,13 @@ _SIGNATURES = {
     "ezb_l2_normalize_fwd": ([c_vp, c_int, c_int, c_int, c_f32, c_vp, c_vp], c_int),
     "ezb_warp_fwd": ([c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp], c_int),
     "ezb_warp_bwd": ([c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp], c_int),
+    "ezb_vcn_corr_fwd": ([c_vp, c_vp] + [c_int] * 6 + [c_f32, c_vp, c_vp], c_int),
+    "ezb_vcn_corr_bwd": ([c_vp, c_vp, c_vp] + [c_int] * 6 + [c_f32, c_vp, c_vp, c_vp], c_int),
+    "ezb_dicl_volume_fwd": ([c_vp, c_vp] + [c_int] * 7 + [c_vp, c_vp, c_vp], c_int),
+    "ezb_dicl_volume_bwd": ([c_vp, c_vp] + [c_int] * 6 + [c_vp, c_vp, c_vp], c_int),
+    "ezb_corr_ondemand_workspace_bytes": ([c_int] * 5 + [_P(c_sz)], c_int),
+    "ezb_corr_ondemand_prepare": ([c_vp, c_vp] + [c_int] * 5 + [c_vp, c_sz, c_vp], c_int),
+    "ezb_corr_ondemand_lookup": ([c_vp, c_vp] + [c_int] * 6 + [c_vp, c_vp], c_int),
     "ezb_convex_upsample_fwd": ([c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp], c_int),
     "ezb_convex_upsample_bwd_workspace_bytes": ([c_int, c_int, c_int, c_int, _P(c_sz)], c_int),
     "ezb_convex_upsample_bwd": ([c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_sz, c_vp], c_int),

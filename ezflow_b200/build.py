@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIBPATH = os.path.join(LIBDIR, "libezflow_b200.so")
 SOURCES = ["cabi.cu", "corr_pyramid.cu", "corr_lookup.cu", "corr_lookup_conv.cu", "corr_bwd.cu", "corr_bwd_tc.cu", "local_corr.cu", "local_corr_tc.cu", "warp.cu",
-           "convex_upsample.cu"]
+           "convex_upsample.cu", "volume_ops.cu"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",

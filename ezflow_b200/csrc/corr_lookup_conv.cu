@@ -24,6 +24,8 @@
 #include "ezb_ptx.cuh"
 #include "ezb_tma.cuh"
 
+#include <type_traits>
+
 namespace ezb {
 namespace k3c {
 
@@ -231,6 +233,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) lookup_conv1x1_kernel(const __
     if (n_stages > 0) issue_gather(0);
     const int gq = warp & 3, part = warp >> 2;  // query group (= TMEM lane quadrant) and share of the window columns
     const int qrow = gq * 32 + lane;  // A row / TMEM lane of this thread's query
+    // this warp's share of the window columns i: K columns dealt to the 4 parts (at most 3 each for K <= 9).  The share is
+    // fixed for the whole kernel, so the swizzled byte offsets of the thread's tap-slot pairs are computed once.
+    const int i0 = (K * part) >> 2, ni = ((K * (part + 1)) >> 2) - i0;
+    const int swz = (qrow >> 1) & 3;
+    uint32_t soff[3][5];  // [column a][pair m]: offset (inside the A row's k-blocks) of slots (i0 + a, 2m), (i0 + a, 2m + 1)
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int m = 0; m < 5; ++m) {
+        const int t = tap_slot(K, i0 + a, 2 * m);
+        soff[a][m] = (uint32_t)((t >> 5) * A_KB_BYTES + ((((t >> 3) & 3) ^ swz) << 4) + (t & 7) * 2);
+      }
     for (int s = 0; s < n_stages; ++s) {
       const int ti = s / P.L, l = s - ti * P.L;
       // stage s + 1 goes into the buffer stage s - 1 was read from (everybody left it at the barrier that ended iteration
@@ -250,18 +264,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) lookup_conv1x1_kernel(const __
       const float wl0 = 1.f - fx, wl1 = fx;
       const int xs = max(-D, min(P.W >> l, floor_clamped(cx) - r));
       const int off = xs - ((((xs + 64) >> 3) - 8) << 3);  // taps start `off` pixels into the fetched row
-      // this warp's share of the window columns i: K columns dealt to the 4 parts (at most 3 each for K <= 9), the
-      // remainder rotating with the level
-      const int pr = (part + l) & 3;
-      const int i0 = (K * pr) >> 2, ni = ((K * (pr + 1)) >> 2) - i0;
       const __half* pl = reinterpret_cast<const __half*>(base_ptr + SMEM_STG + (s & 1) * STG_BYTES + qrow * QSTRIDE) + off + i0;
 
       const int abuf = s & 1;
       ptx::mbar_wait(a_empty(abuf), (((uint32_t)s >> 1) & 1u) ^ 1u);  // the MMAs that read this buffer two stages ago are done
       uint8_t* arow = base_ptr + SMEM_A + abuf * (KBS * A_KB_BYTES) + qrow * 64;
-      const int swz = (qrow >> 1) & 3;
-      // byte offset (inside the row's k-blocks) of the aligned slot pair starting at even slot t
-      auto pair_off = [&](int t) { return (uint32_t)((t >> 5) * A_KB_BYTES + ((((t >> 3) & 3) ^ swz) << 4) + (t & 7) * 2); };
       // Walk down the window rows once: a row's ni + 1 pixels give the ni horizontally interpolated values, two
       // consecutive rows give the taps (i, j); taps (i, 2m), (i, 2m + 1) leave as one half2.
       float top[3], held[3];
@@ -274,7 +281,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) lookup_conv1x1_kernel(const __
       };
       hrow(pl, top);
       const __half* p = pl;
-      auto body = [&](int j) {
+      auto body = [&](int j, auto unrolled_tag) {
         p += ROW_EL;
         float bot[3];
         hrow(p, bot);
@@ -283,18 +290,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) lookup_conv1x1_kernel(const __
           const float v = top[a] + fy * (bot[a] - top[a]);
           top[a] = bot[a];
           if (a < ni) {
-            const int t = tap_slot(K, i0 + a, j);
-            if (j & 1) *reinterpret_cast<__half2*>(arow + pair_off(t - 1)) = __floats2half2_rn(held[a], v);
-            else if (j == K - 1) *reinterpret_cast<__half*>(arow + pair_off(t)) = __float2half_rn(v);  // odd K: the last tap is alone
+            uint32_t so;
+            if constexpr (decltype(unrolled_tag)::value) {
+              so = soff[a][j >> 1];  // compile-time indices: registers
+            } else {
+              const int t = tap_slot(K, i0 + a, j & ~1);
+              so = (uint32_t)((t >> 5) * A_KB_BYTES + ((((t >> 3) & 3) ^ swz) << 4) + (t & 7) * 2);
+            }
+            if (j & 1) *reinterpret_cast<__half2*>(arow + so) = __floats2half2_rn(held[a], v);
+            else if (j == K - 1) *reinterpret_cast<__half*>(arow + so) = __float2half_rn(v);  // odd K: the last tap is alone
             else held[a] = v;
           }
         }
       };
       if (K == 9) {
 #pragma unroll
-        for (int j = 0; j < 9; ++j) body(j);
+        for (int j = 0; j < 9; ++j) body(j, std::true_type{});
       } else {
-        for (int j = 0; j < K; ++j) body(j);
+        for (int j = 0; j < K; ++j) body(j, std::false_type{});
       }
       fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
       __syncwarp();
@@ -307,17 +320,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) lookup_conv1x1_kernel(const __
       const uint32_t idesc = ptx::umma_idesc(/*f16*/ 0, TQ, (uint32_t)P.Np);
       for (int s = 0; s < n_stages; ++s) {
         const int ti = s / P.L, l = s - ti * P.L;
-        mbar_wait_backoff(b_empty, ((uint32_t)s & 1u) ^ 1u, 32);  // MMAs of stage s - 1 (the previous user of the weight buffer) are done
+        mbar_wait_backoff(b_empty, ((uint32_t)s & 1u) ^ 1u, 100);  // MMAs of stage s - 1 (the previous user of the weight buffer) are done
         ptx::mbar_expect_tx(b_full, (uint32_t)(KBS * B_KB_BYTES));
         for (int kb = 0; kb < KBS; ++kb)
           ptx::tma_load_2d_hint(sB + kb * B_KB_BYTES, &tmW, b_full, l * KL + kb * KB_EL, 0, ptx::kEvictLast);
         const int dbuf = ti & 1;
         if (l == 0) {
-          mbar_wait_backoff(d_empty(dbuf), (((uint32_t)ti >> 1) & 1u) ^ 1u, 32);
+          mbar_wait_backoff(d_empty(dbuf), (((uint32_t)ti >> 1) & 1u) ^ 1u, 200);
           ptx::tc_fence_after();
         }
-        mbar_wait_backoff(b_full, (uint32_t)s & 1u, 32);
-        mbar_wait_backoff(a_full(s & 1), ((uint32_t)s >> 1) & 1u, 64);
+        mbar_wait_backoff(b_full, (uint32_t)s & 1u, 100);
+        mbar_wait_backoff(a_full(s & 1), ((uint32_t)s >> 1) & 1u, 200);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + dbuf * N_MAX;
         const uint32_t a_base = sA + (s & 1) * (KBS * A_KB_BYTES);
@@ -343,7 +356,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) lookup_conv1x1_kernel(const __
       const int q = q0 + quad * 32 + lane;
       const float sc = __ldg(P.deq + b) * wscale;
       const int dbuf = ti & 1;
-      mbar_wait_backoff(d_full(dbuf), ((uint32_t)ti >> 1) & 1u, 256);
+      mbar_wait_backoff(d_full(dbuf), ((uint32_t)ti >> 1) & 1u, 1000);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + dbuf * N_MAX + ((uint32_t)(quad * 32) << 16);
       float* o = P.out + (long long)b * P.Cout * P.N + q;

@@ -59,7 +59,8 @@ struct Geo {
   static constexpr int SMEM_A = 0;
   static constexpr int SMEM_B = SMEM_A + KB_MAX * A_KB_BYTES;
   static constexpr int SMEM_S = SMEM_B + STAGES * B_STAGE_BYTES;
-  static constexpr int SMEM_BAR = SMEM_S + BM * S_STRIDE * 4;
+  static constexpr int SMEM_TS = SMEM_S + BM * S_STRIDE * 4;  // [4 quadrants][BN] power-of-two scales of the tile's target pixels
+  static constexpr int SMEM_BAR = SMEM_TS + 4 * BN * 4;
   static constexpr int SMEM_BYTES = SMEM_BAR + 256 + 1024;
   static_assert(CPW % 8 == 0 && CPW <= 56 && BN % 16 == 0 && SMEM_BYTES <= 232448 && (2 * STAGES + 4 + 2 * NACC) * 8 + 4 <= 256, "tile geometry");
 };
@@ -99,39 +100,52 @@ struct Params {
   int out_h, out_w;  // full output plane
   int dph[MAX_DIL], dpw[MAX_DIL];
   float slope;
-  const float* qscale;  // [BG * lat^2][oh] 2^e of every query row: the fp16 operand row was scaled by 2^-e
-  const float* tscale;  // [BG][Hf]       2^e of every in2 row
+  const float* qscale;  // [BG * lat^2][oh * ow] 2^e of every query pixel: its fp16 operand row was scaled by 2^-e
+  const float* tscale;  // [BG][Hf * Wf]         2^e of every in2 pixel
   float scale;          // user scale (CorrelationLayer: 1/C)
   float* out;
   long long out_bstride;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-// Operand conversion: fp32 NCHW -> fp16 K-major, one block per destination image row, per-row power-of-two scale.
-//   dst[img, oy, ox, c] = 2^-e(img,oy) * value(c, oy, ox),   rowscale[img * oh + oy] = 2^e,  e = floor(log2 max_row |value|)
+// Operand conversion: fp32 NCHW -> fp16 K-major with a power-of-two scale per PIXEL (= per operand row of the GEMM).
+//   dst[img, oy, ox, c] = 2^-e * value(c, oy, ox),   rowscale[img * oh * ow + oy * ow + ox] = 2^e,  e = floor(log2 max_c |value|)
 //   value = src[bg, c, oy*sh - padh, ox*sw - padw]  (0 outside the image or for c >= C), or, with a flow field, the
 //   bilinear warp of K5 (ezflow/utils/warp.py:5-42) evaluated at that pixel — the warped fp32 tensor is never written.
 // In lattice mode (queries of a dilation-lat problem) img = bg * lat^2 + class and the class (cy, cx) acts as a negative
-// padding with stride lat.  Sweep 1 finds the row's absmax, sweep 2 (same addresses: L2 hits) converts 32-pixel x 64-channel
-// chunks through a shared-memory transpose.  Up to two jobs (targets, queries) share one launch (blockIdx.z ranges).
+// padding with stride lat.  One pass over the inputs: no absmax kernel, no second read.  Up to two jobs (targets, queries)
+// share one launch (blockIdx.z ranges).
 struct ConvJob {
   const float* src;
   const float* flow;  // (B,2,H,W) or null
   __half* dst;
-  float* rowscale;
+  float* rowscale;  // one power-of-two scale per destination pixel
   int C, Cp, H, W, oh, ow, sh, sw, padh, padw, lat, nimg, G;
 };
 struct ConvJobs {
   ConvJob j[2];
+  int groups_per_block;
 };
 
-__global__ void __launch_bounds__(256) convert_rows_kmajor_kernel(const ConvJobs JJ) {
-  __shared__ float tile[64][33];
-  __shared__ float red[8];
+constexpr int CONV_THREADS = 256;
+constexpr int CONV_PX = 32;  // destination pixels per block
+
+// Block = 32 consecutive destination pixels of one image x all channels: one sweep loads them (coalesced along x, 8 loads in
+// flight per thread) into shared memory [Cp][33] while tracking every pixel's absmax, then a warp per pixel writes the
+// K-major row scaled by the pixel's own power of two.  33.8 KB of shared memory at C = 256: six blocks per SM.
+__global__ void __launch_bounds__(CONV_THREADS) convert_pixels_kmajor_kernel(const ConvJobs JJ) {
+  extern __shared__ float pxbuf[];  // [Cp][33]
+  __shared__ float red[CONV_THREADS / 32][CONV_PX];
+  __shared__ float s_scale[CONV_PX];
   const bool second = (int)blockIdx.z >= JJ.j[0].nimg;
   const ConvJob& J = JJ.j[second ? 1 : 0];
-  const int img = (int)blockIdx.z - (second ? JJ.j[0].nimg : 0), oy = blockIdx.x;
-  if (oy >= J.oh) return;
+  const int img = (int)blockIdx.z - (second ? JJ.j[0].nimg : 0);
+  const int npx = J.oh * J.ow;
+  // few channels: a block takes several 32-pixel groups in turn, so that it still moves >= 32 KB
+  const int gpb = JJ.groups_per_block;
+  for (int grp = 0; grp < gpb; ++grp) {
+  const int n0 = (blockIdx.x * gpb + grp) * CONV_PX;
+  if (n0 >= npx) return;
   int sh = J.sh, sw = J.sw, padh = J.padh, padw = J.padw, bg = img;
   if (J.lat > 1) {
     const int ncls = J.lat * J.lat, cls = img % ncls;
@@ -140,81 +154,86 @@ __global__ void __launch_bounds__(256) convert_rows_kmajor_kernel(const ConvJobs
     padh = -(cls / J.lat);
     padw = -(cls % J.lat);
   }
-  const int HW = J.H * J.W, y = oy * sh - padh;
-  const bool row_in = y >= 0 && y < J.H;
+  const int HW = J.H * J.W;
   const float* src = J.src + (long long)bg * J.C * HW;
   const float* fl = J.flow ? J.flow + (long long)(bg / J.G) * 2 * HW : nullptr;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = CONV_THREADS / 32;
 
-  // value of channel c at destination column ox (plain gather); the warp path goes through gather_at
-  auto gather_at = [&](int x) {  // taps of the warped pixel (x, y)
-    const k5::Taps t = k5::make_taps(__ldg(fl + y * J.W + x), __ldg(fl + HW + y * J.W + x), x, y, J.H, J.W);
-    return k5::make_gather(t, J.W);
-  };
-  auto warped = [&](const k5::Gather& g, const float* sp) {
-    return g.zero ? 0.f : ((g.w00 * __ldg(sp + g.oaa) + g.w01 * __ldg(sp + g.oab)) + (g.w10 * __ldg(sp + g.oba) + g.w11 * __ldg(sp + g.obb)));
-  };
-
-  // ---- sweep 1: absmax of the row.  Thread -> (column slot, channel slice): consecutive threads take consecutive columns
+  // ---- sweep 1: lane = pixel, the warps split the channels
+  const int n = n0 + lane;
+  const int oy = n / J.ow, ox = n - oy * J.ow;
+  const int y = oy * sh - padh, x = ox * sw - padw;
+  const bool in_img = n < npx && y >= 0 && y < J.H && x >= 0 && x < J.W;
   float m = 0.f;
-  if (row_in) {
-    int owp = 32;
-    while (owp < J.ow && owp < 256) owp <<= 1;
-    const int xs = threadIdx.x % owp, cs = threadIdx.x / owp, ncs = 256 / owp;
-    for (int ox = xs; ox < J.ow; ox += owp) {
-      const int x = ox * sw - padw;
-      if (x < 0 || x >= J.W) continue;
-      if (fl) {
-        const k5::Gather g = gather_at(x);
-        if (!g.zero)
-          for (int c = cs; c < J.C; c += ncs) m = fmaxf(m, fabsf(warped(g, src + (long long)c * HW)));
-      } else {
-        const float* sp = src + (long long)y * J.W + x;
-        int c = cs;
-        for (; c + 3 * ncs < J.C; c += 4 * ncs) {  // four independent loads in flight
-          const float a0 = __ldg(sp + (long long)c * HW), a1 = __ldg(sp + (long long)(c + ncs) * HW);
-          const float a2 = __ldg(sp + (long long)(c + 2 * ncs) * HW), a3 = __ldg(sp + (long long)(c + 3 * ncs) * HW);
-          m = fmaxf(m, fmaxf(fmaxf(fabsf(a0), fabsf(a1)), fmaxf(fabsf(a2), fabsf(a3))));
-        }
-        for (; c < J.C; c += ncs) m = fmaxf(m, fabsf(__ldg(sp + (long long)c * HW)));
-      }
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if (lane == 0) red[warp] = m;
-  __syncthreads();
-  m = fmaxf(fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])), fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7])));
-  const int eb = (int)((__float_as_uint(m) >> 23) & 0xff);
-  const int e = (eb == 0 || eb == 255) ? 0 : max(-126, min(126, eb - 127));  // 0 for an all-zero row
-  const float sc = __uint_as_float((unsigned int)(127 - e) << 23);
-  if (threadIdx.x == 0) J.rowscale[(long long)img * J.oh + oy] = __uint_as_float((unsigned int)(127 + e) << 23);
-
-  // ---- sweep 2: convert 32-pixel x 64-channel chunks
-  __half* drow = J.dst + ((long long)img * J.oh + oy) * J.ow * J.Cp;
-  for (int x0 = 0; x0 < J.ow; x0 += 32) {
-    const int ox = x0 + lane, x = ox * sw - padw;
-    const bool in_img = row_in && ox < J.ow && x >= 0 && x < J.W;
+  if (fl) {
     k5::Gather g;
     g.zero = true;
-    if (fl && in_img) g = gather_at(x);
-    for (int c0 = 0; c0 < J.Cp; c0 += 64) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int c = c0 + warp * 8 + i;
-        float v = 0.f;
-        if (in_img && c < J.C) v = fl ? warped(g, src + (long long)c * HW) : __ldg(src + (long long)c * HW + (long long)y * J.W + x);
-        tile[warp * 8 + i][lane] = v * sc;
-      }
-      __syncthreads();
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int nl = warp * 4 + i;
-        if (x0 + nl < J.ow)
-          *reinterpret_cast<__half2*>(drow + (long long)(x0 + nl) * J.Cp + c0 + 2 * lane) = __floats2half2_rn(tile[2 * lane][nl], tile[2 * lane + 1][nl]);
-      }
-      __syncthreads();
+    if (in_img) {
+      const k5::Taps t = k5::make_taps(__ldg(fl + y * J.W + x), __ldg(fl + HW + y * J.W + x), x, y, J.H, J.W);
+      g = k5::make_gather(t, J.W);
     }
+    for (int c = warp; c < J.Cp; c += NW) {
+      float v = 0.f;
+      if (c < J.C && !g.zero) {
+        const float* sp = src + (long long)c * HW;
+        v = (g.w00 * __ldg(sp + g.oaa) + g.w01 * __ldg(sp + g.oab)) + (g.w10 * __ldg(sp + g.oba) + g.w11 * __ldg(sp + g.obb));
+      }
+      m = fmaxf(m, fabsf(v));
+      pxbuf[c * 33 + lane] = v;
+    }
+  } else {
+    const float* sp = src + (long long)y * J.W + x;
+    int c = warp;
+    for (; c + 7 * NW < J.C; c += 8 * NW) {  // eight independent loads in flight
+      float a[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] = in_img ? __ldg(sp + (long long)(c + u * NW) * HW) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        m = fmaxf(m, fabsf(a[u]));
+        pxbuf[(c + u * NW) * 33 + lane] = a[u];
+      }
+    }
+    for (; c + 3 * NW < J.Cp; c += 4 * NW) {  // remaining channels, four loads in flight (rows up to Cp are zero-filled)
+      float a[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a[u] = (in_img && c + u * NW < J.C) ? __ldg(sp + (long long)(c + u * NW) * HW) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        m = fmaxf(m, fabsf(a[u]));
+        pxbuf[(c + u * NW) * 33 + lane] = a[u];
+      }
+    }
+    for (; c < J.Cp; c += NW) {
+      const float v = (in_img && c < J.C) ? __ldg(sp + (long long)c * HW) : 0.f;
+      m = fmaxf(m, fabsf(v));
+      pxbuf[c * 33 + lane] = v;
+    }
+  }
+  red[warp][lane] = m;
+  __syncthreads();
+  if (warp == 0) {
+    float mm = red[0][lane];
+#pragma unroll
+    for (int i = 1; i < NW; ++i) mm = fmaxf(mm, red[i][lane]);
+    const int eb = (int)((__float_as_uint(mm) >> 23) & 0xff);
+    const int e = (eb == 0 || eb == 255) ? 0 : max(-126, min(126, eb - 127));  // 0 for an all-zero pixel
+    s_scale[lane] = __uint_as_float((unsigned int)(127 - e) << 23);
+    if (n < npx) J.rowscale[(long long)img * npx + n] = __uint_as_float((unsigned int)(127 + e) << 23);
+  }
+  __syncthreads();
+
+  // ---- sweep 2: a warp per pixel, a lane per channel pair of a 64-channel chunk (128-byte stores)
+  __half* dimg = J.dst + (long long)img * npx * J.Cp;
+  for (int pl = warp; pl < CONV_PX && n0 + pl < npx; pl += NW) {
+    const float sc = s_scale[pl];
+    for (int c0 = 0; c0 < J.Cp; c0 += 64) {
+      const int c = c0 + 2 * lane;
+      *reinterpret_cast<__half2*>(dimg + (long long)(n0 + pl) * J.Cp + c) = __floats2half2_rn(pxbuf[c * 33 + pl] * sc, pxbuf[(c + 1) * 33 + pl] * sc);
+    }
+  }
+  __syncthreads();  // the buffers are reused by the next group
   }
 }
 
@@ -236,6 +255,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   uint8_t* base_ptr = smem_raw + (base - raw_addr);
   const uint32_t sA = base + SMEM_A, sB = base + SMEM_B, sBar = base + SMEM_BAR;
   float* S = reinterpret_cast<float*>(base_ptr + SMEM_S);
+  float* TS = reinterpret_cast<float*>(base_ptr + G::SMEM_TS);
   auto full_bar = [&](int s) { return sBar + 8u * s; };
   auto empty_bar = [&](int s) { return sBar + 8u * (STAGES + s); };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -389,6 +409,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     const int q = quad * 32 + lane;
     const long long plane = (long long)P.out_h * P.out_w;
     float* Srow = S + q * S_STRIDE;
+    float* tsq = TS + quad * BN;  // this quadrant's target-pixel scales of the current tile
     auto quad_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "n"(32 * EPI_SPLIT) : "memory"); };
     int tcount = 0;
     for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
@@ -399,8 +420,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       const bool q_ok = oy < it.oh_ && ox < it.ow_;
       const int b = fdiv(it.bg, P.d_G), g = it.bg - b * P.G;
       // power-of-two factors of the operand rows: the query row's is folded into deq, the target rows' into the drain below
-      const float deq = P.scale * (q_ok ? __ldg(P.qscale + (long long)it.zq * P.oh + oy) : 0.f);
-      const float* trow_scale = P.tscale + (long long)it.bg * P.Hf;
+      const float deq = P.scale * (q_ok ? __ldg(P.qscale + ((long long)it.zq * P.oh + oy) * P.ow + ox) : 0.f);
+      const float* tpix_scale = P.tscale + (long long)it.bg * P.Hf * P.Wf;
       // offsets inside one batch entry of the output fit 32 bits (checked by the launcher): one IMAD per store address
       float* out_q = P.out + (long long)b * P.out_bstride + (long long)(it.cy + P.lat * oy) * P.out_w + (it.cx + P.lat * ox);
       const unsigned uplane = (unsigned)plane;
@@ -441,12 +462,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           if constexpr (k32) ptx::tmem_ld_32x32b_x32(taddr, r0);
           if constexpr (k16) ptx::tmem_ld_32x32b_x16(taddr + (k32 ? 32 : 0), r1);
           if constexpr (k8) ptx::tmem_ld_32x32b_x8(taddr + (k32 ? 32 : 0) + (k16 ? 16 : 0), r2);
-          // this warp's columns are the target-tile rows [part * RPW, (part + 1) * RPW): their in2 row scales
-          constexpr int RPW = CPW / TTW;
-          static_assert(CPW % TTW == 0 && RPW >= 1, "an epilogue warp's columns are whole target-tile rows");
-          float ts[RPW];
-#pragma unroll
-          for (int u = 0; u < RPW; ++u) ts[u] = __ldg(trow_scale + min(it.cy + P.lat * (ty0 + part * RPW + u), P.Hf - 1));
+          // power-of-two scales of the target pixels behind this warp's CPW accumulator columns -> the quadrant's scale row
+          // (applied when an element is extracted: far fewer elements are extracted than drained)
+          {
+            auto col_scale = [&](int col) {
+              const int tyr = col / TTW, txr = col - tyr * TTW;
+              const int yy = it.cy + P.lat * (ty0 + tyr), xx = it.cx + P.lat * (tx0 + txr);
+              return (yy < P.Hf && xx < P.Wf) ? __ldg(tpix_scale + (long long)yy * P.Wf + xx) : 0.f;
+            };
+            if (lane < CPW) tsq[part * CPW + lane] = col_scale(part * CPW + lane);
+            if constexpr (CPW > 32) {
+              if (lane + 32 < CPW) tsq[part * CPW + 32 + lane] = col_scale(part * CPW + 32 + lane);
+            }
+          }
           ptx::tmem_ld_wait();
           ptx::tc_fence_before();
           __syncwarp();
@@ -454,18 +482,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           float* dst = Srow + part * CPW;
           if constexpr (k32) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) dst[j] = __uint_as_float(r0[j]) * ts[j / TTW];
+            for (int j = 0; j < 32; ++j) dst[j] = __uint_as_float(r0[j]);
           }
           if constexpr (k16) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) dst[(k32 ? 32 : 0) + j] = __uint_as_float(r1[j]) * ts[((k32 ? 32 : 0) + j) / TTW];
+            for (int j = 0; j < 16; ++j) dst[(k32 ? 32 : 0) + j] = __uint_as_float(r1[j]);
           }
           if constexpr (k8) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[(k32 ? 32 : 0) + (k16 ? 16 : 0) + j] = __uint_as_float(r2[j]) * ts[((k32 ? 32 : 0) + (k16 ? 16 : 0) + j) / TTW];
+            for (int j = 0; j < 8; ++j) dst[(k32 ? 32 : 0) + (k16 ? 16 : 0) + j] = __uint_as_float(r2[j]);
           }
         }
-        quad_sync();  // all column shares of the rows are in shared memory
+        // regular case: a warp extracts exactly the tile rows it drained itself, so the warps of a quadrant never wait for
+        // each other and drift apart over the accumulators (one tile's extraction overlaps the next tile's drain)
+        if (P.regular == 1) __syncwarp(); else quad_sync();  // all column shares of the rows are in shared memory
 
         if (P.regular) {
           // Regular case (PWC-Net, CorrelationLayer, FlowNetC in lattice mode): a tile row tr holds, for every query of this
@@ -478,15 +508,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           const unsigned o_d = (unsigned)(g * P.Ph * P.Pw) * uplane;
           auto rows = [&](auto act_tag) {
             constexpr bool ACT = decltype(act_tag)::value;
-            for (int tr = part; tr < TTH && ty0 + tr <= ty1; tr += EPI_SPLIT) {
+            constexpr int RPW = CPW / TTW;  // tile rows per epilogue warp: its own accumulator columns
+            static_assert(CPW % TTW == 0, "an epilogue warp's columns are whole target-tile rows");
+            for (int tr = part * RPW; tr < (part + 1) * RPW && ty0 + tr <= ty1; ++tr) {
               const int pi = ty0 + tr - oy + mdh;
               if (!(q_ok && pi >= 0 && pi < P.Ph)) continue;
               const float* srow = Srow + tr * TTW + xoff;
+              const float* trow = tsq + tr * TTW + xoff;
               float* o = out_q + (o_d + (unsigned)(pi * P.Pw) * uplane);
               if (x_inside) {
                 int pj = 0;
                 for (; pj + 3 <= P.Pw; pj += 3) {  // three independent load -> store chains in flight
-                  float w0 = srow[pj] * deq, w1 = srow[pj + 1] * deq, w2 = srow[pj + 2] * deq;
+                  float w0 = srow[pj] * (trow[pj] * deq), w1 = srow[pj + 1] * (trow[pj + 1] * deq), w2 = srow[pj + 2] * (trow[pj + 2] * deq);
                   if (ACT) {
                     w0 = w0 >= 0.f ? w0 : w0 * P.slope;
                     w1 = w1 >= 0.f ? w1 : w1 * P.slope;
@@ -498,14 +531,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                   o += 3 * uplane;
                 }
                 for (; pj < P.Pw; ++pj) {
-                  float w = srow[pj] * deq;
+                  float w = srow[pj] * (trow[pj] * deq);
                   if (ACT) w = w >= 0.f ? w : w * P.slope;
                   *o = w;
                   o += uplane;
                 }
               } else {
                 for (int pj = b_lo; pj <= b_hi; ++pj) {
-                  float w = srow[pj] * deq;
+                  float w = srow[pj] * (trow[pj] * deq);
                   if (ACT) w = w >= 0.f ? w : w * P.slope;
                   o[(unsigned)pj * uplane] = w;
                 }
@@ -548,14 +581,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
               ci += EPI_SPLIT;
               while (ci >= nchunk) { ci -= nchunk; ++ai; }
               const bool row_ok = a >= a_lo && a <= a_hi;
-              const float* srow = Srow + (y2_0 + a * dph - ty0) * TTW + (x2_0 - tx0) + bb * dpw;
+              const int col0 = (y2_0 + a * dph - ty0) * TTW + (x2_0 - tx0) + bb * dpw;
+              const float* srow = Srow + col0;
+              const float* trow = tsq + col0;
               const unsigned o_ab = o_d + (unsigned)(a * P.Pw + bb) * uplane;
               float v[CH];
               bool ok[CH];
 #pragma unroll
               for (int u = 0; u < CH; ++u) {  // CH independent load -> store chains in flight
                 ok[u] = row_ok && bb + u >= b_lo && bb + u <= b_hi;
-                v[u] = ok[u] ? srow[u * dpw] : 0.f;
+                v[u] = ok[u] ? srow[u * dpw] * trow[u * dpw] : 0.f;
               }
 #pragma unroll
               for (int u = 0; u < CH; ++u) {
@@ -575,7 +610,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             else extract(std::integral_constant<int, 4>{}, std::false_type{});
           }
         }
-        quad_sync();  // every warp is done with the rows before the next tile overwrites them
+        if (P.regular == 1) __syncwarp(); else quad_sync();  // every warp is done with the rows before the next tile overwrites them
       }
     }
   }
@@ -586,8 +621,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 }
 
 struct Workspace {
-  float* qscale;  // [BG * lat^2][oh]
-  float* tscale;  // [BG][H]
+  float* qscale;  // [BG * lat^2][oh * ow]
+  float* tscale;  // [BG][H * W]
   __half* in1h;   // queries: (BG * lat^2, oh, ow, Cp)
   __half* in2h;
 };
@@ -601,9 +636,9 @@ static size_t ws_layout(int BG, int C, int H, int W, int padh, int padw, void* b
     p += bytes;
     return r;
   };
-  // lattice mode: lat^2 classes of ceil(H / lat) <= (H + lat) / lat rows each, lat <= 8
-  const uintptr_t qsc = take((size_t)BG * 8 * (H + 2 * padh + 8) * 4, 256);
-  const uintptr_t tsc = take((size_t)BG * H * 4, 256);
+  // one scale per operand pixel (the query tensor is at most (H + 2 padh + 8) x (W + 2 padw + 8) pixels per image, see below)
+  const uintptr_t qsc = take((size_t)BG * (H + 2 * padh + 8) * (W + 2 * padw + 8) * 4, 256);
+  const uintptr_t tsc = take((size_t)BG * H * W * 4, 256);
   // queries: (oh, ow) <= (H + 2 padh, W + 2 padw) pixels per map (stride only shrinks it)
   // (+8: in lattice mode every residue class is rounded up to the size of class (0,0))
   const uintptr_t a = take((size_t)BG * (H + 2 * padh + 8) * (W + 2 * padw + 8) * Cp * 2, 1024);
@@ -667,7 +702,10 @@ int local_corr_tc_launch(const float* in1, const float* in2, const float* flow2,
     Q.C = C; Q.Cp = Cp; Q.H = H; Q.W = W; Q.oh = oh; Q.ow = ow; Q.sh = sh; Q.sw = sw; Q.padh = padh; Q.padw = padw; Q.lat = lat;
     Q.nimg = BG * ncls; Q.G = G;
     EZB_REQUIRE((long long)BG * (1 + ncls) <= 65535, "batch too large for one launch (split it)");
-    convert_rows_kmajor_kernel<<<dim3(std::max(H, oh), 1, BG * (1 + ncls)), 256, 0, st>>>(JJ);
+    JJ.groups_per_block = std::max(1, std::min(8, 256 / Cp));
+    const size_t conv_smem = (size_t)Cp * 33 * 4;
+    EZB_CUDA_OK(cudaFuncSetAttribute(convert_pixels_kmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem));
+    convert_pixels_kmajor_kernel<<<dim3(cdiv(std::max(H * W, oh * ow), CONV_PX * JJ.groups_per_block), 1, BG * (1 + ncls)), CONV_THREADS, conv_smem, st>>>(JJ);
     EZB_LAUNCH_OK();
   }
 
@@ -698,7 +736,7 @@ int local_corr_tc_launch(const float* in1, const float* in2, const float* flow2,
   P.D = D; P.KB = Cp / BK;
   for (int d = 0; d < D; ++d) { P.dph[d] = dph_u[d]; P.dpw[d] = dpw_u[d]; }
   P.regular = (D == 1 && dph_u[0] == 1 && dpw_u[0] == 1 && sh == 1 && sw == 1 && padh == 0 && padw == 0 && TTW != 16 &&
-               getenv("EZB_LOCAL_CORR_GENERIC_EXTRACT") == nullptr) ? 1 : 0;
+               getenv("EZB_LOCAL_CORR_GENERIC_EXTRACT") == nullptr) ? (getenv("EZB_LOCAL_CORR_QUADSYNC") ? 2 : 1) : 0;
   P.lat = lat; P.BG = BG; P.Hf = H; P.Wf = W; P.out_h = out_h; P.out_w = out_w;
   P.slope = slope;
   P.qscale = ws.qscale;

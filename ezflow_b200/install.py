@@ -60,6 +60,23 @@ def install(patch_warp=True, patch_upsample=True, fuse_warp=True):
         _rebind("ezflow.decoder.pyramid", "warp", S.lazy_warp if fuse_warp else U.warp)
         _rebind("ezflow.utils.warp", "warp", U.warp)
         _rebind("ezflow.utils", "warp", U.warp)
+    # VCN's inline correlation (a method, ezflow/models/vcn.py:162-206) and DICL's volume assembly
+    # (LearnableMatchingCost.forward, ezflow/similarity/learnable_cost.py:157-231; the class keeps its matching network)
+    from .similarity import volume as VOL
+
+    try:
+        vcn_mod = importlib.import_module("ezflow.models.vcn")
+        key = ("ezflow.models.vcn", "VCN._corr_fn")
+        if key not in _saved:
+            _saved[key] = vcn_mod.VCN._corr_fn
+        vcn_mod.VCN._corr_fn = lambda self, features1, features2, max_disp, factorization=1: VOL.vcn_corr(features1, features2, max_disp, factorization)
+        lc_mod = importlib.import_module("ezflow.similarity.learnable_cost")
+        key = ("ezflow.similarity.learnable_cost", "LearnableMatchingCost.forward")
+        if key not in _saved:
+            _saved[key] = lc_mod.LearnableMatchingCost.forward
+        lc_mod.LearnableMatchingCost.forward = VOL.learnable_matching_cost_forward
+    except (ImportError, AttributeError):
+        pass
     if patch_upsample:
         # convex upsampling of every iteration's flow (ezflow/models/raft.py:9,127; decoder/dilated_flow_stack_filter.py:8,219)
         for modname in ("ezflow.utils.resampling", "ezflow.utils", "ezflow.models.raft", "ezflow.decoder.dilated_flow_stack_filter"):
@@ -119,6 +136,9 @@ def uninstall():
                 ez_sim.SIMILARITY_REGISTRY._obj_map.pop(attr, None)
             else:
                 ez_sim.SIMILARITY_REGISTRY._obj_map[attr] = old
+        elif "." in attr:  # a method of a class in that module
+            cls_name, meth = attr.split(".")
+            setattr(getattr(importlib.import_module(modname), cls_name), meth, old)
         elif old is not None:
             setattr(importlib.import_module(modname), attr, old)
     _saved.clear()

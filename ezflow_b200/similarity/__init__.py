@@ -3,6 +3,7 @@ from .layer import CorrelationLayer
 from .matryoshka import MatryoshkaDilatedCostVolume, MatryoshkaDilatedCostVolumeList
 from .lookup_conv import LazyLookup, LookupConv2d, lookup_conv1x1
 from .pairwise import LazyLookupPairwise4DCorr, MutliScalePairwise4DCorr, get_pyramid_dtype, set_pyramid_dtype
+from .volume import OnDemandPairwise4DCorr, dicl_cost_volume, vcn_corr
 from .sampler import (
     IterSpatialCorrelationSampler,
     WarpedFeatures,
@@ -31,4 +32,7 @@ __all__ = [
     "LookupConv2d",
     "lookup_conv1x1",
     "LazyLookupPairwise4DCorr",
+    "OnDemandPairwise4DCorr",
+    "dicl_cost_volume",
+    "vcn_corr",
 ]

@@ -212,6 +212,34 @@ int ezb_convex_upsample_bwd(const float* flow, const float* mask_logits, const f
                             int H, int W, int out_stride, float* dflow, float* dmask_logits,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * the remaining models' volume assemblies and the memory-free lookup
+ *
+ * VCN per-channel shifted products    replaces VCN._corr_fn  ezflow/models/vcn.py:162-206
+ *   out (B, C, 2*mdx+1, 2*mdy+1, H, W):  out[b,c,i,j,y,x] = leaky_relu(f1[b,c,y,x] * f2[b,c,y+j-mdy,x+i-mdx], slope),
+ *   0 where the shifted pixel is outside (mdx = max_disp, mdy = max_disp // factorization).
+ * DICL displacement-stacked volume     replaces the assembly in LearnableMatchingCost.forward
+ *   ezflow/similarity/learnable_cost.py:157-231 (everything before self.matching_net):
+ *   out (B*U*V, 2C, H, W), image (b,i,j) = [x[b] ; y[b] shifted by (j-max_v, i-max_u)] on the overlap, zero elsewhere and
+ *   (remove_warp_hole) where the shifted y sums to zero over the channels.  `mask` (B*U*V, H, W) bytes, optional, receives
+ *   the keep-mask the backward needs.
+ * On-demand correlation lookup: the output of ezb_corr_lookup_fwd (pairwise.py:43-69) computed from the feature maps
+ *   without the all-pairs volume (exact fp32); prepare() lays fmap1 and the pooled fmap2 levels out in `workspace`.
+ * ------------------------------------------------------------------------------------------- */
+int ezb_vcn_corr_fwd(const float* f1, const float* f2, int B, int C, int H, int W, int max_disp_x, int max_disp_y,
+                     float slope, float* out, void* stream);
+int ezb_vcn_corr_bwd(const float* f1, const float* f2, const float* dout, int B, int C, int H, int W, int max_disp_x,
+                     int max_disp_y, float slope, float* df1, float* df2, void* stream);
+int ezb_dicl_volume_fwd(const float* x, const float* y, int B, int C, int H, int W, int max_u, int max_v,
+                        int remove_warp_hole, float* out, unsigned char* mask /* may be NULL */, void* stream);
+int ezb_dicl_volume_bwd(const float* dout, const unsigned char* mask, int B, int C, int H, int W, int max_u, int max_v,
+                        float* dx, float* dy, void* stream);
+int ezb_corr_ondemand_workspace_bytes(int B, int C, int H, int W, int L, size_t* bytes /*host*/);
+int ezb_corr_ondemand_prepare(const float* fmap1, const float* fmap2, int B, int C, int H, int W, int L, void* workspace,
+                              size_t workspace_bytes, void* stream);
+int ezb_corr_ondemand_lookup(const void* workspace, const float* coords, int B, int C, int H, int W, int L, int radius,
+                             float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -425,3 +425,47 @@ def convex_upsample_flow_bwd(flow: np.ndarray, mask_logits: np.ndarray, out_stri
         for kx in range(3):
             dpad[:, :, ky : ky + h, kx : kx + w] += dtaps[:, :, ky * 3 + kx]
     return dpad[:, :, 1:-1, 1:-1].astype(flow.dtype), dlogits.reshape(mask_logits.shape).astype(flow.dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# VCN's per-channel correlation volume and DICL's displacement-stacked volume
+# ------------------------------------------------------------------------------------------------
+def vcn_corr(features1: np.ndarray, features2: np.ndarray, max_disp: int, factorization: int = 1, slope: float = 0.1) -> np.ndarray:
+    """VCN._corr_fn (reference ezflow/models/vcn.py:162-206): cost[b,c,i,j,y,x] = leaky_relu(f1[b,c,y,x] * f2[b,c,y+indd,x+ind]),
+    ind = i - max_disp (x shift), indd = j - max_disp // factorization (y shift), zero where the shifted pixel is outside."""
+    b, c, h, w = features1.shape
+    mv = int(max_disp // factorization)
+    cost = np.zeros((b, c, 2 * max_disp + 1, 2 * mv + 1, h, w), dtype=np.float32)
+    for i in range(2 * max_disp + 1):
+        ind = i - max_disp
+        for j in range(2 * mv + 1):
+            indd = j - mv
+            ys, ye = max(0, -indd), min(h, h - indd)
+            xs, xe = max(0, -ind), min(w, w - ind)
+            if ys >= ye or xs >= xe:
+                continue
+            cost[:, :, i, j, ys:ye, xs:xe] = features1[:, :, ys:ye, xs:xe] * features2[:, :, ys + indd : ye + indd, xs + ind : xe + ind]
+    return leaky_relu(cost, slope)
+
+
+def dicl_cost_volume(x: np.ndarray, y: np.ndarray, max_u: int, max_v: int, remove_warp_hole: bool = True) -> np.ndarray:
+    """The volume LearnableMatchingCost.forward hands to its matching network (reference
+    ezflow/similarity/learnable_cost.py:181-226): (B*U*V, 2C, H, W), image (b,i,j) = [x ; y shifted by (j - max_v, i - max_u)]
+    on the overlap, zero elsewhere; with remove_warp_hole also zero where the shifted y sums to 0 over its channels."""
+    b, c, h, w = x.shape
+    U, V = 2 * max_u + 1, 2 * max_v + 1
+    cost = np.zeros((b, 2 * c, U, V, h, w), dtype=np.float32)
+    for i in range(U):
+        ind = i - max_u
+        for j in range(V):
+            indd = j - max_v
+            ys, ye = max(0, -indd), min(h, h - indd)
+            xs, xe = max(0, -ind), min(w, w - ind)
+            if ys >= ye or xs >= xe:
+                continue
+            cost[:, :c, i, j, ys:ye, xs:xe] = x[:, :, ys:ye, xs:xe]
+            cost[:, c:, i, j, ys:ye, xs:xe] = y[:, :, ys + indd : ye + indd, xs + ind : xe + ind]
+    if remove_warp_hole:
+        valid = cost[:, c:].sum(axis=1) != 0
+        cost = cost * valid[:, None].astype(np.float32)
+    return np.ascontiguousarray(cost.transpose(0, 2, 3, 1, 4, 5)).reshape(b * U * V, 2 * c, h, w)

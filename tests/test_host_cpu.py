@@ -126,6 +126,13 @@ def test_install_into_reference_and_yaml_models():
         assert E.fuse_model(pwc) == 1 and isinstance(pwc.decoder.leaky_relu, torch.nn.Identity)
         assert pwc.decoder.correlation_layer.fused_negative_slope == pytest.approx(0.1)
         assert E.fuse_model(fnc) == 1 and isinstance(fnc.corr_activation, torch.nn.Identity)
+        # VCN's inline correlation and DICL's volume assembly are rebound at class level
+        import ezflow.models.vcn as ref_vcn
+        import ezflow.similarity.learnable_cost as ref_lc
+        from ezflow_b200.similarity import volume as VOL
+
+        assert ref_lc.LearnableMatchingCost.forward is VOL.learnable_matching_cost_forward
+        assert ref_vcn.VCN._corr_fn.__module__ == "ezflow_b200.install"
         dcv = build_model("DCVNet", cfg_path=refshim.reference_config_path("dcvnet.yaml"), custom_cfg=True)
         assert isinstance(dcv.cost_volume_list, E.MatryoshkaDilatedCostVolumeList)
         ref_keys = {k for k in dcv.state_dict() if "offsets" in k}
@@ -134,3 +141,7 @@ def test_install_into_reference_and_yaml_models():
     finally:
         E.uninstall()
     assert R.get("MutliScalePairwise4DCorr").__module__.startswith("ezflow.")
+    import ezflow.models.vcn as ref_vcn
+    import ezflow.similarity.learnable_cost as ref_lc
+
+    assert ref_vcn.VCN._corr_fn.__module__ == "ezflow.models.vcn" and ref_lc.LearnableMatchingCost.forward.__module__.startswith("ezflow.")

@@ -143,3 +143,19 @@ def test_convex_upsample(golden, name):
     dflow, dlogits = O.convex_upsample_flow_bwd(g["flow"], g["logits"], s, g["dout"])
     close(dflow, g["dflow"], rtol=5e-5)
     close(dlogits, g["dlogits"], rtol=5e-5)
+
+
+@pytest.mark.parametrize("name", ["vcn_corr_md3", "vcn_corr_md4_f2"])
+def test_vcn_corr_oracle_vs_reference_golden(golden, name):
+    g = golden(name)
+    out = O.vcn_corr(g["f1"], g["f2"], int(g["max_disp"]), int(g["factorization"]))
+    assert out.shape == g["out"].shape
+    np.testing.assert_allclose(out, g["out"], rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["dicl_volume_u3v3", "dicl_volume_u2v1_keep"])
+def test_dicl_volume_oracle_vs_reference_golden(golden, name):
+    g = golden(name)
+    out = O.dicl_cost_volume(g["x"], g["y"], int(g["max_u"]), int(g["max_v"]), bool(g["remove_warp_hole"]))
+    assert out.shape == g["out"].shape
+    np.testing.assert_array_equal(out, g["out"])  # pure data movement: bit-exact

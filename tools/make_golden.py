@@ -140,5 +140,42 @@ def main():
         save(name, flow=flow, logits=logits, out=out, dout=dout, dflow=flow.grad, dlogits=logits.grad, out_stride=st)
 
 
+def volume_cases():
+    """VCN._corr_fn and the volume LearnableMatchingCost.forward feeds its matching net, forward + autograd."""
+    from ezflow.models.vcn import VCN
+    from ezflow.similarity.learnable_cost import LearnableMatchingCost
+
+    g = torch.Generator().manual_seed(61)
+    f1 = torch.randn(2, 5, 9, 12, generator=g).requires_grad_(True)
+    f2 = torch.randn(2, 5, 9, 12, generator=g).requires_grad_(True)
+    for name, (md, fac) in {"vcn_corr_md3": (3, 1), "vcn_corr_md4_f2": (4, 2)}.items():
+        f1.grad = f2.grad = None
+        out = VCN._corr_fn(None, f1, f2, md, fac)
+        dout = torch.randn(out.shape, generator=g)
+        (out * dout).sum().backward()
+        save(name, f1=f1, f2=f2, out=out, dout=dout, df1=f1.grad, df2=f2.grad, max_disp=md, factorization=fac)
+
+    class Capture(torch.nn.Module):  # stands in for the matching network: records the assembled volume
+        def forward(self, cost):
+            self.cost = cost
+            return cost[:, :1]
+
+    x = torch.randn(2, 4, 8, 11, generator=g)
+    y = torch.randn(2, 4, 8, 11, generator=g)
+    y[:, :, 2:4, 3:6] = 0.0  # warp holes
+    x.requires_grad_(True)
+    y.requires_grad_(True)
+    for name, (mu, mv, holes) in {"dicl_volume_u3v3": (3, 3, True), "dicl_volume_u2v1_keep": (2, 1, False)}.items():
+        x.grad = y.grad = None
+        m = LearnableMatchingCost(max_u=mu, max_v=mv, remove_warp_hole=holes)
+        m.matching_net = Capture()
+        m(x, y)
+        vol = m.matching_net.cost
+        dout = torch.randn(vol.shape, generator=g)
+        (vol * dout).sum().backward()
+        save(name, x=x, y=y, out=vol, dout=dout, dx=x.grad, dy=y.grad, max_u=mu, max_v=mv, remove_warp_hole=int(holes))
+
+
 if __name__ == "__main__":
     main()
+    volume_cases()
