@@ -53,6 +53,9 @@ _SIGNATURES = {
     "ezb_local_corr_fwd": ([c_vp, c_vp] + [c_int] * 12 + [c_f32, c_f32, c_vp, c_i64, c_vp, c_sz, c_vp], c_int),
     "ezb_warp_local_corr_fwd": ([c_vp, c_vp, c_vp] + [c_int] * 12 + [c_f32, c_f32, c_vp, c_i64, c_vp, c_sz, c_vp], c_int),
     "ezb_local_corr_bwd": ([c_vp, c_vp, c_vp] + [c_int] * 12 + [c_f32, c_i64, c_vp, c_vp, c_vp], c_int),
+    "ezb_local_corr_bwd_workspace_bytes": ([c_int, c_int, c_int, c_int, _P(c_sz)], c_int),
+    "ezb_local_corr_bwd_ex": ([c_vp, c_vp, c_vp] + [c_int] * 12 + [c_f32, c_i64, c_vp, c_vp, c_vp, c_sz, c_vp], c_int),
+    "ezb_matryoshka_bwd": ([c_vp, c_vp, c_vp] + [c_int] * 7 + [_P(c_int), c_int, c_i64, c_vp, c_vp, c_vp, c_sz, c_int, c_vp], c_int),
     "ezb_matryoshka_fwd": (
         [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P(c_int), c_int, c_f32, c_vp, c_i64, c_vp, c_sz, c_vp],
         c_int,

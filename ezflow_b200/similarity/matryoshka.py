@@ -59,6 +59,23 @@ class _MatryoshkaFn(torch.autograd.Function):
         B, C, H, W = x1.shape
         x1g = x1.view(B * G, C // G, H, W)
         x2g = x2.view(B * G, C // G, H, W)
+        from .sampler import get_local_corr_mode
+
+        lib = _cabi.lib()
+        # one call for all dilations (ezb_matryoshka_bwd): tensor-core adjoints accumulate straight into the outputs; the fp32
+        # fallback inside it needs one group (DCVNet), otherwise the per-dilation loop below runs
+        if G == 1:
+            d1 = torch.empty_like(x1g)
+            d2 = torch.empty_like(x2g)
+            dil = (ctypes.c_int * len(dilations))(*[int(d) for d in dilations])
+            n = ctypes.c_size_t(0)
+            with torch.cuda.device(x1.device):
+                _cabi.check(lib.ezb_local_corr_bwd_workspace_bytes(B * G, C // G, H, W, ctypes.byref(n)))
+                ws = torch.empty(n.value, dtype=torch.uint8, device=x1.device)
+                _cabi.check(lib.ezb_matryoshka_bwd(_cabi.ptr(x1g), _cabi.ptr(x2g), _cabi.ptr(dout), B, G, C // G, H, W, P, stride, dil, len(dilations),
+                                                   int(dout.stride(0)), _cabi.ptr(d1), _cabi.ptr(d2), _cabi.ptr(ws), n.value,
+                                                   1 if get_local_corr_mode() == "tc" else 0, _cabi.stream_ptr(x1.device)))
+            return d1.view_as(x1), d2.view_as(x2), None, None, None, None, None
         d1 = torch.zeros_like(x1g)
         d2 = torch.zeros_like(x2g)
         for i, d in enumerate(dilations):

@@ -81,20 +81,42 @@ def local_corr_forward(in1, in2, patch, stride, padding, dpatch, scale=1.0, slop
     return out
 
 
+def bwd_tc_covers(B, C, H, W, patch, stride, padding, dpatch):
+    """True when the tensor-core adjoint (csrc/local_corr_bwd_tc.cu) both handles the problem — the regular case; the library
+    has the last word — and pays off: it has ~0.1 ms of fixed cost (three scale reductions, two operand conversions) plus ~11.5 ns
+    per million gradient elements, against ~0.31 ms per 1e9 FMAs of the fp32 kernels (tools/micro/k4b_levels.py on B200:
+    FlowNetC 0.88 -> 0.17 ms, DCVNet's stride-1 dilations 0.16-0.24 -> 0.10-0.14 ms; PWC-Net's small / few-channel levels stay
+    on the fp32 kernels)."""
+    d = dpatch[0]
+    regular = (
+        _LOCAL_CORR_MODE == "tc" and C <= TC_MAX_CHANNELS and patch[0] == patch[1] and patch[0] % 2 == 1 and patch[0] <= 25
+        and stride == (1, 1) and padding == (0, 0) and dpatch[0] == dpatch[1] and 1 <= d <= 8
+        and (d == 1 or (-(-H // d) >= 8 and -(-W // d) >= 16))
+    )
+    elems = B * patch[0] * patch[1] * H * W  # gradient elements
+    return regular and elems * (0.31 * C - 11.5) > 65e6
+
+
 def local_corr_backward(in1, in2, dout, patch, stride, padding, dpatch, scale=1.0, need1=True, need2=True, dout_batch_stride=0):
+    """Both adjoints of the local correlation.  'tc' mode: banded tcgen05 GEMMs (fp16 operands, <= 1e-3 relative) where the
+    problem is regular (stride 1, no padding, square window, one dilation); otherwise, and in 'exact' mode, fp32 CUDA-core kernels."""
     B, C, H, W = in1.shape
     d1 = torch.empty_like(in1) if need1 else None
     d2 = torch.empty_like(in2) if need2 else None
     if B == 0 or (d1 is None and d2 is None):
         return d1, d2
+    lib = _cabi.lib()
+    geom = (B, C, H, W, patch[0], patch[1], stride[0], stride[1], padding[0], padding[1], dpatch[0], dpatch[1])
     with torch.cuda.device(in1.device):
-        _cabi.check(
-            _cabi.lib().ezb_local_corr_bwd(
-                _cabi.ptr(in1), _cabi.ptr(in2), _cabi.ptr(dout), B, C, H, W, patch[0], patch[1], stride[0], stride[1],
-                padding[0], padding[1], dpatch[0], dpatch[1], float(scale), int(dout_batch_stride), _cabi.ptr(d1), _cabi.ptr(d2),
-                _cabi.stream_ptr(in1.device),
-            )
-        )
+        if bwd_tc_covers(B, C, H, W, patch, stride, padding, dpatch):
+            n = ctypes.c_size_t(0)
+            _cabi.check(lib.ezb_local_corr_bwd_workspace_bytes(B, C, H, W, ctypes.byref(n)))
+            ws = torch.empty(n.value, dtype=torch.uint8, device=in1.device)
+            _cabi.check(lib.ezb_local_corr_bwd_ex(_cabi.ptr(in1), _cabi.ptr(in2), _cabi.ptr(dout), *geom, float(scale), int(dout_batch_stride),
+                                                  _cabi.ptr(d1), _cabi.ptr(d2), _cabi.ptr(ws), n.value, _cabi.stream_ptr(in1.device)))
+        else:
+            _cabi.check(lib.ezb_local_corr_bwd(_cabi.ptr(in1), _cabi.ptr(in2), _cabi.ptr(dout), *geom, float(scale), int(dout_batch_stride),
+                                               _cabi.ptr(d1), _cabi.ptr(d2), _cabi.stream_ptr(in1.device)))
     return d1, d2
 
 

@@ -174,6 +174,16 @@ int ezb_local_corr_bwd(const float* in1, const float* in2, const float* dout, in
                        float scale, int64_t dout_batch_stride,
                        float* din1, float* din2, void* stream);
 
+/* Tensor-core adjoints (K4b on tcgen05): with a workspace of ezb_local_corr_bwd_workspace_bytes(), the regular case —
+ * stride 1, no padding, square odd window <= 25, one isotropic patch dilation <= 8, C <= 256 — runs as two banded GEMMs
+ * (fp16 operands, fp32 accumulation, <= 1e-3 relative); anything else, or workspace == NULL, takes ezb_local_corr_bwd's exact
+ * fp32 kernels. */
+int ezb_local_corr_bwd_workspace_bytes(int BG, int C, int H, int W, size_t* bytes /*host*/);
+int ezb_local_corr_bwd_ex(const float* in1, const float* in2, const float* dout, int B, int C, int H, int W,
+                          int Ph, int Pw, int sh, int sw, int padh, int padw, int dph, int dpw,
+                          float scale, int64_t dout_batch_stride,
+                          float* din1, float* din2, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * DCVNet Matryoshka dilated cost volume (K6): all dilations of one scale in one launch
  *   replaces MatryoshkaDilatedCostVolume.forward  ezflow/similarity/learnable_cost.py:306-325
@@ -183,6 +193,15 @@ int ezb_local_corr_bwd(const float* in1, const float* in2, const float* dout, in
 int ezb_matryoshka_fwd(const float* x1, const float* x2, int B, int G, int Cg, int H, int W,
                        int P, int stride, const int* dil /*[D] host*/, int D, float slope,
                        float* out, int64_t out_batch_stride, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Adjoint of ezb_matryoshka_fwd over ALL dilations in one call (autograd of learnable_cost.py:306-325): dx1, dx2
+ * (B, G*Cg, H, W) from dout (B, D*G, P, P, oh, ow).  workspace: ezb_local_corr_bwd_workspace_bytes(B*G, Cg, H, W).
+ * use_tensor_cores != 0: dilations the tcgen05 adjoint covers accumulate straight into the outputs; the rest (and all of them
+ * when 0) go through the fp32 kernels, which need G == 1 here (EZB_ERR_UNSUPPORTED otherwise: call ezb_local_corr_bwd per
+ * dilation and group). */
+int ezb_matryoshka_bwd(const float* x1, const float* x2, const float* dout, int B, int G, int Cg, int H, int W,
+                       int P, int stride, const int* dil /*[D] host*/, int D, int64_t dout_batch_stride,
+                       float* dx1, float* dx2, void* workspace, size_t workspace_bytes, int use_tensor_cores, void* stream);
 
 /* x / (||x||_2 over channels + eps)   learnable_cost.py:426-428 */
 int ezb_l2_normalize_fwd(const float* x, int B, int C, int HW, float eps, float* out, void* stream);

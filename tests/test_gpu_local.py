@@ -13,6 +13,7 @@ pytestmark = pytest.mark.gpu
 
 TOL = 2e-5
 FWD_TOL = {"tc": 1e-3, "exact": 2e-5}
+BWD_TOL = {"tc": 1e-3, "exact": 5e-5}  # adjoints: tensor-core path (fp16 operands) / exact fp32 kernels
 SAMPLER = ["sampler_p9", "sampler_flownetc", "sampler_stride2", "sampler_aniso", "sampler_dcv_s4", "sampler_dil16"]
 
 
@@ -46,8 +47,9 @@ def test_sampler_vs_reference_golden(golden, name, mode):
     assert out.is_contiguous() and tuple(out.shape) == g["out"].shape
     assert_close(out, g["out"], FWD_TOL[mode], f"{name} fwd ({mode})")
     (out * to_gpu(g["dout"])).sum().backward()
-    assert_close(x1.grad, g["dx1"], TOL, f"{name} dinput1")
-    assert_close(x2.grad, g["dx2"], TOL, f"{name} dinput2")
+    btol = BWD_TOL[mode]  # 'tc': the regular cases run their adjoints on tensor cores too (fp16 operands)
+    assert_close(x1.grad, g["dx1"], btol, f"{name} dinput1 ({mode})")
+    assert_close(x2.grad, g["dx2"], btol, f"{name} dinput2 ({mode})")
     # functional form, no grad
     with torch.no_grad():
         out2 = E.iter_spatial_correlation_sample(to_gpu(g["x1"]), to_gpu(g["x2"]), **kw)
@@ -115,7 +117,7 @@ def test_matryoshka_list(golden, mode):
     assert_close(l1(xa, xb), g["out_norm_relu"], FWD_TOL[mode], "matryoshka list norm+relu")
 
 
-def test_matryoshka_backward_vs_oracle():
+def test_matryoshka_backward_vs_oracle(mode):
     import ezflow_b200 as E
     from oracle import similarity_oracle as O
 
@@ -134,8 +136,8 @@ def test_matryoshka_backward_vs_oracle():
         e1, e2 = O.iter_spatial_correlation_sample_bwd(x1.reshape(2, 4, 9, 11), x2.reshape(2, 4, 9, 11), g, 3, 1, 0, d)
         d1 += e1
         d2 += e2
-    assert_close(a.grad, d1.reshape(x1.shape), TOL, "matryoshka dx1")
-    assert_close(b.grad, d2.reshape(x2.shape), TOL, "matryoshka dx2")
+    assert_close(a.grad, d1.reshape(x1.shape), BWD_TOL[mode], f"matryoshka dx1 ({mode})")
+    assert_close(b.grad, d2.reshape(x2.shape), BWD_TOL[mode], f"matryoshka dx2 ({mode})")
 
 
 def test_warp(golden):
@@ -318,7 +320,7 @@ def test_baseline_configs_full_batch(cfg, mode):
 
 
 @pytest.mark.parametrize("cfg", ["cfg2", "cfg3_fine", "pad_dil"])
-def test_adjoints_full_size_vs_torch_autograd(cfg):
+def test_adjoints_full_size_vs_torch_autograd(cfg, mode):
     """K4b at BASELINE shapes (tiled stride-1 kernels, many tiles / channel chunks) against autograd of the PyTorch restatement."""
     import ezflow_b200 as E
 
@@ -337,5 +339,49 @@ def test_adjoints_full_size_vs_torch_autograd(cfg):
     b1, b2 = x1.clone().requires_grad_(True), x2.clone().requires_grad_(True)
     m = E.IterSpatialCorrelationSampler(kernel_size=1, patch_size=kw["patch"], padding=kw.get("padding", 0), dilation_patch=kw.get("dp", 1))
     m(b1, b2).backward(dout)
-    assert_close(b1.grad, a1.grad, 5e-5, f"{cfg} d input1")
-    assert_close(b2.grad, a2.grad, 5e-5, f"{cfg} d input2")
+    btol = BWD_TOL[mode] if cfg == "cfg2" else 5e-5  # cfg2: tensor-core adjoint in 'tc' mode; the other two take the fp32 kernels
+    assert_close(b1.grad, a1.grad, btol, f"{cfg} d input1 ({mode})")
+    assert_close(b2.grad, a2.grad, btol, f"{cfg} d input2 ({mode})")
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(shape=(2, 8, 13, 18), patch=9, dp=1),      # ragged map, two query tiles per row, image borders everywhere
+    dict(shape=(1, 16, 12, 20), patch=21, dp=1),    # window wider than the map (4x40 target tiles)
+    dict(shape=(1, 40, 19, 37), patch=5, dp=2),     # lattice mode with ragged residue classes, C not a multiple of 64
+    dict(shape=(2, 256, 9, 17), patch=3, dp=1),     # full 256 channels (4 chunks)
+    dict(shape=(1, 24, 48, 64), patch=7, dp=3),     # lattice 3: classes of different sizes
+])
+def test_tensor_core_adjoint_vs_oracle(cfg):
+    """K4b on tcgen05 called directly through the C ABI (ezb_local_corr_bwd_ex with a workspace), whatever the size heuristic of
+    the host class would choose: both adjoints against the numpy oracle, 1e-3 (fp16 operands); then the same call without a
+    workspace (fp32 kernels) at 5e-5."""
+    import ctypes
+
+    from ezflow_b200 import _cabi
+    from oracle import similarity_oracle as O
+
+    rng = np.random.default_rng(sum(cfg["shape"]) + cfg["patch"])
+    B, C, H, W = cfg["shape"]
+    P, dp = cfg["patch"], cfg["dp"]
+    x1 = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    x2 = (rng.standard_normal((B, C, H, W)) * 3.0).astype(np.float32)
+    dout = (rng.standard_normal((B, P, P, H, W)) * 0.01).astype(np.float32)
+    d1, d2 = O.iter_spatial_correlation_sample_bwd(x1, x2, dout, patch_size=P, stride=1, padding=0, dilation_patch=dp)
+    lib = _cabi.lib()
+    a, b, g = to_gpu(x1), to_gpu(x2), to_gpu(dout)
+    n = ctypes.c_size_t(0)
+    _cabi.check(lib.ezb_local_corr_bwd_workspace_bytes(B, C, H, W, ctypes.byref(n)))
+    for ws_bytes, tol in ((n.value, 1e-3), (0, 5e-5)):
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev())
+        o1, o2 = torch.full_like(a, float("nan")), torch.full_like(b, float("nan"))  # every element must be written
+        _cabi.check(lib.ezb_local_corr_bwd_ex(_cabi.ptr(a), _cabi.ptr(b), _cabi.ptr(g), B, C, H, W, P, P, 1, 1, 0, 0, dp, dp, 1.0, 0,
+                                              _cabi.ptr(o1), _cabi.ptr(o2), _cabi.ptr(ws) if ws_bytes else None, ws_bytes,
+                                              _cabi.stream_ptr(dev())))
+        assert_close(o1, d1, tol, f"{cfg} din1 ({'tensor cores' if ws_bytes else 'fp32'})")
+        assert_close(o2, d2, tol, f"{cfg} din2 ({'tensor cores' if ws_bytes else 'fp32'})")
+    # one gradient only
+    o1 = torch.full_like(a, float("nan"))
+    ws = torch.empty(n.value, dtype=torch.uint8, device=dev())
+    _cabi.check(lib.ezb_local_corr_bwd_ex(_cabi.ptr(a), _cabi.ptr(b), _cabi.ptr(g), B, C, H, W, P, P, 1, 1, 0, 0, dp, dp, 0.5, 0,
+                                          _cabi.ptr(o1), None, _cabi.ptr(ws), n.value, _cabi.stream_ptr(dev())))
+    assert_close(o1, 0.5 * d1, 1e-3, f"{cfg} din1 only, scale 0.5")
