@@ -77,13 +77,22 @@ __device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src, 
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// waits that normally last microseconds (a whole stage / tile): back off between polls so the spinning warp does not
-// compete with the compute warps for issue slots
+// Waits that normally last microseconds (a whole stage / tile): mbarrier.try_wait with a suspend-time hint parks the thread in
+// hardware until the phase completes (or the hint expires), instead of polling and competing with the compute warps for issue slots.
 __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, unsigned ns) {
-  uint32_t spins = 0;
-  while (!ptx::mbar_try_wait(bar, parity)) {
-    __nanosleep(ns);
-    if (++spins > (1u << 24)) __trap();
+  uint32_t spins = 0, ok = 0;
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(ns)
+        : "memory");
+    if (ok) break;
+    if (++spins > (1u << 22)) __trap();
   }
 }
 __device__ __forceinline__ void compute_bar() { asm volatile("bar.sync 1, %0;" ::"n"(COMPUTE_WARPS * 32) : "memory"); }
@@ -187,10 +196,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) lookup_conv1x1_kernel(const __
     // ================================ gather + taps ================================
     // stage s = (tile ti = s / L of this CTA, level l = s % L).  Iteration s: wait for stage s's windows, issue the
     // copies of stage s + 1 into the other staging buffer, compute stage s into A[s & 1].
-    auto issue_gather = [&](int s) {
-      const int ti = s / P.L, l = s - ti * P.L;
+    // (pair, first query) of tile ti of this CTA; the integer division is paid once per tile, not per stage
+    auto tile_of = [&](int ti, int& b, int& q0) {
       const int work = (int)blockIdx.x + ti * (int)gridDim.x;
-      const int b = work / P.tiles_per_pair, q0 = (work - b * P.tiles_per_pair) * TQ;
+      b = work / P.tiles_per_pair;
+      q0 = (work - b * P.tiles_per_pair) * TQ;
+    };
+    int g_ti = 0, g_l = 0, g_b, g_q0;  // stage the next issue_gather call fetches
+    tile_of(0, g_b, g_q0);
+    auto issue_gather = [&]() {
+      const int l = g_l, b = g_b, q0 = g_q0;
+      const int s = g_ti * P.L + g_l;
+      if (++g_l == P.L) {
+        g_l = 0;
+        ++g_ti;
+        tile_of(g_ti, g_b, g_q0);
+      }
       const float* cx_ptr = P.coords + (long long)b * 2 * P.N;
       const float* cy_ptr = cx_ptr + P.N;
       const uint32_t stg = sStg + (uint32_t)(s & 1) * STG_BYTES;
@@ -230,7 +251,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) lookup_conv1x1_kernel(const __
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    if (n_stages > 0) issue_gather(0);
+    if (n_stages > 0) issue_gather();
     const int gq = warp & 3, part = warp >> 2;  // query group (= TMEM lane quadrant) and share of the window columns
     const int qrow = gq * 32 + lane;  // A row / TMEM lane of this thread's query
     // this warp's share of the window columns i: K columns dealt to the 4 parts (at most 3 each for K <= 9).  The share is
@@ -245,17 +266,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) lookup_conv1x1_kernel(const __
         const int t = tap_slot(K, i0 + a, 2 * m);
         soff[a][m] = (uint32_t)((t >> 5) * A_KB_BYTES + ((((t >> 3) & 3) ^ swz) << 4) + (t & 7) * 2);
       }
+    int c_l = 0, c_ti = 0, b, q0;  // stage being computed
+    tile_of(0, b, q0);
     for (int s = 0; s < n_stages; ++s) {
-      const int ti = s / P.L, l = s - ti * P.L;
+      const int l = c_l;
       // stage s + 1 goes into the buffer stage s - 1 was read from (everybody left it at the barrier that ended iteration
       // s - 1), BEFORE waiting for stage s: two stages of windows are in flight while this one is awaited
-      if (s + 1 < n_stages) issue_gather(s + 1);
+      if (s + 1 < n_stages) issue_gather();
       else asm volatile("cp.async.commit_group;" ::: "memory");
       asm volatile("cp.async.wait_group 1;" ::: "memory");
       compute_bar();  // stage s has landed for every thread
 
-      const int work = (int)blockIdx.x + ti * (int)gridDim.x;
-      const int b = work / P.tiles_per_pair, q0 = (work - b * P.tiles_per_pair) * TQ;
       const int q = min(q0 + qrow, P.N - 1);
       const float* cx_ptr = P.coords + (long long)b * 2 * P.N;
       const float inv = 1.0f / (float)(1 << l);
@@ -313,6 +334,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) lookup_conv1x1_kernel(const __
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(a_full(abuf));
       compute_bar();  // everybody is done reading this stage's windows: the buffer may be refilled
+      if (++c_l == P.L) {
+        c_l = 0;
+        ++c_ti;
+        tile_of(c_ti, b, q0);
+      }
     }
   } else if (warp == MMA_WARP) {
     // ================================ weight TMA + MMA issue ================================
@@ -320,17 +346,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) lookup_conv1x1_kernel(const __
       const uint32_t idesc = ptx::umma_idesc(/*f16*/ 0, TQ, (uint32_t)P.Np);
       for (int s = 0; s < n_stages; ++s) {
         const int ti = s / P.L, l = s - ti * P.L;
-        mbar_wait_backoff(b_empty, ((uint32_t)s & 1u) ^ 1u, 100);  // MMAs of stage s - 1 (the previous user of the weight buffer) are done
+        mbar_wait_backoff(b_empty, ((uint32_t)s & 1u) ^ 1u, 20000);  // MMAs of stage s - 1 (the previous user of the weight buffer) are done
         ptx::mbar_expect_tx(b_full, (uint32_t)(KBS * B_KB_BYTES));
         for (int kb = 0; kb < KBS; ++kb)
           ptx::tma_load_2d_hint(sB + kb * B_KB_BYTES, &tmW, b_full, l * KL + kb * KB_EL, 0, ptx::kEvictLast);
         const int dbuf = ti & 1;
         if (l == 0) {
-          mbar_wait_backoff(d_empty(dbuf), (((uint32_t)ti >> 1) & 1u) ^ 1u, 200);
+          mbar_wait_backoff(d_empty(dbuf), (((uint32_t)ti >> 1) & 1u) ^ 1u, 20000);
           ptx::tc_fence_after();
         }
-        mbar_wait_backoff(b_full, (uint32_t)s & 1u, 100);
-        mbar_wait_backoff(a_full(s & 1), ((uint32_t)s >> 1) & 1u, 200);
+        mbar_wait_backoff(b_full, (uint32_t)s & 1u, 20000);
+        mbar_wait_backoff(a_full(s & 1), ((uint32_t)s >> 1) & 1u, 20000);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + dbuf * N_MAX;
         const uint32_t a_base = sA + (s & 1) * (KBS * A_KB_BYTES);
@@ -356,7 +382,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) lookup_conv1x1_kernel(const __
       const int q = q0 + quad * 32 + lane;
       const float sc = __ldg(P.deq + b) * wscale;
       const int dbuf = ti & 1;
-      mbar_wait_backoff(d_full(dbuf), ((uint32_t)ti >> 1) & 1u, 1000);
+      mbar_wait_backoff(d_full(dbuf), ((uint32_t)ti >> 1) & 1u, 100000);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + dbuf * N_MAX + ((uint32_t)(quad * 32) << 16);
       float* o = P.out + (long long)b * P.Cout * P.N + q;
