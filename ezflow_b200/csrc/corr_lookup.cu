@@ -16,6 +16,8 @@
 // HBM-bound: algorithmic bytes per query = L*[(2r+2)^2*es + (2r+1)^2*4] + 8  (SURVEY.md §8d).
 #include "ezb_common.cuh"
 
+#include <cstdlib>
+
 namespace ezb {
 namespace k3 {
 
@@ -184,6 +186,7 @@ struct LookupBwdParams {
   const float* dout;    // (B, L*K*K, N)
   const float* coords;  // (B,2,N)
   int B, N, L, r;
+  int rmw_rows;         // plain vector read-modify-writes where a level's rows are 16-byte aligned (else atomics)
 };
 
 // dpyr[l][b,q,y,x] += sum over window taps of weight * dout.  A query's gradient window is private to that query (no
@@ -247,6 +250,37 @@ __global__ void __launch_bounds__(NTHREADS) corr_lookup_bwd_kernel(const LookupB
       prev = cur;
       return g;
     };
+    if (P.rmw_rows && ((P.pitch[l] | (int)P.qstride[l]) & 3) == 0) {
+      // The rows of this level start 16-byte aligned (pitch and per-query stride are multiples of 4 floats), and a map row of a
+      // query is touched by exactly one thread per launch: plain 16-byte read-modify-writes of the aligned slots that
+      // cover the window row (elements outside the window add 0) replace the atomics — the L2 atomic units were the limit.
+      float* rowbase = row - xs;                 // element (yy, 0)
+      const int xa = xs & ~3;                    // first aligned slot (floor, also for negative xs)
+      float4 v[4];
+      bool live[4];
+#pragma unroll
+      for (int sl = 0; sl < 4; ++sl) {
+        const int x0 = xa + 4 * sl;
+        float e[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int Xw = x0 + u - xs;            // window column of this element
+          e[u] = (Xw >= 0 && Xw < D) ? next(Xw) : 0.f;
+        }
+        live[sl] = x0 >= 0 && x0 < wl && x0 - xs < D && x0 + 3 - xs >= 0;  // inside the image (whole slots: wl % 4 == 0) and touching the window
+        v[sl] = make_float4(e[0], e[1], e[2], e[3]);
+      }
+      float4 old[4];
+#pragma unroll
+      for (int sl = 0; sl < 4; ++sl)
+        if (live[sl]) old[sl] = *reinterpret_cast<const float4*>(rowbase + xa + 4 * sl);
+#pragma unroll
+      for (int sl = 0; sl < 4; ++sl)
+        if (live[sl])
+          *reinterpret_cast<float4*>(rowbase + xa + 4 * sl) =
+              make_float4(old[sl].x + v[sl].x, old[sl].y + v[sl].y, old[sl].z + v[sl].z, old[sl].w + v[sl].w);
+      continue;
+    }
     int X = 0;
     if ((reinterpret_cast<uintptr_t>(row) >> 2) & 1) {  // first address 8-byte misaligned: scalar head
       const float g = next(0);
@@ -367,6 +401,9 @@ extern "C" int ezb_corr_lookup_bwd(const float* dout, const float* coords, int B
   P.N = N;
   P.L = L;
   P.r = radius;
+  P.rmw_rows = (2 * radius + 2 <= 13 && getenv("EZB_LOOKUP_BWD_ATOMICS") == nullptr) ? 1 : 0;  // a window row spans at most 4 aligned slots
+  for (int l = 0; l < L; ++l)
+    if (reinterpret_cast<uintptr_t>(dlvl_ptrs[l]) & 15) P.rmw_rows = 0;
   const int K = 2 * radius + 1;
   const size_t smem = (size_t)k3::QB * ((L * K * K) | 1) * sizeof(float);
   if (smem > 200 * 1024) return fail(EZB_ERR_UNSUPPORTED, "lookup window too large (L=%d, r=%d)", L, radius);

@@ -44,13 +44,20 @@ def get_local_corr_mode():
     return _LOCAL_CORR_MODE
 
 
+_WS_BYTES = {}  # (BG, C, H, W, padh, padw) -> bytes: the size query is a pure function of the shape
+
+
 def local_corr_workspace(BG, C, H, W, device, padding=(0, 0)):
     """Scratch for the tensor-core path (fp16 K-major operand copies + scales), or (None, 0) in 'exact' mode."""
     if _LOCAL_CORR_MODE != "tc":
         return None, 0
-    n = ctypes.c_size_t(0)
-    _cabi.check(_cabi.lib().ezb_local_corr_workspace_bytes(BG, C, H, W, int(padding[0]), int(padding[1]), ctypes.byref(n)))
-    return torch.empty(n.value, dtype=torch.uint8, device=device), n.value
+    key = (BG, C, H, W, int(padding[0]), int(padding[1]))
+    nbytes = _WS_BYTES.get(key)
+    if nbytes is None:
+        n = ctypes.c_size_t(0)
+        _cabi.check(_cabi.lib().ezb_local_corr_workspace_bytes(*key, ctypes.byref(n)))
+        nbytes = _WS_BYTES[key] = n.value
+    return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
 
 
 TC_MAX_CHANNELS = 256  # per group; above it (or in 'exact' mode) the fp32 CUDA-core kernel runs
