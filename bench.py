@@ -416,8 +416,10 @@ def run_secondary(args, dev, world, rank, peaks, headline_step):
             rec["frac_graph"] = (nbytes / rec["ms_graph"] / 1e6) / peaks["hbm_gbs"]
         records.append(rec)
 
+    OPT_IN = {"cfg4_dcvnet_matryoshka_bwd"}  # not a BASELINE configuration: only when named in --secondary
+
     def enabled(name):
-        return not want or name in want
+        return (name in want) if (want or name in OPT_IN) else True
 
     with torch.no_grad():
         if enabled("cfg2_flownetc_corr_fwd") or enabled("cfg2_flownetc_corr_bwd"):
@@ -471,13 +473,28 @@ def run_secondary(args, dev, world, rank, peaks, headline_step):
                     t_fb = timed(fb3)
                 add("cfg3_pwc_finest_bwd", t_fb - t_f, 2 * 2 * a0.numel() * 4 + dout.numel() * 4, "both adjoints of the finest PWC level (8,32,112,256), P=9")
             del xs
-        if enabled("cfg4_dcvnet_matryoshka_fwd"):
+        if enabled("cfg4_dcvnet_matryoshka_fwd") or enabled("cfg4_dcvnet_matryoshka_bwd"):
             xa = [torch.randn(4, 128, 192, 384, device=dev), torch.randn(4, 256, 48, 96, device=dev)]
             xb = [torch.randn(4, 128, 192, 384, device=dev), torch.randn(4, 256, 48, 96, device=dev)]
             mm = E.MatryoshkaDilatedCostVolumeList().to(dev)
             add("cfg4_dcvnet_matryoshka_fwd", timed(lambda: mm(xa, xb)), int(240.0e6),
                 "MatryoshkaDilatedCostVolumeList on (4,128,192,384)+(4,256,48,96) feature pairs (BASELINE config 4)",
                 ms_graph=timed_graph(lambda: mm(xa, xb)))
+            if enabled("cfg4_dcvnet_matryoshka_bwd"):
+                t_f = timed(lambda: mm(xa, xb))
+                with torch.enable_grad():
+                    ga = [t.clone().requires_grad_(True) for t in xa]
+                    gb = [t.clone().requires_grad_(True) for t in xb]
+                    dout = torch.randn(4, 7, 9, 9, 48, 96, device=dev)
+
+                    def fb4():
+                        for t in ga + gb:
+                            t.grad = None
+                        mm(ga, gb).backward(dout)
+
+                    t_fb = timed(fb4)
+                add("cfg4_dcvnet_matryoshka_bwd", t_fb - t_f, 2 * 2 * sum(t.numel() for t in xa) * 4 + dout.numel() * 4,
+                    "both adjoints of config 4 (ezb_matryoshka_bwd per scale: tensor-core adjoints for the dilations that fit, fp32 kernels for the rest)")
             del xa, xb
     torch.cuda.empty_cache()
 

@@ -472,7 +472,7 @@ extern "C" int ezb_local_corr_bwd(const float* in1, const float* in2, const floa
 extern "C" int ezb_local_corr_bwd_workspace_bytes(int BG, int C, int H, int W, size_t* bytes) {
   EZB_REQUIRE(BG > 0 && C > 0 && H > 0 && W > 0 && bytes, "bad arguments");
   // tensor-core operands + (K6) two gradient-sized scratch tensors for dilations the tensor-core path does not cover
-  *bytes = local_corr_bwd_tc_workspace_bytes(BG, C, H, W) + 2 * ((size_t)BG * C * H * W * 4 + 256);
+  *bytes = local_corr_bwd_tc_workspace_bytes(BG, C, H, W) + 2 * ((size_t)BG * C * H * W * 4 + 256) + 1024;  // + alignment slack
   return EZB_OK;
 }
 

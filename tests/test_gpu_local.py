@@ -385,3 +385,35 @@ def test_tensor_core_adjoint_vs_oracle(cfg):
     _cabi.check(lib.ezb_local_corr_bwd_ex(_cabi.ptr(a), _cabi.ptr(b), _cabi.ptr(g), B, C, H, W, P, P, 1, 1, 0, 0, dp, dp, 0.5, 0,
                                           _cabi.ptr(o1), None, _cabi.ptr(ws), n.value, _cabi.stream_ptr(dev())))
     assert_close(o1, 0.5 * d1, 1e-3, f"{cfg} din1 only, scale 0.5")
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(shape=(2, 16, 26, 50), md=2, dil=[1, 2, 3], relu=False),   # every dilation on the tensor-core adjoint ('tc' mode)
+    dict(shape=(1, 24, 32, 48), md=4, dil=[1, 9], relu=True),       # dilation 9 leaves too few pixels per residue class: fp32 kernels + add
+    dict(shape=(1, 8, 9, 11), md=1, dil=[2, 1], relu=False),        # tiny map: dilation 2 on the fp32 kernels first, dilation 1 accumulates
+])
+def test_matryoshka_backward_single_group_all_dilations_in_one_call(cfg, mode):
+    """ezb_matryoshka_bwd (one C call for all dilations, G = 1 as in DCVNet) against the oracle's per-dilation adjoints."""
+    import ezflow_b200 as E
+    from oracle import similarity_oracle as O
+
+    rng = np.random.default_rng(sum(cfg["shape"]))
+    x1 = rng.standard_normal(cfg["shape"]).astype(np.float32)
+    x2 = rng.standard_normal(cfg["shape"]).astype(np.float32)
+    P = 2 * cfg["md"] + 1
+    m = E.MatryoshkaDilatedCostVolume(num_groups=1, max_displacement=cfg["md"], dilations=cfg["dil"], use_relu=cfg["relu"]).to(dev())
+    a, b = to_gpu(x1, True), to_gpu(x2, True)
+    out = m(a, b)
+    dout = rng.standard_normal(tuple(out.shape)).astype(np.float32)
+    (out * to_gpu(dout)).sum().backward()
+    # the activation mask is taken from the forward that actually ran: at a cost within fp16 rounding of zero the tensor-core
+    # forward and the oracle may sit on different sides of the LeakyReLU kink, which is not what this test is about
+    mask = out.detach().cpu().numpy() > 0
+    g = dout * np.where(mask, 1.0, 0.1).astype(np.float32) if cfg["relu"] else dout
+    d1, d2 = np.zeros_like(x1), np.zeros_like(x2)
+    for i, d in enumerate(cfg["dil"]):
+        e1, e2 = O.iter_spatial_correlation_sample_bwd(x1, x2, np.ascontiguousarray(g[:, i]), P, 1, 0, d)
+        d1 += e1
+        d2 += e2
+    assert_close(a.grad, d1, BWD_TOL[mode], f"{cfg} dx1 ({mode})")
+    assert_close(b.grad, d2, BWD_TOL[mode], f"{cfg} dx2 ({mode})")
