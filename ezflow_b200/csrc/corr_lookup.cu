@@ -17,6 +17,7 @@
 #include "ezb_common.cuh"
 
 #include <cstdlib>
+#include <type_traits>
 
 namespace ezb {
 namespace k3 {
@@ -125,9 +126,15 @@ __global__ void __launch_bounds__(NTHREADS, 3) corr_lookup_fwd_kernel(const Look
           const char* src = pair_base;
           uint32_t nbytes = 0;
           if ((unsigned)y < (unsigned)(P.H >> l) && (unsigned)xg < (unsigned)(P.W >> l)) {
-            const unsigned sidx = (unsigned)(P.sub_base[l] + (y / PYR_SY) * P.sw[l] + xg / PYR_SX);
-            const int col = (int)(sidx % PYR_SUBS_PER_TILE) * PYR_SUB + (y % PYR_SY) * PYR_SX + xg % PYR_SX;
-            src = pair_base + (unsigned long long)(sidx / PYR_SUBS_PER_TILE) * tile_stride + (unsigned)pyr_record_offset(ES, ql, col);
+            const unsigned sidx = (unsigned)(P.sub_base[l] + (y >> 3) * P.sw[l] + (xg >> 3));
+            if constexpr (ES == 2) {
+              // an fp16 chunk is one whole row of one 8x8 subtile: section sidx % 4 of the group block, 16 bytes at
+              // (y % 8) * 16 of the query's 128-byte line (ezb_common.cuh, pyr_record_offset with column % 8 == 0)
+              src = pair_base + (unsigned long long)(sidx >> 2) * tile_stride + (((sidx & 3u) << 12) + ((unsigned)ql << 7) + ((unsigned)(y & 7) << 4));
+            } else {
+              const int col = (int)(sidx % PYR_SUBS_PER_TILE) * PYR_SUB + (y % PYR_SY) * PYR_SX + xg % PYR_SX;
+              src = pair_base + (unsigned long long)(sidx / PYR_SUBS_PER_TILE) * tile_stride + (unsigned)pyr_record_offset(ES, ql, col);
+            }
             nbytes = 16;
           }
           cp_async_16(dst_task + qi * (qstride_words * 4) + l * D * row_el * ES, src, nbytes);
@@ -163,17 +170,36 @@ __global__ void __launch_bounds__(NTHREADS, 3) corr_lookup_fwd_kernel(const Look
     const int off = xs - G::chunk_floor(xs) * G::VW;  // taps start `off` pixels into the fetched row
     const T* pl = sm_q + l * D * row_el + off;
     float* o = out + (long long)(l * KK + i0 * K) * P.N;  // i offsets x (slow output index!), j offsets y   pairwise.py:53-61
-    for (int i = i0; i < i1; ++i) {
-      const T* p = pl + i;
-      float top = wl0 * (float)p[0] + wl1 * (float)p[1];  // horizontal lerp of row j
+    // NC adjacent window columns at a time: a window row's NC + 1 pixels give NC horizontally interpolated values (the
+    // pixel between two columns is loaded once), two consecutive rows give the taps
+    auto columns = [&](auto nc_tag, const T* p, float* oc) {
+      constexpr int NC = decltype(nc_tag)::value;
+      float top[NC], x[NC + 1];
+#pragma unroll
+      for (int a = 0; a <= NC; ++a) x[a] = (float)p[a];
+#pragma unroll
+      for (int a = 0; a < NC; ++a) top[a] = wl0 * x[a] + wl1 * x[a + 1];
       for (int j = 0; j < K; ++j) {
         p += row_el;
-        const float bot = wl0 * (float)p[0] + wl1 * (float)p[1];
-        *o = top + fy * (bot - top);
-        o += P.N;
-        top = bot;
+#pragma unroll
+        for (int a = 0; a <= NC; ++a) x[a] = (float)p[a];
+#pragma unroll
+        for (int a = 0; a < NC; ++a) {
+          const float bot = wl0 * x[a] + wl1 * x[a + 1];
+          oc[(long long)a * K * P.N] = top[a] + fy * (bot - top[a]);
+          top[a] = bot;
+        }
+        oc += P.N;
       }
+    };
+    int i = i0;
+    for (; i + 3 <= i1; i += 3, o += 3ll * K * P.N) columns(std::integral_constant<int, 3>{}, pl + i, o);
+    if (i + 2 <= i1) {
+      columns(std::integral_constant<int, 2>{}, pl + i, o);
+      i += 2;
+      o += 2ll * K * P.N;
     }
+    if (i < i1) columns(std::integral_constant<int, 1>{}, pl + i, o);
     item += i1 - i0;
   }
 }
