@@ -124,28 +124,27 @@ struct ConvJob {
 };
 struct ConvJobs {
   ConvJob j[2];
-  int groups_per_block;
+  int groups;  // 32-pixel groups a block converts at once
 };
 
 constexpr int CONV_THREADS = 256;
-constexpr int CONV_PX = 32;  // destination pixels per block
+constexpr int CONV_MAX_PX = 256;  // destination pixels per block at most (few channels: more pixels, same bytes)
 
-// Block = 32 consecutive destination pixels of one image x all channels: one sweep loads them (coalesced along x, 8 loads in
-// flight per thread) into shared memory [Cp][33] while tracking every pixel's absmax, then a warp per pixel writes the
-// K-major row scaled by the pixel's own power of two.  33.8 KB of shared memory at C = 256: six blocks per SM.
+// Block = `npx` consecutive destination pixels of one image x all channels, npx = 32 * groups (JJ.groups: 1 at Cp = 256, 4 at
+// Cp = 64, ...), so that a block moves ~32 KB whatever the channel count.  Thread -> (pixel, channel slice): one sweep loads
+// the values (coalesced along x, up to 8 loads in flight per thread) into shared memory [Cp][npx + 1] while tracking every pixel's
+// absmax, then a warp per pixel writes the K-major row scaled by the pixel's own power of two.
 __global__ void __launch_bounds__(CONV_THREADS) convert_pixels_kmajor_kernel(const ConvJobs JJ) {
-  extern __shared__ float pxbuf[];  // [Cp][33]
-  __shared__ float red[CONV_THREADS / 32][CONV_PX];
-  __shared__ float s_scale[CONV_PX];
+  extern __shared__ float pxbuf[];  // [Cp][npx + 1]
+  __shared__ float red[CONV_THREADS];
+  __shared__ float s_scale[CONV_MAX_PX];
   const bool second = (int)blockIdx.z >= JJ.j[0].nimg;
   const ConvJob& J = JJ.j[second ? 1 : 0];
   const int img = (int)blockIdx.z - (second ? JJ.j[0].nimg : 0);
-  const int npx = J.oh * J.ow;
-  // few channels: a block takes several 32-pixel groups in turn, so that it still moves >= 32 KB
-  const int gpb = JJ.groups_per_block;
-  for (int grp = 0; grp < gpb; ++grp) {
-  const int n0 = (blockIdx.x * gpb + grp) * CONV_PX;
-  if (n0 >= npx) return;
+  const int total_px = J.oh * J.ow;
+  const int npx = 32 * JJ.groups, pitch = npx + 1, nsl = CONV_THREADS / npx;  // pixels per block, channel slices
+  const int n0 = blockIdx.x * npx;
+  if (n0 >= total_px) return;
   int sh = J.sh, sw = J.sw, padh = J.padh, padw = J.padw, bg = img;
   if (J.lat > 1) {
     const int ncls = J.lat * J.lat, cls = img % ncls;
@@ -160,11 +159,12 @@ __global__ void __launch_bounds__(CONV_THREADS) convert_pixels_kmajor_kernel(con
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NW = CONV_THREADS / 32;
 
-  // ---- sweep 1: lane = pixel, the warps split the channels
-  const int n = n0 + lane;
+  // ---- sweep 1: thread = (pixel, channel slice); consecutive threads take consecutive pixels
+  const int pl = threadIdx.x % npx, sl = threadIdx.x / npx;
+  const int n = n0 + pl;
   const int oy = n / J.ow, ox = n - oy * J.ow;
   const int y = oy * sh - padh, x = ox * sw - padw;
-  const bool in_img = n < npx && y >= 0 && y < J.H && x >= 0 && x < J.W;
+  const bool in_img = n < total_px && y >= 0 && y < J.H && x >= 0 && x < J.W;
   float m = 0.f;
   if (fl) {
     k5::Gather g;
@@ -173,67 +173,54 @@ __global__ void __launch_bounds__(CONV_THREADS) convert_pixels_kmajor_kernel(con
       const k5::Taps t = k5::make_taps(__ldg(fl + y * J.W + x), __ldg(fl + HW + y * J.W + x), x, y, J.H, J.W);
       g = k5::make_gather(t, J.W);
     }
-    for (int c = warp; c < J.Cp; c += NW) {
+    for (int c = sl; c < J.Cp; c += nsl) {
       float v = 0.f;
       if (c < J.C && !g.zero) {
         const float* sp = src + (long long)c * HW;
         v = (g.w00 * __ldg(sp + g.oaa) + g.w01 * __ldg(sp + g.oab)) + (g.w10 * __ldg(sp + g.oba) + g.w11 * __ldg(sp + g.obb));
       }
       m = fmaxf(m, fabsf(v));
-      pxbuf[c * 33 + lane] = v;
+      pxbuf[c * pitch + pl] = v;
     }
   } else {
     const float* sp = src + (long long)y * J.W + x;
-    int c = warp;
-    for (; c + 7 * NW < J.C; c += 8 * NW) {  // eight independent loads in flight
+    int c = sl;
+    for (; c + 7 * nsl < J.Cp; c += 8 * nsl) {  // eight independent loads in flight (channels >= C are zero-filled)
       float a[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) a[u] = in_img ? __ldg(sp + (long long)(c + u * NW) * HW) : 0.f;
+      for (int u = 0; u < 8; ++u) a[u] = (in_img && c + u * nsl < J.C) ? __ldg(sp + (long long)(c + u * nsl) * HW) : 0.f;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         m = fmaxf(m, fabsf(a[u]));
-        pxbuf[(c + u * NW) * 33 + lane] = a[u];
+        pxbuf[(c + u * nsl) * pitch + pl] = a[u];
       }
     }
-    for (; c + 3 * NW < J.Cp; c += 4 * NW) {  // remaining channels, four loads in flight (rows up to Cp are zero-filled)
-      float a[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) a[u] = (in_img && c + u * NW < J.C) ? __ldg(sp + (long long)(c + u * NW) * HW) : 0.f;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        m = fmaxf(m, fabsf(a[u]));
-        pxbuf[(c + u * NW) * 33 + lane] = a[u];
-      }
-    }
-    for (; c < J.Cp; c += NW) {
+    for (; c < J.Cp; c += nsl) {
       const float v = (in_img && c < J.C) ? __ldg(sp + (long long)c * HW) : 0.f;
       m = fmaxf(m, fabsf(v));
-      pxbuf[c * 33 + lane] = v;
+      pxbuf[c * pitch + pl] = v;
     }
   }
-  red[warp][lane] = m;
+  red[threadIdx.x] = m;  // [slice][pixel]
   __syncthreads();
-  if (warp == 0) {
-    float mm = red[0][lane];
-#pragma unroll
-    for (int i = 1; i < NW; ++i) mm = fmaxf(mm, red[i][lane]);
+  if ((int)threadIdx.x < npx) {
+    float mm = red[threadIdx.x];
+    for (int i = 1; i < nsl; ++i) mm = fmaxf(mm, red[i * npx + threadIdx.x]);
     const int eb = (int)((__float_as_uint(mm) >> 23) & 0xff);
     const int e = (eb == 0 || eb == 255) ? 0 : max(-126, min(126, eb - 127));  // 0 for an all-zero pixel
-    s_scale[lane] = __uint_as_float((unsigned int)(127 - e) << 23);
-    if (n < npx) J.rowscale[(long long)img * npx + n] = __uint_as_float((unsigned int)(127 + e) << 23);
+    s_scale[threadIdx.x] = __uint_as_float((unsigned int)(127 - e) << 23);
+    if (n0 + (int)threadIdx.x < total_px) J.rowscale[(long long)img * total_px + n0 + threadIdx.x] = __uint_as_float((unsigned int)(127 + e) << 23);
   }
   __syncthreads();
 
   // ---- sweep 2: a warp per pixel, a lane per channel pair of a 64-channel chunk (128-byte stores)
-  __half* dimg = J.dst + (long long)img * npx * J.Cp;
-  for (int pl = warp; pl < CONV_PX && n0 + pl < npx; pl += NW) {
-    const float sc = s_scale[pl];
+  __half* dimg = J.dst + (long long)img * total_px * J.Cp;
+  for (int p = warp; p < npx && n0 + p < total_px; p += NW) {
+    const float sc = s_scale[p];
     for (int c0 = 0; c0 < J.Cp; c0 += 64) {
       const int c = c0 + 2 * lane;
-      *reinterpret_cast<__half2*>(dimg + (long long)(n0 + pl) * J.Cp + c) = __floats2half2_rn(pxbuf[c * 33 + pl] * sc, pxbuf[(c + 1) * 33 + pl] * sc);
+      *reinterpret_cast<__half2*>(dimg + (long long)(n0 + p) * J.Cp + c) = __floats2half2_rn(pxbuf[c * pitch + p] * sc, pxbuf[(c + 1) * pitch + p] * sc);
     }
-  }
-  __syncthreads();  // the buffers are reused by the next group
   }
 }
 
@@ -702,10 +689,11 @@ int local_corr_tc_launch(const float* in1, const float* in2, const float* flow2,
     Q.C = C; Q.Cp = Cp; Q.H = H; Q.W = W; Q.oh = oh; Q.ow = ow; Q.sh = sh; Q.sw = sw; Q.padh = padh; Q.padw = padw; Q.lat = lat;
     Q.nimg = BG * ncls; Q.G = G;
     EZB_REQUIRE((long long)BG * (1 + ncls) <= 65535, "batch too large for one launch (split it)");
-    JJ.groups_per_block = std::max(1, std::min(8, 256 / Cp));
-    const size_t conv_smem = (size_t)Cp * 33 * 4;
+    JJ.groups = Cp <= 64 ? 4 : 1;  // measured (ncu): 4 concurrent groups help at 64 channels (58 -> 47 us on PWC-Net's finest level), not at 128
+    const int conv_px = 32 * JJ.groups;
+    const size_t conv_smem = (size_t)Cp * (conv_px + 1) * 4;
     EZB_CUDA_OK(cudaFuncSetAttribute(convert_pixels_kmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem));
-    convert_pixels_kmajor_kernel<<<dim3(cdiv(std::max(H * W, oh * ow), CONV_PX * JJ.groups_per_block), 1, BG * (1 + ncls)), CONV_THREADS, conv_smem, st>>>(JJ);
+    convert_pixels_kmajor_kernel<<<dim3(cdiv(std::max(H * W, oh * ow), conv_px), 1, BG * (1 + ncls)), CONV_THREADS, conv_smem, st>>>(JJ);
     EZB_LAUNCH_OK();
   }
 
