@@ -66,6 +66,12 @@ def _get_args_from_config(from_config_func, *args, **kwargs):
 
 
 def configurable(init_func):
+    """The reference's own decorator when ``ezflow`` is already loaded in this process (the drop-in classes then go
+    through exactly the reference's config plumbing); otherwise — on a machine without ezflow, e.g. the GPU box's tests that
+    never import it — the equivalent below."""
+    ref = sys.modules.get("ezflow.config")
+    if ref is not None and callable(getattr(ref, "configurable", None)) and "omegaconf" in sys.modules:
+        return ref.configurable(init_func)
     assert inspect.isfunction(init_func) and init_func.__name__ == "__init__", "Incorrect use of @configurable."
 
     @functools.wraps(init_func)

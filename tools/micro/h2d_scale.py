@@ -14,7 +14,7 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 
-steps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+steps = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 20
 world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
@@ -30,7 +30,29 @@ if world > 1:
 
     dist.init_process_group("nccl", device_id=dev)
 H, W, C, L, R, ITERS, P = 135, 240, 256, 4, 4, 12, 8
-h_in = [torch.empty(P, C, H, W).pin_memory(), torch.empty(P, C, H, W).pin_memory()] + [torch.empty(P, 2, H, W).pin_memory() for _ in range(ITERS)]
+WC = "--wc" in sys.argv  # H2D sources in write-combined pinned memory (cudaHostAllocWriteCombined)
+
+
+def host_buffer(*shape):
+    if not WC:
+        return torch.empty(*shape).pin_memory()
+    import ctypes
+
+    import numpy as np
+
+    rt = ctypes.CDLL("libcudart.so.12")
+    n = 4
+    for d in shape:
+        n *= d
+    p = ctypes.c_void_p()
+    rc = rt.cudaHostAlloc(ctypes.byref(p), ctypes.c_size_t(n), ctypes.c_uint(0x04))
+    assert rc == 0, f"cudaHostAlloc failed: {rc}"
+    arr = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_float)), shape=(n // 4,))
+    arr[:] = 0.5
+    return torch.from_numpy(arr).view(*shape)
+
+
+h_in = [host_buffer(P, C, H, W), host_buffer(P, C, H, W)] + [host_buffer(P, 2, H, W) for _ in range(ITERS)]
 d_in = [torch.empty_like(t, device=dev) for t in h_in]
 d_out = torch.empty(P, L * (2 * R + 1) ** 2, H, W, device=dev)
 h_out = torch.empty(d_out.shape).pin_memory()
