@@ -574,6 +574,35 @@ def run_secondary(args, dev, world, rank, peaks, headline_step):
         del f1, f2, coords, douts, bucket
         torch.cuda.empty_cache()
 
+    if enabled("reference_ops_on_this_gpu"):
+        # the honest GPU competitor: the unmodified reference class (cuBLAS bmm, avg_pool2d, grid_sample; TF32 off) on this GPU,
+        # one 1080p pair at a time (its fp32 volume + pooled copies take ~7 GB per pair)
+        cls = _import_reference_class()
+        if cls is not None:
+            old_tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+            torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+            try:
+                with torch.no_grad():
+                    g = torch.Generator(device="cpu").manual_seed(5 + rank)
+                    f1 = torch.randn(1, C, H, W, generator=g).to(dev)
+                    f2 = torch.randn(1, C, H, W, generator=g).to(dev)
+                    grid = E.coords_grid(1, H, W)
+                    coords = [(grid + torch.randn(1, 2, H, W, generator=g) * (2 + k)).clamp_(-16, W + 16).to(dev) for k in range(ITERS)]
+
+                    def ref_pair():
+                        fn = cls(f1, f2, num_levels=L, corr_radius=R)
+                        for k in range(ITERS):
+                            fn(coords[k])
+
+                    ms = timed(ref_pair, iters=5, warm=2)
+                records.append({"name": "reference_ops_on_this_gpu", "ms": ms, "pairs_per_s": world * 1e3 / ms,
+                                "note": "ezflow.similarity.MutliScalePairwise4DCorr (unmodified reference, PyTorch ops, TF32 off) on this GPU: "
+                                        "build + 12 lookups of ONE 1080p pair per call; pairs/s = ranks / time"})
+                del f1, f2, coords
+            finally:
+                torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old_tf32
+            torch.cuda.empty_cache()
+
     if enabled("headline_sustained") and args.sustained_seconds > 0:
         # the headline step repeated for >= sustained_seconds of device time: the SM clock settles at the power cap
         with torch.no_grad():
