@@ -27,6 +27,11 @@ def _worker(rank, world, port, q):
         ms = 10.0 + 5.0 * rank  # rank 1 is slower
         (mx,) = max_over_ranks([ms])
         (total,) = sum_over_ranks([hi - lo])
+        # config 5 (bench.py): every rank takes its block of the global batch, then ONE all-reduce(sum) of the gradient bucket
+        blo, bhi = shard_range(64, world, rank)
+        bucket = torch.full((1024,), float(bhi - blo))
+        dist.all_reduce(bucket)
+        assert bucket.eq(64.0).all()
         q.put((rank, lo, hi, mx, total))
     finally:
         dist.destroy_process_group()
