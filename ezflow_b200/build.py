@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIBPATH = os.path.join(LIBDIR, "libezflow_b200.so")
-SOURCES = ["cabi.cu", "corr_pyramid.cu", "corr_lookup.cu", "corr_lookup_conv.cu", "corr_bwd.cu", "corr_bwd_tc.cu", "local_corr.cu", "local_corr_tc.cu", "local_corr_bwd_tc.cu", "warp.cu",
+SOURCES = ["cabi.cu", "corr_pyramid.cu", "corr_lookup.cu", "corr_lookup_conv.cu", "corr_bwd.cu", "corr_bwd_tc.cu", "local_corr.cu", "local_corr_rt.cu", "local_corr_tc.cu", "local_corr_bwd_tc.cu", "warp.cu",
            "convex_upsample.cu", "volume_ops.cu"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",

@@ -35,6 +35,8 @@ struct LookupParams {
   const float* deq;     // [B]
   const float* coords;  // (B,2,N)
   float* out;           // (B, L*K*K, N)
+  const float* dout;    // coords-gradient mode: (B, L*K*K, N)
+  float* dcoords;       // coords-gradient mode: (B,2,N)
   int B, N, L, r;
 };
 
@@ -69,9 +71,12 @@ struct Gather {
   __device__ static __forceinline__ int chunk_floor(int xs) { return ((xs + 64) >> VW_LOG) - (64 >> VW_LOG); }  // xs >= -64
 };
 
-template <typename T>
+// DCOORDS = false: the lookup.  DCOORDS = true: its adjoint w.r.t. coords (autograd of grid_sample's grid argument,
+// pairwise.py:50-67) — same gather, but phase 2 contracts the window's horizontal / vertical tap differences with dout
+// instead of writing the taps; the per-warp partial sums of a query meet in shared memory.
+template <typename T, bool DCOORDS>
 __global__ void __launch_bounds__(NTHREADS, 3) corr_lookup_fwd_kernel(const LookupParams P, const int qstride_words) {
-  extern __shared__ __align__(16) uint32_t sm_words[];  // [QB][qstride_words] patches, then [L*QB] int2 item parameters
+  extern __shared__ __align__(16) uint32_t sm_words[];  // [QB][qstride_words] patches, then [L*QB] int2 item parameters (+ [2][QB] sums)
   constexpr int ES = (int)sizeof(T);
   const int r = P.r, D = 2 * r + 2, K = 2 * r + 1, KK = K * K;
   const int b = blockIdx.y, grp = blockIdx.x, q0 = grp * QB;  // QB == PYR_QG: a block serves one query group
@@ -81,6 +86,8 @@ __global__ void __launch_bounds__(NTHREADS, 3) corr_lookup_fwd_kernel(const Look
   const char* pair_base = P.pyr + (long long)b * P.n_tiles * P.n_groups * P.group_bytes + (long long)grp * P.group_bytes;
   const unsigned int tile_stride = (unsigned int)(P.n_groups * P.group_bytes);  // < 2^32, checked by the host
   int2* items = reinterpret_cast<int2*>(sm_words + QB * qstride_words);
+  float* gsum = reinterpret_cast<float*>(items + P.L * QB);  // DCOORDS only
+  if (DCOORDS && threadIdx.x < 2 * QB) gsum[threadIdx.x] = 0.f;
 
   // ---------------- phase 0: window origins ----------------
   // Every warp serves 4 queries of the block; lane k < 16 owns item (query k/4, level k%4) and keeps its
@@ -151,6 +158,51 @@ __global__ void __launch_bounds__(NTHREADS, 3) corr_lookup_fwd_kernel(const Look
   // Every warp takes a contiguous run of items, so the per-level setup is done once per warp (with 4 levels
   // and 8 warps: two warps per level).
   const int q = q0 + lane;
+  if constexpr (DCOORDS) {
+    // d out / d x = deq * [(1-fy)*(v01-v00) + fy*(v11-v10)] / 2^l,  d out / d y = (bot - top) / 2^l with the forward's
+    // horizontally interpolated rows `top`, `bot`; taps outside a level are the zeros the gather stored.
+    float gx = 0.f, gy = 0.f;
+    if (q < P.N) {
+      const float deq = __ldg(P.deq + b);
+      const float x = __ldg(cx_ptr + q), y = __ldg(cy_ptr + q);
+      const float* dq = P.dout + (long long)b * P.L * KK * P.N + q;
+      const T* sm_q = reinterpret_cast<const T*>(sm_words + lane * qstride_words);
+      const int n_items = P.L * K, n_warps = NTHREADS / 32;
+      for (int item = n_items * warp / n_warps; item < n_items * (warp + 1) / n_warps; ++item) {
+        const int l = item / K, i = item - l * K;
+        const float inv = 1.0f / (float)(1 << l);
+        const float cx = x * inv, cy = y * inv;
+        const float fx = cx - floorf(cx), fy = cy - floorf(cy);
+        const int xs = items[l * QB + lane].x;
+        const T* p = sm_q + l * D * row_el + (xs - G::chunk_floor(xs) * G::VW) + i;
+        const float* d = dq + (long long)(l * KK + i * K) * P.N;
+        float x0 = (float)p[0], x1 = (float)p[1];
+        float top = x0 + fx * (x1 - x0), dtop = x1 - x0, sx = 0.f, sy = 0.f;
+        for (int j = 0; j < K; ++j) {
+          p += row_el;
+          x0 = (float)p[0];
+          x1 = (float)p[1];
+          const float bot = x0 + fx * (x1 - x0), dbot = x1 - x0;
+          const float g = __ldg(d);
+          sx += g * (dtop + fy * (dbot - dtop));
+          sy += g * (bot - top);
+          top = bot;
+          dtop = dbot;
+          d += P.N;
+        }
+        gx += sx * (deq * inv);
+        gy += sy * (deq * inv);
+      }
+    }
+    atomicAdd(gsum + lane, gx);  // zeroed before the barrier that ends phase 1
+    atomicAdd(gsum + QB + lane, gy);
+    __syncthreads();
+    if (threadIdx.x < 2 * QB) {
+      const int c = threadIdx.x >> 5, qq = q0 + (threadIdx.x & 31);
+      if (qq < P.N) P.dcoords[((long long)b * 2 + c) * P.N + qq] = gsum[threadIdx.x];
+    }
+    return;
+  }
   if (q >= P.N) return;
   const float deq = __ldg(P.deq + b);
   const float x = __ldg(cx_ptr + q), y = __ldg(cy_ptr + q);
@@ -337,9 +389,9 @@ __global__ void __launch_bounds__(NTHREADS) corr_lookup_bwd_kernel(const LookupB
 
 using namespace ezb;
 
-extern "C" int ezb_corr_lookup_fwd(const void* pyramid, const float* deq_scale, const float* coords, int B, int H, int W, int L,
-                                   int radius, int dtype, float* out, void* stream) {
-  EZB_REQUIRE(pyramid && deq_scale && coords && out, "null pointer");
+static int lookup_launch(const void* pyramid, const float* deq_scale, const float* coords, int B, int H, int W, int L, int radius,
+                         int dtype, float* out, const float* dout, float* dcoords, void* stream) {
+  const bool dc = dcoords != nullptr;
   EZB_REQUIRE(B > 0 && H > 0 && W > 0 && L >= 1, "bad shape B=%d H=%d W=%d L=%d", B, H, W, L);
   EZB_REQUIRE(radius >= 0 && radius <= k3::MAX_RADIUS, "corr_radius %d outside [0,%d]", radius, k3::MAX_RADIUS);
   EZB_REQUIRE(dtype == EZB_F32 || dtype == EZB_F16, "bad dtype %d", dtype);
@@ -363,6 +415,8 @@ extern "C" int ezb_corr_lookup_fwd(const void* pyramid, const float* deq_scale, 
   P.deq = deq_scale;
   P.coords = coords;
   P.out = out;
+  P.dout = dout;
+  P.dcoords = dcoords;
   P.B = B;
   P.N = N;
   P.L = L;
@@ -375,20 +429,31 @@ extern "C" int ezb_corr_lookup_fwd(const void* pyramid, const float* deq_scale, 
   int qchunks = L * D * row_el * es / 16;
   qchunks |= 1;
   const int qwords = qchunks * 4;
-  const size_t smem = (size_t)k3::QB * qwords * 4 + (size_t)L * k3::QB * sizeof(int2);
+  const size_t smem = (size_t)k3::QB * qwords * 4 + (size_t)L * k3::QB * sizeof(int2) + (dc ? 2 * k3::QB * sizeof(float) : 0);
   if (smem > 200 * 1024) return fail(EZB_ERR_UNSUPPORTED, "lookup window too large (L=%d, r=%d)", L, radius);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static_assert(k3::QB == PYR_QG, "one lookup block per pyramid query group");
   dim3 grid(lay.n_groups, B);
-  if (dtype == EZB_F16) {
-    EZB_CUDA_OK(cudaFuncSetAttribute(k3::corr_lookup_fwd_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k3::corr_lookup_fwd_kernel<__half><<<grid, k3::NTHREADS, smem, st>>>(P, qwords);
-  } else {
-    EZB_CUDA_OK(cudaFuncSetAttribute(k3::corr_lookup_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k3::corr_lookup_fwd_kernel<float><<<grid, k3::NTHREADS, smem, st>>>(P, qwords);
-  }
-  EZB_LAUNCH_OK();
-  return EZB_OK;
+  auto launch = [&](auto kernel) -> int {
+    EZB_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<grid, k3::NTHREADS, smem, st>>>(P, qwords);
+    EZB_LAUNCH_OK();
+    return EZB_OK;
+  };
+  if (dtype == EZB_F16) return dc ? launch(k3::corr_lookup_fwd_kernel<__half, true>) : launch(k3::corr_lookup_fwd_kernel<__half, false>);
+  return dc ? launch(k3::corr_lookup_fwd_kernel<float, true>) : launch(k3::corr_lookup_fwd_kernel<float, false>);
+}
+
+extern "C" int ezb_corr_lookup_fwd(const void* pyramid, const float* deq_scale, const float* coords, int B, int H, int W, int L,
+                                   int radius, int dtype, float* out, void* stream) {
+  EZB_REQUIRE(pyramid && deq_scale && coords && out, "null pointer");
+  return lookup_launch(pyramid, deq_scale, coords, B, H, W, L, radius, dtype, out, nullptr, nullptr, stream);
+}
+
+extern "C" int ezb_corr_lookup_bwd_coords(const void* pyramid, const float* deq_scale, const float* coords, const float* dout, int B,
+                                          int H, int W, int L, int radius, int dtype, float* dcoords, void* stream) {
+  EZB_REQUIRE(pyramid && deq_scale && coords && dout && dcoords, "null pointer");
+  return lookup_launch(pyramid, deq_scale, coords, B, H, W, L, radius, dtype, nullptr, dout, dcoords, stream);
 }
 
 extern "C" int ezb_corr_grad_layout(int H, int W, int L, int* h, int* w, int* pitch, int64_t* qstride) {

@@ -336,6 +336,11 @@ size_t local_corr_tc_workspace_bytes(int BG, int C, int H, int W, int padh, int 
 int local_corr_tc_launch(const float* in1, const float* in2, const float* flow2, int BG, int G, int C, int H, int W, int Ph, int Pw, int sh, int sw,
                          int padh, int padw, int D, const int* dph, const int* dpw, float scale, float slope, float* out,
                          long long out_bstride, void* workspace, size_t workspace_bytes, cudaStream_t st);
+// local_corr_rt.cu
+bool local_corr_rt_supported(int H, int W, int BG, int Ph, int Pw, int sh, int sw, int padh, int padw, int dph, int dpw);
+bool local_corr_rt_preferred(int BG, int C, int H, int W, bool tc_available);
+int local_corr_rt_launch(const float* in1, const float* in2, int BG, int G, int C, int H, int W, int P, float scale,
+                         float slope, float* out, long long out_bstride, cudaStream_t st);
 // local_corr_bwd_tc.cu
 bool local_corr_bwd_tc_supported(int C, int H, int W, int Ph, int Pw, int sh, int sw, int padh, int padw, int dph, int dpw);
 size_t local_corr_bwd_tc_workspace_bytes(int BG, int C, int H, int W);
@@ -345,6 +350,8 @@ int local_corr_bwd_tc_launch(const float* in1, const float* in2, const float* do
 }  // namespace ezb
 
 using namespace ezb;
+
+extern "C" int ezb_warp_fwd(const float* x, const float* flow, int B, int C, int H, int W, float* out, void* stream);  // warp.cu
 
 static int check_local_args(int B, int C, int H, int W, int Ph, int Pw, int sh, int sw, int padh, int padw, int dph, int dpw) {
   EZB_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "bad input shape B=%d C=%d H=%d W=%d", B, C, H, W);
@@ -364,7 +371,12 @@ extern "C" int ezb_local_corr_fwd(const float* in1, const float* in2, int B, int
                                   int64_t out_batch_stride, void* workspace, size_t workspace_bytes, void* stream) {
   EZB_REQUIRE(in1 && in2 && out, "null pointer");
   if (int r = check_local_args(B, C, H, W, Ph, Pw, sh, sw, padh, padw, dph, dpw)) return r;
-  if (workspace != nullptr && local_corr_tc_supported(C, sh, sw, 1)) {
+  const bool tc_ok = workspace != nullptr && local_corr_tc_supported(C, sh, sw, 1);
+  // PWC-Net's shape (9x9 window, stride 1) on large maps with few channels: register-tiled fp32 kernel, no operand conversion
+  if (local_corr_rt_supported(H, W, B, Ph, Pw, sh, sw, padh, padw, dph, dpw) && local_corr_rt_preferred(B, C, H, W, tc_ok))
+    return local_corr_rt_launch(in1, in2, B, 1, C, H, W, Ph, scale, slope, out,
+                                out_batch_stride > 0 ? out_batch_stride : (int64_t)Ph * Pw * H * W, static_cast<cudaStream_t>(stream));
+  if (tc_ok) {
     const int oh = cdiv(H + 2 * padh, sh), ow = cdiv(W + 2 * padw, sw);
     return local_corr_tc_launch(in1, in2, nullptr, B, 1, C, H, W, Ph, Pw, sh, sw, padh, padw, 1, &dph, &dpw, scale, slope, out,
                                 out_batch_stride > 0 ? out_batch_stride : (int64_t)Ph * Pw * oh * ow, workspace, workspace_bytes,
@@ -416,9 +428,19 @@ extern "C" int ezb_warp_local_corr_fwd(const float* in1, const float* in2, const
                                        void* stream) {
   EZB_REQUIRE(in1 && in2 && flow && out, "null pointer");
   if (int r = check_local_args(B, C, H, W, Ph, Pw, sh, sw, padh, padw, dph, dpw)) return r;
-  if (workspace == nullptr || !local_corr_tc_supported(C, sh, sw, 1))
-    return fail(EZB_ERR_UNSUPPORTED, "the warp-fused correlation runs on the tensor-core path only (needs a workspace and C <= 256); "
-                                     "call ezb_warp_fwd and ezb_local_corr_fwd instead");
+  const bool tc_ok = workspace != nullptr && local_corr_tc_supported(C, sh, sw, 1);
+  // Where the register-tiled kernel beats the tensor-core path (PWC-Net's finest levels), warping into the workspace first
+  // (K5, one read + one write of in2) and correlating from there is faster than warping inside the tensor-core path's
+  // conversion pass: 71 vs 162 us on the (8,32,112,256) level.  The workspace is always large enough (>= 4 bytes per element).
+  if (tc_ok && local_corr_rt_supported(H, W, B, Ph, Pw, sh, sw, padh, padw, dph, dpw) && local_corr_rt_preferred(B, C, H, W, true) &&
+      workspace_bytes >= (size_t)B * C * H * W * sizeof(float)) {
+    float* warped = static_cast<float*>(workspace);
+    if (int r = ezb_warp_fwd(in2, flow, B, C, H, W, warped, stream)) return r;
+    return local_corr_rt_launch(in1, warped, B, 1, C, H, W, Ph, scale, slope, out,
+                                out_batch_stride > 0 ? out_batch_stride : (int64_t)Ph * Pw * H * W, static_cast<cudaStream_t>(stream));
+  }
+  if (!tc_ok)
+    return fail(EZB_ERR_UNSUPPORTED, "the warp-fused correlation needs a workspace and C <= 256; call ezb_warp_fwd and ezb_local_corr_fwd instead");
   const int oh = cdiv(H + 2 * padh, sh), ow = cdiv(W + 2 * padw, sw);
   return local_corr_tc_launch(in1, in2, flow, B, 1, C, H, W, Ph, Pw, sh, sw, padh, padw, 1, &dph, &dpw, scale, slope, out,
                               out_batch_stride > 0 ? out_batch_stride : (int64_t)Ph * Pw * oh * ow, workspace, workspace_bytes,

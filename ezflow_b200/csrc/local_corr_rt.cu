@@ -1,0 +1,311 @@
+// K4 on CUDA cores, register-tiled: the PWC-Net shape of the local correlation (9x9 window, stride 1, no dilation) for
+// large maps with few channels, exact fp32.
+//
+// Replaces iter_spatial_correlation_sample (reference ezflow/similarity/correlation/sampler.py:96-129) for
+//   stride 1, padding 0, dilation_patch 1, square odd patch P <= 9:
+//   out[bg,pi,pj,y,x] = act( scale * sum_c in1[bg,c,y,x] * in2[bg,c, y + pi - md, x + pj - md] ),  md = (P-1)/2, 0 outside.
+//
+// Why not the tensor-core kernel (local_corr_tc.cu) here: PWC-Net's two finest levels have 32 / 64 channels, i.e. only
+// 2.6-5.2 kFMA per output pixel.  The tcgen05 path computes a (queries x targets) band of which 1/5 is kept, after a
+// conversion pass that moves as many bytes as the whole problem, and spends its time extracting the band from TMEM
+// (138 us for the (8,32,112,256) level: 58 us conversion + 80 us kernel).  On CUDA cores the same level is 0.59 GFMA:
+// 16 us at the FMA peak.  The products have to come out of shared memory at >= 16 FMA per 16-byte load to get there;
+// the tiling below reaches 10.8 (shared-memory-bound at ~2/3 of the FMA peak), needs no workspace and no operand
+// scaling, and is bit-comparable to the fp32 reference up to summation order.
+//
+//   block  : 32 x 8 output pixels of one image, 64 * ceil(P/3) threads.
+//   thread : 4 consecutive pixels (x) x 3 displacement rows (pi) x all P displacement columns: 12 * P accumulators.
+//            Per channel it reads its in1 quad (one LDS.128) and, per displacement row, the 12 in2 values
+//            x - 4 .. x + 7 of that row (three LDS.128, 128 contiguous bytes per quarter-warp: conflict-free)
+//            -> 36 FMAs per three loads.
+//   stages : CC = 8 channels of the in1 tile (8 x 32) and of the in2 halo tile (16 x 40), fetched with 16-byte cp.async
+//            (zero-filled outside the image / beyond C) through a three-stage ring with one barrier per stage; a thread
+//            copies the same (row, quad) chunk for every channel, so its addresses are decoded once.
+//   stores : float4 per (pi, pj): 8 lanes write 128 contiguous bytes of the (B, G, P, P, H, W) output.
+// The warp-fused entry point (ezb_warp_local_corr_fwd) uses it too where it is the faster kernel: K5 warps in2 into the
+// workspace first (a halo-warping variant of this kernel was 3x slower than that: every halo pixel is warped 2.5 times).
+#include "ezb_common.cuh"
+
+#include <cstdlib>
+
+namespace ezb {
+namespace k4rt {
+
+constexpr int TW = 32;   // output tile width
+constexpr int CC = 8;    // channels per stage
+constexpr int MDA = 4;   // the halo starts MDA columns left of the tile (aligned for LDS.128), MDA >= md
+
+// TH output rows per tile, PR displacement rows per thread.  <8, 3>: the large-map configuration described above.
+// <4, 1>: small maps (fewer than one 32 x 8 tile per SM): half the tile, a third of the accumulators, i.e. 6x the threads
+// per pixel, at 9 instead of 10.8 FMAs per shared-memory load.
+template <int P, int TH_, int PR_>
+struct Cfg {
+  static constexpr int TH = TH_, PR = PR_;
+  static constexpr int MD = (P - 1) / 2;
+  static constexpr int NPG = (P + PR - 1) / PR;       // displacement-row groups
+  static constexpr int NT = (TW / 4) * TH * NPG;      // threads
+  static constexpr int HALO_W = MDA + TW + 4;         // x0 - 4 .. x0 + 35 (MD <= 4)
+  static constexpr int HALO_H = TH + 2 * MD;
+  static constexpr int IN2_STAGE = CC * HALO_H * HALO_W;  // floats
+  static constexpr int IN1_STAGE = CC * TH * TW;
+  static constexpr int STAGE = IN2_STAGE + IN1_STAGE;
+  static constexpr int NSTAGE = 3;
+  static constexpr size_t SMEM = (size_t)NSTAGE * STAGE * sizeof(float);
+  // staging geometry of the vector path: a thread copies the same (row, quad) chunk of the halo for every channel of a stage
+  static constexpr int N2PC = HALO_H * (HALO_W / 4);        // 16-byte chunks of one channel's halo
+  static constexpr int J2 = (N2PC + NT - 1) / NT;           // ... per thread
+  static constexpr int N1PC = TH * (TW / 4);                // chunks of one channel's in1 tile (64)
+  static constexpr int CPP = NT / N1PC;                     // in1 channels covered by one pass of the block
+  static_assert(P % 2 == 1 && MD <= MDA, "patch size");
+};
+
+struct Params {
+  const float* in1;
+  const float* in2;
+  float* out;
+  int BG, G, C, H, W;
+  float scale, slope;
+  long long out_bstride;
+};
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t nbytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src, uint32_t nbytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+}
+
+// VEC: W % 4 == 0 and 16-byte aligned tensors, so an aligned quad of pixels is entirely inside or outside the image
+template <int P, int TH, int PR, bool VEC>
+__global__ void __launch_bounds__(Cfg<P, TH, PR>::NT, 2) local_corr_rt_kernel(const Params Q) {
+  using K = Cfg<P, TH, PR>;
+  constexpr int MD = K::MD, HALO_W = K::HALO_W, HALO_H = K::HALO_H, NT = K::NT;
+  extern __shared__ __align__(16) float sm_rt[];
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, bg = blockIdx.z;
+  const long long HW = (long long)Q.H * Q.W;
+  const float* in1 = Q.in1 + (long long)bg * Q.C * HW;
+  const float* in2 = Q.in2 + (long long)bg * Q.C * HW;
+  const uint32_t sm_base = (uint32_t)__cvta_generic_to_shared(sm_rt);
+
+  // ---- vector path: the (row, quad) chunks this thread copies in every stage, decoded once
+  [[maybe_unused]] int goff2[K::J2];
+  [[maybe_unused]] unsigned ok2 = 0;
+  [[maybe_unused]] const int ccs1 = tid / K::N1PC, ch1 = tid - (tid / K::N1PC) * K::N1PC;
+  [[maybe_unused]] int goff1 = 0;
+  [[maybe_unused]] bool ok1 = false;
+  if constexpr (VEC) {
+#pragma unroll
+    for (int j = 0; j < K::J2; ++j) {
+      const int ch = tid + j * NT, hy = ch / (HALO_W / 4), hq = ch - hy * (HALO_W / 4);
+      const int y = y0 - MD + hy, x = x0 - MDA + 4 * hq;
+      goff2[j] = y * Q.W + x;
+      if (ch < K::N2PC && y >= 0 && y < Q.H && x >= 0 && x < Q.W) ok2 |= 1u << j;
+    }
+    const int ty1 = ch1 / (TW / 4), qx1 = ch1 - ty1 * (TW / 4);
+    goff1 = (y0 + ty1) * Q.W + x0 + 4 * qx1;
+    ok1 = y0 + ty1 < Q.H && x0 + 4 * qx1 < Q.W;
+  }
+
+  // ---- staging of one channel chunk into buffer `buf`
+  auto stage = [&](int buf, int c0) {
+    [[maybe_unused]] float* s2 = sm_rt + buf * K::STAGE;
+    const uint32_t a2 = sm_base + (uint32_t)(buf * K::STAGE) * 4u, a1 = a2 + (uint32_t)K::IN2_STAGE * 4u;
+    if constexpr (VEC) {
+      const float* g2 = in2 + (long long)c0 * HW;
+#pragma unroll
+      for (int j = 0; j < K::J2; ++j) {
+        const int ch = tid + j * NT;
+        if (K::N2PC % NT != 0 && ch >= K::N2PC) break;
+        const uint32_t dst = a2 + (uint32_t)ch * 16u;
+        if ((ok2 >> j) & 1u) {
+          const float* src = g2 + goff2[j];
+#pragma unroll
+          for (int cc = 0; cc < CC; ++cc) {
+            if (c0 + cc < Q.C)
+              cp_async_16(dst + (uint32_t)(cc * K::N2PC) * 16u, src + (long long)cc * HW, 16u);
+            else
+              *reinterpret_cast<float4*>(s2 + (cc * K::N2PC + ch) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        } else {  // outside the image: plain zero stores (ordered before the readers by the stage barrier)
+#pragma unroll
+          for (int cc = 0; cc < CC; ++cc) *reinterpret_cast<float4*>(s2 + (cc * K::N2PC + ch) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    } else {
+      constexpr int N2 = CC * HALO_H * HALO_W;
+      for (int i = tid; i < N2; i += NT) {
+        const int cc = i / (HALO_H * HALO_W), rem = i - cc * (HALO_H * HALO_W), hy = rem / HALO_W, hx = rem - hy * HALO_W;
+        const int y = y0 - MD + hy, x = x0 - MDA + hx, c = c0 + cc;
+        const bool ok = c < Q.C && y >= 0 && y < Q.H && x >= 0 && x < Q.W;
+        cp_async_4(a2 + (uint32_t)i * 4u, ok ? in2 + (long long)c * HW + (long long)y * Q.W + x : in2, ok ? 4u : 0u);
+      }
+    }
+    if constexpr (VEC) {
+      const float* g1 = in1 + (long long)c0 * HW + goff1;
+      float* s1 = s2 + K::IN2_STAGE;
+#pragma unroll
+      for (int cc = ccs1; cc < CC; cc += K::CPP) {
+        if (ok1 && c0 + cc < Q.C)
+          cp_async_16(a1 + (uint32_t)(cc * K::N1PC + ch1) * 16u, g1 + (long long)cc * HW, 16u);
+        else
+          *reinterpret_cast<float4*>(s1 + (cc * K::N1PC + ch1) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else {
+      constexpr int N1 = CC * TH * TW;
+      for (int i = tid; i < N1; i += NT) {
+        const int cc = i / (TH * TW), rem = i - cc * (TH * TW), ty = rem / TW, xx = rem - ty * TW;
+        const int y = y0 + ty, x = x0 + xx, c = c0 + cc;
+        const bool ok = c < Q.C && y < Q.H && x < Q.W;
+        cp_async_4(a1 + (uint32_t)i * 4u, ok ? in1 + (long long)c * HW + (long long)y * Q.W + x : in1, ok ? 4u : 0u);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  // ---- thread geometry
+  const int pg = tid / K::N1PC, r64 = tid - pg * K::N1PC, qx = r64 & 7, ty = r64 >> 3;
+  const int pi0 = pg * PR;
+  float acc[PR][P][4];
+#pragma unroll
+  for (int r = 0; r < PR; ++r)
+#pragma unroll
+    for (int pj = 0; pj < P; ++pj)
+#pragma unroll
+      for (int px = 0; px < 4; ++px) acc[r][pj][px] = 0.f;
+
+  // three-stage cp.async pipeline, one barrier per stage: the barrier of iteration k orders every thread's reads of buffer
+  // (k - 1) % 3 before the copies of stage k + 2 that overwrite it
+  const int nk = (Q.C + CC - 1) / CC;
+  stage(0, 0);
+  if (nk > 1) stage(1, CC);
+  for (int k = 0; k < nk; ++k) {
+    if (k + 1 < nk) {
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    if (k + 2 < nk) stage((k + 2) % K::NSTAGE, (k + 2) * CC);
+    const float* s2 = sm_rt + (k % K::NSTAGE) * K::STAGE;
+    const float* s1 = s2 + K::IN2_STAGE;
+    // the loads of displacement row r + 1 (or of the next channel's first row and in1 quad) are issued before the 36 FMAs of row r
+    const float4* rowp = reinterpret_cast<const float4*>(s2 + (ty + pi0) * HALO_W + 4 * qx);
+    const float4* ap = reinterpret_cast<const float4*>(s1 + ty * TW + 4 * qx);
+    constexpr int ROW4 = HALO_W / 4, CH4 = HALO_H * HALO_W / 4, A4 = TH * TW / 4;
+    const int nrows = (P % PR != 0 && pi0 + PR > P) ? P - pi0 : PR;  // the last group of P = 5, 7 has fewer rows
+    float4 a = ap[0], v0 = rowp[0], v1 = rowp[1], v2 = rowp[2];
+#pragma unroll 2
+    for (int cc = 0; cc < CC; ++cc) {
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      float4 an = a;
+#pragma unroll
+      for (int r = 0; r < PR; ++r) {
+        if (P % PR != 0 && r >= nrows) break;
+        const float v[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+        const bool last_row = (P % PR != 0) ? r + 1 >= nrows : r + 1 == PR;
+        if (!last_row) {
+          const float4* nx = rowp + cc * CH4 + (r + 1) * ROW4;
+          v0 = nx[0]; v1 = nx[1]; v2 = nx[2];
+        } else if (cc + 1 < CC) {
+          const float4* nx = rowp + (cc + 1) * CH4;
+          v0 = nx[0]; v1 = nx[1]; v2 = nx[2];
+          an = ap[(cc + 1) * A4];
+        }
+#pragma unroll
+        for (int pj = 0; pj < P; ++pj)
+#pragma unroll
+          for (int px = 0; px < 4; ++px) acc[r][pj][px] = fmaf(av[px], v[MDA - MD + pj + px], acc[r][pj][px]);
+      }
+      a = an;
+    }
+  }
+
+  // ---- epilogue
+  const int y = y0 + ty, x = x0 + 4 * qx;
+  if (y >= Q.H || x >= Q.W) return;
+  const int b = bg / Q.G, g = bg - b * Q.G;
+  float* dst = Q.out + (long long)b * Q.out_bstride + ((long long)g * P * P + (long long)pi0 * P) * HW + (long long)y * Q.W + x;
+  const bool plain = Q.slope == 1.f;
+#pragma unroll
+  for (int r = 0; r < PR; ++r) {
+    if (pi0 + r >= P) break;
+#pragma unroll
+    for (int pj = 0; pj < P; ++pj, dst += HW) {
+      float o[4];
+#pragma unroll
+      for (int px = 0; px < 4; ++px) {
+        const float v = acc[r][pj][px] * Q.scale;
+        o[px] = (plain || v >= 0.f) ? v : v * Q.slope;
+      }
+      if constexpr (VEC) {
+        __stcs(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
+      } else {
+#pragma unroll
+        for (int px = 0; px < 4; ++px)
+          if (x + px < Q.W) dst[px] = o[px];
+      }
+    }
+  }
+}
+
+template <int P, int TH, int PR, bool VEC>
+static int launch(const Params& Q, cudaStream_t st) {
+  using K = Cfg<P, TH, PR>;
+  auto kern = local_corr_rt_kernel<P, TH, PR, VEC>;
+  EZB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
+  dim3 grid(cdiv(Q.W, TW), cdiv(Q.H, TH), Q.BG);
+  kern<<<grid, K::NT, K::SMEM, st>>>(Q);
+  EZB_LAUNCH_OK();
+  return EZB_OK;
+}
+
+}  // namespace k4rt
+
+bool local_corr_rt_supported(int H, int W, int BG, int Ph, int Pw, int sh, int sw, int padh, int padw, int dph, int dpw) {
+  return Ph == Pw && (Ph == 3 || Ph == 5 || Ph == 7 || Ph == 9) && sh == 1 && sw == 1 && padh == 0 && padw == 0 && dph == 1 && dpw == 1 &&
+         cdiv(H, 4) <= 65535 && BG <= 65535;
+}
+
+static long long rt_tiles(int BG, int H, int W) { return (long long)cdiv(W, k4rt::TW) * cdiv(H, 8) * BG; }  // 32 x 8 tiles
+
+// Small maps (fewer 32 x 8 tiles than SMs) run the <4, 1> configuration.
+static bool rt_small(int BG, int H, int W) {
+  if (const char* e = getenv("EZB_LOCAL_CORR_RT_SMALL")) return atoi(e) != 0;
+  return rt_tiles(BG, H, W) < 148;
+}
+
+// Preferred over the tensor-core path?  The register-tiled kernel's only parallelism is over pixels, and its cost grows with
+// 81 FMAs per channel and pixel where the band GEMM's does not: it wins on PWC-Net's finest levels (few channels, large maps),
+// not on the coarse ones (measured per level: profiles/r02_local_corr_rt.md).
+bool local_corr_rt_preferred(int BG, int C, int H, int W, bool tc_available) {
+  if (const char* e = getenv("EZB_LOCAL_CORR_RT")) return atoi(e) != 0;
+  const long long tiles = rt_tiles(BG, H, W);
+  if (!tc_available) return tiles >= 4;  // against the generic fp32 kernel (which splits displacement rows over blocks for tiny maps)
+  return tiles >= 200 && C <= 96;
+}
+
+int local_corr_rt_launch(const float* in1, const float* in2, int BG, int G, int C, int H, int W, int P, float scale,
+                         float slope, float* out, long long out_bstride, cudaStream_t st) {
+  k4rt::Params Q;
+  Q.in1 = in1; Q.in2 = in2; Q.out = out;
+  Q.BG = BG; Q.G = G; Q.C = C; Q.H = H; Q.W = W;
+  Q.scale = scale; Q.slope = slope; Q.out_bstride = out_bstride;
+  const bool vec = W % 4 == 0 && ((reinterpret_cast<uintptr_t>(in1) | reinterpret_cast<uintptr_t>(in2) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
+                   out_bstride % 4 == 0;
+  const bool small = rt_small(BG, H, W);
+#define EZB_RT_CASE(PP)                                                                                                   \
+  case PP:                                                                                                                \
+    if (small) return vec ? k4rt::launch<PP, 4, 1, true>(Q, st) : k4rt::launch<PP, 4, 1, false>(Q, st);                   \
+    return vec ? k4rt::launch<PP, 8, 3, true>(Q, st) : k4rt::launch<PP, 8, 3, false>(Q, st);
+  switch (P) {
+    EZB_RT_CASE(9)
+    EZB_RT_CASE(7)
+    EZB_RT_CASE(5)
+    EZB_RT_CASE(3)
+  }
+#undef EZB_RT_CASE
+  return fail(EZB_ERR_UNSUPPORTED, "register-tiled local correlation: patch size %d", P);
+}
+
+}  // namespace ezb

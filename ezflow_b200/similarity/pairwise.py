@@ -231,16 +231,27 @@ class _LookupFn(torch.autograd.Function):
         (coords,) = ctx.saved_tensors
         st = ctx.state
         dout = dout.contiguous().float()
-        glv = st.ensure_grad()
         B, _, H, W = coords.shape
+        gtoken = dcoords = None
         with torch.cuda.device(st.device):
-            _cabi.check(
-                _cabi.lib().ezb_corr_lookup_bwd(
-                    _cabi.ptr(dout), _cabi.ptr(coords), B, H, W, st.L, ctx.radius, _cabi.ptr_array(glv),
-                    _cabi.stream_ptr(st.device),
+            if ctx.needs_input_grad[0]:  # towards the feature maps: accumulate into the gradient pyramid (K3b)
+                glv = st.ensure_grad()
+                _cabi.check(
+                    _cabi.lib().ezb_corr_lookup_bwd(
+                        _cabi.ptr(dout), _cabi.ptr(coords), B, H, W, st.L, ctx.radius, _cabi.ptr_array(glv),
+                        _cabi.stream_ptr(st.device),
+                    )
                 )
-            )
-        return torch.zeros((), dtype=torch.float32, device=dout.device), None, None, None
+                gtoken = torch.zeros((), dtype=torch.float32, device=dout.device)
+            if ctx.needs_input_grad[1]:  # towards coords (RAFT detaches them, models/raft.py:115; the reference's op has it)
+                dcoords = torch.empty_like(coords)
+                _cabi.check(
+                    _cabi.lib().ezb_corr_lookup_bwd_coords(
+                        _cabi.ptr(st.pyr), _cabi.ptr(st.deq), _cabi.ptr(coords), _cabi.ptr(dout), B, H, W, st.L, ctx.radius,
+                        st.dtype_code, _cabi.ptr(dcoords), _cabi.stream_ptr(st.device),
+                    )
+                )
+        return gtoken, dcoords, None, None
 
 
 @SIMILARITY_REGISTRY.register()
@@ -303,8 +314,8 @@ class MutliScalePairwise4DCorr:
         st = self._state
         if c.dim() != 4 or c.shape[0] != st.B or c.shape[1] != 2 or c.shape[2] != st.H or c.shape[3] != st.W:
             raise ValueError(f"coords must be ({st.B},2,{st.H},{st.W}); got {tuple(coords.shape)}")
-        if self._token is not None and torch.is_grad_enabled():
-            return _LookupFn.apply(self._token, c.detach(), st, int(self.corr_radius))
+        if torch.is_grad_enabled() and (self._token is not None or c.requires_grad):
+            return _LookupFn.apply(self._token, c, st, int(self.corr_radius))
         if self._lazy_lookup:
             from .lookup_conv import LazyLookup
 

@@ -128,6 +128,12 @@ int ezb_corr_grad_layout(int H, int W, int L, int* h, int* w, int* pitch, int64_
 int ezb_corr_lookup_bwd(const float* dout /* (B, L*(2r+1)^2, H, W) */, const float* coords,
                         int B, int H, int W, int L, int radius,
                         float* const* dlvl_ptrs /*[L] host*/, void* stream);
+/* Adjoint of ezb_corr_lookup_fwd w.r.t. coords (autograd of `coords / 2**i`, bilinear_sampler's normalisation and
+ * grid_sample's grid argument, pairwise.py:50-67, utils/resampling.py:71-83): dcoords (B,2,H,W) fp32 is overwritten.
+ * RAFT detaches coords (models/raft.py:115); the entry point exists for callers that do not. */
+int ezb_corr_lookup_bwd_coords(const void* pyramid, const float* deq_scale /*[B]*/, const float* coords,
+                               const float* dout /* (B, L*(2r+1)^2, H, W) */, int B, int H, int W, int L, int radius,
+                               int dtype, float* dcoords, void* stream);
 
 /* Adjoint of the pyramid build (K2b + K1b): dfmap1, dfmap2 (B,C,H,W) fp32 from the gradient levels.
  * With a workspace of ezb_corr_pyramid_bwd_workspace_bytes() (non-zero when C <= 256, L <= 4 and H*W % 4 == 0) both

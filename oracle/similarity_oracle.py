@@ -148,7 +148,7 @@ def corr_lookup_bwd(
     """Adjoint of corr_lookup w.r.t. the pyramid (autograd of grid_sample, zeros padding).
 
     pyramid_shapes[l] = (h_l, w_l); returns list of (B*N,1,h_l,w_l) gradients.
-    Gradient w.r.t. coords is not produced (RAFT detaches coords, models/raft.py:115)."""
+    The gradient w.r.t. coords is corr_lookup_bwd_coords below."""
     r = radius
     k = 2 * r + 1
     b, _, h1, w1 = coords.shape
@@ -186,6 +186,53 @@ def corr_lookup_bwd(
                 )
         grads.append(g.reshape(n, 1, hl, wl))
     return grads
+
+
+def corr_lookup_bwd_coords(pyramid: Sequence[np.ndarray], coords: np.ndarray, dout: np.ndarray, radius: int = 4) -> np.ndarray:
+    """Adjoint of corr_lookup w.r.t. coords -> (B,2,H,W): autograd of ``coords / 2**l`` (pairwise.py:50-52), the
+    normalisation in bilinear_sampler (utils/resampling.py:71-77) and grid_sample's grid gradient (bilinear, zeros
+    padding, align_corners=True).  RAFT never uses it (``coords1.detach()``, models/raft.py:115); the reference's op
+    produces it all the same.
+
+    d sample / d ix = (1-fy)*(v01 - v00) + fy*(v11 - v10), d sample / d iy = (1-fx)*(v10 - v00) + fx*(v11 - v01), where
+    neighbours outside the level count as 0; the (W_l-1)/2 of the un-normalisation and the 2/(W_l-1) of the
+    normalisation cancel up to rounding, leaving the factor 1/2**l per level."""
+    r = radius
+    k = 2 * r + 1
+    b, _, h1, w1 = coords.shape
+    n = b * h1 * w1
+    dt = np.float32
+    c = np.transpose(coords, (0, 2, 3, 1)).reshape(n, 2).astype(dt)
+    do = np.transpose(dout, (0, 2, 3, 1)).reshape(n, len(pyramid), k, k).astype(dt)
+    d = np.arange(-r, r + 1).astype(dt)
+    g = np.zeros((n, 2), dtype=np.float64)
+    qidx = np.broadcast_to(np.arange(n)[:, None, None], (n, k, k))
+    for lvl, corr in enumerate(pyramid):
+        hl, wl = corr.shape[-2:]
+        img = corr.reshape(n, hl, wl).astype(dt)
+        sx = c[:, 0, None, None] / dt(2**lvl) + d[None, :, None]
+        sy = c[:, 1, None, None] / dt(2**lvl) + d[None, None, :]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            gx = dt(2) * sx / dt(wl - 1) - dt(1)
+            gy = dt(2) * sy / dt(hl - 1) - dt(1)
+        ix = np.broadcast_to(((gx + dt(1)) / dt(2)) * dt(wl - 1), (n, k, k))
+        iy = np.broadcast_to(((gy + dt(1)) / dt(2)) * dt(hl - 1), (n, k, k))
+        x0 = np.floor(ix)
+        y0 = np.floor(iy)
+        fx = ix - x0
+        fy = iy - y0
+        v = {}
+        for dy in (0, 1):
+            for dx in (0, 1):
+                xi = x0.astype(np.int64) + dx
+                yi = y0.astype(np.int64) + dy
+                valid = (xi >= 0) & (xi < wl) & (yi >= 0) & (yi < hl)
+                v[dy, dx] = np.where(valid, img[qidx, np.clip(yi, 0, hl - 1), np.clip(xi, 0, wl - 1)], dt(0))
+        dix = (dt(1) - fy) * (v[0, 1] - v[0, 0]) + fy * (v[1, 1] - v[1, 0])
+        diy = (dt(1) - fx) * (v[1, 0] - v[0, 0]) + fx * (v[1, 1] - v[0, 1])
+        g[:, 0] += (do[:, lvl] * dix).sum(axis=(1, 2), dtype=np.float64) / 2**lvl
+        g[:, 1] += (do[:, lvl] * diy).sum(axis=(1, 2), dtype=np.float64) / 2**lvl
+    return np.ascontiguousarray(np.transpose(g.reshape(b, h1, w1, 2), (0, 3, 1, 2))).astype(np.float32)
 
 
 def avg_pool2x2_bwd(dy: np.ndarray, in_hw: Tuple[int, int]) -> np.ndarray:

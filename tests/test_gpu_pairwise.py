@@ -73,6 +73,46 @@ def test_backward_vs_reference_golden(golden, name):
     assert_close(f2.grad, g["df2"], GRAD_TOL, f"{name} dfmap2")
 
 
+@pytest.mark.parametrize("store", ["fp16", "fp32"])
+@pytest.mark.parametrize("name", ["lookup_dcoords_l4_r4", "lookup_dcoords_l2_r1"])
+def test_coords_gradient_vs_reference_golden(golden, name, store):
+    """RAFT detaches coords (models/raft.py:115), but the reference's lookup is differentiable in them: so is this one."""
+    import ezflow_b200 as E
+
+    g = golden(name)
+    L, r = int(g["levels"]), int(g["radius"])
+    E.set_pyramid_dtype(store)
+    coords = to_gpu(g["coords"], True)
+    obj = E.MutliScalePairwise4DCorr(to_gpu(g["f1"]), to_gpu(g["f2"]), num_levels=L, corr_radius=r)  # fmaps without grad
+    out = obj(coords)
+    assert_close(out, g["out"], LOOK_TOL, f"{name} lookup ({store})")
+    (out * to_gpu(g["dout"])).sum().backward()
+    assert tuple(coords.grad.shape) == g["dcoords"].shape
+    assert_close(coords.grad, g["dcoords"], GRAD_TOL, f"{name} dcoords ({store})")
+
+
+def test_coords_and_feature_gradients_together():
+    """coords = coords0 + flow(f1): both adjoints in one backward pass, against the oracle's chain."""
+    import ezflow_b200 as E
+    from oracle import similarity_oracle as O
+
+    rng = np.random.default_rng(7)
+    B, C, H, W, L, r = 2, 32, 12, 18, 3, 2
+    f1 = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    f2 = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    coords = O.coords_grid(B, H, W) + rng.uniform(-4, 4, (B, 2, H, W)).astype(np.float32)
+    dout = rng.standard_normal((B, L * (2 * r + 1) ** 2, H, W)).astype(np.float32)
+    t1, t2, tc = to_gpu(f1, True), to_gpu(f2, True), to_gpu(coords, True)
+    out = E.MutliScalePairwise4DCorr(t1, t2, num_levels=L, corr_radius=r)(tc * 1.0)  # non-leaf coords
+    (out * to_gpu(dout)).sum().backward()
+    pyr = O.corr_pyramid(f1, f2, L)
+    dpyr = O.corr_lookup_bwd([p.shape[-2:] for p in pyr], coords, dout, r)
+    d1, d2 = O.corr_pyramid_bwd(f1, f2, dpyr)
+    assert_close(tc.grad, O.corr_lookup_bwd_coords(pyr, coords, dout, r), GRAD_TOL, "dcoords")
+    assert_close(t1.grad, d1, GRAD_TOL, "dfmap1")
+    assert_close(t2.grad, d2, GRAD_TOL, "dfmap2")
+
+
 @pytest.mark.parametrize("shape", [(2, 40, 9, 11), (2, 256, 12, 20), (1, 256, 11, 13)])
 def test_backward_vs_oracle_shapes(shape):
     """Adjoints vs the numpy oracle on shapes the golden fixtures do not hold: H*W % 4 != 0 (TMA cannot describe the

@@ -52,6 +52,16 @@ def test_pairwise_backward(golden, name):
     close(df2, g["df2"], rtol=5e-5)
 
 
+@pytest.mark.parametrize("name", ["lookup_dcoords_l4_r4", "lookup_dcoords_l2_r1"])
+def test_lookup_coords_gradient(golden, name):
+    # the reference's autograd through coords/2**l, the normalisation and grid_sample's grid argument
+    g = golden(name)
+    L, r = int(g["levels"]), int(g["radius"])
+    pyr = O.corr_pyramid(g["f1"], g["f2"], L)
+    close(O.corr_lookup(pyr, g["coords"], r), g["out"])
+    close(O.corr_lookup_bwd_coords(pyr, g["coords"], g["dout"], r), g["dcoords"], rtol=5e-5)
+
+
 SAMPLER = ["sampler_p9", "sampler_flownetc", "sampler_stride2", "sampler_aniso", "sampler_dcv_s4", "sampler_dil16"]
 
 

@@ -34,7 +34,8 @@ for i in range(n_cases):
     E.set_pyramid_dtype(store)
     ref = O.corr_lookup(O.corr_pyramid(f1, f2, L), coords, r)
     t1, t2 = g(f1).requires_grad_(i % 3 == 0), g(f2).requires_grad_(i % 3 == 0)
-    out_t = E.MutliScalePairwise4DCorr(t1, t2, num_levels=L, corr_radius=r)(g(coords))
+    tc = g(coords).requires_grad_(i % 3 == 0)
+    out_t = E.MutliScalePairwise4DCorr(t1, t2, num_levels=L, corr_radius=r)(tc)
     rf, mr = rel(out_t.detach().cpu().numpy(), ref)
     ok = rf <= 1e-3 and mr <= 1e-3
     if i % 3 == 0:
@@ -43,7 +44,8 @@ for i in range(n_cases):
         dpyr = O.corr_lookup_bwd([(H >> l, W >> l) for l in range(L)], coords, dout, r)
         d1, d2 = O.corr_pyramid_bwd(f1, f2, dpyr)
         e1, e2 = rel(t1.grad.cpu().numpy(), d1), rel(t2.grad.cpu().numpy(), d2)
-        ok = ok and max(e1 + e2) <= 2e-3
+        ec = rel(tc.grad.cpu().numpy(), O.corr_lookup_bwd_coords(O.corr_pyramid(f1, f2, L), coords, dout, r))
+        ok = ok and max(e1 + e2 + ec) <= 2e-3
     if not ok:
         fails += 1
         print("FAIL pairwise", (B, C, H, W, L, r, store, scale), rf, mr)

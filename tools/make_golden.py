@@ -71,6 +71,20 @@ def pairwise_case(name, shape, levels, radius, seed, jitter, scale=1.0):
     save(name, **arrs)
 
 
+def lookup_dcoords_case(name, shape, levels, radius, seed, jitter):
+    """The lookup's gradient w.r.t. coords (RAFT detaches coords, but the reference's op produces it)."""
+    g = torch.Generator().manual_seed(seed)
+    b, c, h, w = shape
+    f1 = torch.randn(shape, generator=g)
+    f2 = torch.randn(shape, generator=g)
+    coords = (coords_grid(b, h, w) + (torch.rand(b, 2, h, w, generator=g) * 2 - 1) * jitter).requires_grad_(True)
+    dout = torch.randn(b, levels * (2 * radius + 1) ** 2, h, w, generator=g)
+    obj = SIMILARITY_REGISTRY.get("MutliScalePairwise4DCorr")(f1, f2, num_levels=levels, corr_radius=radius)
+    out = obj(coords)
+    (out * dout).sum().backward()
+    save(name, f1=f1, f2=f2, coords=coords, dout=dout, out=out, dcoords=coords.grad, levels=levels, radius=radius)
+
+
 def sampler_case(name, shape, seed, **kw):
     g = torch.Generator().manual_seed(seed)
     x1 = torch.randn(shape, generator=g).requires_grad_(True)
@@ -87,6 +101,8 @@ def main():
     pairwise_case("pairwise_l4_r4", (2, 32, 16, 21), 4, 4, seed=1, jitter=6.0)
     pairwise_case("pairwise_l3_r3", (1, 24, 10, 14), 3, 3, seed=2, jitter=3.0)
     pairwise_case("pairwise_scaled", (1, 64, 9, 12), 2, 2, seed=3, jitter=2.0, scale=30.0)
+    lookup_dcoords_case("lookup_dcoords_l4_r4", (2, 16, 16, 21), 4, 4, seed=4, jitter=7.0)
+    lookup_dcoords_case("lookup_dcoords_l2_r1", (1, 8, 9, 13), 2, 1, seed=5, jitter=12.0)
 
     # ---- local correlation (K4, K4b) ----
     sampler_case("sampler_p9", (2, 8, 13, 18), 11, patch_size=9)
