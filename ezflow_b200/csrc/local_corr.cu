@@ -341,6 +341,10 @@ bool local_corr_rt_supported(int H, int W, int BG, int Ph, int Pw, int sh, int s
 bool local_corr_rt_preferred(int BG, int C, int H, int W, bool tc_available);
 int local_corr_rt_launch(const float* in1, const float* in2, int BG, int G, int C, int H, int W, int P, float scale,
                          float slope, float* out, long long out_bstride, cudaStream_t st);
+bool local_corr_bwd_rt_supported(const float* in1, const float* in2, const float* dout, const float* din1, const float* din2, int B, int C,
+                                 int H, int W, int Ph, int Pw, int sh, int sw, int padh, int padw, int dph, int dpw, long long dout_bstride);
+int local_corr_bwd_rt_launch(const float* in1, const float* in2, const float* dout, int B, int C, int H, int W, int P, float scale,
+                             long long dout_bstride, float* din1, float* din2, cudaStream_t st);
 // local_corr_bwd_tc.cu
 bool local_corr_bwd_tc_supported(int C, int H, int W, int Ph, int Pw, int sh, int sw, int padh, int padw, int dph, int dpw);
 size_t local_corr_bwd_tc_workspace_bytes(int BG, int C, int H, int W);
@@ -460,6 +464,9 @@ static int local_corr_bwd_simt(const float* in1, const float* in2, const float* 
   P.scale = scale;
   P.dout_bstride = dout_batch_stride > 0 ? dout_batch_stride : (int64_t)Ph * Pw * P.oh * P.ow;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // PWC-Net's shape (odd window <= 9, stride 1, no dilation / padding): register-tiled kernels (local_corr_rt.cu)
+  if (local_corr_bwd_rt_supported(in1, in2, dout, din1, din2, B, C, H, W, Ph, Pw, sh, sw, padh, padw, dph, dpw, P.dout_bstride))
+    return local_corr_bwd_rt_launch(in1, in2, dout, B, C, H, W, Ph, scale, P.dout_bstride, din1, din2, st);
   const long long total = (long long)B * C * H * W;
   const int blocks = (int)std::min<long long>(cdiv64(total, 256), 148 * 32);
   // stride 1: tiled kernels (products out of shared memory); otherwise the gather kernels

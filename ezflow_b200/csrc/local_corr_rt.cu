@@ -260,6 +260,154 @@ static int launch(const Params& Q, cudaStream_t st) {
   return EZB_OK;
 }
 
+// ------------------------------------------------------------------------------------ adjoints (K4b), same regular case
+//   SECOND = false: din1[c,y,x] = scale * sum_{pi,pj} dout[pi,pj,y,x] * in2[c, y + pi - md, x + pj - md]
+//   SECOND = true : din2[c,y,x] = scale * sum_{pi,pj} dout[P-1-pi, P-1-pj, y + pi - md, x + pj - md] * in1[c, y + pi - md, x + pj - md]
+// (autograd of sampler.py:121-127; the second form is the scatter of din2 rewritten as a gather with the flipped displacement).
+// Both are "12-value window of the other operand x 9 displacement columns" products like the forward, with the contraction
+// over displacements instead of channels:
+//   block  : 32 x 8 gradient pixels x 16 channels, 128 threads; thread = 4 consecutive pixels x 8 channels (32 accumulators).
+//   staged : the other operand's 16-channel halo tile (16 x 40 per channel) once per block; per displacement row the P planes
+//            of dout for that row (8 x 40 with halo, double-buffered, one barrier per displacement row).
+//   per displacement row a thread loads its P dout quads (aligned LDS.128 for din1; for din2 the quad sits pj - md pixels off
+//   the thread's own, four scalar loads) and per channel the 12-value window (three LDS.128) -> 36 FMAs.
+// Vector path only (W % 4 == 0, 16-byte aligned tensors); everything else stays on local_corr_bwd_tiled_kernel.
+constexpr int BCB = 16, BCT = 8, BTH = 8;  // channels per block / per thread, tile rows
+constexpr int BNT = (TW / 4) * BTH * (BCB / BCT);
+
+struct BwdParams {
+  const float* other;  // in2 (din1) / in1 (din2)
+  const float* dout;
+  float* din;
+  int C, H, W;
+  float scale;
+  long long dout_bstride;
+};
+
+template <int P>
+struct BwdCfg {
+  static constexpr int MD = (P - 1) / 2, HALO_W = MDA + TW + 4, HALO_H = BTH + 2 * MD;
+  static constexpr int OTHER = BCB * HALO_H * HALO_W;  // floats
+  static constexpr int DROW = P * BTH * HALO_W;        // floats per displacement row
+  static constexpr size_t SMEM = (size_t)(OTHER + 2 * DROW) * sizeof(float);
+};
+
+template <int P, bool SECOND>
+__global__ void __launch_bounds__(BNT, 3) local_corr_bwd_rt_kernel(const BwdParams Q) {
+  using K = BwdCfg<P>;
+  constexpr int MD = K::MD, HALO_W = K::HALO_W, HALO_H = K::HALO_H, Q4 = HALO_W / 4;
+  extern __shared__ __align__(16) float sm_brt[];
+  float* so = sm_brt;              // [BCB][HALO_H][HALO_W]
+  float* sd = sm_brt + K::OTHER;   // [2][P][BTH][HALO_W]
+  const uint32_t so_a = (uint32_t)__cvta_generic_to_shared(so), sd_a = (uint32_t)__cvta_generic_to_shared(sd);
+  const int tid = threadIdx.x;
+  const int xtiles = (Q.W + TW - 1) / TW;
+  const int x0 = (blockIdx.x % xtiles) * TW, y0 = (blockIdx.x / xtiles) * BTH;
+  const int c0 = blockIdx.y * BCB, b = blockIdx.z;
+  const long long HW = (long long)Q.H * Q.W;
+  const float* other = Q.other + ((long long)b * Q.C + c0) * HW;
+  const float* dout = Q.dout + (long long)b * Q.dout_bstride;
+
+  // ---- the other operand's halo tile, all 16 channels (zero outside the image / beyond C)
+  for (int i = tid; i < HALO_H * Q4; i += BNT) {
+    const int hy = i / Q4, hq = i - hy * Q4;
+    const int y = y0 - MD + hy, x = x0 - MDA + 4 * hq;
+    const bool ok = y >= 0 && y < Q.H && x >= 0 && x < Q.W;
+    const float* src = other + (long long)y * Q.W + x;
+#pragma unroll
+    for (int c = 0; c < BCB; ++c) {
+      if (ok && c0 + c < Q.C)
+        cp_async_16(so_a + (uint32_t)((c * HALO_H + hy) * HALO_W + 4 * hq) * 4u, src + (long long)c * HW, 16u);
+      else
+        *reinterpret_cast<float4*>(so + (c * HALO_H + hy) * HALO_W + 4 * hq) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  // ---- dout planes of one displacement row: sd[buf][pj][r][t] = G[pi][pj][y0 + r + dy][x0 - 4 + t]
+  //      din1: G = dout, dy = 0 (only t in [4, 36) is read);  din2: G = dout with both displacements flipped, dy = pi - md
+  auto stage_d = [&](int buf, int pi) {
+    const int dy = SECOND ? pi - MD : 0;
+    const float* plane0 = dout + (long long)(SECOND ? (P - 1 - pi) * P + (P - 1) : pi * P) * HW;
+    constexpr int QB = SECOND ? 0 : 1, QN = SECOND ? Q4 : Q4 - 2;  // quads of a row that are read
+    for (int i = tid; i < P * BTH * QN; i += BNT) {
+      const int pj = i / (BTH * QN), rem = i - pj * (BTH * QN), r = rem / QN, hq = QB + rem - r * QN;
+      const int y = y0 + r + dy, x = x0 - MDA + 4 * hq;
+      const int off = ((buf * P + pj) * BTH + r) * HALO_W + 4 * hq;
+      if (y >= 0 && y < Q.H && x >= 0 && x < Q.W)
+        cp_async_16(sd_a + (uint32_t)off * 4u, plane0 + (SECOND ? -(long long)pj : (long long)pj) * HW + (long long)y * Q.W + x, 16u);
+      else
+        *reinterpret_cast<float4*>(sd + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage_d(0, 0);  // (the halo copies above belong to this first group)
+
+  const int cg = tid / ((TW / 4) * BTH), r64 = tid - cg * ((TW / 4) * BTH), qx = r64 & 7, ty = r64 >> 3;
+  float acc[BCT][4];
+#pragma unroll
+  for (int k = 0; k < BCT; ++k)
+#pragma unroll
+    for (int px = 0; px < 4; ++px) acc[k][px] = 0.f;
+
+  for (int pi = 0; pi < P; ++pi) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // row pi has landed; every thread is done with the buffer row pi + 1 goes into
+    if (pi + 1 < P) stage_d((pi + 1) & 1, pi + 1);
+    const float* dr = sd + (((pi & 1) * P) * BTH + ty) * HALO_W + 4 * qx;
+    float d[P][4];
+#pragma unroll
+    for (int pj = 0; pj < P; ++pj) {
+      const float* dp = dr + pj * (BTH * HALO_W);
+      if constexpr (!SECOND) {
+        const float4 v = *reinterpret_cast<const float4*>(dp + MDA);
+        d[pj][0] = v.x; d[pj][1] = v.y; d[pj][2] = v.z; d[pj][3] = v.w;
+      } else {
+#pragma unroll
+        for (int px = 0; px < 4; ++px) d[pj][px] = dp[MDA - MD + pj + px];
+      }
+    }
+    const float4* wrow = reinterpret_cast<const float4*>(so + ((cg * BCT) * HALO_H + ty + pi) * HALO_W + 4 * qx);
+#pragma unroll
+    for (int k = 0; k < BCT; ++k) {
+      const float4 v0 = wrow[k * (HALO_H * Q4)], v1 = wrow[k * (HALO_H * Q4) + 1], v2 = wrow[k * (HALO_H * Q4) + 2];
+      const float w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+      for (int pj = 0; pj < P; ++pj)
+#pragma unroll
+        for (int px = 0; px < 4; ++px) acc[k][px] = fmaf(d[pj][px], w[MDA - MD + pj + px], acc[k][px]);
+    }
+  }
+
+  const int y = y0 + ty, x = x0 + 4 * qx;
+  if (y >= Q.H || x >= Q.W) return;
+  float* dst = Q.din + ((long long)b * Q.C + c0 + cg * BCT) * HW + (long long)y * Q.W + x;
+#pragma unroll
+  for (int k = 0; k < BCT; ++k)
+    if (c0 + cg * BCT + k < Q.C)
+      *reinterpret_cast<float4*>(dst + (long long)k * HW) = make_float4(acc[k][0] * Q.scale, acc[k][1] * Q.scale, acc[k][2] * Q.scale, acc[k][3] * Q.scale);
+}
+
+template <int P>
+static int launch_bwd(const float* in1, const float* in2, const float* dout, int B, int C, int H, int W, float scale, long long dout_bstride,
+                      float* din1, float* din2, cudaStream_t st) {
+  using K = BwdCfg<P>;
+  BwdParams Q;
+  Q.dout = dout; Q.C = C; Q.H = H; Q.W = W; Q.scale = scale; Q.dout_bstride = dout_bstride;
+  const dim3 grid((unsigned)(cdiv(W, TW) * cdiv(H, BTH)), cdiv(C, BCB), B);
+  if (din1) {
+    Q.other = in2; Q.din = din1;
+    EZB_CUDA_OK(cudaFuncSetAttribute(local_corr_bwd_rt_kernel<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
+    local_corr_bwd_rt_kernel<P, false><<<grid, BNT, K::SMEM, st>>>(Q);
+    EZB_LAUNCH_OK();
+  }
+  if (din2) {
+    Q.other = in1; Q.din = din2;
+    EZB_CUDA_OK(cudaFuncSetAttribute(local_corr_bwd_rt_kernel<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
+    local_corr_bwd_rt_kernel<P, true><<<grid, BNT, K::SMEM, st>>>(Q);
+    EZB_LAUNCH_OK();
+  }
+  return EZB_OK;
+}
+
 }  // namespace k4rt
 
 bool local_corr_rt_supported(int H, int W, int BG, int Ph, int Pw, int sh, int sw, int padh, int padw, int dph, int dpw) {
@@ -306,6 +454,27 @@ int local_corr_rt_launch(const float* in1, const float* in2, int BG, int G, int 
   }
 #undef EZB_RT_CASE
   return fail(EZB_ERR_UNSUPPORTED, "register-tiled local correlation: patch size %d", P);
+}
+
+bool local_corr_bwd_rt_supported(const float* in1, const float* in2, const float* dout, const float* din1, const float* din2, int B, int C,
+                                 int H, int W, int Ph, int Pw, int sh, int sw, int padh, int padw, int dph, int dpw, long long dout_bstride) {
+  if (const char* e = getenv("EZB_LOCAL_CORR_BWD_RT"))
+    if (atoi(e) == 0) return false;
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(in1) | reinterpret_cast<uintptr_t>(in2) | reinterpret_cast<uintptr_t>(dout) |
+                         reinterpret_cast<uintptr_t>(din1) | reinterpret_cast<uintptr_t>(din2);
+  return Ph == Pw && (Ph == 3 || Ph == 5 || Ph == 7 || Ph == 9) && sh == 1 && sw == 1 && padh == 0 && padw == 0 && dph == 1 && dpw == 1 &&
+         W % 4 == 0 && (bits & 15) == 0 && dout_bstride % 4 == 0 && B <= 65535 && cdiv(C, k4rt::BCB) <= 65535;
+}
+
+int local_corr_bwd_rt_launch(const float* in1, const float* in2, const float* dout, int B, int C, int H, int W, int P, float scale,
+                             long long dout_bstride, float* din1, float* din2, cudaStream_t st) {
+  switch (P) {
+    case 9: return k4rt::launch_bwd<9>(in1, in2, dout, B, C, H, W, scale, dout_bstride, din1, din2, st);
+    case 7: return k4rt::launch_bwd<7>(in1, in2, dout, B, C, H, W, scale, dout_bstride, din1, din2, st);
+    case 5: return k4rt::launch_bwd<5>(in1, in2, dout, B, C, H, W, scale, dout_bstride, din1, din2, st);
+    case 3: return k4rt::launch_bwd<3>(in1, in2, dout, B, C, H, W, scale, dout_bstride, din1, din2, st);
+  }
+  return fail(EZB_ERR_UNSUPPORTED, "register-tiled local correlation adjoint: patch size %d", P);
 }
 
 }  // namespace ezb

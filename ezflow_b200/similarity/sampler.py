@@ -92,8 +92,8 @@ def bwd_tc_covers(B, C, H, W, patch, stride, padding, dpatch):
     """True when the tensor-core adjoint (csrc/local_corr_bwd_tc.cu) both handles the problem — the regular case; the library
     has the last word — and pays off: it has ~0.1 ms of fixed cost (three scale reductions, two operand conversions) plus ~11.5 ns
     per million gradient elements, against ~0.31 ms per 1e9 FMAs of the fp32 kernels (tools/micro/k4b_levels.py on B200:
-    FlowNetC 0.88 -> 0.17 ms, DCVNet's stride-1 dilations 0.16-0.24 -> 0.10-0.14 ms; PWC-Net's small / few-channel levels stay
-    on the fp32 kernels)."""
+    FlowNetC 0.88 -> 0.17 ms, DCVNet's stride-1 dilations 0.16-0.24 -> 0.10-0.14 ms; PWC-Net's levels stay on the fp32 kernels,
+    which for that shape are the register-tiled ones: finest level 0.25 -> 0.155 ms)."""
     d = dpatch[0]
     regular = (
         _LOCAL_CORR_MODE == "tc" and C <= TC_MAX_CHANNELS and patch[0] == patch[1] and patch[0] % 2 == 1 and patch[0] <= 25
@@ -101,7 +101,10 @@ def bwd_tc_covers(B, C, H, W, patch, stride, padding, dpatch):
         and (d == 1 or (-(-H // d) >= 8 and -(-W // d) >= 16))
     )
     elems = B * patch[0] * patch[1] * H * W  # gradient elements
-    return regular and elems * (0.31 * C - 11.5) > 65e6
+    # fp32 side: 0.31 ms per 1e9 FMAs for the tiled kernels, 0.10 where the register-tiled adjoints of csrc/local_corr_rt.cu
+    # apply (window <= 9, no dilation, W % 4 == 0: PWC-Net, DCVNet's dilation-1 volume)
+    fp32_cost = 0.10 if (patch[0] <= 9 and d == 1 and W % 4 == 0) else 0.31
+    return regular and elems * (fp32_cost * C - 11.5) > 65e6
 
 
 def local_corr_backward(in1, in2, dout, patch, stride, padding, dpatch, scale=1.0, need1=True, need2=True, dout_batch_stride=0):

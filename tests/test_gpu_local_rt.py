@@ -125,3 +125,58 @@ def test_register_tiled_gradients_flow(force_rt):
     d1, d2 = O.iter_spatial_correlation_sample_bwd(x1, x2, dout, patch_size=9)
     assert_close(t1.grad, d1, 5e-5, "dinput1")
     assert_close(t2.grad, d2, 5e-5, "dinput2")
+
+
+# (B, C, H, W, P): W % 4 == 0 (the register-tiled adjoints' vector path); ragged tiles, channel tails, every patch size
+BWD_SHAPES = [(2, 32, 16, 64, 9), (1, 13, 9, 36, 9), (1, 40, 11, 44, 9), (2, 17, 19, 48, 7), (2, 9, 7, 32, 5), (1, 6, 12, 20, 3), (1, 3, 1, 4, 9)]
+
+
+@pytest.mark.parametrize("shape", BWD_SHAPES)
+def test_register_tiled_adjoints_vs_oracle(shape):
+    """din1 / din2 through local_corr_bwd_rt_kernel (the 'exact' path for stride 1, no dilation, odd window <= 9) vs the oracle,
+    and bit-for-bit reproducible; the round-1 tiled kernels (EZB_LOCAL_CORR_BWD_RT=0) must agree to summation order."""
+    import ezflow_b200 as E
+    from oracle import similarity_oracle as O
+
+    B, C, H, W, P = shape
+    rng = np.random.default_rng(P * 1000 + C)
+    x1 = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    x2 = (rng.standard_normal((B, C, H, W)) * 2).astype(np.float32)
+    dout = rng.standard_normal((B, P, P, H, W)).astype(np.float32)
+    d1, d2 = O.iter_spatial_correlation_sample_bwd(x1, x2, dout, patch_size=P)
+    old_mode = E.get_local_corr_mode()
+    E.set_local_corr_mode("exact")
+    grads = {}
+    try:
+        for flag in ("1", "0"):
+            old = _setenv(EZB_LOCAL_CORR_BWD_RT=flag)
+            try:
+                t1, t2 = to_gpu(x1, True), to_gpu(x2, True)
+                E.IterSpatialCorrelationSampler(kernel_size=1, patch_size=P)(t1, t2).backward(to_gpu(dout))
+                grads[flag] = (t1.grad.clone(), t2.grad.clone())
+            finally:
+                _setenv(**old)
+    finally:
+        E.set_local_corr_mode(old_mode)
+    for flag, (g1, g2) in grads.items():
+        assert_close(g1, d1, 5e-5, f"dinput1 {shape} rt={flag}")
+        assert_close(g2, d2, 5e-5, f"dinput2 {shape} rt={flag}")
+
+
+def test_register_tiled_adjoints_only_one_gradient():
+    """Only input2 requires grad (the other launch is skipped)."""
+    import ezflow_b200 as E
+    from oracle import similarity_oracle as O
+
+    rng = np.random.default_rng(8)
+    x1 = rng.standard_normal((1, 20, 10, 24)).astype(np.float32)
+    x2 = rng.standard_normal((1, 20, 10, 24)).astype(np.float32)
+    dout = rng.standard_normal((1, 9, 9, 10, 24)).astype(np.float32)
+    old_mode = E.get_local_corr_mode()
+    E.set_local_corr_mode("exact")
+    try:
+        t2 = to_gpu(x2, True)
+        E.IterSpatialCorrelationSampler(kernel_size=1, patch_size=9)(to_gpu(x1), t2).backward(to_gpu(dout))
+    finally:
+        E.set_local_corr_mode(old_mode)
+    assert_close(t2.grad, O.iter_spatial_correlation_sample_bwd(x1, x2, dout, patch_size=9)[1], 5e-5, "dinput2 only")

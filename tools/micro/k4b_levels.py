@@ -37,8 +37,10 @@ for name, shape, kw in cases:
     x2 = torch.randn(shape, device=dev, requires_grad=True)
     m = E.IterSpatialCorrelationSampler(kernel_size=1, padding=0, **kw)
     res = {}
-    for mode in ("tc", "exact"):
-        E.set_local_corr_mode(mode)
+    for mode in ("tc", "exact", "exact_tiled"):
+        # 'exact_tiled': the round-1 fp32 tiled kernels (the register-tiled adjoints of local_corr_rt.cu switched off)
+        os.environ["EZB_LOCAL_CORR_BWD_RT"] = "0" if mode == "exact_tiled" else "1"
+        E.set_local_corr_mode("tc" if mode == "tc" else "exact")
         out = m(x1, x2)
         dout = torch.randn_like(out)
         with torch.no_grad():
@@ -49,4 +51,4 @@ for name, shape, kw in cases:
             m(x1, x2).backward(dout)
 
         res[mode] = (tf, timed(fb) - tf)
-    print(f"{name:30s} fwd tc {res['tc'][0]:.3f} exact {res['exact'][0]:.3f} | bwd tc {res['tc'][1]:.3f} exact {res['exact'][1]:.3f} ms")
+    print(f"{name:30s} fwd tc {res['tc'][0]:.3f} exact {res['exact'][0]:.3f} | bwd tc {res['tc'][1]:.3f} exact {res['exact'][1]:.3f} exact_tiled(r1) {res['exact_tiled'][1]:.3f} ms", flush=True)
