@@ -345,6 +345,10 @@ bool local_corr_bwd_rt_supported(const float* in1, const float* in2, const float
                                  int H, int W, int Ph, int Pw, int sh, int sw, int padh, int padw, int dph, int dpw, long long dout_bstride);
 int local_corr_bwd_rt_launch(const float* in1, const float* in2, const float* dout, int B, int C, int H, int W, int P, float scale,
                              long long dout_bstride, float* din1, float* din2, cudaStream_t st);
+bool local_corr_rt_strided_supported(const float* in1, const float* in2, const float* out, int BG, int C, int H, int W, int Ph, int Pw,
+                                     int sh, int sw, int padh, int padw, int dph, int dpw, long long out_bstride);
+int local_corr_rt_strided_launch(const float* in1, const float* in2, int BG, int G, int C, int H, int W, int P, int S, float scale, float slope,
+                                 float* out, long long out_bstride, cudaStream_t st);
 // local_corr_bwd_tc.cu
 bool local_corr_bwd_tc_supported(int C, int H, int W, int Ph, int Pw, int sh, int sw, int padh, int padw, int dph, int dpw);
 size_t local_corr_bwd_tc_workspace_bytes(int BG, int C, int H, int W);
@@ -380,6 +384,11 @@ extern "C" int ezb_local_corr_fwd(const float* in1, const float* in2, int B, int
   if (local_corr_rt_supported(H, W, B, Ph, Pw, sh, sw, padh, padw, dph, dpw) && local_corr_rt_preferred(B, C, H, W, tc_ok))
     return local_corr_rt_launch(in1, in2, B, 1, C, H, W, Ph, scale, slope, out,
                                 out_batch_stride > 0 ? out_batch_stride : (int64_t)Ph * Pw * H * W, static_cast<cudaStream_t>(stream));
+  {  // stride 2 / 4 (16 or fewer window products per input pixel): strided register-tiled fp32 kernel, bound by reading in2 once
+    const int64_t obs = out_batch_stride > 0 ? out_batch_stride : (int64_t)Ph * Pw * cdiv(H, sh) * cdiv(W, sw);
+    if (local_corr_rt_strided_supported(in1, in2, out, B, C, H, W, Ph, Pw, sh, sw, padh, padw, dph, dpw, obs))
+      return local_corr_rt_strided_launch(in1, in2, B, 1, C, H, W, Ph, sh, scale, slope, out, obs, static_cast<cudaStream_t>(stream));
+  }
   if (tc_ok) {
     const int oh = cdiv(H + 2 * padh, sh), ow = cdiv(W + 2 * padw, sw);
     return local_corr_tc_launch(in1, in2, nullptr, B, 1, C, H, W, Ph, Pw, sh, sw, padh, padw, 1, &dph, &dpw, scale, slope, out,
@@ -404,6 +413,11 @@ extern "C" int ezb_matryoshka_fwd(const float* x1, const float* x2, int B, int G
   EZB_REQUIRE(G > 0 && D > 0 && D <= k4::MAX_DIL, "bad group/dilation count G=%d D=%d (max %d dilations)", G, D, k4::MAX_DIL);
   if (int r = check_local_args(B, Cg, H, W, P_, P_, stride, stride, 0, 0, 1, 1)) return r;
   for (int d = 0; d < D; ++d) EZB_REQUIRE(dil[d] > 0, "dilation must be positive");
+  if (D == 1) {  // DCVNet's fine scale (stride-2 features sampled every 4 pixels, one dilation of 1): local_corr_rt.cu
+    const int64_t obs = out_batch_stride > 0 ? out_batch_stride : (int64_t)G * P_ * P_ * cdiv(H, stride) * cdiv(W, stride);
+    if (local_corr_rt_strided_supported(x1, x2, out, B * G, Cg, H, W, P_, P_, stride, stride, 0, 0, dil[0], dil[0], obs))
+      return local_corr_rt_strided_launch(x1, x2, B * G, G, Cg, H, W, P_, stride, 1.f, slope, out, obs, static_cast<cudaStream_t>(stream));
+  }
   if (workspace != nullptr && local_corr_tc_supported(Cg, stride, stride, D)) {
     const int oh = cdiv(H, stride), ow = cdiv(W, stride);
     return local_corr_tc_launch(x1, x2, nullptr, B * G, G, Cg, H, W, P_, P_, stride, stride, 0, 0, D, dil, dil, 1.f, slope, out,

@@ -260,6 +260,191 @@ static int launch(const Params& Q, cudaStream_t st) {
   return EZB_OK;
 }
 
+// ------------------------------------------------------------------------------------ strided forward (DCVNet's fine scale)
+// MatryoshkaDilatedCostVolumeList samples its stride-2 feature maps every 4 pixels (learnable_cost.py:420-434: stride =
+// 8 // feat_stride), one dilation of 1:  out[bg,pi,pj,y,x] = sum_c in1[bg,c,S*y,S*x] * in2[bg,c,S*y + pi - md, S*x + pj - md].
+// That is 81 * C FMAs per *sixteen* input pixels: the op is bound by reading in2 once (151 MB at BASELINE config 4), and the
+// tensor-core path's conversion pass alone moved more than that.  Same scheme as local_corr_rt_kernel with the window walking
+// S pixels per query:
+//   block  : 16 x 4 queries; thread = 4 consecutive queries x 1 displacement row x P displacement columns (4 * P accumulators).
+//   stage  : 4 channels of the (S*16 + 8) x (S*3 + P) in2 halo (16-byte cp.async, addresses decoded once per block) and of
+//            the 64 in1 query pixels (4-byte gathers), three-stage ring, one barrier per stage.
+//   per channel and thread: the in1 quad (one LDS.128), S*3 + P (+ alignment) in2 values as LDS.128, 4 * P FMAs.
+//   banks  : a thread's row segment starts 4*S floats after its neighbour's, so the eight lanes of a quarter-warp are dealt
+//            QXL query quads x PIL displacement rows and the halo row pitch is 3 (mod 8) 16-byte groups: S = 4 -> lanes
+//            (2 quads x 4 rows) hit groups {0,3,6,1} + {0,4}; S = 2 -> (4 quads x 2 rows) hit {0,2,4,6} + {0,3}: conflict-free.
+//            Displacement rows are padded to a multiple of PIL; the padding threads only stage.
+constexpr int SQW = 16, SQH = 4, SCC = 4;
+
+template <int P, int S>
+struct SCfg {
+  static constexpr int MD = (P - 1) / 2;
+  static constexpr int QXL = S == 4 ? 2 : 4;                    // query quads per quarter-warp
+  static constexpr int PIL = 8 / QXL;                           // displacement rows per quarter-warp
+  static constexpr int PROWS = ((P + PIL - 1) / PIL) * PIL;
+  static constexpr int NQ = (S * SQW + 8) / 4;                  // 16-byte chunks fetched per halo row: S*x0 - 4 .. S*x0 + S*16 + 3
+  static constexpr int HALO_W = S == 4 ? 76 : 44;               // row pitch in floats (19 / 11 groups = 3 mod 8)
+  static constexpr int HALO_H = S * (SQH - 1) + P;
+  static constexpr int NV = ((MDA - MD) + S * 3 + P + 3) & ~3;  // in2 values a thread reads per row
+  static constexpr int NT = (SQW / 4) * SQH * PROWS;
+  static constexpr int N2PC = HALO_H * NQ;                      // chunks of one channel's halo
+  static constexpr int J2 = (N2PC + NT - 1) / NT;
+  static constexpr int IN2_STAGE = SCC * HALO_H * HALO_W, IN1_STAGE = SCC * SQH * SQW, STAGE = IN2_STAGE + IN1_STAGE;
+  static constexpr int NSTAGE = 3;
+  static constexpr size_t SMEM = (size_t)NSTAGE * STAGE * sizeof(float);
+  static_assert((S == 2 || S == 4) && S * 12 + NV <= HALO_W && 4 * NQ <= HALO_W && MD <= MDA && (HALO_W / 4) % 8 == 3, "geometry");
+};
+
+struct SParams {
+  const float* in1;
+  const float* in2;
+  float* out;
+  int BG, G, C, H, W, oh, ow;
+  float scale, slope;
+  long long out_bstride;
+};
+
+template <int P, int S>
+__global__ void __launch_bounds__(SCfg<P, S>::NT, 2) local_corr_rt_strided_kernel(const SParams Q) {
+  using K = SCfg<P, S>;
+  constexpr int MD = K::MD, HALO_W = K::HALO_W, HALO_H = K::HALO_H, NT = K::NT, NQ = K::NQ, NV = K::NV;
+  extern __shared__ __align__(16) float sm_srt[];
+  const uint32_t sm_base = (uint32_t)__cvta_generic_to_shared(sm_srt);
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * SQW, y0 = blockIdx.y * SQH, bg = blockIdx.z;  // first query of the tile
+  const long long HW = (long long)Q.H * Q.W;
+  const float* in1 = Q.in1 + (long long)bg * Q.C * HW;
+  const float* in2 = Q.in2 + (long long)bg * Q.C * HW;
+
+  // the halo chunks and in1 pixels this thread copies in every stage
+  int goff2[K::J2], soff2[K::J2];
+  unsigned ok2 = 0, in2range = 0;
+#pragma unroll
+  for (int j = 0; j < K::J2; ++j) {
+    const int ch = tid + j * NT, hy = ch / NQ, hq = ch - hy * NQ;
+    const int y = S * y0 - MD + hy, x = S * x0 - MDA + 4 * hq;
+    goff2[j] = y * Q.W + x;
+    soff2[j] = hy * HALO_W + 4 * hq;
+    if (ch < K::N2PC) {
+      in2range |= 1u << j;
+      if (y >= 0 && y < Q.H && x >= 0 && x < Q.W) ok2 |= 1u << j;
+    }
+  }
+  constexpr int J1 = (K::IN1_STAGE + NT - 1) / NT;
+  int goff1[J1];
+  unsigned ok1 = 0, in1range = 0;
+#pragma unroll
+  for (int j = 0; j < J1; ++j) {
+    const int i = tid + j * NT, cc = i / (SQH * SQW), rem = i - cc * (SQH * SQW), qy = rem / SQW, qxx = rem - qy * SQW;
+    const int y = S * (y0 + qy), x = S * (x0 + qxx);
+    goff1[j] = y * Q.W + x;  // plus (c0 + cc) * HW at staging time
+    if (i < K::IN1_STAGE) {
+      in1range |= 1u << j;
+      if (y < Q.H && x < Q.W) ok1 |= 1u << j;
+    }
+  }
+
+  auto stage = [&](int buf, int c0) {
+    float* s2 = sm_srt + buf * K::STAGE;
+    float* s1 = s2 + K::IN2_STAGE;
+    const uint32_t a2 = sm_base + (uint32_t)(buf * K::STAGE) * 4u, a1 = a2 + (uint32_t)K::IN2_STAGE * 4u;
+    const float* g2 = in2 + (long long)c0 * HW;
+#pragma unroll
+    for (int j = 0; j < K::J2; ++j) {
+      if (!((in2range >> j) & 1u)) break;
+      const bool ok = (ok2 >> j) & 1u;
+#pragma unroll
+      for (int cc = 0; cc < SCC; ++cc) {
+        if (ok && c0 + cc < Q.C)
+          cp_async_16(a2 + (uint32_t)(cc * HALO_H * HALO_W + soff2[j]) * 4u, g2 + (long long)cc * HW + goff2[j], 16u);
+        else
+          *reinterpret_cast<float4*>(s2 + cc * HALO_H * HALO_W + soff2[j]) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < J1; ++j) {
+      if (!((in1range >> j) & 1u)) break;
+      const int i = tid + j * NT, cc = i / (SQH * SQW);
+      if (((ok1 >> j) & 1u) && c0 + cc < Q.C)
+        cp_async_4(a1 + (uint32_t)i * 4u, in1 + (long long)(c0 + cc) * HW + goff1[j], 4u);
+      else
+        s1[i] = 0.f;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  // thread geometry: lane bits (low to high) = displacement row within its group, query quad within its group
+  const int lane8 = tid & 7, upper = tid >> 3;
+  const int pi_lo = lane8 % K::PIL, qx_lo = lane8 / K::PIL;
+  const int qx_hi = upper % (4 / K::QXL), t2 = upper / (4 / K::QXL), ty = t2 % SQH, pi_hi = t2 / SQH;
+  const int pi = pi_hi * K::PIL + pi_lo, qx = qx_hi * K::QXL + qx_lo;
+  const bool active = pi < P;
+  float acc[P][4];
+#pragma unroll
+  for (int pj = 0; pj < P; ++pj)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[pj][q] = 0.f;
+
+  const int nk = (Q.C + SCC - 1) / SCC;
+  stage(0, 0);
+  if (nk > 1) stage(1, SCC);
+  for (int k = 0; k < nk; ++k) {
+    if (k + 1 < nk) {
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    if (k + 2 < nk) stage((k + 2) % K::NSTAGE, (k + 2) * SCC);
+    if (!active) continue;
+    const float* s2 = sm_srt + (k % K::NSTAGE) * K::STAGE;
+    const float* s1 = s2 + K::IN2_STAGE;
+#pragma unroll
+    for (int cc = 0; cc < SCC; ++cc) {
+      const float4 a = *reinterpret_cast<const float4*>(s1 + (cc * SQH + ty) * SQW + 4 * qx);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float4* row = reinterpret_cast<const float4*>(s2 + (cc * HALO_H + S * ty + pi) * HALO_W + S * 4 * qx);
+      float v[NV];
+#pragma unroll
+      for (int j = 0; j < NV / 4; ++j) {
+        const float4 t = row[j];
+        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+      }
+#pragma unroll
+      for (int pj = 0; pj < P; ++pj)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[pj][q] = fmaf(av[q], v[MDA - MD + pj + S * q], acc[pj][q]);
+    }
+  }
+
+  const int y = y0 + ty, x = x0 + 4 * qx;
+  if (!active || y >= Q.oh || x >= Q.ow) return;
+  const long long ohw = (long long)Q.oh * Q.ow;
+  const int b = bg / Q.G, g = bg - b * Q.G;
+  float* dst = Q.out + (long long)b * Q.out_bstride + ((long long)g * P * P + (long long)pi * P) * ohw + (long long)y * Q.ow + x;
+  const bool plain = Q.slope == 1.f;
+#pragma unroll
+  for (int pj = 0; pj < P; ++pj, dst += ohw) {
+    float o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float t = acc[pj][q] * Q.scale;
+      o[q] = (plain || t >= 0.f) ? t : t * Q.slope;
+    }
+    __stcs(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));  // ow % 4 == 0: the quad is inside or outside
+  }
+}
+
+template <int P, int S>
+static int launch_strided(const SParams& Q, cudaStream_t st) {
+  using K = SCfg<P, S>;
+  auto kern = local_corr_rt_strided_kernel<P, S>;
+  EZB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM));
+  kern<<<dim3(cdiv(Q.ow, SQW), cdiv(Q.oh, SQH), Q.BG), K::NT, K::SMEM, st>>>(Q);
+  EZB_LAUNCH_OK();
+  return EZB_OK;
+}
+
 // ------------------------------------------------------------------------------------ adjoints (K4b), same regular case
 //   SECOND = false: din1[c,y,x] = scale * sum_{pi,pj} dout[pi,pj,y,x] * in2[c, y + pi - md, x + pj - md]
 //   SECOND = true : din2[c,y,x] = scale * sum_{pi,pj} dout[P-1-pi, P-1-pj, y + pi - md, x + pj - md] * in1[c, y + pi - md, x + pj - md]
@@ -475,6 +660,36 @@ int local_corr_bwd_rt_launch(const float* in1, const float* in2, const float* do
     case 3: return k4rt::launch_bwd<3>(in1, in2, dout, B, C, H, W, scale, dout_bstride, din1, din2, st);
   }
   return fail(EZB_ERR_UNSUPPORTED, "register-tiled local correlation adjoint: patch size %d", P);
+}
+
+// Strided forward: one dilation of 1, stride 2 or 4 in both directions, no padding, square window 9 (DCVNet) .. 3.
+bool local_corr_rt_strided_supported(const float* in1, const float* in2, const float* out, int BG, int C, int H, int W, int Ph, int Pw,
+                                     int sh, int sw, int padh, int padw, int dph, int dpw, long long out_bstride) {
+  if (const char* e = getenv("EZB_LOCAL_CORR_RT"))
+    if (atoi(e) == 0) return false;
+  const int ow = cdiv(W, sw);
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(in1) | reinterpret_cast<uintptr_t>(in2) | reinterpret_cast<uintptr_t>(out);
+  return Ph == Pw && (Ph == 9 || Ph == 7 || Ph == 5 || Ph == 3) && sh == sw && (sh == 2 || sh == 4) && padh == 0 && padw == 0 && dph == 1 && dpw == 1 &&
+         W % 4 == 0 && ow % 4 == 0 && (bits & 15) == 0 && out_bstride % 4 == 0 && BG <= 65535 && cdiv(cdiv(H, sh), k4rt::SQH) <= 65535 &&
+         (sh == 4 || C <= 128);
+}
+
+int local_corr_rt_strided_launch(const float* in1, const float* in2, int BG, int G, int C, int H, int W, int P, int S, float scale, float slope,
+                                 float* out, long long out_bstride, cudaStream_t st) {
+  k4rt::SParams Q;
+  Q.in1 = in1; Q.in2 = in2; Q.out = out;
+  Q.BG = BG; Q.G = G; Q.C = C; Q.H = H; Q.W = W; Q.oh = cdiv(H, S); Q.ow = cdiv(W, S);
+  Q.scale = scale; Q.slope = slope; Q.out_bstride = out_bstride;
+#define EZB_RTS_CASE(PP)                                                                              \
+  case PP: return S == 4 ? k4rt::launch_strided<PP, 4>(Q, st) : k4rt::launch_strided<PP, 2>(Q, st);
+  switch (P) {
+    EZB_RTS_CASE(9)
+    EZB_RTS_CASE(7)
+    EZB_RTS_CASE(5)
+    EZB_RTS_CASE(3)
+  }
+#undef EZB_RTS_CASE
+  return fail(EZB_ERR_UNSUPPORTED, "strided register-tiled local correlation: patch size %d", P);
 }
 
 }  // namespace ezb

@@ -180,3 +180,59 @@ def test_register_tiled_adjoints_only_one_gradient():
     finally:
         E.set_local_corr_mode(old_mode)
     assert_close(t2.grad, O.iter_spatial_correlation_sample_bwd(x1, x2, dout, patch_size=9)[1], 5e-5, "dinput2 only")
+
+
+# (B, C, H, W, P, S): stride 2 / 4, W % 4 == 0 and ceil(W / S) % 4 == 0 (the strided kernel's vector path); ragged tiles in both
+# directions, channel counts off the 4-channel stage, maps whose last query row / column is not a multiple of the stride
+STRIDED_SHAPES = [
+    (2, 16, 32, 64, 9, 4), (1, 13, 19, 48, 9, 4), (1, 5, 70, 144, 9, 4), (2, 7, 9, 16, 9, 4), (1, 130, 16, 32, 9, 4),
+    (2, 12, 18, 40, 9, 2), (1, 9, 33, 72, 9, 2), (1, 6, 21, 32, 7, 4), (1, 10, 14, 24, 5, 2), (2, 4, 12, 16, 3, 4),
+    (1, 8, 17, 62 * 4, 9, 4),
+]
+
+
+@pytest.mark.parametrize("shape", STRIDED_SHAPES)
+def test_strided_register_tiled_forward_vs_oracle(shape, mode):
+    """local_corr_rt_strided_kernel (DCVNet's fine scale: stride-2 features sampled every 4 pixels, learnable_cost.py:420-434)
+    through the sampler class, in both modes (the kernel is exact fp32), and switched off (EZB_LOCAL_CORR_RT=0: the generic
+    path) on the same inputs."""
+    import ezflow_b200 as E
+    from oracle import similarity_oracle as O
+
+    B, C, H, W, P, S = shape
+    rng = np.random.default_rng(hash(shape) % (1 << 31))
+    x1 = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    x2 = (rng.standard_normal((B, C, H, W)) * 2).astype(np.float32)
+    ref = O.iter_spatial_correlation_sample(x1, x2, patch_size=P, stride=S)
+    m = E.IterSpatialCorrelationSampler(kernel_size=1, patch_size=P, stride=S)
+    out = m(to_gpu(x1), to_gpu(x2))
+    assert tuple(out.shape) == ref.shape and out.is_contiguous()
+    covered = W % 4 == 0 and -(-W // S) % 4 == 0  # otherwise the generic path runs (fp16 operands in 'tc' mode)
+    assert_close(out, ref, 2e-5 if covered or mode == "exact" else 1e-3, f"strided register-tiled {shape} ({mode})")
+    old = _setenv(EZB_LOCAL_CORR_RT="0")
+    try:
+        other = m(to_gpu(x1), to_gpu(x2))
+    finally:
+        _setenv(**old)
+    assert_close(other, ref, 1e-3 if mode == "tc" else 2e-5, f"generic path {shape} ({mode})")
+
+
+@pytest.mark.parametrize("use_relu", [False, True])
+def test_strided_register_tiled_in_matryoshka_list(use_relu):
+    """The DCVNet cost-volume list (fine scale at stride 4 -> strided kernel, coarse scale -> band GEMM) into one concatenated
+    volume, groups > 1 and the fused LeakyReLU included."""
+    import ezflow_b200 as E
+    from oracle import similarity_oracle as O
+
+    rng = np.random.default_rng(21)
+    x1 = [rng.standard_normal((2, 8, 32, 64)).astype(np.float32), rng.standard_normal((2, 16, 8, 16)).astype(np.float32)]
+    x2 = [rng.standard_normal((2, 8, 32, 64)).astype(np.float32), rng.standard_normal((2, 16, 8, 16)).astype(np.float32)]
+    ref = O.matryoshka_cost_volume_list(x1, x2, num_groups=2, max_displacement=4, encoder_output_strides=(2, 8),
+                                        dilations=((1,), (1, 2, 3)), normalize_feat_l2=False, use_relu=use_relu)
+    m = E.MatryoshkaDilatedCostVolumeList(num_groups=2, max_displacement=4, encoder_output_strides=[2, 8], dilations=[[1], [1, 2, 3]],
+                                          normalize_feat_l2=False, use_relu=use_relu).to(dev())
+    out = m([to_gpu(a) for a in x1], [to_gpu(a) for a in x2])
+    assert tuple(out.shape) == ref.shape
+    assert_close(out, ref, 1e-3, f"matryoshka list use_relu={use_relu}")
+    fine = out[:, :2]  # the stride-4 scale's groups: exact fp32
+    assert_close(fine, ref[:, :2], 2e-5, "fine scale (strided register-tiled kernel)")
