@@ -99,6 +99,8 @@ struct Params {
   int Hf, Wf;        // full-resolution input size (lattice mode)
   int out_h, out_w;  // full output plane
   int dph[MAX_DIL], dpw[MAX_DIL];
+  int mh[MAX_DIL], mw[MAX_DIL];             // dph * (Ph - 1) / 2, dpw * (Pw - 1) / 2
+  float inv_dph[MAX_DIL], inv_dpw[MAX_DIL];  // 1 / dph, 1 / dpw (round to nearest)
   float slope;
   const float* qscale;  // [BG * lat^2][oh * ow] 2^e of every query pixel: its fp16 operand row was scaled by 2^-e
   const float* tscale;  // [BG][Hf * Wf]         2^e of every in2 pixel
@@ -228,6 +230,15 @@ __global__ void __launch_bounds__(CONV_THREADS) convert_pixels_kmajor_kernel(con
 // integer, far more than the rounding error of the float product, so the floor is exact (|a| < 2^15)
 __device__ __forceinline__ int floor_div(int a, float inv_b) { return __float2int_rd(((float)a + 0.5f) * inv_b); }
 __device__ __forceinline__ int ceil_div(int a, float inv_b) { return -floor_div(-a, inv_b); }
+
+// bit nb set: a row of nb window columns wastes fewer slots in chunks of 3 than in chunks of 4
+constexpr unsigned ch3_mask() {
+  unsigned m = 0;
+  for (int nb = 1; nb < 32; ++nb)
+    if ((nb + 2) / 3 * 3 < (nb + 3) / 4 * 4) m |= 1u << nb;
+  return m;
+}
+constexpr unsigned kCh3Mask = ch3_mask();
 
 template <int TTW_, int TTH_>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -433,6 +444,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         }
       }
 
+      // general case: this lane's undisplaced target and the query tile's undisplaced box (CTA-uniform), once per item
+      const int yq = oy * P.sh - P.padh, xq = ox * P.sw - P.padw;
+      const int qbox_y0 = qy0 * P.sh - P.padh, qbox_y1 = (qy0 + QTH - 1) * P.sh - P.padh;
+      const int qbox_x0 = qx0 * P.sw - P.padw, qbox_x1 = (qx0 + QTW - 1) * P.sw - P.padw;
+
       int tyi = it.ntiles > 0 ? it.tt_begin / it.ntx : 0, txi = it.tt_begin - tyi * it.ntx;
       for (int tt = 0; tt < it.ntiles; ++tt, ++tcount) {
         const int ty0 = it.y_lo + tyi * TTH, tx0 = it.x_lo + txi * TTW;
@@ -536,23 +552,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           else rows(std::false_type{});
         } else
         for (int d = 0; d < P.D; ++d) {
-          const int dph = P.dph[d], dpw = P.dpw[d];
-          if (P.D > 1) {  // CTA-uniform early out: this dilation's box around the query tile does not reach the target tile
-            const int mh = dph * (P.Ph - 1) / 2, mw = dpw * (P.Pw - 1) / 2;
-            if (ty1 < qy0 * P.sh - P.padh - mh || ty0 > (qy0 + QTH - 1) * P.sh - P.padh + mh ||
-                tx1 < qx0 * P.sw - P.padw - mw || tx0 > (qx0 + QTW - 1) * P.sw - P.padw + mw)
-              continue;
-          }
-          const int y2_0 = oy * P.sh - P.padh - dph * (P.Ph - 1) / 2, x2_0 = ox * P.sw - P.padw - dpw * (P.Pw - 1) / 2;
-          // this lane's displacement ranges whose target lies in the in-image part of the tile
-          const float inv_dph = __frcp_rn((float)dph), inv_dpw = __frcp_rn((float)dpw);
+          const int dph = P.dph[d], dpw = P.dpw[d], mh = P.mh[d], mw = P.mw[d];
+          // CTA-uniform early out: this dilation's box around the query tile does not reach the target tile
+          if (P.D > 1 && (ty1 < qbox_y0 - mh || ty0 > qbox_y1 + mh || tx1 < qbox_x0 - mw || tx0 > qbox_x1 + mw)) continue;
+          const int y2_0 = yq - mh, x2_0 = xq - mw;
+          // this lane's displacement ranges whose target lies in the in-image part of the tile (the reciprocals are launch constants)
+          const float inv_dph = P.inv_dph[d], inv_dpw = P.inv_dpw[d];
           int a_lo = max(0, ceil_div(ty0 - y2_0, inv_dph)), a_hi = min(P.Ph - 1, floor_div(ty1 - y2_0, inv_dph));
-          int b_lo = max(0, ceil_div(tx0 - x2_0, inv_dpw)), b_hi = min(P.Pw - 1, floor_div(tx1 - x2_0, inv_dpw));
-          if (!q_ok || a_lo > a_hi || b_lo > b_hi) { a_lo = b_lo = INT_MAX; a_hi = b_hi = INT_MIN; }
+          if (!q_ok || a_lo > a_hi) { a_lo = INT_MAX; a_hi = INT_MIN; }
           // all lanes walk the union so that a store instruction covers one (pi, pj): contiguous output pixels
           const int ua_lo = __reduce_min_sync(0xffffffffu, a_lo), ua_hi = __reduce_max_sync(0xffffffffu, a_hi);
+          if (ua_lo > ua_hi) continue;  // no lattice row of this dilation in the tile (half of the tiles at dilation 16)
+          int b_lo = max(0, ceil_div(tx0 - x2_0, inv_dpw)), b_hi = min(P.Pw - 1, floor_div(tx1 - x2_0, inv_dpw));
+          if (a_lo > a_hi || b_lo > b_hi) { a_lo = b_lo = INT_MAX; a_hi = b_hi = INT_MIN; }
           const int ub_lo = __reduce_min_sync(0xffffffffu, b_lo), ub_hi = __reduce_max_sync(0xffffffffu, b_hi);
-          if (ua_lo > ua_hi) continue;
+          if (ub_lo > ub_hi) continue;
           const unsigned o_d = (unsigned)((d * P.G + g) * P.Ph * P.Pw) * uplane;
           // work items = (pi, chunk of CH pj), dealt round-robin to the warps of the quadrant.  CH (3 or 4) is whichever
           // wastes fewer slots on this row width (a 9- or 21-wide window splits into chunks of 3 without remainder);
@@ -587,8 +601,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
               }
             }
           };
+          // chunks of 3 where ceil(nb / 3) * 3 < ceil(nb / 4) * 4 (nb = 1, 2, 3, 6, 9 for nb <= 31; wider rows: chunks of 4)
           const int nb = ub_hi - ub_lo + 1;
-          const bool ch3 = (nb + 2) / 3 * 3 < (nb + 3) / 4 * 4, act = P.slope != 1.f;
+          const bool ch3 = nb < 32 && ((kCh3Mask >> nb) & 1u), act = P.slope != 1.f;
           if (ch3) {
             if (act) extract(std::integral_constant<int, 3>{}, std::true_type{});
             else extract(std::integral_constant<int, 3>{}, std::false_type{});
@@ -722,7 +737,11 @@ int local_corr_tc_launch(const float* in1, const float* in2, const float* flow2,
   P.oh = oh; P.ow = ow;
   P.Ph = Ph; P.Pw = Pw; P.sh = sh; P.sw = sw; P.padh = padh; P.padw = padw;
   P.D = D; P.KB = Cp / BK;
-  for (int d = 0; d < D; ++d) { P.dph[d] = dph_u[d]; P.dpw[d] = dpw_u[d]; }
+  for (int d = 0; d < D; ++d) {
+    P.dph[d] = dph_u[d]; P.dpw[d] = dpw_u[d];
+    P.mh[d] = dph_u[d] * (Ph - 1) / 2; P.mw[d] = dpw_u[d] * (Pw - 1) / 2;
+    P.inv_dph[d] = 1.f / (float)dph_u[d]; P.inv_dpw[d] = 1.f / (float)dpw_u[d];
+  }
   P.regular = (D == 1 && dph_u[0] == 1 && dpw_u[0] == 1 && sh == 1 && sw == 1 && padh == 0 && padw == 0 && TTW != 16 &&
                getenv("EZB_LOCAL_CORR_GENERIC_EXTRACT") == nullptr) ? (getenv("EZB_LOCAL_CORR_QUADSYNC") ? 2 : 1) : 0;
   P.lat = lat; P.BG = BG; P.Hf = H; P.Wf = W; P.out_h = out_h; P.out_w = out_w;
