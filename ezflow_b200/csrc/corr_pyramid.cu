@@ -231,6 +231,154 @@ __global__ void __launch_bounds__(256) pack_record_operand_kernel(const PackPara
   for (int row = warp; row < PYR_REC; row += 8) dst[(long long)row * P.Cp] = __float2half_rn(tile[lane][row]);
 }
 
+// Pool + pack in ONE pass over f2 (round 2; replaces L-1 pool2x2 launches and pack_record_operand for the forward build):
+// block = (16 x 16 level-0 pixels of one pair, 64 channels), 512 threads.  The region is loaded once (16-byte loads, 8 in flight per
+// thread) and transposed into shared memory [pixel][channel]; level 1 is pooled in registers on the way, levels 2..3 from
+// shared memory, with the exact expression of pool2x2_kernel (floor pooling: a valid level-l pixel always has its four sources, invalid ones are
+// zero), so the region yields 256 + 64 + 16 + 4 operand rows; each row leaves as 128 contiguous bytes (64 channels fp16)
+// of the (B, n_recs, 256, Cp) operand.  f2 is read once (pool + pack read it 1.3 + 1.3 times and wrote the pooled levels),
+// and the row pieces are full 128-byte lines instead of 64-byte ones.  The region grid is extended so that every pixel
+// of every existing subtile of every level is written (zeros outside a level); the blocks of region 0 also zero the
+// padding subtiles at the end of the sequence.
+constexpr int PP_R = 16, PP_CH = 64, PP_PITCH = PP_CH + 4, PP_ROWS = 256 + 64 + 16 + 4, PP_NT = 512;
+constexpr size_t PP_SMEM = (size_t)PP_ROWS * PP_PITCH * sizeof(float);
+struct PoolPackParams {
+  const float* f2;  // (B, C, H, W)
+  int H, W, C, Cp, L, n_recs, epl, rx, ry;
+  int h[PYR_MAX_LEVELS], w[PYR_MAX_LEVELS], sw[PYR_MAX_LEVELS], nsy[PYR_MAX_LEVELS], sub_base[PYR_MAX_LEVELS + 1];
+  const float* bscale;
+  __half* bp;
+};
+template <bool VEC>
+__global__ void __launch_bounds__(PP_NT, 2) pool_pack_kernel(const PoolPackParams P) {
+  extern __shared__ __align__(16) float pp[];  // [PP_ROWS][PP_PITCH]
+  __shared__ int rowoff[PP_ROWS];
+  const int tid = threadIdx.x;
+  const int ry = blockIdx.x / P.rx, rx = blockIdx.x - ry * P.rx, c0 = blockIdx.y * PP_CH, b = blockIdx.z;
+  const int y0 = ry * PP_R, x0 = rx * PP_R;
+  const long long HW = (long long)P.H * P.W;
+  const float* src = P.f2 + ((long long)b * P.C + c0) * HW;
+
+  // ---- level 0 + level 1: thread = (4 consecutive channels, 2 rows, pixel quad): 8 loads in flight; the 4 channels of a pixel
+  //      leave as ONE 16-byte shared-memory store (a quarter-warp = 8 channel groups of one pixel: conflict-free), and the
+  //      thread pools its 2 x 4 pixels into two level-1 pixels in registers (same expression as pool2x2_kernel)
+  float4 v[2][4];
+  {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int cg = (lane & 7) + 8 * (warp & 1), xq = lane >> 3, rp = warp >> 1;
+    const int x = x0 + 4 * xq;
+    const float* g0 = src + (long long)(4 * cg) * HW + (long long)(y0 + 2 * rp) * P.W + x;
+    const int nch = min(4, P.C - c0 - 4 * cg);  // channels of this group inside C (the rest are zero)
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v[rr][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < nch && y0 + 2 * rp + rr < P.H) {
+          const float* g = g0 + (long long)k * HW + rr * P.W;
+          if constexpr (VEC) {
+            if (x < P.W) v[rr][k] = __ldg(reinterpret_cast<const float4*>(g));
+          } else {
+            if (x < P.W) v[rr][k].x = __ldg(g);
+            if (x + 1 < P.W) v[rr][k].y = __ldg(g + 1);
+            if (x + 2 < P.W) v[rr][k].z = __ldg(g + 2);
+            if (x + 3 < P.W) v[rr][k].w = __ldg(g + 3);
+          }
+        }
+      }
+  }
+  // ---- while the loads are in flight: the operand row every one of the region's pixels goes to (element offset inside the
+  //      pair's operand, -1: no such subtile on the extended region grid), computed once per row instead of once per lane
+  if (tid < PP_ROWS) {
+    const int r = tid;
+    int l = 0, base = 0, nsh = 4;  // the region holds (1 << nsh)^2 pixels of level l
+    if (r >= 336) { l = 3; base = 336; nsh = 1; } else if (r >= 320) { l = 2; base = 320; nsh = 2; } else if (r >= 256) { l = 1; base = 256; nsh = 3; }
+    const int p = r - base, py = p >> nsh, px = p & ((1 << nsh) - 1);
+    const int y = (y0 >> l) + py, x = (x0 >> l) + px;
+    const int sy = y / PYR_SY, sx = x / PYR_SX;
+    int off = -1;
+    if (l < P.L && sy < P.nsy[l] && sx < P.sw[l]) {
+      const int epl_mask = P.epl - 1, e8_shift = P.epl == 64 ? 3 : 2;  // epl = 64 (fp16 pyramid) or 32 (fp32): shifts, no divisions
+      const int sidx = P.sub_base[l] + sy * P.sw[l] + sx;
+      const int n = (sidx % PYR_SUBS_PER_TILE) * PYR_SUB + (y % PYR_SY) * PYR_SX + x % PYR_SX, m = n & epl_mask, t = m >> 1;
+      const int col = n - m + (t & ((1 << e8_shift) - 1)) * 8 + (t >> e8_shift) * 2 + (m & 1);  // inverse of pyr_line_element_of_column
+      off = ((sidx / PYR_SUBS_PER_TILE) * PYR_REC + col) * P.Cp;
+    }
+    rowoff[r] = off;
+  }
+  {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int cg = (lane & 7) + 8 * (warp & 1), xq = lane >> 3, rp = warp >> 1;
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      float* d = pp + ((2 * rp + rr) * PP_R + 4 * xq) * PP_PITCH + 4 * cg;
+      *reinterpret_cast<float4*>(d) = make_float4(v[rr][0].x, v[rr][1].x, v[rr][2].x, v[rr][3].x);
+      *reinterpret_cast<float4*>(d + PP_PITCH) = make_float4(v[rr][0].y, v[rr][1].y, v[rr][2].y, v[rr][3].y);
+      *reinterpret_cast<float4*>(d + 2 * PP_PITCH) = make_float4(v[rr][0].z, v[rr][1].z, v[rr][2].z, v[rr][3].z);
+      *reinterpret_cast<float4*>(d + 3 * PP_PITCH) = make_float4(v[rr][0].w, v[rr][1].w, v[rr][2].w, v[rr][3].w);
+    }
+    if (P.L > 1) {
+      const bool oky = (y0 >> 1) + rp < P.h[1];
+      const bool ok0 = oky && (x0 >> 1) + 2 * xq < P.w[1], ok1 = oky && (x0 >> 1) + 2 * xq + 1 < P.w[1];
+      float a[4], b2[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        a[k] = ok0 ? 0.25f * ((v[0][k].x + v[0][k].y) + (v[1][k].x + v[1][k].y)) : 0.f;
+        b2[k] = ok1 ? 0.25f * ((v[0][k].z + v[0][k].w) + (v[1][k].z + v[1][k].w)) : 0.f;
+      }
+      float* d = pp + (256 + rp * 8 + 2 * xq) * PP_PITCH + 4 * cg;
+      *reinterpret_cast<float4*>(d) = make_float4(a[0], a[1], a[2], a[3]);
+      *reinterpret_cast<float4*>(d + PP_PITCH) = make_float4(b2[0], b2[1], b2[2], b2[3]);
+    }
+  }
+  __syncthreads();
+  // ---- levels 2, 3 from the level below (rows 320.., 336..)
+  {
+    const int c = tid & 63, q = tid >> 6;  // 8 pixels per pass
+    int src_row = 256, dst_row = 320, n = 4;  // n x n pixels at the level being produced
+#pragma unroll
+    for (int l = 2; l < PYR_MAX_LEVELS; ++l) {
+      if (l < P.L) {
+        for (int p = q; p < n * n; p += PP_NT / 64) {
+          const int py = p / n, px = p - py * n;
+          const float* s0 = pp + (src_row + (2 * py) * (2 * n) + 2 * px) * PP_PITCH + c;
+          const float* s1 = s0 + 2 * n * PP_PITCH;
+          const bool ok = (y0 >> l) + py < P.h[l] && (x0 >> l) + px < P.w[l];
+          pp[(dst_row + p) * PP_PITCH + c] = ok ? 0.25f * ((s0[0] + s0[PP_PITCH]) + (s1[0] + s1[PP_PITCH])) : 0.f;
+        }
+      }
+      __syncthreads();
+      src_row = dst_row;
+      dst_row += n * n;
+      n >>= 1;
+    }
+  }
+  // ---- rows out: a quarter-warp per row, 16 bytes (8 channels) per lane
+  const float sc = __ldg(P.bscale + b);
+  const int piece = tid & 7;
+  __half* bp = P.bp + (long long)b * P.n_recs * PYR_REC * P.Cp + c0 + 8 * piece;
+  for (int r = tid >> 3; r < PP_ROWS; r += PP_NT / 8) {
+    const int off = rowoff[r];
+    if (off < 0) continue;
+    const float* rs = pp + r * PP_PITCH + 8 * piece;
+    const float4 a = *reinterpret_cast<const float4*>(rs), c = *reinterpret_cast<const float4*>(rs + 4);
+    const __half2 h0 = __floats2half2_rn(a.x * sc, a.y * sc), h1 = __floats2half2_rn(a.z * sc, a.w * sc);
+    const __half2 h2 = __floats2half2_rn(c.x * sc, c.y * sc), h3 = __floats2half2_rn(c.z * sc, c.w * sc);
+    uint4 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&h0); u.y = *reinterpret_cast<const uint32_t*>(&h1);
+    u.z = *reinterpret_cast<const uint32_t*>(&h2); u.w = *reinterpret_cast<const uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(bp + off) = u;
+  }
+  if (blockIdx.x == 0) {  // padding subtiles behind the last level: zero rows
+    const int s_end = P.n_recs * PYR_SUBS_PER_TILE;
+    for (int i = (tid >> 3); i < (s_end - P.sub_base[PYR_MAX_LEVELS]) * PYR_SUB; i += PP_NT / 8) {  // any column order: all zero
+      const int sidx = P.sub_base[PYR_MAX_LEVELS] + i / PYR_SUB;
+      const long long row = (long long)(sidx / PYR_SUBS_PER_TILE) * PYR_REC + (sidx % PYR_SUBS_PER_TILE) * PYR_SUB + i % PYR_SUB;
+      *reinterpret_cast<uint4*>(bp + row * P.Cp) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------- epilogue
 __device__ __forceinline__ uint32_t pack_half2(uint32_t a_bits, uint32_t b_bits) {
   __half2 h = __floats2half2_rn(__uint_as_float(a_bits), __uint_as_float(b_bits));
@@ -669,27 +817,55 @@ extern "C" int ezb_corr_pyramid_fwd_ex(const float* fmap1, const float* fmap2, i
   k1::scales_kernel<<<cdiv(B, 128), 128, 0, st>>>(ws.amax, B, C, dtype, ws.bscale, ws.epi, deq_scale);
   EZB_LAUNCH_OK();
   if (int r = prep::launch_convert_kmajor(fmap1, ws.f1h, ws.amax, B, C, Cp, N, st)) return r;
-  k1::PackParams pk;
-  for (int l = 0; l < PYR_MAX_LEVELS; ++l) {
-    pk.lvl[l] = l == 0 ? fmap2 : ws.f2l[l];
-    pk.h[l] = H >> l;
-    pk.w[l] = W >> l;
-    pk.sw[l] = lay.sw[l];
-    pk.sub_base[l] = lay.sub_base[l];
-  }
-  pk.sub_base[PYR_MAX_LEVELS] = lay.sub_base[PYR_MAX_LEVELS];
-  pk.L = L; pk.C = C; pk.Cp = Cp; pk.n_recs = lay.n_tiles; pk.epl = 128 / lay.es;
-  pk.bscale = ws.bscale;
-  pk.bp = ws.f2p;
-  for (int l = 1; l < L; ++l) {
-    const long long total = (long long)B * C * pk.h[l] * pk.w[l];
-    const int gx = (int)std::min<long long>(cdiv64(total, 256), 148 * 64);
-    k1::pool2x2_kernel<<<gx, 256, 0, st>>>(pk.lvl[l - 1], ws.f2l[l], (long long)B * C, pk.h[l - 1], pk.w[l - 1],
-                                           (long long)pk.h[l - 1] * pk.w[l - 1], pk.h[l], pk.w[l], (long long)pk.h[l] * pk.w[l]);
+  static const bool split_prep = getenv("EZB_PYRAMID_SPLIT_PREP") != nullptr;  // A/B switch: round-1 pool + pack launches
+  if (!split_prep) {
+    k1::PoolPackParams pp;
+    pp.f2 = fmap2; pp.H = H; pp.W = W; pp.C = C; pp.Cp = Cp; pp.L = L; pp.n_recs = lay.n_tiles; pp.epl = 128 / lay.es;
+    pp.rx = pp.ry = 1;
+    for (int l = 0; l < PYR_MAX_LEVELS; ++l) {
+      pp.h[l] = l < L ? H >> l : 0;
+      pp.w[l] = l < L ? W >> l : 0;
+      pp.sw[l] = lay.sw[l];
+      pp.nsy[l] = l < L ? cdiv(H >> l, PYR_SY) : 0;
+      pp.sub_base[l] = lay.sub_base[l];
+      if (l < L) {  // regions needed to cover every subtile of this level: a region holds (16 >> l)^2 of its pixels
+        pp.rx = std::max(pp.rx, cdiv(pp.sw[l] * PYR_SX, k1::PP_R >> l));
+        pp.ry = std::max(pp.ry, cdiv(pp.nsy[l] * PYR_SY, k1::PP_R >> l));
+      }
+    }
+    pp.sub_base[PYR_MAX_LEVELS] = lay.sub_base[PYR_MAX_LEVELS];
+    pp.bscale = ws.bscale;
+    pp.bp = ws.f2p;
+    EZB_REQUIRE(B <= 65535 && Cp / k1::PP_CH <= 65535, "batch too large for one launch (split it)");
+    const dim3 grid(pp.rx * pp.ry, Cp / k1::PP_CH, B);
+    const bool vec = W % 4 == 0 && (reinterpret_cast<uintptr_t>(fmap2) & 15) == 0;
+    auto kern = vec ? k1::pool_pack_kernel<true> : k1::pool_pack_kernel<false>;
+    EZB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1::PP_SMEM));
+    kern<<<grid, k1::PP_NT, k1::PP_SMEM, st>>>(pp);
+    EZB_LAUNCH_OK();
+  } else {
+    k1::PackParams pk;
+    for (int l = 0; l < PYR_MAX_LEVELS; ++l) {
+      pk.lvl[l] = l == 0 ? fmap2 : ws.f2l[l];
+      pk.h[l] = H >> l;
+      pk.w[l] = W >> l;
+      pk.sw[l] = lay.sw[l];
+      pk.sub_base[l] = lay.sub_base[l];
+    }
+    pk.sub_base[PYR_MAX_LEVELS] = lay.sub_base[PYR_MAX_LEVELS];
+    pk.L = L; pk.C = C; pk.Cp = Cp; pk.n_recs = lay.n_tiles; pk.epl = 128 / lay.es;
+    pk.bscale = ws.bscale;
+    pk.bp = ws.f2p;
+    for (int l = 1; l < L; ++l) {
+      const long long total = (long long)B * C * pk.h[l] * pk.w[l];
+      const int gx = (int)std::min<long long>(cdiv64(total, 256), 148 * 64);
+      k1::pool2x2_kernel<<<gx, 256, 0, st>>>(pk.lvl[l - 1], ws.f2l[l], (long long)B * C, pk.h[l - 1], pk.w[l - 1],
+                                             (long long)pk.h[l - 1] * pk.w[l - 1], pk.h[l], pk.w[l], (long long)pk.h[l] * pk.w[l]);
+      EZB_LAUNCH_OK();
+    }
+    k1::pack_record_operand_kernel<<<dim3(lay.n_tiles, Cp / k1::PACK_CH, B), 256, 0, st>>>(pk);
     EZB_LAUNCH_OK();
   }
-  k1::pack_record_operand_kernel<<<dim3(lay.n_tiles, Cp / k1::PACK_CH, B), 256, 0, st>>>(pk);
-  EZB_LAUNCH_OK();
 
   cudaEvent_t ev0 = static_cast<cudaEvent_t>(ev_gemm_start), ev1 = static_cast<cudaEvent_t>(ev_gemm_end);
   return dtype == EZB_F16 ? k1::launch_gemm<__half>(ws, B, C, lay, pyramid, st, ev0, ev1)
