@@ -349,6 +349,10 @@ bool local_corr_rt_strided_supported(const float* in1, const float* in2, const f
                                      int sh, int sw, int padh, int padw, int dph, int dpw, long long out_bstride);
 int local_corr_rt_strided_launch(const float* in1, const float* in2, int BG, int G, int C, int H, int W, int P, int S, float scale, float slope,
                                  float* out, long long out_bstride, cudaStream_t st);
+bool local_corr_bwd_strided_supported(const float* in1, const float* in2, const float* dout, const float* din1, const float* din2, int BG,
+                                      int C, int H, int W, int Ph, int Pw, int sh, int sw, int padh, int padw, int dph, int dpw);
+int local_corr_bwd_strided_launch(const float* in1, const float* in2, const float* dout, int BG, int G, int C, int H, int W, int P, float scale,
+                                  long long dout_bstride, float* din1, float* din2, cudaStream_t st);
 // local_corr_bwd_tc.cu
 bool local_corr_bwd_tc_supported(int C, int H, int W, int Ph, int Pw, int sh, int sw, int padh, int padw, int dph, int dpw);
 size_t local_corr_bwd_tc_workspace_bytes(int BG, int C, int H, int W);
@@ -481,6 +485,9 @@ static int local_corr_bwd_simt(const float* in1, const float* in2, const float* 
   // PWC-Net's shape (odd window <= 9, stride 1, no dilation / padding): register-tiled kernels (local_corr_rt.cu)
   if (local_corr_bwd_rt_supported(in1, in2, dout, din1, din2, B, C, H, W, Ph, Pw, sh, sw, padh, padw, dph, dpw, P.dout_bstride))
     return local_corr_bwd_rt_launch(in1, in2, dout, B, C, H, W, Ph, scale, P.dout_bstride, din1, din2, st);
+  // DCVNet's fine scale (stride 4): strided gather kernels with the window products in registers (local_corr_rt.cu)
+  if (local_corr_bwd_strided_supported(in1, in2, dout, din1, din2, B, C, H, W, Ph, Pw, sh, sw, padh, padw, dph, dpw))
+    return local_corr_bwd_strided_launch(in1, in2, dout, B, 1, C, H, W, Ph, scale, P.dout_bstride, din1, din2, st);
   const long long total = (long long)B * C * H * W;
   const int blocks = (int)std::min<long long>(cdiv64(total, 256), 148 * 32);
   // stride 1: tiled kernels (products out of shared memory); otherwise the gather kernels
@@ -567,6 +574,8 @@ extern "C" int ezb_matryoshka_bwd(const float* x1, const float* x2, const float*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long n = (long long)BG * Cg * H * W;
   const int64_t bstride = dout_batch_stride > 0 ? dout_batch_stride : (int64_t)D * G * P_ * P_ * oh * ow;
+  if (D == 1 && local_corr_bwd_strided_supported(x1, x2, dout, dx1, dx2, BG, Cg, H, W, P_, P_, stride, stride, 0, 0, dil[0], dil[0]))
+    return local_corr_bwd_strided_launch(x1, x2, dout, BG, G, Cg, H, W, P_, 1.f, bstride, dx1, dx2, st);  // any group count
   bool first = true;
   for (int d = 0; d < D; ++d) {
     EZB_REQUIRE(dil[d] > 0, "dilation must be positive");

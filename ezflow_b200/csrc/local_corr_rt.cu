@@ -26,6 +26,7 @@
 // workspace first (a halo-warping variant of this kernel was 3x slower than that: every halo pixel is warped 2.5 times).
 #include "ezb_common.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace ezb {
@@ -445,6 +446,126 @@ static int launch_strided(const SParams& Q, cudaStream_t st) {
   return EZB_OK;
 }
 
+// ------------------------------------------------------------------------------------ strided adjoints (stride 4: DCVNet's fine scale)
+// Autograd of the strided forward above (sampler.py:96-129 with stride 4, learnable_cost.py:420-434), gather form, exact fp32:
+//   din1[c, 4y, 4x]   = scale * sum_{pi,pj} dout[pi,pj,y,x] * in2[c, 4y + pi - md, 4x + pj - md]          (0 off the query lattice)
+//   din2[c, 4Y+i, 4X+j] = scale * sum over the (pi,pj) with pi - md = i, pj - md = j (mod 4) of
+//                         dout[pi,pj, Y - (pi-md-i)/4, X - (pj-md-j)/4] * in1[c, 4(Y - ..), 4(X - ..)]
+// Both are "one query cell = P*P products per channel": thread = cell (y, x) (lane = x), its P*P upstream gradients live in
+// registers for the whole channel loop.  din1: per channel and window row three 16-byte loads (4x-4 .. 4x+7: each perfectly
+// coalesced over the warp, two of the three L1 hits) -> P FMAs; the thread writes the whole 4 x 4 block of din1 (the value and
+// 15 zeros) as four 16-byte stores, so no memset pass is needed.  din2: every (pi,pj) feeds exactly one of the cell's 4 x 4
+// outputs from one of the 3 x 3 neighbouring queries: 9 scalar in1 loads, P*P FMAs, four 16-byte stores per channel.
+// The round-1 gather kernels tested every (pi,pj) of every output element for divisibility: 5.5 ms at BASELINE config 4.
+struct SBwdParams {
+  const float* in1;
+  const float* in2;
+  const float* dout;
+  float* din1;
+  float* din2;
+  int BG, G, C, H, W, oh, ow, nchunk, cpc;  // nchunk channel chunks of cpc channels (blockIdx.z = bg * nchunk + chunk)
+  float scale;
+  long long dout_bstride;
+};
+
+template <int P, bool SECOND>
+__global__ void __launch_bounds__(128) local_corr_bwd_strided_kernel(const SBwdParams Q) {
+  constexpr int S = 4, MD = (P - 1) / 2;
+  static_assert(MD <= 4, "window");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x = blockIdx.x * 32 + lane, y = blockIdx.y * 4 + warp;
+  const int bg = blockIdx.z / Q.nchunk, chunk = blockIdx.z - bg * Q.nchunk;
+  if (x >= Q.ow || y >= Q.oh) return;  // no barriers below
+  const int b = bg / Q.G, g = bg - b * Q.G;
+  const long long ohw = (long long)Q.oh * Q.ow, HW = (long long)Q.H * Q.W;
+  const float* dbase = Q.dout + (long long)b * Q.dout_bstride + (long long)g * P * P * ohw;
+  const int c_begin = chunk * Q.cpc, c_end = min(Q.C, c_begin + Q.cpc);
+
+  float dv[P][P];
+  if constexpr (!SECOND) {
+#pragma unroll
+    for (int pi = 0; pi < P; ++pi)
+#pragma unroll
+      for (int pj = 0; pj < P; ++pj) dv[pi][pj] = __ldg(dbase + (long long)(pi * P + pj) * ohw + (long long)y * Q.ow + x) * Q.scale;
+    const float* img = Q.in2 + ((long long)bg * Q.C + c_begin) * HW + (long long)(S * y) * Q.W + S * x;
+    float* o = Q.din1 + ((long long)bg * Q.C + c_begin) * HW + (long long)(S * y) * Q.W + S * x;
+    const bool left = x > 0, right = S * x + 4 < Q.W;
+    for (int c = c_begin; c < c_end; ++c, img += HW, o += HW) {
+      float acc3[3] = {0.f, 0.f, 0.f};  // three independent FMA chains
+#pragma unroll
+      for (int pi = 0; pi < P; ++pi) {
+        const int yy = S * y + pi - MD;
+        if (yy < 0 || yy >= Q.H) continue;
+        float& acc = acc3[pi % 3];
+        const float* r = img + (long long)(pi - MD) * Q.W;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 a = (MD > 0 && left) ? __ldg(reinterpret_cast<const float4*>(r - 4)) : z;
+        const float4 m = __ldg(reinterpret_cast<const float4*>(r));
+        const float4 e = (MD == 4 && right) ? __ldg(reinterpret_cast<const float4*>(r + 4)) : z;
+        const float v[12] = {a.x, a.y, a.z, a.w, m.x, m.y, m.z, m.w, e.x, e.y, e.z, e.w};
+#pragma unroll
+        for (int pj = 0; pj < P; ++pj) acc = fmaf(dv[pi][pj], v[4 - MD + pj], acc);
+      }
+      __stcs(reinterpret_cast<float4*>(o), make_float4((acc3[0] + acc3[1]) + acc3[2], 0.f, 0.f, 0.f));
+#pragma unroll
+      for (int rr = 1; rr < S; ++rr)
+        if (S * y + rr < Q.H) __stcs(reinterpret_cast<float4*>(o + (long long)rr * Q.W), make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+  } else {
+    // displacement pi lands on output row i = (pi - MD) mod 4 of the cell and comes from the query dy = -(pi - MD - i) / 4 cells away
+    auto sub = [](int p) { const int t = p - MD; return ((t % S) + S) % S; };
+    auto off = [&](int p) { const int t = p - MD; return -(t - sub(p)) / S; };
+#pragma unroll
+    for (int pi = 0; pi < P; ++pi)
+#pragma unroll
+      for (int pj = 0; pj < P; ++pj) {
+        const int yq = y + off(pi), xq = x + off(pj);
+        const bool ok = yq >= 0 && yq < Q.oh && xq >= 0 && xq < Q.ow;
+        dv[pi][pj] = ok ? __ldg(dbase + (long long)(pi * P + pj) * ohw + (long long)yq * Q.ow + xq) * Q.scale : 0.f;
+      }
+    const float* img = Q.in1 + ((long long)bg * Q.C + c_begin) * HW + (long long)(S * y) * Q.W + S * x;
+    float* o = Q.din2 + ((long long)bg * Q.C + c_begin) * HW + (long long)(S * y) * Q.W + S * x;
+    bool okq[3][3];
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) okq[dy + 1][dx + 1] = y + dy >= 0 && y + dy < Q.oh && x + dx >= 0 && x + dx < Q.ow;
+    for (int c = c_begin; c < c_end; ++c, img += HW, o += HW) {
+      float a[3][3];
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) a[dy + 1][dx + 1] = okq[dy + 1][dx + 1] ? __ldg(img + (long long)(S * dy) * Q.W + S * dx) : 0.f;
+      float acc[S][S];
+#pragma unroll
+      for (int i = 0; i < S; ++i)
+#pragma unroll
+        for (int j = 0; j < S; ++j) acc[i][j] = 0.f;
+#pragma unroll
+      for (int pi = 0; pi < P; ++pi)
+#pragma unroll
+        for (int pj = 0; pj < P; ++pj) acc[sub(pi)][sub(pj)] = fmaf(dv[pi][pj], a[off(pi) + 1][off(pj) + 1], acc[sub(pi)][sub(pj)]);
+#pragma unroll
+      for (int i = 0; i < S; ++i)
+        if (S * y + i < Q.H) __stcs(reinterpret_cast<float4*>(o + (long long)i * Q.W), make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+    }
+  }
+}
+
+template <int P>
+static int launch_bwd_strided(SBwdParams Q, cudaStream_t st) {
+  // enough channel chunks to fill the GPU a few times over; at least 8 channels per thread to amortise its P*P gradient loads
+  const long long cells = (long long)cdiv(Q.ow, 32) * cdiv(Q.oh, 4) * Q.BG;
+  int nchunk = (int)std::min<long long>(std::max<long long>(1, (148 * 16) / std::max<long long>(cells, 1)), std::max(1, Q.C / 8));
+  nchunk = std::max(1, std::min(nchunk, Q.C));
+  Q.cpc = cdiv(Q.C, nchunk);
+  Q.nchunk = cdiv(Q.C, Q.cpc);
+  const dim3 grid(cdiv(Q.ow, 32), cdiv(Q.oh, 4), Q.BG * Q.nchunk);
+  if (Q.din1) { local_corr_bwd_strided_kernel<P, false><<<grid, 128, 0, st>>>(Q); EZB_LAUNCH_OK(); }
+  if (Q.din2) { local_corr_bwd_strided_kernel<P, true><<<grid, 128, 0, st>>>(Q); EZB_LAUNCH_OK(); }
+  return EZB_OK;
+}
+
 // ------------------------------------------------------------------------------------ adjoints (K4b), same regular case
 //   SECOND = false: din1[c,y,x] = scale * sum_{pi,pj} dout[pi,pj,y,x] * in2[c, y + pi - md, x + pj - md]
 //   SECOND = true : din2[c,y,x] = scale * sum_{pi,pj} dout[P-1-pi, P-1-pj, y + pi - md, x + pj - md] * in1[c, y + pi - md, x + pj - md]
@@ -690,6 +811,33 @@ int local_corr_rt_strided_launch(const float* in1, const float* in2, int BG, int
   }
 #undef EZB_RTS_CASE
   return fail(EZB_ERR_UNSUPPORTED, "strided register-tiled local correlation: patch size %d", P);
+}
+
+// Strided adjoints: stride 4 in both directions, one dilation of 1, no padding, square odd window <= 9, W % 4 == 0.
+bool local_corr_bwd_strided_supported(const float* in1, const float* in2, const float* dout, const float* din1, const float* din2, int BG,
+                                      int C, int H, int W, int Ph, int Pw, int sh, int sw, int padh, int padw, int dph, int dpw) {
+  if (const char* e = getenv("EZB_LOCAL_CORR_BWD_RT"))
+    if (atoi(e) == 0) return false;
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(in1) | reinterpret_cast<uintptr_t>(in2) | reinterpret_cast<uintptr_t>(din1) |
+                         reinterpret_cast<uintptr_t>(din2);
+  (void)dout;  // read with scalar loads: no alignment requirement
+  return Ph == Pw && (Ph == 9 || Ph == 7 || Ph == 5 || Ph == 3) && sh == 4 && sw == 4 && padh == 0 && padw == 0 && dph == 1 && dpw == 1 &&
+         W % 4 == 0 && (bits & 15) == 0 && cdiv(cdiv(H, 4), 4) <= 65535 && (long long)BG * C <= 65535;
+}
+
+int local_corr_bwd_strided_launch(const float* in1, const float* in2, const float* dout, int BG, int G, int C, int H, int W, int P, float scale,
+                                  long long dout_bstride, float* din1, float* din2, cudaStream_t st) {
+  k4rt::SBwdParams Q;
+  Q.in1 = in1; Q.in2 = in2; Q.dout = dout; Q.din1 = din1; Q.din2 = din2;
+  Q.BG = BG; Q.G = G; Q.C = C; Q.H = H; Q.W = W; Q.oh = cdiv(H, 4); Q.ow = W / 4;
+  Q.nchunk = 1; Q.cpc = C; Q.scale = scale; Q.dout_bstride = dout_bstride;
+  switch (P) {
+    case 9: return k4rt::launch_bwd_strided<9>(Q, st);
+    case 7: return k4rt::launch_bwd_strided<7>(Q, st);
+    case 5: return k4rt::launch_bwd_strided<5>(Q, st);
+    case 3: return k4rt::launch_bwd_strided<3>(Q, st);
+  }
+  return fail(EZB_ERR_UNSUPPORTED, "strided local correlation adjoint: patch size %d", P);
 }
 
 }  // namespace ezb

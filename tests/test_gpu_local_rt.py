@@ -236,3 +236,68 @@ def test_strided_register_tiled_in_matryoshka_list(use_relu):
     assert_close(out, ref, 1e-3, f"matryoshka list use_relu={use_relu}")
     fine = out[:, :2]  # the stride-4 scale's groups: exact fp32
     assert_close(fine, ref[:, :2], 2e-5, "fine scale (strided register-tiled kernel)")
+
+
+# (B, C, H, W, P): stride 4, W % 4 == 0; H not a multiple of 4, single-row / single-column query grids, channel counts that
+# do not divide into the launch's channel chunks, every patch size
+STRIDED_BWD_SHAPES = [(2, 16, 32, 64, 9), (1, 13, 19, 48, 9), (1, 5, 70, 144, 9), (2, 7, 9, 16, 9), (1, 3, 4, 4, 9), (1, 6, 21, 32, 7),
+                      (2, 10, 14, 24, 5), (1, 4, 12, 16, 3), (1, 37, 6, 132, 9)]
+
+
+@pytest.mark.parametrize("shape", STRIDED_BWD_SHAPES)
+def test_strided_adjoints_vs_oracle(shape):
+    """local_corr_bwd_strided_kernel (DCVNet's fine scale, stride 4) vs the oracle's closed-form adjoint; the round-1 gather
+    kernels (EZB_LOCAL_CORR_BWD_RT=0) must agree to summation order; din1 is exactly zero off the query lattice."""
+    import ezflow_b200 as E
+    from oracle import similarity_oracle as O
+
+    B, C, H, W, P = shape
+    rng = np.random.default_rng(P * 100 + C)
+    x1 = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    x2 = (rng.standard_normal((B, C, H, W)) * 2).astype(np.float32)
+    oh, ow = -(-H // 4), -(-W // 4)
+    dout = rng.standard_normal((B, P, P, oh, ow)).astype(np.float32)
+    d1, d2 = O.iter_spatial_correlation_sample_bwd(x1, x2, dout, patch_size=P, stride=4)
+    grads = {}
+    for flag in ("1", "0"):
+        old = _setenv(EZB_LOCAL_CORR_BWD_RT=flag)
+        try:
+            t1, t2 = to_gpu(x1, True), to_gpu(x2, True)
+            E.IterSpatialCorrelationSampler(kernel_size=1, patch_size=P, stride=4)(t1, t2).backward(to_gpu(dout))
+            grads[flag] = (t1.grad.clone(), t2.grad.clone())
+        finally:
+            _setenv(**old)
+    for flag, (g1, g2) in grads.items():
+        assert_close(g1, d1, 5e-5, f"dinput1 {shape} rt={flag}")
+        assert_close(g2, d2, 5e-5, f"dinput2 {shape} rt={flag}")
+    g1 = grads["1"][0]
+    lattice = torch.zeros_like(g1, dtype=torch.bool)
+    lattice[:, :, ::4, ::4] = True
+    assert float(g1[~lattice].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("groups", [1, 2])
+def test_strided_adjoints_in_matryoshka_list(groups):
+    """Backward of the DCVNet cost-volume list (fine scale at stride 4 through the strided adjoints, any group count) against
+    the oracle, with the fused LeakyReLU mask."""
+    import ezflow_b200 as E
+    from oracle import similarity_oracle as O
+
+    rng = np.random.default_rng(31)
+    x1 = [rng.standard_normal((2, 8, 32, 64)).astype(np.float32), rng.standard_normal((2, 16, 8, 16)).astype(np.float32)]
+    x2 = [rng.standard_normal((2, 8, 32, 64)).astype(np.float32), rng.standard_normal((2, 16, 8, 16)).astype(np.float32)]
+    m = E.MatryoshkaDilatedCostVolumeList(num_groups=groups, max_displacement=4, encoder_output_strides=[2, 8], dilations=[[1], [1, 2]],
+                                          normalize_feat_l2=False, use_relu=False).to(dev())
+    t1 = [to_gpu(a, True) for a in x1]
+    t2 = [to_gpu(a, True) for a in x2]
+    out = m(t1, t2)
+    dout = rng.standard_normal(tuple(out.shape)).astype(np.float32)
+    out.backward(to_gpu(dout))
+    # fine scale: channels [0, groups) of the concatenated volume
+    P = 9
+    g = dout[:, :groups].reshape(2 * groups, P, P, 8, 16)
+    a = x1[0].reshape(2 * groups, 8 // groups, 32, 64)
+    b = x2[0].reshape(2 * groups, 8 // groups, 32, 64)
+    d1, d2 = O.iter_spatial_correlation_sample_bwd(a, b, g, patch_size=P, stride=4)
+    assert_close(t1[0].grad, d1.reshape(2, 8, 32, 64), 5e-5, f"fine-scale dx1 groups={groups}")
+    assert_close(t2[0].grad, d2.reshape(2, 8, 32, 64), 5e-5, f"fine-scale dx2 groups={groups}")

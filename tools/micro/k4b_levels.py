@@ -31,7 +31,8 @@ def timed(fn, iters=10, warm=3):
 cases = [("PWC 196x7x16", (8, 196, 7, 16), dict(patch_size=9)), ("PWC 128x14x32", (8, 128, 14, 32), dict(patch_size=9)),
          ("PWC 96x28x64", (8, 96, 28, 64), dict(patch_size=9)), ("PWC 64x56x128", (8, 64, 56, 128), dict(patch_size=9)),
          ("PWC 32x112x256", (8, 32, 112, 256), dict(patch_size=9)), ("FlowNetC 256x48x64 P21 dp2", (8, 256, 48, 64), dict(patch_size=21, dilation_patch=2)),
-         ("DCV s8 d1 256x48x96", (4, 256, 48, 96), dict(patch_size=9)), ("DCV s8 d5", (4, 256, 48, 96), dict(patch_size=9, dilation_patch=5))]
+         ("DCV s8 d1 256x48x96", (4, 256, 48, 96), dict(patch_size=9)), ("DCV s8 d5", (4, 256, 48, 96), dict(patch_size=9, dilation_patch=5)),
+         ("DCV s2 stride 4 128x192x384", (4, 128, 192, 384), dict(patch_size=9, stride=4))]
 for name, shape, kw in cases:
     x1 = torch.randn(shape, device=dev, requires_grad=True)
     x2 = torch.randn(shape, device=dev, requires_grad=True)
