@@ -523,7 +523,10 @@ def run_secondary(args, dev, world, rank, peaks, headline_step):
             del fn, lazy, f1, f2
         torch.cuda.empty_cache()
 
-    if enabled("cfg5_raft_1080p_train_step"):
+    for c5_name in ("cfg5_raft_1080p_train_step", "cfg5_raft_1080p_train_step_smooth_flow"):
+        if not enabled(c5_name):
+            continue
+        smooth = c5_name.endswith("smooth_flow")
         # per pair: build (K1+K2), 12 lookups (K3), 12 lookup adjoints (K3b), pyramid adjoint (K1b+K2b); then the all-reduce
         lo, hi = shard_range(args.train_batch, world, rank)
         g = torch.Generator(device="cpu").manual_seed(99 + rank)
@@ -532,7 +535,14 @@ def run_secondary(args, dev, world, rank, peaks, headline_step):
         f1 = torch.randn(TMB, C, H, W, generator=g).to(dev).requires_grad_(True)
         f2 = torch.randn(TMB, C, H, W, generator=g).to(dev).requires_grad_(True)
         grid = E.coords_grid(TMB, H, W, device=dev)
-        coords = [(grid + torch.randn(TMB, 2, H, W, generator=g).to(dev) * (2 + k)).clamp_(-16, W + 16) for k in range(ITERS)]
+        if smooth:
+            # a RAFT-like trajectory: a smooth flow field of up to ~+-20 feature pixels (160 image pixels), approached
+            # geometrically over the iterations, plus half a pixel of per-query noise
+            flow = torch.nn.functional.interpolate(torch.randn(TMB, 2, 5, 8, generator=g) * 10, size=(H, W), mode="bicubic", align_corners=True).to(dev)
+            coords = [(grid + flow * (1 - 0.5 ** (k + 1)) + torch.randn(TMB, 2, H, W, generator=g).to(dev) * 0.5).clamp_(-16, W + 16)
+                      for k in range(ITERS)]
+        else:
+            coords = [(grid + torch.randn(TMB, 2, H, W, generator=g).to(dev) * (2 + k)).clamp_(-16, W + 16) for k in range(ITERS)]
         douts = [torch.randn(TMB, L * (2 * R + 1) ** 2, H, W, generator=g).to(dev) for _ in range(ITERS)]
         bucket = torch.randn(RAFT_PARAMS, device=dev)
 
@@ -566,9 +576,10 @@ def run_secondary(args, dev, world, rank, peaks, headline_step):
         torch.cuda.synchronize()
         (ms,) = max_over_ranks([t0.elapsed_time(t1) / nsteps], device=dev)
         per_pair = N * LEVEL_ELEMS * 2 + ITERS * 68.2e6 + ITERS * 145.7e6 + 2 * N * LEVEL_ELEMS * 4  # BASELINE.md §3 (fwd fp16 pyramid + bwd)
-        add("cfg5_raft_1080p_train_step", ms, int(per_pair * (hi - lo)),
+        add(c5_name, ms, int(per_pair * (hi - lo)),
             "RAFT 1080p correlation fwd+bwd training step, global batch sharded over the ranks, NCCL all-reduce(sum) of the "
-            "RAFT-sized fp32 gradient bucket per step (BASELINE config 5); bytes = this rank's pairs",
+            "RAFT-sized fp32 gradient bucket per step (BASELINE config 5); bytes = this rank's pairs; lookup coords = "
+            + ("grid + a smooth flow field (+-20 px) approached over the 12 iterations + 0.5 px noise" if smooth else "grid + randn * (2 + k) for lookup k (windows scattered +-40 px)"),
             global_batch=args.train_batch, pairs_per_rank=hi - lo, micro_batch=TMB, pairs_per_s=args.train_batch / (ms / 1e3),
             ms_per_pair=ms / max(hi - lo, 1), allreduce_elems=RAFT_PARAMS if world > 1 else 0, scaling="strong", steps=nsteps)
         del f1, f2, coords, douts, bucket

@@ -25,6 +25,7 @@ from .similarity import (
     iter_spatial_correlation_sample,
     lazy_warp,
     lookup_conv1x1,
+    release_gradient_pool,
     set_local_corr_mode,
     set_pyramid_dtype,
     vcn_corr,

@@ -50,6 +50,11 @@ _SIGNATURES = {
     "ezb_corr_lookup_bwd_coords": ([c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp], c_int),
     "ezb_corr_pyramid_bwd_workspace_bytes": ([c_int, c_int, c_int, c_int, c_int, _P(c_sz)], c_int),
     "ezb_corr_pyramid_bwd": ([_P(c_vp), c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_sz, c_vp], c_int),
+    "ezb_corr_grad_ranges_supported": ([c_int, c_int, c_int, c_int], c_int),
+    "ezb_corr_grad_ranges_count": ([c_int, c_int, c_int, _P(c_i64)], c_int),
+    "ezb_corr_grad_ranges": ([_P(c_vp), c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp], c_int),
+    "ezb_corr_pyramid_bwd_ex": ([_P(c_vp), c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_sz, c_vp, c_vp], c_int),
+    "ezb_corr_grad_rezero": ([_P(c_vp), c_vp, c_int, c_int, c_int, c_int, c_vp], c_int),
     "ezb_local_corr_workspace_bytes": ([c_int, c_int, c_int, c_int, c_int, c_int, _P(c_sz)], c_int),
     "ezb_local_corr_fwd": ([c_vp, c_vp] + [c_int] * 12 + [c_f32, c_f32, c_vp, c_i64, c_vp, c_sz, c_vp], c_int),
     "ezb_warp_local_corr_fwd": ([c_vp, c_vp, c_vp] + [c_int] * 12 + [c_f32, c_f32, c_vp, c_i64, c_vp, c_sz, c_vp], c_int),

@@ -8,6 +8,7 @@
 // folding; the fold kernel and the fp32 shared-memory-tiled SIMT GEMMs below cover the remaining shapes.
 #include "ezb_common.cuh"
 
+#include <climits>
 #include <cstdlib>
 
 namespace ezb {
@@ -25,6 +26,92 @@ __global__ void fold_level_kernel(const float* __restrict__ up, float* __restric
     d[1] += g;
     d[pitch_down] += g;
     d[pitch_down + 1] += g;
+  }
+}
+
+// ---- support of the gradient pyramid -------------------------------------------------------------------------------
+// A query's gradient maps are non-zero only inside the lookup windows of the step's lookups (12 for RAFT), i.e. ~1 % of
+// a 1080p pyramid.  ranges[b][T][l] = [t0, t1): the 256-target tiles of level l that any window of any query of the
+// 256-query tile T can touch (same window arithmetic as corr_lookup_bwd_kernel).  The adjoint GEMMs skip everything
+// outside (corr_bwd_tc.cu), and after the GEMMs only these ranges are zeroed again, so a gradient pyramid that starts
+// all-zero is all-zero again for the next step without a 5.6 GB memset per pair.
+constexpr int RG_MAX_LOOKUPS = 32, RG_LEVELS = 4;
+struct RangeParams {
+  const float* coords[RG_MAX_LOOKUPS];  // (B,2,N) each
+  int n, B, N, L, r, nT;
+  int h[RG_LEVELS], w[RG_LEVELS];
+  int2* ranges;  // [B][nT][RG_LEVELS], pre-set to (INT_MAX, 0)
+};
+__device__ __forceinline__ int floor_clamped(float v) {
+  // floorf with the same saturation as the lookup kernels (NaN / huge coordinates fall outside every level)
+  if (!(v > -16777216.f)) return -(1 << 24);
+  if (!(v < 16777216.f)) return 1 << 24;
+  return (int)floorf(v);
+}
+__global__ void __launch_bounds__(256) grad_ranges_kernel(const RangeParams P) {
+  const int b = blockIdx.y, T = blockIdx.x, q = T * 256 + threadIdx.x;
+  int lo[RG_LEVELS], hi[RG_LEVELS];
+#pragma unroll
+  for (int l = 0; l < RG_LEVELS; ++l) { lo[l] = INT_MAX; hi[l] = -1; }
+  if (q < P.N) {
+    const int D = 2 * P.r + 2;
+    for (int i = 0; i < P.n; ++i) {
+      const float cx0 = __ldg(P.coords[i] + (long long)b * 2 * P.N + q), cy0 = __ldg(P.coords[i] + (long long)b * 2 * P.N + P.N + q);
+#pragma unroll
+      for (int l = 0; l < RG_LEVELS; ++l) {
+        if (l >= P.L) break;
+        const float inv = 1.0f / (float)(1 << l);
+        const int hl = P.h[l], wl = P.w[l];
+        const int xs = max(-D, min(wl, floor_clamped(cx0 * inv) - P.r)), ys = max(-D, min(hl, floor_clamped(cy0 * inv) - P.r));
+        const int x0 = max(xs, 0), x1 = min(xs + D, wl) - 1, y0 = max(ys, 0), y1 = min(ys + D, hl) - 1;  // window clipped to the level
+        if (x0 > x1 || y0 > y1) continue;
+        lo[l] = min(lo[l], y0 * wl + x0);
+        hi[l] = max(hi[l], y1 * wl + x1);
+      }
+    }
+  }
+  __shared__ int s_lo[RG_LEVELS], s_hi[RG_LEVELS];
+  if (threadIdx.x < RG_LEVELS) { s_lo[threadIdx.x] = INT_MAX; s_hi[threadIdx.x] = -1; }
+  __syncthreads();
+#pragma unroll
+  for (int l = 0; l < RG_LEVELS; ++l) {
+    const int a = __reduce_min_sync(0xffffffffu, lo[l]), c = __reduce_max_sync(0xffffffffu, hi[l]);
+    if ((threadIdx.x & 31) == 0) { atomicMin(&s_lo[l], a); atomicMax(&s_hi[l], c); }
+  }
+  __syncthreads();
+  if (threadIdx.x < RG_LEVELS && s_hi[threadIdx.x] >= 0) {
+    int2* r = P.ranges + ((long long)b * P.nT + T) * RG_LEVELS + threadIdx.x;
+    atomicMin(&r->x, s_lo[threadIdx.x] >> 8);
+    atomicMax(&r->y, (s_hi[threadIdx.x] >> 8) + 1);
+  }
+}
+__global__ void __launch_bounds__(256) grad_ranges_init_kernel(int2* ranges, long long n) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) ranges[i] = make_int2(INT_MAX, 0);
+}
+// zero rows q of tile T over the columns of its range, level by level (blockIdx.x = T, blockIdx.y = b, blockIdx.z = row slice)
+struct RezeroParams {
+  float* dlvl[RG_LEVELS];
+  long long qstride[RG_LEVELS];
+  int nl[RG_LEVELS];
+  const int2* ranges;
+  int N, L, nT;
+};
+__global__ void __launch_bounds__(256) grad_rezero_kernel(const RezeroParams P) {
+  const int b = blockIdx.y, T = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int l = 0; l < P.L; ++l) {
+    const int2 r = __ldg(P.ranges + ((long long)b * P.nT + T) * RG_LEVELS + l);
+    const int c0 = r.x == INT_MAX ? 0 : r.x * 256, c1 = min(P.nl[l], r.y * 256);  // columns, multiples of 4 except the level's end
+    if (c1 <= c0) continue;
+    const int c1v = c0 + ((c1 - c0) & ~3);
+    // a warp per row (qstride and c0 are multiples of 4 floats: 16-byte stores), rows dealt over blockIdx.z
+    for (int row = blockIdx.z * 8 + warp; row < 256; row += gridDim.z * 8) {
+      const int q = T * 256 + row;
+      if (q >= P.N) break;
+      float* d = P.dlvl[l] + ((long long)b * P.N + q) * P.qstride[l];
+      for (int c = c0 + 4 * lane; c < c1v; c += 128) *reinterpret_cast<float4*>(d + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lane < c1 - c1v) d[c1v + lane] = 0.f;
+    }
   }
 }
 
@@ -100,7 +187,7 @@ bool corr_bwd_tc_supported(int C, int N);
 size_t corr_bwd_tc_workspace_bytes(int B, int C, int H, int W, int L);
 int corr_bwd_tc_launch(float* const* dlvl, const long long* qstride, const float* fmap1, const float* fmap2, int B, int C, int H,
                        int W, int L, float alpha, float* dfmap1, float* dfmap2, void* workspace, size_t workspace_bytes,
-                       cudaStream_t st);
+                       const int32_t* ranges, cudaStream_t st);
 }  // namespace ezb
 
 using namespace ezb;
@@ -111,9 +198,9 @@ extern "C" int ezb_corr_pyramid_bwd_workspace_bytes(int B, int C, int H, int W, 
   return EZB_OK;
 }
 
-extern "C" int ezb_corr_pyramid_bwd(float* const* dlvl_ptrs, const float* fmap1, const float* fmap2, int B, int C, int H,
-                                    int W, int L, float* dfmap1, float* dfmap2, void* workspace, size_t workspace_bytes,
-                                    void* stream) {
+extern "C" int ezb_corr_pyramid_bwd_ex(float* const* dlvl_ptrs, const float* fmap1, const float* fmap2, int B, int C, int H,
+                                       int W, int L, float* dfmap1, float* dfmap2, void* workspace, size_t workspace_bytes,
+                                       const int32_t* ranges, void* stream) {
   EZB_REQUIRE(dlvl_ptrs && fmap1 && fmap2 && (dfmap1 || dfmap2), "null pointer");
   EZB_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && L >= 1 && L <= EZB_MAX_LEVELS, "bad shape B=%d C=%d H=%d W=%d L=%d", B, C,
               H, W, L);
@@ -128,8 +215,10 @@ extern "C" int ezb_corr_pyramid_bwd(float* const* dlvl_ptrs, const float* fmap1,
     // tensor cores, no fold: the K loop of the df1 GEMM runs over the targets of all levels (corr_bwd_tc.cu)
     long long qs[EZB_MAX_LEVELS];
     for (int l = 0; l < L; ++l) qs[l] = g[l].qstride;
-    return corr_bwd_tc_launch(dlvl_ptrs, qs, fmap1, fmap2, B, C, H, W, L, alpha, dfmap1, dfmap2, workspace, workspace_bytes, st);
+    return corr_bwd_tc_launch(dlvl_ptrs, qs, fmap1, fmap2, B, C, H, W, L, alpha, dfmap1, dfmap2, workspace, workspace_bytes, ranges, st);
   }
+  if (ranges != nullptr)
+    return fail(EZB_ERR_UNSUPPORTED, "gradient ranges need the tensor-core adjoint (ezb_corr_grad_ranges_supported)");
   for (int l = L - 1; l >= 1; --l) {
     const long long total = rows * g[l].h * g[l].w;
     const int blocks = (int)std::min<long long>(cdiv64(total, 256), 148 * 32);
@@ -147,5 +236,67 @@ extern "C" int ezb_corr_pyramid_bwd(float* const* dlvl_ptrs, const float* fmap1,
     k1b::corr_bwd_gemm_kernel<false><<<grid, 256, 0, st>>>(fmap1, G, dfmap2, C, N, alpha);
     EZB_LAUNCH_OK();
   }
+  return EZB_OK;
+}
+
+extern "C" int ezb_corr_pyramid_bwd(float* const* dlvl_ptrs, const float* fmap1, const float* fmap2, int B, int C, int H,
+                                    int W, int L, float* dfmap1, float* dfmap2, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
+  return ezb_corr_pyramid_bwd_ex(dlvl_ptrs, fmap1, fmap2, B, C, H, W, L, dfmap1, dfmap2, workspace, workspace_bytes, nullptr, stream);
+}
+
+extern "C" int ezb_corr_grad_ranges_supported(int C, int H, int W, int L) {
+  return (L >= 1 && L <= 4 && C > 0 && H > 0 && W > 0 && corr_bwd_tc_supported(C, H * W) && getenv("EZB_BWD_SIMT") == nullptr &&
+          getenv("EZB_BWD_DENSE") == nullptr) ? 1 : 0;
+}
+
+extern "C" int ezb_corr_grad_ranges_count(int B, int H, int W, int64_t* n_int32) {
+  EZB_REQUIRE(B > 0 && H > 0 && W > 0 && n_int32, "bad arguments");
+  *n_int32 = (int64_t)B * cdiv(H * W, 256) * k1b::RG_LEVELS * 2;
+  return EZB_OK;
+}
+
+extern "C" int ezb_corr_grad_ranges(const float* const* coords_ptrs, int n_lookups, int B, int H, int W, int L, int radius,
+                                    int32_t* ranges, void* stream) {
+  EZB_REQUIRE(coords_ptrs && ranges && n_lookups >= 0, "bad arguments");
+  EZB_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0 && L >= 1 && L <= k1b::RG_LEVELS && radius >= 0, "bad shape B=%d H=%d W=%d L=%d r=%d", B, H, W,
+              L, radius);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int N = H * W, nT = cdiv(N, 256);
+  const long long n = (long long)B * nT * k1b::RG_LEVELS;
+  k1b::grad_ranges_init_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, st>>>(reinterpret_cast<int2*>(ranges), n);
+  EZB_LAUNCH_OK();
+  for (int i0 = 0; i0 < n_lookups; i0 += k1b::RG_MAX_LOOKUPS) {
+    k1b::RangeParams P;
+    P.n = std::min(k1b::RG_MAX_LOOKUPS, n_lookups - i0);
+    for (int i = 0; i < P.n; ++i) {
+      EZB_REQUIRE(coords_ptrs[i0 + i], "coords %d is null", i0 + i);
+      P.coords[i] = coords_ptrs[i0 + i];
+    }
+    P.B = B; P.N = N; P.L = L; P.r = radius; P.nT = nT;
+    for (int l = 0; l < k1b::RG_LEVELS; ++l) { P.h[l] = l < L ? H >> l : 0; P.w[l] = l < L ? W >> l : 0; }
+    P.ranges = reinterpret_cast<int2*>(ranges);
+    k1b::grad_ranges_kernel<<<dim3(nT, B), 256, 0, st>>>(P);
+    EZB_LAUNCH_OK();
+  }
+  return EZB_OK;
+}
+
+extern "C" int ezb_corr_grad_rezero(float* const* dlvl_ptrs, const int32_t* ranges, int B, int H, int W, int L, void* stream) {
+  EZB_REQUIRE(dlvl_ptrs && ranges, "null pointer");
+  EZB_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0 && L >= 1 && L <= k1b::RG_LEVELS, "bad shape B=%d H=%d W=%d L=%d", B, H, W, L);
+  LevelGeom g[EZB_MAX_LEVELS];
+  EZB_REQUIRE(pyramid_geom(H, W, L, EZB_F32, g), "feature map %dx%d too small for %d pyramid levels", H, W, L);
+  k1b::RezeroParams P;
+  for (int l = 0; l < k1b::RG_LEVELS; ++l) {
+    P.dlvl[l] = l < L ? dlvl_ptrs[l] : nullptr;
+    P.qstride[l] = l < L ? g[l].qstride : 0;
+    P.nl[l] = l < L ? g[l].h * g[l].w : 0;
+    if (l < L) EZB_REQUIRE(dlvl_ptrs[l] && (reinterpret_cast<uintptr_t>(dlvl_ptrs[l]) & 15) == 0, "level %d gradient pointer is null or misaligned", l);
+  }
+  P.ranges = reinterpret_cast<const int2*>(ranges);
+  P.N = H * W; P.L = L; P.nT = cdiv(P.N, 256);
+  k1b::grad_rezero_kernel<<<dim3(P.nT, B, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(P);
+  EZB_LAUNCH_OK();
   return EZB_OK;
 }

@@ -45,7 +45,15 @@ struct Params {
   int tile_base[MAXL + 1];  // mode 1: first grid tile of level l
   float alpha;
   float* out[MAXL];         // mode 0: out[0] = dfmap1 (B,C,N);  mode 1: out[l] = (B, C, Nl[l]) (out[0] = dfmap2)
+  // Optional support of the gradient pyramid (ezb_corr_grad_ranges): for every (pair, 256-query tile T, level l) the
+  // half-open range [t0, t1) of 256-target tiles outside which the rows of T are exact zeros.  mode 0 restricts its K
+  // loop to it, mode 1 skips the query blocks whose range misses its target tile.  NULL: dense.
+  const int2* ranges;       // [B][nT][MAXL]
+  int nT;
 };
+__device__ __forceinline__ int2 range_of(const Params& P, int b, int T, int l) {
+  return __ldg(P.ranges + ((long long)b * P.nT + T) * MAXL + l);
+}
 
 __device__ __forceinline__ uint64_t desc_mnmajor_sw128_base32(uint32_t smem_addr, uint32_t lbo_bytes) {
   // MN-major 32-bit operands only exist in the SWIZZLE_128B_BASE32B layout (cute::UMMA::Layout_MN_SW128_32B_Atom): an
@@ -101,12 +109,50 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_slot;
 
+  // k-blocks (BK = 32 targets / queries) this CTA's K loop visits at level l: [k0, k1), and in mode 1 only the blocks whose
+  // 256-query tile has this CTA's target tile in its range
+  auto k_bounds = [&](int l, int& k0, int& k1) {
+    const int nk = ((P.mode == 0 ? P.Nl[l] : P.N) + BK - 1) / BK;
+    k0 = 0;
+    k1 = nk;
+    if (P.ranges != nullptr && P.mode == 0) {
+      const int2 r = range_of(P, b, blockIdx.x, l);
+      k0 = min(nk, r.x * (256 / BK));
+      k1 = max(k0, min(nk, r.y * (256 / BK)));
+    }
+  };
+  const int my_tt = tile0 >> 8;  // mode 1: this CTA's 256-target tile of level lvl
+  auto k_live = [&](int l, int k) {
+    if (P.ranges == nullptr || P.mode == 0) return true;
+    const int2 r = range_of(P, b, (k * BK) >> 8, l);
+    return my_tt >= r.x && my_tt < r.y;
+  };
+  // does the K loop visit anything at all?  (an all-zero gradient support leaves the accumulators unwritten)
+  __shared__ int s_any;
+  if (threadIdx.x == 0) {
+    int any = 0;
+    for (int l = l_begin; l < l_end && !any; ++l) {
+      int k0, k1;
+      k_bounds(l, k0, k1);
+      if (P.ranges == nullptr || P.mode == 0) {
+        any = k1 > k0;
+      } else {
+        for (int k = k0; k < k1 && !any; k += 256 / BK) any = k_live(l, k);
+      }
+    }
+    s_any = any;
+  }
+  __syncthreads();
+  const bool any_k = s_any != 0;
+
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
     uint32_t stage = 0, phase = 0;
     for (int l = l_begin; l < l_end; ++l) {
-      const int nk = ((P.mode == 0 ? P.Nl[l] : P.N) + BK - 1) / BK;
-      for (int k = 0; k < nk; ++k) {
+      int k0, k1;
+      k_bounds(l, k0, k1);
+      for (int k = k0; k < k1; ++k) {
+        if (!k_live(l, k)) { k |= 256 / BK - 1; continue; }  // skip the whole 256-query tile
         ptx::mbar_wait(empty_bar(stage), phase ^ 1);
         const uint32_t sA = base + stage * STAGE_BYTES, sB = sA + 2 * A_BYTES;
         ptx::mbar_expect_tx(full_bar(stage), STAGE_BYTES);
@@ -132,8 +178,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     const uint32_t idesc = ptx::umma_idesc(/*tf32*/ 2, BM, BN) | (P.mode == 1 ? (1u << 16) : 0u);  // bit 16: B is MN-major
     uint32_t stage = 0, phase = 0, first = 1;
     for (int l = l_begin; l < l_end; ++l) {
-      const int nk = ((P.mode == 0 ? P.Nl[l] : P.N) + BK - 1) / BK;
-      for (int k = 0; k < nk; ++k) {
+      int k0, k1;
+      k_bounds(l, k0, k1);
+      for (int k = k0; k < k1; ++k) {
+        if (!k_live(l, k)) { k |= 256 / BK - 1; continue; }
         ptx::mbar_wait(full_bar(stage), phase);
         ptx::tc_fence_after();
         const uint32_t sA = base + stage * STAGE_BYTES, sB = sA + 2 * A_BYTES;
@@ -151,12 +199,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-    ptx::umma_commit(done_bar);
+    if (any_k) ptx::umma_commit(done_bar);
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int quad = warp & 3;
-    ptx::mbar_wait(done_bar, 0);
-    ptx::tc_fence_after();
+    if (any_k) {
+      ptx::mbar_wait(done_bar, 0);
+      ptx::tc_fence_after();
+    }
     const int ncol = P.mode == 0 ? P.N : P.Nl[lvl];  // row length of the output matrix
     float* out_b = P.out[lvl] + (long long)b * P.C * ncol;
 #pragma unroll 1
@@ -165,8 +215,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(tmem_base + h * BN + c0 + ((uint32_t)(quad * 32) << 16), r);
-        ptx::tmem_ld_wait();
+        if (any_k) {
+          ptx::tmem_ld_32x32b_x32(tmem_base + h * BN + c0 + ((uint32_t)(quad * 32) << 16), r);
+          ptx::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
         if (P.mode == 0) {
           // row = query, columns = channels: for a fixed channel the warp writes 32 consecutive queries
           const int q = tile0 + row;
@@ -243,7 +298,7 @@ size_t corr_bwd_tc_workspace_bytes(int B, int C, int H, int W, int L) {
 // dlvl[l]: gradient level l, row (b*N + q) at dlvl[l] + row*qstride[l], targets contiguous.  Computes dfmap1 and/or dfmap2.
 int corr_bwd_tc_launch(float* const* dlvl, const long long* qstride, const float* fmap1, const float* fmap2, int B, int C, int H,
                        int W, int L, float alpha, float* dfmap1, float* dfmap2, void* workspace, size_t workspace_bytes,
-                       cudaStream_t st) {
+                       const int32_t* ranges, cudaStream_t st) {
   using namespace k1btc;
   const int N = H * W;
   EZB_REQUIRE(L <= MAXL, "at most %d levels", MAXL);
@@ -278,6 +333,7 @@ int corr_bwd_tc_launch(float* const* dlvl, const long long* qstride, const float
     memset(&M, 0, sizeof(M));
     Params P;
     P.mode = mode; P.C = C; P.N = N; P.L = L; P.alpha = alpha;
+    P.ranges = reinterpret_cast<const int2*>(ranges); P.nT = cdiv(N, 256);
     int tiles = 0;
     for (int l = 0; l < MAXL; ++l) {
       P.Nl[l] = l < L ? Nl[l] : 0;

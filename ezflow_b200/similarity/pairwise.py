@@ -14,6 +14,7 @@ Deviations, all documented in DESIGN.md §6:
 """
 
 import ctypes
+import threading
 import os
 
 import torch
@@ -98,6 +99,20 @@ def grad_layout(H, W, L):
     return [(h[i], w[i], pitch[i], qs[i]) for i in range(L)]
 
 
+# Gradient pyramids (5.6 GB per 1080p pair) that are all-zero and free for the next backward pass.  With the ranged adjoint
+# (ezb_corr_grad_ranges) a pass dirties only the support of its lookup windows and zeroes exactly that again afterwards, so
+# the buffer set is handed from step to step instead of being memset (1 ms per pair) every time.  One set is kept, for the
+# most recent (device, stream, shape); release_gradient_pool() frees it.
+_GRAD_POOL = {}
+_GRAD_POOL_LOCK = threading.Lock()
+
+
+def release_gradient_pool():
+    """Frees the cached all-zero gradient pyramid (training with MutliScalePairwise4DCorr keeps one between steps)."""
+    with _GRAD_POOL_LOCK:
+        _GRAD_POOL.clear()
+
+
 class _PyramidState:
     """Device buffers of one pyramid plus (lazily) its fp32 gradient accumulator."""
 
@@ -115,6 +130,8 @@ class _PyramidState:
         self.grad_levels = None
         self.grad_layout = None
         self.grad_task = None  # autograd graph-task id of the backward pass that is filling grad_levels
+        self.lookup_coords = []  # coords of every differentiable lookup of this pyramid (forward order)
+        self.grad_ranges = None  # int32 support ranges of the gradient pyramid (ezb_corr_grad_ranges), or None: dense
 
     def build(self, ev_gemm=None):
         """ev_gemm: optional (start, end) raw cudaEvent handles recorded around the GEMM launch (bench only)."""
@@ -157,7 +174,10 @@ class _PyramidState:
             out[i0 : i0 + chunk] = self.pyr[block * ge + rec[(qq % 32).expand(-1, h * w), col[None, :].expand(len(bb), -1)]]
         return out.view(len(queries), 1, h, w)
 
-    def ensure_grad(self):
+    def _pool_key(self):
+        return (self.device.index, torch.cuda.current_stream(self.device).cuda_stream, self.B, self.H, self.W, self.L)
+
+    def ensure_grad(self, radius):
         # A backward pass that never reached _BuildFn.backward (it raised half-way) leaves its partial sums behind; they must
         # not leak into the next pass.  Every engine run has its own graph-task id.
         task = torch._C._current_graph_task_id() if hasattr(torch._C, "_current_graph_task_id") else None
@@ -166,10 +186,42 @@ class _PyramidState:
                 g.zero_()
         self.grad_task = task
         if self.grad_levels is None:
+            lib = _cabi.lib()
             self.grad_layout = grad_layout(self.H, self.W, self.L)
             rows = self.B * self.N
-            self.grad_levels = [torch.zeros(rows * qs, dtype=torch.float32, device=self.device) for (_, _, _, qs) in self.grad_layout]
+            ranged = bool(self.lookup_coords) and lib.ezb_corr_grad_ranges_supported(self.C, self.H, self.W, self.L) == 1
+            if ranged:
+                with _GRAD_POOL_LOCK:
+                    self.grad_levels = _GRAD_POOL.pop(self._pool_key(), None)
+            if self.grad_levels is None:
+                self.grad_levels = [torch.zeros(rows * qs, dtype=torch.float32, device=self.device) for (_, _, _, qs) in self.grad_layout]
+            if ranged:
+                # the support of this pass: the windows of every lookup recorded in the forward pass (a superset of the
+                # lookups whose backward will actually run)
+                n = ctypes.c_int64(0)
+                _cabi.check(lib.ezb_corr_grad_ranges_count(self.B, self.H, self.W, ctypes.byref(n)))
+                self.grad_ranges = torch.empty(n.value, dtype=torch.int32, device=self.device)
+                _cabi.check(
+                    lib.ezb_corr_grad_ranges(
+                        _cabi.ptr_array(self.lookup_coords), len(self.lookup_coords), self.B, self.H, self.W, self.L, int(radius),
+                        _cabi.ptr(self.grad_ranges), _cabi.stream_ptr(self.device),
+                    )
+                )
         return self.grad_levels
+
+    def release_grad(self):
+        """After the adjoint GEMMs: zero the support again and hand the (all-zero) buffers to the next pass."""
+        if self.grad_ranges is not None and self.grad_levels is not None:
+            _cabi.check(
+                _cabi.lib().ezb_corr_grad_rezero(
+                    _cabi.ptr_array(self.grad_levels), _cabi.ptr(self.grad_ranges), self.B, self.H, self.W, self.L,
+                    _cabi.stream_ptr(self.device),
+                )
+            )
+            with _GRAD_POOL_LOCK:
+                _GRAD_POOL.clear()  # one set at most
+                _GRAD_POOL[self._pool_key()] = self.grad_levels
+        self.grad_levels, self.grad_task, self.grad_ranges = None, None, None
 
 
 class _BuildFn(torch.autograd.Function):
@@ -196,12 +248,12 @@ class _BuildFn(torch.autograd.Function):
             _cabi.check(lib.ezb_corr_pyramid_bwd_workspace_bytes(st.B, st.C, st.H, st.W, st.L, ctypes.byref(nws)))
             ws = torch.empty(nws.value, dtype=torch.uint8, device=st.device) if nws.value else None
             _cabi.check(
-                lib.ezb_corr_pyramid_bwd(
+                lib.ezb_corr_pyramid_bwd_ex(
                     _cabi.ptr_array(st.grad_levels), _cabi.ptr(fmap1), _cabi.ptr(fmap2), st.B, st.C, st.H, st.W, st.L,
-                    _cabi.ptr(df1), _cabi.ptr(df2), _cabi.ptr(ws), nws.value, _cabi.stream_ptr(st.device),
+                    _cabi.ptr(df1), _cabi.ptr(df2), _cabi.ptr(ws), nws.value, _cabi.ptr(st.grad_ranges), _cabi.stream_ptr(st.device),
                 )
             )
-        st.grad_levels, st.grad_task = None, None  # consumed
+            st.release_grad()  # consumed
         return df1, df2, None
 
 
@@ -224,6 +276,8 @@ class _LookupFn(torch.autograd.Function):
     def forward(ctx, token, coords, state, radius):
         ctx.state, ctx.radius = state, radius
         ctx.save_for_backward(coords)
+        if token is not None and token.requires_grad:
+            state.lookup_coords.append(coords.detach())  # the support of the gradient pyramid (ensure_grad)
         return _lookup_forward(state, coords, radius)
 
     @staticmethod
@@ -235,7 +289,7 @@ class _LookupFn(torch.autograd.Function):
         gtoken = dcoords = None
         with torch.cuda.device(st.device):
             if ctx.needs_input_grad[0]:  # towards the feature maps: accumulate into the gradient pyramid (K3b)
-                glv = st.ensure_grad()
+                glv = st.ensure_grad(ctx.radius)
                 _cabi.check(
                     _cabi.lib().ezb_corr_lookup_bwd(
                         _cabi.ptr(dout), _cabi.ptr(coords), B, H, W, st.L, ctx.radius, _cabi.ptr_array(glv),

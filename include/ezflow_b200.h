@@ -145,6 +145,27 @@ int ezb_corr_pyramid_bwd(float* const* dlvl_ptrs /*[L] host*/, const float* fmap
                          int B, int C, int H, int W, int L, float* dfmap1, float* dfmap2,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* Support of the gradient pyramid.  The reference's autograd materialises the full gradient of the 4-D volume
+ * (pairwise.py:31-41 under .backward(): (B*N, 1, H, W) per level), although a query's gradient is non-zero only inside the
+ * windows its lookups read (pairwise.py:50-63: (2r+1)^2 taps per level and lookup, 12 lookups per RAFT step,
+ * models/raft.py:114-129) — about 1 % of a 1080p pyramid.
+ *   ezb_corr_grad_ranges        ranges[b][T][l] = {t0, t1} (int32 pairs, l < 4; ezb_corr_grad_ranges_count int32 in all):
+ *                               the 256-target tiles [t0, t1) of level l that a window of any query of the 256-query tile T
+ *                               can touch, over the coords of all `n_lookups` lookups of the step ((B,2,H,W) each).
+ *   ezb_corr_pyramid_bwd_ex     ezb_corr_pyramid_bwd that skips everything outside `ranges` (NULL: dense).  Only with the
+ *                               tensor-core adjoint (ezb_corr_grad_ranges_supported() == 1), else EZB_ERR_UNSUPPORTED.
+ *   ezb_corr_grad_rezero        zeroes the ranges again: gradient levels that were all-zero before the step's
+ *                               ezb_corr_lookup_bwd calls are all-zero afterwards, without a memset of the whole pyramid. */
+int ezb_corr_grad_ranges_supported(int C, int H, int W, int L);
+int ezb_corr_grad_ranges_count(int B, int H, int W, int64_t* n_int32 /*host*/);
+int ezb_corr_grad_ranges(const float* const* coords_ptrs /*[n_lookups] host array of device pointers*/, int n_lookups,
+                         int B, int H, int W, int L, int radius, int32_t* ranges /*device, written*/, void* stream);
+int ezb_corr_pyramid_bwd_ex(float* const* dlvl_ptrs /*[L] host*/, const float* fmap1, const float* fmap2,
+                            int B, int C, int H, int W, int L, float* dfmap1, float* dfmap2,
+                            void* workspace, size_t workspace_bytes, const int32_t* ranges /*device or NULL*/, void* stream);
+int ezb_corr_grad_rezero(float* const* dlvl_ptrs /*[L] host*/, const int32_t* ranges /*device*/, int B, int H, int W, int L,
+                         void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Local displacement-window correlation (K4 / K4b), also CorrelationLayer and the engine of K6
  *   replaces iter_spatial_correlation_sample  ezflow/similarity/correlation/sampler.py:29-129

@@ -4,6 +4,8 @@ class, against (a) golden vectors produced by the unmodified reference and (b) t
 Tolerances (north_star): correlation volumes <= 1e-3 relative error (fp16 tensor-core contraction vs the
 reference's fp32); lookups inherit that bound."""
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -377,3 +379,81 @@ def test_aborted_backward_leaves_no_stale_gradient():
     h1, h2 = grads(True)
     assert_close(h1, g1, 1e-6, "df1 after an aborted pass")
     assert_close(h2, g2, 1e-6, "df2 after an aborted pass")
+
+
+def _train_like_step(E, f1n, f2n, coords_list, douts, L, r):
+    f1, f2 = to_gpu(f1n, True), to_gpu(f2n, True)
+    fn = E.MutliScalePairwise4DCorr(f1, f2, num_levels=L, corr_radius=r)
+    loss = 0
+    for c, d in zip(coords_list, douts):
+        loss = loss + (fn(to_gpu(c)) * to_gpu(d)).sum()
+    loss.backward()
+    return f1.grad.clone(), f2.grad.clone()
+
+
+def test_ranged_adjoint_matches_dense_and_oracle():
+    """The adjoint restricted to the support of the lookup windows (ezb_corr_grad_ranges + ezb_corr_pyramid_bwd_ex +
+    ezb_corr_grad_rezero) against the dense adjoint (EZB_BWD_DENSE=1) and the oracle: several lookups whose windows wander
+    (incl. partly and wholly outside the levels), H*W spanning several 256-query / 256-target tiles, two pairs."""
+    import ezflow_b200 as E
+    from ezflow_b200.similarity import pairwise as PW
+    from oracle import similarity_oracle as O
+
+    rng = np.random.default_rng(77)
+    B, C, H, W, L, r = 2, 48, 28, 36, 3, 3  # N = 1008: four 256-query tiles, the last one ragged
+    f1n = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    f2n = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    grid = O.coords_grid(B, H, W)
+    coords_list = [grid + rng.normal(0, 1.5 + 2 * k, (B, 2, H, W)).astype(np.float32) for k in range(4)]
+    coords_list[3][1, :, :5, :] += 100.0  # some windows entirely outside every level
+    douts = [rng.standard_normal((B, L * (2 * r + 1) ** 2, H, W)).astype(np.float32) for _ in coords_list]
+    shapes = [(H >> l, W >> l) for l in range(L)]
+    dpyr = None
+    for c, d in zip(coords_list, douts):
+        g = O.corr_lookup_bwd(shapes, c, d, r)
+        dpyr = g if dpyr is None else [a + b for a, b in zip(dpyr, g)]
+    d1, d2 = O.corr_pyramid_bwd(f1n, f2n, dpyr)
+
+    E.release_gradient_pool()
+    r1, r2 = _train_like_step(E, f1n, f2n, coords_list, douts, L, r)
+    assert len(PW._GRAD_POOL) == 1, "the ranged path should have handed its gradient pyramid to the pool"
+    for lv in next(iter(PW._GRAD_POOL.values())):
+        assert float(lv.abs().max()) == 0.0, "the pooled gradient pyramid must be all-zero again"
+    os.environ["EZB_BWD_DENSE"] = "1"
+    try:
+        e1, e2 = _train_like_step(E, f1n, f2n, coords_list, douts, L, r)
+    finally:
+        del os.environ["EZB_BWD_DENSE"]
+    assert_close(r1, d1, GRAD_TOL, "ranged dfmap1 vs oracle")
+    assert_close(r2, d2, GRAD_TOL, "ranged dfmap2 vs oracle")
+    assert_close(r1, e1, 1e-6, "ranged vs dense dfmap1")  # same products in the same order, only all-zero blocks skipped
+    assert_close(r2, e2, 1e-6, "ranged vs dense dfmap2")
+
+
+def test_ranged_adjoint_pool_reuse_across_steps():
+    """Step 2 reuses step 1's gradient pyramid from the pool: different windows, no residue; a pass whose lookups all fall
+    outside the levels yields exact zeros."""
+    import ezflow_b200 as E
+    from oracle import similarity_oracle as O
+
+    rng = np.random.default_rng(5)
+    B, C, H, W, L, r = 1, 32, 24, 32, 2, 4
+    f1n = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    f2n = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    grid = O.coords_grid(B, H, W)
+    shapes = [(H >> l, W >> l) for l in range(L)]
+    E.release_gradient_pool()
+    for step, shift in enumerate([(-6.3, 2.2), (7.1, -4.6), (0.4, 0.2)]):
+        c = grid.copy()
+        c[:, 0] += shift[0]
+        c[:, 1] += shift[1]
+        d = rng.standard_normal((B, L * (2 * r + 1) ** 2, H, W)).astype(np.float32)
+        g1, g2 = _train_like_step(E, f1n, f2n, [c], [d], L, r)
+        d1, d2 = O.corr_pyramid_bwd(f1n, f2n, O.corr_lookup_bwd(shapes, c, d, r))
+        assert_close(g1, d1, GRAD_TOL, f"step {step} dfmap1")
+        assert_close(g2, d2, GRAD_TOL, f"step {step} dfmap2")
+    far = grid + 1000.0
+    d = rng.standard_normal((B, L * (2 * r + 1) ** 2, H, W)).astype(np.float32)
+    g1, g2 = _train_like_step(E, f1n, f2n, [far], [d], L, r)
+    assert float(g1.abs().max()) == 0.0 and float(g2.abs().max()) == 0.0
+    E.release_gradient_pool()
