@@ -17,6 +17,9 @@
 // One CTA owns a 256x256 output tile and runs the whole K loop (N/32 k-blocks of 64 KB through a 3-stage TMA ring);
 // the two accumulators fill TMEM (512 columns).  HBM-bound: g is read exactly once per GEMM.
 #include "ezb_common.cuh"
+
+#include <algorithm>
+#include <cstdlib>
 #include "ezb_ptx.cuh"
 #include "ezb_tma.cuh"
 
@@ -42,7 +45,10 @@ struct Params {
   int mode;  // 0: df1 (rows = queries, cols = channels)   1: df2 (rows = channels, cols = targets of one level)
   int C, N, L;
   int Nl[MAXL];             // targets per level
-  int tile_base[MAXL + 1];  // mode 1: first grid tile of level l
+  int tile_base[MAXL + 1];  // mode 1: first grid tile of level l (a level has cdiv(Nl, 256) * split[l] of them)
+  int split[MAXL];          // mode 1: CTAs sharing one target tile of level l, each with a slice of the query (K) range; their
+                            // partial sums go to out[l] + slice * B * C * Nl[l] and are added by reduce_slices_kernel.  The coarse
+                            // levels have few target tiles with (under ranges) long K loops: without the split they are the tail.
   float alpha;
   float* out[MAXL];         // mode 0: out[0] = dfmap1 (B,C,N);  mode 1: out[l] = (B, C, Nl[l]) (out[0] = dfmap2)
   // Optional support of the gradient pyramid (ezb_corr_grad_ranges): for every (pair, 256-query tile T, level l) the
@@ -84,7 +90,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   int lvl = 0;  // mode 1: the level this tile belongs to
   if (P.mode == 1)
     while (lvl + 1 < P.L && (int)blockIdx.x >= P.tile_base[lvl + 1]) ++lvl;
-  const int tile0 = (P.mode == 0 ? blockIdx.x : blockIdx.x - P.tile_base[lvl]) * 256;  // first query / first target
+  const int lt = P.mode == 0 ? (int)blockIdx.x : (int)blockIdx.x - P.tile_base[lvl];     // tile (x split slice) inside the level
+  const int nsplit = P.mode == 0 ? 1 : P.split[lvl], slice = lt % nsplit;
+  const int tile0 = (lt / nsplit) * 256;  // first query / first target
   // K loop: mode 0 walks the targets of every level, mode 1 the queries
   const int l_begin = P.mode == 0 ? 0 : lvl, l_end = P.mode == 0 ? P.L : lvl + 1;
 
@@ -119,6 +127,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       const int2 r = range_of(P, b, blockIdx.x, l);
       k0 = min(nk, r.x * (256 / BK));
       k1 = max(k0, min(nk, r.y * (256 / BK)));
+    }
+    if (P.mode == 1 && nsplit > 1) {  // this slice's 256-query tiles
+      k0 = min(nk, (int)((long long)P.nT * slice / nsplit) * (256 / BK));
+      k1 = min(nk, (int)((long long)P.nT * (slice + 1) / nsplit) * (256 / BK));
     }
   };
   const int my_tt = tile0 >> 8;  // mode 1: this CTA's 256-target tile of level lvl
@@ -208,7 +220,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       ptx::tc_fence_after();
     }
     const int ncol = P.mode == 0 ? P.N : P.Nl[lvl];  // row length of the output matrix
-    float* out_b = P.out[lvl] + (long long)b * P.C * ncol;
+    float* out_b = P.out[lvl] + ((long long)slice * gridDim.y + b) * P.C * ncol;
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
       const int row = h * BM + quad * 32 + lane;
@@ -255,6 +267,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   if (warp == 2) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// dB_l[0][i] += dB_l[1][i] + ... + dB_l[n - 1][i]: the K slices of a coarse level, added in a fixed order (deterministic)
+__global__ void __launch_bounds__(256) reduce_slices_kernel(float* __restrict__ p, long long part, int n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < part; i += (long long)gridDim.x * blockDim.x) {
+    float sum = p[i];
+    for (int sl = 1; sl < n; ++sl) sum += __ldg(p + sl * part + i);
+    p[i] = sum;
+  }
+}
+
 // dfmap2[b,c,y,x] += sum_{l>=1} dB_l[b,c,y>>l,x>>l] / 4^l   (adjoint of l floor 2x2 average pools; pixels outside the
 // pooled area of a level get nothing from it)
 struct UnpoolParams {
@@ -284,13 +305,19 @@ __global__ void __launch_bounds__(256) unpool_add_kernel(float* __restrict__ df2
 // true when the tcgen05 path covers this problem (TMA needs 16-byte-aligned row strides)
 bool corr_bwd_tc_supported(int C, int N) { return C <= 256 && (N % 4) == 0; }
 
-// scratch: pooled fmap2 levels (padded rows) and the per-level dB matrices
+// K-split of the df2 GEMM per level: 1, 4, 16, 32 slices (at most one per 256-query tile)
+static int df2_split(int l, int N) {
+  static const bool off = getenv("EZB_BWD_NOSPLIT") != nullptr;  // A/B switch
+  return (l == 0 || off) ? 1 : std::max(1, std::min(std::min(1 << (2 * l), 32), cdiv(N, 256)));
+}
+
+// scratch: pooled fmap2 levels (padded rows) and the per-level dB matrices (one per K slice)
 size_t corr_bwd_tc_workspace_bytes(int B, int C, int H, int W, int L) {
   size_t n = 1024;
   for (int l = 1; l < L; ++l) {
     const long long nl = (long long)(H >> l) * (W >> l);
-    n += (size_t)B * C * round_up((int)nl, 4) * 4 + 256;  // pool_l(f2)
-    n += (size_t)B * C * nl * 4 + 256;                     // dB_l
+    n += (size_t)B * C * round_up((int)nl, 4) * 4 + 256;          // pool_l(f2)
+    n += (size_t)df2_split(l, H * W) * B * C * nl * 4 + 256;     // dB_l partial sums
   }
   return n;
 }
@@ -320,7 +347,7 @@ int corr_bwd_tc_launch(float* const* dlvl, const long long* qstride, const float
   f2l[0] = fmap2; Npad[0] = N; dB[0] = dfmap2;
   for (int l = 1; l < L; ++l) {
     float* p = take((size_t)B * C * Npad[l] * 4);
-    dB[l] = take((size_t)B * C * Nl[l] * 4);
+    dB[l] = take((size_t)df2_split(l, N) * B * C * Nl[l] * 4);
     if (dfmap1) {
       if (int r = prep::launch_pool2x2(f2l[l - 1], p, (long long)B * C, hl[l - 1], wl[l - 1], Npad[l - 1], hl[l], wl[l], Npad[l], st)) return r;
     }
@@ -338,7 +365,8 @@ int corr_bwd_tc_launch(float* const* dlvl, const long long* qstride, const float
     for (int l = 0; l < MAXL; ++l) {
       P.Nl[l] = l < L ? Nl[l] : 0;
       P.tile_base[l] = tiles;
-      if (l < L) tiles += cdiv(Nl[l], 256);
+      P.split[l] = l < L ? df2_split(l, N) : 1;
+      if (l < L) tiles += cdiv(Nl[l], 256) * (mode == 1 ? P.split[l] : 1);
       P.out[l] = mode == 0 ? dfmap1 : (l < L ? dB[l] : nullptr);
     }
     P.tile_base[MAXL] = tiles;
@@ -365,6 +393,13 @@ int corr_bwd_tc_launch(float* const* dlvl, const long long* qstride, const float
     EZB_LAUNCH_OK();
     if (mode == 1 && L > 1) {
       UnpoolParams U;
+      for (int l = 1; l < L; ++l) {  // the K slices of the coarse levels -> slice 0
+        const int ns = df2_split(l, N);
+        if (ns == 1) continue;
+        const long long part = (long long)B * C * Nl[l];
+        reduce_slices_kernel<<<(int)std::min<long long>(cdiv64(part, 256), 148 * 8), 256, 0, st>>>(dB[l], part, ns);
+        EZB_LAUNCH_OK();
+      }
       for (int l = 0; l < MAXL; ++l) { U.dB[l] = l < L ? dB[l] : nullptr; U.h[l] = l < L ? hl[l] : 0; U.w[l] = l < L ? wl[l] : 0; }
       U.L = L; U.H = H; U.W = W; U.planes = (long long)B * C;
       const long long total = U.planes * N;
