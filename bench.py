@@ -862,7 +862,7 @@ def run_b200(args):
                 "gemm_share_of_step": (sum(gemm_ms) / ms) if ms > 0 else None,
             },
             "clocks": clocks,
-            "gpu_launches": args.steps * (P // MB) * (4 + (L - 1) + 1 + ITERS),  # absmax, scales, convert, pools, pack, gemm + lookups
+            "gpu_launches": args.steps * (P // MB) * (5 + ITERS),  # absmax, scales, convert, pool+pack, gemm + lookups (profiles/r02_launches.txt)
         }
         if e2e:
             line["e2e"] = {
