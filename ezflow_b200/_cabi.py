@@ -47,6 +47,7 @@ _SIGNATURES = {
     "ezb_lookup_conv_pack_weights": ([c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp], c_int),
     "ezb_corr_lookup_conv1x1_fwd": ([c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp], c_int),
     "ezb_corr_lookup_bwd": ([c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, _P(c_vp), c_vp], c_int),
+    "ezb_corr_lookup_bwd_multi": ([_P(c_vp), _P(c_vp), c_int, c_int, c_int, c_int, c_int, c_int, _P(c_vp), c_vp], c_int),
     "ezb_corr_lookup_bwd_coords": ([c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp], c_int),
     "ezb_corr_pyramid_bwd_workspace_bytes": ([c_int, c_int, c_int, c_int, c_int, _P(c_sz)], c_int),
     "ezb_corr_pyramid_bwd": ([_P(c_vp), c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_sz, c_vp], c_int),

@@ -16,6 +16,9 @@
 // HBM-bound: algorithmic bytes per query = L*[(2r+2)^2*es + (2r+1)^2*4] + 8  (SURVEY.md §8d).
 #include "ezb_common.cuh"
 
+#include <algorithm>
+#include <climits>
+
 #include <cstdlib>
 #include <type_traits>
 
@@ -384,6 +387,138 @@ __global__ void __launch_bounds__(NTHREADS) corr_lookup_bwd_kernel(const LookupB
   }
 }
 
+
+// ------------------------------------------------------------------------------------ K3b, all lookups of a step at once
+// RAFT runs 12 lookups per step through one pyramid (models/raft.py:114-129) and, once it converges, their windows of a query
+// largely overlap: 12 launches of corr_lookup_bwd_kernel read-modify-write nearly the same DRAM lines 12 times (~1.3 lines per
+// window row and launch: what bounds that kernel).  Here a block owns 16 queries for ALL lookups: per (query, level) a
+// MT_H x MT_W fp32 tile in shared memory is placed where the lookups' windows cluster; every lookup's window
+// gradients are added into the tile (same sliding-row arithmetic as above, dout staged per lookup), and the tile is added to
+// HBM once, skipping untouched 16-byte slots.  The tile is centred on the window of the first lookup passed (the caller puts
+// the most converged iterate there); a lookup whose window does not fit inside it (early iterations, scattered coordinates)
+// takes the per-lookup path (atomics) inside the same kernel, so any coordinates are handled.
+constexpr int MQB = 16, MT_H = 16, MT_W = 20, M_MAXLK = 16, M_MAXL = 4;
+struct LookupBwdMultiParams {
+  float* dlvl[M_MAXL];
+  long long qstride[M_MAXL];
+  int h[M_MAXL], w[M_MAXL], pitch[M_MAXL];
+  const float* dout[M_MAXLK];    // (B, L*K*K, N) each
+  const float* coords[M_MAXLK];  // (B,2,N) each
+  int n, B, N, L, r;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 2) corr_lookup_bwd_multi_kernel(const LookupBwdMultiParams P) {
+  extern __shared__ __align__(16) float sm[];
+  const int r = P.r, D = 2 * r + 2, K = 2 * r + 1, KK = K * K, nch = P.L * KK;
+  const int dstride = nch | 1;  // dout values per query (odd stride)
+  float* s_d = sm;                                                   // [MQB][dstride]
+  float* tiles = sm + ((MQB * dstride + 3) & ~3);                    // [MQB * L][MT_H * MT_W]
+  int* s_org = reinterpret_cast<int*>(tiles + MQB * P.L * MT_H * MT_W);  // [MQB * L][3]: ox, oy, compact
+  const int b = blockIdx.y, q0 = blockIdx.x * MQB, tid = threadIdx.x;
+
+  auto window_origin = [&](int k, int q, int l, int& xs, int& ys, float& fx, float& fy) {
+    const float inv = 1.0f / (float)(1 << l);
+    const float* c = P.coords[k] + (long long)b * 2 * P.N;
+    const float cx = __ldg(c + q) * inv, cy = __ldg(c + P.N + q) * inv;
+    fx = cx - floorf(cx);
+    fy = cy - floorf(cy);
+    xs = max(-D, min(P.w[l], float_floor_to_int_clamped(cx, -(1 << 24), 1 << 24) - r));
+    ys = max(-D, min(P.h[l], float_floor_to_int_clamped(cy, -(1 << 24), 1 << 24) - r));
+    return xs + D > 0 && xs < P.w[l] && ys + D > 0 && ys < P.h[l];  // the window overlaps the level
+  };
+
+  // ---- phase 0: centre the tile of every (query, level) on the window of lookup 0 (the caller passes the most converged
+  //      iterate first: the other late iterations cluster around it, the early ones take the per-lookup path); zero the tiles
+  if (tid < MQB * P.L) {
+    const int ql = tid % MQB, l = tid / MQB, q = q0 + ql;
+    int xs = 0, ys = 0;
+    float fx, fy;
+    const bool any = q < P.N && P.n > 0 && window_origin(0, q, l, xs, ys, fx, fy);
+    s_org[3 * tid] = any ? ((xs - (MT_W - D) / 2) & ~3) : INT_MIN / 2;  // 16-byte aligned columns (floor, also for negatives)
+    s_org[3 * tid + 1] = any ? ys - (MT_H - D) / 2 : INT_MIN / 2;      // no tile: nothing fits
+    s_org[3 * tid + 2] = any ? 1 : 0;
+  }
+  for (int i = tid; i < MQB * P.L * MT_H * MT_W / 4; i += NTHREADS) reinterpret_cast<float4*>(tiles)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int k = 0; k < P.n; ++k) {
+    __syncthreads();  // phase 0 / the previous lookup's readers of s_d are done
+    // ---- stage dout of lookup k: consecutive threads take consecutive queries (64-byte segments); asynchronous 4-byte copies,
+    //      all ~20 per thread in flight at once (one memory round trip per lookup)
+    {
+      const float* src = P.dout[k] + (long long)b * nch * P.N + q0;
+      const int ql = tid % MQB, c0 = tid / MQB, cstep = NTHREADS / MQB;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_d + ql * dstride);
+      if (q0 + ql < P.N) {
+        for (int c = c0; c < nch; c += cstep)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * c), "l"(src + (long long)c * P.N + ql) : "memory");
+      } else {
+        for (int c = c0; c < nch; c += cstep) s_d[ql * dstride + c] = 0.f;
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    // ---- thread -> (level, window row Y, query)
+    for (int idx = tid; idx < MQB * P.L * D; idx += NTHREADS) {
+      const int ql = idx % MQB, ly = idx / MQB, l = ly / D, Y = ly - l * D;
+      const int q = q0 + ql;
+      if (q >= P.N) continue;
+      int xs, ys;
+      float fx, fy;
+      if (!window_origin(k, q, l, xs, ys, fx, fy)) continue;
+      const int hl = P.h[l], wl = P.w[l];
+      const int yy = ys + Y;
+      // out(i,j) touches window (row j+a, col i+c) with weight wy[a]*wx[c]  =>  row Y collects j = Y (a=0) and j = Y-1 (a=1)
+      const float wy0 = (Y < K) ? 1.f - fy : 0.f, wy1 = (Y >= 1) ? fy : 0.f;
+      const float* d0 = s_d + ql * dstride + l * KK + min(Y, K - 1);  // + i*K: dout(i, j=Y)
+      const float* d1 = s_d + ql * dstride + l * KK + max(Y - 1, 0);  // + i*K: dout(i, j=Y-1)
+      float prev = 0.f;  // vertically combined dout of window column X-1
+      auto next = [&](int X) {  // gradient of window element (Y, X); X must advance by one per call
+        const float cur = (X < K) ? wy0 * d0[X * K] + wy1 * d1[X * K] : 0.f;
+        const float g = (1.f - fx) * cur + fx * prev;
+        prev = cur;
+        return g;
+      };
+      const int* org = s_org + 3 * (l * MQB + ql);
+      if (xs >= org[0] && xs + D <= org[0] + MT_W && ys >= org[1] && ys + D <= org[1] + MT_H) {  // this lookup's window is inside the tile
+        float* t = tiles + (l * MQB + ql) * (MT_H * MT_W) + (yy - org[1]) * MT_W + (xs - org[0]);
+        for (int X = 0; X < D; ++X) t[X] += next(X);  // this (query, level, row) belongs to this thread: no conflicts
+      } else {
+        if (yy < 0 || yy >= hl) continue;
+        float* row = P.dlvl[l] + ((long long)b * P.N + q) * P.qstride[l] + (long long)yy * P.pitch[l] + xs;
+        for (int X = 0; X < D; ++X) {
+          const float g = next(X);
+          if (xs + X >= 0 && xs + X < wl) atomicAdd(row + X, g);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- flush: every touched 16-byte slot of every compact tile is added to HBM once
+  constexpr int SLOTS = MT_W / 4;
+  for (int idx = tid; idx < MQB * P.L * MT_H * SLOTS; idx += NTHREADS) {
+    const int sl = idx % SLOTS, row = (idx / SLOTS) % MT_H, item = idx / (SLOTS * MT_H);
+    const int ql = item % MQB, l = item / MQB, q = q0 + ql;
+    const int* org = s_org + 3 * item;
+    if (q >= P.N || !org[2]) continue;
+    const int y = org[1] + row, x = org[0] + 4 * sl;
+    if (y < 0 || y >= P.h[l] || x + 3 < 0 || x >= P.w[l]) continue;
+    const float4 v = *reinterpret_cast<const float4*>(tiles + item * (MT_H * MT_W) + row * MT_W + 4 * sl);
+    if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
+    float* dst = P.dlvl[l] + ((long long)b * P.N + q) * P.qstride[l] + (long long)y * P.pitch[l] + x;
+    if (x >= 0 && x + 3 < P.w[l] && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      float4 o = *reinterpret_cast<const float4*>(dst);  // a map row of a query is touched by exactly one thread per launch
+      o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+      *reinterpret_cast<float4*>(dst) = o;
+    } else {
+      const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (x + u >= 0 && x + u < P.w[l] && e[u] != 0.f) atomicAdd(dst + u, e[u]);
+    }
+  }
+}
+
 }  // namespace k3
 }  // namespace ezb
 
@@ -502,5 +637,47 @@ extern "C" int ezb_corr_lookup_bwd(const float* dout, const float* coords, int B
   EZB_CUDA_OK(cudaFuncSetAttribute(k3::corr_lookup_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k3::corr_lookup_bwd_kernel<<<dim3(cdiv(N, k3::QB), B), k3::NTHREADS, smem, st>>>(P);
   EZB_LAUNCH_OK();
+  return EZB_OK;
+}
+
+extern "C" int ezb_corr_lookup_bwd_multi(const float* const* dout_ptrs, const float* const* coords_ptrs, int n_lookups, int B, int H, int W,
+                                         int L, int radius, float* const* dlvl_ptrs, void* stream) {
+  EZB_REQUIRE(dout_ptrs && coords_ptrs && dlvl_ptrs && n_lookups >= 0, "bad arguments");
+  EZB_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0 && L >= 1 && L <= EZB_MAX_LEVELS, "bad shape B=%d H=%d W=%d L=%d", B, H, W, L);
+  EZB_REQUIRE(radius >= 0 && radius <= k3::MAX_RADIUS, "corr_radius %d outside [0,%d]", radius, k3::MAX_RADIUS);
+  const int K = 2 * radius + 1, D = K + 1;
+  // tiles hold windows of at most 10 x 10 (radius <= 4) with room for a few pixels of drift; otherwise one launch per lookup
+  if (L > k3::M_MAXL || D > 10 || getenv("EZB_LOOKUP_BWD_SEPARATE") != nullptr) {
+    for (int k = 0; k < n_lookups; ++k)
+      if (int rc = ezb_corr_lookup_bwd(dout_ptrs[k], coords_ptrs[k], B, H, W, L, radius, dlvl_ptrs, stream)) return rc;
+    return EZB_OK;
+  }
+  LevelGeom g[EZB_MAX_LEVELS];
+  EZB_REQUIRE(pyramid_geom(H, W, L, EZB_F32, g), "feature map %dx%d too small for %d pyramid levels", H, W, L);
+  k3::LookupBwdMultiParams P;
+  const int N = H * W;
+  for (int l = 0; l < k3::M_MAXL; ++l) {
+    if (l < L) EZB_REQUIRE(dlvl_ptrs[l], "level %d gradient pointer is null", l);
+    P.dlvl[l] = l < L ? dlvl_ptrs[l] : nullptr;
+    P.h[l] = l < L ? g[l].h : 0;
+    P.w[l] = l < L ? g[l].w : 0;
+    P.pitch[l] = l < L ? g[l].pitch : 0;
+    P.qstride[l] = l < L ? g[l].qstride : 0;
+  }
+  P.B = B; P.N = N; P.L = L; P.r = radius;
+  const size_t smem = ((size_t)((k3::MQB * ((L * K * K) | 1) + 3) & ~3) + (size_t)k3::MQB * L * k3::MT_H * k3::MT_W) * sizeof(float) +
+                      (size_t)k3::MQB * L * 3 * sizeof(int);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  EZB_CUDA_OK(cudaFuncSetAttribute(k3::corr_lookup_bwd_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int k0 = 0; k0 < n_lookups; k0 += k3::M_MAXLK) {
+    P.n = std::min(k3::M_MAXLK, n_lookups - k0);
+    for (int k = 0; k < P.n; ++k) {
+      EZB_REQUIRE(dout_ptrs[k0 + k] && coords_ptrs[k0 + k], "lookup %d: null pointer", k0 + k);
+      P.dout[k] = dout_ptrs[k0 + k];
+      P.coords[k] = coords_ptrs[k0 + k];
+    }
+    k3::corr_lookup_bwd_multi_kernel<<<dim3(cdiv(N, k3::MQB), B), k3::NTHREADS, smem, st>>>(P);
+    EZB_LAUNCH_OK();
+  }
   return EZB_OK;
 }

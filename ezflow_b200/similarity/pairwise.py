@@ -131,6 +131,8 @@ class _PyramidState:
         self.grad_layout = None
         self.grad_task = None  # autograd graph-task id of the backward pass that is filling grad_levels
         self.lookup_coords = []  # coords of every differentiable lookup of this pyramid (forward order)
+        self.pending = []  # (dout, coords) of the lookups whose adjoint waits for _BuildFn.backward (ezb_corr_lookup_bwd_multi)
+        self.pending_task = None
         self.grad_ranges = None  # int32 support ranges of the gradient pyramid (ezb_corr_grad_ranges), or None: dense
 
     def build(self, ev_gemm=None):
@@ -238,12 +240,24 @@ class _BuildFn(torch.autograd.Function):
     def backward(ctx, _gtoken):
         st = ctx.state
         fmap1, fmap2 = ctx.saved_tensors
-        if st.grad_levels is None:  # no lookup contributed a gradient
+        task = torch._C._current_graph_task_id() if hasattr(torch._C, "_current_graph_task_id") else None
+        pending = st.pending if task == st.pending_task else []
+        st.pending, st.pending_task = [], None
+        if not pending and st.grad_levels is None:  # no lookup contributed a gradient
             return torch.zeros_like(fmap1), torch.zeros_like(fmap2), None
         df1 = torch.empty_like(fmap1)
         df2 = torch.empty_like(fmap2)
         with torch.cuda.device(st.device):
             lib = _cabi.lib()
+            if pending:  # K3b for all lookups of the pass (one radius per object)
+                glv = st.ensure_grad(pending[0][2])
+                _cabi.check(
+                    lib.ezb_corr_lookup_bwd_multi(
+                        _cabi.ptr_array([p[0] for p in pending]), _cabi.ptr_array([p[1] for p in pending]), len(pending),
+                        st.B, st.H, st.W, st.L, pending[0][2], _cabi.ptr_array(glv), _cabi.stream_ptr(st.device),
+                    )
+                )
+                del pending
             nws = ctypes.c_size_t(0)
             _cabi.check(lib.ezb_corr_pyramid_bwd_workspace_bytes(st.B, st.C, st.H, st.W, st.L, ctypes.byref(nws)))
             ws = torch.empty(nws.value, dtype=torch.uint8, device=st.device) if nws.value else None
@@ -288,14 +302,15 @@ class _LookupFn(torch.autograd.Function):
         B, _, H, W = coords.shape
         gtoken = dcoords = None
         with torch.cuda.device(st.device):
-            if ctx.needs_input_grad[0]:  # towards the feature maps: accumulate into the gradient pyramid (K3b)
-                glv = st.ensure_grad(ctx.radius)
-                _cabi.check(
-                    _cabi.lib().ezb_corr_lookup_bwd(
-                        _cabi.ptr(dout), _cabi.ptr(coords), B, H, W, st.L, ctx.radius, _cabi.ptr_array(glv),
-                        _cabi.stream_ptr(st.device),
-                    )
-                )
+            if ctx.needs_input_grad[0]:  # towards the feature maps: the lookup adjoint (K3b) into the gradient pyramid
+                # Deferred: the build node runs after every lookup of the pass and adds all of them in one launch, so that
+                # overlapping windows of a query meet in shared memory instead of in HBM.  A pass that never got that far
+                # (it raised) must not leak its entries into the next one: every engine run has its own graph-task id.
+                task = torch._C._current_graph_task_id() if hasattr(torch._C, "_current_graph_task_id") else None
+                if st.pending and task != st.pending_task:
+                    st.pending.clear()
+                st.pending_task = task
+                st.pending.append((dout, coords, ctx.radius))
                 gtoken = torch.zeros((), dtype=torch.float32, device=dout.device)
             if ctx.needs_input_grad[1]:  # towards coords (RAFT detaches them, models/raft.py:115; the reference's op has it)
                 dcoords = torch.empty_like(coords)

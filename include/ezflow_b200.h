@@ -128,6 +128,14 @@ int ezb_corr_grad_layout(int H, int W, int L, int* h, int* w, int* pitch, int64_
 int ezb_corr_lookup_bwd(const float* dout /* (B, L*(2r+1)^2, H, W) */, const float* coords,
                         int B, int H, int W, int L, int radius,
                         float* const* dlvl_ptrs /*[L] host*/, void* stream);
+/* The same for ALL lookups of a step at once (RAFT: 12 per step, models/raft.py:114-129): dlvl += sum_k adjoint(dout_k, coords_k).
+ * Per (query, level) the window gradients of the lookups that fall inside a 16 x 20 tile centred on the window of lookup 0
+ * (pass the most converged iterate first) are summed in shared memory and each DRAM line is read-modify-written once instead
+ * of once per lookup; windows outside the tile (and radius > 4 or L > 4 altogether) take the per-lookup path, so any
+ * coordinates and any order are valid. */
+int ezb_corr_lookup_bwd_multi(const float* const* dout_ptrs /*[n] host array of device pointers*/,
+                              const float* const* coords_ptrs /*[n] host*/, int n_lookups, int B, int H, int W, int L, int radius,
+                              float* const* dlvl_ptrs /*[L] host*/, void* stream);
 /* Adjoint of ezb_corr_lookup_fwd w.r.t. coords (autograd of `coords / 2**i`, bilinear_sampler's normalisation and
  * grid_sample's grid argument, pairwise.py:50-67, utils/resampling.py:71-83): dcoords (B,2,H,W) fp32 is overwritten.
  * RAFT detaches coords (models/raft.py:115); the entry point exists for callers that do not. */

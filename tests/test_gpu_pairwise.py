@@ -370,7 +370,7 @@ def test_aborted_backward_leaves_no_stale_gradient():
             out = fn(coords)
             with pytest.raises(ValueError):
                 (out.sum() + boom).backward()
-            assert fn._state.grad_levels is not None  # the aborted pass did leave partial sums behind
+            assert fn._state.pending  # the aborted pass did leave its deferred lookup adjoints behind
             f1.grad = f2.grad = None
         fn(coords).sum().backward()
         return f1.grad.clone(), f2.grad.clone()
@@ -456,4 +456,41 @@ def test_ranged_adjoint_pool_reuse_across_steps():
     d = rng.standard_normal((B, L * (2 * r + 1) ** 2, H, W)).astype(np.float32)
     g1, g2 = _train_like_step(E, f1n, f2n, [far], [d], L, r)
     assert float(g1.abs().max()) == 0.0 and float(g2.abs().max()) == 0.0
+    E.release_gradient_pool()
+
+
+@pytest.mark.parametrize("spread", [0.3, 2.0, 9.0])
+def test_merged_lookup_adjoint_matches_per_lookup_launches(spread):
+    """ezb_corr_lookup_bwd_multi (all lookups of the pass in one launch, overlapping windows summed in shared memory) against
+    one ezb_corr_lookup_bwd launch per lookup (EZB_LOOKUP_BWD_SEPARATE=1) and the oracle: windows that stay together
+    (tile path), drift apart (mixed) and scatter (per-lookup path inside the kernel), ragged query blocks, levels whose row
+    pitch is not a multiple of 4 (scalar flush)."""
+    import ezflow_b200 as E
+    from oracle import similarity_oracle as O
+
+    rng = np.random.default_rng(int(spread * 10))
+    B, C, H, W, L, r = 2, 24, 22, 30, 3, 4  # N = 660 (not a multiple of 16 x ...: 41.25 blocks), w = 30, 15, 7
+    f1n = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    f2n = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    base = O.coords_grid(B, H, W) + rng.uniform(-6, 6, (B, 2, 1, 1)).astype(np.float32)
+    coords_list = [base + rng.normal(0, spread, (B, 2, H, W)).astype(np.float32) for _ in range(5)]
+    coords_list[2][0, :, 3:6, :] -= 40.0  # windows outside on one side
+    douts = [rng.standard_normal((B, L * (2 * r + 1) ** 2, H, W)).astype(np.float32) for _ in coords_list]
+    shapes = [(H >> l, W >> l) for l in range(L)]
+    dpyr = None
+    for c, d in zip(coords_list, douts):
+        g = O.corr_lookup_bwd(shapes, c, d, r)
+        dpyr = g if dpyr is None else [a + b for a, b in zip(dpyr, g)]
+    d1, d2 = O.corr_pyramid_bwd(f1n, f2n, dpyr)
+    m1, m2 = _train_like_step(E, f1n, f2n, coords_list, douts, L, r)
+    os.environ["EZB_LOOKUP_BWD_SEPARATE"] = "1"
+    try:
+        s1, s2 = _train_like_step(E, f1n, f2n, coords_list, douts, L, r)
+    finally:
+        del os.environ["EZB_LOOKUP_BWD_SEPARATE"]
+    assert_close(m1, d1, GRAD_TOL, f"merged dfmap1 vs oracle (spread {spread})")
+    assert_close(m2, d2, GRAD_TOL, f"merged dfmap2 vs oracle (spread {spread})")
+    # same terms in another summation order, then tf32 GEMMs: the truncation can fall differently (measured 9e-5 max)
+    assert_close(m1, s1, 3e-4, "merged vs per-lookup dfmap1")
+    assert_close(m2, s2, 3e-4, "merged vs per-lookup dfmap2")
     E.release_gradient_pool()
