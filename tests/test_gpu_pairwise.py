@@ -494,3 +494,35 @@ def test_merged_lookup_adjoint_matches_per_lookup_launches(spread):
     assert_close(m1, s1, 3e-4, "merged vs per-lookup dfmap1")
     assert_close(m2, s2, 3e-4, "merged vs per-lookup dfmap2")
     E.release_gradient_pool()
+
+
+@pytest.mark.parametrize("cfg", [(2, 22, 30, 3, 4, 5), (1, 9, 12, 2, 2, 3), (1, 28, 36, 4, 3, 17)])
+def test_grad_ranges_cover_the_lookup_adjoint_support(cfg):
+    """C ABI level: whatever ezb_corr_lookup_bwd_multi writes into an all-zero gradient pyramid lies inside the ranges of
+    ezb_corr_grad_ranges — ezb_corr_grad_rezero brings the pyramid back to all-zero (the invariant the pooled buffers rely
+    on); 17 lookups exercise the 16-lookup chunking, shifted rows put windows wholly outside the levels."""
+    import ctypes
+
+    import ezflow_b200 as E
+    from ezflow_b200 import _cabi
+    from ezflow_b200.similarity.pairwise import grad_layout
+
+    B, H, W, L, r, n = cfg
+    K = 2 * r + 1
+    g = torch.Generator(device="cpu").manual_seed(n)
+    lib, st = _cabi.lib(), _cabi.stream_ptr(dev())
+    lv = [torch.zeros(B * H * W * qs, device=dev()) for (_, _, _, qs) in grad_layout(H, W, L)]
+    grid = E.coords_grid(B, H, W)
+    coords = [(grid + torch.randn(B, 2, H, W, generator=g) * (0.5 + 3 * (k % 3))).to(dev()).contiguous() for k in range(n)]
+    coords[-1][:, :, :2] += 500.0
+    douts = [torch.randn(B, L * K * K, H, W, generator=g).to(dev()) for _ in range(n)]
+    _cabi.check(lib.ezb_corr_lookup_bwd_multi(_cabi.ptr_array(douts), _cabi.ptr_array(coords), n, B, H, W, L, r, _cabi.ptr_array(lv), st))
+    assert any(float(t.abs().max()) > 0 for t in lv)
+    cnt = ctypes.c_int64(0)
+    _cabi.check(lib.ezb_corr_grad_ranges_count(B, H, W, ctypes.byref(cnt)))
+    rg = torch.empty(cnt.value, dtype=torch.int32, device=dev())
+    _cabi.check(lib.ezb_corr_grad_ranges(_cabi.ptr_array(coords), n, B, H, W, L, r, _cabi.ptr(rg), st))
+    _cabi.check(lib.ezb_corr_grad_rezero(_cabi.ptr_array(lv), _cabi.ptr(rg), B, H, W, L, st))
+    torch.cuda.synchronize()
+    for l, t in enumerate(lv):
+        assert float(t.abs().max()) == 0.0, f"level {l}: the ranges miss part of the adjoint's support"
