@@ -398,6 +398,7 @@ __global__ void __launch_bounds__(NTHREADS) corr_lookup_bwd_kernel(const LookupB
 // the most converged iterate there); a lookup whose window does not fit inside it (early iterations, scattered coordinates)
 // takes the per-lookup path (atomics) inside the same kernel, so any coordinates are handled.
 constexpr int MQB = 16, MT_H = 16, MT_W = 20, M_MAXLK = 16, M_MAXL = 4;
+constexpr int MT_STRIDE = MT_H * MT_W + 1;  // odd: the 16 queries of a half-warp update 16 different banks
 struct LookupBwdMultiParams {
   float* dlvl[M_MAXL];
   long long qstride[M_MAXL];
@@ -407,13 +408,15 @@ struct LookupBwdMultiParams {
   int n, B, N, L, r;
 };
 
+// RT: compile-time radius (RAFT: 4, small model 3) so that the window loops unroll; 0 = runtime radius
+template <int RT>
 __global__ void __launch_bounds__(NTHREADS, 2) corr_lookup_bwd_multi_kernel(const LookupBwdMultiParams P) {
   extern __shared__ __align__(16) float sm[];
-  const int r = P.r, D = 2 * r + 2, K = 2 * r + 1, KK = K * K, nch = P.L * KK;
+  const int r = RT > 0 ? RT : P.r, D = 2 * r + 2, K = 2 * r + 1, KK = K * K, nch = P.L * KK;
   const int dstride = nch | 1;  // dout values per query (odd stride)
   float* s_d = sm;                                                   // [MQB][dstride]
-  float* tiles = sm + ((MQB * dstride + 3) & ~3);                    // [MQB * L][MT_H * MT_W]
-  int* s_org = reinterpret_cast<int*>(tiles + MQB * P.L * MT_H * MT_W);  // [MQB * L][3]: ox, oy, compact
+  float* tiles = sm + ((MQB * dstride + 3) & ~3);                    // [MQB * L][MT_STRIDE]
+  int* s_org = reinterpret_cast<int*>(tiles + MQB * P.L * MT_STRIDE);  // [MQB * L][3]: ox, oy, any
   const int b = blockIdx.y, q0 = blockIdx.x * MQB, tid = threadIdx.x;
 
   auto window_origin = [&](int k, int q, int l, int& xs, int& ys, float& fx, float& fy) {
@@ -438,7 +441,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) corr_lookup_bwd_multi_kernel(cons
     s_org[3 * tid + 1] = any ? ys - (MT_H - D) / 2 : INT_MIN / 2;      // no tile: nothing fits
     s_org[3 * tid + 2] = any ? 1 : 0;
   }
-  for (int i = tid; i < MQB * P.L * MT_H * MT_W / 4; i += NTHREADS) reinterpret_cast<float4*>(tiles)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < MQB * P.L * MT_STRIDE; i += NTHREADS) tiles[i] = 0.f;
 
   for (int k = 0; k < P.n; ++k) {
     __syncthreads();  // phase 0 / the previous lookup's readers of s_d are done
@@ -481,8 +484,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) corr_lookup_bwd_multi_kernel(cons
       };
       const int* org = s_org + 3 * (l * MQB + ql);
       if (xs >= org[0] && xs + D <= org[0] + MT_W && ys >= org[1] && ys + D <= org[1] + MT_H) {  // this lookup's window is inside the tile
-        float* t = tiles + (l * MQB + ql) * (MT_H * MT_W) + (yy - org[1]) * MT_W + (xs - org[0]);
-        for (int X = 0; X < D; ++X) t[X] += next(X);  // this (query, level, row) belongs to this thread: no conflicts
+        float* t = tiles + (l * MQB + ql) * MT_STRIDE + (yy - org[1]) * MT_W + (xs - org[0]);
+        if constexpr (RT > 0) {
+#pragma unroll
+          for (int X = 0; X < 2 * RT + 2; ++X) t[X] += next(X);  // this (query, level, row) belongs to this thread: no conflicts
+        } else {
+          for (int X = 0; X < D; ++X) t[X] += next(X);
+        }
       } else {
         if (yy < 0 || yy >= hl) continue;
         float* row = P.dlvl[l] + ((long long)b * P.N + q) * P.qstride[l] + (long long)yy * P.pitch[l] + xs;
@@ -503,7 +511,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) corr_lookup_bwd_multi_kernel(cons
     if (q >= P.N || !org[2]) continue;
     const int y = org[1] + row, x = org[0] + 4 * sl;
     if (y < 0 || y >= P.h[l] || x + 3 < 0 || x >= P.w[l]) continue;
-    const float4 v = *reinterpret_cast<const float4*>(tiles + item * (MT_H * MT_W) + row * MT_W + 4 * sl);
+    const float* tv = tiles + item * MT_STRIDE + row * MT_W + 4 * sl;
+    const float4 v = make_float4(tv[0], tv[1], tv[2], tv[3]);
     if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
     float* dst = P.dlvl[l] + ((long long)b * P.N + q) * P.qstride[l] + (long long)y * P.pitch[l] + x;
     if (x >= 0 && x + 3 < P.w[l] && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
@@ -665,10 +674,11 @@ extern "C" int ezb_corr_lookup_bwd_multi(const float* const* dout_ptrs, const fl
     P.qstride[l] = l < L ? g[l].qstride : 0;
   }
   P.B = B; P.N = N; P.L = L; P.r = radius;
-  const size_t smem = ((size_t)((k3::MQB * ((L * K * K) | 1) + 3) & ~3) + (size_t)k3::MQB * L * k3::MT_H * k3::MT_W) * sizeof(float) +
+  const size_t smem = ((size_t)((k3::MQB * ((L * K * K) | 1) + 3) & ~3) + (size_t)k3::MQB * L * k3::MT_STRIDE) * sizeof(float) +
                       (size_t)k3::MQB * L * 3 * sizeof(int);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  EZB_CUDA_OK(cudaFuncSetAttribute(k3::corr_lookup_bwd_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto kern = radius == 4 ? k3::corr_lookup_bwd_multi_kernel<4> : radius == 3 ? k3::corr_lookup_bwd_multi_kernel<3> : k3::corr_lookup_bwd_multi_kernel<0>;
+  EZB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   for (int k0 = 0; k0 < n_lookups; k0 += k3::M_MAXLK) {
     P.n = std::min(k3::M_MAXLK, n_lookups - k0);
     for (int k = 0; k < P.n; ++k) {
@@ -676,7 +686,7 @@ extern "C" int ezb_corr_lookup_bwd_multi(const float* const* dout_ptrs, const fl
       P.dout[k] = dout_ptrs[k0 + k];
       P.coords[k] = coords_ptrs[k0 + k];
     }
-    k3::corr_lookup_bwd_multi_kernel<<<dim3(cdiv(N, k3::MQB), B), k3::NTHREADS, smem, st>>>(P);
+    kern<<<dim3(cdiv(N, k3::MQB), B), k3::NTHREADS, smem, st>>>(P);
     EZB_LAUNCH_OK();
   }
   return EZB_OK;

@@ -86,10 +86,29 @@ def cfg5():
     loss.backward()
 
 
+def cfg5_smooth():
+    """The bench's smooth-flow training step on 2 pairs: build, 12 lookups, loss, backward (two passes: the second reuses the
+    pooled gradient pyramid)."""
+    global P
+    P = 2
+    g = torch.Generator(device="cpu").manual_seed(1)
+    f1 = torch.randn(P, C, H, W, generator=g).to(dev).requires_grad_(True)
+    f2 = torch.randn(P, C, H, W, generator=g).to(dev).requires_grad_(True)
+    grid = E.coords_grid(P, H, W, device=dev)
+    flow = torch.nn.functional.interpolate(torch.randn(P, 2, 5, 8, generator=g) * 10, size=(H, W), mode="bicubic", align_corners=True).to(dev)
+    coords = [(grid + flow * (1 - 0.5 ** (k + 1)) + torch.randn(P, 2, H, W, generator=g).to(dev) * 0.5).clamp_(-16, W + 16) for k in range(12)]
+    douts = [torch.randn(P, L * (2 * R + 1) ** 2, H, W, generator=g).to(dev) for _ in range(12)]
+    for _ in range(2):
+        f1.grad = f2.grad = None
+        fn = E.MutliScalePairwise4DCorr(f1, f2, num_levels=L, corr_radius=R)
+        outs = [fn(c) for c in coords]
+        torch.autograd.backward(outs, douts)
+
+
 if __name__ == "__main__":
     with torch.no_grad():
         for name in sys.argv[1:]:
-            if name in ("cfg2_bwd", "cfg5"):
+            if name in ("cfg2_bwd", "cfg5", "cfg5_smooth"):
                 with torch.enable_grad():
                     globals()[name]()
             else:
