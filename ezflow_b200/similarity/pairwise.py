@@ -359,6 +359,8 @@ class MutliScalePairwise4DCorr:
         if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
             self._token = _BuildFn.apply(f1, f2, self._state)
         else:
+            if _GRAD_POOL:  # inference after training: do not sit on the pooled gradient pyramid (5.6 GB per 1080p pair)
+                release_gradient_pool()
             self._state.build()
             self._token = None
 
