@@ -40,8 +40,19 @@ for i in range(n_cases):
     ok = rf <= 1e-3 and mr <= 1e-3
     if i % 3 == 0:
         dout = rng.standard_normal(ref.shape).astype(np.float32)
-        (out_t * g(dout)).sum().backward()
+        loss = (out_t * g(dout)).sum()
         dpyr = O.corr_lookup_bwd([(H >> l, W >> l) for l in range(L)], coords, dout, r)
+        # 0-3 more lookups through the same pyramid at drifting coordinates (RAFT's iterations): the merged lookup adjoint's
+        # shared-memory tiles, its per-lookup fallback, and the support ranges of the pyramid adjoint
+        fn_t = out_t.grad_fn  # noqa: F841  (keeps the first lookup's graph alive until backward)
+        obj = E.MutliScalePairwise4DCorr(t1, t2, num_levels=L, corr_radius=r)
+        loss = (obj(tc) * g(dout)).sum()
+        for _ in range(int(rng.integers(0, 4))):
+            ck = coords + rng.normal(0, float(rng.choice([0.3, 2.0, 8.0])), coords.shape).astype(np.float32)
+            dk = rng.standard_normal(ref.shape).astype(np.float32)
+            loss = loss + (obj(g(ck)) * g(dk)).sum()
+            dpyr = [a + b for a, b in zip(dpyr, O.corr_lookup_bwd([(H >> l, W >> l) for l in range(L)], ck, dk, r))]
+        loss.backward()
         d1, d2 = O.corr_pyramid_bwd(f1, f2, dpyr)
         e1, e2 = rel(t1.grad.cpu().numpy(), d1), rel(t2.grad.cpu().numpy(), d2)
         ec = rel(tc.grad.cpu().numpy(), O.corr_lookup_bwd_coords(O.corr_pyramid(f1, f2, L), coords, dout, r))
