@@ -523,6 +523,24 @@ def run_secondary(args, dev, world, rank, peaks, headline_step):
             del fn, lazy, f1, f2
         torch.cuda.empty_cache()
 
+    if enabled("ondemand_lookup_fp32"):
+        # the volume-free lookup (no 2.9 GB pyramid per pair): prepare (pooled fmap2 levels) + one lookup of 2 pairs
+        with torch.no_grad():
+            g = torch.Generator(device="cpu").manual_seed(5 + rank)
+            f1 = torch.randn(2, C, H, W, generator=g).to(dev)
+            f2 = torch.randn(2, C, H, W, generator=g).to(dev)
+            flow = torch.nn.functional.interpolate(torch.randn(2, 2, 5, 8, generator=g) * 10, size=(H, W), mode="bicubic", align_corners=True)
+            coords = (E.coords_grid(2, H, W) + flow + torch.randn(2, 2, H, W, generator=g) * 0.5).to(dev)  # a smooth flow + 0.5 px noise
+            od = E.OnDemandPairwise4DCorr(f1, f2, num_levels=L, corr_radius=R)
+            nb = 2 * N * (L * (2 * R + 1) ** 2 * 4 + 8) + 2 * 2 * C * N * 4  # lookup features out + coords + both feature maps in
+            add("ondemand_lookup_fp32", timed(lambda: od(coords)), nb,
+                "OnDemandPairwise4DCorr: one lookup of 2 1080p pairs straight from the feature maps (fp32 CUDA cores, 3.3 GFMA per pair, "
+                "shared-memory tiled: neighbouring queries share the fmap2 pixels of their windows; coords = grid + smooth flow + 0.5 px noise; "
+                "the path for inputs whose all-pairs volume does not fit)", ms_per_pair_lookup=None)
+            records[-1]["ms_per_pair_lookup"] = records[-1]["ms"] / 2
+            del od, f1, f2, coords
+        torch.cuda.empty_cache()
+
     for c5_name in ("cfg5_raft_1080p_train_step", "cfg5_raft_1080p_train_step_smooth_flow"):
         if not enabled(c5_name):
             continue

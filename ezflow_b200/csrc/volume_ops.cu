@@ -15,6 +15,10 @@
 // All three are HBM/L2-bound data-movement kernels on CUDA cores: one pass, every output element written once.
 #include "ezb_common.cuh"
 
+#include <cstdlib>
+
+#include <climits>
+
 namespace ezb {
 namespace k8 {
 
@@ -250,6 +254,153 @@ __global__ void __launch_bounds__(OD_WARPS * 32) corr_ondemand_lookup_kernel(con
   }
 }
 
+
+// The same lookup with the fmap2 pixels shared between neighbouring queries (round 2).  The kernel above fetches every
+// window pixel's C-float row from L2 for every query: 100 KB per (query, level), 13 GB of L2 traffic per 1080p pair and
+// lookup (3 ms).  Here a block owns 8 x 8 queries of one level; when the bounding box of their windows fits a 24 x 28
+// region (coherent flow: always at the coarse levels) the region is staged in shared memory 32 channels at a time and shared
+// by the 64 queries: thread = (query, every fifth window row), <= 20 running dot products in registers, per chunk the
+// query's 32 f1 values in registers and eight LDS.128 per window pixel (pixel pitch 36 floats: consecutive pixels = different
+// bank groups).  Blocks whose windows scatter wider fall back to per-pixel global loads inside the same kernel.
+constexpr int ODT_QW = 8, ODT_QH = 8, ODT_Q = ODT_QW * ODT_QH, ODT_RH = 24, ODT_RW = 28, ODT_CK = 32, ODT_PITCH = ODT_CK + 4;
+constexpr int ODT_PARTS = 5, ODT_THREADS = ODT_Q * ODT_PARTS, ODT_MAXD = 10, ODT_NR = (ODT_MAXD + ODT_PARTS - 1) / ODT_PARTS;
+constexpr size_t ODT_SMEM = ((size_t)ODT_RH * ODT_RW + ODT_Q) * ODT_PITCH * sizeof(float);
+__global__ void __launch_bounds__(ODT_THREADS, 2) corr_ondemand_tiled_kernel(const OnDemandParams P) {
+  extern __shared__ __align__(16) float sm[];
+  float* s_reg = sm;                                 // [ODT_RH * ODT_RW][ODT_PITCH]; afterwards the windows of dot products
+  float* s_f1 = sm + ODT_RH * ODT_RW * ODT_PITCH;    // [ODT_Q][ODT_PITCH]
+  __shared__ int s_box[4];
+  const int r = P.r, D = 2 * r + 2, K = 2 * r + 1, KK = K * K, DD = D * D;
+  const int tid = threadIdx.x, ql = tid % ODT_Q, part = tid / ODT_Q;
+  const int b = blockIdx.z / P.L, l = blockIdx.z - b * P.L;
+  const int qx = blockIdx.x * ODT_QW + (ql % ODT_QW), qy = blockIdx.y * ODT_QH + ql / ODT_QW;
+  const bool qok = qx < P.W && qy < P.H;
+  const long long q = (long long)qy * P.W + qx;
+  const int hl = P.H >> l, wl = P.W >> l;
+  int xs = -D, ys = -D;
+  float fx = 0.f, fy = 0.f;
+  if (qok) {
+    const float inv = 1.0f / (float)(1 << l);
+    const float cx = __ldg(P.coords + (long long)b * 2 * P.N + q) * inv, cy = __ldg(P.coords + (long long)b * 2 * P.N + P.N + q) * inv;
+    float fxf = floorf(cx), fyf = floorf(cy);
+    fxf = fminf(fmaxf(fxf, -16777216.f), 16777216.f);
+    fyf = fminf(fmaxf(fyf, -16777216.f), 16777216.f);
+    const int x0 = (fxf == fxf) ? (int)fxf : -(1 << 24), y0 = (fyf == fyf) ? (int)fyf : -(1 << 24);
+    fx = cx - floorf(cx);
+    fy = cy - floorf(cy);
+    xs = max(-D, min(wl, x0 - r));
+    ys = max(-D, min(hl, y0 - r));  // a window entirely outside stays outside
+  }
+  const bool any = qok && xs + D > 0 && xs < wl && ys + D > 0 && ys < hl;
+  if (tid == 0) { s_box[0] = INT_MAX; s_box[1] = INT_MAX; s_box[2] = INT_MIN; s_box[3] = INT_MIN; }
+  __syncthreads();
+  if (part == 0 && any) {
+    atomicMin(&s_box[0], xs); atomicMin(&s_box[1], ys);
+    atomicMax(&s_box[2], xs); atomicMax(&s_box[3], ys);
+  }
+  __syncthreads();
+  const bool none = s_box[0] == INT_MAX;  // no window of this block touches the level: all zeros
+  const int rx0 = none ? 0 : max(s_box[0], 0), ry0 = none ? 0 : max(s_box[1], 0);
+  const int rw = none ? 0 : min(s_box[2] + D, wl) - rx0, rh = none ? 0 : min(s_box[3] + D, hl) - ry0;
+  const bool tiled = rw <= ODT_RW && rh <= ODT_RH;
+  const float* lvl = P.f2[l] + (long long)b * hl * wl * P.C;
+  const float* f1row = P.f1 + ((long long)b * P.N + (qok ? q : 0)) * P.C;
+
+  // this thread's window rows wy = part, part + ODT_PARTS (a 10 x 10 window: two rows each) x all D columns
+  float acc[ODT_NR][ODT_MAXD];
+  bool rowok[ODT_NR];
+  unsigned colmask = 0;
+#pragma unroll
+  for (int wx = 0; wx < ODT_MAXD; ++wx)
+    if (wx < D && xs + wx >= 0 && xs + wx < wl) colmask |= 1u << wx;
+#pragma unroll
+  for (int k = 0; k < ODT_NR; ++k) {
+    const int wy = part + k * ODT_PARTS, y = ys + wy;
+    rowok[k] = any && wy < D && y >= 0 && y < hl;
+#pragma unroll
+    for (int wx = 0; wx < ODT_MAXD; ++wx) acc[k][wx] = 0.f;
+  }
+
+  if (tiled && !none) {
+    for (int c0 = 0; c0 < P.C; c0 += ODT_CK) {
+      __syncthreads();  // the previous chunk's readers are done
+      for (int i = tid; i < rh * rw * (ODT_CK / 4); i += ODT_THREADS) {
+        const int px = i / (ODT_CK / 4), k = i - px * (ODT_CK / 4), ry = px / rw, rx = px - ry * rw;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 + 4 * k < P.C) v = __ldg(reinterpret_cast<const float4*>(lvl + ((long long)(ry0 + ry) * wl + rx0 + rx) * P.C + c0 + 4 * k));
+        *reinterpret_cast<float4*>(s_reg + (ry * ODT_RW + rx) * ODT_PITCH + 4 * k) = v;
+      }
+      for (int i = tid; i < ODT_Q * (ODT_CK / 4); i += ODT_THREADS) {
+        const int qq = i / (ODT_CK / 4), k = i - qq * (ODT_CK / 4);
+        const int x = blockIdx.x * ODT_QW + (qq % ODT_QW), y = blockIdx.y * ODT_QH + qq / ODT_QW;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (x < P.W && y < P.H && c0 + 4 * k < P.C)
+          v = __ldg(reinterpret_cast<const float4*>(P.f1 + ((long long)b * P.N + (long long)y * P.W + x) * P.C + c0 + 4 * k));
+        *reinterpret_cast<float4*>(s_f1 + qq * ODT_PITCH + 4 * k) = v;
+      }
+      __syncthreads();
+      float4 a[ODT_CK / 4];
+#pragma unroll
+      for (int k = 0; k < ODT_CK / 4; ++k) a[k] = *reinterpret_cast<const float4*>(s_f1 + ql * ODT_PITCH + 4 * k);
+#pragma unroll
+      for (int k = 0; k < ODT_NR; ++k) {
+        if (!rowok[k]) continue;
+        const float* rowp = s_reg + ((ys + part + k * ODT_PARTS - ry0) * ODT_RW + (xs - rx0)) * ODT_PITCH;
+#pragma unroll
+        for (int wx = 0; wx < ODT_MAXD; ++wx) {
+          if (!((colmask >> wx) & 1u)) continue;
+          const float4* pv = reinterpret_cast<const float4*>(rowp + wx * ODT_PITCH);
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int j = 0; j < ODT_CK / 4; j += 2) {
+            const float4 v = pv[j], w = pv[j + 1];
+            s0 = fmaf(v.x, a[j].x, s0); s0 = fmaf(v.y, a[j].y, s0); s0 = fmaf(v.z, a[j].z, s0); s0 = fmaf(v.w, a[j].w, s0);
+            s1 = fmaf(w.x, a[j + 1].x, s1); s1 = fmaf(w.y, a[j + 1].y, s1); s1 = fmaf(w.z, a[j + 1].z, s1); s1 = fmaf(w.w, a[j + 1].w, s1);
+          }
+          acc[k][wx] += s0 + s1;
+        }
+      }
+    }
+  } else if (!none) {
+#pragma unroll
+    for (int k = 0; k < ODT_NR; ++k) {
+      if (!rowok[k]) continue;
+      const float* rowp = lvl + ((long long)(ys + part + k * ODT_PARTS) * wl + xs) * P.C;
+#pragma unroll
+      for (int wx = 0; wx < ODT_MAXD; ++wx) {
+        if (!((colmask >> wx) & 1u)) continue;
+        const float* p = rowp + (long long)wx * P.C;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int c = 0; c < P.C; c += 4) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(p + c)), u = __ldg(reinterpret_cast<const float4*>(f1row + c));
+          a0 = fmaf(v.x, u.x, a0); a1 = fmaf(v.y, u.y, a1); a2 = fmaf(v.z, u.z, a2); a3 = fmaf(v.w, u.w, a3);
+        }
+        acc[k][wx] = (a0 + a1) + (a2 + a3);
+      }
+    }
+  }
+  __syncthreads();  // the region is dead: its memory now holds every query's window of dot products
+  const int WP = DD | 1;
+  float* win = s_reg + ql * WP;
+#pragma unroll
+  for (int k = 0; k < ODT_NR; ++k) {
+    const int wy = part + k * ODT_PARTS;
+    if (wy >= D) continue;
+#pragma unroll
+    for (int wx = 0; wx < ODT_MAXD; ++wx)
+      if (wx < D) win[wy * D + wx] = acc[k][wx] * P.scale;
+  }
+  __syncthreads();
+  if (!qok) return;
+  float* o = P.out + ((long long)b * P.L * KK + (long long)l * KK) * P.N + q;
+  for (int t = part; t < KK; t += ODT_PARTS) {
+    const int i = t / K, j = t - i * K;  // i offsets x (slow output index), j offsets y   pairwise.py:53-61
+    const float* w = win + j * D + i;
+    const float top = (1.f - fx) * w[0] + fx * w[1], bot = (1.f - fx) * w[D] + fx * w[D + 1];
+    o[(long long)t * P.N] = top + fy * (bot - top);
+  }
+}
+
 }  // namespace k8
 }  // namespace ezb
 
@@ -372,6 +523,15 @@ extern "C" int ezb_corr_ondemand_lookup(const void* workspace, const float* coor
   P.coords = coords; P.out = out;
   P.B = B; P.C = C; P.H = H; P.W = W; P.N = N; P.L = L; P.r = radius;
   P.scale = 1.0f / sqrtf((float)C);
+  cudaStream_t st0 = static_cast<cudaStream_t>(stream);
+  if (2 * radius + 2 <= k8::ODT_MAXD && C % 4 == 0 && (long long)B * L <= 65535 && cdiv(H, k8::ODT_QH) <= 65535 &&
+      getenv("EZB_ONDEMAND_UNTILED") == nullptr) {
+    // shared-memory tiled kernel: neighbouring queries share the fmap2 pixels of their windows
+    EZB_CUDA_OK(cudaFuncSetAttribute(k8::corr_ondemand_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k8::ODT_SMEM));
+    k8::corr_ondemand_tiled_kernel<<<dim3(cdiv(W, k8::ODT_QW), cdiv(H, k8::ODT_QH), B * L), k8::ODT_THREADS, k8::ODT_SMEM, st0>>>(P);
+    EZB_LAUNCH_OK();
+    return EZB_OK;
+  }
   const int qpb = std::max(1, k8::OD_WARPS / L), D = 2 * radius + 2;
   const size_t smem = ((size_t)qpb * C + (size_t)k8::OD_WARPS * D * D) * 4;
   if (smem > 200 * 1024) return fail(EZB_ERR_UNSUPPORTED, "feature dimension too large for the on-demand lookup (C=%d)", C);

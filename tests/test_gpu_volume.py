@@ -98,3 +98,32 @@ def test_ondemand_edge_cases():
         E.OnDemandPairwise4DCorr(a, a, num_levels=5, corr_radius=1)
     with pytest.raises(RuntimeError):
         E.OnDemandPairwise4DCorr(torch.zeros(1, 4, 8, 8), torch.zeros(1, 4, 8, 8))  # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("cfg", [(2, 64, 30, 44, 4, 4, 0.4), (1, 40, 17, 23, 3, 3, 1.5), (1, 256, 46, 62, 4, 4, 0.2), (1, 32, 20, 36, 2, 4, 30.0)])
+def test_ondemand_tiled_lookup_coherent_and_scattered(cfg):
+    """corr_ondemand_tiled_kernel: a smooth flow (the windows of a 4 x 16 query block fit the shared-memory region at every
+    level), mild noise (mixed), and wide scatter (every block on the per-pixel fallback), against the oracle and against
+    the untiled kernel (EZB_ONDEMAND_UNTILED=1); channel counts off the 32-channel chunk, ragged query blocks."""
+    import os
+
+    import ezflow_b200 as E
+
+    b, c, h, w, L, r, noise = cfg
+    rng = np.random.default_rng(int(noise * 10) + c)
+    f1 = rng.standard_normal((b, c, h, w)).astype(np.float32)
+    f2 = rng.standard_normal((b, c, h, w)).astype(np.float32)
+    yy, xx = np.meshgrid(np.linspace(0, 3, h), np.linspace(0, 3, w), indexing="ij")
+    flow = np.stack([6 * np.sin(xx + yy), 5 * np.cos(xx - yy)]).astype(np.float32)[None]
+    coords = O.coords_grid(b, h, w) + flow + rng.normal(0, noise, (b, 2, h, w)).astype(np.float32)
+    ref = O.corr_lookup(O.corr_pyramid(f1, f2, L), coords, r)
+    with torch.no_grad():
+        fn = E.OnDemandPairwise4DCorr(to_gpu(f1), to_gpu(f2), num_levels=L, corr_radius=r)
+        out = fn(to_gpu(coords))
+        os.environ["EZB_ONDEMAND_UNTILED"] = "1"
+        try:
+            old = fn(to_gpu(coords))
+        finally:
+            del os.environ["EZB_ONDEMAND_UNTILED"]
+    assert_close(out, ref, 2e-5, f"tiled on-demand lookup {cfg}")
+    assert_close(out, old, 2e-5, "tiled vs untiled kernel")
