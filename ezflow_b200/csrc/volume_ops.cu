@@ -260,9 +260,11 @@ __global__ void __launch_bounds__(OD_WARPS * 32) corr_ondemand_lookup_kernel(con
 // lookup (3 ms).  Here a block owns 8 x 8 queries of one level; when the bounding box of their windows fits a 24 x 28
 // region (coherent flow: always at the coarse levels) the region is staged in shared memory 32 channels at a time and shared
 // by the 64 queries: thread = (query, every fifth window row), <= 20 running dot products in registers, per chunk the
-// query's 32 f1 values in registers and eight LDS.128 per window pixel (pixel pitch 36 floats: consecutive pixels = different
-// bank groups).  Blocks whose windows scatter wider fall back to per-pixel global loads inside the same kernel.
-constexpr int ODT_QW = 8, ODT_QH = 8, ODT_Q = ODT_QW * ODT_QH, ODT_RH = 24, ODT_RW = 28, ODT_CK = 32, ODT_PITCH = ODT_CK + 4;
+// query's 32 f1 values in registers and eight LDS.128 per window pixel (pixel pitch 36 floats and 24 pixels per region row:
+// the eight x-adjacent queries of a quarter-warp hit eight different bank groups whatever rows their windows start in).  A
+// bounding box of up to four regions is swept region by region; blocks whose windows scatter wider fall back to per-pixel
+// global loads inside the same kernel.
+constexpr int ODT_QW = 8, ODT_QH = 8, ODT_Q = ODT_QW * ODT_QH, ODT_RH = 28, ODT_RW = 24, ODT_CK = 32, ODT_PITCH = ODT_CK + 4;
 constexpr int ODT_PARTS = 5, ODT_THREADS = ODT_Q * ODT_PARTS, ODT_MAXD = 10, ODT_NR = (ODT_MAXD + ODT_PARTS - 1) / ODT_PARTS;
 constexpr size_t ODT_SMEM = ((size_t)ODT_RH * ODT_RW + ODT_Q) * ODT_PITCH * sizeof(float);
 __global__ void __launch_bounds__(ODT_THREADS, 2) corr_ondemand_tiled_kernel(const OnDemandParams P) {
@@ -302,69 +304,83 @@ __global__ void __launch_bounds__(ODT_THREADS, 2) corr_ondemand_tiled_kernel(con
   const bool none = s_box[0] == INT_MAX;  // no window of this block touches the level: all zeros
   const int rx0 = none ? 0 : max(s_box[0], 0), ry0 = none ? 0 : max(s_box[1], 0);
   const int rw = none ? 0 : min(s_box[2] + D, wl) - rx0, rh = none ? 0 : min(s_box[3] + D, hl) - ry0;
-  const bool tiled = rw <= ODT_RW && rh <= ODT_RH;
+  // the bounding box is swept in sub-rectangles of at most ODT_RH x ODT_RW pixels (one when the flow is coherent); more than
+  // four: the windows are scattered and sharing does not pay -> per-pixel loads below
+  const int nsy = (rh + ODT_RH - 1) / ODT_RH, nsx = (rw + ODT_RW - 1) / ODT_RW;
+  const bool tiled = nsy * nsx <= 4;
   const float* lvl = P.f2[l] + (long long)b * hl * wl * P.C;
   const float* f1row = P.f1 + ((long long)b * P.N + (qok ? q : 0)) * P.C;
 
   // this thread's window rows wy = part, part + ODT_PARTS (a 10 x 10 window: two rows each) x all D columns
   float acc[ODT_NR][ODT_MAXD];
-  bool rowok[ODT_NR];
-  unsigned colmask = 0;
 #pragma unroll
-  for (int wx = 0; wx < ODT_MAXD; ++wx)
-    if (wx < D && xs + wx >= 0 && xs + wx < wl) colmask |= 1u << wx;
-#pragma unroll
-  for (int k = 0; k < ODT_NR; ++k) {
-    const int wy = part + k * ODT_PARTS, y = ys + wy;
-    rowok[k] = any && wy < D && y >= 0 && y < hl;
+  for (int k = 0; k < ODT_NR; ++k)
 #pragma unroll
     for (int wx = 0; wx < ODT_MAXD; ++wx) acc[k][wx] = 0.f;
-  }
 
   if (tiled && !none) {
-    for (int c0 = 0; c0 < P.C; c0 += ODT_CK) {
-      __syncthreads();  // the previous chunk's readers are done
-      for (int i = tid; i < rh * rw * (ODT_CK / 4); i += ODT_THREADS) {
-        const int px = i / (ODT_CK / 4), k = i - px * (ODT_CK / 4), ry = px / rw, rx = px - ry * rw;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c0 + 4 * k < P.C) v = __ldg(reinterpret_cast<const float4*>(lvl + ((long long)(ry0 + ry) * wl + rx0 + rx) * P.C + c0 + 4 * k));
-        *reinterpret_cast<float4*>(s_reg + (ry * ODT_RW + rx) * ODT_PITCH + 4 * k) = v;
-      }
-      for (int i = tid; i < ODT_Q * (ODT_CK / 4); i += ODT_THREADS) {
-        const int qq = i / (ODT_CK / 4), k = i - qq * (ODT_CK / 4);
-        const int x = blockIdx.x * ODT_QW + (qq % ODT_QW), y = blockIdx.y * ODT_QH + qq / ODT_QW;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (x < P.W && y < P.H && c0 + 4 * k < P.C)
-          v = __ldg(reinterpret_cast<const float4*>(P.f1 + ((long long)b * P.N + (long long)y * P.W + x) * P.C + c0 + 4 * k));
-        *reinterpret_cast<float4*>(s_f1 + qq * ODT_PITCH + 4 * k) = v;
-      }
-      __syncthreads();
-      float4 a[ODT_CK / 4];
+    for (int sub = 0; sub < nsy * nsx; ++sub) {
+      const int sy0 = ry0 + (sub / nsx) * ODT_RH, sx0 = rx0 + (sub % nsx) * ODT_RW;    // this pass's sub-rectangle of the level
+      const int sh = min(ODT_RH, ry0 + rh - sy0), sw = min(ODT_RW, rx0 + rw - sx0);
+      bool rowok[ODT_NR];
+      unsigned colmask = 0;
 #pragma unroll
-      for (int k = 0; k < ODT_CK / 4; ++k) a[k] = *reinterpret_cast<const float4*>(s_f1 + ql * ODT_PITCH + 4 * k);
+      for (int wx = 0; wx < ODT_MAXD; ++wx)
+        if (wx < D && xs + wx >= sx0 && xs + wx < sx0 + sw) colmask |= 1u << wx;
 #pragma unroll
       for (int k = 0; k < ODT_NR; ++k) {
-        if (!rowok[k]) continue;
-        const float* rowp = s_reg + ((ys + part + k * ODT_PARTS - ry0) * ODT_RW + (xs - rx0)) * ODT_PITCH;
+        const int wy = part + k * ODT_PARTS, y = ys + wy;
+        rowok[k] = any && wy < D && y >= sy0 && y < sy0 + sh;
+      }
+      for (int c0 = 0; c0 < P.C; c0 += ODT_CK) {
+        __syncthreads();  // the previous chunk's readers are done
+        for (int i = tid; i < sh * sw * (ODT_CK / 4); i += ODT_THREADS) {
+          const int px = i / (ODT_CK / 4), k = i - px * (ODT_CK / 4), ry = px / sw, rx = px - ry * sw;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c0 + 4 * k < P.C) v = __ldg(reinterpret_cast<const float4*>(lvl + ((long long)(sy0 + ry) * wl + sx0 + rx) * P.C + c0 + 4 * k));
+          *reinterpret_cast<float4*>(s_reg + (ry * ODT_RW + rx) * ODT_PITCH + 4 * k) = v;
+        }
+        for (int i = tid; i < ODT_Q * (ODT_CK / 4); i += ODT_THREADS) {
+          const int qq = i / (ODT_CK / 4), k = i - qq * (ODT_CK / 4);
+          const int x = blockIdx.x * ODT_QW + (qq % ODT_QW), y = blockIdx.y * ODT_QH + qq / ODT_QW;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (x < P.W && y < P.H && c0 + 4 * k < P.C)
+            v = __ldg(reinterpret_cast<const float4*>(P.f1 + ((long long)b * P.N + (long long)y * P.W + x) * P.C + c0 + 4 * k));
+          *reinterpret_cast<float4*>(s_f1 + qq * ODT_PITCH + 4 * k) = v;
+        }
+        __syncthreads();
+        float4 a[ODT_CK / 4];
 #pragma unroll
-        for (int wx = 0; wx < ODT_MAXD; ++wx) {
-          if (!((colmask >> wx) & 1u)) continue;
-          const float4* pv = reinterpret_cast<const float4*>(rowp + wx * ODT_PITCH);
-          float s0 = 0.f, s1 = 0.f;
+        for (int k = 0; k < ODT_CK / 4; ++k) a[k] = *reinterpret_cast<const float4*>(s_f1 + ql * ODT_PITCH + 4 * k);
 #pragma unroll
-          for (int j = 0; j < ODT_CK / 4; j += 2) {
-            const float4 v = pv[j], w = pv[j + 1];
-            s0 = fmaf(v.x, a[j].x, s0); s0 = fmaf(v.y, a[j].y, s0); s0 = fmaf(v.z, a[j].z, s0); s0 = fmaf(v.w, a[j].w, s0);
-            s1 = fmaf(w.x, a[j + 1].x, s1); s1 = fmaf(w.y, a[j + 1].y, s1); s1 = fmaf(w.z, a[j + 1].z, s1); s1 = fmaf(w.w, a[j + 1].w, s1);
+        for (int k = 0; k < ODT_NR; ++k) {
+          if (!rowok[k]) continue;
+          const float* rowp = s_reg + ((ys + part + k * ODT_PARTS - sy0) * ODT_RW + (xs - sx0)) * ODT_PITCH;
+#pragma unroll
+          for (int wx = 0; wx < ODT_MAXD; ++wx) {
+            if (!((colmask >> wx) & 1u)) continue;
+            const float4* pv = reinterpret_cast<const float4*>(rowp + wx * ODT_PITCH);
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < ODT_CK / 4; j += 2) {
+              const float4 v = pv[j], w = pv[j + 1];
+              s0 = fmaf(v.x, a[j].x, s0); s0 = fmaf(v.y, a[j].y, s0); s0 = fmaf(v.z, a[j].z, s0); s0 = fmaf(v.w, a[j].w, s0);
+              s1 = fmaf(w.x, a[j + 1].x, s1); s1 = fmaf(w.y, a[j + 1].y, s1); s1 = fmaf(w.z, a[j + 1].z, s1); s1 = fmaf(w.w, a[j + 1].w, s1);
+            }
+            acc[k][wx] += s0 + s1;
           }
-          acc[k][wx] += s0 + s1;
         }
       }
     }
   } else if (!none) {
+    unsigned colmask = 0;
+#pragma unroll
+    for (int wx = 0; wx < ODT_MAXD; ++wx)
+      if (wx < D && xs + wx >= 0 && xs + wx < wl) colmask |= 1u << wx;
 #pragma unroll
     for (int k = 0; k < ODT_NR; ++k) {
-      if (!rowok[k]) continue;
+      const int wy0 = part + k * ODT_PARTS;
+      if (!(any && wy0 < D && ys + wy0 >= 0 && ys + wy0 < hl)) continue;
       const float* rowp = lvl + ((long long)(ys + part + k * ODT_PARTS) * wl + xs) * P.C;
 #pragma unroll
       for (int wx = 0; wx < ODT_MAXD; ++wx) {
