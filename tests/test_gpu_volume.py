@@ -127,3 +127,49 @@ def test_ondemand_tiled_lookup_coherent_and_scattered(cfg):
             del os.environ["EZB_ONDEMAND_UNTILED"]
     assert_close(out, ref, 2e-5, f"tiled on-demand lookup {cfg}")
     assert_close(out, old, 2e-5, "tiled vs untiled kernel")
+
+
+def test_ondemand_lookup_where_the_volume_does_not_fit():
+    """8K input (feature maps 540 x 960, N = 518 400): the all-pairs volume would take 537 GB in fp16 — more than the GPU has —
+    while the on-demand path needs 1.3 GB.  Sampled queries against an fp64 evaluation of pairwise.py:43-69 on the same GPU."""
+    import ezflow_b200 as E
+
+    B, C, H, W, L, r = 1, 64, 540, 960, 4, 4
+    K = 2 * r + 1
+    g = torch.Generator(device="cpu").manual_seed(8)
+    f1 = torch.randn(B, C, H, W, generator=g).to(dev())
+    f2 = torch.randn(B, C, H, W, generator=g).to(dev())
+    flow = torch.nn.functional.interpolate(torch.randn(B, 2, 6, 10, generator=g) * 12, size=(H, W), mode="bicubic", align_corners=True)
+    coords = (E.coords_grid(B, H, W) + flow + torch.randn(B, 2, H, W, generator=g) * 0.4).to(dev())
+    with pytest.raises((RuntimeError, torch.OutOfMemoryError)):
+        E.MutliScalePairwise4DCorr(f1, f2, num_levels=L, corr_radius=r)  # the pyramid path cannot allocate its volume
+    torch.cuda.empty_cache()
+    with torch.no_grad():
+        out = E.OnDemandPairwise4DCorr(f1, f2, num_levels=L, corr_radius=r)(coords)
+    assert tuple(out.shape) == (B, L * K * K, H, W)
+    # reference for 400 sampled queries: pooled fmap2 levels (avg-pooling the volume = correlating with the pooled features),
+    # dot products in fp64, bilinear taps with zeros outside (grid_sample, align_corners=True, padding zeros)
+    qs = torch.randint(0, H * W, (400,), generator=g).to(dev())
+    f1q = f1[0].reshape(C, -1)[:, qs].double()  # (C, 400)
+    lv = f2[0].double()
+    worst = 0.0
+    for l in range(L):
+        if l > 0:
+            lv = torch.nn.functional.avg_pool2d(lv[None], 2, stride=2)[0]
+        hl, wl = lv.shape[-2:]
+        cx, cy = coords[0, 0].reshape(-1)[qs].double() / 2 ** l, coords[0, 1].reshape(-1)[qs].double() / 2 ** l
+        for i in range(K):      # i offsets x (slow index), j offsets y: pairwise.py:53-61
+            for j in range(0, K, 4):
+                sx, sy = cx + (i - r), cy + (j - r)
+                x0, y0 = torch.floor(sx), torch.floor(sy)
+                val = torch.zeros_like(sx)
+                for dy in (0, 1):
+                    for dx in (0, 1):
+                        xx, yy = (x0 + dx).long(), (y0 + dy).long()
+                        wgt = (1 - (sx - x0 - dx).abs()) * (1 - (sy - y0 - dy).abs())
+                        ok = (xx >= 0) & (xx < wl) & (yy >= 0) & (yy < hl)
+                        feat = lv[:, yy.clamp(0, hl - 1), xx.clamp(0, wl - 1)]  # (C, 400)
+                        val += torch.where(ok, wgt * (feat * f1q).sum(0), torch.zeros_like(wgt))
+                got = out[0, l * K * K + i * K + j].reshape(-1)[qs].double()
+                worst = max(worst, float((got - val / C ** 0.5).abs().max()))
+    assert worst <= 2e-4, f"on-demand lookup at 8K: max abs error {worst:.2e} (values are O(1))"
