@@ -391,14 +391,15 @@ __global__ void __launch_bounds__(NTHREADS) corr_lookup_bwd_kernel(const LookupB
 // ------------------------------------------------------------------------------------ K3b, all lookups of a step at once
 // RAFT runs 12 lookups per step through one pyramid (models/raft.py:114-129) and, once it converges, their windows of a query
 // largely overlap: 12 launches of corr_lookup_bwd_kernel read-modify-write nearly the same DRAM lines 12 times (~1.3 lines per
-// window row and launch: what bounds that kernel).  Here a block owns 16 queries for ALL lookups: per (query, level) a
+// window row and launch: what bounds that kernel).  Here a block owns 8 queries for ALL lookups: per (query, level) a
 // MT_H x MT_W fp32 tile in shared memory is placed where the lookups' windows cluster; every lookup's window
 // gradients are added into the tile (same sliding-row arithmetic as above, dout staged per lookup), and the tile is added to
 // HBM once, skipping untouched 16-byte slots.  The tile is centred on the window of the first lookup passed (the caller puts
 // the most converged iterate there); a lookup whose window does not fit inside it (early iterations, scattered coordinates)
 // takes the per-lookup path (atomics) inside the same kernel, so any coordinates are handled.
-constexpr int MQB = 16, MT_H = 16, MT_W = 20, M_MAXLK = 16, M_MAXL = 4;
-constexpr int MT_STRIDE = MT_H * MT_W + 1;  // odd: the 16 queries of a half-warp update 16 different banks
+constexpr int MQB = 8, MT_H = 16, MT_W = 20, M_MAXLK = 16, M_MAXL = 4;
+constexpr int M_NT = 320, M_NBUF = 3;  // one pass over 8 queries x 4 levels x 10 window rows; dout staged three lookups deep
+constexpr int MT_STRIDE = MT_H * MT_W + 1;  // odd: the 8 queries of a quarter-warp update 8 different banks
 struct LookupBwdMultiParams {
   float* dlvl[M_MAXL];
   long long qstride[M_MAXL];
@@ -410,12 +411,13 @@ struct LookupBwdMultiParams {
 
 // RT: compile-time radius (RAFT: 4, small model 3) so that the window loops unroll; 0 = runtime radius
 template <int RT>
-__global__ void __launch_bounds__(NTHREADS, 2) corr_lookup_bwd_multi_kernel(const LookupBwdMultiParams P) {
+__global__ void __launch_bounds__(M_NT, 3) corr_lookup_bwd_multi_kernel(const LookupBwdMultiParams P) {
   extern __shared__ __align__(16) float sm[];
   const int r = RT > 0 ? RT : P.r, D = 2 * r + 2, K = 2 * r + 1, KK = K * K, nch = P.L * KK;
   const int dstride = nch | 1;  // dout values per query (odd stride)
-  float* s_d = sm;                                                   // [MQB][dstride]
-  float* tiles = sm + ((MQB * dstride + 3) & ~3);                    // [MQB * L][MT_STRIDE]
+  const int dbuf = (MQB * dstride + 3) & ~3;                         // floats per dout buffer
+  float* s_dall = sm;                                                // [M_NBUF][MQB][dstride]
+  float* tiles = sm + M_NBUF * dbuf;                                 // [MQB * L][MT_STRIDE]
   int* s_org = reinterpret_cast<int*>(tiles + MQB * P.L * MT_STRIDE);  // [MQB * L][3]: ox, oy, any
   const int b = blockIdx.y, q0 = blockIdx.x * MQB, tid = threadIdx.x;
 
@@ -441,28 +443,36 @@ __global__ void __launch_bounds__(NTHREADS, 2) corr_lookup_bwd_multi_kernel(cons
     s_org[3 * tid + 1] = any ? ys - (MT_H - D) / 2 : INT_MIN / 2;      // no tile: nothing fits
     s_org[3 * tid + 2] = any ? 1 : 0;
   }
-  for (int i = tid; i < MQB * P.L * MT_STRIDE; i += NTHREADS) tiles[i] = 0.f;
+  for (int i = tid; i < MQB * P.L * MT_STRIDE; i += M_NT) tiles[i] = 0.f;
 
+  // dout of lookup k -> buffer k % M_NBUF: consecutive threads take consecutive queries (32-byte segments); asynchronous
+  // 4-byte copies, ~8 per thread, issued two lookups ahead of their use
+  auto stage = [&](int k) {
+    float* s_d = s_dall + (k % M_NBUF) * dbuf;
+    const float* src = P.dout[k] + (long long)b * nch * P.N + q0;
+    const int ql = tid % MQB, c0 = tid / MQB, cstep = M_NT / MQB;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_d + ql * dstride);
+    if (q0 + ql < P.N) {
+      for (int c = c0; c < nch; c += cstep)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * c), "l"(src + (long long)c * P.N + ql) : "memory");
+    } else {
+      for (int c = c0; c < nch; c += cstep) s_d[ql * dstride + c] = 0.f;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage(0);
+  if (P.n > 1) stage(1);
   for (int k = 0; k < P.n; ++k) {
-    __syncthreads();  // phase 0 / the previous lookup's readers of s_d are done
-    // ---- stage dout of lookup k: consecutive threads take consecutive queries (64-byte segments); asynchronous 4-byte copies,
-    //      all ~20 per thread in flight at once (one memory round trip per lookup)
-    {
-      const float* src = P.dout[k] + (long long)b * nch * P.N + q0;
-      const int ql = tid % MQB, c0 = tid / MQB, cstep = NTHREADS / MQB;
-      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_d + ql * dstride);
-      if (q0 + ql < P.N) {
-        for (int c = c0; c < nch; c += cstep)
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * c), "l"(src + (long long)c * P.N + ql) : "memory");
-      } else {
-        for (int c = c0; c < nch; c += cstep) s_d[ql * dstride + c] = 0.f;
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
+    if (k + 1 < P.n) {
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    __syncthreads();
+    __syncthreads();  // dout k has landed for every thread; everyone is done with lookup k - 1 (its buffer is refilled next)
+    if (k + 2 < P.n) stage(k + 2);
+    const float* s_d = s_dall + (k % M_NBUF) * dbuf;
     // ---- thread -> (level, window row Y, query)
-    for (int idx = tid; idx < MQB * P.L * D; idx += NTHREADS) {
+    for (int idx = tid; idx < MQB * P.L * D; idx += M_NT) {
       const int ql = idx % MQB, ly = idx / MQB, l = ly / D, Y = ly - l * D;
       const int q = q0 + ql;
       if (q >= P.N) continue;
@@ -504,7 +514,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) corr_lookup_bwd_multi_kernel(cons
   __syncthreads();
   // ---- flush: every touched 16-byte slot of every compact tile is added to HBM once
   constexpr int SLOTS = MT_W / 4;
-  for (int idx = tid; idx < MQB * P.L * MT_H * SLOTS; idx += NTHREADS) {
+  for (int idx = tid; idx < MQB * P.L * MT_H * SLOTS; idx += M_NT) {
     const int sl = idx % SLOTS, row = (idx / SLOTS) % MT_H, item = idx / (SLOTS * MT_H);
     const int ql = item % MQB, l = item / MQB, q = q0 + ql;
     const int* org = s_org + 3 * item;
@@ -674,7 +684,7 @@ extern "C" int ezb_corr_lookup_bwd_multi(const float* const* dout_ptrs, const fl
     P.qstride[l] = l < L ? g[l].qstride : 0;
   }
   P.B = B; P.N = N; P.L = L; P.r = radius;
-  const size_t smem = ((size_t)((k3::MQB * ((L * K * K) | 1) + 3) & ~3) + (size_t)k3::MQB * L * k3::MT_STRIDE) * sizeof(float) +
+  const size_t smem = ((size_t)k3::M_NBUF * ((k3::MQB * ((L * K * K) | 1) + 3) & ~3) + (size_t)k3::MQB * L * k3::MT_STRIDE) * sizeof(float) +
                       (size_t)k3::MQB * L * 3 * sizeof(int);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   auto kern = radius == 4 ? k3::corr_lookup_bwd_multi_kernel<4> : radius == 3 ? k3::corr_lookup_bwd_multi_kernel<3> : k3::corr_lookup_bwd_multi_kernel<0>;
@@ -686,7 +696,7 @@ extern "C" int ezb_corr_lookup_bwd_multi(const float* const* dout_ptrs, const fl
       P.dout[k] = dout_ptrs[k0 + k];
       P.coords[k] = coords_ptrs[k0 + k];
     }
-    kern<<<dim3(cdiv(N, k3::MQB), B), k3::NTHREADS, smem, st>>>(P);
+    kern<<<dim3(cdiv(N, k3::MQB), B), k3::M_NT, smem, st>>>(P);
     EZB_LAUNCH_OK();
   }
   return EZB_OK;
