@@ -12,7 +12,7 @@ import sys
 prefix, out = sys.argv[1], sys.argv[2]
 # op of tools/profile_ops.py -> (bench.py secondary record, invocations per profile_ops run, kernels to leave out)
 OPS = {
-    "lookup_conv": ("lookup_convc1_fused", 2, ("pack_weights", "absmax", "scales", "convert_kmajor", "pool2x2", "pack_record", "corr_pyramid_gemm")),
+    "lookup_conv": ("lookup_convc1_fused", 2, ("pack_weights", "absmax", "scales", "convert_kmajor", "pool2x2", "pack_record", "pool_pack", "corr_pyramid_gemm")),
     "cfg2": ("cfg2_flownetc_corr_fwd", 2, ()),
     "cfg3": ("cfg3_pwc_corr_fwd", 2, ()),
     "cfg4": ("cfg4_dcvnet_matryoshka_fwd", 2, ()),
