@@ -526,3 +526,37 @@ def test_grad_ranges_cover_the_lookup_adjoint_support(cfg):
     torch.cuda.synchronize()
     for l, t in enumerate(lv):
         assert float(t.abs().max()) == 0.0, f"level {l}: the ranges miss part of the adjoint's support"
+
+
+def test_pooled_gradient_pyramid_soak():
+    """Twelve consecutive training-like steps through the pooled gradient pyramid with a different number of lookups, spread and
+    offset each step (tight clusters, drifting windows, wide scatter, windows leaving the levels): every step's gradients
+    must equal the dense adjoint's on a fresh zero-filled pyramid — any residue a step left behind would show up in the next."""
+    import ezflow_b200 as E
+    from oracle import similarity_oracle as O
+
+    rng = np.random.default_rng(1234)
+    B, C, H, W, L, r = 2, 16, 20, 28, 3, 4
+    f1n = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    f2n = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    grid = O.coords_grid(B, H, W)
+    E.release_gradient_pool()
+    for step in range(12):
+        n = int(rng.integers(1, 6))
+        spread = float(rng.choice([0.2, 1.0, 4.0, 15.0]))
+        shift = rng.uniform(-12, 12, (1, 2, 1, 1)).astype(np.float32) * (3.0 if step % 5 == 4 else 1.0)
+        coords = [grid + shift + rng.normal(0, spread, (B, 2, H, W)).astype(np.float32) for _ in range(n)]
+        douts = [rng.standard_normal((B, L * (2 * r + 1) ** 2, H, W)).astype(np.float32) for _ in range(n)]
+        g1, g2 = _train_like_step(E, f1n, f2n, coords, douts, L, r)
+        os.environ["EZB_BWD_DENSE"] = "1"
+        os.environ["EZB_LOOKUP_BWD_SEPARATE"] = "1"
+        try:
+            d1, d2 = _train_like_step(E, f1n, f2n, coords, douts, L, r)
+        finally:
+            del os.environ["EZB_BWD_DENSE"], os.environ["EZB_LOOKUP_BWD_SEPARATE"]
+        if float(d1.abs().max()) == 0.0:
+            assert float(g1.abs().max()) == 0.0 and float(g2.abs().max()) == 0.0
+            continue
+        assert_close(g1, d1.cpu().numpy(), 3e-4, f"step {step} (n={n}, spread={spread}) dfmap1")
+        assert_close(g2, d2.cpu().numpy(), 3e-4, f"step {step} (n={n}, spread={spread}) dfmap2")
+    E.release_gradient_pool()

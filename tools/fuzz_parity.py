@@ -69,8 +69,10 @@ for i in range(n_cases):
         E.set_local_corr_mode(mode)
         out = E.IterSpatialCorrelationSampler(kernel_size=1, patch_size=P, stride=s, padding=pad, dilation_patch=dp)(g(x1), g(x2)).cpu().numpy()
         rf, mr = rel(out, ref) if out.shape == ref.shape else (9, 9)
-        if mode == "tc" and out.size < 200:
-            tol *= 8  # a handful of random-sign dot products: error relative to the result is not a stable statistic
+        if mode == "tc" and int(np.count_nonzero(ref)) < 200:
+            tol *= 8  # a handful of random-sign dot products (displacements outside the image are exact zeros and do not count):
+            #           error relative to the result is not a stable statistic (tests/test_gpu_local.py keeps one such case with
+            #           its bound against the dot-product scale written out)
         if not (rf <= tol and mr <= tol):
             fails += 1
             print("FAIL local", mode, (B, C, H, W, P, s, pad, dp), rf, mr)
