@@ -227,3 +227,114 @@ def test_raft_yaml_training_step_parameter_gradients(reference):
     assert at_conv_out <= 5e-3, f"gradient at the encoder's output convolution differs by {at_conv_out:.2e} relative"
     assert worst <= 2e-2, f"feature-encoder gradients differ by {worst:.2e} relative"
     E.release_gradient_pool()
+
+
+def _capture_similarity_inputs(module, store, first_only=False):
+    """Forward pre-hook: keeps every floating-point tensor entering the similarity module (lists included) and asks autograd to
+    retain its gradient — the quantity this repo's adjoint kernels produce, before any parameter reduction."""
+
+    def hook(_mod, args):
+        for a in (args[:1] if first_only else args):
+            for t in (a if isinstance(a, (list, tuple)) else [a]):
+                if torch.is_tensor(t) and t.requires_grad:
+                    t.retain_grad()
+                    store.append(t)
+
+    return module.register_forward_pre_hook(hook)
+
+
+@pytest.mark.parametrize("which", ["FlowNetC", "PWCNet", "DCVNet"])
+@pytest.mark.parametrize("mode", ["tc", "exact"])
+def test_cost_volume_models_training_step_gradients(reference, which, mode):
+    """Training-mode forward + backward of the reference's FlowNetC / PWCNet / DCVNet with the reference's sampler ops and with
+    this repo's classes (same weights): the loss, and the gradients arriving at every input of the similarity module (feature
+    maps; for PWCNet the warped features of all five levels) — what K4b (tensor-core band GEMMs in 'tc' mode, register-tiled /
+    tiled fp32 in 'exact'), the Matryoshka adjoint incl. the stride-4 scale (DCVNet) and the chain behind them produce.
+    The tolerance is measured, not guessed: the same quantities of the reference itself when its own similarity output is
+    perturbed by what this repo's forward differs from it (see `eps` below); parameter gradients likewise.
+    Reference: engine/trainer.py:269-299."""
+    import ezflow_b200 as E
+
+    yaml_name, size, seed = {"FlowNetC": ("flownet_c.yaml", (256, 320), 7), "PWCNet": ("pwcnet.yaml", (256, 448), 11),
+                             "DCVNet": ("dcvnet.yaml", (256, 384), 5)}[which]
+    ref_model, new_model = _build_both(which, yaml_name)
+    ref_model.train()
+    new_model.train()
+    sim = {"FlowNetC": lambda m: m.correlation_layer, "PWCNet": lambda m: m.decoder.correlation_layer, "DCVNet": lambda m: m.cost_volume_list}[which]
+    img1, img2 = (t.to(dev()) for t in _smooth_pair(2, size[0], size[1], seed=seed))
+
+    def loss_of(out):
+        return sum(p.abs().mean() + 0.1 * (p * p).mean() for p in out["flow_preds"])
+
+    old = E.get_local_corr_mode()
+    E.set_local_corr_mode(mode)
+    try:
+        # The yardstick: the reference against itself when its own similarity output is perturbed at the level this repo's
+        # forward differs from it (fp32 rounding in 'exact' mode, 3e-4 of fp16 operands in 'tc' mode).  A deep network in
+        # training mode (batch statistics, LeakyReLU kinks, cancelling sums in bias gradients) amplifies such a perturbation,
+        # and cuDNN's backward kernels add run-to-run differences of their own; an adjoint that is right stays within a small
+        # multiple of that, a wrong one does not.
+        eps = 3e-4 if mode == "tc" else 3e-7
+        gen = torch.Generator(device=dev()).manual_seed(123)
+
+        def perturb(_mod, _args, out):
+            return out + eps * out.abs().mean() * torch.randn(out.shape, device=out.device, generator=gen)
+
+        pert_in = []
+        h = _capture_similarity_inputs(sim(ref_model), pert_in, first_only=which == "PWCNet")
+        h2 = sim(ref_model).register_forward_hook(perturb)
+        torch.manual_seed(1)
+        loss_of(ref_model(img1, img2)).backward()
+        h.remove()
+        h2.remove()
+        first = {n: p.grad.clone() for n, p in ref_model.named_parameters() if p.grad is not None}
+        first_in = [t.grad.clone() for t in pert_in]
+        ref_model.zero_grad(set_to_none=True)
+        ref_in = []
+        # PWCNet: this repo's sampler receives a lazy-warp handle as its second input (the warped tensor is never materialised)
+        h = _capture_similarity_inputs(sim(ref_model), ref_in, first_only=which == "PWCNet")
+        torch.manual_seed(1)
+        loss_ref = loss_of(ref_model(img1, img2))
+        loss_ref.backward()
+        h.remove()
+        noise = {n: ((p.grad - first[n]).norm() / first[n].norm().clamp_min(1e-30)).item() for n, p in ref_model.named_parameters() if p.grad is not None}
+        noise_in = max(((a - t.grad).norm() / t.grad.norm().clamp_min(1e-30)).item() for a, t in zip(first_in, ref_in))
+        new_in = []
+        h = _capture_similarity_inputs(sim(new_model), new_in, first_only=which == "PWCNet")
+        E.install()
+        try:
+            torch.manual_seed(1)
+            loss_new = loss_of(new_model(img1, img2))
+            loss_new.backward()
+        finally:
+            E.uninstall()
+            h.remove()
+    finally:
+        E.set_local_corr_mode(old)
+    tol_loss = 1e-3 if mode == "tc" else 1e-5
+    assert abs(loss_new.item() - loss_ref.item()) <= tol_loss * abs(loss_ref.item()), (loss_new.item(), loss_ref.item())
+    assert len(new_in) == len(ref_in) and len(ref_in) >= 2
+    worst_in = 0.0
+    for i, (a, b) in enumerate(zip(new_in, ref_in)):
+        assert a.grad is not None and b.grad is not None and a.grad.shape == b.grad.shape
+        worst_in = max(worst_in, ((a.grad - b.grad).norm() / b.grad.norm().clamp_min(1e-30)).item())
+    ref_params = dict(ref_model.named_parameters())
+    gmax = max(p.grad.norm().item() for p in ref_params.values() if p.grad is not None)
+    worst, worst_name, checked = 0.0, "", 0
+    for name, p in new_model.named_parameters():
+        gr = ref_params[name].grad
+        if gr is None or p.grad is None:
+            assert gr is None and p.grad is None, name
+            continue
+        assert torch.isfinite(p.grad).all(), name
+        if gr.norm().item() <= 1e-5 * gmax:
+            continue  # analytically zero (a bias in front of a normalisation) or negligible
+        rel = ((p.grad - gr).norm() / gr.norm()).item() - 4.0 * noise.get(name, 0.0)
+        if rel > worst:
+            worst, worst_name = rel, name
+        checked += 1
+    print(f"\n{which} training step {size} ({mode}): loss {loss_new.item():.6f} vs {loss_ref.item():.6f}; gradients at the {len(ref_in)} "
+          f"similarity inputs within {worst_in:.2e} (the reference under a {eps:.0e} perturbation of its own similarity output: {noise_in:.2e}); "
+          f"{checked} parameter tensors, worst relative difference beyond 4x that yardstick {worst:.2e} ({worst_name})")
+    assert worst_in <= 4.0 * noise_in + 1e-5, f"gradients at the similarity module's inputs differ by {worst_in:.2e} relative (yardstick {noise_in:.2e})"
+    assert checked >= 10 and worst <= 2e-2, f"{worst_name}: parameter gradients differ by {worst:.2e} relative beyond the yardstick"
