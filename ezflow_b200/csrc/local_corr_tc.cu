@@ -28,6 +28,7 @@
 #include "ezb_warp.cuh"
 
 #include <climits>
+#include <cstring>
 #include <type_traits>
 #include <cstdlib>
 
@@ -40,8 +41,9 @@ constexpr int A_KB_BYTES = BM * BK * 2;           // 16 KB
 constexpr int EPI_SPLIT = 4;                      // epilogue warps per TMEM lane quadrant
 constexpr int EPI_WARPS = 4 * EPI_SPLIT;
 constexpr int NUM_THREADS = 128 + EPI_WARPS * 32;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4.. epilogue
-constexpr int MAX_DIL = 8;
+constexpr int MAX_DIL = 8;  // also the bit width of the sparse-sweep tables (one bit per dilation)
 constexpr int TMEM_COLS = 512;
+constexpr int SWEEP_TAB = 288;  // entries of the sparse-sweep tables: 2 * max margin + query tile extent must fit
 
 // Target-tile geometry (rows x columns of in2 pixels = UMMA N).  8x16 (N = 128) is the general tile.  When the x-extent of a
 // query tile's bounding box is small, the tile spans the whole box width instead, so that no displacement straddles two
@@ -107,6 +109,11 @@ struct Params {
   float scale;          // user scale (CorrelationLayer: 1/C)
   float* out;
   long long out_bstride;
+  // Sparse sweep (general extraction): a target tile of the bounding box is visited only if some displacement of some
+  // dilation takes a query of the tile into it.  Separable per dilation: bit d of rowtab[ty0 - query-box y0 + max margin]
+  // and of coltab[tx0 - query-box x0 + max margin].  DCVNet's {1,2,3,5,9,16} needs 123 of the 153 tiles of its box.
+  int sparse;
+  unsigned char rowtab[SWEEP_TAB], coltab[SWEEP_TAB];
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -307,6 +314,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     return it;
   };
 
+  // CTA-uniform, identical in every role: does any displacement reach the target tile at (ty0, tx0) from this query tile?
+  auto tile_needed = [&](const Item& it, int ty0, int tx0) {
+    if (!P.sparse) return true;
+    const int ky = ty0 - (it.qy0 * P.sh - P.padh) + mdh_max, kx = tx0 - (it.qx0 * P.sw - P.padw) + mdw_max;
+    return (P.rowtab[ky] & P.coltab[kx]) != 0;
+  };
+
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
@@ -357,6 +371,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       for (int tt = 0; tt < it.ntiles; ++tt) {
         const int ty0 = it.y_lo + tyi * TTH, tx0 = it.x_lo + txi * TTW;
         if (++txi == it.ntx) { txi = 0; ++tyi; }
+        if (!tile_needed(it, ty0, tx0)) continue;
         for (int kb = 0; kb < P.KB; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1);
           ptx::mbar_expect_tx(full_bar(stage), B_STAGE_BYTES);
@@ -380,8 +395,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       ++acount;
       ptx::mbar_wait(a_full(slot), aph);
       ptx::tc_fence_after();
-      for (int tt = 0; tt < it.ntiles; ++tt, ++tcount) {
+      int tyi = it.tt_begin / it.ntx, txi = it.tt_begin - tyi * it.ntx;
+      for (int tt = 0; tt < it.ntiles; ++tt) {
+        const int ty0 = it.y_lo + tyi * TTH, tx0 = it.x_lo + txi * TTW;
+        if (++txi == it.ntx) { txi = 0; ++tyi; }
+        if (!tile_needed(it, ty0, tx0)) continue;
         const uint32_t acc = tcount % NACC, aphase = (tcount / NACC) & 1;
+        ++tcount;
         ptx::mbar_wait(tmem_empty(acc), aphase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
@@ -450,11 +470,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       const int qbox_x0 = qx0 * P.sw - P.padw, qbox_x1 = (qx0 + QTW - 1) * P.sw - P.padw;
 
       int tyi = it.ntiles > 0 ? it.tt_begin / it.ntx : 0, txi = it.tt_begin - tyi * it.ntx;
-      for (int tt = 0; tt < it.ntiles; ++tt, ++tcount) {
+      for (int tt = 0; tt < it.ntiles; ++tt) {
         const int ty0 = it.y_lo + tyi * TTH, tx0 = it.x_lo + txi * TTW;
         if (++txi == it.ntx) { txi = 0; ++tyi; }
+        if (!tile_needed(it, ty0, tx0)) continue;
         const int ty1 = min(ty0 + TTH, H_) - 1, tx1 = min(tx0 + TTW, W_) - 1;  // last in-image row / column of the tile
         const uint32_t acc = tcount % NACC, aphase = (tcount / NACC) & 1;
+        ++tcount;
         ptx::mbar_wait(tmem_full(acc), aphase);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + acc * ACC_STRIDE + ((uint32_t)(quad * 32) << 16) + part * CPW;
@@ -550,11 +572,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           };
           if (P.slope != 1.f) rows(std::true_type{});
           else rows(std::false_type{});
-        } else
+        } else {
+        // sparse sweep: the dilations with a displacement into this tile, straight from the tables (CTA-uniform)
+        const unsigned dmask = P.sparse ? (unsigned)(P.rowtab[ty0 - qbox_y0 + mdh_max] & P.coltab[tx0 - qbox_x0 + mdw_max]) : 0xffu;
         for (int d = 0; d < P.D; ++d) {
+          if (!((dmask >> d) & 1u)) continue;
           const int dph = P.dph[d], dpw = P.dpw[d], mh = P.mh[d], mw = P.mw[d];
           // CTA-uniform early out: this dilation's box around the query tile does not reach the target tile
-          if (P.D > 1 && (ty1 < qbox_y0 - mh || ty0 > qbox_y1 + mh || tx1 < qbox_x0 - mw || tx0 > qbox_x1 + mw)) continue;
+          if (!P.sparse && P.D > 1 && (ty1 < qbox_y0 - mh || ty0 > qbox_y1 + mh || tx1 < qbox_x0 - mw || tx0 > qbox_x1 + mw)) continue;
           const int y2_0 = yq - mh, x2_0 = xq - mw;
           // this lane's displacement ranges whose target lies in the in-image part of the tile (the reciprocals are launch constants)
           const float inv_dph = P.inv_dph[d], inv_dpw = P.inv_dpw[d];
@@ -611,6 +636,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             if (act) extract(std::integral_constant<int, 4>{}, std::true_type{});
             else extract(std::integral_constant<int, 4>{}, std::false_type{});
           }
+        }
         }
         if (P.regular == 1) __syncwarp(); else quad_sync();  // every warp is done with the rows before the next tile overwrites them
       }
@@ -745,6 +771,32 @@ int local_corr_tc_launch(const float* in1, const float* in2, const float* flow2,
   P.regular = (D == 1 && dph_u[0] == 1 && dpw_u[0] == 1 && sh == 1 && sw == 1 && padh == 0 && padw == 0 && TTW != 16 &&
                getenv("EZB_LOCAL_CORR_GENERIC_EXTRACT") == nullptr) ? (getenv("EZB_LOCAL_CORR_QUADSYNC") ? 2 : 1) : 0;
   P.lat = lat; P.BG = BG; P.Hf = H; P.Wf = W; P.out_h = out_h; P.out_w = out_w;
+  // Sparse sweep: which tiles of the bounding box hold a target at all.  A tile whose first row is `rel` rows below the query
+  // box's first row holds a target of displacement `off` iff rel <= r + off <= rel + TTH - 1 for a query row offset
+  // 0 <= r <= (QTH - 1) * sh (stride granularity ignored: a superset), i.e. rel in [off - (TTH - 1), off + (QTH - 1) * sh].
+  P.sparse = 0;
+  {
+    int mh_max = 0, mw_max = 0;
+    for (int d = 0; d < D; ++d) { mh_max = std::max(mh_max, P.mh[d]); mw_max = std::max(mw_max, P.mw[d]); }
+    const int ny = 2 * mh_max + (QTH - 1) * sh + 1, nx = 2 * mw_max + (QTW - 1) * sw + 1;
+    if (P.regular == 0 && lat == 1 && ny <= SWEEP_TAB && nx <= SWEEP_TAB && getenv("EZB_LOCAL_CORR_DENSE_SWEEP") == nullptr) {
+      std::memset(P.rowtab, 0, sizeof(P.rowtab));
+      std::memset(P.coltab, 0, sizeof(P.coltab));
+      for (int d = 0; d < D; ++d) {
+        for (int a = 0; a < Ph; ++a) {
+          const int off = a * P.dph[d] - P.mh[d];
+          for (int rel = off - (TTH - 1); rel <= off + (QTH - 1) * sh; ++rel)
+            if (rel + mh_max >= 0 && rel + mh_max < ny) P.rowtab[rel + mh_max] |= (unsigned char)(1u << d);
+        }
+        for (int b = 0; b < Pw; ++b) {
+          const int off = b * P.dpw[d] - P.mw[d];
+          for (int rel = off - (TTW - 1); rel <= off + (QTW - 1) * sw; ++rel)
+            if (rel + mw_max >= 0 && rel + mw_max < nx) P.coltab[rel + mw_max] |= (unsigned char)(1u << d);
+        }
+      }
+      P.sparse = 1;
+    }
+  }
   P.slope = slope;
   P.qscale = ws.qscale;
   P.tscale = ws.tscale;

@@ -274,7 +274,10 @@ def test_cost_volume_models_training_step_gradients(reference, which, mode):
         # training mode (batch statistics, LeakyReLU kinks, cancelling sums in bias gradients) amplifies such a perturbation,
         # and cuDNN's backward kernels add run-to-run differences of their own; an adjoint that is right stays within a small
         # multiple of that, a wrong one does not.
-        eps = 3e-4 if mode == "tc" else 3e-7
+        # 'exact': 2e-6 — the fp32 kernels differ from the reference's op sequence by summation order (K4 'exact' is tested
+        # to 2e-5 against the oracle), and the yardstick has to cover cuDNN's own run-to-run differences, which at 3e-7 it did
+        # not (PWCNet's bias gradients moved by 0.9-2.3e-2 beyond it from one run to the next on the same box).
+        eps = 3e-4 if mode == "tc" else 2e-6
         gen = torch.Generator(device=dev()).manual_seed(123)
 
         def perturb(_mod, _args, out):
