@@ -575,8 +575,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         } else {
         // sparse sweep: the dilations with a displacement into this tile, straight from the tables (CTA-uniform)
         const unsigned dmask = P.sparse ? (unsigned)(P.rowtab[ty0 - qbox_y0 + mdh_max] & P.coltab[tx0 - qbox_x0 + mdw_max]) : 0xffu;
+        // Many dilations (DCVNet: 6): a (tile, dilation) pair has few work items (1-27 warp iterations), so whole pairs are dealt
+        // to the EPI_SPLIT warps of a quadrant instead of every warp evaluating every pair's ranges for a quarter of its items.
+        const bool pair_mode = P.D >= 4;
+        const int w0 = pair_mode ? 0 : part, wstep = pair_mode ? 1 : EPI_SPLIT;
         for (int d = 0; d < P.D; ++d) {
           if (!((dmask >> d) & 1u)) continue;
+          if (pair_mode && ((d + tcount) & (EPI_SPLIT - 1)) != part) continue;
           const int dph = P.dph[d], dpw = P.dpw[d], mh = P.mh[d], mw = P.mw[d];
           // CTA-uniform early out: this dilation's box around the query tile does not reach the target tile
           if (!P.sparse && P.D > 1 && (ty1 < qbox_y0 - mh || ty0 > qbox_y1 + mh || tx1 < qbox_x0 - mw || tx0 > qbox_x1 + mw)) continue;
@@ -600,11 +605,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             constexpr int CH = decltype(ch_tag)::value;
             constexpr bool ACT = decltype(act_tag)::value;
             const int nchunk = (ub_hi - ub_lo) / CH + 1, nitems = (ua_hi - ua_lo + 1) * nchunk;
-            int ai = 0, ci = part;  // work item wi = ai * nchunk + ci, kept incrementally (no division per item)
+            int ai = 0, ci = w0;  // work item wi = ai * nchunk + ci, kept incrementally (no division per item)
             while (ci >= nchunk) { ci -= nchunk; ++ai; }
-            for (int wi = part; wi < nitems; wi += EPI_SPLIT) {
+            for (int wi = w0; wi < nitems; wi += wstep) {
               const int a = ua_lo + ai, bb = ub_lo + ci * CH;
-              ci += EPI_SPLIT;
+              ci += wstep;
               while (ci >= nchunk) { ci -= nchunk; ++ai; }
               const bool row_ok = a >= a_lo && a <= a_hi;
               const int col0 = (y2_0 + a * dph - ty0) * TTW + (x2_0 - tx0) + bb * dpw;
@@ -817,6 +822,7 @@ int local_corr_tc_launch(const float* in1, const float* in2, const float* flow2,
       if (c < best) { best = c; P.nsplit = k; }
     }
   }
+  if (const char* e = getenv("EZB_LOCAL_CORR_NSPLIT")) P.nsplit = std::max(1, std::min(8, atoi(e)));  // experiments
   P.qtx = cdiv(ow, QTW);
   P.qty = cdiv(oh, QTH);
   P.d_qtx = make_fastdiv(P.qtx); P.d_qty = make_fastdiv(P.qty); P.d_nsplit = make_fastdiv(P.nsplit);
