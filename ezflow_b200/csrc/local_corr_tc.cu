@@ -113,6 +113,8 @@ struct Params {
   // dilation takes a query of the tile into it.  Separable per dilation: bit d of rowtab[ty0 - query-box y0 + max margin]
   // and of coltab[tx0 - query-box x0 + max margin].  DCVNet's {1,2,3,5,9,16} needs 123 of the 153 tiles of its box.
   int sparse;
+  int zero_idle;     // 1: the out-of-image zeros are written by the two idle warps, 0: by the epilogue warps before the sweep
+  int xclip_unroll;  // regular case, window clipped in x: warp-uniform unrolled walk (1) or the per-lane loop (0)
   unsigned char rowtab[SWEEP_TAB], coltab[SWEEP_TAB];
 };
 
@@ -321,6 +323,47 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     return (P.rowtab[ky] & P.coltab[kx]) != 0;
   };
 
+  // Displacements that point outside the image: act(0) = 0, written once.  A query tile whose whole displacement box lies
+  // inside the image has none.  The calling warp(s) cover queries q0, q0 + qstep, ... < BM and window rows a0, a0 + astep, ...;
+  // the loops over (pi, pj) are warp-uniform with a per-lane bit mask of the out-of-image columns, so a store instruction
+  // still covers contiguous output pixels.  All 32 lanes of a warp must call it together.
+  auto zero_fill = [&](const Item& it, int q0, int qstep, int a0, int astep) {
+    if (!it.valid || it.split != 0) return;
+    const int qx0 = it.qx0, qy0 = it.qy0, H_ = it.H_, W_ = it.W_;
+    const bool box_inside = qy0 * P.sh - P.padh - mdh_max >= 0 && (min(qy0 + QTH, it.oh_) - 1) * P.sh - P.padh + mdh_max < H_ &&
+                            qx0 * P.sw - P.padw - mdw_max >= 0 && (min(qx0 + QTW, it.ow_) - 1) * P.sw - P.padw + mdw_max < W_;
+    if (box_inside) return;
+    const unsigned uplane = (unsigned)(P.out_h * P.out_w);
+    const int b = fdiv(it.bg, P.d_G), g = it.bg - b * P.G;
+    for (int q = q0; q < BM; q += qstep) {
+      const int oy = qy0 + q / QTW, ox = qx0 + q % QTW;
+      const bool q_ok = oy < it.oh_ && ox < it.ow_;
+      float* out_q = P.out + (long long)b * P.out_bstride + (long long)(it.cy + P.lat * oy) * P.out_w + (it.cx + P.lat * ox);
+      for (int d = 0; d < P.D; ++d) {
+        const int dph = P.dph[d], dpw = P.dpw[d];
+        const int y2_0 = oy * P.sh - P.padh - P.mh[d], x2_0 = ox * P.sw - P.padw - P.mw[d];
+        const unsigned o_d = (unsigned)((d * P.G + g) * P.Ph * P.Pw) * uplane;  // offsets inside a batch entry fit 32 bits (launcher)
+        for (int bb0 = 0; bb0 < P.Pw; bb0 += 32) {  // 32 window columns at a time (one pass for every window <= 31 wide)
+          const int nb = min(32, P.Pw - bb0);
+          unsigned zx = 0;  // columns of this lane's window that fall outside the image
+          for (int u = 0; u < nb; ++u) {
+            const int x2 = x2_0 + (bb0 + u) * dpw;
+            zx |= (unsigned)(x2 < 0 || x2 >= W_) << u;
+          }
+          const unsigned all = nb == 32 ? 0xffffffffu : (1u << nb) - 1u;
+          for (int a = a0; a < P.Ph; a += astep) {
+            const int y2 = y2_0 + a * dph;
+            const unsigned m = !q_ok ? 0u : (y2 >= 0 && y2 < H_) ? zx : all;
+            if (!__any_sync(0xffffffffu, m != 0u)) continue;
+            unsigned off = o_d + (unsigned)(a * P.Pw + bb0) * uplane;
+            for (int u = 0; u < nb; ++u, off += uplane)
+              if ((m >> u) & 1u) out_q[off] = 0.f;
+          }
+        }
+      }
+    }
+  };
+
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
@@ -419,6 +462,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       }
       ptx::umma_commit(a_empty(slot));  // arrives once every MMA that read this query operand is done
     }
+  } else if (warp == 2 || warp == 3) {
+    // ===================== zero fill on the two otherwise idle warps (P.zero_idle) =====================
+    // Concurrent with the sweep: the epilogue only writes in-image targets, so the two never touch the same element.
+    if (P.zero_idle) {
+      const int t = threadIdx.x - 64;
+      for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+        const Item it = item_geometry(item);
+        zero_fill(it, t, 64, 0, 1);
+      }
+    }
   } else if (warp >= 4) {
     // ===================== epilogue: lane = query =====================
     // EPI_SPLIT warps share a TMEM lane quadrant (= 32 queries): each drains its share of the accumulator columns
@@ -444,25 +497,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       float* out_q = P.out + (long long)b * P.out_bstride + (long long)(it.cy + P.lat * oy) * P.out_w + (it.cx + P.lat * ox);
       const unsigned uplane = (unsigned)plane;
 
-      // displacements that point outside the image: zeros (act(0) = 0), written once, up front; a tile whose whole
-      // displacement box lies inside the image has none
-      const bool box_inside = qy0 * P.sh - P.padh - mdh_max >= 0 && (min(qy0 + QTH, it.oh_) - 1) * P.sh - P.padh + mdh_max < H_ &&
-                              qx0 * P.sw - P.padw - mdw_max >= 0 && (min(qx0 + QTW, it.ow_) - 1) * P.sw - P.padw + mdw_max < W_;
-      if (q_ok && it.split == 0 && !box_inside) {
-        for (int d = 0; d < P.D; ++d) {
-          const int dph = P.dph[d], dpw = P.dpw[d];
-          const int y2_0 = oy * P.sh - P.padh - dph * (P.Ph - 1) / 2, x2_0 = ox * P.sw - P.padw - dpw * (P.Pw - 1) / 2;
-          float* o = out_q + (long long)(d * P.G + g) * P.Ph * P.Pw * plane;
-          for (int a = part; a < P.Ph; a += EPI_SPLIT) {
-            const int y2 = y2_0 + a * dph;
-            const bool row_in = y2 >= 0 && y2 < H_;
-            for (int bb = 0; bb < P.Pw; ++bb) {
-              const int x2 = x2_0 + bb * dpw;
-              if (!(row_in && x2 >= 0 && x2 < W_)) o[(long long)(a * P.Pw + bb) * plane] = 0.f;
-            }
-          }
-        }
-      }
+      if (!P.zero_idle) zero_fill(it, q, BM, part, EPI_SPLIT);  // this lane's query, every EPI_SPLIT-th window row
 
       // general case: this lane's undisplaced target and the query tile's undisplaced box (CTA-uniform), once per item
       const int yq = oy * P.sh - P.padh, xq = ox * P.sw - P.padw;
@@ -530,6 +565,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           const int xoff = ox - mdw - tx0;
           const int b_lo = max(0, mdw - ox), b_hi = min(P.Pw - 1, W_ - 1 - ox + mdw);  // window columns inside the image
           const bool x_inside = qx0 - mdw >= 0 && qx0 + QTW - 1 + mdw < W_ && qx0 + QTW <= it.ow_;  // CTA-uniform: no clipping in x
+          // union of the warp's column ranges (clipped case)
+          const int ub_lo = x_inside ? 0 : __reduce_min_sync(0xffffffffu, q_ok ? b_lo : INT_MAX);
+          const int ub_hi = x_inside ? P.Pw - 1 : __reduce_max_sync(0xffffffffu, q_ok ? b_hi : INT_MIN);
           const unsigned o_d = (unsigned)(g * P.Ph * P.Pw) * uplane;
           auto rows = [&](auto act_tag) {
             constexpr bool ACT = decltype(act_tag)::value;
@@ -561,11 +599,39 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                   *o = w;
                   o += uplane;
                 }
-              } else {
+              } else if (!P.xclip_unroll) {
                 for (int pj = b_lo; pj <= b_hi; ++pj) {
                   float w = srow[pj] * (trow[pj] * deq);
                   if (ACT) w = w >= 0.f ? w : w * P.slope;
                   o[(unsigned)pj * uplane] = w;
+                }
+              } else {
+                // clipped in x (every tile of FlowNetC's 32-pixel-wide lattice): the warp walks the union of its lanes' column
+                // ranges, three independent load -> store chains in flight, a lane keeps what lies inside its own range
+                float* oo = o + (unsigned)ub_lo * uplane;
+                int pj = ub_lo;
+                for (; pj + 2 <= ub_hi; pj += 3) {
+                  const bool k0 = pj >= b_lo && pj <= b_hi, k1 = pj + 1 >= b_lo && pj + 1 <= b_hi, k2 = pj + 2 >= b_lo && pj + 2 <= b_hi;
+                  float w0 = k0 ? srow[pj] * (trow[pj] * deq) : 0.f;
+                  float w1 = k1 ? srow[pj + 1] * (trow[pj + 1] * deq) : 0.f;
+                  float w2 = k2 ? srow[pj + 2] * (trow[pj + 2] * deq) : 0.f;
+                  if (ACT) {
+                    w0 = w0 >= 0.f ? w0 : w0 * P.slope;
+                    w1 = w1 >= 0.f ? w1 : w1 * P.slope;
+                    w2 = w2 >= 0.f ? w2 : w2 * P.slope;
+                  }
+                  if (k0) oo[0] = w0;
+                  if (k1) oo[uplane] = w1;
+                  if (k2) oo[2 * uplane] = w2;
+                  oo += 3 * uplane;
+                }
+                for (; pj <= ub_hi; ++pj) {
+                  if (pj >= b_lo && pj <= b_hi) {
+                    float w = srow[pj] * (trow[pj] * deq);
+                    if (ACT) w = w >= 0.f ? w : w * P.slope;
+                    *oo = w;
+                  }
+                  oo += uplane;
                 }
               }
             }
@@ -579,9 +645,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         // to the EPI_SPLIT warps of a quadrant instead of every warp evaluating every pair's ranges for a quarter of its items.
         const bool pair_mode = P.D >= 4;
         const int w0 = pair_mode ? 0 : part, wstep = pair_mode ? 1 : EPI_SPLIT;
-        for (int d = 0; d < P.D; ++d) {
-          if (!((dmask >> d) & 1u)) continue;
-          if (pair_mode && ((d + tcount) & (EPI_SPLIT - 1)) != part) continue;
+        static_assert(EPI_SPLIT == 4 && MAX_DIL == 8, "the pair-mode mask below deals dilations d = k, k + 4 to warp k");
+        unsigned dm = dmask & ((1u << P.D) - 1u);
+        if (pair_mode) dm &= 0x11u << ((part - tcount) & (EPI_SPLIT - 1));  // this warp's dilations: (d + tcount) % 4 == part
+        for (; dm; dm &= dm - 1u) {
+          const int d = __ffs(dm) - 1;
           const int dph = P.dph[d], dpw = P.dpw[d], mh = P.mh[d], mw = P.mw[d];
           // CTA-uniform early out: this dilation's box around the query tile does not reach the target tile
           if (!P.sparse && P.D > 1 && (ty1 < qbox_y0 - mh || ty0 > qbox_y1 + mh || tx1 < qbox_x0 - mw || tx0 > qbox_x1 + mw)) continue;
@@ -802,6 +870,12 @@ int local_corr_tc_launch(const float* in1, const float* in2, const float* flow2,
       P.sparse = 1;
     }
   }
+  // many dilations (DCVNet): few zeros, many (row, column) tests -> the idle warps; FlowNetC / PWC-Net: a third of the outputs
+  // are zeros, which two warps cannot store fast enough (measured: 44 -> 64 us on config 2) -> the sixteen epilogue warps
+  P.zero_idle = D >= 4 ? 1 : 0;
+  if (const char* e = getenv("EZB_LOCAL_CORR_ZERO_IDLE")) P.zero_idle = atoi(e) != 0;
+  P.xclip_unroll = 1;
+  if (const char* e = getenv("EZB_LOCAL_CORR_XCLIP_UNROLL")) P.xclip_unroll = atoi(e) != 0;
   P.slope = slope;
   P.qscale = ws.qscale;
   P.tscale = ws.tscale;
