@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
   // the loops over (pi, pj) are warp-uniform with a per-lane bit mask of the out-of-image columns, so a store instruction
   // still covers contiguous output pixels.  All 32 lanes of a warp must call it together.
   auto zero_fill = [&](const Item& it, int q0, int qstep, int a0, int astep) {
-    if (!it.valid || it.split != 0) return;
+    if (!it.valid) return;  // the items sharing a query tile (nsplit) share its zeros too: the callers deal them window rows
     const int qx0 = it.qx0, qy0 = it.qy0, H_ = it.H_, W_ = it.W_;
     const bool box_inside = qy0 * P.sh - P.padh - mdh_max >= 0 && (min(qy0 + QTH, it.oh_) - 1) * P.sh - P.padh + mdh_max < H_ &&
                             qx0 * P.sw - P.padw - mdw_max >= 0 && (min(qx0 + QTW, it.ow_) - 1) * P.sw - P.padw + mdw_max < W_;
@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       const int t = threadIdx.x - 64;
       for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
         const Item it = item_geometry(item);
-        zero_fill(it, t, 64, 0, 1);
+        zero_fill(it, t, 64, it.split, P.nsplit);
       }
     }
   } else if (warp >= 4) {
@@ -497,7 +497,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
       float* out_q = P.out + (long long)b * P.out_bstride + (long long)(it.cy + P.lat * oy) * P.out_w + (it.cx + P.lat * ox);
       const unsigned uplane = (unsigned)plane;
 
-      if (!P.zero_idle) zero_fill(it, q, BM, part, EPI_SPLIT);  // this lane's query, every EPI_SPLIT-th window row
+      // this lane's query; window rows dealt over the EPI_SPLIT warps of the quadrant and the nsplit items of the query tile
+      if (!P.zero_idle) zero_fill(it, q, BM, part + EPI_SPLIT * it.split, EPI_SPLIT * P.nsplit);
 
       // general case: this lane's undisplaced target and the query tile's undisplaced box (CTA-uniform), once per item
       const int yq = oy * P.sh - P.padh, xq = ox * P.sw - P.padw;
@@ -804,6 +805,7 @@ int local_corr_tc_launch(const float* in1, const float* in2, const float* flow2,
     Q.nimg = BG * ncls; Q.G = G;
     EZB_REQUIRE((long long)BG * (1 + ncls) <= 65535, "batch too large for one launch (split it)");
     JJ.groups = Cp <= 64 ? 4 : 1;  // measured (ncu): 4 concurrent groups help at 64 channels (58 -> 47 us on PWC-Net's finest level), not at 128
+    if (const char* e = getenv("EZB_LOCAL_CORR_CONV_GROUPS")) JJ.groups = std::max(1, std::min(CONV_MAX_PX / 32, atoi(e)));  // experiments
     const int conv_px = 32 * JJ.groups;
     const size_t conv_smem = (size_t)Cp * (conv_px + 1) * 4;
     EZB_CUDA_OK(cudaFuncSetAttribute(convert_pixels_kmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem));
