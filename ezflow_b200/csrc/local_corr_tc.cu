@@ -196,12 +196,13 @@ __global__ void __launch_bounds__(CONV_THREADS) convert_pixels_kmajor_kernel(con
   } else {
     const float* sp = src + (long long)y * J.W + x;
     int c = sl;
-    for (; c + 7 * nsl < J.Cp; c += 8 * nsl) {  // eight independent loads in flight (channels >= C are zero-filled)
-      float a[8];
+    constexpr int LD = 16;  // independent loads in flight per thread (channels >= C are zero-filled)
+    for (; c + (LD - 1) * nsl < J.Cp; c += LD * nsl) {
+      float a[LD];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) a[u] = (in_img && c + u * nsl < J.C) ? __ldg(sp + (long long)(c + u * nsl) * HW) : 0.f;
+      for (int u = 0; u < LD; ++u) a[u] = (in_img && c + u * nsl < J.C) ? __ldg(sp + (long long)(c + u * nsl) * HW) : 0.f;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < LD; ++u) {
         m = fmaxf(m, fabsf(a[u]));
         pxbuf[(c + u * nsl) * pitch + pl] = a[u];
       }
