@@ -86,12 +86,12 @@ __global__ void absmax_kernel(const float* __restrict__ f1, const float* __restr
   if (vec_ok) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    for (; i + 3 * stride < n4; i += 4 * stride) {  // four independent 16-byte loads in flight per thread
-      const float4 a = __ldg(x4 + i), b = __ldg(x4 + i + stride), c = __ldg(x4 + i + 2 * stride), d = __ldg(x4 + i + 3 * stride);
-      m = fmaxf(m, fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
-                         fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)))));
-      m = fmaxf(m, fmaxf(fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fmaxf(fabsf(c.z), fabsf(c.w))),
-                         fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fmaxf(fabsf(d.z), fabsf(d.w)))));
+    for (; i + 7 * stride < n4; i += 8 * stride) {  // eight independent 16-byte loads in flight per thread
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(x4 + i + u * stride);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) m = fmaxf(m, fmaxf(fmaxf(fabsf(v[u].x), fabsf(v[u].y)), fmaxf(fabsf(v[u].z), fabsf(v[u].w))));
     }
     for (; i < n4; i += stride) {
       float4 v = __ldg(x4 + i);
@@ -709,7 +709,9 @@ namespace prep {
 int launch_absmax(const float* t0, const float* t1, long long per_b, unsigned int* amax, int B, cudaStream_t st) {
   EZB_REQUIRE(B <= 65535, "batch too large for one launch (split it)");
   EZB_CUDA_OK(cudaMemsetAsync(amax, 0, (size_t)2 * B * 4, st));
-  int gx = (int)std::min<long long>(cdiv64(per_b, 256 * 64), 4096);  // 16 float4 per thread
+  // at least 16 float4 per thread; large inputs: ~8 resident blocks per SM in total walk the tensors grid-stride with 8 loads in
+  // flight per thread (a block per 64 KB was bound by the block launch rate: 93 -> 81 us for 8 pairs of 1080p features)
+  int gx = (int)std::min<long long>(cdiv64(per_b, 256 * 64), std::max(1, num_sms() * 8 / (2 * B)));
   if (gx < 1) gx = 1;
   k1::absmax_kernel<<<dim3(gx, B, 2), 256, 0, st>>>(t0, t1, per_b, amax, B);
   EZB_LAUNCH_OK();

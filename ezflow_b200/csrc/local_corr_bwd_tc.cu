@@ -268,6 +268,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             uint8_t* dstrow = arow;
             const int col0 = tr * TTW + xoff;
             int pj = b_lo;
+            for (; pj + 6 <= b_hi; pj += 7) {     // seven independent loads in flight (a 21-wide window row = 3 rounds)
+              float v[7];
+#pragma unroll
+              for (int u = 0; u < 7; ++u) v[u] = __ldg(src + (pj + u) * pj_stride);
+#pragma unroll
+              for (int u = 0; u < 7; ++u) *reinterpret_cast<__half*>(dstrow + a_off(col0 + pj + u)) = __float2half_rn(v[u] * sd);
+            }
             for (; pj + 2 <= b_hi; pj += 3) {     // three independent loads in flight
               const float v0 = __ldg(src + pj * pj_stride), v1 = __ldg(src + (pj + 1) * pj_stride), v2 = __ldg(src + (pj + 2) * pj_stride);
               *reinterpret_cast<__half*>(dstrow + a_off(col0 + pj)) = __float2half_rn(v0 * sd);
