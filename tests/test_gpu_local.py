@@ -444,3 +444,49 @@ def test_few_surviving_dot_products_bound_against_their_scale():
         err = float(np.abs(out.astype(np.float64) - ref).max())
         assert err <= 1e-3 * scale, f"seed {seed}: max abs error {err:.3e} vs dot-product scale {scale:.3e}"
         assert np.array_equal(out == 0, ref == 0), "displacements outside the image must be exact zeros"
+
+
+def _torch_matryoshka(x1, x2, groups, md, stride, dilations, relu):
+    """fp32 PyTorch restatement of MatryoshkaDilatedCostVolume.forward (reference learnable_cost.py:306-325) on the GPU."""
+    b, c, h, w = x1.shape
+    a = x1.reshape(b * groups, c // groups, h, w)
+    t = x2.reshape(b * groups, c // groups, h, w)
+    outs = []
+    for d in dilations:
+        o = _torch_sampler(a, t, 2 * md + 1, stride, 0, d)
+        outs.append(o.reshape(b, groups, 2 * md + 1, 2 * md + 1, o.shape[-2], o.shape[-1]))
+    out = torch.cat(outs, dim=1)
+    return torch.nn.functional.leaky_relu(out, 0.1) if relu else out
+
+
+@pytest.mark.parametrize(
+    "cfg",
+    [
+        ((4, 256, 48, 96), 1, 4, 1, [1, 2, 3, 5, 9, 16], False),   # config 4's stride-1 scale at its full batch
+        ((2, 96, 37, 53), 2, 4, 1, [1, 2, 3, 5, 9, 16], True),     # ragged map (partial query / target tiles), groups, LeakyReLU
+        ((1, 64, 40, 72), 1, 2, 1, [1, 4, 7, 40], False),          # a dilation whose margin exceeds the sparse-sweep tables
+        ((2, 64, 33, 47), 1, 3, 2, [1, 2, 4, 6, 11], True),        # stride 2 with five dilations
+        ((1, 32, 24, 40), 4, 1, 1, [1, 2, 3, 4, 5, 6, 7, 8], False),  # eight dilations (every table bit), 3x3 window
+    ],
+)
+def test_many_dilations_sparse_sweep_vs_torch(cfg, mode):
+    """K6 with D >= 4: the sparse sweep (tiles no displacement reaches are skipped by all three roles), (tile, dilation) pairs
+    dealt to the epilogue warps, zeros written by the idle warps — against the PyTorch fp32 restatement of the reference's loop
+    (learnable_cost.py:306-325), full batch, ragged borders, table overflow; and run-to-run determinism."""
+    import ezflow_b200 as E
+
+    shape, groups, md, stride, dilations, relu = cfg
+    g = torch.Generator(device=dev()).manual_seed(41)
+    x1 = torch.randn(shape, device=dev(), generator=g)
+    x2 = torch.randn(shape, device=dev(), generator=g)
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = _torch_matryoshka(x1, x2, groups, md, stride, dilations, relu)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    m = E.MatryoshkaDilatedCostVolume(num_groups=groups, max_displacement=md, stride=stride, dilations=dilations, use_relu=relu).to(dev())
+    out = m(x1, x2)
+    assert tuple(out.shape) == tuple(ref.shape)
+    assert_close(out, ref, FWD_TOL[mode] if mode == "tc" else 5e-5, f"{cfg} ({mode})")
+    assert torch.equal(out, m(x1, x2))
