@@ -18,8 +18,12 @@
 //   epilogue: lane = query.  The 128 accumulator columns of a tile go TMEM -> registers -> a private row of
 //             shared memory (dynamic column indexing), then every (dilation, pi, pj) whose target falls into this
 //             tile is picked up and stored: for a fixed (pi,pj) the 16 queries of a tile row write 64
-//             contiguous bytes of the (B, D*G, Ph, Pw, oh, ow) output.  Displacements that point outside the
-//             image are written as zeros up front.  Every output element is written exactly once.
+//             contiguous bytes of the (B, D*G, Ph, Pw, oh, ow) output.  With several dilations only the tiles some
+//             displacement reaches are visited (per-dilation row / column tables from the launcher: Params::rowtab/coltab)
+//             and, for D >= 4, whole (tile, dilation) pairs are dealt to the warps of a TMEM lane quadrant.
+//   zeros   : displacements that point outside the image: act(0) = 0, written from a per-lane bit mask of the out-of-image
+//             columns — by warps 2-3 concurrently with the sweep when D >= 4, else by the epilogue warps before it.
+//             Every output element is written exactly once.
 // Only 1/5 to 1/40 of the computed products are kept (the window is a band of the all-pairs matrix), which is
 // still 20-40x faster than fp32 FMAs on CUDA cores for these shapes (profiles/r01_local_corr.md).
 #include "ezb_common.cuh"
@@ -40,7 +44,7 @@ constexpr int BK = 64, KB_MAX = 4;                // C <= 256
 constexpr int A_KB_BYTES = BM * BK * 2;           // 16 KB
 constexpr int EPI_SPLIT = 4;                      // epilogue warps per TMEM lane quadrant
 constexpr int EPI_WARPS = 4 * EPI_SPLIT;
-constexpr int NUM_THREADS = 128 + EPI_WARPS * 32;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4.. epilogue
+constexpr int NUM_THREADS = 128 + EPI_WARPS * 32;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 2-3 zero fill (D >= 4), 4.. epilogue
 constexpr int MAX_DIL = 8;  // also the bit width of the sparse-sweep tables (one bit per dilation)
 constexpr int TMEM_COLS = 512;
 constexpr int SWEEP_TAB = 288;  // entries of the sparse-sweep tables: 2 * max margin + query tile extent must fit
