@@ -96,7 +96,10 @@ __global__ void __launch_bounds__(NTHREADS, 3) corr_lookup_fwd_kernel(const Look
   // Every warp serves 4 queries of the block; lane k < 16 owns item (query k/4, level k%4) and keeps its
   // window origin in a register (shuffled to the other lanes below) and in shared memory (phase 2).
   using G = Gather<ES>;
-  int org_packed;  // (first chunk index << 16) | (first row & 0xffff), both small signed numbers
+  // (first chunk index << 19) | (chunks the window's 2r+2 columns actually span - 1) << 16 | (first row & 0xffff); chunk index and
+  // row are small signed numbers.  A window spans ng chunks only when it starts in the last pixels of a chunk (fp16, r = 4: one
+  // start in eight); the chunks beyond its last column are not fetched — each would be a DRAM line of its own
+  int org_packed;
   {
     const int qi = (lane >> 2) & 3, l = lane & 3;
     const int q = min(q0 + warp * 4 + qi, P.N - 1);
@@ -106,7 +109,8 @@ __global__ void __launch_bounds__(NTHREADS, 3) corr_lookup_fwd_kernel(const Look
     // clamped so that a window entirely outside the level stays entirely outside
     const int2 org = make_int2(max(-D, min(P.W >> l, x0 - r)), max(-D, min(P.H >> l, y0 - r)));
     if (lane < 16 && l < P.L) items[l * QB + warp * 4 + qi] = org;
-    org_packed = (G::chunk_floor(org.x) << 16) | (org.y & 0xffff);
+    const int cf = G::chunk_floor(org.x);
+    org_packed = (cf << 19) | ((G::chunk_floor(org.x + D - 1) - cf) << 16) | (org.y & 0xffff);
   }
 
   // ---------------- phase 1: gather windows ----------------
@@ -132,10 +136,10 @@ __global__ void __launch_bounds__(NTHREADS, 3) corr_lookup_fwd_kernel(const Look
         const int pk = __shfl_sync(0xffffffffu, org_packed, qi * 4 + l);
         if (l < P.L && task_ok) {
           const int y = (int)(short)(pk & 0xffff) + row;
-          const int xg = ((pk >> 16) + gi) * G::VW;  // first pixel of the chunk
+          const int xg = ((pk >> 19) + gi) * G::VW;  // first pixel of the chunk
           const char* src = pair_base;
           uint32_t nbytes = 0;
-          if ((unsigned)y < (unsigned)(P.H >> l) && (unsigned)xg < (unsigned)(P.W >> l)) {
+          if ((unsigned)y < (unsigned)(P.H >> l) && (unsigned)xg < (unsigned)(P.W >> l) && gi <= ((pk >> 16) & 7)) {
             const unsigned sidx = (unsigned)(P.sub_base[l] + (y >> 3) * P.sw[l] + (xg >> 3));
             if constexpr (ES == 2) {
               // an fp16 chunk is one whole row of one 8x8 subtile: section sidx % 4 of the group block, 16 bytes at

@@ -223,7 +223,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) lookup_conv1x1_kernel(const __
         const int q = min(q0 + warp * QPW + (lane & (QPW - 1)), P.N - 1);
         const int x0 = floor_clamped(__ldg(cx_ptr + q) * inv), y0 = floor_clamped(__ldg(cy_ptr + q) * inv);
         const int ox = max(-D, min(wl, x0 - r)), oy = max(-D, min(hl, y0 - r));
-        org_packed = ((((ox + 64) >> 3) - 8) << 16) | (oy & 0xffff);  // first 8-pixel chunk, first row
+        // first 8-pixel chunk << 19 | (chunks the 2r+2 window columns span - 1) << 16 | first row: a window reaches into the ng-th
+        // chunk only when it starts in the last pixels of a chunk; the chunks beyond its last column (each a DRAM line of its
+        // own) are not fetched
+        const int cf = ((ox + 64) >> 3) - 8;
+        org_packed = (cf << 19) | (((((ox + D - 1) + 64) >> 3) - 8 - cf) << 16) | (oy & 0xffff);
       }
       const int ng = (7 + D + 7) >> 3;  // chunks per window row (3 for r = 4)
       const int row = lane / ng >= D ? 0 : lane / ng, gi = lane - (lane / ng) * ng;
@@ -238,11 +242,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) lookup_conv1x1_kernel(const __
         if (task_ok) {
           const int q = min(q0 + warp * QPW + qi, P.N - 1);
           const int y = (int)(short)(pk & 0xffff) + row;
-          const int xc = (pk >> 16) + gi;  // 8-pixel chunk = subtile column
+          const int xc = (pk >> 19) + gi;  // 8-pixel chunk = subtile column
           // a chunk is one row of one 8x8 subtile: record column (s % 4) * 64 + (y % 8) * 8, i.e. section s % 4 of the
           // query's group block, 16 bytes at (y % 8) * 16 of its 128-byte line (ezb_common.cuh)
           const unsigned sidx = (unsigned)(sb + (y >> 3) * swl + xc);
-          const bool ok = (unsigned)y < (unsigned)hl && xc >= 0 && xc * 8 < wl;
+          const bool ok = (unsigned)y < (unsigned)hl && xc >= 0 && xc * 8 < wl && gi <= ((pk >> 16) & 7);
           const char* src = pair_base + (unsigned long long)(sidx >> 2) * tile_stride + (long long)(q >> 5) * P.group_bytes +
                             (((sidx & 3u) << 12) + ((unsigned)(q & 31) << 7) + ((unsigned)(y & 7) << 4));
           cp_async_16(dst_lane + qi * QSTRIDE, ok ? src : pair_base, ok ? 16u : 0u);
