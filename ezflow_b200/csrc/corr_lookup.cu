@@ -134,12 +134,13 @@ __global__ void __launch_bounds__(NTHREADS, 3) corr_lookup_fwd_kernel(const Look
 #pragma unroll
       for (int l = 0; l < PYR_MAX_LEVELS; ++l) {
         const int pk = __shfl_sync(0xffffffffu, org_packed, qi * 4 + l);
-        if (l < P.L && task_ok) {
+        // chunks beyond the window's last column are neither fetched nor zero-filled: phase 2 never reads them
+        if (l < P.L && task_ok && gi <= ((pk >> 16) & 7)) {
           const int y = (int)(short)(pk & 0xffff) + row;
           const int xg = ((pk >> 19) + gi) * G::VW;  // first pixel of the chunk
           const char* src = pair_base;
           uint32_t nbytes = 0;
-          if ((unsigned)y < (unsigned)(P.H >> l) && (unsigned)xg < (unsigned)(P.W >> l) && gi <= ((pk >> 16) & 7)) {
+          if ((unsigned)y < (unsigned)(P.H >> l) && (unsigned)xg < (unsigned)(P.W >> l)) {
             const unsigned sidx = (unsigned)(P.sub_base[l] + (y >> 3) * P.sw[l] + (xg >> 3));
             if constexpr (ES == 2) {
               // an fp16 chunk is one whole row of one 8x8 subtile: section sidx % 4 of the group block, 16 bytes at
