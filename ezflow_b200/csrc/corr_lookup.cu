@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) corr_lookup_fwd_kernel(const Look
   // Every warp serves 4 queries of the block; lane k < 16 owns item (query k/4, level k%4) and keeps its
   // window origin in a register (shuffled to the other lanes below) and in shared memory (phase 2).
   using G = Gather<ES>;
-  // (first chunk index << 19) | (chunks the window's 2r+2 columns actually span - 1) << 16 | (first row & 0xffff); chunk index and
+  // (first chunk index << 20) | (chunks the window's 2r+2 columns actually span - 1) << 16 | (first row & 0xffff); chunk index and
   // row are small signed numbers.  A window spans ng chunks only when it starts in the last pixels of a chunk (fp16, r = 4: one
   // start in eight); the chunks beyond its last column are not fetched — each would be a DRAM line of its own
   int org_packed;
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) corr_lookup_fwd_kernel(const Look
     const int2 org = make_int2(max(-D, min(P.W >> l, x0 - r)), max(-D, min(P.H >> l, y0 - r)));
     if (lane < 16 && l < P.L) items[l * QB + warp * 4 + qi] = org;
     const int cf = G::chunk_floor(org.x);
-    org_packed = (cf << 19) | ((G::chunk_floor(org.x + D - 1) - cf) << 16) | (org.y & 0xffff);
+    org_packed = (cf << 20) | ((G::chunk_floor(org.x + D - 1) - cf) << 16) | (org.y & 0xffff);  // span - 1 <= 15: any window that fits shared memory
   }
 
   // ---------------- phase 1: gather windows ----------------
@@ -135,9 +135,9 @@ __global__ void __launch_bounds__(NTHREADS, 3) corr_lookup_fwd_kernel(const Look
       for (int l = 0; l < PYR_MAX_LEVELS; ++l) {
         const int pk = __shfl_sync(0xffffffffu, org_packed, qi * 4 + l);
         // chunks beyond the window's last column are neither fetched nor zero-filled: phase 2 never reads them
-        if (l < P.L && task_ok && gi <= ((pk >> 16) & 7)) {
+        if (l < P.L && task_ok && gi <= ((pk >> 16) & 15)) {
           const int y = (int)(short)(pk & 0xffff) + row;
-          const int xg = ((pk >> 19) + gi) * G::VW;  // first pixel of the chunk
+          const int xg = ((pk >> 20) + gi) * G::VW;  // first pixel of the chunk
           const char* src = pair_base;
           uint32_t nbytes = 0;
           if ((unsigned)y < (unsigned)(P.H >> l) && (unsigned)xg < (unsigned)(P.W >> l)) {

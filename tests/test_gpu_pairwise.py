@@ -560,3 +560,36 @@ def test_pooled_gradient_pyramid_soak():
         assert_close(g1, d1.cpu().numpy(), 3e-4, f"step {step} (n={n}, spread={spread}) dfmap1")
         assert_close(g2, d2.cpu().numpy(), 3e-4, f"step {step} (n={n}, spread={spread}) dfmap2")
     E.release_gradient_pool()
+
+
+@pytest.mark.parametrize("store", ["fp16", "fp32"])
+@pytest.mark.parametrize("cfg", [(1, 1, 21, 45), (2, 2, 33, 70), (5, 2, 30, 52), (7, 1, 40, 64), (8, 1, 36, 72)])
+def test_lookup_radii_and_window_alignments_vs_oracle(cfg, store):
+    """The gather fetches only the 16-byte chunks a window's 2r+2 columns span (their number travels with the window origin):
+    every window start residue modulo the chunk width, radii from 1 to 8, the library's maximum (up to 6 chunks per row in fp32), windows hanging over every
+    border, in both storage modes, against the oracle lookup (reference pairwise.py:43-69) — and the coords adjoint, which shares
+    the gather."""
+    import ezflow_b200 as E
+    from oracle import similarity_oracle as O
+
+    r, L, H, W = cfg
+    rng = np.random.default_rng(100 + r)
+    f1 = rng.standard_normal((1, 32, H, W)).astype(np.float32)
+    f2 = rng.standard_normal((1, 32, H, W)).astype(np.float32)
+    # integer offsets 0..15 along x make every chunk residue appear with every fraction; a margin beyond the borders
+    coords = O.coords_grid(1, H, W)
+    coords[:, 0] += (np.arange(W) % 16)[None, None, :] * 0.5 + rng.uniform(-9, 9, (1, H, W))
+    coords[:, 1] += rng.uniform(-6, 6, (1, H, W))
+    coords = coords.astype(np.float32)
+    ref = O.corr_lookup(O.corr_pyramid(f1, f2, L), coords, r)
+    E.set_pyramid_dtype(store)
+    obj = E.MutliScalePairwise4DCorr(to_gpu(f1), to_gpu(f2), num_levels=L, corr_radius=r)
+    out = obj(to_gpu(coords))
+    assert tuple(out.shape) == ref.shape
+    assert_close(out, ref, LOOK_TOL, f"lookup r={r} L={L} ({store})")
+    if r <= 5:
+        dout = rng.standard_normal(ref.shape).astype(np.float32)
+        c = to_gpu(coords, True)
+        (obj(c) * to_gpu(dout)).sum().backward()
+        dref = O.corr_lookup_bwd_coords(O.corr_pyramid(f1, f2, L), coords, dout, r)
+        assert_close(c.grad, dref, 5e-3, f"coords adjoint r={r} ({store})")
