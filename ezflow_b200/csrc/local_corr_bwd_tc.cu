@@ -76,7 +76,26 @@ __global__ void __launch_bounds__(256) absmax_dout_kernel(const float* __restric
                                                           unsigned int* __restrict__ amax) {
   const float* x = dout + (long long)blockIdx.y * bstride;
   float m = 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_b; i += (long long)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(__ldg(x + i)));
+  const long long stride = (long long)gridDim.x * blockDim.x, t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) {  // 16-byte loads, four in flight per thread
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const long long n4 = per_b >> 2;
+    long long i = t0;
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(x4 + i + u * stride);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) m = fmaxf(m, fmaxf(fmaxf(fabsf(v[u].x), fabsf(v[u].y)), fmaxf(fabsf(v[u].z), fabsf(v[u].w))));
+    }
+    for (; i < n4; i += stride) {
+      const float4 v = __ldg(x4 + i);
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    for (long long k = (n4 << 2) + t0; k < per_b; k += stride) m = fmaxf(m, fabsf(__ldg(x + k)));
+  } else {
+    for (long long i = t0; i < per_b; i += stride) m = fmaxf(m, fabsf(__ldg(x + i)));
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax + blockIdx.y, __float_as_uint(m));
@@ -393,7 +412,8 @@ int local_corr_bwd_tc_launch(const float* in1, const float* in2, const float* do
   EZB_CUDA_OK(cudaMemsetAsync(ws.amax + 2 * BG, 0, (size_t)BG * 4, st));
   {
     const long long per_b = (long long)G * Pn * Pn * N;
-    const int gx = (int)std::max<long long>(1, std::min<long long>(cdiv64(per_b, 256 * 16), 1024));
+    // at least 16 float4 per thread; ~8 resident blocks per SM in total
+    const int gx = (int)std::max<long long>(1, std::min<long long>(cdiv64(per_b, 256 * 64), std::max(1, num_sms() * 8 / B)));
     absmax_dout_kernel<<<dim3(gx, B), 256, 0, st>>>(dout, dout_bstride, per_b, ws.amax + 2 * BG);
     EZB_LAUNCH_OK();
   }
